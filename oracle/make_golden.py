@@ -1,0 +1,256 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):
+
+    python oracle/make_golden.py
+
+It puts ``oracle/shims`` (stand-ins for the absent third-party imports) and
+``/root/reference/examples`` on ``sys.path``, neutralises ``.cuda()`` / ``device="cuda"`` so the
+CUDA-only reference code executes on CPU, imports the reference modules as they are, calls the
+hot-path functions on seeded inputs and stores inputs + outputs.  The fixtures pin
+``oracle/quadfield_oracle.py`` (tests/test_oracle_golden.py) and, through it, the CUDA kernels.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("QF_REFERENCE", "/root/reference/examples")
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _install():
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    warnings.filterwarnings("ignore")
+    # CUDA-only reference code → CPU
+    torch.Tensor.cuda = lambda self, *a, **k: self
+
+    def _strip(fn):
+        def wrapped(*a, **k):
+            dev = k.get("device", None)
+            if dev is not None and "cuda" in str(dev):
+                k.pop("device")
+            return fn(*a, **k)
+        return wrapped
+
+    for name in ("zeros", "ones", "zeros_like", "ones_like", "rand", "empty", "tensor", "full"):
+        setattr(torch, name, _strip(getattr(torch, name)))
+
+
+def golden_field_rendering():
+    """a12–a15: reference field_rendering.py (behind the nerfacc pack/scan stand-in)."""
+    import field_rendering as FR
+    g = torch.Generator().manual_seed(42)
+    counts = torch.tensor([3, 0, 5, 1, 0, 0, 8, 2, 4, 1, 7, 0], dtype=torch.long)
+    n_rays = counts.numel()
+    ray_indices = torch.repeat_interleave(torch.arange(n_rays), counts)
+    M = int(counts.sum())
+    alphas = torch.rand(M, generator=g)
+    alphas[5] = 0.0
+    alphas[9] = 1.0
+    sigmas = torch.rand(M, generator=g) * 40
+    t_starts = torch.rand(M, generator=g).cumsum(0) * 0.05
+    t_ends = t_starts + 0.02 + 0.01 * torch.rand(M, generator=g)
+    rgbs = torch.rand(M, 3, generator=g)
+    prefix = torch.rand(M, generator=g)
+    bkgd = torch.tensor([0.2, 0.5, 0.9])
+    out = dict(counts=counts, ray_indices=ray_indices, alphas=alphas, sigmas=sigmas, t_starts=t_starts,
+               t_ends=t_ends, rgbs=rgbs, prefix=prefix, bkgd=bkgd)
+    out["T_alpha"] = FR.render_transmittance_from_alpha(alphas, ray_indices=ray_indices, n_rays=n_rays)
+    out["T_alpha_prefix"] = FR.render_transmittance_from_alpha(alphas, ray_indices=ray_indices, n_rays=n_rays,
+                                                               prefix_trans=prefix)
+    w, T = FR.render_weight_from_alpha(alphas, ray_indices=ray_indices, n_rays=n_rays)
+    out["w_alpha"], out["T_alpha2"] = w, T
+    w, T, a = FR.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays)
+    out["w_density"], out["T_density"], out["a_density"] = w, T, a
+    w, T, a = FR.render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices, n_rays=n_rays,
+                                            prefix_trans=prefix)
+    out["w_density_prefix"] = w
+    out["vis_alpha"] = FR.render_visibility_from_alpha(alphas, ray_indices=ray_indices, n_rays=n_rays,
+                                                       early_stop_eps=0.3, alpha_thre=0.2)
+    out["vis_density"] = FR.render_visibility_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices,
+                                                           n_rays=n_rays, early_stop_eps=0.05, alpha_thre=0.3)
+    out["acc_rgb"] = FR.accumulate_along_rays(out["w_density"], rgbs, ray_indices, n_rays)
+    out["acc_w"] = FR.accumulate_along_rays(out["w_density"], None, ray_indices, n_rays)
+    c, o, d, ex = FR.rendering(t_starts, t_ends, ray_indices, n_rays, rgb_sigma_fn=lambda a, b, c: (rgbs, sigmas),
+                               render_bkgd=bkgd)
+    out["rend_c"], out["rend_o"], out["rend_d"] = c, o, d
+    c, o, d, ex = FR.rendering(t_starts, t_ends, ray_indices, n_rays, rgb_alpha_fn=lambda a, b, c: (rgbs, alphas))
+    out["renda_c"], out["renda_o"], out["renda_d"] = c, o, d
+    c, o, d, w, wr = FR.rendering_field(t_starts, t_ends, ray_indices, n_rays,
+                                        rgb_sigma_fn=lambda a, b, c: (rgbs, sigmas), render_bkgd=bkgd)
+    out["rf_c"], out["rf_o"], out["rf_d"], out["rf_w"], out["rf_wrev"] = c, o, d, w, wr
+    # batched layout (n_rays, S)
+    ab = torch.rand(6, 9, generator=g)
+    sb = torch.rand(6, 9, generator=g) * 30
+    tsb = torch.rand(6, 9, generator=g).cumsum(1) * 0.05
+    teb = tsb + 0.02
+    vb = torch.rand(6, 9, 3, generator=g)
+    out.update(b_alphas=ab, b_sigmas=sb, b_ts=tsb, b_te=teb, b_vals=vb)
+    out["b_w_alpha"], out["b_T_alpha"] = FR.render_weight_from_alpha(ab)
+    out["b_w_density"], out["b_T_density"], out["b_a_density"] = FR.render_weight_from_density(tsb, teb, sb)
+    out["b_acc"] = FR.accumulate_along_rays(out["b_w_density"], vb)
+    # docstring KATs (field_rendering.py:192-195, 246-253, 298-302, 347-355, 403-409)
+    ka = torch.tensor([0.4, 0.8, 0.1, 0.8, 0.1, 0.0, 0.9])
+    kr = torch.tensor([0, 0, 0, 1, 1, 2, 2])
+    out["kat_T"] = FR.render_transmittance_from_alpha(ka, ray_indices=kr)
+    out["kat_w"], _ = FR.render_weight_from_alpha(ka, ray_indices=kr)
+    kts, kte = torch.arange(7.0), torch.arange(7.0) + 1
+    out["kat_wd"], out["kat_Td"], out["kat_ad"] = FR.render_weight_from_density(kts, kte, ka, ray_indices=kr)
+    out["kat_vis"] = FR.render_visibility_from_alpha(ka, ray_indices=kr, early_stop_eps=0.3, alpha_thre=0.2)
+    return out
+
+
+def golden_sg_decode():
+    """a7, a8, a9: reference texture_utils.FeatureCompression / ngp.py dequantisers / SG head / _TruncExp."""
+    import radiance_fields.ngp as NGP
+    from texture_utils import FeatureCompression
+    from oracle import quadfield_oracle as O
+    out = {}
+    for L, ctype, lam in ((3, "linear", 5.0), (6, "sigmoid", 7.5), (2, "sigma", 7.5)):
+        S = 24
+        tex = O.make_texture_set(S, L, seed=100 + L, compression_type=ctype, lambda_thres=lam)
+        fc = object.__new__(FeatureCompression)
+        fc.num_lobes, fc.texture_size, fc.compression_type, fc.lambda_thres = L, S, ctype, lam
+        fc.alpha, fc.diffuse = tex.alpha, tex.diffuse
+        fc.sg_colors = {i: tex.sg_colors[i] for i in range(L)}
+        fc.lambdas = {i: tex.lambdas[i] for i in range(L)}
+        g = torch.Generator().manual_seed(7 + L)
+        idx = torch.randint(0, S, (300, 2), generator=g)
+        # make sure extreme quantised values are exercised
+        tex.alpha[idx[0, 0], idx[0, 1]] = 255
+        tex.alpha[idx[1, 0], idx[1, 1]] = 0
+        feats = fc.get_features_from_texture_map(idx)
+        dirs = torch.nn.functional.normalize(torch.randn(300, 3, generator=g), dim=-1)
+        sg = object.__new__(NGP.NGPRadianceFieldSGNew)
+        torch.nn.Module.__init__(sg)
+        sg.num_g_lobes, sg.discretize = L, False
+        rgb = sg.features_to_rgb(feats[:, :-1], dirs)
+        rgb2 = fc.features_to_rgb(feats[:, :-1], dirs)
+        assert torch.equal(rgb, rgb2)
+        k = f"L{L}_{ctype}"
+        out[k + "_idx"], out[k + "_feats"], out[k + "_dirs"], out[k + "_rgb"] = idx, feats, dirs, rgb
+        out[k + "_alpha"], out[k + "_diffuse"] = tex.alpha, tex.diffuse
+        for i in range(L):
+            out[k + f"_color{i}"], out[k + f"_lambda{i}"] = tex.sg_colors[i], tex.lambdas[i]
+    x = torch.tensor([-3.0, -1.0, 0.0, 0.5, 2.0, 14.0, 16.0, 20.0], requires_grad=True)
+    y = NGP.trunc_exp(x)
+    y.backward(torch.ones_like(y))
+    out["trunc_exp_x"], out["trunc_exp_y"], out["trunc_exp_g"] = x.detach(), y.detach(), x.grad
+    return out
+
+
+def golden_geometry():
+    """a2 (plane-hit formula), a3, a4: reference mesh_utils functions; the intersector itself
+    (Embree/OptiX, absent) is replaced by the oracle's brute-force `intersects_id`."""
+    import mesh_utils as MU
+    import trimesh
+    from oracle import quadfield_oracle as O
+    verts, faces = O.shell_mesh([0.5, 0.8, 1.0], subdivisions=2, jitter=1e-3, seed=3)
+    f, cx, cy, W, H = O.pinhole_intrinsics(24, 24, 0.6911)
+    c2w = O.look_at_c2w((2.4, 1.9, 1.3))
+    origins, viewdirs = O.generate_rays(c2w, W, H, f, cx, cy)
+    K = 4
+    mesh = trimesh.Trimesh(vertices=verts, faces=faces, process=False)
+
+    class FakeIntersector:
+        def intersects_id(self, o, v, multiple_hits=True, return_locations=True, max_hits=10):
+            return O.intersects_id(o, v, verts, faces, max_hits)
+
+    mi = object.__new__(MU.MeshIntersection)
+    mi.mesh, mi.num_intersections, mi.render_step_size = mesh, K, 0.005
+    mi.rayintersector = FakeIntersector()
+    tup = mi.sampling_raytrace_numpy(viewdirs, origins)
+    points, vectors, index_ray, depth, index_tri, _, org = tup
+    out = dict(verts=verts, faces=faces, origins=origins, viewdirs=viewdirs, K=np.int64(K),
+               points=points, vectors=vectors, index_ray=index_ray, depth=depth, index_tri=index_tri, org=org)
+    # reference plane-hit formula on its own (jit function, mesh_utils.py:33-40)
+    n = torch.from_numpy(mesh.face_normals[index_tri].astype(np.float32))
+    v = torch.from_numpy(mesh.vertices[mesh.faces[index_tri][:, 0]].astype(np.float32))
+    psi = MU.ray_triangle_intersection(torch.from_numpy(origins[index_ray]), torch.from_numpy(viewdirs[index_ray]), n, v)
+    out["psi"] = psi
+    # a4: perturb depths so the re-sort actually permutes, then reference sampling_indexing
+    g = torch.Generator().manual_seed(5)
+    d2 = torch.from_numpy(depth.astype(np.float32)) + 0.3 * torch.randn(depth.shape[0], generator=g)
+    res = mi.sampling_indexing(torch.from_numpy(points.astype(np.float32)), torch.from_numpy(org.astype(np.float32)),
+                               torch.from_numpy(vectors.astype(np.float32)), torch.from_numpy(index_ray),
+                               d2, torch.from_numpy(index_tri))
+    names = ("points", "deltas", "boundary", "vectors", "index_ray", "depth", "index_tri", "origins")
+    out["si_in_depth"] = d2
+    for nme, r in zip(names, res):
+        out["si_" + nme] = r
+    return out
+
+
+def golden_derive_properties():
+    """a11: reference utils.derive_properties (kaolin pack scans behind the stand-in)."""
+    import utils as U
+    g = torch.Generator().manual_seed(11)
+    counts = torch.tensor([2, 0, 4, 1, 0, 8, 3, 0], dtype=torch.long)
+    N = counts.numel()
+    index_ray = torch.repeat_interleave(torch.arange(N), counts)
+    M = int(counts.sum())
+    color = torch.rand(M, 3, generator=g)
+    density = torch.rand(M, generator=g) * 300
+    depths = torch.rand(M, generator=g) * 5
+    deltas = torch.full((M,), 0.005)
+    boundary = torch.ones(M, dtype=torch.bool)
+    boundary[1:] = index_ray[1:] != index_ray[:-1]
+    bk = torch.tensor([0.1, 0.6, 0.3])
+    out = dict(counts=counts, index_ray=index_ray, color=color, density=density, depths=depths, deltas=deltas,
+               boundary=boundary, bk=bk)
+    for bg in ("white", "black", "random"):
+        rgb, a, ids, D, w = U.derive_properties(color, density, depths, deltas, boundary, index_ray,
+                                                render_bkgd=bk, bg_color=bg, N=N)
+        out[bg + "_rgb"], out[bg + "_alpha"], out[bg + "_ids"], out[bg + "_depth"], out[bg + "_w"] = rgb, a, ids, D, w
+    return out
+
+
+def golden_ngp():
+    """a5, a6: reference NGPRadianceField module glue over the tinycudann stand-in."""
+    import radiance_fields.ngp as NGP
+    from oracle import quadfield_oracle as O
+    log2_T = 12
+    p = O.make_ngp_params(seed=42, log2_hashmap_size=log2_T, table_scale=2e3)
+    rf = NGP.NGPRadianceField(aabb=p.aabb.tolist(), log2_hashmap_size=log2_T)
+    with torch.no_grad():
+        rf.mlp_base.params.copy_(torch.cat([w.flatten() for w in p.base_w] + [p.table.flatten()]))
+        rf.mlp_head.params.copy_(torch.cat([w.flatten() for w in p.head_w]))
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(400, 3, generator=g) * 2 - 1) * 1.45
+    x[:8] *= 1.2  # a few points outside the aabb (selector path)
+    d = torch.nn.functional.normalize(torch.randn(400, 3, generator=g), dim=-1)
+    rgb, density = rf(x, d)
+    dens2, feat = rf.query_density(x, return_feat=True)
+    sel, xn = rf.normalize(x)
+    return dict(log2_T=np.int64(log2_T), seed=np.int64(42), table_scale=np.float64(2e3), x=x, d=d,
+                rgb=rgb.detach(), density=density.detach(), feat=feat.detach(), selector=sel, xn=xn)
+
+
+def _np(v):
+    if isinstance(v, torch.Tensor):
+        return v.detach().cpu().numpy()
+    return np.asarray(v)
+
+
+def main():
+    _install()
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
+                     ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
+                     ("ngp", golden_ngp)):
+        data = {k: _np(v) for k, v in fn().items()}
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **data)
+        print(f"wrote {path}: {len(data)} arrays, {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()

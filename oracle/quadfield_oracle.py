@@ -1,0 +1,873 @@
+"""TEST INFRASTRUCTURE ONLY — CPU oracle (numpy / PyTorch fp32) for the Quadfield render hot path.
+
+Standalone restatement of the reference algorithm, row by row of SURVEY.md §8(a).  It never
+touches ``/root/reference`` at run time (that tree does not exist on the GPU box); it is pinned
+against the reference by ``tests/test_oracle_golden.py`` using fixtures that
+``oracle/make_golden.py`` produced from the unmodified reference modules.
+
+All ``file:line`` citations are into ``/root/reference/examples/``.
+
+Numeric conventions shared with the CUDA kernels:
+  * geometry is fp32 with one rounding per operation, no fused multiply-add, in the operand
+    order spelled out below (numpy evaluates ``a*b-c*d`` as three separately rounded ops;
+    the kernel uses ``__fmul_rn/__fadd_rn``), so hit ids / counts are bit-exact;
+  * tcnn module boundaries round to fp16 (hash-grid output, SH output, head input) because
+    tinycudann's encodings emit ``__half``; MLP arithmetic itself is restated in fp32.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+F32 = np.float32
+
+# --------------------------------------------------------------------------------------
+# a1  ray generation — datasets/nerf_synthetic.py:219-226, 289-378
+# --------------------------------------------------------------------------------------
+
+
+def pinhole_intrinsics(width: int, height: int, camera_angle_x: float, upsample: int = 1):
+    """K as built at nerf_synthetic.py:101-102 (focal) and :214-226 (upsample)."""
+    focal = 0.5 * width / math.tan(0.5 * camera_angle_x)
+    focal = focal * upsample
+    W, H = int(width * upsample), int(height * upsample)
+    return F32(focal), F32(W / 2.0), F32(H / 2.0), W, H
+
+
+def generate_rays(c2w: np.ndarray, W: int, H: int, focal, cx, cy, opengl: bool = True):
+    """Eval-mode rays of one camera: nerf_synthetic.py:310-317 (row-major ``meshgrid(indexing="xy")``),
+    :341-360 (camera dirs, rotate, normalise).  Returns origins (N,3), viewdirs (N,3) fp32."""
+    c2w = torch.as_tensor(np.asarray(c2w, dtype=np.float32))
+    x, y = torch.meshgrid(torch.arange(W), torch.arange(H), indexing="xy")
+    x = x.flatten()
+    y = y.flatten()
+    K00 = torch.tensor(focal, dtype=torch.float32)
+    cxt = torch.tensor(cx, dtype=torch.float32)
+    cyt = torch.tensor(cy, dtype=torch.float32)
+    sgn = -1.0 if opengl else 1.0
+    camera_dirs = torch.nn.functional.pad(
+        torch.stack([(x - cxt + 0.5) / K00, (y - cyt + 0.5) / K00 * sgn], dim=-1), (0, 1), value=sgn
+    )
+    directions = (camera_dirs[:, None, :] * c2w[None, :3, :3]).sum(dim=-1)
+    origins = torch.broadcast_to(c2w[:3, -1], directions.shape)
+    viewdirs = directions / torch.linalg.norm(directions, dim=-1, keepdims=True)
+    return origins.contiguous().numpy().copy(), viewdirs.contiguous().numpy().copy()
+
+
+def look_at_c2w(eye, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)) -> np.ndarray:
+    """OpenGL-convention camera-to-world (camera looks down −z), used only to make synthetic poses."""
+    eye = np.asarray(eye, dtype=np.float64)
+    f = np.asarray(target, dtype=np.float64) - eye
+    f /= np.linalg.norm(f)
+    r = np.cross(f, np.asarray(up, dtype=np.float64))
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    m = np.zeros((3, 4), dtype=np.float64)
+    m[:, 0], m[:, 1], m[:, 2], m[:, 3] = r, u, -f, eye
+    return m.astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# synthetic scene: jittered concentric icospheres
+# --------------------------------------------------------------------------------------
+
+
+def icosphere(subdivisions: int) -> Tuple[np.ndarray, np.ndarray]:
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array(
+        [[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+         [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    f = np.array(
+        [[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+         [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5],
+         [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    for _ in range(subdivisions):
+        edges = {}
+        verts = list(v)
+        new_f = []
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in edges:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                edges[key] = len(verts) - 1
+            return edges[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            new_f += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        v = np.array(verts)
+        f = np.array(new_f, dtype=np.int64)
+    return v, f
+
+
+def shell_mesh(radii: Sequence[float], subdivisions: int, jitter: float = 1e-3, seed: int = 42):
+    """Concentric jittered icospheres → (vertices f32 (V,3), faces i32 (F,3))."""
+    rng = np.random.RandomState(seed)
+    v0, f0 = icosphere(subdivisions)
+    vs, fs, base = [], [], 0
+    for r in radii:
+        vs.append(v0 * r + rng.normal(0.0, jitter, size=v0.shape))
+        fs.append(f0 + base)
+        base += v0.shape[0]
+    return np.concatenate(vs).astype(np.float32), np.concatenate(fs).astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# a2  ray–mesh intersection, first K hits by t
+#     replaces trimesh/Embree `intersects_id(..., multiple_hits=True, max_hits=K)`
+#     (mesh_utils.py:223,350-354) and the OptiX `Intersector.find_intersections`
+#     (mesh_utils.py:77-96).  PARITY UNPINNED: neither native library is available; the
+#     predicate below is the definition both the oracle and the kernel implement.
+# --------------------------------------------------------------------------------------
+
+BOX_PAD_REL = F32(1e-4)
+
+
+def mesh_box_pad(vertices: np.ndarray) -> np.float32:
+    """pad = 1e-4 · (largest scene extent), one fp32 multiply."""
+    v = np.asarray(vertices, dtype=np.float32)
+    ext = (v.max(axis=0) - v.min(axis=0)).max()
+    return F32(F32(ext) * BOX_PAD_REL)
+
+
+def triangle_arrays(vertices: np.ndarray, faces: np.ndarray):
+    v = np.asarray(vertices, dtype=np.float32)[np.asarray(faces, dtype=np.int64)]
+    v0, v1, v2 = v[:, 0], v[:, 1], v[:, 2]
+    pad = mesh_box_pad(vertices)
+    lo = np.minimum(np.minimum(v0, v1), v2) - pad
+    hi = np.maximum(np.maximum(v0, v1), v2) + pad
+    return v0, v1 - v0, v2 - v0, lo, hi
+
+
+def face_normals(vertices: np.ndarray, faces: np.ndarray) -> np.ndarray:
+    """trimesh 3.23.5 ``Trimesh.face_normals`` restated (absent dependency, requirements.txt:5):
+    fp64 cross(v1−v0, v2−v1), divided by its length, zero for degenerate faces; the reference
+    casts it to fp32 at mesh_utils.py:104."""
+    v = np.asarray(vertices, dtype=np.float32).astype(np.float64)[np.asarray(faces, dtype=np.int64)]
+    a = v[:, 1] - v[:, 0]
+    b = v[:, 2] - v[:, 1]
+    n = np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1],
+                  a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2],
+                  a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], axis=1)
+    ln = np.sqrt((n[:, 0] * n[:, 0] + n[:, 1] * n[:, 1]) + n[:, 2] * n[:, 2])
+    ok = ln > 0.0
+    out = np.zeros_like(n)
+    out[ok] = n[ok] / ln[ok, None]
+    return out.astype(np.float32)
+
+
+def _ray_tri_block(o, d, v0, e1, e2, lo, hi):
+    """All pairs of R rays × F triangles. o,d: (R,1,3); triangle arrays (1,F,3). Returns hit (R,F) bool, t (R,F) f32.
+
+    Möller–Trumbore in fp32, op order fixed; plus the ray-vs-padded-triangle-box slab test that
+    makes BVH culling exact by monotonicity."""
+    ox, oy, oz = o[..., 0], o[..., 1], o[..., 2]
+    dx, dy, dz = d[..., 0], d[..., 1], d[..., 2]
+    e1x, e1y, e1z = e1[..., 0], e1[..., 1], e1[..., 2]
+    e2x, e2y, e2z = e2[..., 0], e2[..., 1], e2[..., 2]
+    px = dy * e2z - dz * e2y
+    py = dz * e2x - dx * e2z
+    pz = dx * e2y - dy * e2x
+    det = (e1x * px + e1y * py) + e1z * pz
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        inv = F32(1.0) / det
+        tx, ty, tz = ox - v0[..., 0], oy - v0[..., 1], oz - v0[..., 2]
+        u = ((tx * px + ty * py) + tz * pz) * inv
+        qx = ty * e1z - tz * e1y
+        qy = tz * e1x - tx * e1z
+        qz = tx * e1y - ty * e1x
+        v = ((dx * qx + dy * qy) + dz * qz) * inv
+        t = ((e2x * qx + e2y * qy) + e2z * qz) * inv
+        hit = (det != 0) & (u >= 0) & (v >= 0) & ((u + v) <= 1) & (t > 0)
+        # slab test against the triangle's own padded box (fminf/fmaxf semantics = np.fmin/np.fmax)
+        idx, idy, idz = F32(1.0) / dx, F32(1.0) / dy, F32(1.0) / dz
+        ax0, ax1 = (lo[..., 0] - ox) * idx, (hi[..., 0] - ox) * idx
+        ay0, ay1 = (lo[..., 1] - oy) * idy, (hi[..., 1] - oy) * idy
+        az0, az1 = (lo[..., 2] - oz) * idz, (hi[..., 2] - oz) * idz
+        tn = np.fmax(np.fmax(np.fmin(ax0, ax1), np.fmin(ay0, ay1)), np.fmax(np.fmin(az0, az1), F32(0.0)))
+        tf = np.fmin(np.fmin(np.fmax(ax0, ax1), np.fmax(ay0, ay1)), np.fmax(az0, az1))
+        hit &= (tn <= tf) & (t >= tn) & (t <= tf)
+    return hit, t
+
+
+def intersect_firstk(origins, dirs, vertices, faces, K: int, pair_budget: int = 1 << 21):
+    """Brute force over all triangles.  Per ray: every hit, sorted by (t, triangle id), first K.
+
+    Returns tri (N,K) int32 (−1 padded), t (N,K) f32 (+inf padded), count (N,) int32 = min(total,K),
+    total (N,) int32 = untruncated hit count."""
+    o_all = np.ascontiguousarray(origins, dtype=np.float32)
+    d_all = np.ascontiguousarray(dirs, dtype=np.float32)
+    N = o_all.shape[0]
+    v0, e1, e2, lo, hi = (a[None] for a in triangle_arrays(vertices, faces))
+    Fn = v0.shape[1]
+    tri = np.full((N, K), -1, dtype=np.int32)
+    tt = np.full((N, K), np.inf, dtype=np.float32)
+    count = np.zeros(N, dtype=np.int32)
+    total = np.zeros(N, dtype=np.int32)
+    R = max(1, pair_budget // max(Fn, 1))
+    for s in range(0, N, R):
+        o = o_all[s:s + R, None, :]
+        d = d_all[s:s + R, None, :]
+        hit, t = _ray_tri_block(o, d, v0, e1, e2, lo, hi)
+        rr, ff = np.nonzero(hit)
+        if rr.size == 0:
+            continue
+        th = t[rr, ff]
+        order = np.lexsort((ff, th, rr))  # ray, then t, then triangle id
+        rr, ff, th = rr[order], ff[order], th[order]
+        first = np.searchsorted(rr, rr, side="left")
+        rank = np.arange(rr.size) - first
+        np.add.at(total, s + rr, 1)
+        keep = rank < K
+        tri[s + rr[keep], rank[keep]] = ff[keep]
+        tt[s + rr[keep], rank[keep]] = th[keep]
+    count[:] = np.minimum(total, K)
+    return tri, tt, count, total
+
+
+def plane_hit_points(o, r, n, v):
+    """mesh_utils.py:33-40 ``ray_triangle_intersection``: d=−(n·v); t=−((n·o)+d)/(n·r); t←|t|; ψ=o+t r.  fp32."""
+    o, r, n, v = (np.asarray(a, dtype=np.float32) for a in (o, r, n, v))
+    dot = lambda a, b: (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dd = -dot(n, v)
+        t = -(dot(n, o) + dd) / dot(n, r)
+        t = np.abs(t)
+    return o + t[:, None] * r
+
+
+def intersects_id(origins, vectors, vertices, faces, max_hits: int):
+    """The `RayIntersector.intersects_id` contract (mesh_utils.py:87-109): flat
+    (triangle_indices, ray_indices, psi) over all kept hits, ray-major in slot order."""
+    tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits)
+    slot = np.arange(max_hits)[None, :] < count[:, None]
+    ray_indices, _ = np.nonzero(slot)
+    triangle_indices = tri[slot].astype(np.int64)
+    o = np.asarray(origins, dtype=np.float32)[ray_indices]
+    r = np.asarray(vectors, dtype=np.float32)[ray_indices]
+    n = face_normals(vertices, faces)[triangle_indices]
+    v = np.asarray(vertices, dtype=np.float32)[np.asarray(faces, dtype=np.int64)[triangle_indices, 0]]
+    psi = plane_hit_points(o, r, n, v)
+    return triangle_indices, ray_indices.astype(np.int64), psi
+
+
+# --------------------------------------------------------------------------------------
+# a3 / a4  hit tuple and re-sort — mesh_utils.py:343-387, 389-412, 225-231
+# --------------------------------------------------------------------------------------
+
+
+def sampling_raytrace(vectors, origins, vertices, faces, max_hits: int):
+    """`MeshIntersection.sampling_raytrace_numpy` (mesh_utils.py:343-387).  Returns the 7-tuple
+    (points, vectors, index_ray, depth, index_tri, 0, origins) or None when nothing is hit.
+    The reference's `np.argsort` (:359) is not a stable sort; ties keep (t, triangle id) order here."""
+    vectors = np.asarray(vectors, dtype=np.float32)
+    origins = np.asarray(origins, dtype=np.float32)
+    index_tri, index_ray, points = intersects_id(origins, vectors, vertices, faces, max_hits)
+    if index_tri.shape[0] == 0:
+        return None
+    indices = np.argsort(index_ray, kind="stable")
+    index_tri, index_ray, points = index_tri[indices], index_ray[indices], points[indices]
+    vectors = vectors[index_ray]
+    origins = origins[index_ray]
+    norm = _norm3(vectors) + F32(1e-7)
+    vectors = vectors / norm[:, None]
+    depth = _norm3(points - origins)
+    new_indices = np.lexsort((depth, index_ray))
+    return (points[new_indices], vectors[new_indices], index_ray[new_indices], depth[new_indices],
+            index_tri[new_indices], 0, origins)
+
+
+def _norm3(a):
+    return np.sqrt((a[:, 0] * a[:, 0] + a[:, 1] * a[:, 1]) + a[:, 2] * a[:, 2])
+
+
+def mark_pack_boundaries(ids: torch.Tensor) -> torch.Tensor:
+    """kaolin 0.14.0 `render.spc.mark_pack_boundaries` restated (absent dependency): True where a new pack starts."""
+    b = torch.ones_like(ids, dtype=torch.bool)
+    if ids.numel() > 1:
+        b[1:] = ids[1:] != ids[:-1]
+    return b
+
+
+def sampling_indexing(points, origins, vectors, index_ray, depth, index_tri, render_step_size: float = 0.005):
+    """`MeshIntersection.sampling_indexing` (mesh_utils.py:389-412) + `find_deltas` (:225-231)."""
+    new_indices = torch.from_numpy(np.lexsort((depth.numpy(), index_ray.numpy())))
+    index_tri, index_ray = index_tri[new_indices], index_ray[new_indices]
+    points, depth = points[new_indices], depth[new_indices]
+    origins, vectors = origins[new_indices], vectors[new_indices]
+    boundary = mark_pack_boundaries(index_ray)
+    deltas = torch.full((depth.shape[0],), render_step_size, dtype=torch.float32)
+    return points, deltas, boundary, vectors, index_ray, depth, index_tri, origins
+
+
+# --------------------------------------------------------------------------------------
+# a5 / a6 / a7  Instant-NGP field — radiance_fields/ngp.py:146-159, 657-809
+#   tinycudann (un-pinned git dependency, ngp.py:17-21) is absent: HashGrid, FullyFusedMLP and
+#   SphericalHarmonics are restated from its published algorithm.  PARITY UNPINNED for those.
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class GridMeta:
+    n_levels: int
+    n_features: int
+    scale: np.ndarray       # (L,) f32   grid_scale(level)
+    resolution: np.ndarray  # (L,) u32   ceil(scale)+1
+    offset: np.ndarray      # (L+1,) i64 entry offsets
+    size: np.ndarray        # (L,) i64   entries in level ("hashmap_size")
+    hashed: np.ndarray      # (L,) bool  index goes through the spatial hash
+
+    @property
+    def n_entries(self) -> int:
+        return int(self.offset[-1])
+
+
+def make_grid_meta(n_levels: int = 16, base_resolution: int = 16, max_resolution: int = 4096,
+                   log2_hashmap_size: int = 19, n_features: int = 2,
+                   per_level_scale: Optional[float] = None) -> GridMeta:
+    """tcnn GridEncoding level table: scale_l = exp2f(l·log2(b))·base − 1; res_l = ceil(scale_l)+1;
+    size_l = min(align8(res_l³), 2^log2_T); dense indexing while res³ ≤ size_l.  b as at ngp.py:689-691."""
+    if per_level_scale is None:
+        per_level_scale = float(np.exp((np.log(max_resolution) - np.log(base_resolution)) / (n_levels - 1)))
+    log2_pls = F32(np.log2(F32(per_level_scale)))
+    scale = np.zeros(n_levels, dtype=np.float32)
+    res = np.zeros(n_levels, dtype=np.uint32)
+    size = np.zeros(n_levels, dtype=np.int64)
+    hashed = np.zeros(n_levels, dtype=bool)
+    offset = np.zeros(n_levels + 1, dtype=np.int64)
+    T = 1 << log2_hashmap_size
+    for l in range(n_levels):
+        s = F32(F32(np.exp2(F32(F32(l) * log2_pls))) * F32(base_resolution)) - F32(1.0)
+        scale[l] = s
+        r = int(np.ceil(s)) + 1
+        res[l] = r
+        dense = r ** 3
+        n = min((dense + 7) // 8 * 8, T)
+        size[l] = n
+        hashed[l] = dense > n
+        offset[l + 1] = offset[l] + n
+    return GridMeta(n_levels, n_features, scale, res, offset, size, hashed)
+
+
+_PRIMES = (1, 2654435761, 805459861)
+_U32 = 0xFFFFFFFF
+
+
+def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> torch.Tensor:
+    """tcnn `kernel_grid` forward restated.  x01 (M,3) fp32, table (n_entries, F) fp32 holding
+    fp16-representable values.  Output (M, L·F) fp32 holding fp16-rounded values, level-major."""
+    M = x01.shape[0]
+    Fdim = meta.n_features
+    out = torch.empty((M, meta.n_levels * Fdim), dtype=torch.float32)
+    xd = x01.double()
+    for l in range(meta.n_levels):
+        scale = float(meta.scale[l])
+        res = int(meta.resolution[l])
+        size = int(meta.size[l])
+        pos = (xd * scale + 0.5).float()              # fmaf(scale, x, 0.5f)
+        cell = torch.floor(pos)
+        frac = pos - cell
+        cu = cell.to(torch.int64) & _U32              # (uint32_t)(int)floorf(pos)
+        acc = torch.zeros((M, Fdim), dtype=torch.float32)
+        for corner in range(8):
+            w = torch.ones(M, dtype=torch.float32)
+            g = []
+            for dim in range(3):
+                if (corner >> dim) & 1:
+                    w = w * frac[:, dim]
+                    g.append((cu[:, dim] + 1) & _U32)
+                else:
+                    w = w * (1.0 - frac[:, dim])
+                    g.append(cu[:, dim])
+            if meta.hashed[l]:
+                idx = ((g[0] * _PRIMES[0]) & _U32) ^ ((g[1] * _PRIMES[1]) & _U32) ^ ((g[2] * _PRIMES[2]) & _U32)
+            else:
+                idx = (g[0] + ((g[1] * res) & _U32) + ((g[2] * ((res * res) & _U32)) & _U32)) & _U32
+            idx = idx % size + int(meta.offset[l])
+            acc = acc + w[:, None] * table[idx]
+        out[:, l * Fdim:(l + 1) * Fdim] = acc.half().float()
+    return out
+
+
+def sh4(d: torch.Tensor) -> torch.Tensor:
+    """tcnn SphericalHarmonics degree 4 on unit-ish direction d (already mapped back from [0,1]); (M,16) fp32."""
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    xy, xz, yz, x2, y2, z2 = x * y, x * z, y * z, x * x, y * y, z * z
+    o = torch.empty((d.shape[0], 16), dtype=torch.float32)
+    o[:, 0] = 0.28209479177387814
+    o[:, 1] = -0.48860251190291987 * y
+    o[:, 2] = 0.48860251190291987 * z
+    o[:, 3] = -0.48860251190291987 * x
+    o[:, 4] = 1.0925484305920792 * xy
+    o[:, 5] = -1.0925484305920792 * yz
+    o[:, 6] = 0.94617469575755997 * z2 - 0.31539156525251999
+    o[:, 7] = -1.0925484305920792 * xz
+    o[:, 8] = 0.54627421529603959 * x2 - 0.54627421529603959 * y2
+    o[:, 9] = 0.59004358992664352 * y * (-3.0 * x2 + y2)
+    o[:, 10] = 2.8906114426405538 * xy * z
+    o[:, 11] = 0.45704579946446572 * y * (1.0 - 5.0 * z2)
+    o[:, 12] = 0.3731763325901154 * z * (5.0 * z2 - 3.0)
+    o[:, 13] = 0.45704579946446572 * x * (1.0 - 5.0 * z2)
+    o[:, 14] = 1.4453057213202769 * z * (x2 - y2)
+    o[:, 15] = 0.59004358992664352 * x * (-x2 + 3.0 * y2)
+    return o
+
+
+def mlp_forward(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """tcnn FullyFusedMLP semantics: bias-free, ReLU hidden, linear output; weights[i] is (out,in).  fp32 math."""
+    h = x
+    for W in weights[:-1]:
+        h = torch.relu(h @ W.t())
+    return h @ weights[-1].t()
+
+
+@dataclass
+class NGPParams:
+    """Explicit parameters of `NGPRadianceField` (ngp.py:660-746) in tcnn's layout.
+
+    table   (n_entries, 2) fp32, fp16-representable
+    base_w  [(64,32), (16,64)]            mlp_base  32→64→16
+    head_w  [(64,32), (64,64), (16,64)]   mlp_head  31(+1 pad)→64→64→3(+13 pad)
+    """
+    aabb: torch.Tensor
+    meta: GridMeta
+    table: torch.Tensor
+    base_w: List[torch.Tensor]
+    head_w: List[torch.Tensor]
+
+
+HEAD_PAD_VALUE = 1.0  # tcnn pads the 31-wide head input to 32 with ones (Identity-encoding alignment padding)
+
+
+def make_ngp_params(seed: int = 42, log2_hashmap_size: int = 19, table_scale: float = 1e3,
+                    aabb=(-1.5, -1.5, -1.5, 1.5, 1.5, 1.5)) -> NGPParams:
+    """Random-init field of SURVEY §8d C1: table U(−1e-4,1e-4)·table_scale, Xavier-uniform MLPs, rounded to fp16."""
+    g = torch.Generator().manual_seed(seed)
+    meta = make_grid_meta(log2_hashmap_size=log2_hashmap_size)
+    table = ((torch.rand((meta.n_entries, 2), generator=g) * 2 - 1) * 1e-4 * table_scale).half().float()
+
+    def xavier(o, i):
+        b = math.sqrt(6.0 / (i + o))
+        return ((torch.rand((o, i), generator=g) * 2 - 1) * b).half().float()
+
+    base_w = [xavier(64, 32), xavier(16, 64)]
+    head_w = [xavier(64, 32), xavier(64, 64), xavier(16, 64)]
+    return NGPParams(torch.tensor(aabb, dtype=torch.float32), meta, table, base_w, head_w)
+
+
+def ngp_normalize(x: torch.Tensor, aabb: torch.Tensor):
+    """ngp.py:748-755."""
+    aabb_min, aabb_max = aabb[:3], aabb[3:]
+    x = (x - aabb_min) / (aabb_max - aabb_min)
+    selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
+    return selector, x
+
+
+def ngp_query_density(x: torch.Tensor, p: NGPParams):
+    """ngp.py:757-779: σ = trunc_exp(h0 − 1)·selector, feat = h[1:16]."""
+    selector, x01 = ngp_normalize(x, p.aabb)
+    enc = hashgrid_encode(x01, p.table, p.meta)
+    h = mlp_forward(enc, p.base_w)
+    density = torch.exp(h[:, 0:1] - 1.0) * selector[:, None]
+    return density, h[:, 1:16]
+
+
+def ngp_query_rgb(dirs: torch.Tensor, embedding: torch.Tensor, p: NGPParams, apply_act: bool = True):
+    """ngp.py:781-796: SH4((d+1)/2) ⊕ feat → head MLP → sigmoid."""
+    d01 = (dirs + 1.0) / 2.0
+    sh = sh4(d01 * 2.0 - 1.0).half().float()
+    pad = torch.full((dirs.shape[0], 1), HEAD_PAD_VALUE, dtype=torch.float32)
+    h = torch.cat([sh, embedding.half().float(), pad], dim=-1)
+    rgb = mlp_forward(h, p.head_w)[:, :3]
+    return torch.sigmoid(rgb) if apply_act else rgb
+
+
+def ngp_forward(positions: torch.Tensor, directions: torch.Tensor, p: NGPParams):
+    """ngp.py:798-809 → (rgb (M,3), density (M,1))."""
+    assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+    density, emb = ngp_query_density(positions, p)
+    return ngp_query_rgb(directions, emb, p), density
+
+
+# --------------------------------------------------------------------------------------
+# a8  spherical-Gaussian head — ngp.py:371-393, 456-461 ;  texture_utils.py:126-147
+# --------------------------------------------------------------------------------------
+
+
+def sg_features_to_rgb(features: torch.Tensor, dirs: torch.Tensor, num_lobes: int) -> torch.Tensor:
+    """rgb = sigmoid(diffuse + Σ_l c_l·exp(|λ_l|·(â_l·d − 1))), lobe layout [a(3), λ, c(3)] (ngp.py:371-393,456-461)."""
+    rgb = features[:, :3].clone()
+    x = features[:, 3:3 + 7 * num_lobes]
+    for l in range(num_lobes):
+        lobe = x[:, 7 * l:7 * l + 7]
+        axis = lobe[:, :3]
+        axis = axis / torch.linalg.norm(axis, dim=-1, keepdim=True)
+        lam = torch.abs(lobe[:, 3])
+        rgb = rgb + lobe[:, 4:7] * torch.exp(lam * (torch.sum(axis * dirs, -1) - 1))[:, None]
+    return torch.sigmoid(rgb)
+
+
+# --------------------------------------------------------------------------------------
+# a9  baked texture decode — texture_utils.py:149-175, 61-65 ; ngp.py:245-281
+# --------------------------------------------------------------------------------------
+
+
+@dataclass
+class TextureSet:
+    alpha: torch.Tensor            # (S,S) u8
+    diffuse: torch.Tensor          # (S,S,3) u8
+    sg_colors: List[torch.Tensor]  # L × (S,S,3) u8
+    lambdas: List[torch.Tensor]    # L × (S,S,3) u8  [λ, azimuth, elevation]
+    compression_type: str = "linear"
+    lambda_thres: float = 7.5
+
+    @property
+    def num_lobes(self):
+        return len(self.sg_colors)
+
+    @property
+    def texture_size(self):
+        return self.alpha.shape[0]
+
+
+def make_texture_set(size: int, num_lobes: int, seed: int = 42, compression_type="linear", lambda_thres=7.5):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randint(0, 256, s, generator=g, dtype=torch.int32).to(torch.uint8)
+    return TextureSet(r(size, size), r(size, size, 3), [r(size, size, 3) for _ in range(num_lobes)],
+                      [r(size, size, 3) for _ in range(num_lobes)], compression_type, lambda_thres)
+
+
+def _inv_colors(c_u8: torch.Tensor, compress_type: str, thres: float = 12.0):
+    """ngp.py:275-281.  Quirk Q5: only the literal "sigma" takes the logit branch."""
+    c = c_u8.to(torch.float32) / 255.0
+    if compress_type == "sigma":
+        return torch.log(torch.clip(c / (1 - c), 1e-8, 1e37))
+    return c * 2 * thres - thres
+
+
+def texture_decode(indices: torch.Tensor, tex: TextureSet) -> torch.Tensor:
+    """`FeatureCompression.get_features_from_texture_map` (texture_utils.py:149-175) → (M, 3+7L+1) fp32
+    laid out [diffuse(3), L×(axis3, λ, c3), σ]."""
+    i0, i1 = indices[:, 0], indices[:, 1]
+    a = tex.alpha[i0, i1].to(torch.float32) / 255.0
+    sigma = -torch.log(torch.clip(1 - a, 1e-6)) / 0.005                       # texture_utils.py:61-65
+    diffuse = _inv_colors(tex.diffuse[i0, i1], tex.compression_type)
+    cols = [diffuse]
+    for l in range(tex.num_lobes):
+        sh = tex.lambdas[l][i0, i1]
+        lam = torch.exp(sh[:, 0] * tex.lambda_thres / 255 - 2.5)               # ngp.py:260-262
+        az = (sh[:, 1] - 128) / 128 * np.pi                                   # ngp.py:245-252, uint8 wrap (Q6)
+        el = sh[:, 2] / 256 * np.pi
+        axis = torch.stack([torch.cos(az) * torch.sin(el), torch.sin(az) * torch.sin(el), torch.cos(el)], dim=-1)
+        cols += [axis, lam[:, None], _inv_colors(tex.sg_colors[l][i0, i1], tex.compression_type)]
+    cols.append(sigma[:, None])
+    return torch.cat(cols, dim=-1)
+
+
+# --------------------------------------------------------------------------------------
+# a10  barycentric → texel — utils.py:1055-1063 (trimesh.triangles.points_to_barycentric, fp64)
+# --------------------------------------------------------------------------------------
+
+
+def points_to_barycentric(triangles: np.ndarray, points: np.ndarray) -> np.ndarray:
+    """trimesh 3.23.5 `triangles.points_to_barycentric(method="cramer")` restated, fp64 (absent dependency)."""
+    tri = np.asarray(triangles, dtype=np.float64)
+    pts = np.asarray(points, dtype=np.float64)
+    ev = tri[:, 1:] - tri[:, :1]
+    w = pts - tri[:, 0]
+    dot = lambda a, b: (a * b).sum(axis=1)
+    d00, d01, d11 = dot(ev[:, 0], ev[:, 0]), dot(ev[:, 0], ev[:, 1]), dot(ev[:, 1], ev[:, 1])
+    d02, d12 = dot(ev[:, 0], w), dot(ev[:, 1], w)
+    inv = 1.0 / (d00 * d11 - d01 * d01)
+    b = np.zeros((tri.shape[0], 3), dtype=np.float64)
+    b[:, 2] = (d00 * d12 - d01 * d02) * inv
+    b[:, 1] = (d11 * d02 - d01 * d12) * inv
+    b[:, 0] = 1.0 - b[:, 1] - b[:, 2]
+    return b
+
+
+def hit_texels(points: torch.Tensor, index_tri: torch.Tensor, vertices: np.ndarray, faces: np.ndarray,
+               uv_scaled: torch.Tensor, texture_size: int) -> torch.Tensor:
+    """utils.py:1055-1063: b = clamp(bary,0,1); b/=Σb; uv = Σ b_k uv_k; floor; clip to [0,S−1].  (M,2) int64."""
+    f = np.asarray(faces, dtype=np.int64)[index_tri.numpy()]
+    uv_ = uv_scaled[torch.from_numpy(f)]
+    b = points_to_barycentric(np.asarray(vertices, dtype=np.float64)[f], points.numpy())
+    b = torch.clamp(torch.from_numpy(b.astype(np.float32)), 0, 1)
+    b = b / b.sum(-1, keepdim=True)
+    uv_points = torch.sum(uv_ * b[..., None], 1)
+    return torch.clip(torch.floor(uv_points).long(), 0, texture_size - 1)
+
+
+def scale_uv(uv: np.ndarray, size: int) -> torch.Tensor:
+    """test_baking_texture_images.py:325-328."""
+    uv = np.asarray(uv) - 1e-7
+    uv = np.array(uv).astype(np.float32) * size
+    return torch.from_numpy(np.clip(uv, 0, size - 1))
+
+
+# --------------------------------------------------------------------------------------
+# a11  mesh-path compositing — utils.py:863-898 (kaolin exponential_integration / sum_reduce restated)
+# --------------------------------------------------------------------------------------
+
+
+def _segment_ids(boundary: torch.Tensor) -> torch.Tensor:
+    return torch.cumsum(boundary.to(torch.int64), 0) - 1
+
+
+def segmented_exclusive_cumsum(x: torch.Tensor, boundary: torch.Tensor) -> torch.Tensor:
+    """kaolin `cumsum(..., exclusive=True)` per pack; fp64 accumulate so the oracle is order-independent."""
+    seg = _segment_ids(boundary)
+    xd = x.double()
+    inc = torch.cumsum(xd, 0)
+    exc = inc - xd
+    starts = torch.nonzero(boundary).flatten()
+    base = exc[starts]
+    return (exc - base[seg]).to(x.dtype)
+
+
+def segmented_sum(x: torch.Tensor, boundary: torch.Tensor) -> torch.Tensor:
+    seg = _segment_ids(boundary)
+    n = int(seg[-1]) + 1 if seg.numel() else 0
+    out = torch.zeros((n,) + x.shape[1:], dtype=torch.float64)
+    out.index_add_(0, seg, x.double())
+    return out.to(x.dtype)
+
+
+def exponential_integration(feats, tau, boundary):
+    """kaolin 0.14.0 `render.spc.exponential_integration(exclusive=True)` restated: returns
+    (Σ_pack w·feat, w) with w = exp(−excl-cumsum τ)·(1 − e^{−τ})."""
+    alpha = 1.0 - torch.exp(-tau)
+    w = torch.exp(-segmented_exclusive_cumsum(tau, boundary)) * alpha
+    return segmented_sum(w * feats, boundary), w
+
+
+def derive_properties(color, density, depths, deltas, boundary, index_ray, render_bkgd=None,
+                      bg_color="white", N=0):
+    """utils.py:863-898 including quirks Q1 (α multiplies the already-weighted colour) and Q2 (fills)."""
+    color = color.reshape(-1, 3)
+    tau = (density * deltas).reshape(-1, 1)
+    ray_colors, transmittance = exponential_integration(color, tau, boundary)
+    depths, _ = exponential_integration(depths.reshape(-1, 1), tau, boundary)
+    alpha = segmented_sum(transmittance, boundary)
+    out_alpha = torch.zeros(N, 1)
+    Depth = torch.zeros(N, 1)
+    if bg_color == "white":
+        rgb = torch.ones(N, 3)
+        color = (1.0 - alpha) + alpha * ray_colors
+    elif bg_color == "black":
+        rgb = torch.zeros(N, 3)
+        color = alpha * ray_colors
+    else:
+        rgb = torch.ones(N, 3)
+        color = alpha * ray_colors + (1.0 - alpha) * render_bkgd
+    ids = index_ray[boundary]
+    Depth[ids] = depths.float()
+    rgb[ids] = color.float()
+    out_alpha[ids] = alpha.float()
+    return rgb, out_alpha, ids, Depth, transmittance
+
+
+# --------------------------------------------------------------------------------------
+# a12–a15  nerfacc-style compositing — field_rendering.py (nerfacc 0.5.3 pack/scan restated)
+# --------------------------------------------------------------------------------------
+
+
+def pack_info(ray_indices: torch.Tensor, n_rays: Optional[int] = None) -> torch.Tensor:
+    """nerfacc 0.5.3 `pack.pack_info`: counts by index_add, starts by cumsum; assumes ascending ids (Q3)."""
+    if n_rays is None:
+        n_rays = int(ray_indices.max()) + 1 if ray_indices.numel() else 0
+    cnt = torch.zeros((n_rays,), dtype=torch.long)
+    cnt.index_add_(0, ray_indices.long(), torch.ones_like(ray_indices, dtype=torch.long))
+    start = cnt.cumsum(0) - cnt
+    return torch.stack([start, cnt], dim=-1)
+
+
+def _packed_scan(x: torch.Tensor, packed_info: Optional[torch.Tensor], prod: bool) -> torch.Tensor:
+    if packed_info is None:  # batched (n_rays, S)
+        if prod:
+            return torch.cumprod(torch.cat([torch.ones_like(x[..., :1]), x[..., :-1]], dim=-1), dim=-1)
+        return torch.cumsum(torch.cat([torch.zeros_like(x[..., :1]), x[..., :-1]], dim=-1), dim=-1)
+    out = torch.empty_like(x)
+    for s, c in packed_info.tolist():
+        seg = x[s:s + c]
+        if c == 0:
+            continue
+        if prod:
+            out[s:s + c] = torch.cumprod(torch.cat([torch.ones(1, dtype=x.dtype), seg[:-1]]), 0)
+        else:
+            out[s:s + c] = torch.cumsum(torch.cat([torch.zeros(1, dtype=x.dtype), seg[:-1]]), 0)
+    return out
+
+
+def exclusive_sum(x, packed_info=None):
+    return _packed_scan(x, packed_info, prod=False)
+
+
+def exclusive_prod(x, packed_info=None):
+    return _packed_scan(x, packed_info, prod=True)
+
+
+def render_transmittance_from_alpha(alphas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+    """field_rendering.py:161-206."""
+    if ray_indices is not None and packed_info is None:
+        packed_info = pack_info(ray_indices, n_rays)
+    trans = exclusive_prod(1 - alphas, packed_info)
+    if prefix_trans is not None:
+        trans = trans * prefix_trans
+    return trans
+
+
+def render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None,
+                                      n_rays=None, prefix_trans=None):
+    """field_rendering.py:209-264."""
+    if ray_indices is not None and packed_info is None:
+        packed_info = pack_info(ray_indices, n_rays)
+    sigmas_dt = sigmas * (t_ends - t_starts)
+    alphas = 1.0 - torch.exp(-sigmas_dt)
+    trans = torch.exp(-exclusive_sum(sigmas_dt, packed_info))
+    if prefix_trans is not None:
+        trans = trans * prefix_trans
+    return trans, alphas
+
+
+def render_weight_from_alpha(alphas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+    """field_rendering.py:267-309."""
+    trans = render_transmittance_from_alpha(alphas, packed_info, ray_indices, n_rays, prefix_trans)
+    return trans * alphas, trans
+
+
+def render_weight_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None,
+                               prefix_trans=None):
+    """field_rendering.py:312-362."""
+    trans, alphas = render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices,
+                                                      n_rays, prefix_trans)
+    return trans * alphas, trans, alphas
+
+
+def render_visibility_from_alpha(alphas, packed_info=None, ray_indices=None, n_rays=None,
+                                 early_stop_eps=1e-4, alpha_thre=0.0, prefix_trans=None):
+    """field_rendering.py:365-418."""
+    trans = render_transmittance_from_alpha(alphas, packed_info, ray_indices, n_rays, prefix_trans)
+    vis = trans >= early_stop_eps
+    if alpha_thre > 0:
+        vis = vis & (alphas >= alpha_thre)
+    return vis
+
+
+def render_visibility_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None,
+                                   early_stop_eps=1e-4, alpha_thre=0.0, prefix_trans=None):
+    """field_rendering.py:421-480."""
+    trans, alphas = render_transmittance_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices,
+                                                      n_rays, prefix_trans)
+    vis = trans >= early_stop_eps
+    if alpha_thre > 0:
+        vis = vis & (alphas >= alpha_thre)
+    return vis
+
+
+def accumulate_along_rays(weights, values=None, ray_indices=None, n_rays=None):
+    """field_rendering.py:483-547."""
+    src = weights[..., None] if values is None else weights[..., None] * values
+    if ray_indices is not None:
+        out = torch.zeros((n_rays, src.shape[-1]), dtype=src.dtype)
+        out.index_add_(0, ray_indices, src)
+        return out
+    return torch.sum(src, dim=-2)
+
+
+def rendering(t_starts, t_ends, ray_indices=None, n_rays=None, rgbs=None, sigmas=None, alphas=None,
+              render_bkgd=None):
+    """field_rendering.py:14-158 with the callback already evaluated (rgbs + sigmas, or rgbs + alphas)."""
+    if sigmas is not None:
+        weights, trans, alphas = render_weight_from_density(t_starts, t_ends, sigmas, ray_indices=ray_indices,
+                                                            n_rays=n_rays)
+    else:
+        weights, trans = render_weight_from_alpha(alphas, ray_indices=ray_indices, n_rays=n_rays)
+    colors = accumulate_along_rays(weights, rgbs, ray_indices, n_rays)
+    opac = accumulate_along_rays(weights, None, ray_indices, n_rays)
+    depths = accumulate_along_rays(weights, (t_starts + t_ends)[..., None] / 2.0, ray_indices, n_rays)
+    depths = depths / opac.clamp_min(torch.finfo(rgbs.dtype).eps)
+    if render_bkgd is not None:
+        colors = colors + render_bkgd * (1.0 - opac)
+    return colors, opac, depths, dict(weights=weights, trans=trans, alphas=alphas)
+
+
+def reversed_weights(t_starts, t_ends, sigmas, ray_indices, n_rays):
+    """field_rendering.py:719-731 (quirk Q3: pack_info of the *flipped* descending ray ids)."""
+    max_val = torch.max(t_starts) + torch.max(t_ends)
+    ts = torch.flip(max_val - t_starts, dims=[0])
+    te = torch.flip(max_val - t_ends, dims=[0])
+    sg = torch.flip(sigmas, dims=[0])
+    w_rev, _, _ = render_weight_from_density(te, ts, sg, ray_indices=torch.flip(ray_indices, dims=[0]), n_rays=n_rays)
+    return torch.flip(w_rev, dims=[0])
+
+
+# --------------------------------------------------------------------------------------
+# end-to-end drivers (what `bench.py`'s cpu_baseline and the parity tests run)
+# --------------------------------------------------------------------------------------
+
+
+def render_mesh_ngp(origins, viewdirs, vertices, faces, params: NGPParams, K: int, render_step_size=0.005,
+                    bg_color="white", render_bkgd=None, timings: Optional[dict] = None):
+    """utils.py:465-607 with scaling=0 (no deformation): intersect → sort → field(points, viewdirs[index_ray])
+    → derive_properties.  Returns dict(rgb (N,3), opacity (N,1), depth (N,1), + per-hit arrays)."""
+    import time
+    N = origins.shape[0]
+    t0 = time.perf_counter()
+    tup = sampling_raytrace(viewdirs, origins, vertices, faces, K)
+    t1 = time.perf_counter()
+    if tup is None:  # Q9 → Q2 fill
+        fill = 0.0 if bg_color == "black" else 1.0
+        return dict(rgb=torch.full((N, 3), fill), opacity=torch.zeros(N, 1), depth=torch.zeros(N, 1),
+                    index_ray=torch.zeros(0, dtype=torch.long), index_tri=torch.zeros(0, dtype=torch.long),
+                    weights=torch.zeros(0, 1), points=torch.zeros(0, 3), ts=torch.zeros(0))
+    points, dirs, index_ray, depth, index_tri, _, _ = tup
+    points_t = torch.from_numpy(points.astype(np.float32))
+    index_ray_t = torch.from_numpy(index_ray.astype(np.int64))
+    depth_t = torch.from_numpy(depth.astype(np.float32))
+    t_dirs = torch.from_numpy(np.asarray(viewdirs, dtype=np.float32))[index_ray_t]      # Q7: original viewdirs
+    rgbs, sigmas = ngp_forward(points_t, t_dirs, params)
+    t2 = time.perf_counter()
+    boundary = mark_pack_boundaries(index_ray_t)
+    deltas = torch.full((points_t.shape[0],), render_step_size, dtype=torch.float32)
+    rgb, opacity, _, Depth, weights = derive_properties(rgbs, sigmas.squeeze(-1), depth_t, deltas, boundary,
+                                                        index_ray_t, render_bkgd=render_bkgd, bg_color=bg_color, N=N)
+    t3 = time.perf_counter()
+    if timings is not None:
+        timings.update(intersect_s=t1 - t0, field_s=t2 - t1, composite_s=t3 - t2)
+    return dict(rgb=rgb, opacity=opacity, depth=Depth, index_ray=index_ray_t,
+                index_tri=torch.from_numpy(index_tri.astype(np.int64)), weights=weights, points=points_t,
+                ts=depth_t, rgbs=rgbs, sigmas=sigmas)
+
+
+def render_mesh_baked(origins, viewdirs, vertices, faces, uv_scaled, tex: TextureSet, K: int,
+                      render_step_size=0.005, bg_color="white"):
+    """utils.py:998-1095: intersect → sort → texel lookup → decode → SG (tuple dirs, Q7) → derive_properties."""
+    N = origins.shape[0]
+    tup = sampling_raytrace(viewdirs, origins, vertices, faces, K)
+    if tup is None:
+        fill = 0.0 if bg_color == "black" else 1.0
+        return dict(rgb=torch.full((N, 3), fill), opacity=torch.zeros(N, 1), depth=torch.zeros(N, 1))
+    points, dirs, index_ray, depth, index_tri, _, _ = tup
+    points_t = torch.from_numpy(points.astype(np.float32))
+    dirs_t = torch.from_numpy(dirs.astype(np.float32))
+    index_ray_t = torch.from_numpy(index_ray.astype(np.int64))
+    index_tri_t = torch.from_numpy(index_tri.astype(np.int64))
+    depth_t = torch.from_numpy(depth.astype(np.float32))
+    texels = hit_texels(points_t, index_tri_t, vertices, faces, uv_scaled, tex.texture_size)
+    feats = texture_decode(texels, tex)
+    sigmas = feats[:, -1]
+    rgbs = sg_features_to_rgb(feats[:, :-1], dirs_t, tex.num_lobes)
+    boundary = mark_pack_boundaries(index_ray_t)
+    deltas = torch.full((points_t.shape[0],), render_step_size, dtype=torch.float32)
+    rgb, opacity, _, Depth, weights = derive_properties(rgbs, sigmas, depth_t, deltas, boundary, index_ray_t,
+                                                        bg_color=bg_color, N=N)
+    return dict(rgb=rgb, opacity=opacity, depth=Depth, index_ray=index_ray_t, index_tri=index_tri_t,
+                weights=weights, texels=texels, rgbs=rgbs, sigmas=sigmas, points=points_t)

@@ -1,0 +1,1 @@
+"""Import stub (absent offline).  TEST INFRASTRUCTURE ONLY."""

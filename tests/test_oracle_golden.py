@@ -1,0 +1,139 @@
+"""Pin oracle/quadfield_oracle.py against fixtures produced from the unmodified reference
+(oracle/make_golden.py) and against the reference's docstring known-answer vectors."""
+import numpy as np
+import torch
+
+from oracle import quadfield_oracle as O
+
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+def close(a, b, tol=1e-6):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    assert np.max(np.abs(a - b), initial=0.0) <= tol, np.max(np.abs(a - b))
+
+
+def test_docstring_kats():
+    """field_rendering.py:192-195, 246-253, 298-302, 347-355, 403-409."""
+    a = torch.tensor([0.4, 0.8, 0.1, 0.8, 0.1, 0.0, 0.9])
+    r = torch.tensor([0, 0, 0, 1, 1, 2, 2])
+    close(O.render_transmittance_from_alpha(a, ray_indices=r), [1.0, 0.6, 0.12, 1.0, 0.2, 1.0, 1.0])
+    w, tr = O.render_weight_from_alpha(a, ray_indices=r)
+    close(w, [0.4, 0.48, 0.012, 0.8, 0.02, 0.0, 0.9])
+    ts, te = torch.arange(7.0), torch.arange(7.0) + 1
+    w, tr, al = O.render_weight_from_density(ts, te, a, ray_indices=r)
+    close(tr, [1.00, 0.67, 0.30, 1.00, 0.45, 1.00, 1.00], 5e-3)
+    close(al, [0.33, 0.55, 0.095, 0.55, 0.095, 0.00, 0.59], 5e-3)
+    close(w, [0.33, 0.37, 0.03, 0.55, 0.04, 0.00, 0.59], 5e-3)
+    vis = O.render_visibility_from_alpha(a, ray_indices=r, early_stop_eps=0.3, alpha_thre=0.2)
+    assert vis.tolist() == [True, True, False, True, False, False, True]
+    vis = O.render_visibility_from_density(ts, te, a, ray_indices=r, early_stop_eps=0.3, alpha_thre=0.2)
+    assert vis.tolist() == [True, True, False, True, False, False, True]
+
+
+def test_field_rendering_golden(golden):
+    g = golden("field_rendering")
+    ri, n = T(g["ray_indices"]), len(g["counts"])
+    al, sg, ts, te, rgbs, pf = (T(g[k]) for k in ("alphas", "sigmas", "t_starts", "t_ends", "rgbs", "prefix"))
+    close(O.render_transmittance_from_alpha(al, ray_indices=ri, n_rays=n), g["T_alpha"])
+    close(O.render_transmittance_from_alpha(al, ray_indices=ri, n_rays=n, prefix_trans=pf), g["T_alpha_prefix"])
+    w, tr = O.render_weight_from_alpha(al, ray_indices=ri, n_rays=n)
+    close(w, g["w_alpha"])
+    w, tr, a = O.render_weight_from_density(ts, te, sg, ray_indices=ri, n_rays=n)
+    close(w, g["w_density"]), close(tr, g["T_density"]), close(a, g["a_density"])
+    w2, _, _ = O.render_weight_from_density(ts, te, sg, ray_indices=ri, n_rays=n, prefix_trans=pf)
+    close(w2, g["w_density_prefix"])
+    assert np.array_equal(O.render_visibility_from_alpha(al, ray_indices=ri, n_rays=n, early_stop_eps=0.3,
+                                                         alpha_thre=0.2).numpy(), g["vis_alpha"])
+    assert np.array_equal(O.render_visibility_from_density(ts, te, sg, ray_indices=ri, n_rays=n,
+                                                           early_stop_eps=0.05, alpha_thre=0.3).numpy(), g["vis_density"])
+    close(O.accumulate_along_rays(w, rgbs, ri, n), g["acc_rgb"])
+    close(O.accumulate_along_rays(w, None, ri, n), g["acc_w"])
+    c, o, d, _ = O.rendering(ts, te, ri, n, rgbs=rgbs, sigmas=sg, render_bkgd=T(g["bkgd"]))
+    close(c, g["rend_c"]), close(o, g["rend_o"]), close(d, g["rend_d"], 1e-5)
+    c, o, d, _ = O.rendering(ts, te, ri, n, rgbs=rgbs, alphas=al)
+    close(c, g["renda_c"]), close(o, g["renda_o"]), close(d, g["renda_d"], 1e-5)
+    close(O.reversed_weights(ts, te, sg, ri, n), g["rf_wrev"])
+    close(g["rf_w"], g["w_density"])
+    # batched layout
+    w, tr = O.render_weight_from_alpha(T(g["b_alphas"]))
+    close(w, g["b_w_alpha"]), close(tr, g["b_T_alpha"])
+    w, tr, a = O.render_weight_from_density(T(g["b_ts"]), T(g["b_te"]), T(g["b_sigmas"]))
+    close(w, g["b_w_density"]), close(tr, g["b_T_density"]), close(a, g["b_a_density"])
+    close(O.accumulate_along_rays(w, T(g["b_vals"])), g["b_acc"])
+    # the generator also ran the docstring vectors through the reference
+    close(g["kat_T"], [1.0, 0.6, 0.12, 1.0, 0.2, 1.0, 1.0])
+    close(g["kat_w"], [0.4, 0.48, 0.012, 0.8, 0.02, 0.0, 0.9])
+    assert g["kat_vis"].tolist() == [True, True, False, True, False, False, True]
+
+
+def test_sg_decode_golden(golden):
+    g = golden("sg_decode")
+    for L, ctype, lam in ((3, "linear", 5.0), (6, "sigmoid", 7.5), (2, "sigma", 7.5)):
+        k = f"L{L}_{ctype}"
+        tex = O.TextureSet(T(g[k + "_alpha"]), T(g[k + "_diffuse"]), [T(g[k + f"_color{i}"]) for i in range(L)],
+                           [T(g[k + f"_lambda{i}"]) for i in range(L)], ctype, lam)
+        feats = O.texture_decode(T(g[k + "_idx"]), tex)
+        ref = g[k + "_feats"]
+        assert feats.shape == ref.shape == (300, 3 + 7 * L + 1)
+        close(feats, ref, 0.0)
+        close(O.sg_features_to_rgb(feats[:, :-1], T(g[k + "_dirs"]), L), g[k + "_rgb"], 1e-6)
+    close(torch.exp(T(g["trunc_exp_x"])), g["trunc_exp_y"], 0.0)
+    close(torch.exp(torch.clamp(T(g["trunc_exp_x"]), max=15)), g["trunc_exp_g"], 0.0)
+
+
+def test_geometry_golden(golden):
+    g = golden("geometry")
+    K = int(g["K"])
+    tup = O.sampling_raytrace(g["viewdirs"], g["origins"], g["verts"], g["faces"], K)
+    points, vectors, index_ray, depth, index_tri, _, org = tup
+    assert np.array_equal(index_ray, g["index_ray"]) and np.array_equal(index_tri, g["index_tri"])
+    close(points, g["points"], 0.0), close(depth, g["depth"], 0.0), close(vectors, g["vectors"], 0.0)
+    close(org, g["org"], 0.0)
+    # plane-hit formula vs the reference's jit function (torch .sum(1) order may differ by an ulp)
+    close(points, g["psi"], 2e-6)
+    assert index_ray.shape[0] > 500 and np.bincount(index_ray).max() == K
+    res = O.sampling_indexing(T(g["points"]), T(g["org"]), T(g["vectors"]), T(g["index_ray"]), T(g["si_in_depth"]),
+                              T(g["index_tri"]))
+    for nme, r in zip(("points", "deltas", "boundary", "vectors", "index_ray", "depth", "index_tri", "origins"), res):
+        close(r.numpy().astype(np.float64), g["si_" + nme].astype(np.float64), 0.0)
+
+
+def test_derive_properties_golden(golden):
+    g = golden("derive_properties")
+    N = len(g["counts"])
+    for bg in ("white", "black", "random"):
+        rgb, a, ids, D, w = O.derive_properties(T(g["color"]), T(g["density"]), T(g["depths"]), T(g["deltas"]),
+                                                T(g["boundary"]), T(g["index_ray"]), render_bkgd=T(g["bk"]),
+                                                bg_color=bg, N=N)
+        close(rgb, g[bg + "_rgb"]), close(a, g[bg + "_alpha"]), close(D, g[bg + "_depth"], 1e-5)
+        close(w, g[bg + "_w"])
+        assert np.array_equal(ids.numpy(), g[bg + "_ids"])
+    # Q2: rays without hits keep the fill
+    empty = np.nonzero(g["counts"] == 0)[0]
+    assert np.all(g["white_rgb"][empty] == 1.0) and np.all(g["random_rgb"][empty] == 1.0)
+    assert np.all(g["black_rgb"][empty] == 0.0) and np.all(g["white_alpha"][empty] == 0.0)
+
+
+def test_ngp_golden(golden):
+    g = golden("ngp")
+    p = O.make_ngp_params(seed=int(g["seed"]), log2_hashmap_size=int(g["log2_T"]), table_scale=float(g["table_scale"]))
+    x, d = T(g["x"]), T(g["d"])
+    sel, xn = O.ngp_normalize(x, p.aabb)
+    assert np.array_equal(sel.numpy(), g["selector"]) and not sel.all() and sel.any()
+    close(xn, g["xn"], 0.0)
+    dens, feat = O.ngp_query_density(x, p)
+    close(dens, g["density"], 1e-5 * float(g["density"].max())), close(feat, g["feat"], 1e-5)
+    rgb, dens2 = O.ngp_forward(x, d, p)
+    close(rgb, g["rgb"], 1e-5)
+    assert g["rgb"].std() > 0.01 and g["density"].std() > 0.01, "fixture must not be degenerate"
+
+
+def test_grid_meta_matches_survey():
+    """6 299 960 entries at T=2^19 (levels 0-4 dense), 22 565 520 at T=2^21 (0-5 dense)."""
+    m = O.make_grid_meta(log2_hashmap_size=19)
+    assert m.n_entries == 6299960 and m.resolution[:5].tolist() == [16, 24, 34, 49, 71]
+    assert m.hashed.tolist() == [False] * 5 + [True] * 11
+    m = O.make_grid_meta(log2_hashmap_size=21)
+    assert m.n_entries == 22565520 and m.hashed.tolist() == [False] * 6 + [True] * 10
