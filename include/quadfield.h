@@ -1,0 +1,213 @@
+/*
+ * quadfield.h — C ABI of libquadfield.so, the B200 (sm_100a) drop-in for the Quadfield
+ * (ubc-vision/quadraturefields) render hot path.
+ *
+ * Conventions
+ *   - every pointer whose name starts with d_ is DEVICE memory on the current CUDA device;
+ *     h_ is host memory.  The caller owns all buffers it passes (outputs come from torch.empty).
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised, unless the
+ *     function is documented as synchronous (the *_create functions and qf_hits_total).
+ *   - return value 0 = ok; anything else = error, text via qf_last_error() (thread local).
+ *   - no exceptions cross this boundary; no torch types appear in it.
+ *
+ * Each entry point names the reference interface it replaces; file:line is into
+ * /root/reference/examples/ (see SURVEY.md §8b).  The reference-side binding a maintainer would
+ * add is shown in INTEGRATION.md.
+ */
+#ifndef QUADFIELD_H
+#define QUADFIELD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QF_OK 0
+#define QF_ERR_INVALID 1
+#define QF_ERR_CUDA 2
+#define QF_ERR_UNSUPPORTED 3
+
+#define QF_MAX_HITS 32       /* largest K (max_hits / num_intersections) supported */
+#define QF_MAX_LEVELS 16     /* hash-grid levels */
+#define QF_MAX_LOBES 8       /* spherical-Gaussian lobes in the baked texture set */
+
+#define QF_BG_WHITE 0
+#define QF_BG_BLACK 1
+#define QF_BG_RANDOM 2       /* "random": hit rays mix with render_bkgd, missed rays stay white (quirk Q2) */
+
+const char* qf_last_error(void);
+int qf_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Geometry: quadrature mesh + BVH.
+ * Replaces the private OptiX pybind object `intersector.Intersector(vertices_flat, max_hits, device)`
+ * with `.find_intersections(rays_flat)` / `.update_vertices(vertices)` (mesh_utils.py:77-96) and the
+ * Embree `RayMeshIntersector(mesh).intersects_id(...)` default (mesh_utils.py:223,350-354).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qf_mesh qf_mesh;
+
+/* Build: padded triangle boxes, fp64 face normals, 63-bit Morton LBVH.  Synchronous. */
+int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const int32_t* d_faces, int64_t n_faces,
+                   void* stream, qf_mesh** out);
+/* `Intersector.update_vertices` (mesh_utils.py:83-84; train_finetune.py:714-718): same topology, new
+ * positions; rebuilds the hierarchy on `stream`. */
+int qf_mesh_update_vertices(qf_mesh* mesh, const float* d_vertices, void* stream);
+void qf_mesh_destroy(qf_mesh* mesh);
+/* info[0]=n_faces, [1]=n_vertices, [2]=n_nodes, [3]=device bytes held */
+int qf_mesh_info(const qf_mesh* mesh, int64_t* info4, float* box_pad);
+
+/* `find_intersections`: first K hits of every ray ordered by (t, triangle id); d_tri is the
+ * reference's int[N*max_hits] with -1 padding (mesh_utils.py:91-96).  d_t (may be NULL) gets the
+ * Möller–Trumbore t (+inf padded), d_count min(total,K), d_total (may be NULL) the untruncated count. */
+int qf_trace_firstk(const qf_mesh* mesh, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
+                    int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* stream);
+
+/* Exclusive scan of d_count into d_offsets[n_rays+1] (ray-major hit layout).  workspace >= qf_scan_workspace_bytes. */
+size_t qf_scan_workspace_bytes(int64_t n);
+int qf_hits_offsets(const int32_t* d_count, int64_t n_rays, int64_t* d_offsets, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
+/* Synchronous read of d_offsets[n_rays] (the reference syncs here too: it returns numpy arrays). */
+int qf_hits_total(const int64_t* d_offsets, int64_t n_rays, int64_t* h_total, void* stream);
+
+/* `MeshIntersection.sampling_raytrace_numpy` (mesh_utils.py:343-387) after the intersector call:
+ * plane-hit points (mesh_utils.py:33-40), dirs/(|d|+1e-7), depth=|p-o|, per-ray stable sort by depth.
+ * Outputs are the reference's data tuple (nerf_synthetic.py:256-257) in ray-major order. */
+int qf_hits_pack(const qf_mesh* mesh, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
+                 const int32_t* d_tri, const int32_t* d_count, const int64_t* d_offsets,
+                 float* d_points, float* d_vectors, int64_t* d_index_ray, float* d_depth, int64_t* d_index_tri,
+                 float* d_origins_out, void* stream);
+
+/* `sampling_indexing` (mesh_utils.py:389-412): per-ray stable re-sort by depth of a ray-major tuple
+ * (the reference does a GPU->CPU lexsort here), pack boundaries (kaolin mark_pack_boundaries) and the
+ * constant quadrature step (find_deltas, :225-231).  d_perm receives the permutation applied. */
+int qf_hits_resort(const int64_t* d_index_ray, const float* d_depth, int64_t n_hits, int64_t* d_perm,
+                   uint8_t* d_boundary, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2)+(3) Instant-NGP radiance field: multiresolution hash grid + fully fused 64-wide MLPs.
+ * Replaces tinycudann HashGrid / FullyFusedMLP / SphericalHarmonics as used by
+ * NGPRadianceField (radiance_fields/ngp.py:657-809).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t n_levels;                    /* <= QF_MAX_LEVELS, 2 features per level */
+  float scale[QF_MAX_LEVELS];          /* tcnn grid_scale(level) */
+  uint32_t resolution[QF_MAX_LEVELS];  /* ceil(scale)+1 */
+  uint32_t offset[QF_MAX_LEVELS];      /* first entry of the level in the table */
+  uint32_t size[QF_MAX_LEVELS];        /* entries in the level */
+  uint32_t hashed[QF_MAX_LEVELS];      /* 1: spatial hash, 0: dense index */
+  float aabb[6];                       /* NGPRadianceField.aabb buffer */
+} qf_grid_desc;
+
+typedef struct qf_ngp qf_ngp;
+
+/* Parameters in tinycudann's layout, fp32 master copies on the device (converted to fp16 inside):
+ *   d_table   (n_entries, 2)
+ *   d_base_w  [64x32 | 16x64]            mlp_base  32 -> 64 -> 16   (row-major (out,in), no bias)
+ *   d_head_w  [64x32 | 64x64 | 16x64]    mlp_head  31(+pad) -> 64 -> 64 -> 3(+pad)
+ * Synchronous. */
+int qf_ngp_create(const qf_grid_desc* desc, const float* d_table, int64_t n_entries, const float* d_base_w,
+                  const float* d_head_w, void* stream, qf_ngp** out);
+/* refresh the fp16 working copies after an optimizer step */
+int qf_ngp_update(qf_ngp* f, const float* d_table, const float* d_base_w, const float* d_head_w, void* stream);
+void qf_ngp_destroy(qf_ngp* f);
+
+/* tcnn HashGrid forward alone: x01 (M,3) in [0,1] -> (M, 2*n_levels) fp32 holding fp16-rounded features. */
+int qf_hashgrid_forward(const qf_ngp* f, const float* d_x01, int64_t M, float* d_enc, void* stream);
+/* `NGPRadianceField.query_density(x, return_feat)` (ngp.py:757-779): d_feat (M,15) may be NULL. */
+int qf_ngp_query_density(const qf_ngp* f, const float* d_positions, int64_t M, float* d_density, float* d_feat,
+                         void* stream);
+/* `NGPRadianceField.forward(positions, directions)` (ngp.py:798-809) -> rgb (M,3), density (M,1).
+ * If d_ray_index != NULL directions are gathered as d_directions[d_ray_index[i]] (utils.py:515-529). */
+int qf_ngp_forward(const qf_ngp* f, const float* d_positions, const float* d_directions,
+                   const int64_t* d_ray_index, int64_t M, float* d_rgb, float* d_density, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) Baked spherical-Gaussian texture path.
+ * Replaces FeatureCompression.get_features_from_texture_map (texture_utils.py:149-175), the
+ * barycentric texel lookup (utils.py:1055-1063) and features_to_rgb (ngp.py:371-393,456-461).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct qf_texture qf_texture;
+/* planes as the reference holds them: alpha (S,S) u8, diffuse (S,S,3) u8, per lobe colour (S,S,3) u8 and
+ * [lambda,azimuth,elevation] (S,S,3) u8.  Repacked into one interleaved record per texel.
+ * colour_logit = 1 only for compression_type == "sigma" (quirk Q5).  Synchronous. */
+int qf_texture_create(int size, int num_lobes, const uint8_t* d_alpha, const uint8_t* d_diffuse,
+                      const uint8_t* const* h_d_colors, const uint8_t* const* h_d_lambdas, int colour_logit,
+                      float lambda_thres, void* stream, qf_texture** out);
+void qf_texture_destroy(qf_texture* t);
+/* get_features_from_texture_map: indices (M,2) int64 -> features (M, 3+7L+1) fp32 */
+int qf_texture_decode(const qf_texture* t, const int64_t* d_indices, int64_t M, float* d_features, void* stream);
+/* features_to_rgb: features (M, 3+7L[+1]) with row stride `stride` floats, dirs (M,3) -> rgb (M,3) */
+int qf_sg_features_to_rgb(const float* d_features, int64_t stride, int num_lobes, const float* d_dirs, int64_t M,
+                          float* d_rgb, void* stream);
+/* utils.py:1055-1063: hit points + triangle ids -> texel (M,2) int64; uv_scaled (V,2) fp32 */
+int qf_hit_texels(const qf_mesh* mesh, const float* d_points, const int64_t* d_index_tri, int64_t M,
+                  const float* d_uv_scaled, int texture_size, int64_t* d_texels, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (5) Compositing.
+ * ------------------------------------------------------------------------------------------ */
+/* `utils.derive_properties` (utils.py:863-898) on ray-major hits described by offsets (n_rays+1):
+ * rgb (N,3), alpha (N,1), depth (N,1), weights (M) [may be NULL].  d_bkgd (3) only for QF_BG_RANDOM. */
+int qf_derive_properties(const float* d_color, const float* d_density, const float* d_depths, float delta,
+                         const int64_t* d_offsets, int64_t n_rays, int bg_mode, const float* d_bkgd,
+                         float* d_rgb, float* d_alpha, float* d_depth_out, float* d_weights, void* stream);
+
+/* nerfacc-style segmented scans behind field_rendering.py (exclusive_prod / exclusive_sum, :203,:261).
+ * packed_info (n_rays,2) int64 [start,count].  mode 0: from alphas; 1: from sigmas*(t_ends-t_starts).
+ * Writes weights, trans, alphas (any may be NULL).  Warp-per-ray segmented scan. */
+int qf_render_weights(int mode, const float* d_alphas_or_sigmas, const float* d_t_starts, const float* d_t_ends,
+                      const int64_t* d_packed_info, int64_t n_rays, int64_t n_samples, const float* d_prefix_trans,
+                      float* d_weights, float* d_trans, float* d_alphas_out, void* stream);
+/* backward of the above w.r.t. alphas / sigmas given dL/dweights and dL/dtrans (either may be NULL) */
+int qf_render_weights_backward(int mode, const float* d_alphas_or_sigmas, const float* d_t_starts,
+                               const float* d_t_ends, const int64_t* d_packed_info, int64_t n_rays,
+                               int64_t n_samples, const float* d_prefix_trans, const float* d_grad_weights,
+                               const float* d_grad_trans, float* d_grad_in, void* stream);
+/* `accumulate_along_rays` (field_rendering.py:483-547): out (n_rays,D) = sum_i w_i * v_i, deterministic
+ * (segment order) when packed_info is given; values may be NULL (D=1). */
+int qf_accumulate_along_rays(const float* d_weights, const float* d_values, int D, const int64_t* d_packed_info,
+                             int64_t n_rays, float* d_out, int accumulate_into, void* stream);
+/* same for arbitrary (unsorted) ray_indices — `index_add_` semantics (field_rendering.py:544,571), atomics;
+ * d_out must be pre-initialised (zeros, or the tensor of accumulate_along_rays_). */
+int qf_accumulate_along_rays_indexed(const float* d_weights, const float* d_values, int D, const int64_t* d_ray_indices,
+                                     int64_t n_samples, float* d_out, void* stream);
+/* autograd of accumulate_along_rays: grad_weights (M) and grad_values (M,D), either may be NULL */
+int qf_accumulate_along_rays_backward(const float* d_weights, const float* d_values, int D, const int64_t* d_ray_indices,
+                                      int64_t n_samples, const float* d_grad_out, float* d_grad_weights,
+                                      float* d_grad_values, void* stream);
+/* nerfacc pack.pack_info: counts by index, starts by exclusive scan (so a *descending* index array
+ * reproduces quirk Q3).  workspace >= qf_pack_info_workspace_bytes(n_rays). */
+size_t qf_pack_info_workspace_bytes(int64_t n_rays);
+int qf_pack_info(const int64_t* d_ray_indices, int64_t n_samples, int64_t n_rays, int64_t* d_packed_info,
+                 void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused frame render: rays -> image, everything resident (utils.py:465-607 with scaling=0, and
+ * utils.py:998-1095).  Outputs rgb (N,3), alpha (N,1), depth (N,1); d_hits_total (1 x int32, may be NULL)
+ * receives the number of hit samples shaded.
+ * ------------------------------------------------------------------------------------------ */
+size_t qf_render_workspace_bytes(int64_t n_rays, int K);
+int qf_render_mesh_ngp(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
+                       int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
+                       float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
+                       size_t workspace_bytes, void* stream);
+int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled,
+                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta,
+                         int bg_mode, const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth,
+                         int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Optional per-stage CUDA-event timing of the fused render on its own stream (off by default).
+ * qf_profile_read sums {trace, shade, composite} milliseconds recorded since the last read (synchronises). */
+int qf_profile_enable(int on);
+int qf_profile_read(double* ms3, int64_t* n_chunks);
+
+/* a1: eval-mode pinhole rays of one camera (datasets/nerf_synthetic.py:310-360), c2w (3,4) row-major on host */
+int qf_generate_rays(const float* h_c2w, int W, int H, float focal, float cx, float cy, int opengl,
+                     float* d_origins, float* d_viewdirs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADFIELD_H */

@@ -197,11 +197,12 @@ def _ray_tri_block(o, d, v0, e1, e2, lo, hi):
     return hit, t
 
 
-def intersect_firstk(origins, dirs, vertices, faces, K: int, pair_budget: int = 1 << 21):
+def intersect_firstk(origins, dirs, vertices, faces, K: int, pair_budget: int = 1 << 21, threads: int = 1):
     """Brute force over all triangles.  Per ray: every hit, sorted by (t, triangle id), first K.
 
     Returns tri (N,K) int32 (−1 padded), t (N,K) f32 (+inf padded), count (N,) int32 = min(total,K),
-    total (N,) int32 = untruncated hit count."""
+    total (N,) int32 = untruncated hit count.  `threads` > 1 runs ray chunks on a thread pool (numpy
+    releases the GIL inside ufuncs); the result does not depend on it."""
     o_all = np.ascontiguousarray(origins, dtype=np.float32)
     d_all = np.ascontiguousarray(dirs, dtype=np.float32)
     N = o_all.shape[0]
@@ -212,22 +213,32 @@ def intersect_firstk(origins, dirs, vertices, faces, K: int, pair_budget: int = 
     count = np.zeros(N, dtype=np.int32)
     total = np.zeros(N, dtype=np.int32)
     R = max(1, pair_budget // max(Fn, 1))
-    for s in range(0, N, R):
+
+    def chunk(s):
         o = o_all[s:s + R, None, :]
         d = d_all[s:s + R, None, :]
         hit, t = _ray_tri_block(o, d, v0, e1, e2, lo, hi)
         rr, ff = np.nonzero(hit)
         if rr.size == 0:
-            continue
+            return
         th = t[rr, ff]
         order = np.lexsort((ff, th, rr))  # ray, then t, then triangle id
         rr, ff, th = rr[order], ff[order], th[order]
         first = np.searchsorted(rr, rr, side="left")
         rank = np.arange(rr.size) - first
-        np.add.at(total, s + rr, 1)
+        np.add.at(total, s + rr, 1)       # chunks own disjoint ray ranges
         keep = rank < K
         tri[s + rr[keep], rank[keep]] = ff[keep]
         tt[s + rr[keep], rank[keep]] = th[keep]
+
+    starts = list(range(0, N, R))
+    if threads > 1 and len(starts) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(chunk, starts))
+    else:
+        for s in starts:
+            chunk(s)
     count[:] = np.minimum(total, K)
     return tri, tt, count, total
 
@@ -243,10 +254,10 @@ def plane_hit_points(o, r, n, v):
     return o + t[:, None] * r
 
 
-def intersects_id(origins, vectors, vertices, faces, max_hits: int):
+def intersects_id(origins, vectors, vertices, faces, max_hits: int, threads: int = 1):
     """The `RayIntersector.intersects_id` contract (mesh_utils.py:87-109): flat
     (triangle_indices, ray_indices, psi) over all kept hits, ray-major in slot order."""
-    tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits)
+    tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits, threads=threads)
     slot = np.arange(max_hits)[None, :] < count[:, None]
     ray_indices, _ = np.nonzero(slot)
     triangle_indices = tri[slot].astype(np.int64)
@@ -263,13 +274,13 @@ def intersects_id(origins, vectors, vertices, faces, max_hits: int):
 # --------------------------------------------------------------------------------------
 
 
-def sampling_raytrace(vectors, origins, vertices, faces, max_hits: int):
+def sampling_raytrace(vectors, origins, vertices, faces, max_hits: int, threads: int = 1):
     """`MeshIntersection.sampling_raytrace_numpy` (mesh_utils.py:343-387).  Returns the 7-tuple
     (points, vectors, index_ray, depth, index_tri, 0, origins) or None when nothing is hit.
     The reference's `np.argsort` (:359) is not a stable sort; ties keep (t, triangle id) order here."""
     vectors = np.asarray(vectors, dtype=np.float32)
     origins = np.asarray(origins, dtype=np.float32)
-    index_tri, index_ray, points = intersects_id(origins, vectors, vertices, faces, max_hits)
+    index_tri, index_ray, points = intersects_id(origins, vectors, vertices, faces, max_hits, threads=threads)
     if index_tri.shape[0] == 0:
         return None
     indices = np.argsort(index_ray, kind="stable")
@@ -582,7 +593,7 @@ def points_to_barycentric(triangles: np.ndarray, points: np.ndarray) -> np.ndarr
     pts = np.asarray(points, dtype=np.float64)
     ev = tri[:, 1:] - tri[:, :1]
     w = pts - tri[:, 0]
-    dot = lambda a, b: (a * b).sum(axis=1)
+    dot = lambda a, b: (a[:, 0] * b[:, 0] + a[:, 1] * b[:, 1]) + a[:, 2] * b[:, 2]
     d00, d01, d11 = dot(ev[:, 0], ev[:, 0]), dot(ev[:, 0], ev[:, 1]), dot(ev[:, 1], ev[:, 1])
     d02, d12 = dot(ev[:, 0], w), dot(ev[:, 1], w)
     inv = 1.0 / (d00 * d11 - d01 * d01)
@@ -600,8 +611,8 @@ def hit_texels(points: torch.Tensor, index_tri: torch.Tensor, vertices: np.ndarr
     uv_ = uv_scaled[torch.from_numpy(f)]
     b = points_to_barycentric(np.asarray(vertices, dtype=np.float64)[f], points.numpy())
     b = torch.clamp(torch.from_numpy(b.astype(np.float32)), 0, 1)
-    b = b / b.sum(-1, keepdim=True)
-    uv_points = torch.sum(uv_ * b[..., None], 1)
+    b = b / ((b[:, 0] + b[:, 1]) + b[:, 2])[:, None]
+    uv_points = (uv_[:, 0] * b[:, 0:1] + uv_[:, 1] * b[:, 1:2]) + uv_[:, 2] * b[:, 2:3]
     return torch.clip(torch.floor(uv_points).long(), 0, texture_size - 1)
 
 
@@ -815,13 +826,13 @@ def reversed_weights(t_starts, t_ends, sigmas, ray_indices, n_rays):
 
 
 def render_mesh_ngp(origins, viewdirs, vertices, faces, params: NGPParams, K: int, render_step_size=0.005,
-                    bg_color="white", render_bkgd=None, timings: Optional[dict] = None):
+                    bg_color="white", render_bkgd=None, timings: Optional[dict] = None, threads: int = 1):
     """utils.py:465-607 with scaling=0 (no deformation): intersect → sort → field(points, viewdirs[index_ray])
     → derive_properties.  Returns dict(rgb (N,3), opacity (N,1), depth (N,1), + per-hit arrays)."""
     import time
     N = origins.shape[0]
     t0 = time.perf_counter()
-    tup = sampling_raytrace(viewdirs, origins, vertices, faces, K)
+    tup = sampling_raytrace(viewdirs, origins, vertices, faces, K, threads=threads)
     t1 = time.perf_counter()
     if tup is None:  # Q9 → Q2 fill
         fill = 0.0 if bg_color == "black" else 1.0

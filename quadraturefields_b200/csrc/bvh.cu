@@ -1,0 +1,522 @@
+// (1) Quadrature-mesh BVH: GPU LBVH build (63-bit Morton, Karras 2012) and first-K all-hits traversal.
+//
+// Replaces the OptiX `intersector.Intersector` pybind object (mesh_utils.py:77-96) and the Embree
+// default (mesh_utils.py:223,350-354).  B200 has no RT cores, so traversal is a software
+// while-while loop on the SMs: 64-byte two-child nodes fetched as 4 x LDG.128 through the
+// read-only path, Morton-ordered 48-byte triangle records, a per-ray sorted K-buffer held in
+// registers, and the K-th hit's t used as the culling distance once the buffer is full.
+//
+// Exactness: a node is entered iff the fp32 slab test of its box passes; the triangle predicate
+// contains the same slab test on the triangle's own padded box, and node boxes are exact unions
+// of those, so by monotonicity of rounding no triangle that the brute-force oracle accepts can be
+// culled.
+//
+// This file is compiled with -fmad=false; all predicate arithmetic additionally uses explicit
+// round-to-nearest intrinsics.
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <float.h>
+
+#include "traverse.cuh"
+
+namespace qf {
+
+// ---------------------------------------------------------------- scene bounds + pad
+__device__ __forceinline__ int float_to_ordered(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void bounds_init_kernel(int* __restrict__ ob) {
+  if (threadIdx.x < 3) ob[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) ob[threadIdx.x] = INT_MIN;
+}
+
+__global__ void bounds_kernel(const float* __restrict__ v, int64_t n, int* __restrict__ ob) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float x = __ldg(v + 3 * i + c);
+      lo[c] = fminf(lo[c], x);
+      hi[c] = fmaxf(hi[c], x);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(ob + c, float_to_ordered(lo[c]));
+      atomicMax(ob + 3 + c, float_to_ordered(hi[c]));
+    }
+  }
+}
+
+// scene[0..5] = bounds, scene[6] = pad = (largest extent) * 1e-4f  (oracle: mesh_box_pad)
+__global__ void bounds_finish_kernel(const int* __restrict__ ob, float* __restrict__ scene) {
+  float lo[3], hi[3];
+  for (int c = 0; c < 3; ++c) {
+    lo[c] = ordered_to_float(ob[c]);
+    hi[c] = ordered_to_float(ob[3 + c]);
+    scene[c] = lo[c];
+    scene[3 + c] = hi[c];
+  }
+  float ext = fmaxf(fmaxf(__fsub_rn(hi[0], lo[0]), __fsub_rn(hi[1], lo[1])), __fsub_rn(hi[2], lo[2]));
+  scene[6] = __fmul_rn(ext, 1e-4f);
+}
+
+// ---------------------------------------------------------------- per-triangle setup
+__device__ __forceinline__ uint64_t expand21(uint64_t x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void tri_setup_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, int64_t F,
+                                 const float* __restrict__ scene, uint64_t* __restrict__ keys,
+                                 uint32_t* __restrict__ idx, float4* __restrict__ planes) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  int a = faces[3 * f], b = faces[3 * f + 1], c = faces[3 * f + 2];
+  float v0[3], v1[3], v2[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v0[k] = verts[3 * (int64_t)a + k]; v1[k] = verts[3 * (int64_t)b + k]; v2[k] = verts[3 * (int64_t)c + k]; }
+  // Morton key of the box centre, 21 bits per axis
+  uint64_t q[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    float lo = scene[k], hi = scene[3 + k];
+    float cen = 0.5f * (min3(v0[k], v1[k], v2[k]) + max3(v0[k], v1[k], v2[k]));
+    float ext = hi - lo;
+    float u = ext > 0.f ? (cen - lo) / ext : 0.f;
+    u = fminf(fmaxf(u, 0.f), 1.f);
+    q[k] = (uint64_t)fminf(u * 2097152.0f, 2097151.0f);
+  }
+  keys[f] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+  idx[f] = (uint32_t)f;
+  // trimesh face_normals: fp64 cross(v1-v0, v2-v1) / |.|, zero if degenerate; cast to fp32 (mesh_utils.py:104)
+  double ax = (double)v1[0] - (double)v0[0], ay = (double)v1[1] - (double)v0[1], az = (double)v1[2] - (double)v0[2];
+  double bx = (double)v2[0] - (double)v1[0], by = (double)v2[1] - (double)v1[1], bz = (double)v2[2] - (double)v1[2];
+  double nx = __dsub_rn(__dmul_rn(ay, bz), __dmul_rn(az, by));
+  double ny = __dsub_rn(__dmul_rn(az, bx), __dmul_rn(ax, bz));
+  double nz = __dsub_rn(__dmul_rn(ax, by), __dmul_rn(ay, bx));
+  double ln = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny)), __dmul_rn(nz, nz)));
+  float fx = 0.f, fy = 0.f, fz = 0.f;
+  if (ln > 0.0) { fx = (float)__ddiv_rn(nx, ln); fy = (float)__ddiv_rn(ny, ln); fz = (float)__ddiv_rn(nz, ln); }
+  float d = -__fadd_rn(__fadd_rn(__fmul_rn(fx, v0[0]), __fmul_rn(fy, v0[1])), __fmul_rn(fz, v0[2]));
+  planes[f] = make_float4(fx, fy, fz, d);
+}
+
+__global__ void tri_gather_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, int64_t F,
+                                  const uint32_t* __restrict__ idx_sorted, float4* __restrict__ tris) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= F) return;
+  uint32_t f = idx_sorted[k];
+  int a = faces[3 * (int64_t)f], b = faces[3 * (int64_t)f + 1], c = faces[3 * (int64_t)f + 2];
+  tris[3 * k + 0] = make_float4(verts[3 * (int64_t)a], verts[3 * (int64_t)a + 1], verts[3 * (int64_t)a + 2], __int_as_float((int)f));
+  tris[3 * k + 1] = make_float4(verts[3 * (int64_t)b], verts[3 * (int64_t)b + 1], verts[3 * (int64_t)b + 2], 0.f);
+  tris[3 * k + 2] = make_float4(verts[3 * (int64_t)c], verts[3 * (int64_t)c + 1], verts[3 * (int64_t)c + 2], 0.f);
+}
+
+// ---------------------------------------------------------------- Karras hierarchy
+__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void karras_kernel(const uint64_t* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                              int* __restrict__ parent, int* __restrict__ leaf_parent, int* __restrict__ first,
+                              int* __restrict__ last) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta_fn(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta_fn(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  // child refs: >=0 internal, ~k leaf k
+  int L = (lo == gamma) ? ~gamma : gamma;
+  int R = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  left[i] = L; right[i] = R; first[i] = lo; last[i] = hi;
+  if (L >= 0) parent[L] = i; else leaf_parent[gamma] = i;
+  if (R >= 0) parent[R] = i; else leaf_parent[gamma + 1] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+__device__ __forceinline__ void tri_box(const float4* __restrict__ tris, int k, float pad, float* lo, float* hi) {
+  float4 a = tris[3 * (int64_t)k], b = tris[3 * (int64_t)k + 1], c = tris[3 * (int64_t)k + 2];
+  lo[0] = __fsub_rn(min3(a.x, b.x, c.x), pad); lo[1] = __fsub_rn(min3(a.y, b.y, c.y), pad); lo[2] = __fsub_rn(min3(a.z, b.z, c.z), pad);
+  hi[0] = __fadd_rn(max3(a.x, b.x, c.x), pad); hi[1] = __fadd_rn(max3(a.y, b.y, c.y), pad); hi[2] = __fadd_rn(max3(a.z, b.z, c.z), pad);
+}
+
+// bottom-up box fit: the second thread to reach a node unions its two children
+__global__ void fit_kernel(const float4* __restrict__ tris, int n, const float* __restrict__ scene,
+                           const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ parent,
+                           const int* __restrict__ leaf_parent, int* __restrict__ flags, float4* __restrict__ ibox) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float pad = scene[6];
+  int cur = leaf_parent[k];
+  while (cur >= 0) {
+    __threadfence();
+    if (atomicAdd(flags + cur, 1) == 0) return;
+    __threadfence();
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int refs[2] = {left[cur], right[cur]};
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      float cl[3], ch[3];
+      if (refs[c] < 0) tri_box(tris, ~refs[c], pad, cl, ch);
+      else {
+        float4 a = __ldcg(ibox + 2 * (int64_t)refs[c]), b = __ldcg(ibox + 2 * (int64_t)refs[c] + 1);
+        cl[0] = a.x; cl[1] = a.y; cl[2] = a.z; ch[0] = b.x; ch[1] = b.y; ch[2] = b.z;
+      }
+#pragma unroll
+      for (int q = 0; q < 3; ++q) { lo[q] = fminf(lo[q], cl[q]); hi[q] = fmaxf(hi[q], ch[q]); }
+    }
+    ibox[2 * (int64_t)cur] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    ibox[2 * (int64_t)cur + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    cur = parent[cur];
+  }
+}
+
+// final 64-byte traversal nodes; subtrees of <= kLeafMax triangles collapse into one leaf reference
+__global__ void emit_nodes_kernel(const float4* __restrict__ tris, int n, const float* __restrict__ scene,
+                                  const int* __restrict__ left, const int* __restrict__ right,
+                                  const int* __restrict__ first, const int* __restrict__ last,
+                                  const float4* __restrict__ ibox, float4* __restrict__ nodes) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  float pad = scene[6];
+  int refs[2] = {left[i], right[i]};
+  float lo[2][3], hi[2][3];
+  int out[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    int r = refs[c];
+    if (r < 0) {
+      tri_box(tris, ~r, pad, lo[c], hi[c]);
+      out[c] = make_leaf_ref(~r, 1);
+    } else {
+      float4 a = ibox[2 * (int64_t)r], b = ibox[2 * (int64_t)r + 1];
+      lo[c][0] = a.x; lo[c][1] = a.y; lo[c][2] = a.z; hi[c][0] = b.x; hi[c][1] = b.y; hi[c][2] = b.z;
+      int cnt = last[r] - first[r] + 1;
+      out[c] = cnt <= kLeafMax ? make_leaf_ref(first[r], cnt) : r;
+    }
+  }
+  nodes[4 * (int64_t)i + 0] = make_float4(lo[0][0], lo[0][1], lo[0][2], hi[0][0]);
+  nodes[4 * (int64_t)i + 1] = make_float4(hi[0][1], hi[0][2], lo[1][0], lo[1][1]);
+  nodes[4 * (int64_t)i + 2] = make_float4(lo[1][2], hi[1][0], hi[1][1], hi[1][2]);
+  nodes[4 * (int64_t)i + 3] = make_float4(__int_as_float(out[0]), __int_as_float(out[1]), 0.f, 0.f);
+}
+
+// meshes of 1..kLeafMax triangles: one root whose first child is the only leaf
+__global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, int n, const float* __restrict__ scene,
+                                      float4* __restrict__ nodes) {
+  float pad = scene[6];
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < n; ++k) {
+    float cl[3], ch[3];
+    tri_box(tris, k, pad, cl, ch);
+    for (int q = 0; q < 3; ++q) { lo[q] = fminf(lo[q], cl[q]); hi[q] = fmaxf(hi[q], ch[q]); }
+  }
+  nodes[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+  nodes[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+  nodes[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  nodes[3] = make_float4(__int_as_float(make_leaf_ref(0, n)), __int_as_float(kEmptyRef), 0.f, 0.f);
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                    const float* __restrict__ scene, const float* __restrict__ origins,
+                                                    const float* __restrict__ dirs, int64_t N, int K,
+                                                    int32_t* __restrict__ out_tri, float* __restrict__ out_t,
+                                                    int32_t* __restrict__ out_count, int32_t* __restrict__ out_total) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  Ray r = make_ray(origins, dirs, i);
+  HitBuf<KMAX> hb;
+  int total;
+  traverse<KMAX>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) {
+    if (s < K) {
+      out_tri[i * K + s] = hb.id[s];
+      if (out_t) out_t[i * K + s] = hb.t[s];
+    }
+  }
+  out_count[i] = hb.cnt;
+  if (out_total) out_total[i] = total;
+}
+
+// Note on the swap above: when both children are hit and child 1 is nearer, r0/r1 are swapped but
+// h0/h1 are both true, so the flags stay valid.
+
+// ---------------------------------------------------------------- tuple packing (a3)
+// thread per ray: plane-hit points, normalised dirs, depth, stable insertion sort by depth, ray-major write
+__global__ void hits_pack_kernel(const float4* __restrict__ planes, const float* __restrict__ origins,
+                                 const float* __restrict__ dirs, int64_t N, int K, const int32_t* __restrict__ tri,
+                                 const int32_t* __restrict__ count, const int64_t* __restrict__ offsets,
+                                 float* __restrict__ points, float* __restrict__ vectors, int64_t* __restrict__ index_ray,
+                                 float* __restrict__ depth, int64_t* __restrict__ index_tri, float* __restrict__ origins_out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int c = count[i];
+  if (c == 0) return;
+  Ray r = make_ray(origins, dirs, i);
+  float nrm = __fadd_rn(norm3(r.dx, r.dy, r.dz), 1e-7f);
+  float vx = __fdiv_rn(r.dx, nrm), vy = __fdiv_rn(r.dy, nrm), vz = __fdiv_rn(r.dz, nrm);
+  float px[QF_MAX_HITS], py[QF_MAX_HITS], pz[QF_MAX_HITS], dp[QF_MAX_HITS];
+  int id[QF_MAX_HITS];
+  for (int s = 0; s < c; ++s) {
+    int t = tri[i * K + s];
+    float x, y, z;
+    plane_hit(r, __ldg(planes + t), x, y, z);
+    float d = norm3(__fsub_rn(x, r.ox), __fsub_rn(y, r.oy), __fsub_rn(z, r.oz));
+    int q = s;  // stable insertion by depth
+    while (q > 0 && dp[q - 1] > d) { px[q] = px[q - 1]; py[q] = py[q - 1]; pz[q] = pz[q - 1]; dp[q] = dp[q - 1]; id[q] = id[q - 1]; --q; }
+    px[q] = x; py[q] = y; pz[q] = z; dp[q] = d; id[q] = t;
+  }
+  int64_t base = offsets[i];
+  for (int s = 0; s < c; ++s) {
+    int64_t o = base + s;
+    points[3 * o] = px[s]; points[3 * o + 1] = py[s]; points[3 * o + 2] = pz[s];
+    vectors[3 * o] = vx; vectors[3 * o + 1] = vy; vectors[3 * o + 2] = vz;
+    origins_out[3 * o] = r.ox; origins_out[3 * o + 1] = r.oy; origins_out[3 * o + 2] = r.oz;
+    index_ray[o] = i; depth[o] = dp[s]; index_tri[o] = id[s];
+  }
+}
+
+// a4: per-segment stable re-sort by depth of a ray-major tuple; thread per hit finds its rank inside
+// its segment (segments are <= K long, so the O(len) scan is a handful of L1 hits).
+__global__ void hits_resort_kernel(const int64_t* __restrict__ index_ray, const float* __restrict__ depth, int64_t M,
+                                   int64_t* __restrict__ perm, uint8_t* __restrict__ boundary) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  int64_t ray = index_ray[i];
+  float d = depth[i];
+  int64_t s = i, rank = 0;
+  while (s > 0 && index_ray[s - 1] == ray) { --s; if (depth[s] <= d) ++rank; }   // earlier equal keys stay first
+  int64_t e = i + 1;
+  while (e < M && index_ray[e] == ray) { if (depth[e] < d) ++rank; ++e; }
+  perm[s + rank] = i;
+  boundary[i] = (i == s) ? 1 : 0;
+}
+
+__global__ void widen_count_kernel(const int32_t* __restrict__ c, int64_t n, int64_t* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = c[i];
+  if (i == n) out[n] = 0;
+}
+
+static int build(qf_mesh* m, cudaStream_t st) {
+  const int64_t F = m->n_faces, V = m->n_vertices;
+  int* ob = m->d_flags;  // 6 ints of scratch before flags are needed
+  bounds_init_kernel<<<1, 32, 0, st>>>(ob);
+  bounds_kernel<<<kNumSMs * 2, 256, 0, st>>>(m->d_vertices, V, ob);
+  bounds_finish_kernel<<<1, 1, 0, st>>>(ob, m->d_scene);
+  QF_LAUNCH_CHECK();
+  int blocks = (int)ceil_div(F, 256);
+  tri_setup_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->d_faces, F, m->d_scene, m->d_keys, m->d_idx, m->d_planes);
+  QF_LAUNCH_CHECK();
+  size_t tmp = m->sort_tmp_bytes;
+  QF_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(m->d_sort_tmp, tmp, m->d_keys, m->d_keys_sorted, m->d_idx,
+                                                m->d_idx_sorted, (int)F, 0, 63, st));
+  tri_gather_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->d_faces, F, m->d_idx_sorted, m->d_tris);
+  QF_LAUNCH_CHECK();
+  if (F <= kLeafMax) {
+    emit_tiny_root_kernel<<<1, 1, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_nodes);
+    QF_LAUNCH_CHECK();
+    m->n_nodes = 1;
+  } else {
+    QF_CUDA_CHECK(cudaMemsetAsync(m->d_flags, 0, sizeof(int) * F, st));
+    karras_kernel<<<blocks, 256, 0, st>>>(m->d_keys_sorted, (int)F, m->d_left, m->d_right, m->d_parent,
+                                          m->d_leaf_parent, m->d_first, m->d_last);
+    fit_kernel<<<blocks, 256, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_parent,
+                                       m->d_leaf_parent, m->d_flags, m->d_ibox);
+    emit_nodes_kernel<<<blocks, 256, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_first,
+                                              m->d_last, m->d_ibox, m->d_nodes);
+    QF_LAUNCH_CHECK();
+    m->n_nodes = F - 1;
+  }
+  return QF_OK;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t count, size_t* total) {
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  QF_CUDA_CHECK(cudaMalloc((void**)p, bytes));
+  *total += bytes;
+  return QF_OK;
+}
+
+}  // namespace qf
+
+using namespace qf;
+
+extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const int32_t* d_faces, int64_t n_faces,
+                              void* stream, qf_mesh** out) {
+  QF_REQUIRE(out != nullptr, "qf_mesh_create: out is NULL");
+  QF_REQUIRE(d_vertices && d_faces && n_vertices > 0 && n_faces > 0, "qf_mesh_create: empty mesh (V=%lld F=%lld)",
+             (long long)n_vertices, (long long)n_faces);
+  QF_REQUIRE(n_faces < (1ll << 28), "qf_mesh_create: at most 2^28 faces");
+  cudaStream_t st = (cudaStream_t)stream;
+  qf_mesh* m = new qf_mesh();
+  m->n_vertices = n_vertices;
+  m->n_faces = n_faces;
+  const size_t F = (size_t)n_faces;
+  int rc = QF_OK;
+#define QF_A(call) if (rc == QF_OK) rc = (call)
+  QF_A(dev_alloc(&m->d_vertices, 3 * (size_t)n_vertices, &m->bytes));
+  QF_A(dev_alloc(&m->d_faces, 3 * F, &m->bytes));
+  QF_A(dev_alloc(&m->d_tris, 3 * F, &m->bytes));
+  QF_A(dev_alloc(&m->d_planes, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_nodes, 4 * F, &m->bytes));
+  QF_A(dev_alloc(&m->d_scene, 8, &m->bytes));
+  QF_A(dev_alloc(&m->d_keys, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_keys_sorted, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_idx, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_idx_sorted, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_left, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_right, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_parent, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_leaf_parent, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_first, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_last, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_flags, F + 8, &m->bytes));
+  QF_A(dev_alloc(&m->d_ibox, 2 * F, &m->bytes));
+#undef QF_A
+  if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_keys, m->d_keys_sorted, m->d_idx, m->d_idx_sorted, (int)F, 0, 63, st);
+  m->sort_tmp_bytes = tmp;
+  if (cudaMalloc(&m->d_sort_tmp, tmp ? tmp : 16) != cudaSuccess) { set_error("qf_mesh_create: sort scratch alloc failed"); qf_mesh_destroy(m); return QF_ERR_CUDA; }
+  m->bytes += tmp;
+  cudaError_t e = cudaMemcpyAsync(m->d_faces, d_faces, sizeof(int32_t) * 3 * F, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) { set_error("qf_mesh_create: copy failed: %s", cudaGetErrorString(e)); qf_mesh_destroy(m); return QF_ERR_CUDA; }
+  rc = build(m, st);
+  if (rc == QF_OK) {
+    e = cudaMemcpyAsync(&m->h_pad, m->d_scene + 6, sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { set_error("qf_mesh_create: build failed: %s", cudaGetErrorString(e)); rc = QF_ERR_CUDA; }
+  }
+  if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
+  *out = m;
+  return QF_OK;
+}
+
+extern "C" int qf_mesh_update_vertices(qf_mesh* m, const float* d_vertices, void* stream) {
+  QF_REQUIRE(m && d_vertices, "qf_mesh_update_vertices: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  QF_CUDA_CHECK(cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * m->n_vertices, cudaMemcpyDeviceToDevice, st));
+  int rc = build(m, st);
+  if (rc != QF_OK) return rc;
+  QF_CUDA_CHECK(cudaMemcpyAsync(&m->h_pad, m->d_scene + 6, sizeof(float), cudaMemcpyDeviceToHost, st));
+  return QF_OK;
+}
+
+extern "C" void qf_mesh_destroy(qf_mesh* m) {
+  if (!m) return;
+  void* ptrs[] = {m->d_vertices, m->d_faces, m->d_tris, m->d_planes, m->d_nodes, m->d_scene, m->d_keys, m->d_keys_sorted,
+                  m->d_idx, m->d_idx_sorted, m->d_left, m->d_right, m->d_parent, m->d_leaf_parent, m->d_first, m->d_last,
+                  m->d_flags, m->d_ibox, m->d_sort_tmp};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete m;
+}
+
+extern "C" int qf_mesh_info(const qf_mesh* m, int64_t* info4, float* box_pad) {
+  QF_REQUIRE(m, "qf_mesh_info: NULL mesh");
+  if (info4) { info4[0] = m->n_faces; info4[1] = m->n_vertices; info4[2] = m->n_nodes; info4[3] = (int64_t)m->bytes; }
+  if (box_pad) *box_pad = m->h_pad;
+  return QF_OK;
+}
+
+extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
+                               int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* stream) {
+  QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count, "qf_trace_firstk: NULL argument");
+  QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_trace_firstk: K=%d outside [1,%d]", K, QF_MAX_HITS);
+  if (n_rays == 0) return QF_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int blocks = (int)ceil_div(n_rays, 128);
+  if (K <= 8) trace_kernel<8><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
+  else if (K <= 16) trace_kernel<16><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
+  else trace_kernel<32><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" size_t qf_scan_workspace_bytes(int64_t n) {
+  size_t tmp = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, (int64_t*)nullptr, (int64_t*)nullptr, n + 1);
+  return tmp + sizeof(int64_t) * (size_t)(n + 1) + 256;
+}
+
+extern "C" int qf_hits_offsets(const int32_t* d_count, int64_t n_rays, int64_t* d_offsets, void* d_workspace,
+                               size_t workspace_bytes, void* stream) {
+  QF_REQUIRE(d_count && d_offsets && d_workspace, "qf_hits_offsets: NULL argument");
+  QF_REQUIRE(workspace_bytes >= qf_scan_workspace_bytes(n_rays), "qf_hits_offsets: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t* wide = (int64_t*)d_workspace;
+  size_t wide_bytes = (sizeof(int64_t) * (size_t)(n_rays + 1) + 255) / 256 * 256;
+  void* tmp = (char*)d_workspace + wide_bytes;
+  size_t tmp_bytes = workspace_bytes - wide_bytes;
+  widen_count_kernel<<<(int)ceil_div(n_rays + 1, 256), 256, 0, st>>>(d_count, n_rays, wide);
+  QF_LAUNCH_CHECK();
+  QF_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, wide, d_offsets, n_rays + 1, st));
+  return QF_OK;
+}
+
+extern "C" int qf_hits_total(const int64_t* d_offsets, int64_t n_rays, int64_t* h_total, void* stream) {
+  QF_REQUIRE(d_offsets && h_total, "qf_hits_total: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  QF_CUDA_CHECK(cudaMemcpyAsync(h_total, d_offsets + n_rays, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  QF_CUDA_CHECK(cudaStreamSynchronize(st));
+  return QF_OK;
+}
+
+extern "C" int qf_hits_pack(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
+                            const int32_t* d_tri, const int32_t* d_count, const int64_t* d_offsets, float* d_points,
+                            float* d_vectors, int64_t* d_index_ray, float* d_depth, int64_t* d_index_tri,
+                            float* d_origins_out, void* stream) {
+  QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count && d_offsets, "qf_hits_pack: NULL input");
+  QF_REQUIRE(d_points && d_vectors && d_index_ray && d_depth && d_index_tri && d_origins_out, "qf_hits_pack: NULL output");
+  QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_hits_pack: K=%d outside [1,%d]", K, QF_MAX_HITS);
+  if (n_rays == 0) return QF_OK;
+  hits_pack_kernel<<<(int)ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
+      m->d_planes, d_origins, d_dirs, n_rays, K, d_tri, d_count, d_offsets, d_points, d_vectors, d_index_ray, d_depth,
+      d_index_tri, d_origins_out);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_hits_resort(const int64_t* d_index_ray, const float* d_depth, int64_t n_hits, int64_t* d_perm,
+                              uint8_t* d_boundary, void* stream) {
+  QF_REQUIRE(d_index_ray && d_depth && d_perm && d_boundary, "qf_hits_resort: NULL argument");
+  if (n_hits == 0) return QF_OK;
+  hits_resort_kernel<<<(int)ceil_div(n_hits, 256), 256, 0, (cudaStream_t)stream>>>(d_index_ray, d_depth, n_hits, d_perm, d_boundary);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}

@@ -1,0 +1,72 @@
+// Shared host/device helpers for libquadfield.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "quadfield.h"
+
+namespace qf {
+
+void set_error(const char* fmt, ...);
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace qf
+
+#define QF_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess) {                                                                     \
+      qf::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));        \
+      return QF_ERR_CUDA;                                                                        \
+    }                                                                                            \
+  } while (0)
+
+#define QF_REQUIRE(cond, ...)                                                                    \
+  do {                                                                                           \
+    if (!(cond)) {                                                                               \
+      qf::set_error(__VA_ARGS__);                                                                \
+      return QF_ERR_INVALID;                                                                     \
+    }                                                                                            \
+  } while (0)
+
+#define QF_LAUNCH_CHECK() QF_CUDA_CHECK(cudaGetLastError())
+
+// ---- opaque handle layouts (shared between translation units) --------------------------------
+
+struct qf_mesh {
+  int64_t n_vertices = 0, n_faces = 0, n_nodes = 0;
+  float* d_vertices = nullptr;    // (V,3) copy
+  int32_t* d_faces = nullptr;     // (F,3) copy
+  float4* d_tris = nullptr;       // Morton-sorted: 3 x float4 per triangle: (v0,id) (v1,0) (v2,0)
+  float4* d_planes = nullptr;     // per ORIGINAL triangle id: (n.xyz from fp64, d=-(n.v0))
+  float4* d_nodes = nullptr;      // 4 x float4 per node: both children's boxes + refs
+  float* d_scene = nullptr;       // [0..2] lo, [3..5] hi, [6] pad
+  // build scratch (kept so update_vertices does not allocate)
+  uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
+  uint32_t *d_idx = nullptr, *d_idx_sorted = nullptr;
+  int32_t *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr, *d_leaf_parent = nullptr;
+  int32_t *d_first = nullptr, *d_last = nullptr, *d_flags = nullptr;
+  float4* d_ibox = nullptr;       // 2 x float4 per internal node (lo, hi)
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  size_t bytes = 0;
+  float h_pad = 0.f;
+};
+
+struct qf_ngp {
+  qf_grid_desc desc;
+  int64_t n_entries = 0;
+  __half2* d_table = nullptr;     // fp16 working copy, 2 features per entry
+  __half* d_weights = nullptr;    // fp16 working copy of all five matrices, smem-ready layout
+};
+
+struct qf_texture {
+  int size = 0, num_lobes = 0, colour_logit = 0, record_bytes = 0;
+  float lambda_thres = 7.5f;
+  uint8_t* d_records = nullptr;   // interleaved texel records (see baked.cu)
+};

@@ -1,0 +1,436 @@
+// (2)+(3) Instant-NGP field: multiresolution hash-grid gather fused with the 64-wide density and
+// colour MLPs on tensor cores.  Replaces tinycudann HashGrid / FullyFusedMLP / SphericalHarmonics
+// behind NGPRadianceField (radiance_fields/ngp.py:657-809).
+//
+// One lane encodes one hit sample (16 levels x 8 corner gathers of one half2 = 512 B algorithmic,
+// served from L2: the 25 MB fp16 table of T=2^19 is L2-resident on B200).  A warp then owns 32
+// samples = two m16 row tiles; the five weight matrices (24 KB fp16, padded so B-fragment loads are
+// bank-conflict free) are staged once per CTA in shared memory, and the layers are chained in
+// registers: the fp32 accumulator fragment of layer n is re-packed as the fp16 A fragment of layer
+// n+1 (mma.sync m16n8k16, fp32 accumulate), so activations never touch shared or global memory.
+// The density logit uses a hi+lo fp16 split of the hidden activations, which keeps sigma within
+// ~1e-6 of the fp32 oracle.
+#include "common.cuh"
+
+namespace qf {
+
+// ---- shared-memory weight image (halves); strides padded for conflict-free fragment loads
+constexpr int kS32 = 40;   // row stride of a (out x 32) matrix
+constexpr int kS64 = 72;   // row stride of a (out x 64) matrix
+constexpr int kW1 = 0;                    // base  L1  64 x 32
+constexpr int kW2 = kW1 + 64 * kS32;      // base  L2  16 x 64
+constexpr int kW3 = kW2 + 16 * kS64;      // head  L1  64 x 32 (columns permuted, see prep)
+constexpr int kW4 = kW3 + 64 * kS32;      // head  L2  64 x 64
+constexpr int kW5 = kW4 + 64 * kS64;      // head  L3  16 x 64
+constexpr int kWTotal = kW5 + 16 * kS64;  // 12032 halves = 24064 B
+constexpr int kTileStride = 56;           // per-sample staging row: 32 enc + 16 SH + 8 pad (halves)
+
+// tcnn layout (row-major (out,in), fp32) -> padded fp16 image.  Head L1 input order in tcnn is
+// [SH(16) | feat(15) | pad(1)]; the kernel feeds [SH(16) | pad | feat(15)] so that the base MLP's
+// output fragment (sigma_raw, feat0..14) can be reused in place with sigma_raw replaced by the pad value.
+__global__ void prep_weights_kernel(const float* __restrict__ base_w, const float* __restrict__ head_w,
+                                    __half* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kWTotal) return;
+  float v = 0.f;
+  if (i < kW2) { int r = i / kS32, c = i % kS32; if (c < 32) v = base_w[r * 32 + c]; }
+  else if (i < kW3) { int j = i - kW2, r = j / kS64, c = j % kS64; if (c < 64) v = base_w[64 * 32 + r * 64 + c]; }
+  else if (i < kW4) {
+    int j = i - kW3, r = j / kS32, c = j % kS32;
+    if (c < 16) v = head_w[r * 32 + c];
+    else if (c == 16) v = head_w[r * 32 + 31];
+    else if (c < 32) v = head_w[r * 32 + c - 1];
+  }
+  else if (i < kW5) { int j = i - kW4, r = j / kS64, c = j % kS64; if (c < 64) v = head_w[64 * 32 + r * 64 + c]; }
+  else { int j = i - kW5, r = j / kS64, c = j % kS64; if (c < 64) v = head_w[64 * 32 + 64 * 64 + r * 64 + c]; }
+  out[i] = __float2half_rn(v);
+}
+
+__global__ void prep_table_kernel(const float* __restrict__ t, int64_t n_entries, __half2* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __floats2half2_rn(t[2 * i], t[2 * i + 1]);
+}
+
+// ---- hash-grid encode of one point: 16 levels, trilinear, fp32 interpolation, fp16 result
+struct Enc { uint32_t h[QF_MAX_LEVELS]; };  // packed half2 per level
+
+__device__ __forceinline__ Enc encode_point(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
+                                            float z) {
+  Enc e;
+#pragma unroll
+  for (int l = 0; l < QF_MAX_LEVELS; ++l) {
+    if (l >= d.n_levels) { e.h[l] = 0u; continue; }
+    const float scale = d.scale[l];
+    const uint32_t res = d.resolution[l], size = d.size[l];
+    const bool hashed = d.hashed[l] != 0;
+    const bool pow2 = (size & (size - 1)) == 0;
+    float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    uint32_t cx = (uint32_t)(int)fx, cy = (uint32_t)(int)fy, cz = (uint32_t)(int)fz;
+    px -= fx; py -= fy; pz -= fz;
+    const __half2* lvl = table + d.offset[l];
+    __half2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      uint32_t gx = cx + (c & 1), gy = cy + ((c >> 1) & 1), gz = cz + ((c >> 2) & 1);
+      uint32_t idx = hashed ? (gx ^ (gy * 2654435761u) ^ (gz * 805459861u)) : (gx + gy * res + gz * (res * res));
+      idx = pow2 ? (idx & (size - 1)) : (idx >= size ? idx % size : idx);
+      v[c] = __ldg(lvl + idx);
+    }
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float w = ((c & 1) ? px : 1.f - px) * ((c & 2) ? py : 1.f - py);
+      w *= (c & 4) ? pz : 1.f - pz;
+      float2 f = __half22float2(v[c]);
+      r0 = __fadd_rn(r0, __fmul_rn(w, f.x));   // separately rounded like the oracle: the encoding is bit-exact
+      r1 = __fadd_rn(r1, __fmul_rn(w, f.y));
+    }
+    __half2 hv = __floats2half2_rn(r0, r1);
+    e.h[l] = *reinterpret_cast<uint32_t*>(&hv);
+  }
+  return e;
+}
+// The weight of corner c is ((wx*wy)*wz) in the oracle's order: w starts at 1 and is multiplied by the
+// x, y, z factors in turn; (1*wx)*wy*wz == (wx*wy)*wz exactly.
+
+__device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
+  float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// ---- tensor-core helpers (legacy HMMA path; the tcgen05 variant lives in field_tc.cu)
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// D[16 x 8*NT] += A[16 x 16*KT] * W^T, W row-major (n, k) in shared memory with row stride `stride`
+template <int KT, int NT>
+__device__ __forceinline__ void layer(float (*acc)[4], const uint32_t (*a)[4], const __half* __restrict__ w, int stride,
+                                      int g, int t) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const __half* wr = w + (n * 8 + g) * stride + t * 2;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) mma16816(acc[n], a[k], lds32(wr + k * 16), lds32(wr + k * 16 + 8));
+  }
+}
+
+struct FieldArgs {
+  qf_grid_desc desc;
+  const __half2* table;
+  const __half* weights;
+  const float* pos;          // sample positions, `pos_stride` floats apart
+  int pos_stride;
+  const float* dirs;         // directions: per sample, or per ray when a ray index is given
+  const int64_t* ray64;      // optional int64 ray index per sample
+  const int32_t* ray32;      // optional int32 ray index per sample, `ray32_stride` ints apart
+  int ray32_stride;
+  int64_t M;                 // number of samples (used when d_M == NULL)
+  const int32_t* d_M;        // optional device-side count
+  float4* out4;              // (rgb, sigma) per sample            [mode 0, fused path]
+  float* rgb;                // (M,3)                               [mode 0]
+  float* density;            // (M,1)                               [mode 0/1]
+  float* feat;               // (M,15)                              [mode 1]
+};
+
+template <int MODE>  // 0: full forward (rgb + sigma); 1: density + geo features only
+__global__ void __launch_bounds__(128, 3) ngp_forward_kernel(const FieldArgs a) {
+  __shared__ __align__(16) __half s_w[kWTotal];
+  __shared__ __align__(16) __half s_tile[4][32 * kTileStride];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.weights);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    constexpr int n16 = (MODE == 0 ? kWTotal : kW3) / 8;
+    for (int i = tid; i < n16; i += 128) dst[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int64_t M = a.d_M ? (int64_t)__ldg(a.d_M) : a.M;
+  __half* tile = s_tile[warp];
+  const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
+  const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
+
+  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < M; base += (int64_t)gridDim.x * 128) {
+    const int64_t i = base + lane;
+    const bool valid = i < M;
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    bool sel = false;
+    if (valid) {
+      const float* p = a.pos + i * a.pos_stride;
+      x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);       // ngp.py:761-763
+      y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
+      z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
+      sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
+    }
+    Enc e = encode_point(a.desc, a.table, x, y, z);
+    uint4* row = reinterpret_cast<uint4*>(tile + lane * kTileStride);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) row[q] = make_uint4(e.h[4 * q], e.h[4 * q + 1], e.h[4 * q + 2], e.h[4 * q + 3]);
+    if (MODE == 0) {
+      float dx = 0.f, dy = 0.f, dz = 1.f;
+      if (valid) {
+        int64_t r = a.ray64 ? __ldg(a.ray64 + i) : (a.ray32 ? (int64_t)__ldg(a.ray32 + i * a.ray32_stride) : i);
+        const float* dp = a.dirs + 3 * r;
+        // (d+1)/2 then tcnn maps back with *2-1 (ngp.py:784; tcnn SH kernel)
+        dx = ((__ldg(dp) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+        dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+        dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+      }
+      float sh[16];
+      sh4(dx, dy, dz, sh);
+      row[4] = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sh[3]), pack_h2(sh[4], sh[5]), pack_h2(sh[6], sh[7]));
+      row[5] = make_uint4(pack_h2(sh[8], sh[9]), pack_h2(sh[10], sh[11]), pack_h2(sh[12], sh[13]), pack_h2(sh[14], sh[15]));
+    }
+    const unsigned selmask = __ballot_sync(0xffffffffu, sel);
+    __syncwarp();
+
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      if (base + mt * 16 >= M) break;
+      const __half* ta = tile + (mt * 16 + g) * kTileStride + t * 2;
+      const __half* tb = ta + 8 * kTileStride;
+      // ---- base layer 1: 32 -> 64, ReLU
+      uint32_t a1[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        a1[k][0] = lds32(ta + k * 16); a1[k][1] = lds32(tb + k * 16);
+        a1[k][2] = lds32(ta + k * 16 + 8); a1[k][3] = lds32(tb + k * 16 + 8);
+      }
+      float acc[8][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<2, 8>(acc, a1, s_w + kW1, kS32, g, t);
+      // ---- base layer 2: 64 -> 16 with hi+lo split of the hidden activations
+      uint32_t ahi[4][4], alo[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* c = acc[2 * k + h];
+          float r0 = fmaxf(c[0], 0.f), r1 = fmaxf(c[1], 0.f), r2 = fmaxf(c[2], 0.f), r3 = fmaxf(c[3], 0.f);
+          __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+          float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          ahi[k][2 * h] = *reinterpret_cast<uint32_t*>(&h01);
+          ahi[k][2 * h + 1] = *reinterpret_cast<uint32_t*>(&h23);
+          alo[k][2 * h] = pack_h2(r0 - f01.x, r1 - f01.y);
+          alo[k][2 * h + 1] = pack_h2(r2 - f23.x, r3 - f23.y);
+        }
+      }
+      float acc2[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
+      layer<4, 2>(acc2, alo, s_w + kW2, kS64, g, t);
+      layer<4, 2>(acc2, ahi, s_w + kW2, kS64, g, t);
+      // sigma = trunc_exp(h0 - 1) * selector   (ngp.py:772-775; _TruncExp forward is plain exp)
+      const int64_t r_lo = base + mt * 16 + g, r_hi = r_lo + 8;
+      const float s_lo = ((selmask >> (mt * 16 + g)) & 1u) ? expf(acc2[0][0] - 1.0f) : 0.f;
+      const float s_hi = ((selmask >> (mt * 16 + g + 8)) & 1u) ? expf(acc2[0][2] - 1.0f) : 0.f;
+      if (MODE == 1) {
+        if (t == 0) {
+          if (r_lo < M) a.density[r_lo] = s_lo;
+          if (r_hi < M) a.density[r_hi] = s_hi;
+        }
+        if (a.feat) {
+#pragma unroll
+          for (int n = 0; n < 2; ++n) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              int col = n * 8 + t * 2 + q - 1;  // output column 0 is the density logit
+              if (col >= 0) {
+                if (r_lo < M) a.feat[r_lo * 15 + col] = acc2[n][q];
+                if (r_hi < M) a.feat[r_hi * 15 + col] = acc2[n][2 + q];
+              }
+            }
+          }
+        }
+        continue;
+      }
+      // ---- head layer 1: [SH(16) | pad, feat(15)] -> 64, ReLU
+      uint32_t a3[2][4];
+      a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
+      a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
+      a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
+      a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
+      a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
+      // ---- head layer 2: 64 -> 64, ReLU
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* c = acc[2 * k + h];
+          ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+          ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+        }
+      }
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<4, 8>(acc, ahi, s_w + kW4, kS64, g, t);
+      // ---- head layer 3: 64 -> 3 (first n-tile only), sigmoid
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float* c = acc[2 * k + h];
+          ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+          ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+        }
+      }
+      float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+      layer<4, 1>(acc5, ahi, s_w + kW5, kS64, g, t);
+      const float b_lo = __shfl_down_sync(0xffffffffu, acc5[0][0], 1);
+      const float b_hi = __shfl_down_sync(0xffffffffu, acc5[0][2], 1);
+      if (t == 0) {
+        auto sig = [](float v) { return 1.0f / (1.0f + __expf(-v)); };
+        float4 o_lo = make_float4(sig(acc5[0][0]), sig(acc5[0][1]), sig(b_lo), s_lo);
+        float4 o_hi = make_float4(sig(acc5[0][2]), sig(acc5[0][3]), sig(b_hi), s_hi);
+        if (a.out4) {
+          if (r_lo < M) a.out4[r_lo] = o_lo;
+          if (r_hi < M) a.out4[r_hi] = o_hi;
+        } else {
+          if (r_lo < M) { a.rgb[3 * r_lo] = o_lo.x; a.rgb[3 * r_lo + 1] = o_lo.y; a.rgb[3 * r_lo + 2] = o_lo.z; a.density[r_lo] = o_lo.w; }
+          if (r_hi < M) { a.rgb[3 * r_hi] = o_hi.x; a.rgb[3 * r_hi + 1] = o_hi.y; a.rgb[3 * r_hi + 2] = o_hi.z; a.density[r_hi] = o_hi.w; }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void hashgrid_forward_kernel(const qf_grid_desc desc, const __half2* __restrict__ table,
+                                        const float* __restrict__ x01, int64_t M, float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  Enc e = encode_point(desc, table, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2]);
+  const int L = desc.n_levels;
+  for (int l = 0; l < L; ++l) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&e.h[l]));
+    out[i * 2 * L + 2 * l] = f.x;
+    out[i * 2 * L + 2 * l + 1] = f.y;
+  }
+}
+
+int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {
+  a.desc = f->desc;
+  a.table = f->d_table;
+  a.weights = f->d_weights;
+  int64_t tiles = a.d_M ? (int64_t)kNumSMs * 3 * 4 : ceil_div(a.M, 128);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 * 4 ? tiles : (int64_t)kNumSMs * 3 * 4);
+  if (blocks < 1) blocks = 1;
+  if (mode == 0) ngp_forward_kernel<0><<<blocks, 128, 0, st>>>(a);
+  else ngp_forward_kernel<1><<<blocks, 128, 0, st>>>(a);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+// shading entry for the fused render (render.cu): compact hit records in, (rgb, sigma) out
+int launch_ngp_forward_hits(const qf_ngp* f, const float4* hit_pd, const int2* hit_rt, const float* d_viewdirs,
+                            const int32_t* d_M, float4* out4, cudaStream_t st) {
+  FieldArgs a = {};
+  a.pos = reinterpret_cast<const float*>(hit_pd); a.pos_stride = 4;
+  a.dirs = d_viewdirs;                               // original unit viewdirs gathered by ray id (utils.py:517, quirk Q7)
+  a.ray32 = reinterpret_cast<const int32_t*>(hit_rt); a.ray32_stride = 2;
+  a.d_M = d_M; a.out4 = out4;
+  return launch_ngp_forward(f, a, 0, st);
+}
+
+static int upload(qf_ngp* f, const float* d_table, const float* d_base_w, const float* d_head_w, cudaStream_t st) {
+  if (d_table) prep_table_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_table, f->n_entries, f->d_table);
+  if (d_base_w && d_head_w) prep_weights_kernel<<<(int)ceil_div(kWTotal, 256), 256, 0, st>>>(d_base_w, d_head_w, f->d_weights);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+}  // namespace qf
+
+using namespace qf;
+
+extern "C" int qf_ngp_create(const qf_grid_desc* desc, const float* d_table, int64_t n_entries, const float* d_base_w,
+                             const float* d_head_w, void* stream, qf_ngp** out) {
+  QF_REQUIRE(desc && d_table && d_base_w && d_head_w && out, "qf_ngp_create: NULL argument");
+  QF_REQUIRE(desc->n_levels == 16, "qf_ngp_create: n_levels=%d; the fused MLP takes the 32-wide encoding (16 levels x 2)",
+             desc->n_levels);
+  int64_t need = (int64_t)desc->offset[desc->n_levels - 1] + desc->size[desc->n_levels - 1];
+  QF_REQUIRE(n_entries >= need, "qf_ngp_create: table has %lld entries, level table needs %lld", (long long)n_entries,
+             (long long)need);
+  qf_ngp* f = new qf_ngp();
+  f->desc = *desc;
+  f->n_entries = n_entries;
+  if (cudaMalloc((void**)&f->d_table, sizeof(__half2) * (size_t)n_entries) != cudaSuccess ||
+      cudaMalloc((void**)&f->d_weights, sizeof(__half) * kWTotal) != cudaSuccess) {
+    set_error("qf_ngp_create: device allocation failed");
+    qf_ngp_destroy(f);
+    return QF_ERR_CUDA;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = upload(f, d_table, d_base_w, d_head_w, st);
+  if (rc == QF_OK && cudaStreamSynchronize(st) != cudaSuccess) { set_error("qf_ngp_create: upload failed"); rc = QF_ERR_CUDA; }
+  if (rc != QF_OK) { qf_ngp_destroy(f); return rc; }
+  *out = f;
+  return QF_OK;
+}
+
+extern "C" int qf_ngp_update(qf_ngp* f, const float* d_table, const float* d_base_w, const float* d_head_w, void* stream) {
+  QF_REQUIRE(f, "qf_ngp_update: NULL field");
+  return upload(f, d_table, d_base_w, d_head_w, (cudaStream_t)stream);
+}
+
+extern "C" void qf_ngp_destroy(qf_ngp* f) {
+  if (!f) return;
+  if (f->d_table) cudaFree(f->d_table);
+  if (f->d_weights) cudaFree(f->d_weights);
+  delete f;
+}
+
+extern "C" int qf_hashgrid_forward(const qf_ngp* f, const float* d_x01, int64_t M, float* d_enc, void* stream) {
+  QF_REQUIRE(f && d_x01 && d_enc, "qf_hashgrid_forward: NULL argument");
+  if (M == 0) return QF_OK;
+  hashgrid_forward_kernel<<<(int)ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(f->desc, f->d_table, d_x01, M, d_enc);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_ngp_query_density(const qf_ngp* f, const float* d_positions, int64_t M, float* d_density, float* d_feat,
+                                    void* stream) {
+  QF_REQUIRE(f && d_positions && d_density, "qf_ngp_query_density: NULL argument");
+  if (M == 0) return QF_OK;
+  FieldArgs a = {};
+  a.pos = d_positions; a.pos_stride = 3; a.M = M; a.density = d_density; a.feat = d_feat;
+  return launch_ngp_forward(f, a, 1, (cudaStream_t)stream);
+}
+
+extern "C" int qf_ngp_forward(const qf_ngp* f, const float* d_positions, const float* d_directions,
+                              const int64_t* d_ray_index, int64_t M, float* d_rgb, float* d_density, void* stream) {
+  QF_REQUIRE(f && d_positions && d_directions && d_rgb && d_density, "qf_ngp_forward: NULL argument");
+  if (M == 0) return QF_OK;
+  FieldArgs a = {};
+  a.pos = d_positions; a.pos_stride = 3; a.dirs = d_directions; a.ray64 = d_ray_index; a.M = M;
+  a.rgb = d_rgb; a.density = d_density;
+  return launch_ngp_forward(f, a, 0, (cudaStream_t)stream);
+}

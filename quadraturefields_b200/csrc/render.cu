@@ -1,0 +1,287 @@
+// Fused frame render: rays -> BVH first-K hits -> compact hit records -> field / baked shading ->
+// per-ray composite, all resident in HBM with no host synchronisation and no Python chunk loops
+// (the reference runs utils.py:465-607 / :998-1095 with a CPU intersector, a GPU->CPU lexsort and
+// 160 000-sample batches).
+//
+//   trace_compact_kernel : one thread per ray; traversal (traverse.cuh), plane-hit point + depth per hit
+//                          (mesh_utils.py:33-40,371), stable depth order (:375), then the CTA reserves a
+//                          contiguous run of the compact hit array with ONE atomicAdd, so samples of
+//                          neighbouring pixels stay adjacent for the gather-bound shading kernel.
+//   shading              : ngp_forward_kernel (field.cu) or baked_shade_kernel (baked.cu) over the M live
+//                          samples only (M is read from device memory; persistent grid of 148 x k CTAs).
+//   composite_rays_kernel: derive_properties (utils.py:863-898) per ray.
+#include <vector>
+
+#include "traverse.cuh"
+
+namespace qf {
+
+struct FieldArgs;  // field.cu
+int launch_ngp_forward_hits(const qf_ngp* f, const float4* hit_pd, const int2* hit_rt, const float* d_viewdirs,
+                            const int32_t* d_M, float4* out4, cudaStream_t st);
+int launch_baked_shade(const qf_texture* tex, const qf_mesh* mesh, const float* d_uv, const float4* hit_pd,
+                       const int2* hit_rt, const float* d_viewdirs, const int32_t* d_M, float4* out4, cudaStream_t st);
+
+struct Workspace {
+  int32_t* cursor;     // [0] live hit samples of the current chunk
+  int32_t* ray_start;  // (CH)
+  int32_t* ray_count;  // (CH)
+  float4* hit_pd;      // (CH*K) psi.xyz, depth
+  int2* hit_rt;        // (CH*K) ray id (global), triangle id
+  float4* hit_out;     // (CH*K) rgb, sigma
+};
+
+constexpr int64_t kChunkRays = 1ll << 21;
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static size_t workspace_layout(int64_t n_rays, int K, Workspace* w, char* base) {
+  int64_t ch = n_rays < kChunkRays ? n_rays : kChunkRays;
+  if (ch < 1) ch = 1;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+  size_t o_cursor = take(256), o_start = take(sizeof(int32_t) * ch), o_count = take(sizeof(int32_t) * ch);
+  size_t o_pd = take(sizeof(float4) * ch * K), o_rt = take(sizeof(int2) * ch * K), o_out = take(sizeof(float4) * ch * K);
+  if (w) {
+    w->cursor = (int32_t*)(base + o_cursor); w->ray_start = (int32_t*)(base + o_start); w->ray_count = (int32_t*)(base + o_count);
+    w->hit_pd = (float4*)(base + o_pd); w->hit_rt = (int2*)(base + o_rt); w->hit_out = (float4*)(base + o_out);
+  }
+  return off;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                            const float4* __restrict__ planes, const float* __restrict__ scene,
+                                                            const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                            int64_t ray0, int64_t n, int K, int32_t* __restrict__ cursor,
+                                                            int32_t* __restrict__ ray_start, int32_t* __restrict__ ray_count,
+                                                            float4* __restrict__ hit_pd, int2* __restrict__ hit_rt) {
+  __shared__ int s_warp[4];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t li = blockIdx.x * (int64_t)blockDim.x + tid;  // ray inside the chunk
+  const bool valid = li < n;
+  HitBuf<KMAX> hb;
+  hb.cnt = 0;
+  int total = 0;
+  Ray r;
+  if (valid) {
+    r = make_ray(origins, dirs, ray0 + li);
+    traverse<KMAX>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
+  }
+  // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
+  int c = valid ? hb.cnt : 0, inc = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (tid == 0) {
+    int t = 0;
+    for (int w = 0; w < 4; ++w) { int v = s_warp[w]; s_warp[w] = t; t += v; }
+    s_base = t ? atomicAdd(cursor, t) : 0;
+  }
+  __syncthreads();
+  if (!valid) return;
+  const int start = s_base + s_warp[warp] + inc - c;
+  ray_start[li] = start;
+  ray_count[li] = c;
+  float prev = -1.f;
+  bool unsorted = false;
+#pragma unroll
+  for (int s = 0; s < KMAX; ++s) {
+    if (s < c) {
+      float px, py, pz;
+      plane_hit(r, __ldg(planes + hb.id[s]), px, py, pz);
+      float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
+      unsorted |= d < prev;
+      prev = d;
+      hit_pd[start + s] = make_float4(px, py, pz, d);
+      hit_rt[start + s] = make_int2((int)(ray0 + li), hb.id[s]);
+    }
+  }
+  if (unsorted) {  // rare: plane-hit depth order differs from Möller–Trumbore t order; stable insertion sort
+    for (int s = 1; s < c; ++s) {
+      float4 pd = hit_pd[start + s];
+      int2 rt = hit_rt[start + s];
+      int q = s;
+      while (q > 0) {
+        float4 o = hit_pd[start + q - 1];
+        if (!(o.w > pd.w)) break;
+        hit_pd[start + q] = o;
+        hit_rt[start + q] = hit_rt[start + q - 1];
+        --q;
+      }
+      hit_pd[start + q] = pd;
+      hit_rt[start + q] = rt;
+    }
+  }
+}
+
+__global__ void composite_rays_kernel(const int32_t* __restrict__ ray_start, const int32_t* __restrict__ ray_count,
+                                      const float4* __restrict__ hit_pd, const float4* __restrict__ hit_out, float delta,
+                                      int64_t ray0, int64_t n, int bg_mode, const float* __restrict__ bkgd,
+                                      float* __restrict__ rgb, float* __restrict__ alpha_out, float* __restrict__ depth_out,
+                                      const int32_t* __restrict__ cursor, int32_t* __restrict__ hits_total) {
+  int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (li == 0 && hits_total) atomicAdd(hits_total, *cursor);
+  if (li >= n) return;
+  const int s = ray_start[li], c = ray_count[li];
+  float fill = bg_mode == QF_BG_BLACK ? 0.f : 1.f;
+  float r = fill, g = fill, b = fill, A = 0.f, D = 0.f;
+  if (c > 0) {
+    float cum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    for (int j = s; j < s + c; ++j) {
+      float4 o = hit_out[j];
+      float tau = o.w * delta;
+      float w = expf(-cum) * (1.0f - expf(-tau));
+      cum += tau;
+      cr += w * o.x; cg += w * o.y; cb += w * o.z;
+      D += w * hit_pd[j].w;
+      A += w;
+    }
+    if (bg_mode == QF_BG_WHITE) { r = (1.f - A) + A * cr; g = (1.f - A) + A * cg; b = (1.f - A) + A * cb; }
+    else if (bg_mode == QF_BG_BLACK) { r = A * cr; g = A * cg; b = A * cb; }
+    else { r = A * cr + (1.f - A) * bkgd[0]; g = A * cg + (1.f - A) * bkgd[1]; b = A * cb + (1.f - A) * bkgd[2]; }
+  }
+  const int64_t i = ray0 + li;
+  rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
+  alpha_out[i] = A;
+  depth_out[i] = D;
+}
+
+__global__ void generate_rays_kernel(float r00, float r01, float r02, float r10, float r11, float r12, float r20, float r21,
+                                     float r22, float tx, float ty, float tz, int W, int H, float focal, float cx, float cy,
+                                     float sgn, float* __restrict__ origins, float* __restrict__ viewdirs) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)W * H) return;
+  int x = (int)(i % W), y = (int)(i / W);  // meshgrid(indexing="xy") flattened row-major (nerf_synthetic.py:311-317)
+  float cxd = __fdiv_rn(__fadd_rn(__fsub_rn((float)x, cx), 0.5f), focal);
+  float cyd = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn((float)y, cy), 0.5f), focal), sgn);
+  float czd = sgn;
+  float dx = __fadd_rn(__fadd_rn(__fmul_rn(cxd, r00), __fmul_rn(cyd, r01)), __fmul_rn(czd, r02));
+  float dy = __fadd_rn(__fadd_rn(__fmul_rn(cxd, r10), __fmul_rn(cyd, r11)), __fmul_rn(czd, r12));
+  float dz = __fadd_rn(__fadd_rn(__fmul_rn(cxd, r20), __fmul_rn(cyd, r21)), __fmul_rn(czd, r22));
+  float n = norm3(dx, dy, dz);
+  viewdirs[3 * i] = __fdiv_rn(dx, n); viewdirs[3 * i + 1] = __fdiv_rn(dy, n); viewdirs[3 * i + 2] = __fdiv_rn(dz, n);
+  origins[3 * i] = tx; origins[3 * i + 1] = ty; origins[3 * i + 2] = tz;
+}
+
+enum class Shade { NGP, BAKED };
+
+// Optional per-stage CUDA-event timing of the fused render (bench.py's roofline uses it): events are recorded on
+// the launching stream around trace / shade / composite; reading them back synchronises.
+struct StageProfile {
+  bool enabled = false;
+  std::vector<cudaEvent_t> ev;   // 4 events per recorded chunk
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    if (!pool.empty()) { e = pool.back(); pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+static StageProfile g_prof;
+
+static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, const qf_texture* tex, const float* d_uv,
+                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta, int bg_mode,
+                         const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total,
+                         void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+  QF_REQUIRE(mesh && d_origins && d_viewdirs && d_rgb && d_alpha && d_depth && d_workspace, "qf_render: NULL argument");
+  QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_render: K=%d outside [1,%d]", K, QF_MAX_HITS);
+  QF_REQUIRE(bg_mode >= 0 && bg_mode <= 2, "qf_render: bg_mode=%d", bg_mode);
+  QF_REQUIRE(bg_mode != QF_BG_RANDOM || d_bkgd, "qf_render: bg 'random' needs render_bkgd");
+  QF_REQUIRE(n_rays < (1ll << 31), "qf_render: at most 2^31-1 rays per call");
+  QF_REQUIRE(workspace_bytes >= qf_render_workspace_bytes(n_rays, K), "qf_render: workspace %zu < %zu bytes", workspace_bytes,
+             qf_render_workspace_bytes(n_rays, K));
+  if (d_hits_total) QF_CUDA_CHECK(cudaMemsetAsync(d_hits_total, 0, sizeof(int32_t), st));
+  if (n_rays == 0) return QF_OK;
+  Workspace w;
+  workspace_layout(n_rays, K, &w, (char*)d_workspace);
+  for (int64_t ray0 = 0; ray0 < n_rays; ray0 += kChunkRays) {
+    const int64_t n = (n_rays - ray0) < kChunkRays ? (n_rays - ray0) : kChunkRays;
+    QF_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t), st));
+    const int blocks = (int)ceil_div(n, 128);
+    cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
+    if (K <= 8)
+      trace_compact_kernel<8><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
+                                                      d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+    else if (K <= 16)
+      trace_compact_kernel<16><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
+                                                       d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+    else
+      trace_compact_kernel<32><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
+                                                       d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+    QF_LAUNCH_CHECK();
+    if (g_prof.enabled) cudaEventRecord(pe[1], st);
+    int rc = mode == Shade::NGP ? launch_ngp_forward_hits(field, w.hit_pd, w.hit_rt, d_viewdirs, w.cursor, w.hit_out, st)
+                                : launch_baked_shade(tex, mesh, d_uv, w.hit_pd, w.hit_rt, d_viewdirs, w.cursor, w.hit_out, st);
+    if (rc != QF_OK) return rc;
+    if (g_prof.enabled) cudaEventRecord(pe[2], st);
+    composite_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(w.ray_start, w.ray_count, w.hit_pd, w.hit_out, delta, ray0, n,
+                                                                 bg_mode, d_bkgd, d_rgb, d_alpha, d_depth, w.cursor, d_hits_total);
+    QF_LAUNCH_CHECK();
+    if (g_prof.enabled) { cudaEventRecord(pe[3], st); for (auto e : pe) g_prof.ev.push_back(e); }
+  }
+  return QF_OK;
+}
+
+}  // namespace qf
+
+using namespace qf;
+
+extern "C" size_t qf_render_workspace_bytes(int64_t n_rays, int K) { return workspace_layout(n_rays, K, nullptr, nullptr); }
+
+extern "C" int qf_render_mesh_ngp(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
+                                  int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
+                                  float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
+                                  size_t workspace_bytes, void* stream) {
+  QF_REQUIRE(field, "qf_render_mesh_ngp: NULL field");
+  return render_common(Shade::NGP, mesh, field, nullptr, nullptr, d_origins, d_viewdirs, n_rays, K, delta, bg_mode, d_bkgd, d_rgb,
+                       d_alpha, d_depth, d_hits_total, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled, const float* d_origins,
+                                    const float* d_viewdirs, int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd,
+                                    float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
+                                    size_t workspace_bytes, void* stream) {
+  QF_REQUIRE(tex && d_uv_scaled, "qf_render_mesh_baked: NULL texture / uv");
+  return render_common(Shade::BAKED, mesh, nullptr, tex, d_uv_scaled, d_origins, d_viewdirs, n_rays, K, delta, bg_mode, d_bkgd,
+                       d_rgb, d_alpha, d_depth, d_hits_total, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int qf_generate_rays(const float* c, int W, int H, float focal, float cx, float cy, int opengl, float* d_origins,
+                                float* d_viewdirs, void* stream) {
+  QF_REQUIRE(c && d_origins && d_viewdirs && W > 0 && H > 0, "qf_generate_rays: bad argument");
+  const int64_t n = (int64_t)W * H;
+  generate_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10],
+                                                                                c[3], c[7], c[11], W, H, focal, cx, cy,
+                                                                                opengl ? -1.0f : 1.0f, d_origins, d_viewdirs);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_profile_enable(int on) {
+  g_prof.enabled = on != 0;
+  return QF_OK;
+}
+
+// Sums the recorded stage times (ms) since the last read: ms3 = {trace, shade, composite}; n_chunks = launches of each.
+extern "C" int qf_profile_read(double* ms3, int64_t* n_chunks) {
+  QF_REQUIRE(ms3 && n_chunks, "qf_profile_read: NULL argument");
+  ms3[0] = ms3[1] = ms3[2] = 0.0;
+  *n_chunks = 0;
+  for (size_t i = 0; i + 3 < g_prof.ev.size(); i += 4) {
+    QF_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[i + 3]));
+    for (int k = 0; k < 3; ++k) {
+      float ms = 0.f;
+      QF_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[i + k], g_prof.ev[i + k + 1]));
+      ms3[k] += ms;
+    }
+    ++*n_chunks;
+  }
+  for (auto e : g_prof.ev) g_prof.pool.push_back(e);
+  g_prof.ev.clear();
+  return QF_OK;
+}

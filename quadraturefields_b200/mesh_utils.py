@@ -1,0 +1,231 @@
+"""Drop-in for the hot-path classes of the reference's `examples/mesh_utils.py`.
+
+`RayIntersector` keeps the surface of the OptiX wrapper (mesh_utils.py:75-109) and
+`MeshIntersection` that of mesh_utils.py:180-412 (`sampling_raytrace_numpy`, `sampling_indexing`,
+`find_deltas`), but intersection runs on the GPU through libquadfield's LBVH + first-K traversal
+(csrc/bvh.cu) instead of Embree in a DataLoader worker, and the depth re-sort stays on the device
+instead of the reference's GPU->CPU `np.lexsort`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+class _Mesh:
+    """Minimal stand-in for the `trimesh.Trimesh` attributes the reference touches (`vertices`, `faces`)."""
+
+    def __init__(self, vertices: np.ndarray, faces: np.ndarray):
+        self.vertices = np.asarray(vertices, dtype=np.float64)
+        self.faces = np.asarray(faces, dtype=np.int64)
+
+
+def load_mesh(path: str) -> _Mesh:
+    """Tiny OBJ / ASCII-PLY reader (`trimesh.load(path, force='mesh', process=False)`, mesh_utils.py:193)."""
+    verts, faces = [], []
+    if path.endswith(".obj"):
+        with open(path) as f:
+            for line in f:
+                p = line.split()
+                if not p:
+                    continue
+                if p[0] == "v":
+                    verts.append([float(p[1]), float(p[2]), float(p[3])])
+                elif p[0] == "f":
+                    idx = [int(q.split("/")[0]) - 1 for q in p[1:]]
+                    for k in range(1, len(idx) - 1):
+                        faces.append([idx[0], idx[k], idx[k + 1]])
+    elif path.endswith(".ply"):
+        with open(path, "rb") as f:
+            header = []
+            while True:
+                line = f.readline().decode("ascii", "replace").strip()
+                header.append(line)
+                if line == "end_header":
+                    break
+            if not any(h.startswith("format ascii") for h in header):
+                raise NotImplementedError("only ASCII PLY is supported")
+            nv = next(int(h.split()[-1]) for h in header if h.startswith("element vertex"))
+            nf = next(int(h.split()[-1]) for h in header if h.startswith("element face"))
+            for _ in range(nv):
+                verts.append([float(x) for x in f.readline().split()[:3]])
+            for _ in range(nf):
+                p = [int(x) for x in f.readline().split()]
+                for k in range(2, p[0]):
+                    faces.append([p[1], p[k], p[k + 1]])
+    else:
+        raise NotImplementedError(f"unsupported mesh format: {path}")
+    return _Mesh(np.array(verts), np.array(faces))
+
+
+class RayIntersector:
+    """mesh_utils.py:75-109.  `intersects_id` returns (triangle_indices, ray_indices, psi) as numpy arrays."""
+
+    def __init__(self, mesh, max_hits: int = 10, device="cuda"):
+        self.mesh = mesh
+        self.max_hits = max_hits
+        self.device = torch.device(device)
+        self._handle = None
+        self._create(torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32),
+                     torch.as_tensor(np.asarray(mesh.faces), dtype=torch.int32))
+
+    def _create(self, vertices: torch.Tensor, faces: torch.Tensor):
+        lib = _lib.load()
+        self.d_vertices = vertices.to(self.device, torch.float32).contiguous()
+        self.d_faces = faces.to(self.device, torch.int32).contiguous()
+        h = C.c_void_p()
+        _lib.check(lib.qf_mesh_create(_lib.ptr(self.d_vertices), self.d_vertices.shape[0], _lib.ptr(self.d_faces),
+                                      self.d_faces.shape[0], _lib.stream(self.device), C.byref(h)), "qf_mesh_create")
+        self._handle = h
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def info(self):
+        lib = _lib.load()
+        info = (C.c_int64 * 4)()
+        pad = C.c_float()
+        _lib.check(lib.qf_mesh_info(self._handle, info, C.byref(pad)), "qf_mesh_info")
+        return dict(n_faces=info[0], n_vertices=info[1], n_nodes=info[2], device_bytes=info[3], box_pad=pad.value)
+
+    def update_intersector(self, vertices):
+        """mesh_utils.py:83-84 (`Intersector.update_vertices`): (V,3) vertex positions, same topology."""
+        lib = _lib.load()
+        v = torch.as_tensor(np.asarray(vertices) if not isinstance(vertices, torch.Tensor) else vertices)
+        v = v.reshape(-1, 3).to(self.device, torch.float32).contiguous()
+        if v.shape[0] != self.d_vertices.shape[0]:
+            raise ValueError("update_intersector expects the (V,3) vertex array of the same topology")
+        self.d_vertices = v
+        _lib.check(lib.qf_mesh_update_vertices(self._handle, _lib.ptr(v), _lib.stream(self.device)), "qf_mesh_update_vertices")
+
+    # ---- device-resident API --------------------------------------------------------------------
+    @torch.no_grad()
+    def trace(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None, with_total=False):
+        """First-K hits per ray: tri (N,K) int32 (-1 padded), t (N,K), count (N,) [, total (N,)]."""
+        lib = _lib.load()
+        K = int(max_hits or self.max_hits)
+        o = _lib.f32(origins, self.device)
+        d = _lib.f32(vectors, self.device)
+        N = o.shape[0]
+        tri = torch.empty((N, K), dtype=torch.int32, device=self.device)
+        t = torch.empty((N, K), dtype=torch.float32, device=self.device)
+        count = torch.empty((N,), dtype=torch.int32, device=self.device)
+        total = torch.empty((N,), dtype=torch.int32, device=self.device) if with_total else None
+        _lib.check(lib.qf_trace_firstk(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(t),
+                                       _lib.ptr(count), _lib.ptr(total), _lib.stream(self.device)), "qf_trace_firstk")
+        return (tri, t, count, total) if with_total else (tri, t, count)
+
+    @torch.no_grad()
+    def trace_tuple(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None):
+        """The reference data tuple on the device, ray-major and depth-sorted:
+        (points (M,3), vectors (M,3), index_ray (M,), depth (M,), index_tri (M,), origins (M,3)); M may be 0."""
+        lib = _lib.load()
+        K = int(max_hits or self.max_hits)
+        o = _lib.f32(origins, self.device)
+        d = _lib.f32(vectors, self.device)
+        N = o.shape[0]
+        tri, _, count = self.trace(o, d, K)
+        offsets = torch.empty((N + 1,), dtype=torch.int64, device=self.device)
+        ws = _lib.workspace(self.device, lib.qf_scan_workspace_bytes(N), "scan")
+        st = _lib.stream(self.device)
+        _lib.check(lib.qf_hits_offsets(_lib.ptr(count), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), st), "qf_hits_offsets")
+        total = C.c_int64()
+        _lib.check(lib.qf_hits_total(_lib.ptr(offsets), N, C.byref(total), st), "qf_hits_total")
+        M = total.value
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
+        points, vecs, org, depth = f(M, 3), f(M, 3), f(M, 3), f(M)
+        index_ray = torch.empty((M,), dtype=torch.int64, device=self.device)
+        index_tri = torch.empty((M,), dtype=torch.int64, device=self.device)
+        if M:
+            _lib.check(lib.qf_hits_pack(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(count),
+                                        _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(vecs), _lib.ptr(index_ray),
+                                        _lib.ptr(depth), _lib.ptr(index_tri), _lib.ptr(org), st), "qf_hits_pack")
+        return points, vecs, index_ray, depth, index_tri, org, offsets
+
+    # ---- reference surface ------------------------------------------------------------------------
+    @torch.no_grad()
+    def intersects_id(self, origins, vectors, multiple_hits=True, return_locations=True, max_hits=10):
+        points, _, index_ray, depth, index_tri, _, _ = self.trace_tuple(torch.as_tensor(np.asarray(origins)),
+                                                                      torch.as_tensor(np.asarray(vectors)),
+                                                                      max_hits if multiple_hits else 1)
+        return index_tri.cpu().numpy(), index_ray.cpu().numpy(), points.cpu().numpy()
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _lib.load().qf_mesh_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+class MeshIntersection:
+    """mesh_utils.py:180-412.  `mesh_path` may also be a `(vertices, faces)` pair."""
+
+    def __init__(self, mesh_path, simplify_mesh=False, scale=1.0, num_repeat=16, optix=False, voxel_size=512,
+                 num_intersections=20, render_step_size=0.005, device="cuda"):
+        if simplify_mesh:
+            # the reference forces the trimesh loader (mesh_utils.py:186), for which simplification is not
+            # available; every shipped script passes simplify_mesh=False
+            raise NotImplementedError("simplify_mesh=True is not supported (no caller uses it)")
+        self.mesh = load_mesh(mesh_path) if isinstance(mesh_path, str) else _Mesh(mesh_path[0], mesh_path[1])
+        self.num_repeat = num_repeat
+        self.num_intersections = num_intersections
+        self.render_step_size = render_step_size
+        self.mesh.vertices = self.mesh.vertices * scale                                   # mesh_utils.py:212
+        self.device = torch.device(device)
+        self.vertices = torch.from_numpy(self.mesh.vertices.astype(np.float32)).to(self.device)   # :214
+        self.rayintersector = RayIntersector(self.mesh, max_hits=self.num_intersections, device=device)
+
+    def find_deltas(self, boundary, depth):
+        """mesh_utils.py:225-231: the constant quadrature step (quirk Q4)."""
+        return torch.full((depth.shape[0],), self.render_step_size, dtype=torch.float32, device=depth.device)
+
+    @torch.no_grad()
+    def sampling_raytrace(self, vectors: torch.Tensor, origins: torch.Tensor):
+        """Device-resident `sampling_raytrace_numpy`: returns the 7-tuple as CUDA tensors, or None on zero hits."""
+        points, vecs, index_ray, depth, index_tri, org, _ = self.rayintersector.trace_tuple(origins, vectors,
+                                                                                          self.num_intersections)
+        if index_tri.shape[0] == 0:
+            return None
+        return points, vecs, index_ray, depth, index_tri, 0, org
+
+    def sampling_raytrace_numpy(self, vectors, origins, random=0):
+        """mesh_utils.py:343-387 (numpy in, numpy out, `None` when nothing is hit)."""
+        res = self.sampling_raytrace(torch.as_tensor(np.asarray(vectors)), torch.as_tensor(np.asarray(origins)))
+        if res is None:
+            return None
+        points, vecs, index_ray, depth, index_tri, _, org = res
+        return (points.cpu().numpy(), vecs.cpu().numpy(), index_ray.cpu().numpy(), depth.cpu().numpy(),
+                index_tri.cpu().numpy(), 0, org.cpu().numpy())
+
+    @torch.no_grad()
+    def sampling_indexing(self, points, origins, vectors, index_ray, depth, index_tri, random=0):
+        """mesh_utils.py:389-412: per-ray re-sort by depth, pack boundaries, constant deltas — all on the device."""
+        lib = _lib.load()
+        dev = self.device
+        index_ray = _lib.i64(index_ray.to(dev))
+        depth = _lib.f32(depth, dev)
+        M = index_ray.shape[0]
+        if M > 1 and bool((index_ray[1:] < index_ray[:-1]).any()):
+            # arbitrary order: full lexsort((depth, index_ray)) with device sorts (stable)
+            o1 = torch.sort(depth, stable=True).indices
+            perm = o1[torch.sort(index_ray[o1], stable=True).indices]
+            boundary = torch.ones(M, dtype=torch.bool, device=dev)
+            boundary[1:] = index_ray[perm][1:] != index_ray[perm][:-1]
+        else:
+            perm = torch.empty((M,), dtype=torch.int64, device=dev)
+            b8 = torch.empty((M,), dtype=torch.uint8, device=dev)
+            _lib.check(lib.qf_hits_resort(_lib.ptr(index_ray), _lib.ptr(depth), M, _lib.ptr(perm), _lib.ptr(b8),
+                                          _lib.stream(dev)), "qf_hits_resort")
+            boundary = b8.bool()
+        g = lambda t: t.to(dev)[perm]
+        depth = depth[perm]
+        deltas = self.find_deltas(boundary, depth)
+        return g(points), deltas, boundary, g(vectors), index_ray[perm], depth, g(index_tri), g(origins)

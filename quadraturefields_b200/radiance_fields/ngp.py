@@ -1,0 +1,224 @@
+"""Drop-in for the reference's `examples/radiance_fields/ngp.py` hot-path classes.
+
+`NGPRadianceField` keeps the constructor signature, buffers and call surface of ngp.py:657-809
+(`normalize`, `query_density`, `_query_rgb`, `forward`) and the tinycudann parameter layout
+(`mlp_base.params` = [MLP weights | grid table], `mlp_head.params`), but evaluates through libquadfield's
+fused hash-grid + tensor-core MLP kernel (csrc/field.cu) — no tinycudann.  CUDA only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Callable, List, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib
+from . import grid as _grid
+
+
+class _TruncExp(torch.autograd.Function):
+    """ngp.py:146-159: forward exp(x), backward g*exp(clamp(x, max=15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.float()
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(torch.clamp(x, max=15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+class _TcnnParams(nn.Module):
+    """Holds one flat fp32 `params` tensor, like a tinycudann module (state_dict key `<name>.params`)."""
+
+    def __init__(self, n: int):
+        super().__init__()
+        self.params = nn.Parameter(torch.zeros(n, dtype=torch.float32))
+
+
+class _DirectionEncoding(nn.Module):
+    n_output_dims = 16  # SphericalHarmonics degree 4 (ngp.py:694-707)
+
+
+_BASE_SHAPES = [(64, 32), (16, 64)]
+_HEAD_SHAPES = [(64, 32), (64, 64), (16, 64)]
+
+
+def _xavier_flat(shapes, gen):
+    out = []
+    for o, i in shapes:
+        b = math.sqrt(6.0 / (i + o))
+        out.append((torch.rand(o * i, generator=gen) * 2 - 1) * b)
+    return torch.cat(out)
+
+
+class NGPRadianceField(nn.Module):
+    """Instant-NGP radiance field (ngp.py:657-809)."""
+
+    def __init__(self, aabb: Union[torch.Tensor, List[float]], num_dim: int = 3, use_viewdirs: bool = True,
+                 density_activation: Callable = lambda x: trunc_exp(x - 1), unbounded: bool = False,
+                 base_resolution: int = 16, max_resolution: int = 4096, geo_feat_dim: int = 15, n_levels: int = 16,
+                 log2_hashmap_size: int = 19, num_layers=2, hidden_size=64, seed: int = 1337) -> None:
+        super().__init__()
+        if not isinstance(aabb, torch.Tensor):
+            aabb = torch.tensor(aabb, dtype=torch.float32)
+        self.register_buffer("aabb", aabb)
+        if num_dim != 3 or not use_viewdirs or unbounded or geo_feat_dim != 15 or n_levels != 16 or hidden_size != 64:
+            raise NotImplementedError("the fused kernel covers the configuration every Quadfield script uses: 3-D, "
+                                      "viewdirs, bounded, 16 levels x 2 features, 64-wide MLPs, 15 geo features")
+        self.num_dim, self.use_viewdirs, self.density_activation, self.unbounded = num_dim, use_viewdirs, density_activation, unbounded
+        self.base_resolution, self.max_resolution, self.geo_feat_dim = base_resolution, max_resolution, geo_feat_dim
+        self.n_levels, self.log2_hashmap_size = n_levels, log2_hashmap_size
+        # num_layers is ignored by the reference as well (quirk Q8, ngp.py:744)
+        self._desc = _grid.make_grid_desc(aabb.tolist(), n_levels, base_resolution, max_resolution, log2_hashmap_size)
+        self._n_entries = _grid.n_entries(self._desc)
+        self._n_base = sum(o * i for o, i in _BASE_SHAPES)
+        self.direction_encoding = _DirectionEncoding()
+        self.mlp_base = _TcnnParams(self._n_base + 2 * self._n_entries)
+        self.mlp_head = _TcnnParams(sum(o * i for o, i in _HEAD_SHAPES))
+        g = torch.Generator().manual_seed(seed)
+        with torch.no_grad():
+            self.mlp_base.params[: self._n_base] = _xavier_flat(_BASE_SHAPES, g)
+            self.mlp_base.params[self._n_base:] = (torch.rand(2 * self._n_entries, generator=g) * 2 - 1) * 1e-4
+            self.mlp_head.params.copy_(_xavier_flat(_HEAD_SHAPES, g))
+        self._handle = None
+        self._handle_key = None
+
+    # ---- native handle management -------------------------------------------------------------
+    def _native(self):
+        p_base, p_head = self.mlp_base.params, self.mlp_head.params
+        if not p_base.is_cuda:
+            raise RuntimeError("NGPRadianceField runs on CUDA only: call .to('cuda') first (no CPU path)")
+        key = (p_base.data_ptr(), p_head.data_ptr(), p_base._version, p_head._version, self.aabb._version)
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        lib = _lib.load()
+        aabb = self.aabb.detach().cpu().tolist()
+        for i in range(6):
+            self._desc.aabb[i] = float(aabb[i])
+        base = p_base.detach()
+        table, base_w, head_w = base[self._n_base:], base[: self._n_base], p_head.detach()
+        st = _lib.stream(p_base.device)
+        if self._handle is None or key[:2] != self._handle_key[:2]:
+            self._free()
+            h = C.c_void_p()
+            _lib.check(lib.qf_ngp_create(C.byref(self._desc), _lib.ptr(table), self._n_entries, _lib.ptr(base_w),
+                                         _lib.ptr(head_w), st, C.byref(h)), "qf_ngp_create")
+            self._handle = h
+        else:
+            _lib.check(lib.qf_ngp_update(self._handle, _lib.ptr(table), _lib.ptr(base_w), _lib.ptr(head_w), st), "qf_ngp_update")
+        self._handle_key = key
+        return self._handle
+
+    def _free(self):
+        if getattr(self, "_handle", None) is not None:
+            _lib.load().qf_ngp_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._free()
+        except Exception:
+            pass
+
+    # ---- reference call surface ----------------------------------------------------------------
+    def normalize(self, x):
+        """ngp.py:748-755."""
+        aabb_min, aabb_max = torch.split(self.aabb, self.num_dim, dim=-1)
+        x = (x - aabb_min) / (aabb_max - aabb_min)
+        selector = ((x > 0.0) & (x < 1.0)).all(dim=-1)
+        return selector, x
+
+    @torch.no_grad()
+    def query_density(self, x, return_feat: bool = False):
+        """ngp.py:757-779 -> density (...,1) [, feat (...,15)]."""
+        lib = _lib.load()
+        h = self._native()
+        shape = list(x.shape[:-1])
+        pos = _lib.f32(x.reshape(-1, 3))
+        M = pos.shape[0]
+        density = torch.empty((M, 1), dtype=torch.float32, device=pos.device)
+        feat = torch.empty((M, 15), dtype=torch.float32, device=pos.device) if return_feat else None
+        _lib.check(lib.qf_ngp_query_density(h, _lib.ptr(pos), M, _lib.ptr(density), _lib.ptr(feat),
+                                            _lib.stream(pos.device)), "qf_ngp_query_density")
+        density = density.view(shape + [1])
+        if return_feat:
+            return density, feat.view(shape + [15])
+        return density
+
+    @torch.no_grad()
+    def forward(self, positions: torch.Tensor, directions: torch.Tensor = None, ray_indices: torch.Tensor = None):
+        """ngp.py:798-809 -> (rgb (M,3), density (M,1)).  `ray_indices` (extension): gather
+        directions[ray_indices] inside the kernel, as utils.py:515-529 does with a separate indexing op."""
+        if not (self.use_viewdirs and (directions is not None)):
+            raise NameError("name 'rgb' is not defined")  # what the reference does (quirk Q8, ngp.py:803-809)
+        if ray_indices is None:
+            assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+        lib = _lib.load()
+        h = self._native()
+        pos = _lib.f32(positions.reshape(-1, 3))
+        dirs = _lib.f32(directions.reshape(-1, 3))
+        ri = _lib.i64(ray_indices) if ray_indices is not None else None
+        M = pos.shape[0]
+        rgb = torch.empty((M, 3), dtype=torch.float32, device=pos.device)
+        density = torch.empty((M, 1), dtype=torch.float32, device=pos.device)
+        _lib.check(lib.qf_ngp_forward(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(rgb), _lib.ptr(density),
+                                      _lib.stream(pos.device)), "qf_ngp_forward")
+        return rgb, density
+
+    @torch.no_grad()
+    def encode(self, x01: torch.Tensor) -> torch.Tensor:
+        """tcnn HashGrid forward alone (for tests / profiling): x in [0,1]^3 -> (M, 32)."""
+        lib = _lib.load()
+        h = self._native()
+        x01 = _lib.f32(x01.reshape(-1, 3))
+        out = torch.empty((x01.shape[0], 2 * self.n_levels), dtype=torch.float32, device=x01.device)
+        _lib.check(lib.qf_hashgrid_forward(h, _lib.ptr(x01), x01.shape[0], _lib.ptr(out), _lib.stream(x01.device)),
+                   "qf_hashgrid_forward")
+        return out
+
+    # ---- parameter helpers ------------------------------------------------------------------------
+    @torch.no_grad()
+    def load_arrays(self, table: torch.Tensor, base_w, head_w):
+        """Set parameters from explicit arrays: table (n_entries,2), base_w [(64,32),(16,64)], head_w [(64,32),(64,64),(16,64)]."""
+        dev = self.mlp_base.params.device
+        self.mlp_base.params.copy_(torch.cat([w.reshape(-1) for w in base_w] + [table.reshape(-1)]).to(dev))
+        self.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in head_w]).to(dev))
+
+
+def spherical_gaussian_features_to_rgb(features: torch.Tensor, dirs: torch.Tensor, num_lobes: int) -> torch.Tensor:
+    """`NGPRadianceFieldSGNew.features_to_rgb` (ngp.py:456-461, 371-393) with discretize=False."""
+    lib = _lib.load()
+    f = _lib.f32(features)
+    d = _lib.f32(dirs)
+    M = f.shape[0]
+    rgb = torch.empty((M, 3), dtype=torch.float32, device=f.device)
+    _lib.check(lib.qf_sg_features_to_rgb(_lib.ptr(f), f.shape[1], num_lobes, _lib.ptr(d), M, _lib.ptr(rgb),
+                                         _lib.stream(f.device)), "qf_sg_features_to_rgb")
+    return rgb
+
+
+class NGPRadianceFieldSGNew(nn.Module):
+    """The stateless part of ngp.py:284-470 the baked path uses (test_baking_texture_images.py:297-305 builds it
+    but never loads weights — SURVEY fact 5): `features_to_rgb`."""
+
+    def __init__(self, aabb=None, use_viewdirs: bool = False, num_g_lobes: int = 3, num_layers: int = 2,
+                 discretize: bool = False, log2_hashmap_size: int = 19, **kwargs) -> None:
+        super().__init__()
+        if discretize:
+            raise NotImplementedError("discretize=True (fake quantisation during SG fitting) is outside the render path")
+        self.num_g_lobes = num_g_lobes
+        self.discretize = discretize
+
+    @torch.no_grad()
+    def features_to_rgb(self, features, dir):
+        return spherical_gaussian_features_to_rgb(features, dir, self.num_g_lobes)

@@ -1,0 +1,484 @@
+"""GPU parity tests: every call goes through the C ABI (libquadfield.so) and is compared with the CPU oracle
+on the same seeded inputs and with the golden fixtures produced from the unmodified reference.
+
+Bars (BASELINE.json north_star): hit counts and triangle ids bit-exact; RGB / opacity within 1e-3 max-abs
+(fp32) and <= 0.05 dB PSNR delta."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import quadfield_oracle as O
+from tests.helpers import maxabs, oracle_params, oracle_texture, psnr_delta_db
+
+pytestmark = pytest.mark.gpu
+
+TOL_IMG = 1e-3
+T = lambda a: torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import __graft_entry__ as entry
+    entry.build()
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def smoke_scene(dev):
+    from quadraturefields_b200 import scene
+    return scene.make_scene("smoke", device=dev)
+
+
+def _rays_for(sc, view=0):
+    o, d = O.generate_rays(sc.poses[view], sc.W, sc.H, np.float32(sc.focal), np.float32(sc.cx), np.float32(sc.cy))
+    return o, d
+
+
+# ----------------------------------------------------------------------------- a1 ray generation
+def test_ray_generation(dev, smoke_scene):
+    sc = smoke_scene
+    o_ref, d_ref = _rays_for(sc, 1)
+    o, d = sc.rays(1)
+    assert maxabs(o, o_ref) == 0.0
+    assert maxabs(d, d_ref) <= 2e-7
+    assert d.shape == (sc.W * sc.H, 3)
+
+
+# ----------------------------------------------------------------------------- a2 intersection: bit-exact ids / counts
+@pytest.mark.parametrize("K", [1, 3, 8, 16, 32])
+def test_trace_firstk_bit_exact(dev, smoke_scene, K):
+    sc = smoke_scene
+    o, d = _rays_for(sc, 0)
+    rng = np.random.RandomState(K)
+    # camera rays + random rays from inside the shells + exactly axis-aligned rays (zero direction components)
+    o2 = rng.uniform(-0.3, 0.3, size=(512, 3)).astype(np.float32)
+    d2 = rng.normal(size=(512, 3)).astype(np.float32)
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    o3 = rng.uniform(-1.2, 1.2, size=(96, 3)).astype(np.float32)
+    d3 = np.zeros((96, 3), dtype=np.float32)
+    d3[np.arange(96), np.arange(96) % 3] = np.where(np.arange(96) % 2 == 0, 1.0, -1.0)
+    for i in range(48, 96):
+        d3[i, (i + 1) % 3] = -0.0
+    origins, dirs = np.concatenate([o, o2, o3]), np.concatenate([d, d2, d3])
+    tri_ref, t_ref, count_ref, total_ref = O.intersect_firstk(origins, dirs, sc.vertices_np, sc.faces_np, K)
+    tri, t, count, total = sc.mesh_intersect.rayintersector.trace(T(origins), T(dirs), K, with_total=True)
+    assert np.array_equal(count.cpu().numpy(), count_ref)
+    assert np.array_equal(total.cpu().numpy(), total_ref)
+    assert np.array_equal(tri.cpu().numpy(), tri_ref)
+    assert np.array_equal(t.cpu().numpy(), t_ref)            # same fp32 op sequence -> identical t, +inf padding
+    assert count_ref.max() == min(K, total_ref.max()) and total_ref.max() >= 6
+
+
+@pytest.mark.parametrize("n_faces", [1, 2, 5, 9])
+def test_trace_tiny_meshes(dev, n_faces):
+    from quadraturefields_b200.mesh_utils import RayIntersector, _Mesh
+    rng = np.random.RandomState(n_faces)
+    verts = rng.uniform(-1, 1, size=(3 * n_faces, 3)).astype(np.float32)
+    faces = np.arange(3 * n_faces, dtype=np.int32).reshape(n_faces, 3)
+    ri = RayIntersector(_Mesh(verts, faces), max_hits=4, device=dev)
+    origins = rng.uniform(-2, 2, size=(4096, 3)).astype(np.float32)
+    target = rng.uniform(-0.7, 0.7, size=(4096, 3)).astype(np.float32)
+    dirs = target - origins
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    tri_ref, _, count_ref, _ = O.intersect_firstk(origins, dirs, verts, faces, 4)
+    tri, _, count = ri.trace(T(origins), T(dirs), 4)
+    assert np.array_equal(tri.cpu().numpy(), tri_ref) and np.array_equal(count.cpu().numpy(), count_ref)
+    assert count_ref.sum() > 50
+    assert ri.info()["box_pad"] == float(O.mesh_box_pad(verts))
+
+
+def test_trace_truncation_is_prefix(dev, smoke_scene):
+    """K-truncation monotonicity: the first K hits are a prefix of the first K' > K."""
+    sc = smoke_scene
+    o, d = sc.rays(0)
+    tri8, t8, c8 = sc.mesh_intersect.rayintersector.trace(o, d, 8)
+    tri3, t3, c3 = sc.mesh_intersect.rayintersector.trace(o, d, 3)
+    assert torch.equal(tri8[:, :3], tri3) and torch.equal(torch.clamp(c8, max=3), c3)
+    valid = t8[:, 1:] != float("inf")
+    assert bool((t8[:, 1:][valid] >= t8[:, :-1][valid]).all())          # sorted by t
+
+
+def test_update_vertices_rebuilds(dev):
+    from quadraturefields_b200.mesh_utils import RayIntersector, _Mesh
+    v, f = O.shell_mesh([0.6, 0.9], 2, seed=5)
+    ri = RayIntersector(_Mesh(v, f), max_hits=6, device=dev)
+    rng = np.random.RandomState(0)
+    v2 = (v * 1.1 + rng.normal(0, 5e-3, size=v.shape)).astype(np.float32)
+    ri.update_intersector(v2)
+    f_, cx, cy, W, H = O.pinhole_intrinsics(40, 40, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((0.5, -3.0, 1.0)), W, H, f_, cx, cy)
+    tri_ref, _, count_ref, _ = O.intersect_firstk(o, d, v2, f, 6)
+    tri, _, count = ri.trace(T(o), T(d), 6)
+    assert np.array_equal(tri.cpu().numpy(), tri_ref) and np.array_equal(count.cpu().numpy(), count_ref)
+
+
+# ----------------------------------------------------------------------------- a3 / a4 hit tuple
+def test_hit_tuple_matches_reference_fixture(dev, golden):
+    """tests/golden/geometry.npz was produced by the reference's own sampling_raytrace_numpy / sampling_indexing."""
+    from quadraturefields_b200.mesh_utils import MeshIntersection
+    g = golden("geometry")
+    K = int(g["K"])
+    mi = MeshIntersection((g["verts"], g["faces"]), simplify_mesh=False, num_intersections=K, device=dev)
+    points, vectors, index_ray, depth, index_tri, _, org = mi.sampling_raytrace_numpy(g["viewdirs"], g["origins"])
+    assert np.array_equal(index_ray, g["index_ray"]) and np.array_equal(index_tri, g["index_tri"])
+    assert maxabs(points, g["points"]) <= 1e-6 and maxabs(depth, g["depth"]) <= 1e-6
+    assert maxabs(vectors, g["vectors"]) <= 1e-7 and maxabs(org, g["org"]) == 0.0
+    # zero-hit frame -> None (mesh_utils.py:357-358, quirk Q9)
+    away = np.tile(np.array([[0, 0, 1.0]], dtype=np.float32), (16, 1))
+    assert mi.sampling_raytrace_numpy(away, np.tile(np.array([[0, 0, 5.0]], dtype=np.float32), (16, 1))) is None
+    # a4: re-sort after perturbing depths
+    res = mi.sampling_indexing(T(g["points"]), T(g["org"]), T(g["vectors"]), T(g["index_ray"]), T(g["si_in_depth"]),
+                               T(g["index_tri"]))
+    for nme, r in zip(("points", "deltas", "boundary", "vectors", "index_ray", "depth", "index_tri", "origins"), res):
+        assert maxabs(r.double(), g["si_" + nme].astype(np.float64)) == 0.0, nme
+    # unsorted ray ids take the general lexsort branch
+    perm = torch.randperm(len(g["index_ray"]), generator=torch.Generator().manual_seed(1))
+    res2 = mi.sampling_indexing(T(g["points"])[perm], T(g["org"])[perm], T(g["vectors"])[perm], T(g["index_ray"])[perm],
+                                T(g["si_in_depth"])[perm], T(g["index_tri"])[perm])
+    assert maxabs(res2[5].double(), g["si_depth"].astype(np.float64)) == 0.0
+    assert maxabs(res2[4].double(), g["si_index_ray"].astype(np.float64)) == 0.0
+
+
+def test_intersects_id_surface(dev, smoke_scene):
+    sc = smoke_scene
+    o, d = _rays_for(sc, 1)
+    tri, ray, psi = sc.mesh_intersect.rayintersector.intersects_id(o, d, max_hits=5)
+    tup = O.sampling_raytrace(d, o, sc.vertices_np, sc.faces_np, 5)
+    assert np.array_equal(tri, tup[4]) and np.array_equal(ray, tup[2]) and maxabs(psi, tup[0]) <= 1e-6
+
+
+# ----------------------------------------------------------------------------- a5 / a6 field
+def test_hashgrid_encode(dev, smoke_scene):
+    sc = smoke_scene
+    p = oracle_params(sc)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(20000, 3, generator=g)
+    x[:64] = torch.tensor([0.0, 1.0, 0.5])[torch.randint(0, 3, (64, 3), generator=g)]   # cell boundaries / box faces
+    ref = O.hashgrid_encode(x, p.table, p.meta)
+    enc = sc.radiance_field.encode(x.to(dev)).cpu()
+    diff = (enc - ref).abs()
+    # same fp32 op sequence on both sides -> the fp16 features agree bit for bit (the oracle emulates fmaf through
+    # fp64, so allow a vanishing fraction of one-ulp flips)
+    assert float((diff / ref.abs().clamp_min(1e-3)).max()) <= 2 ** -10
+    assert float((diff > 0).float().mean()) < 1e-4
+
+
+def test_ngp_forward_matches_oracle(dev, smoke_scene):
+    sc = smoke_scene
+    p = oracle_params(sc)
+    g = torch.Generator().manual_seed(4)
+    x = (torch.rand(30000, 3, generator=g) * 2 - 1) * 1.2
+    x[:300] *= 1.4                                            # outside the aabb -> selector path
+    d = torch.nn.functional.normalize(torch.randn(30000, 3, generator=g), dim=-1)
+    rgb_ref, dens_ref = O.ngp_forward(x, d, p)
+    rgb, dens = sc.radiance_field(x.to(dev), d.to(dev))
+    assert rgb.shape == (30000, 3) and dens.shape == (30000, 1)
+    a_ref, a = 1 - torch.exp(-dens_ref * 0.005), 1 - torch.exp(-dens.cpu() * 0.005)
+    assert maxabs(rgb, rgb_ref) <= TOL_IMG
+    assert maxabs(a, a_ref) <= 2e-4
+    assert float(((dens.cpu() - dens_ref).abs() / dens_ref.clamp_min(1e-3)).max()) <= 2e-4      # hi+lo split keeps sigma tight
+    sel, _ = O.ngp_normalize(x, p.aabb)
+    assert bool((dens.cpu()[~sel] == 0).all()) and float(a_ref.max()) > 0.9 and float(a_ref.min()) < 0.1
+    # query_density surface
+    dens2, feat = sc.radiance_field.query_density(x.to(dev), return_feat=True)
+    dref, fref = O.ngp_query_density(x, p)
+    assert maxabs(dens2, dens) == 0.0 and maxabs(feat, fref) <= 1e-3
+    assert sc.radiance_field.query_density(x[:7].to(dev)).shape == (7, 1)
+    # ragged sizes around the 32-sample warp tile and the in-kernel direction gather
+    for n in (1, 15, 16, 17, 31, 33, 129):
+        r, s = sc.radiance_field(x[:n].to(dev), d[:n].to(dev))
+        assert maxabs(r, rgb[:n]) == 0.0 and maxabs(s, dens[:n]) == 0.0
+    ridx = torch.randint(0, 50, (1000,), generator=g)
+    r, s = sc.radiance_field(x[:1000].to(dev), d[:50].to(dev), ray_indices=ridx.to(dev))
+    r2, s2 = sc.radiance_field(x[:1000].to(dev), d[:50][ridx].to(dev))
+    assert maxabs(r, r2) == 0.0 and maxabs(s, s2) == 0.0
+
+
+def test_ngp_golden_fixture(dev, golden):
+    """tests/golden/ngp.npz: the reference's NGPRadianceField module run over the tinycudann stand-in."""
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceField
+    g = golden("ngp")
+    p = O.make_ngp_params(seed=int(g["seed"]), log2_hashmap_size=int(g["log2_T"]), table_scale=float(g["table_scale"]))
+    rf = NGPRadianceField(aabb=p.aabb.tolist(), log2_hashmap_size=int(g["log2_T"]))
+    rf.load_arrays(p.table, p.base_w, p.head_w)
+    rf = rf.to(dev)
+    rgb, dens = rf(T(g["x"]).to(dev), T(g["d"]).to(dev))
+    assert maxabs(rgb, g["rgb"]) <= TOL_IMG
+    assert float(((dens.cpu() - T(g["density"])).abs() / T(g["density"]).clamp_min(1e-3)).max()) <= 2e-4
+    sel, xn = rf.normalize(T(g["x"]).to(dev))
+    assert np.array_equal(sel.cpu().numpy(), g["selector"]) and maxabs(xn, g["xn"]) <= 1e-7
+    sd = rf.state_dict()
+    assert set(sd) == {"aabb", "mlp_base.params", "mlp_head.params"}            # tinycudann checkpoint keys
+    with pytest.raises(NameError):
+        rf(T(g["x"]).to(dev), None)                                              # quirk Q8
+    with pytest.raises(AssertionError):
+        rf(T(g["x"]).to(dev), T(g["d"])[:5].to(dev))
+
+
+# ----------------------------------------------------------------------------- a8 / a9 / a10 baked path
+def test_texture_decode_and_sg_golden(dev, golden):
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceFieldSGNew
+    from quadraturefields_b200.texture_utils import FeatureCompression
+    g = golden("sg_decode")
+    for L, ctype, lam in ((3, "linear", 5.0), (6, "sigmoid", 7.5), (2, "sigma", 7.5)):
+        k = f"L{L}_{ctype}"
+        planes = dict(alpha=g[k + "_alpha"], diffuse=g[k + "_diffuse"], sg_colors=[g[k + f"_color{i}"] for i in range(L)],
+                      lambdas=[g[k + f"_lambda{i}"] for i in range(L)])
+        fc = FeatureCompression(L, planes=planes, compression_type=ctype, lambda_thres=lam, device=dev)
+        feats = fc.get_features_from_texture_map(T(g[k + "_idx"]).to(dev))
+        ref = T(g[k + "_feats"])
+        assert feats.shape == ref.shape
+        assert float(((feats.cpu() - ref).abs() / ref.abs().clamp_min(1.0)).max()) <= 2e-6
+        rgb = NGPRadianceFieldSGNew(num_g_lobes=L).features_to_rgb(T(g[k + "_feats"])[:, :-1].to(dev), T(g[k + "_dirs"]).to(dev))
+        assert maxabs(rgb, g[k + "_rgb"]) <= 2e-6
+        assert maxabs(fc.features_to_rgb(feats[:, :-1], T(g[k + "_dirs"]).to(dev)), g[k + "_rgb"]) <= 1e-5
+
+
+def test_hit_texels_bit_exact(dev):
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c5_small", device=dev, build_field=False)
+    o, d = _rays_for(sc, 0)
+    tup = O.sampling_raytrace(d, o, sc.vertices_np, sc.faces_np, sc.K)
+    points, index_tri = T(tup[0]), T(tup[4])
+    ref = O.hit_texels(points, index_tri, sc.vertices_np, sc.faces_np, sc.uv_scaled, sc.compressor.texture_size)
+    from quadraturefields_b200 import _lib
+    lib = _lib.load()
+    out = torch.empty((points.shape[0], 2), dtype=torch.int64, device=dev)
+    pts, tri, uv = points.to(dev).contiguous(), index_tri.to(dev).contiguous(), sc.uv_scaled.to(dev).contiguous()
+    _lib.check(lib.qf_hit_texels(sc.mesh_intersect.rayintersector.handle, _lib.ptr(pts), _lib.ptr(tri), pts.shape[0],
+                                 _lib.ptr(uv), sc.compressor.texture_size, _lib.ptr(out), _lib.stream(dev)))
+    assert torch.equal(out.cpu(), ref)
+    assert ref.min() >= 0 and ref.max() <= sc.compressor.texture_size - 1 and len(torch.unique(ref[:, 0])) > 20
+
+
+@pytest.mark.parametrize("bg", ["white", "black"])
+def test_fused_baked_render_matches_oracle(dev, bg):
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c5_small", device=dev, build_field=False)
+    o, d = _rays_for(sc, 1)
+    ref = O.render_mesh_baked(o, d, sc.vertices_np, sc.faces_np, sc.uv_scaled, oracle_texture(sc), sc.K, bg_color=bg)
+    out = sc.render_baked(T(o).to(dev), T(d).to(dev), bg_color=bg)
+    assert int(out["n_hits"]) == ref["index_ray"].shape[0] > 1000
+    assert maxabs(out["rgb"], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"], ref["opacity"]) <= TOL_IMG
+    assert maxabs(out["depth"], ref["depth"]) <= 1e-3
+    # tuple-in driver (utils.py:998-1095 surface)
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.utils import render_image_bake_texture_images_with_occgrid as drv
+    tup = sc.mesh_intersect.sampling_raytrace(T(d), T(o))
+    data = [tup[0], tup[1], tup[2], tup[3], tup[4], tup[6]]
+    res = drv(sc.extras["sg_field"], Rays(T(o), T(d)), data, uv=sc.uv_scaled, mesh_intersect=sc.mesh_intersect,
+              compressor=sc.compressor, bg_color=bg)
+    assert maxabs(res[0], ref["rgb"]) <= TOL_IMG and maxabs(res[1], ref["opacity"]) <= TOL_IMG
+    assert res[3] == ref["index_ray"].shape[0] and maxabs(res[4], ref["weights"]) <= 1e-4
+
+
+# ----------------------------------------------------------------------------- a11 derive_properties
+def test_derive_properties_golden(dev, golden):
+    from quadraturefields_b200.utils import derive_properties
+    g = golden("derive_properties")
+    N = len(g["counts"])
+    c = lambda k: T(g[k]).to(dev)
+    for bg in ("white", "black", "random"):
+        rgb, a, ids, D, w = derive_properties(c("color"), c("density"), c("depths"), c("deltas"), c("boundary"),
+                                              c("index_ray"), render_bkgd=c("bk"), bg_color=bg, N=N)
+        assert maxabs(rgb, g[bg + "_rgb"]) <= 2e-6 and maxabs(a, g[bg + "_alpha"]) <= 2e-6
+        assert maxabs(D, g[bg + "_depth"]) <= 1e-5 and maxabs(w, g[bg + "_w"]) <= 2e-6
+        assert np.array_equal(ids.cpu().numpy(), g[bg + "_ids"])
+    # no hits at all -> pure fill (quirk Q2 / Q9)
+    e = lambda *s: torch.zeros(s, device=dev)
+    rgb, a, ids, D, w = derive_properties(e(0, 3), e(0), e(0), e(0), torch.zeros(0, dtype=torch.bool, device=dev),
+                                          torch.zeros(0, dtype=torch.long, device=dev), N=5)
+    assert bool((rgb == 1).all()) and bool((a == 0).all()) and w.shape == (0, 1)
+
+
+# ----------------------------------------------------------------------------- a12-a15 nerfacc-style surface
+def test_field_rendering_docstring_kats(dev):
+    """field_rendering.py:192-195, 246-253, 298-302, 347-355, 403-409."""
+    from quadraturefields_b200 import field_rendering as FR
+    a = torch.tensor([0.4, 0.8, 0.1, 0.8, 0.1, 0.0, 0.9], device=dev)
+    r = torch.tensor([0, 0, 0, 1, 1, 2, 2], device=dev)
+    assert maxabs(FR.render_transmittance_from_alpha(a, ray_indices=r), [1.0, 0.6, 0.12, 1.0, 0.2, 1.0, 1.0]) <= 1e-6
+    w, tr = FR.render_weight_from_alpha(a, ray_indices=r)
+    assert maxabs(w, [0.4, 0.48, 0.012, 0.8, 0.02, 0.0, 0.9]) <= 1e-6
+    ts, te = torch.arange(7.0, device=dev), torch.arange(7.0, device=dev) + 1
+    w, tr, al = FR.render_weight_from_density(ts, te, a, ray_indices=r)
+    assert maxabs(tr, [1.00, 0.67, 0.30, 1.00, 0.45, 1.00, 1.00]) <= 5e-3
+    assert maxabs(al, [0.33, 0.55, 0.095, 0.55, 0.095, 0.00, 0.59]) <= 5e-3
+    assert maxabs(w, [0.33, 0.37, 0.03, 0.55, 0.04, 0.00, 0.59]) <= 5e-3
+    vis = FR.render_visibility_from_alpha(a, ray_indices=r, early_stop_eps=0.3, alpha_thre=0.2)
+    assert vis.tolist() == [True, True, False, True, False, False, True]
+    vis = FR.render_visibility_from_density(ts, te, a, ray_indices=r, early_stop_eps=0.3, alpha_thre=0.2)
+    assert vis.tolist() == [True, True, False, True, False, False, True]
+    with pytest.raises(ValueError):
+        FR.rendering(ts, te, r, 3)
+    with pytest.raises(AssertionError):
+        FR.rendering(ts, te[:3], r, 3, rgb_sigma_fn=lambda *a: None)
+
+
+def test_field_rendering_golden(dev, golden):
+    from quadraturefields_b200 import field_rendering as FR
+    g = golden("field_rendering")
+    c = lambda k: T(g[k]).to(dev)
+    ri, n = c("ray_indices"), len(g["counts"])
+    al, sg, ts, te, rgbs, pf = (c(k) for k in ("alphas", "sigmas", "t_starts", "t_ends", "rgbs", "prefix"))
+    tol = 2e-6
+    assert maxabs(FR.render_transmittance_from_alpha(al, ray_indices=ri, n_rays=n), g["T_alpha"]) <= tol
+    assert maxabs(FR.render_transmittance_from_alpha(al, ray_indices=ri, n_rays=n, prefix_trans=pf), g["T_alpha_prefix"]) <= tol
+    w, tr = FR.render_weight_from_alpha(al, ray_indices=ri, n_rays=n)
+    assert maxabs(w, g["w_alpha"]) <= tol
+    pk = FR.pack_info(ri, n)
+    assert pk[:, 1].tolist() == g["counts"].tolist()
+    w_pk, _ = FR.render_weight_from_alpha(al, packed_info=pk)
+    assert maxabs(w_pk, w) == 0.0
+    w, tr, a = FR.render_weight_from_density(ts, te, sg, ray_indices=ri, n_rays=n)
+    assert maxabs(w, g["w_density"]) <= tol and maxabs(tr, g["T_density"]) <= tol and maxabs(a, g["a_density"]) <= tol
+    w2, _, _ = FR.render_weight_from_density(ts, te, sg, ray_indices=ri, n_rays=n, prefix_trans=pf)
+    assert maxabs(w2, g["w_density_prefix"]) <= tol
+    assert np.array_equal(FR.render_visibility_from_alpha(al, ray_indices=ri, n_rays=n, early_stop_eps=0.3,
+                                                          alpha_thre=0.2).cpu().numpy(), g["vis_alpha"])
+    assert np.array_equal(FR.render_visibility_from_density(ts, te, sg, ray_indices=ri, n_rays=n, early_stop_eps=0.05,
+                                                            alpha_thre=0.3).cpu().numpy(), g["vis_density"])
+    assert maxabs(FR.accumulate_along_rays(w, rgbs, ri, n), g["acc_rgb"]) <= tol
+    assert maxabs(FR.accumulate_along_rays(w, None, ri, n), g["acc_w"]) <= tol
+    outb = torch.ones((n, 3), device=dev)
+    FR.accumulate_along_rays_(w, rgbs, ri, outb)
+    assert maxabs(outb - 1, g["acc_rgb"]) <= tol
+    col, op, dp, ex = FR.rendering(ts, te, ri, n, rgb_sigma_fn=lambda a, b, c_: (rgbs, sg), render_bkgd=c("bkgd"))
+    assert maxabs(col, g["rend_c"]) <= tol and maxabs(op, g["rend_o"]) <= tol and maxabs(dp, g["rend_d"]) <= 1e-5
+    assert set(ex) == {"weights", "alphas", "trans", "sigmas", "rgbs"}
+    col, op, dp, ex = FR.rendering(ts, te, ri, n, rgb_alpha_fn=lambda a, b, c_: (rgbs, al))
+    assert maxabs(col, g["renda_c"]) <= tol and maxabs(op, g["renda_o"]) <= tol and maxabs(dp, g["renda_d"]) <= 1e-5
+    col, op, dp, wf, wr = FR.rendering_field(ts, te, ri, n, rgb_sigma_fn=lambda a, b, c_: (rgbs, sg), render_bkgd=c("bkgd"))
+    assert maxabs(col, g["rf_c"]) <= tol and maxabs(wf, g["rf_w"]) <= tol
+    assert maxabs(wr, g["rf_wrev"]) <= tol                                       # quirk Q3 reproduced
+    # batched (n_rays, n_samples) layout
+    w, tr = FR.render_weight_from_alpha(c("b_alphas"))
+    assert maxabs(w, g["b_w_alpha"]) <= tol and maxabs(tr, g["b_T_alpha"]) <= tol
+    w, tr, a = FR.render_weight_from_density(c("b_ts"), c("b_te"), c("b_sigmas"))
+    assert maxabs(w, g["b_w_density"]) <= tol and maxabs(tr, g["b_T_density"]) <= tol and maxabs(a, g["b_a_density"]) <= tol
+    assert maxabs(FR.accumulate_along_rays(w, c("b_vals")), g["b_acc"]) <= 1e-5
+    # empty input
+    z = torch.zeros(0, device=dev)
+    col, op, dp, ex = FR.rendering(z, z, torch.zeros(0, dtype=torch.long, device=dev), 4, rgb_sigma_fn=lambda *a: None)
+    assert col.shape == (4, 3) and float(col.abs().sum()) == 0.0
+
+
+def test_field_rendering_long_rays_and_backward(dev):
+    """Segments longer than a warp (volumetric samples) and autograd w.r.t. sigmas / alphas / values."""
+    from quadraturefields_b200 import field_rendering as FR
+    g = torch.Generator().manual_seed(0)
+    counts = torch.tensor([0, 1, 31, 32, 33, 64, 100, 257, 0, 5])
+    n = len(counts)
+    ri = torch.repeat_interleave(torch.arange(n), counts)
+    M = int(counts.sum())
+    sg = torch.rand(M, generator=g) * 5
+    ts = torch.rand(M, generator=g).cumsum(0) * 0.01
+    te = ts + 0.004 + 0.002 * torch.rand(M, generator=g)
+    al = torch.rand(M, generator=g) * 0.6
+    vals = torch.rand(M, 3, generator=g)
+    gw, gT, gc = torch.randn(M, generator=g), torch.randn(M, generator=g), torch.randn(n, 3, generator=g)
+    # oracle (CPU, autograd through torch ops)
+    sg_r, al_r, v_r = sg.clone().requires_grad_(), al.clone().requires_grad_(), vals.clone().requires_grad_()
+    w_r, T_r, a_r = O.render_weight_from_density(ts, te, sg_r, ray_indices=ri, n_rays=n)
+    c_r = O.accumulate_along_rays(w_r, v_r, ri, n)
+    ((w_r * gw).sum() + (T_r * gT).sum() + (c_r * gc).sum()).backward()
+    wa_r, Ta_r = O.render_weight_from_alpha(al_r, ray_indices=ri, n_rays=n)
+    ((wa_r * gw).sum() + (Ta_r * gT).sum()).backward()
+    # device
+    d = lambda t: t.to(dev)
+    sg_d, al_d, v_d = d(sg).requires_grad_(), d(al).requires_grad_(), d(vals).requires_grad_()
+    w_d, T_d, a_d = FR.render_weight_from_density(d(ts), d(te), sg_d, ray_indices=d(ri), n_rays=n)
+    c_d = FR.accumulate_along_rays(w_d, v_d, d(ri), n)
+    ((w_d * d(gw)).sum() + (T_d * d(gT)).sum() + (c_d * d(gc)).sum()).backward()
+    wa_d, Ta_d = FR.render_weight_from_alpha(al_d, ray_indices=d(ri), n_rays=n)
+    ((wa_d * d(gw)).sum() + (Ta_d * d(gT)).sum()).backward()
+    assert maxabs(w_d, w_r) <= 1e-5 and maxabs(T_d, T_r) <= 1e-5 and maxabs(wa_d, wa_r) <= 1e-5
+    assert maxabs(c_d, c_r) <= 1e-4
+    scale = float(sg_r.grad.abs().max())
+    assert maxabs(sg_d.grad, sg_r.grad) <= 1e-4 * max(scale, 1.0)
+    assert maxabs(v_d.grad, v_r.grad) <= 1e-5
+    assert maxabs(al_d.grad, al_r.grad) <= 1e-4 * max(float(al_r.grad.abs().max()), 1.0)
+
+
+# ----------------------------------------------------------------------------- fused render vs oracle
+@pytest.mark.parametrize("bg", ["white", "black", "random"])
+def test_fused_render_smoke_scene(dev, smoke_scene, bg):
+    sc = smoke_scene
+    o, d = _rays_for(sc, 0)
+    bk = torch.tensor([0.3, 0.6, 0.1])
+    ref = O.render_mesh_ngp(o, d, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K, bg_color=bg, render_bkgd=bk)
+    out = sc.render(T(o).to(dev), T(d).to(dev), bg_color=bg, render_bkgd=bk.to(dev))
+    assert int(out["n_hits"]) == ref["index_ray"].shape[0]
+    assert maxabs(out["rgb"], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"], ref["opacity"]) <= TOL_IMG
+    assert maxabs(out["depth"], ref["depth"]) <= 2e-3
+    target = torch.rand(ref["rgb"].shape, generator=torch.Generator().manual_seed(0))
+    assert psnr_delta_db(out["rgb"].cpu(), ref["rgb"], target) <= 0.05
+    miss = torch.ones(sc.W * sc.H, dtype=torch.bool)
+    miss[ref["index_ray"]] = False
+    fill = 0.0 if bg == "black" else 1.0
+    assert miss.any() and bool((out["rgb"].cpu()[miss] == fill).all()) and bool((out["opacity"].cpu()[miss] == 0).all())
+
+
+def test_tuple_driver_matches_fused_and_oracle(dev, smoke_scene):
+    """utils.py:465-607 surface (tuple in, 9-tuple out) vs the fused render vs the oracle."""
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.utils import render_image_finetune_with_occgrid as drv
+    sc = smoke_scene
+    o, d = _rays_for(sc, 1)
+    ref = O.render_mesh_ngp(o, d, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
+    tup = sc.mesh_intersect.sampling_raytrace(T(d), T(o))
+    data = [tup[0], tup[1], tup[2], tup[3], tup[4], tup[6]]
+    rays = Rays(T(o).reshape(sc.H, sc.W, 3), T(d).reshape(sc.H, sc.W, 3))
+    rgb, op, depth, n_samples, weights, points, index_ray, loss, index_tri = drv(
+        sc.radiance_field, None, None, rays, data, mesh_intersect=sc.mesh_intersect, scaling=0.0)
+    assert rgb.shape == (sc.H, sc.W, 3) and n_samples == ref["index_ray"].shape[0]
+    assert maxabs(rgb.reshape(-1, 3), ref["rgb"]) <= TOL_IMG and maxabs(op.reshape(-1, 1), ref["opacity"]) <= TOL_IMG
+    assert torch.equal(index_ray.cpu(), ref["index_ray"]) and torch.equal(index_tri.cpu(), ref["index_tri"])
+    assert maxabs(weights, ref["weights"]) <= 2e-4
+    fused = sc.render(T(o).to(dev), T(d).to(dev))
+    assert maxabs(fused["rgb"], rgb.reshape(-1, 3)) <= 1e-6 and maxabs(fused["depth"], depth.reshape(-1, 1)) <= 1e-6
+
+
+def test_fused_render_c1_reference_config(dev):
+    """BASELINE.json configs[0]: 20 480-triangle mesh, T=2^19 field, 100x100 rays, K=8 — against the oracle."""
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c1", device=dev)
+    assert sc.faces_np.shape[0] == 20480 and sc.n_rays == 10000
+    o, d = _rays_for(sc, 0)
+    ref = O.render_mesh_ngp(o, d, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
+    out = sc.render(T(o).to(dev), T(d).to(dev))
+    assert int(out["n_hits"]) == ref["index_ray"].shape[0] > 10000
+    assert maxabs(out["rgb"], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"], ref["opacity"]) <= TOL_IMG
+    tri, _, count = sc.mesh_intersect.rayintersector.trace(T(o), T(d), sc.K)
+    tri_ref, _, count_ref, _ = O.intersect_firstk(o, d, sc.vertices_np, sc.faces_np, sc.K)
+    assert np.array_equal(tri.cpu().numpy(), tri_ref) and np.array_equal(count.cpu().numpy(), count_ref)
+    assert count_ref.max() == 8
+
+
+# ----------------------------------------------------------------------------- full-size properties (BASELINE configs[1])
+def test_full_size_properties_c2(dev):
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c2", device=dev)
+    o, d = sc.rays(3)
+    out = {k: v.clone() for k, v in sc.render(o, d).items()}
+    N = sc.n_rays
+    assert N == 640000 and out["rgb"].shape == (N, 3)
+    assert bool(((out["opacity"] >= 0) & (out["opacity"] <= 1 + 1e-5)).all())                  # sum of weights <= 1
+    assert bool(((out["rgb"] >= -1e-6) & (out["rgb"] <= 1 + 1e-5)).all())
+    tri, t, count = sc.mesh_intersect.rayintersector.trace(o, d, sc.K)
+    assert int(count.sum()) == int(out["n_hits"])
+    miss = count == 0
+    assert bool((out["rgb"][miss] == 1).all()) and bool((out["depth"][miss] == 0).all()) and 0.3 < float(miss.float().mean()) < 0.8
+    # permuting the rays permutes the outputs (rays are independent units; sharding relies on this)
+    perm = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    out_p = sc.render(o[perm], d[perm])
+    assert torch.equal(out_p["rgb"], out["rgb"][perm]) and torch.equal(out_p["opacity"], out["opacity"][perm])
+    # a slice rendered alone equals the same slice of the full frame (what each rank does in the N-GPU bench)
+    lo, hi = N // 4, N // 2
+    out_s = sc.render(o[lo:hi].contiguous(), d[lo:hi].contiguous())
+    assert torch.equal(out_s["rgb"], out["rgb"][lo:hi]) and torch.equal(out_s["depth"], out["depth"][lo:hi])
+    # subsampled oracle check at full mesh / table size
+    sub = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:1500]
+    ref = O.render_mesh_ngp(o.cpu().numpy()[sub], d.cpu().numpy()[sub], sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
+    assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
