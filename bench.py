@@ -183,9 +183,11 @@ def run_ours(args):
     out = dict(rgb=torch.empty((N, 3), device=dev), opacity=torch.empty((N, 1), device=dev), depth=torch.empty((N, 1), device=dev))
     view_of = lambda step: (step * world + rank) % n_views
 
+    hit_slots = torch.zeros((args.warmup + args.steps, 1), dtype=torch.int32, device=dev)   # one slot per step, written by the kernel
+
     def step_resident(i):
         o, d = rays[view_of(i)]
-        sc.render(o, d, out=out)
+        sc.render(o, d, out=out, hits_out=hit_slots[i])
 
     def barrier():
         if world > 1:
@@ -198,12 +200,10 @@ def run_ours(args):
     clocks = ClockSampler(local) if rank == 0 else None
     lib.qf_profile_enable(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    hits_acc = torch.zeros((), dtype=torch.int64, device=dev)
     barrier()
     ev0.record()
     for i in range(args.steps):
         step_resident(args.warmup + i)
-        hits_acc += out["n_hits"][0]
     if world > 1:  # the final image gather (north star): last frame of every rank to rank 0
         frame = torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1)
         gathered = [torch.empty_like(frame) for _ in range(world)] if rank == 0 else None
@@ -216,6 +216,7 @@ def run_ours(args):
     nch = C.c_int64()
     _lib.check(lib.qf_profile_read(ms3, C.byref(nch)), "qf_profile_read")
     lib.qf_profile_enable(0)
+    hits_acc = hit_slots[args.warmup:].to(torch.int64).sum().reshape(1)
     total_hits = hits_acc.clone()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -247,7 +247,7 @@ __global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, int n, co
   nodes[3] = make_float4(__int_as_float(make_leaf_ref(0, n)), __int_as_float(kEmptyRef), 0.f, 0.f);
 }
 
-template <int KMAX>
+template <int KMAX, bool COUNT_ALL>
 __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                     const float* __restrict__ scene, const float* __restrict__ origins,
                                                     const float* __restrict__ dirs, int64_t N, int K,
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
   Ray r = make_ray(origins, dirs, i);
   HitBuf<KMAX> hb;
   int total;
-  traverse<KMAX>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
+  traverse<KMAX, !COUNT_ALL>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
     if (s < K) {
@@ -461,9 +461,11 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   if (n_rays == 0) return QF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)ceil_div(n_rays, 128);
-  if (K <= 8) trace_kernel<8><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
-  else if (K <= 16) trace_kernel<16><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
-  else trace_kernel<32><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total);
+#define QF_TRACE(KM, ALL) trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total)
+  // the untruncated total needs a traversal without distance culling
+  if (d_total) { if (K <= 8) QF_TRACE(8, true); else if (K <= 16) QF_TRACE(16, true); else QF_TRACE(32, true); }
+  else { if (K <= 8) QF_TRACE(8, false); else if (K <= 16) QF_TRACE(16, false); else QF_TRACE(32, false); }
+#undef QF_TRACE
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

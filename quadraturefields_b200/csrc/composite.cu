@@ -286,8 +286,8 @@ extern "C" int qf_accumulate_along_rays(const float* d_weights, const float* d_v
 extern "C" int qf_accumulate_along_rays_indexed(const float* d_weights, const float* d_values, int D,
                                                 const int64_t* d_ray_indices, int64_t n_samples, float* d_out,
                                                 void* stream) {
-  QF_REQUIRE(d_weights && d_ray_indices && d_out && D >= 1, "qf_accumulate_along_rays_indexed: bad argument");
   if (n_samples == 0) return QF_OK;
+  QF_REQUIRE(d_weights && d_ray_indices && d_out && D >= 1, "qf_accumulate_along_rays_indexed: bad argument");
   accumulate_indexed_kernel<<<(int)ceil_div(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(d_weights, d_values, D, d_ray_indices, n_samples, d_out);
   QF_LAUNCH_CHECK();
   return QF_OK;
@@ -296,8 +296,8 @@ extern "C" int qf_accumulate_along_rays_indexed(const float* d_weights, const fl
 extern "C" int qf_accumulate_along_rays_backward(const float* d_weights, const float* d_values, int D,
                                                  const int64_t* d_ray_indices, int64_t n_samples, const float* d_grad_out,
                                                  float* d_grad_weights, float* d_grad_values, void* stream) {
-  QF_REQUIRE(d_weights && d_ray_indices && d_grad_out && D >= 1, "qf_accumulate_along_rays_backward: bad argument");
   if (n_samples == 0) return QF_OK;
+  QF_REQUIRE(d_weights && d_ray_indices && d_grad_out && D >= 1, "qf_accumulate_along_rays_backward: bad argument");
   accumulate_bwd_kernel<<<(int)ceil_div(n_samples, 256), 256, 0, (cudaStream_t)stream>>>(
       d_weights, d_values, D, d_ray_indices, n_samples, d_grad_out, d_grad_weights, d_grad_values);
   QF_LAUNCH_CHECK();

@@ -264,6 +264,13 @@ extern "C" int qf_generate_rays(const float* c, int W, int H, float focal, float
 
 extern "C" int qf_profile_enable(int on) {
   g_prof.enabled = on != 0;
+  if (on) {  // create the events up front so that recording inside a timed region does no driver allocation
+    while (g_prof.pool.size() < 4096) {
+      cudaEvent_t e;
+      QF_CUDA_CHECK(cudaEventCreate(&e));
+      g_prof.pool.push_back(e);
+    }
+  }
   return QF_OK;
 }
 

@@ -49,7 +49,7 @@ __device__ __forceinline__ void leaf_intersect(const Ray& r, const float4* __res
   }
 }
 
-template <int KMAX>
+template <int KMAX, bool CULL = true>
 __device__ __forceinline__ void traverse(const Ray& r, const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                          float pad, int K, HitBuf<KMAX>& hb, int& total) {
   int stack[128];  // depth <= 64 key bits + 32 index bits
@@ -66,7 +66,8 @@ __device__ __forceinline__ void traverse(const Ray& r, const float4* __restrict_
     float tn0, tf0, tn1, tf1;
     // K-th smallest t so far (+inf until the buffer is full: unused slots stay +inf)
     float tcull = hb.t[KMAX - 1];
-    if (K < KMAX) {
+    if (!CULL) tcull = __int_as_float(0x7f800000);   // counting every hit: no distance culling
+    else if (K < KMAX) {
 #pragma unroll
       for (int s = 0; s < KMAX - 1; ++s) if (s == K - 1) tcull = hb.t[s];
     }

@@ -92,8 +92,10 @@ class MeshRenderer:
         self._hits = torch.zeros((1,), dtype=torch.int32, device=self.device)
 
     @torch.no_grad()
-    def render(self, origins: torch.Tensor, viewdirs: torch.Tensor, bg_color="white", render_bkgd=None, out=None):
-        """-> dict(rgb (N,3), opacity (N,1), depth (N,1), n_hits (device int32 tensor))."""
+    def render(self, origins: torch.Tensor, viewdirs: torch.Tensor, bg_color="white", render_bkgd=None, out=None,
+               hits_out: Optional[torch.Tensor] = None):
+        """-> dict(rgb (N,3), opacity (N,1), depth (N,1), n_hits (device int32 tensor)).
+        `hits_out`: optional 1-element int32 CUDA tensor (e.g. a slot of a per-step buffer) receiving the hit count."""
         lib = _lib.load()
         dev = self.device
         o = _lib.f32(origins.reshape(-1, 3), dev)
@@ -109,17 +111,18 @@ class MeshRenderer:
         bg = _lib.BG_MODES.get(bg_color, 2)
         st = _lib.stream(dev)
         mesh = self.mi.rayintersector.handle
+        hits = self._hits if hits_out is None else hits_out
         if self.compressor is not None:
             _lib.check(lib.qf_render_mesh_baked(mesh, self.compressor.native(), _lib.ptr(self.uv), _lib.ptr(o), _lib.ptr(d), N,
                                                 self.K, self.delta, bg, _lib.ptr(bk), _lib.ptr(out["rgb"]),
-                                                _lib.ptr(out["opacity"]), _lib.ptr(out["depth"]), _lib.ptr(self._hits),
+                                                _lib.ptr(out["opacity"]), _lib.ptr(out["depth"]), _lib.ptr(hits),
                                                 _lib.ptr(ws), ws.numel(), st), "qf_render_mesh_baked")
         else:
             _lib.check(lib.qf_render_mesh_ngp(mesh, self.field._native(), _lib.ptr(o), _lib.ptr(d), N, self.K, self.delta, bg,
                                               _lib.ptr(bk), _lib.ptr(out["rgb"]), _lib.ptr(out["opacity"]),
-                                              _lib.ptr(out["depth"]), _lib.ptr(self._hits), _lib.ptr(ws), ws.numel(), st),
+                                              _lib.ptr(out["depth"]), _lib.ptr(hits), _lib.ptr(ws), ws.numel(), st),
                        "qf_render_mesh_ngp")
-        out["n_hits"] = self._hits
+        out["n_hits"] = hits
         return out
 
 

@@ -1,0 +1,58 @@
+"""Summarise gpurun_out/prof_<tag>.ncu-rep and launches_<tag>.csv into profiles/<tag>_*.  Run in the build container."""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+tag = sys.argv[1]
+out_md = f"profiles/{tag}_ncu_summary.md"
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
+lines = [f"# ncu summary `{tag}`", "",
+         "Source: `ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --views 8 "
+         "--no-cpu-baseline` (B200, one GPU).  Per-launch values; cold-cache, serialised — compare shares, not absolutes.", ""]
+raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+if rows:
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    seen = set()
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0]
+        if name in seen:
+            continue
+        seen.add(name)
+        lines += [f"## `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
+        for w in WANT:
+            if w in idx:
+                lines.append(f"| {w} | {r[idx[w]]} | {units[idx[w]]} |")
+        lines.append("")
+try:
+    rows = list(csv.DictReader(l for l in open(f"gpurun_out/launches_{tag}.csv") if l.startswith('"')))
+    agg = collections.OrderedDict()
+    for r in rows:
+        k = r["Kernel Name"].split("(")[0]
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r["Metric Value"]) / 1e3
+    lines += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`)", "",
+              "| kernel | launches | total us | us / launch |", "|---|---|---|---|"]
+    for k, (n, t) in agg.items():
+        lines.append(f"| `{k[:90]}` | {n} | {t:.1f} | {t / n:.1f} |")
+    step = {k: v for k, v in agg.items() if any(s in k for s in ("trace_compact", "ngp_forward", "composite_rays", "baked_shade"))}
+    tot = sum(v[1] for v in step.values())
+    lines += ["", "Share of one render step: " + ", ".join(f"`{k.split('::')[-1][:30]}` {100 * v[1] / tot:.1f}%" for k, v in step.items()), ""]
+    with open(f"profiles/{tag}_launches.csv", "w") as f:
+        f.write(open(f"gpurun_out/launches_{tag}.csv").read())
+except FileNotFoundError:
+    pass
+open(out_md, "w").write("\n".join(lines))
+print("wrote", out_md)
