@@ -186,15 +186,17 @@ int qf_pack_info(const int64_t* d_ray_indices, int64_t n_samples, int64_t n_rays
 /* ------------------------------------------------------------------------------------------
  * Fused frame render: rays -> image, everything resident (utils.py:465-607 with scaling=0, and
  * utils.py:998-1095).  Outputs rgb (N,3), alpha (N,1), depth (N,1); d_hits_total (1 x int32, may be NULL)
- * receives the number of hit samples shaded.
+ * receives the number of hit samples shaded.  image_width > 0 declares the rays row-major image-ordered (the
+ * reference passes (H,W,3) ray tensors, utils.py:489-495): warps then take 8x4 pixel tiles; 0 = plain ray list.
+ * Results do not depend on it.
  * ------------------------------------------------------------------------------------------ */
 size_t qf_render_workspace_bytes(int64_t n_rays, int K);
 int qf_render_mesh_ngp(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
-                       int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
+                       int64_t n_rays, int image_width, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
                        float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
                        size_t workspace_bytes, void* stream);
 int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled,
-                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta,
+                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta,
                          int bg_mode, const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth,
                          int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
 

@@ -193,7 +193,7 @@ def _ray_tri_block(o, d, v0, e1, e2, lo, hi):
         az0, az1 = (lo[..., 2] - oz) * idz, (hi[..., 2] - oz) * idz
         tn = np.fmax(np.fmax(np.fmin(ax0, ax1), np.fmin(ay0, ay1)), np.fmax(np.fmin(az0, az1), F32(0.0)))
         tf = np.fmin(np.fmin(np.fmax(ax0, ax1), np.fmax(ay0, ay1)), np.fmax(az0, az1))
-        hit &= (tn <= tf) & (t >= tn) & (t <= tf)
+        hit &= (tn <= tf) & (t >= tn)
     return hit, t
 
 

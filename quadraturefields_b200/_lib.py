@@ -59,8 +59,8 @@ _SIGS = {
     "qf_pack_info_workspace_bytes": (_SZ, [_L]),
     "qf_pack_info": (_I, [_P, _L, _L, _P, _P, _SZ, _P]),
     "qf_render_workspace_bytes": (_SZ, [_L, _I]),
-    "qf_render_mesh_ngp": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
-    "qf_render_mesh_baked": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_render_mesh_ngp": (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_render_mesh_baked": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_profile_enable": (_I, [_I]),
     "qf_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(_L)]),
     "qf_generate_rays": (_I, [C.POINTER(_F), _I, _I, _F, _F, _F, _I, _P, _P, _P]),

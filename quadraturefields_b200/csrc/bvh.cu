@@ -2,9 +2,10 @@
 //
 // Replaces the OptiX `intersector.Intersector` pybind object (mesh_utils.py:77-96) and the Embree
 // default (mesh_utils.py:223,350-354).  B200 has no RT cores, so traversal is a software
-// while-while loop on the SMs: 64-byte two-child nodes fetched as 4 x LDG.128 through the
-// read-only path, Morton-ordered 48-byte triangle records, a per-ray sorted K-buffer held in
-// registers, and the K-th hit's t used as the culling distance once the buffer is full.
+// loop on the SMs (traverse.cuh): 64-byte two-child nodes fetched as 4 x LDG.128 through the read-only
+// path, one triangle per leaf so that the child box in the parent IS the triangle's padded box,
+// Morton-ordered 48-byte triangle records, a per-ray sorted K-buffer held in registers, and the
+// K-th hit's t used as the culling distance once the buffer is full.  Coherent warps traverse as a packet.
 //
 // Exactness: a node is entered iff the fp32 slab test of its box passes; the triangle predicate
 // contains the same slab test on the triangle's own padded box, and node boxes are exact unions
@@ -201,77 +202,66 @@ __global__ void fit_kernel(const float4* __restrict__ tris, int n, const float* 
   }
 }
 
-// final 64-byte traversal nodes; subtrees of <= kLeafMax triangles collapse into one leaf reference
+// final 64-byte traversal nodes: both children's boxes + references (leaf = one triangle)
 __global__ void emit_nodes_kernel(const float4* __restrict__ tris, int n, const float* __restrict__ scene,
                                   const int* __restrict__ left, const int* __restrict__ right,
-                                  const int* __restrict__ first, const int* __restrict__ last,
                                   const float4* __restrict__ ibox, float4* __restrict__ nodes) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   float pad = scene[6];
   int refs[2] = {left[i], right[i]};
   float lo[2][3], hi[2][3];
-  int out[2];
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     int r = refs[c];
-    if (r < 0) {
-      tri_box(tris, ~r, pad, lo[c], hi[c]);
-      out[c] = make_leaf_ref(~r, 1);
-    } else {
+    if (r < 0) tri_box(tris, ~r, pad, lo[c], hi[c]);
+    else {
       float4 a = ibox[2 * (int64_t)r], b = ibox[2 * (int64_t)r + 1];
       lo[c][0] = a.x; lo[c][1] = a.y; lo[c][2] = a.z; hi[c][0] = b.x; hi[c][1] = b.y; hi[c][2] = b.z;
-      int cnt = last[r] - first[r] + 1;
-      out[c] = cnt <= kLeafMax ? make_leaf_ref(first[r], cnt) : r;
     }
   }
   nodes[4 * (int64_t)i + 0] = make_float4(lo[0][0], lo[0][1], lo[0][2], hi[0][0]);
   nodes[4 * (int64_t)i + 1] = make_float4(hi[0][1], hi[0][2], lo[1][0], lo[1][1]);
   nodes[4 * (int64_t)i + 2] = make_float4(lo[1][2], hi[1][0], hi[1][1], hi[1][2]);
-  nodes[4 * (int64_t)i + 3] = make_float4(__int_as_float(out[0]), __int_as_float(out[1]), 0.f, 0.f);
+  nodes[4 * (int64_t)i + 3] = make_float4(__int_as_float(refs[0]), __int_as_float(refs[1]), 0.f, 0.f);
 }
 
-// meshes of 1..kLeafMax triangles: one root whose first child is the only leaf
-__global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, int n, const float* __restrict__ scene,
+// single-triangle mesh: a root whose first child is that triangle
+__global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, const float* __restrict__ scene,
                                       float4* __restrict__ nodes) {
-  float pad = scene[6];
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int k = 0; k < n; ++k) {
-    float cl[3], ch[3];
-    tri_box(tris, k, pad, cl, ch);
-    for (int q = 0; q < 3; ++q) { lo[q] = fminf(lo[q], cl[q]); hi[q] = fmaxf(hi[q], ch[q]); }
-  }
+  float lo[3], hi[3];
+  tri_box(tris, 0, scene[6], lo, hi);
   nodes[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
   nodes[1] = make_float4(hi[1], hi[2], 0.f, 0.f);
   nodes[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-  nodes[3] = make_float4(__int_as_float(make_leaf_ref(0, n)), __int_as_float(kEmptyRef), 0.f, 0.f);
+  nodes[3] = make_float4(__int_as_float(~0), __int_as_float(kEmptyRef), 0.f, 0.f);
 }
 
 template <int KMAX, bool COUNT_ALL>
 __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                    const float* __restrict__ scene, const float* __restrict__ origins,
-                                                    const float* __restrict__ dirs, int64_t N, int K,
-                                                    int32_t* __restrict__ out_tri, float* __restrict__ out_t,
-                                                    int32_t* __restrict__ out_count, int32_t* __restrict__ out_total) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  Ray r = make_ray(origins, dirs, i);
+                                                    const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                    int64_t N, int K, int32_t* __restrict__ out_tri,
+                                                    float* __restrict__ out_t, int32_t* __restrict__ out_count,
+                                                    int32_t* __restrict__ out_total) {
+  __shared__ int s_stack[4][kStackDepth];
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = i < N;
+  Ray r = make_ray(origins, dirs, valid ? i : N - 1);
   HitBuf<KMAX> hb;
   int total;
-  traverse<KMAX, !COUNT_ALL>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
+  trace_ray<KMAX, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
+  if (!valid) return;
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
-    if (s < K) {
-      out_tri[i * K + s] = hb.id[s];
-      if (out_t) out_t[i * K + s] = hb.t[s];
+    if (s >= KMAX - K) {
+      const bool hit = hb.t[s] != __int_as_float(0x7f800000);
+      out_tri[i * K + s - (KMAX - K)] = hit ? hb.id[s] : -1;
+      if (out_t) out_t[i * K + s - (KMAX - K)] = hb.t[s];
     }
   }
-  out_count[i] = hb.cnt;
+  out_count[i] = hb.count(K);
   if (out_total) out_total[i] = total;
 }
-
-// Note on the swap above: when both children are hit and child 1 is nearer, r0/r1 are swapped but
-// h0/h1 are both true, so the flags stay valid.
 
 // ---------------------------------------------------------------- tuple packing (a3)
 // thread per ray: plane-hit points, normalised dirs, depth, stable insertion sort by depth, ray-major write
@@ -345,8 +335,8 @@ static int build(qf_mesh* m, cudaStream_t st) {
                                                 m->d_idx_sorted, (int)F, 0, 63, st));
   tri_gather_kernel<<<blocks, 256, 0, st>>>(m->d_vertices, m->d_faces, F, m->d_idx_sorted, m->d_tris);
   QF_LAUNCH_CHECK();
-  if (F <= kLeafMax) {
-    emit_tiny_root_kernel<<<1, 1, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_nodes);
+  if (F == 1) {
+    emit_tiny_root_kernel<<<1, 1, 0, st>>>(m->d_tris, m->d_scene, m->d_nodes);
     QF_LAUNCH_CHECK();
     m->n_nodes = 1;
   } else {
@@ -355,8 +345,7 @@ static int build(qf_mesh* m, cudaStream_t st) {
                                           m->d_leaf_parent, m->d_first, m->d_last);
     fit_kernel<<<blocks, 256, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_parent,
                                        m->d_leaf_parent, m->d_flags, m->d_ibox);
-    emit_nodes_kernel<<<blocks, 256, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_first,
-                                              m->d_last, m->d_ibox, m->d_nodes);
+    emit_nodes_kernel<<<blocks, 256, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_ibox, m->d_nodes);
     QF_LAUNCH_CHECK();
     m->n_nodes = F - 1;
   }
@@ -461,7 +450,7 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   if (n_rays == 0) return QF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)ceil_div(n_rays, 128);
-#define QF_TRACE(KM, ALL) trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, m->d_scene, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total)
+#define QF_TRACE(KM, ALL) trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total)
   // the untruncated total needs a traversal without distance culling
   if (d_total) { if (K <= 8) QF_TRACE(8, true); else if (K <= 16) QF_TRACE(16, true); else QF_TRACE(32, true); }
   else { if (K <= 8) QF_TRACE(8, false); else if (K <= 16) QF_TRACE(16, false); else QF_TRACE(32, false); }

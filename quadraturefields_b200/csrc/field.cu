@@ -52,47 +52,77 @@ __global__ void prep_table_kernel(const float* __restrict__ t, int64_t n_entries
 }
 
 // ---- hash-grid encode of one point: 16 levels, trilinear, fp32 interpolation, fp16 result
-struct Enc { uint32_t h[QF_MAX_LEVELS]; };  // packed half2 per level
+// The level loop is kept ROLLED (two levels per trip, the gathers of both issued before either is consumed):
+// fully unrolled it is ~13k instructions and the kernel stalls on instruction fetch.
+struct Corner8 { uint32_t idx[8]; float fx, fy, fz; };
 
-__device__ __forceinline__ Enc encode_point(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
-                                            float z) {
-  Enc e;
+__device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, float x, float y, float z, Corner8& c) {
+  const float scale = d.scale[l];
+  const uint32_t res = d.resolution[l], size = d.size[l];
+  float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
+  const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
+  const uint32_t cx = (uint32_t)(int)flx, cy = (uint32_t)(int)fly, cz = (uint32_t)(int)flz;
+  c.fx = px - flx; c.fy = py - fly; c.fz = pz - flz;
+  if (d.hashed[l]) {   // hashed levels always have size == 2^log2_hashmap_size
+    const uint32_t mask = size - 1;
+    const uint32_t y0 = cy * 2654435761u, y1 = (cy + 1) * 2654435761u, z0 = cz * 805459861u, z1 = (cz + 1) * 805459861u;
 #pragma unroll
-  for (int l = 0; l < QF_MAX_LEVELS; ++l) {
-    if (l >= d.n_levels) { e.h[l] = 0u; continue; }
-    const float scale = d.scale[l];
-    const uint32_t res = d.resolution[l], size = d.size[l];
-    const bool hashed = d.hashed[l] != 0;
-    const bool pow2 = (size & (size - 1)) == 0;
-    float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
-    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
-    uint32_t cx = (uint32_t)(int)fx, cy = (uint32_t)(int)fy, cz = (uint32_t)(int)fz;
-    px -= fx; py -= fy; pz -= fz;
-    const __half2* lvl = table + d.offset[l];
-    __half2 v[8];
+    for (int k = 0; k < 8; ++k) c.idx[k] = ((cx + (k & 1)) ^ ((k & 2) ? y1 : y0) ^ ((k & 4) ? z1 : z0)) & mask;
+  } else {
+    const uint32_t sy = res, sz = res * res;
+    bool wrap = false;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      uint32_t gx = cx + (c & 1), gy = cy + ((c >> 1) & 1), gz = cz + ((c >> 2) & 1);
-      uint32_t idx = hashed ? (gx ^ (gy * 2654435761u) ^ (gz * 805459861u)) : (gx + gy * res + gz * (res * res));
-      idx = pow2 ? (idx & (size - 1)) : (idx >= size ? idx % size : idx);
-      v[c] = __ldg(lvl + idx);
+    for (int k = 0; k < 8; ++k) {
+      c.idx[k] = (cx + (k & 1)) + (cy + ((k >> 1) & 1)) * sy + (cz + ((k >> 2) & 1)) * sz;
+      wrap |= c.idx[k] >= size;
     }
-    float r0 = 0.f, r1 = 0.f;
+    if (wrap) {   // upper box faces and points outside the aabb wrap exactly like tcnn (index % level size)
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float w = ((c & 1) ? px : 1.f - px) * ((c & 2) ? py : 1.f - py);
-      w *= (c & 4) ? pz : 1.f - pz;
-      float2 f = __half22float2(v[c]);
-      r0 = __fadd_rn(r0, __fmul_rn(w, f.x));   // separately rounded like the oracle: the encoding is bit-exact
-      r1 = __fadd_rn(r1, __fmul_rn(w, f.y));
+      for (int k = 0; k < 8; ++k) c.idx[k] %= size;
     }
-    __half2 hv = __floats2half2_rn(r0, r1);
-    e.h[l] = *reinterpret_cast<uint32_t*>(&hv);
   }
-  return e;
 }
-// The weight of corner c is ((wx*wy)*wz) in the oracle's order: w starts at 1 and is multiplied by the
+
+__device__ __forceinline__ uint32_t level_blend(const Corner8& c, const __half2* v) {
+  float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
+    w *= (k & 4) ? c.fz : 1.f - c.fz;
+    float2 f = __half22float2(v[k]);
+    r0 = __fadd_rn(r0, __fmul_rn(w, f.x));   // separately rounded like the oracle: the encoding is bit-exact
+    r1 = __fadd_rn(r1, __fmul_rn(w, f.y));
+  }
+  __half2 hv = __floats2half2_rn(r0, r1);
+  return *reinterpret_cast<uint32_t*>(&hv);
+}
+// The weight of corner k is ((wx*wy)*wz) in the oracle's order: w starts at 1 and is multiplied by the
 // x, y, z factors in turn; (1*wx)*wy*wz == (wx*wy)*wz exactly.
+
+// writes 2 halves per level to out[2*l] (shared-memory row of the sample, or a local array)
+template <typename Store>
+__device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
+                                             float z, Store store) {
+  const int L = d.n_levels;
+#pragma unroll 1
+  for (int l = 0; l < L; l += 2) {
+    Corner8 c0, c1;
+    __half2 v0[8], v1[8];
+    level_indices(d, l, x, y, z, c0);
+    const __half2* t0 = table + d.offset[l];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v0[k] = __ldg(t0 + c0.idx[k]);
+    const bool two = l + 1 < L;
+    if (two) {
+      level_indices(d, l + 1, x, y, z, c1);
+      const __half2* t1 = table + d.offset[l + 1];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v1[k] = __ldg(t1 + c1.idx[k]);
+    }
+    store(l, level_blend(c0, v0));
+    if (two) store(l + 1, level_blend(c1, v1));
+  }
+}
 
 __device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
   float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
@@ -158,7 +188,7 @@ struct FieldArgs {
 };
 
 template <int MODE>  // 0: full forward (rgb + sigma); 1: density + geo features only
-__global__ void __launch_bounds__(128, 3) ngp_forward_kernel(const FieldArgs a) {
+__global__ void __launch_bounds__(128, 5) ngp_forward_kernel(const FieldArgs a) {
   __shared__ __align__(16) __half s_w[kWTotal];
   __shared__ __align__(16) __half s_tile[4][32 * kTileStride];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -186,10 +216,9 @@ __global__ void __launch_bounds__(128, 3) ngp_forward_kernel(const FieldArgs a) 
       z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
       sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
     }
-    Enc e = encode_point(a.desc, a.table, x, y, z);
-    uint4* row = reinterpret_cast<uint4*>(tile + lane * kTileStride);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) row[q] = make_uint4(e.h[4 * q], e.h[4 * q + 1], e.h[4 * q + 2], e.h[4 * q + 3]);
+    uint32_t* row32 = reinterpret_cast<uint32_t*>(tile + lane * kTileStride);
+    encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) { row32[l] = h2; });
+    uint4* row = reinterpret_cast<uint4*>(row32);
     if (MODE == 0) {
       float dx = 0.f, dy = 0.f, dz = 1.f;
       if (valid) {
@@ -327,13 +356,13 @@ __global__ void hashgrid_forward_kernel(const qf_grid_desc desc, const __half2* 
                                         const float* __restrict__ x01, int64_t M, float* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M) return;
-  Enc e = encode_point(desc, table, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2]);
   const int L = desc.n_levels;
-  for (int l = 0; l < L; ++l) {
-    float2 f = __half22float2(*reinterpret_cast<__half2*>(&e.h[l]));
-    out[i * 2 * L + 2 * l] = f.x;
-    out[i * 2 * L + 2 * l + 1] = f.y;
-  }
+  float* o = out + i * 2 * L;
+  encode_point(desc, table, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], [&](int l, uint32_t h2) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&h2));
+    o[2 * l] = f.x;
+    o[2 * l + 1] = f.y;
+  });
 }
 
 int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {

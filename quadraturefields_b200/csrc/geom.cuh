@@ -34,9 +34,12 @@ __device__ __forceinline__ bool slab(const Ray& r, float lx, float ly, float lz,
 __device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// Möller–Trumbore + the ray-vs-own-padded-box test.  Returns true and t on a hit.
-__device__ __forceinline__ bool ray_triangle(const Ray& r, float v0x, float v0y, float v0z, float v1x, float v1y,
-                                             float v1z, float v2x, float v2y, float v2z, float pad, float& t_out) {
+// Möller–Trumbore.  The full hit predicate is
+//     mt_hit  AND  slab(ray, padded box of the triangle) passes  AND  t >= tn of that slab test.
+// In the BVH the padded triangle box IS the child box stored in the parent node, so the slab part has already
+// been evaluated (bit-identically) when a leaf reference is reached; `tn` travels with the reference.
+__device__ __forceinline__ bool ray_triangle_mt(const Ray& r, float v0x, float v0y, float v0z, float v1x, float v1y,
+                                                float v1z, float v2x, float v2y, float v2z, float tn, float& t_out) {
   float e1x = __fsub_rn(v1x, v0x), e1y = __fsub_rn(v1y, v0y), e1z = __fsub_rn(v1z, v0z);
   float e2x = __fsub_rn(v2x, v0x), e2y = __fsub_rn(v2y, v0y), e2z = __fsub_rn(v2z, v0z);
   float px = __fsub_rn(__fmul_rn(r.dy, e2z), __fmul_rn(r.dz, e2y));
@@ -47,17 +50,14 @@ __device__ __forceinline__ bool ray_triangle(const Ray& r, float v0x, float v0y,
   float inv = __fdiv_rn(1.0f, det);
   float tx = __fsub_rn(r.ox, v0x), ty = __fsub_rn(r.oy, v0y), tz = __fsub_rn(r.oz, v0z);
   float u = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(tx, px), __fmul_rn(ty, py)), __fmul_rn(tz, pz)), inv);
+  if (!(u >= 0.0f)) return false;
   float qx = __fsub_rn(__fmul_rn(ty, e1z), __fmul_rn(tz, e1y));
   float qy = __fsub_rn(__fmul_rn(tz, e1x), __fmul_rn(tx, e1z));
   float qz = __fsub_rn(__fmul_rn(tx, e1y), __fmul_rn(ty, e1x));
   float v = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(r.dx, qx), __fmul_rn(r.dy, qy)), __fmul_rn(r.dz, qz)), inv);
+  if (!((v >= 0.0f) && (__fadd_rn(u, v) <= 1.0f))) return false;
   float t = __fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(e2x, qx), __fmul_rn(e2y, qy)), __fmul_rn(e2z, qz)), inv);
-  if (!((u >= 0.0f) && (v >= 0.0f) && (__fadd_rn(u, v) <= 1.0f) && (t > 0.0f))) return false;
-  float tn, tf;
-  bool in_box = slab(r, __fsub_rn(min3(v0x, v1x, v2x), pad), __fsub_rn(min3(v0y, v1y, v2y), pad),
-                     __fsub_rn(min3(v0z, v1z, v2z), pad), __fadd_rn(max3(v0x, v1x, v2x), pad),
-                     __fadd_rn(max3(v0y, v1y, v2y), pad), __fadd_rn(max3(v0z, v1z, v2z), pad), tn, tf);
-  if (!(in_box && (t >= tn) && (t <= tf))) return false;
+  if (!((t > 0.0f) && (t >= tn))) return false;
   t_out = t;
   return true;
 }
@@ -78,10 +78,9 @@ __device__ __forceinline__ float norm3(float x, float y, float z) {
 
 // ---- BVH node reference encoding -------------------------------------------------------------
 //  ref >= 0           internal node index
-//  ref <  0           leaf: ~ref = first | (count-1) << 28   (first: position in the sorted triangle array)
-//  ref == kEmptyRef   nothing
-constexpr int kLeafMax = 4;
+//  ref <  0           leaf: ~ref = position of ONE triangle in the Morton-sorted triangle array; the child box
+//                     stored beside the reference is exactly that triangle's padded box
+//  ref == kEmptyRef   nothing (only in the single-triangle mesh's root)
 constexpr int kEmptyRef = (int)0x80000000;
-__host__ __device__ __forceinline__ int make_leaf_ref(int first, int count) { return ~(first | ((count - 1) << 28)); }
 
 }  // namespace qf

@@ -10,6 +10,8 @@
 //   shading              : ngp_forward_kernel (field.cu) or baked_shade_kernel (baked.cu) over the M live
 //                          samples only (M is read from device memory; persistent grid of 148 x k CTAs).
 //   composite_rays_kernel: derive_properties (utils.py:863-898) per ray.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "traverse.cuh"
@@ -53,24 +55,29 @@ template <int KMAX>
 __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                             const float4* __restrict__ planes, const float* __restrict__ scene,
                                                             const float* __restrict__ origins, const float* __restrict__ dirs,
-                                                            int64_t ray0, int64_t n, int K, int32_t* __restrict__ cursor,
+                                                            int64_t ray0, int64_t n, int K, int img_w, int mode,
+                                                            int32_t* __restrict__ cursor,
                                                             int32_t* __restrict__ ray_start, int32_t* __restrict__ ray_count,
                                                             float4* __restrict__ hit_pd, int2* __restrict__ hit_rt) {
   __shared__ int s_warp[4];
   __shared__ int s_base;
+  __shared__ int s_stack[4][kStackDepth];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t li = blockIdx.x * (int64_t)blockDim.x + tid;  // ray inside the chunk
+  int64_t li = blockIdx.x * (int64_t)blockDim.x + tid;  // ray inside the chunk
+  if (img_w > 0) {
+    // image-ordered rays: a warp takes an 8x4 pixel tile instead of a 32x1 strip (tighter packets, and the
+    // compacted hit samples of a CTA stay close in space for the gather-bound shading kernel)
+    const int64_t gw = li >> 5;
+    const int tiles = img_w >> 3;
+    li = ((gw / tiles) * 4 + (lane >> 3)) * img_w + (gw % tiles) * 8 + (lane & 7);
+  }
   const bool valid = li < n;
   HitBuf<KMAX> hb;
-  hb.cnt = 0;
   int total = 0;
-  Ray r;
-  if (valid) {
-    r = make_ray(origins, dirs, ray0 + li);
-    traverse<KMAX>(r, nodes, tris, __ldg(scene + 6), K, hb, total);
-  }
+  Ray r = make_ray(origins, dirs, ray0 + (valid ? li : n - 1));
+  trace_ray<KMAX>(r, valid, nodes, tris, K, hb, total, s_stack[warp], mode);
   // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
-  int c = valid ? hb.cnt : 0, inc = c;
+  int c = valid ? hb.count(K) : 0, inc = c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
   if (lane == 31) s_warp[warp] = inc;
@@ -89,14 +96,15 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   bool unsorted = false;
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
-    if (s < c) {
+    if (s >= KMAX - K && hb.t[s] != __int_as_float(0x7f800000)) {   // real slots are [KMAX-K, KMAX), filled in order
       float px, py, pz;
       plane_hit(r, __ldg(planes + hb.id[s]), px, py, pz);
       float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
       unsorted |= d < prev;
       prev = d;
-      hit_pd[start + s] = make_float4(px, py, pz, d);
-      hit_rt[start + s] = make_int2((int)(ray0 + li), hb.id[s]);
+      const int j = start + s - (KMAX - K);
+      hit_pd[j] = make_float4(px, py, pz, d);
+      hit_rt[j] = make_int2((int)(ray0 + li), hb.id[s]);
     }
   }
   if (unsorted) {  // rare: plane-hit depth order differs from Möller–Trumbore t order; stable insertion sort
@@ -184,7 +192,7 @@ struct StageProfile {
 static StageProfile g_prof;
 
 static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, const qf_texture* tex, const float* d_uv,
-                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta, int bg_mode,
+                         const float* d_origins, const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta, int bg_mode,
                          const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total,
                          void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
   QF_REQUIRE(mesh && d_origins && d_viewdirs && d_rgb && d_alpha && d_depth && d_workspace, "qf_render: NULL argument");
@@ -198,21 +206,27 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
   if (n_rays == 0) return QF_OK;
   Workspace w;
   workspace_layout(n_rays, K, &w, (char*)d_workspace);
-  for (int64_t ray0 = 0; ray0 < n_rays; ray0 += kChunkRays) {
-    const int64_t n = (n_rays - ray0) < kChunkRays ? (n_rays - ray0) : kChunkRays;
+  static const int trace_mode = getenv("QF_TRACE_MODE") ? atoi(getenv("QF_TRACE_MODE")) : 0;
+  // the 8x4 tile mapping needs whole tiles: width % 8 == 0 and every chunk made of whole 4-row bands
+  const int64_t band = (int64_t)image_width * 4;
+  const bool tiled = image_width > 0 && image_width % 8 == 0 && n_rays % band == 0 && band <= kChunkRays;
+  const int img_w = tiled ? image_width : 0;
+  const int64_t chunk = tiled ? (kChunkRays / band) * band : kChunkRays;
+  for (int64_t ray0 = 0; ray0 < n_rays; ray0 += chunk) {
+    const int64_t n = (n_rays - ray0) < chunk ? (n_rays - ray0) : chunk;
     QF_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t), st));
     const int blocks = (int)ceil_div(n, 128);
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
     if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
     if (K <= 8)
       trace_compact_kernel<8><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                      d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+                                                      d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
     else if (K <= 16)
       trace_compact_kernel<16><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                       d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
     else
       trace_compact_kernel<32><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                       d_viewdirs, ray0, n, K, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) cudaEventRecord(pe[1], st);
     int rc = mode == Shade::NGP ? launch_ngp_forward_hits(field, w.hit_pd, w.hit_rt, d_viewdirs, w.cursor, w.hit_out, st)
@@ -234,20 +248,20 @@ using namespace qf;
 extern "C" size_t qf_render_workspace_bytes(int64_t n_rays, int K) { return workspace_layout(n_rays, K, nullptr, nullptr); }
 
 extern "C" int qf_render_mesh_ngp(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
-                                  int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
+                                  int64_t n_rays, int image_width, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
                                   float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
                                   size_t workspace_bytes, void* stream) {
   QF_REQUIRE(field, "qf_render_mesh_ngp: NULL field");
-  return render_common(Shade::NGP, mesh, field, nullptr, nullptr, d_origins, d_viewdirs, n_rays, K, delta, bg_mode, d_bkgd, d_rgb,
+  return render_common(Shade::NGP, mesh, field, nullptr, nullptr, d_origins, d_viewdirs, n_rays, image_width, K, delta, bg_mode, d_bkgd, d_rgb,
                        d_alpha, d_depth, d_hits_total, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled, const float* d_origins,
-                                    const float* d_viewdirs, int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd,
-                                    float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
-                                    size_t workspace_bytes, void* stream) {
+                                    const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta, int bg_mode,
+                                    const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total,
+                                    void* d_workspace, size_t workspace_bytes, void* stream) {
   QF_REQUIRE(tex && d_uv_scaled, "qf_render_mesh_baked: NULL texture / uv");
-  return render_common(Shade::BAKED, mesh, nullptr, tex, d_uv_scaled, d_origins, d_viewdirs, n_rays, K, delta, bg_mode, d_bkgd,
+  return render_common(Shade::BAKED, mesh, nullptr, tex, d_uv_scaled, d_origins, d_viewdirs, n_rays, image_width, K, delta, bg_mode, d_bkgd,
                        d_rgb, d_alpha, d_depth, d_hits_total, d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -160,8 +160,9 @@ class Scene:
                                   device=self.device)
         return r.origins, r.viewdirs
 
-    def render(self, origins, viewdirs, bg_color="white", render_bkgd=None, out=None, hits_out=None):
-        return self.renderer.render(origins, viewdirs, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out)
+    def render(self, origins, viewdirs, bg_color="white", render_bkgd=None, out=None, hits_out=None, image_width=None):
+        return self.renderer.render(origins, viewdirs, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out,
+                                    image_width=image_width)
 
     def render_baked(self, origins, viewdirs, bg_color="white", out=None):
         return self.baked_renderer.render(origins, viewdirs, bg_color=bg_color, out=out)

@@ -93,9 +93,12 @@ class MeshRenderer:
 
     @torch.no_grad()
     def render(self, origins: torch.Tensor, viewdirs: torch.Tensor, bg_color="white", render_bkgd=None, out=None,
-               hits_out: Optional[torch.Tensor] = None):
+               hits_out: Optional[torch.Tensor] = None, image_width: Optional[int] = None):
         """-> dict(rgb (N,3), opacity (N,1), depth (N,1), n_hits (device int32 tensor)).
-        `hits_out`: optional 1-element int32 CUDA tensor (e.g. a slot of a per-step buffer) receiving the hit count."""
+        `hits_out`: optional 1-element int32 CUDA tensor (e.g. a slot of a per-step buffer) receiving the hit count.
+        `image_width`: the rays are a row-major image of that width ((H,W,3) inputs imply it) — a pure speed hint."""
+        if image_width is None:
+            image_width = origins.shape[1] if origins.dim() == 3 else 0
         lib = _lib.load()
         dev = self.device
         o = _lib.f32(origins.reshape(-1, 3), dev)
@@ -114,11 +117,11 @@ class MeshRenderer:
         hits = self._hits if hits_out is None else hits_out
         if self.compressor is not None:
             _lib.check(lib.qf_render_mesh_baked(mesh, self.compressor.native(), _lib.ptr(self.uv), _lib.ptr(o), _lib.ptr(d), N,
-                                                self.K, self.delta, bg, _lib.ptr(bk), _lib.ptr(out["rgb"]),
+                                                int(image_width), self.K, self.delta, bg, _lib.ptr(bk), _lib.ptr(out["rgb"]),
                                                 _lib.ptr(out["opacity"]), _lib.ptr(out["depth"]), _lib.ptr(hits),
                                                 _lib.ptr(ws), ws.numel(), st), "qf_render_mesh_baked")
         else:
-            _lib.check(lib.qf_render_mesh_ngp(mesh, self.field._native(), _lib.ptr(o), _lib.ptr(d), N, self.K, self.delta, bg,
+            _lib.check(lib.qf_render_mesh_ngp(mesh, self.field._native(), _lib.ptr(o), _lib.ptr(d), N, int(image_width), self.K, self.delta, bg,
                                               _lib.ptr(bk), _lib.ptr(out["rgb"]), _lib.ptr(out["opacity"]),
                                               _lib.ptr(out["depth"]), _lib.ptr(hits), _lib.ptr(ws), ws.numel(), st),
                        "qf_render_mesh_ngp")

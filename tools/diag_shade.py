@@ -1,0 +1,34 @@
+"""Diagnostic: standalone encode vs fused field kernel on one frame's real hit samples.  Run on the GPU box."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import __graft_entry__ as entry
+entry.build()
+from quadraturefields_b200 import scene as S
+dev = torch.device("cuda:0")
+sc = S.make_scene("c2", device=dev)
+o, d = sc.rays(3)
+tup = sc.mesh_intersect.sampling_raytrace(d, o)
+pts, idx_ray = tup[0], tup[2]
+M = pts.shape[0]
+sel, x01 = sc.radiance_field.normalize(pts)
+x01 = x01.contiguous()
+def timeit(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+print("hits", M)
+print("encode only (ray-major hits): %.3f ms" % timeit(lambda: sc.radiance_field.encode(x01)))
+print("fused forward (ray-major hits): %.3f ms" % timeit(lambda: sc.radiance_field(pts, d, ray_indices=idx_ray)))
+perm = torch.randperm(M, device=dev)
+xs = x01[perm].contiguous()
+print("encode only (shuffled hits): %.3f ms" % timeit(lambda: sc.radiance_field.encode(xs)))
+# sorted by a coarse Morton-ish key (spatial coherence upper bound)
+key = ((x01[:, 2] * 64).long() * 4096 + (x01[:, 1] * 64).long() * 64 + (x01[:, 0] * 64).long())
+xm = x01[torch.argsort(key)].contiguous()
+print("encode only (grid-sorted hits): %.3f ms" % timeit(lambda: sc.radiance_field.encode(xm)))
+print("density only (ray-major): %.3f ms" % timeit(lambda: sc.radiance_field.query_density(pts)))
