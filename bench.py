@@ -181,7 +181,8 @@ def run_ours(args):
     # resident inputs: precomputed ray sets for n_views poses (rank r starts at view r so ranks render different frames)
     rays = [sc.rays(v) for v in range(n_views)]
     out = dict(rgb=torch.empty((N, 3), device=dev), opacity=torch.empty((N, 1), device=dev), depth=torch.empty((N, 1), device=dev))
-    view_of = lambda step: (step * world + rank) % n_views
+    from quadraturefields_b200 import parallel as P
+    view_of = lambda step: P.view_for_step(step, rank, world, n_views)
 
     hit_slots = torch.zeros((args.warmup + args.steps, 1), dtype=torch.int32, device=dev)   # one slot per step, written by the kernel
 
@@ -205,9 +206,7 @@ def run_ours(args):
     for i in range(args.steps):
         step_resident(args.warmup + i)
     if world > 1:  # the final image gather (north star): last frame of every rank to rank 0
-        frame = torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1)
-        gathered = [torch.empty_like(frame) for _ in range(world)] if rank == 0 else None
-        dist.gather(frame, gathered, dst=0)
+        P.gather_frame(torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1), [N] * world, dst=0)
     ev1.record()
     barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)

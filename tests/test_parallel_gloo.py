@@ -1,0 +1,67 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: ray/frame sharding, the final image gather and the
+gradient all-reduce.  The kernels are rank-local; tests/test_gpu_parity.py::test_full_size_properties_c2 checks on
+the GPU that a slice rendered alone equals the same slice of the full frame."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from quadraturefields_b200 import parallel as P
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        W, H = 24, 20
+        N = W * H
+        frame = torch.arange(N * 5, dtype=torch.float32).reshape(N, 5)          # stands for (rgb, alpha, depth) of the frame
+        lo, hi = P.shard_rays(N, rank, ws, image_width=W)
+        sizes = [b - a for a, b in (P.shard_rays(N, r, ws, image_width=W) for r in range(ws))]
+        got = P.gather_frame(frame[lo:hi] * 1.0, sizes, dst=0)
+        ok = True
+        if rank == 0:
+            ok &= torch.equal(got, frame)
+        else:
+            ok &= got is None
+        # gradient all-reduce: per-rank mean gradients, unequal sample counts -> global mean
+        p = torch.nn.Parameter(torch.zeros(7))
+        n_local = 10 + 30 * rank
+        p.grad = torch.full((7,), float(rank + 1))
+        P.all_reduce_gradients([p], n_local)
+        expect = sum((10 + 30 * r) * (r + 1) for r in range(ws)) / sum(10 + 30 * r for r in range(ws))
+        ok &= bool(torch.allclose(p.grad, torch.full((7,), expect)))
+        ok &= P.max_over_ranks(1.0 + rank) == float(ws)
+        ret[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo():
+    ws = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(ws, _free_port(), ret), nprocs=ws, join=True)
+    assert dict(ret) == {0: True, 1: True}
+
+
+def test_sharding_covers_every_ray_once():
+    for n, w in ((640000, 800), (2073600, 1920), (1000, 0), (10, 0), (7, 0)):
+        for ws in (1, 2, 3, 4, 8):
+            cuts = [P.shard_rays(n, r, ws, w) for r in range(ws)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(ws - 1))
+            if w:
+                assert all((b - a) % (4 * w) == 0 for a, b in cuts)
+            assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= (4 * w if w else 1)
+    views = sorted(P.view_for_step(s, r, 4, 200) for s in range(50) for r in range(4))
+    assert views == list(range(200))
