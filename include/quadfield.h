@@ -123,6 +123,15 @@ int qf_ngp_query_density(const qf_ngp* f, const float* d_positions, int64_t M, f
 int qf_ngp_forward(const qf_ngp* f, const float* d_positions, const float* d_directions,
                    const int64_t* d_ray_index, int64_t M, float* d_rgb, float* d_density, void* stream);
 
+/* Training mode (tinycudann grid + MLP backward under autograd: train_finetune.py:494-531, train_fit_sg.py):
+ * given dL/drgb (M,3) and dL/ddensity (M) [may be NULL], ACCUMULATES into caller-initialised fp32 buffers in
+ * tinycudann's layout: d_grad_table (n_entries,2), d_grad_base_w (64x32 | 16x64), d_grad_head_w (64x32 | 64x64 | 16x64).
+ * The forward is recomputed inside; positions/directions get no gradient.  workspace >= qf_ngp_backward_workspace_bytes(M). */
+size_t qf_ngp_backward_workspace_bytes(int64_t M);
+int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const float* d_directions, const int64_t* d_ray_index,
+                    int64_t M, const float* d_grad_rgb, const float* d_grad_density, float* d_grad_table,
+                    float* d_grad_base_w, float* d_grad_head_w, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * (4) Baked spherical-Gaussian texture path.
  * Replaces FeatureCompression.get_features_from_texture_map (texture_utils.py:149-175), the
@@ -153,6 +162,12 @@ int qf_hit_texels(const qf_mesh* mesh, const float* d_points, const int64_t* d_i
 int qf_derive_properties(const float* d_color, const float* d_density, const float* d_depths, float delta,
                          const int64_t* d_offsets, int64_t n_rays, int bg_mode, const float* d_bkgd,
                          float* d_rgb, float* d_alpha, float* d_depth_out, float* d_weights, void* stream);
+
+/* autograd of derive_properties w.r.t. color (M,3) and density (M); grad inputs (N,3)/(N,1)/(N,1) may be NULL */
+int qf_derive_properties_backward(const float* d_color, const float* d_density, const float* d_depths, float delta,
+                                  const int64_t* d_offsets, int64_t n_rays, int64_t n_hits, int bg_mode, const float* d_bkgd,
+                                  const float* d_grad_rgb, const float* d_grad_alpha, const float* d_grad_depth,
+                                  float* d_grad_color, float* d_grad_density, void* stream);
 
 /* nerfacc-style segmented scans behind field_rendering.py (exclusive_prod / exclusive_sum, :203,:261).
  * packed_info (n_rays,2) int64 [start,count].  mode 0: from alphas; 1: from sigmas*(t_ends-t_starts).

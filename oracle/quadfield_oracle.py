@@ -367,6 +367,11 @@ def make_grid_meta(n_levels: int = 16, base_resolution: int = 16, max_resolution
     return GridMeta(n_levels, n_features, scale, res, offset, size, hashed)
 
 
+def _round_h(x: torch.Tensor) -> torch.Tensor:
+    """Round to fp16 with a straight-through gradient (tcnn's __half module boundaries)."""
+    return x + (x.half().float() - x).detach()
+
+
 _PRIMES = (1, 2654435761, 805459861)
 _U32 = 0xFFFFFFFF
 
@@ -376,7 +381,7 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
     fp16-representable values.  Output (M, L·F) fp32 holding fp16-rounded values, level-major."""
     M = x01.shape[0]
     Fdim = meta.n_features
-    out = torch.empty((M, meta.n_levels * Fdim), dtype=torch.float32)
+    outs = []
     xd = x01.double()
     for l in range(meta.n_levels):
         scale = float(meta.scale[l])
@@ -403,8 +408,8 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
                 idx = (g[0] + ((g[1] * res) & _U32) + ((g[2] * ((res * res) & _U32)) & _U32)) & _U32
             idx = idx % size + int(meta.offset[l])
             acc = acc + w[:, None] * table[idx]
-        out[:, l * Fdim:(l + 1) * Fdim] = acc.half().float()
-    return out
+        outs.append(_round_h(acc))
+    return torch.cat(outs, dim=1)
 
 
 def sh4(d: torch.Tensor) -> torch.Tensor:
@@ -431,11 +436,17 @@ def sh4(d: torch.Tensor) -> torch.Tensor:
     return o
 
 
+ROUND_HIDDEN = False  # tcnn keeps hidden activations in __half; the oracle's default is the stricter fp32 restatement
+
+
 def mlp_forward(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
-    """tcnn FullyFusedMLP semantics: bias-free, ReLU hidden, linear output; weights[i] is (out,in).  fp32 math."""
+    """tcnn FullyFusedMLP semantics: bias-free, ReLU hidden, linear output; weights[i] is (out,in).  fp32 math
+    (hidden activations optionally rounded to fp16 with a straight-through gradient, see ROUND_HIDDEN)."""
     h = x
     for W in weights[:-1]:
         h = torch.relu(h @ W.t())
+        if ROUND_HIDDEN:
+            h = _round_h(h)
     return h @ weights[-1].t()
 
 
@@ -495,7 +506,7 @@ def ngp_query_rgb(dirs: torch.Tensor, embedding: torch.Tensor, p: NGPParams, app
     d01 = (dirs + 1.0) / 2.0
     sh = sh4(d01 * 2.0 - 1.0).half().float()
     pad = torch.full((dirs.shape[0], 1), HEAD_PAD_VALUE, dtype=torch.float32)
-    h = torch.cat([sh, embedding.half().float(), pad], dim=-1)
+    h = torch.cat([sh, _round_h(embedding), pad], dim=-1)
     rgb = mlp_forward(h, p.head_w)[:, :3]
     return torch.sigmoid(rgb) if apply_act else rgb
 

@@ -45,6 +45,50 @@ __global__ void derive_properties_kernel(const float* __restrict__ color, const 
   depth_out[i] = D;
 }
 
+// backward of derive_properties w.r.t. color (M,3) and density (M): thread per ray, two sweeps over its <= K samples.
+//   out_c = bgmix(A, C_c),  A = sum w,  C_c = sum w c_c,  Depth = sum w t,  w_i = exp(-sum_{j<i} tau_j)(1-exp(-tau_i))
+//   dL/dw_i = sum_c g_c (dOut_c/dA + dOut_c/dC_c c_ic) + g_A + g_D t_i ;  dL/dtau_k = gw_k T_k e^{-tau_k} - sum_{i>k} gw_i w_i
+__global__ void derive_properties_bwd_kernel(const float* __restrict__ color, const float* __restrict__ density,
+                                             const float* __restrict__ depths, float delta,
+                                             const int64_t* __restrict__ offsets, int64_t N, int bg_mode,
+                                             const float* __restrict__ bkgd, const float* __restrict__ g_rgb,
+                                             const float* __restrict__ g_alpha, const float* __restrict__ g_depth,
+                                             float* __restrict__ g_color, float* __restrict__ g_density) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int64_t s = offsets[i], e = offsets[i + 1];
+  if (e <= s) return;
+  float cum = 0.f, C[3] = {0.f, 0.f, 0.f}, A = 0.f;
+  for (int64_t j = s; j < e; ++j) {
+    float tau = density[j] * delta;
+    float w = expf(-cum) * (1.0f - expf(-tau));
+    cum += tau;
+    C[0] += w * color[3 * j]; C[1] += w * color[3 * j + 1]; C[2] += w * color[3 * j + 2];
+    A += w;
+  }
+  const float g[3] = {g_rgb ? g_rgb[3 * i] : 0.f, g_rgb ? g_rgb[3 * i + 1] : 0.f, g_rgb ? g_rgb[3 * i + 2] : 0.f};
+  const float gA = g_alpha ? g_alpha[i] : 0.f, gD = g_depth ? g_depth[i] : 0.f;
+  // out_c = (1-A) + A C_c (white) | A C_c (black) | A C_c + (1-A) b_c (random)
+  float dA = gA, dC[3];
+  for (int c = 0; c < 3; ++c) {
+    float b = bg_mode == QF_BG_WHITE ? 1.f : (bg_mode == QF_BG_BLACK ? 0.f : bkgd[c]);
+    dA += g[c] * (C[c] - b);
+    dC[c] = g[c] * A;
+  }
+  // reverse sweep: suffix = sum_{i>k} gw_i w_i
+  float suffix = 0.f;
+  for (int64_t j = e - 1; j >= s; --j) {
+    float tau = density[j] * delta;
+    cum -= tau;                                  // exclusive prefix of sample j
+    float T = expf(-cum), ea = expf(-tau);
+    float w = T * (1.0f - ea);
+    float gw = dA + gD * depths[j] + dC[0] * color[3 * j] + dC[1] * color[3 * j + 1] + dC[2] * color[3 * j + 2];
+    if (g_color) { g_color[3 * j] = dC[0] * w; g_color[3 * j + 1] = dC[1] * w; g_color[3 * j + 2] = dC[2] * w; }
+    if (g_density) g_density[j] = delta * (gw * T * ea - suffix);
+    suffix += gw * w;
+  }
+}
+
 // ---------------------------------------------------------------- nerfacc-style scans
 __device__ __forceinline__ float warp_incl_sum(float v, int lane) {
 #pragma unroll
@@ -236,6 +280,25 @@ extern "C" int qf_derive_properties(const float* d_color, const float* d_density
   if (n_rays == 0) return QF_OK;
   derive_properties_kernel<<<(int)ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
       d_color, d_density, d_depths, delta, d_offsets, n_rays, bg_mode, d_bkgd, d_rgb, d_alpha, d_depth_out, d_weights);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_derive_properties_backward(const float* d_color, const float* d_density, const float* d_depths, float delta,
+                                             const int64_t* d_offsets, int64_t n_rays, int64_t n_hits, int bg_mode,
+                                             const float* d_bkgd, const float* d_grad_rgb, const float* d_grad_alpha,
+                                             const float* d_grad_depth, float* d_grad_color, float* d_grad_density,
+                                             void* stream) {
+  QF_REQUIRE(bg_mode >= 0 && bg_mode <= 2, "qf_derive_properties_backward: bg_mode=%d", bg_mode);
+  if (n_rays == 0 || n_hits == 0) return QF_OK;
+  QF_REQUIRE(d_color && d_density && d_depths && d_offsets, "qf_derive_properties_backward: NULL argument");
+  QF_REQUIRE(bg_mode != QF_BG_RANDOM || d_bkgd, "qf_derive_properties_backward: bg 'random' needs render_bkgd");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_grad_color) QF_CUDA_CHECK(cudaMemsetAsync(d_grad_color, 0, sizeof(float) * 3 * n_hits, st));
+  if (d_grad_density) QF_CUDA_CHECK(cudaMemsetAsync(d_grad_density, 0, sizeof(float) * n_hits, st));
+  derive_properties_bwd_kernel<<<(int)ceil_div(n_rays, 256), 256, 0, st>>>(d_color, d_density, d_depths, delta, d_offsets, n_rays,
+                                                                             bg_mode, d_bkgd, d_grad_rgb, d_grad_alpha, d_grad_depth,
+                                                                             d_grad_color, d_grad_density);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

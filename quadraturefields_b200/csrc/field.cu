@@ -10,20 +10,9 @@
 // n+1 (mma.sync m16n8k16, fp32 accumulate), so activations never touch shared or global memory.
 // The density logit uses a hi+lo fp16 split of the hidden activations, which keeps sigma within
 // ~1e-6 of the fp32 oracle.
-#include "common.cuh"
+#include "field_common.cuh"
 
 namespace qf {
-
-// ---- shared-memory weight image (halves); strides padded for conflict-free fragment loads
-constexpr int kS32 = 40;   // row stride of a (out x 32) matrix
-constexpr int kS64 = 72;   // row stride of a (out x 64) matrix
-constexpr int kW1 = 0;                    // base  L1  64 x 32
-constexpr int kW2 = kW1 + 64 * kS32;      // base  L2  16 x 64
-constexpr int kW3 = kW2 + 16 * kS64;      // head  L1  64 x 32 (columns permuted, see prep)
-constexpr int kW4 = kW3 + 64 * kS32;      // head  L2  64 x 64
-constexpr int kW5 = kW4 + 64 * kS64;      // head  L3  16 x 64
-constexpr int kWTotal = kW5 + 16 * kS64;  // 12032 halves = 24064 B
-constexpr int kTileStride = 56;           // per-sample staging row: 32 enc + 16 SH + 8 pad (halves)
 
 // tcnn layout (row-major (out,in), fp32) -> padded fp16 image.  Head L1 input order in tcnn is
 // [SH(16) | feat(15) | pad(1)]; the kernel feeds [SH(16) | pad | feat(15)] so that the base MLP's
@@ -49,124 +38,6 @@ __global__ void prep_weights_kernel(const float* __restrict__ base_w, const floa
 __global__ void prep_table_kernel(const float* __restrict__ t, int64_t n_entries, __half2* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_entries; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = __floats2half2_rn(t[2 * i], t[2 * i + 1]);
-}
-
-// ---- hash-grid encode of one point: 16 levels, trilinear, fp32 interpolation, fp16 result
-// The level loop is kept ROLLED (two levels per trip, the gathers of both issued before either is consumed):
-// fully unrolled it is ~13k instructions and the kernel stalls on instruction fetch.
-struct Corner8 { uint32_t idx[8]; float fx, fy, fz; };
-
-__device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, float x, float y, float z, Corner8& c) {
-  const float scale = d.scale[l];
-  const uint32_t res = d.resolution[l], size = d.size[l];
-  float px = fmaf(scale, x, 0.5f), py = fmaf(scale, y, 0.5f), pz = fmaf(scale, z, 0.5f);
-  const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
-  const uint32_t cx = (uint32_t)(int)flx, cy = (uint32_t)(int)fly, cz = (uint32_t)(int)flz;
-  c.fx = px - flx; c.fy = py - fly; c.fz = pz - flz;
-  if (d.hashed[l]) {   // hashed levels always have size == 2^log2_hashmap_size
-    const uint32_t mask = size - 1;
-    const uint32_t y0 = cy * 2654435761u, y1 = (cy + 1) * 2654435761u, z0 = cz * 805459861u, z1 = (cz + 1) * 805459861u;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c.idx[k] = ((cx + (k & 1)) ^ ((k & 2) ? y1 : y0) ^ ((k & 4) ? z1 : z0)) & mask;
-  } else {
-    const uint32_t sy = res, sz = res * res;
-    bool wrap = false;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      c.idx[k] = (cx + (k & 1)) + (cy + ((k >> 1) & 1)) * sy + (cz + ((k >> 2) & 1)) * sz;
-      wrap |= c.idx[k] >= size;
-    }
-    if (wrap) {   // upper box faces and points outside the aabb wrap exactly like tcnn (index % level size)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) c.idx[k] %= size;
-    }
-  }
-}
-
-__device__ __forceinline__ uint32_t level_blend(const Corner8& c, const __half2* v) {
-  float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
-    w *= (k & 4) ? c.fz : 1.f - c.fz;
-    float2 f = __half22float2(v[k]);
-    r0 = __fadd_rn(r0, __fmul_rn(w, f.x));   // separately rounded like the oracle: the encoding is bit-exact
-    r1 = __fadd_rn(r1, __fmul_rn(w, f.y));
-  }
-  __half2 hv = __floats2half2_rn(r0, r1);
-  return *reinterpret_cast<uint32_t*>(&hv);
-}
-// The weight of corner k is ((wx*wy)*wz) in the oracle's order: w starts at 1 and is multiplied by the
-// x, y, z factors in turn; (1*wx)*wy*wz == (wx*wy)*wz exactly.
-
-// writes 2 halves per level to out[2*l] (shared-memory row of the sample, or a local array)
-template <typename Store>
-__device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
-                                             float z, Store store) {
-  const int L = d.n_levels;
-#pragma unroll 1
-  for (int l = 0; l < L; l += 2) {
-    Corner8 c0, c1;
-    __half2 v0[8], v1[8];
-    level_indices(d, l, x, y, z, c0);
-    const __half2* t0 = table + d.offset[l];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v0[k] = __ldg(t0 + c0.idx[k]);
-    const bool two = l + 1 < L;
-    if (two) {
-      level_indices(d, l + 1, x, y, z, c1);
-      const __half2* t1 = table + d.offset[l + 1];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v1[k] = __ldg(t1 + c1.idx[k]);
-    }
-    store(l, level_blend(c0, v0));
-    if (two) store(l + 1, level_blend(c1, v1));
-  }
-}
-
-__device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
-  float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-  o[0] = 0.28209479177387814f;
-  o[1] = -0.48860251190291987f * y;
-  o[2] = 0.48860251190291987f * z;
-  o[3] = -0.48860251190291987f * x;
-  o[4] = 1.0925484305920792f * xy;
-  o[5] = -1.0925484305920792f * yz;
-  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
-  o[7] = -1.0925484305920792f * xz;
-  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
-  o[10] = 2.8906114426405538f * xy * z;
-  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
-  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
-  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
-  o[14] = 1.4453057213202769f * z * (x2 - y2);
-  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
-}
-
-// ---- tensor-core helpers (legacy HMMA path; the tcgen05 variant lives in field_tc.cu)
-__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t lds32(const __half* p) { return *reinterpret_cast<const uint32_t*>(p); }
-
-// D[16 x 8*NT] += A[16 x 16*KT] * W^T, W row-major (n, k) in shared memory with row stride `stride`
-template <int KT, int NT>
-__device__ __forceinline__ void layer(float (*acc)[4], const uint32_t (*a)[4], const __half* __restrict__ w, int stride,
-                                      int g, int t) {
-#pragma unroll
-  for (int n = 0; n < NT; ++n) {
-    const __half* wr = w + (n * 8 + g) * stride + t * 2;
-#pragma unroll
-    for (int k = 0; k < KT; ++k) mma16816(acc[n], a[k], lds32(wr + k * 16), lds32(wr + k * 16 + 8));
-  }
 }
 
 struct FieldArgs {

@@ -1,0 +1,450 @@
+// Training mode of the Instant-NGP field (NGPRadianceField under autograd: train_finetune.py:494-531,
+// train_fit_sg.py): gradients of the hash table and of the five MLP matrices given dL/drgb and dL/dsigma at the
+// samples.  Replaces tinycudann's grid backward (atomicAdd into the table gradient) and its MLP backward GEMMs.
+//
+//   ngp_backward_kernel   per warp 32 samples: RECOMPUTES the forward (re-gathers the table — cheaper than storing
+//                         512 B of activations per sample in the forward pass), then walks the layers backwards on
+//                         tensor cores (mma.sync, transposed weight images in shared memory, the accumulator fragment
+//                         of one layer re-packed as the A fragment of the next).  The encoding gradient lands in
+//                         exactly the fragment layout where lane (g,t) owns levels {t, t+4, t+8, t+12} of samples
+//                         g and g+8, so the table scatter (8 float2 atomics per level) needs no shuffles.
+//                         Layer inputs and output-gradients are written once as fp16 rows (960 B / sample).
+//   weight_grad_kernel    dW_l = G_l^T A_l as a split-K tensor-core GEMM over the sample dimension
+//                         (ldmatrix.trans fragments, fp32 accumulate, one atomicAdd per element per chunk).
+//   unpack_weight_grads   padded kernel image -> tinycudann flat layout (row-major (out,in), head columns un-permuted).
+#include "field_common.cuh"
+
+namespace qf {
+
+// transposed weight images (halves): WT[n][k] = W[k][n]
+constexpr int kT24 = 24;   // row stride for 16-wide rows
+constexpr int kT5 = 0;                      // W5^T  64 x 16
+constexpr int kT4 = kT5 + 64 * kT24;        // W4^T  64 x 64
+constexpr int kT3 = kT4 + 64 * kS64;        // W3p^T 32 x 64   (kernel column order [SH | pad | feat])
+constexpr int kT2 = kT3 + 32 * kS64;        // W2^T  64 x 16
+constexpr int kT1 = kT2 + 64 * kT24;        // W1^T  32 x 64
+constexpr int kTTotal = kT1 + 32 * kS64;    // 12288 halves
+
+// per-sample rows written for the weight-gradient GEMMs
+constexpr int kActRow = 256;  // [0,32) enc | [32,96) relu(h1) | [96,128) head input (kernel order) | [128,192) relu(h2) | [192,256) relu(h3)
+constexpr int kGrdRow = 224;  // [0,64) dL/dh1pre | [64,80) dL/d base out | [80,144) dL/dh2pre | [144,208) dL/dh3pre | [208,224) dL/d rgb logits
+
+__global__ void transpose_weights_kernel(const __half* __restrict__ img, __half* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTTotal) return;
+  __half v = __float2half_rn(0.f);
+  if (i < kT4) { int n = i / kT24, k = i % kT24; if (k < 16) v = img[kW5 + k * kS64 + n]; }
+  else if (i < kT3) { int j = i - kT4, n = j / kS64, k = j % kS64; if (k < 64) v = img[kW4 + k * kS64 + n]; }
+  else if (i < kT2) { int j = i - kT3, n = j / kS64, k = j % kS64; if (k < 64) v = img[kW3 + k * kS32 + n]; }
+  else if (i < kT1) { int j = i - kT2, n = j / kT24, k = j % kT24; if (k < 16) v = img[kW2 + k * kS64 + n]; }
+  else { int j = i - kT1, n = j / kS64, k = j % kS64; if (k < 64) v = img[kW1 + k * kS32 + n]; }
+  out[i] = v;
+}
+
+struct BwdArgs {
+  qf_grid_desc desc;
+  const __half2* table;
+  const __half* weights;    // forward image (kWTotal)
+  const __half* weights_t;  // transposed image (kTTotal)
+  const float* pos;
+  int pos_stride;
+  const float* dirs;
+  const int64_t* ray64;
+  int64_t M;
+  const float* g_rgb;       // (M,3)
+  const float* g_sigma;     // (M) or NULL
+  float2* g_table;          // (n_entries) float2, atomically accumulated
+  __half* act;              // (M, kActRow)
+  __half* grd;              // (M, kGrdRow)
+};
+
+__device__ __forceinline__ unsigned relu_mask8(float (*acc)[4]) {
+  unsigned m = 0;
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) m |= (acc[n][q] > 0.f ? 1u : 0u) << (n * 4 + q);
+  return m;
+}
+__device__ __forceinline__ void apply_mask8(float (*acc)[4], unsigned m) {
+#pragma unroll
+  for (int n = 0; n < 8; ++n)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[n][q] = ((m >> (n * 4 + q)) & 1u) ? acc[n][q] : 0.f;
+}
+// accumulator fragments (16 x 64, C layout) -> A fragments of a 64-deep contraction; optional ReLU
+template <bool RELU>
+__device__ __forceinline__ void c_to_a(uint32_t (*a)[4], float (*acc)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float* c = acc[2 * k + h];
+      a[k][2 * h] = RELU ? pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)) : pack_h2(c[0], c[1]);
+      a[k][2 * h + 1] = RELU ? pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)) : pack_h2(c[2], c[3]);
+    }
+}
+// A fragments (rows g / g+8) -> fp16 row-major global rows: cols [col0, col0 + 16*KT)
+template <int KT>
+__device__ __forceinline__ void store_a(__half* __restrict__ base, int row_len, int col0, int64_t r_lo, int64_t r_hi, int64_t M,
+                                        const uint32_t (*a)[4], int t) {
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    const int c = col0 + k * 16 + t * 2;
+    if (r_lo < M) {
+      *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c) = a[k][0];
+      *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c + 8) = a[k][2];
+    }
+    if (r_hi < M) {
+      *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c) = a[k][1];
+      *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c + 8) = a[k][3];
+    }
+  }
+}
+// accumulator fragments (C layout, NT n-tiles) -> fp16 rows
+template <int NT>
+__device__ __forceinline__ void store_c(__half* __restrict__ base, int row_len, int col0, int64_t r_lo, int64_t r_hi, int64_t M,
+                                        float (*acc)[4], int t) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    const int c = col0 + n * 8 + t * 2;
+    if (r_lo < M) *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c) = pack_h2(acc[n][0], acc[n][1]);
+    if (r_hi < M) *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c) = pack_h2(acc[n][2], acc[n][3]);
+  }
+}
+
+__device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
+                                              float z, float g0, float g1) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  Corner8 c;
+  level_indices(d, l, x, y, z, c);
+  float2* lvl = g_table + d.offset[l];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
+    w *= (k & 4) ? c.fz : 1.f - c.fz;
+    atomicAdd(lvl + c.idx[k], make_float2(w * g0, w * g1));
+  }
+}
+
+constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4 * 32 * 3 * 4;
+
+__global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __half* s_w = reinterpret_cast<__half*>(smem_raw);
+  __half* s_wt = s_w + kWTotal;
+  __half* s_tile_all = s_wt + kTTotal;
+  float* s_x_all = reinterpret_cast<float*>(s_tile_all + 4 * 32 * kTileStride);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.weights);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = tid; i < kWTotal / 8; i += 128) dst[i] = __ldg(src + i);
+    const uint4* srct = reinterpret_cast<const uint4*>(a.weights_t);
+    uint4* dstt = reinterpret_cast<uint4*>(s_wt);
+    for (int i = tid; i < kTTotal / 8; i += 128) dstt[i] = __ldg(srct + i);
+  }
+  __syncthreads();
+  const int64_t M = a.M;
+  __half* tile = s_tile_all + warp * 32 * kTileStride;
+  float* sx = s_x_all + warp * 32 * 3;
+  const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
+  const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
+
+  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < M; base += (int64_t)gridDim.x * 128) {
+    const int64_t i = base + lane;
+    const bool valid = i < M;
+    float x = 0.5f, y = 0.5f, z = 0.5f;
+    bool sel = false;
+    if (valid) {
+      const float* p = a.pos + i * a.pos_stride;
+      x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);
+      y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
+      z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
+      sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
+    }
+    sx[lane * 3] = x; sx[lane * 3 + 1] = y; sx[lane * 3 + 2] = z;
+    uint32_t* row32 = reinterpret_cast<uint32_t*>(tile + lane * kTileStride);
+    encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) { row32[l] = h2; });
+    uint4* row = reinterpret_cast<uint4*>(row32);
+    {
+      float dx = 0.f, dy = 0.f, dz = 1.f;
+      if (valid) {
+        int64_t r = a.ray64 ? __ldg(a.ray64 + i) : i;
+        const float* dp = a.dirs + 3 * r;
+        dx = ((__ldg(dp) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+        dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+        dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+      }
+      float sh[16];
+      sh4(dx, dy, dz, sh);
+      row[4] = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sh[3]), pack_h2(sh[4], sh[5]), pack_h2(sh[6], sh[7]));
+      row[5] = make_uint4(pack_h2(sh[8], sh[9]), pack_h2(sh[10], sh[11]), pack_h2(sh[12], sh[13]), pack_h2(sh[14], sh[15]));
+    }
+    if (valid) {  // layer-1 input rows (the encoding), one 64-byte row per lane
+      uint4* dst = reinterpret_cast<uint4*>(a.act + i * kActRow);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dst[q] = row[q];
+    }
+    const unsigned selmask = __ballot_sync(0xffffffffu, sel);
+    __syncwarp();
+
+#pragma unroll 1
+    for (int mt = 0; mt < 2; ++mt) {
+      if (base + mt * 16 >= M) break;
+      const int64_t r_lo = base + mt * 16 + g, r_hi = r_lo + 8;
+      const __half* ta = tile + (mt * 16 + g) * kTileStride + t * 2;
+      const __half* tb = ta + 8 * kTileStride;
+      // ================= forward recompute =================
+      uint32_t a1[2][4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        a1[k][0] = lds32(ta + k * 16); a1[k][1] = lds32(tb + k * 16);
+        a1[k][2] = lds32(ta + k * 16 + 8); a1[k][3] = lds32(tb + k * 16 + 8);
+      }
+      float acc[8][4];
+      uint32_t af[4][4];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<2, 8>(acc, a1, s_w + kW1, kS32, g, t);
+      const unsigned mask1 = relu_mask8(acc);
+      c_to_a<true>(af, acc);
+      store_a<4>(a.act, kActRow, 32, r_lo, r_hi, M, af, t);
+      float acc2[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
+      layer<4, 2>(acc2, af, s_w + kW2, kS64, g, t);
+      const float h0_lo = acc2[0][0], h0_hi = acc2[0][2];   // meaningful on t == 0
+      uint32_t a3[2][4];
+      a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
+      a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
+      a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
+      a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
+      a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
+      store_a<2>(a.act, kActRow, 96, r_lo, r_hi, M, a3, t);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
+      const unsigned mask3 = relu_mask8(acc);
+      c_to_a<true>(af, acc);
+      store_a<4>(a.act, kActRow, 128, r_lo, r_hi, M, af, t);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<4, 8>(acc, af, s_w + kW4, kS64, g, t);
+      const unsigned mask4 = relu_mask8(acc);
+      c_to_a<true>(af, acc);
+      store_a<4>(a.act, kActRow, 192, r_lo, r_hi, M, af, t);
+      float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+      layer<4, 1>(acc5, af, s_w + kW5, kS64, g, t);
+      // ================= backward =================
+      // dL/d rgb logits = g_rgb * rgb (1 - rgb); lane t owns logit columns 2t, 2t+1 of rows g and g+8
+      uint32_t ga[1][4] = {{0u, 0u, 0u, 0u}};
+      if (t < 2) {
+        auto dsig = [](float v) { float s = 1.0f / (1.0f + __expf(-v)); return s * (1.0f - s); };
+        float gl0 = 0.f, gl1 = 0.f, gh0 = 0.f, gh1 = 0.f;
+        if (r_lo < M) { gl0 = a.g_rgb[3 * r_lo + 2 * t] * dsig(acc5[0][0]); if (t == 0) gl1 = a.g_rgb[3 * r_lo + 1] * dsig(acc5[0][1]); }
+        if (r_hi < M) { gh0 = a.g_rgb[3 * r_hi + 2 * t] * dsig(acc5[0][2]); if (t == 0) gh1 = a.g_rgb[3 * r_hi + 1] * dsig(acc5[0][3]); }
+        ga[0][0] = pack_h2(gl0, gl1);
+        ga[0][1] = pack_h2(gh0, gh1);
+      }
+      store_a<1>(a.grd, kGrdRow, 208, r_lo, r_hi, M, ga, t);
+      // head L3:  dL/dh3 = g_o W5, masked
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<1, 8>(acc, ga, s_wt + kT5, kT24, g, t);
+      apply_mask8(acc, mask4);
+      store_c<8>(a.grd, kGrdRow, 144, r_lo, r_hi, M, acc, t);
+      c_to_a<false>(af, acc);
+      // head L2:  dL/dh2 = g_h3 W4, masked
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<4, 8>(acc, af, s_wt + kT4, kS64, g, t);
+      apply_mask8(acc, mask3);
+      store_c<8>(a.grd, kGrdRow, 80, r_lo, r_hi, M, acc, t);
+      c_to_a<false>(af, acc);
+      // head L1: only the [pad | feat] half of the input carries gradient on to the base MLP
+      float gin[2][4];
+#pragma unroll
+      for (int n = 0; n < 2; ++n) gin[n][0] = gin[n][1] = gin[n][2] = gin[n][3] = 0.f;
+      layer<4, 2>(gin, af, s_wt + kT3 + 16 * kS64, kS64, g, t);
+      if (t == 0) {  // column 0 of the base output is the density logit: dL/dh0 = dL/dsigma * exp(min(h0-1, 15)) * selector
+        float gs_lo = (a.g_sigma && r_lo < M) ? a.g_sigma[r_lo] : 0.f, gs_hi = (a.g_sigma && r_hi < M) ? a.g_sigma[r_hi] : 0.f;
+        gin[0][0] = ((selmask >> (mt * 16 + g)) & 1u) ? gs_lo * expf(fminf(h0_lo - 1.0f, 15.0f)) : 0.f;
+        gin[0][2] = ((selmask >> (mt * 16 + g + 8)) & 1u) ? gs_hi * expf(fminf(h0_hi - 1.0f, 15.0f)) : 0.f;
+      }
+      store_c<2>(a.grd, kGrdRow, 64, r_lo, r_hi, M, gin, t);
+      uint32_t g2[1][4];
+      g2[0][0] = pack_h2(gin[0][0], gin[0][1]); g2[0][1] = pack_h2(gin[0][2], gin[0][3]);
+      g2[0][2] = pack_h2(gin[1][0], gin[1][1]); g2[0][3] = pack_h2(gin[1][2], gin[1][3]);
+      // base L2:  dL/dh1 = g_out2 W2, masked
+#pragma unroll
+      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+      layer<1, 8>(acc, g2, s_wt + kT2, kT24, g, t);
+      apply_mask8(acc, mask1);
+      store_c<8>(a.grd, kGrdRow, 0, r_lo, r_hi, M, acc, t);
+      c_to_a<false>(af, acc);
+      // base L1:  dL/denc = g_h1 W1 -> table scatter
+      float ge[4][4];
+#pragma unroll
+      for (int n = 0; n < 4; ++n) ge[n][0] = ge[n][1] = ge[n][2] = ge[n][3] = 0.f;
+      layer<4, 4>(ge, af, s_wt + kT1, kS64, g, t);
+      const float* xl = sx + (mt * 16 + g) * 3;
+      const float* xh = xl + 24;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const int l = n * 4 + t;   // accumulator columns n*8 + 2t, +1 are the two features of level n*4 + t
+        if (r_lo < M) scatter_level(a.desc, a.g_table, l, xl[0], xl[1], xl[2], ge[n][0], ge[n][1]);
+        if (r_hi < M) scatter_level(a.desc, a.g_table, l, xh[0], xh[1], xh[2], ge[n][2], ge[n][3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- dW_l = G_l^T A_l
+struct LayerGemm { int N, K, act_off, grd_off, img_off, img_stride; };
+__constant__ LayerGemm c_layers[5] = {
+    {64, 32, 0, 0, kW1, kS32}, {16, 64, 32, 64, kW2, kS64}, {64, 32, 96, 80, kW3, kS32},
+    {64, 64, 128, 144, kW4, kS64}, {16, 64, 192, 208, kW5, kS64}};
+__constant__ int c_item_layer[14] = {0, 0, 0, 0, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4};
+__constant__ int c_item_mtile[14] = {0, 1, 2, 3, 0, 0, 1, 2, 3, 0, 1, 2, 3, 0};
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
+  unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, const void* p) {
+  unsigned addr = (unsigned)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+
+constexpr int kGemmChunk = 4096;  // samples per CTA
+
+__global__ void __launch_bounds__(128) weight_grad_kernel(const __half* __restrict__ act, const __half* __restrict__ grd,
+                                                          int64_t M, float* __restrict__ stage) {
+  __shared__ __align__(16) __half s_g[4][16 * kT24];
+  __shared__ __align__(16) __half s_a[4][16 * kS64];
+  const int item = blockIdx.y;
+  const LayerGemm L = c_layers[c_item_layer[item]];
+  const int mtile = c_item_mtile[item];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  __half* sg = s_g[warp];
+  __half* sa = s_a[warp];
+  const int KT8 = L.K / 8;
+  float acc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+  const int64_t c0 = (int64_t)blockIdx.x * kGemmChunk + warp * (kGemmChunk / 4);
+  const int64_t c1 = min(c0 + kGemmChunk / 4, M);
+  for (int64_t s0 = c0; s0 < c1; s0 += 16) {
+    {  // G block: 16 samples x 16 gradient columns of this m-tile
+      const int r = lane >> 1, seg = lane & 1;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (s0 + r < M) v = __ldg(reinterpret_cast<const uint4*>(grd + (s0 + r) * kGrdRow + L.grd_off + mtile * 16 + seg * 8));
+      *reinterpret_cast<uint4*>(sg + r * kT24 + seg * 8) = v;
+    }
+    for (int q = lane; q < 16 * KT8; q += 32) {  // A block: 16 samples x K layer inputs
+      const int r = q / KT8, seg = q % KT8;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (s0 + r < M) v = __ldg(reinterpret_cast<const uint4*>(act + (s0 + r) * kActRow + L.act_off + seg * 8));
+      *reinterpret_cast<uint4*>(sa + r * kS64 + seg * 8) = v;
+    }
+    __syncwarp();
+    uint32_t af[4];
+    {
+      const int j = lane >> 3, r = lane & 7;
+      ldmatrix_x4_trans(af, sg + ((j >> 1) * 8 + r) * kT24 + (j & 1) * 8);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (n < KT8) {
+        uint32_t b0, b1;
+        ldmatrix_x2_trans(b0, b1, sa + (lane & 15) * kS64 + n * 8);
+        mma16816(acc[n], af, b0, b1);
+      }
+    }
+    __syncwarp();
+  }
+  float* out = stage + L.img_off + (mtile * 16) * L.img_stride;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (n < KT8) {
+      const int c = n * 8 + t * 2;
+      atomicAdd(out + g * L.img_stride + c, acc[n][0]);
+      atomicAdd(out + g * L.img_stride + c + 1, acc[n][1]);
+      atomicAdd(out + (g + 8) * L.img_stride + c, acc[n][2]);
+      atomicAdd(out + (g + 8) * L.img_stride + c + 1, acc[n][3]);
+    }
+  }
+}
+
+// kernel image (fp32) -> tinycudann flat layouts, accumulated into the caller's gradient buffers
+__global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, float* __restrict__ g_base, float* __restrict__ g_head) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_base = 64 * 32 + 16 * 64, n_head = 64 * 32 + 64 * 64 + 16 * 64;
+  if (i < n_base) {
+    float v;
+    if (i < 2048) v = stage[kW1 + (i / 32) * kS32 + (i % 32)];
+    else { int j = i - 2048; v = stage[kW2 + (j / 64) * kS64 + (j % 64)]; }
+    g_base[i] += v;
+  } else if (i < n_base + n_head) {
+    int j = i - n_base;
+    float v;
+    if (j < 2048) {
+      int r = j / 32, c = j % 32;
+      int kc = c < 16 ? c : (c == 31 ? 16 : c + 1);   // tcnn [SH | feat | pad] -> kernel [SH | pad | feat]
+      v = stage[kW3 + r * kS32 + kc];
+    } else if (j < 2048 + 4096) { int q = j - 2048; v = stage[kW4 + (q / 64) * kS64 + (q % 64)]; }
+    else { int q = j - 2048 - 4096; v = stage[kW5 + (q / 64) * kS64 + (q % 64)]; }
+    g_head[j] += v;
+  }
+}
+
+}  // namespace qf
+
+using namespace qf;
+
+static size_t align256b(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" size_t qf_ngp_backward_workspace_bytes(int64_t M) {
+  return align256b(sizeof(__half) * kTTotal) + align256b(sizeof(float) * kWTotal) + align256b(sizeof(__half) * (size_t)M * kActRow) +
+         align256b(sizeof(__half) * (size_t)M * kGrdRow) + 1024;
+}
+
+extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const float* d_directions, const int64_t* d_ray_index,
+                               int64_t M, const float* d_grad_rgb, const float* d_grad_density, float* d_grad_table,
+                               float* d_grad_base_w, float* d_grad_head_w, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (M == 0) return QF_OK;
+  QF_REQUIRE(f && d_positions && d_directions && d_grad_rgb && d_grad_table && d_grad_base_w && d_grad_head_w && d_workspace,
+             "qf_ngp_backward: NULL argument");
+  QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_workspace;
+  __half* wt = (__half*)ws; ws += align256b(sizeof(__half) * kTTotal);
+  float* stage = (float*)ws; ws += align256b(sizeof(float) * kWTotal);
+  __half* act = (__half*)ws; ws += align256b(sizeof(__half) * (size_t)M * kActRow);
+  __half* grd = (__half*)ws;
+  transpose_weights_kernel<<<(int)ceil_div(kTTotal, 256), 256, 0, st>>>(f->d_weights, wt);
+  QF_CUDA_CHECK(cudaMemsetAsync(stage, 0, sizeof(float) * kWTotal, st));
+  BwdArgs a = {};
+  a.desc = f->desc; a.table = f->d_table; a.weights = f->d_weights; a.weights_t = wt;
+  a.pos = d_positions; a.pos_stride = 3; a.dirs = d_directions; a.ray64 = d_ray_index; a.M = M;
+  a.g_rgb = d_grad_rgb; a.g_sigma = d_grad_density; a.g_table = reinterpret_cast<float2*>(d_grad_table);
+  a.act = act; a.grd = grd;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+    attr_set = true;
+  }
+  int64_t tiles = ceil_div(M, 128);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * 2 ? tiles : (int64_t)kNumSMs * 2);
+  ngp_backward_kernel<<<blocks, 128, kBwdSmemBytes, st>>>(a);
+  QF_LAUNCH_CHECK();
+  dim3 grid((unsigned)ceil_div(M, kGemmChunk), 14);
+  weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
+  QF_LAUNCH_CHECK();
+  unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, d_grad_base_w, d_grad_head_w);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}

@@ -49,6 +49,47 @@ class _DirectionEncoding(nn.Module):
     n_output_dims = 16  # SphericalHarmonics degree 4 (ngp.py:694-707)
 
 
+class _NGPForwardFn(torch.autograd.Function):
+    """NGPRadianceField.forward under autograd: gradients for the flat tinycudann parameter tensors
+    (`mlp_base.params` = [MLP weights | grid table], `mlp_head.params`).  Positions / directions get no gradient."""
+
+    @staticmethod
+    def forward(ctx, field, positions, directions, ray_indices, base_params, head_params):
+        lib = _lib.load()
+        h = field._native()
+        pos = _lib.f32(positions.reshape(-1, 3))
+        dirs = _lib.f32(directions.reshape(-1, 3))
+        ri = _lib.i64(ray_indices) if ray_indices is not None else None
+        M = pos.shape[0]
+        rgb = torch.empty((M, 3), dtype=torch.float32, device=pos.device)
+        density = torch.empty((M, 1), dtype=torch.float32, device=pos.device)
+        _lib.check(lib.qf_ngp_forward(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(rgb), _lib.ptr(density),
+                                      _lib.stream(pos.device)), "qf_ngp_forward")
+        ctx.field = field
+        ctx.save_for_backward(pos, dirs, ri)
+        return rgb, density
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_density):
+        lib = _lib.load()
+        field = ctx.field
+        pos, dirs, ri = ctx.saved_tensors
+        M = pos.shape[0]
+        dev = pos.device
+        h = field._native()
+        g_base = torch.zeros_like(field.mlp_base.params)
+        g_head = torch.zeros_like(field.mlp_head.params)
+        if M:
+            g_rgb = _lib.f32(g_rgb) if g_rgb is not None else torch.zeros((M, 3), device=dev)
+            g_den = _lib.f32(g_density.reshape(-1)) if g_density is not None else None
+            nb = field._n_base
+            ws = _lib.workspace(dev, lib.qf_ngp_backward_workspace_bytes(M), "ngp_bwd")
+            _lib.check(lib.qf_ngp_backward(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(g_rgb), _lib.ptr(g_den),
+                                           _lib.ptr(g_base[nb:]), _lib.ptr(g_base[:nb]), _lib.ptr(g_head), _lib.ptr(ws), ws.numel(),
+                                           _lib.stream(dev)), "qf_ngp_backward")
+        return None, None, None, None, g_base, g_head
+
+
 _BASE_SHAPES = [(64, 32), (16, 64)]
 _HEAD_SHAPES = [(64, 32), (64, 64), (16, 64)]
 
@@ -155,14 +196,20 @@ class NGPRadianceField(nn.Module):
             return density, feat.view(shape + [15])
         return density
 
-    @torch.no_grad()
     def forward(self, positions: torch.Tensor, directions: torch.Tensor = None, ray_indices: torch.Tensor = None):
         """ngp.py:798-809 -> (rgb (M,3), density (M,1)).  `ray_indices` (extension): gather
-        directions[ray_indices] inside the kernel, as utils.py:515-529 does with a separate indexing op."""
+        directions[ray_indices] inside the kernel, as utils.py:515-529 does with a separate indexing op.
+        Differentiable w.r.t. the hash table and MLP weights (training mode)."""
         if not (self.use_viewdirs and (directions is not None)):
             raise NameError("name 'rgb' is not defined")  # what the reference does (quirk Q8, ngp.py:803-809)
         if ray_indices is None:
             assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
+        if torch.is_grad_enabled() and (self.mlp_base.params.requires_grad or self.mlp_head.params.requires_grad):
+            return _NGPForwardFn.apply(self, positions, directions, ray_indices, self.mlp_base.params, self.mlp_head.params)
+        with torch.no_grad():
+            return self._forward_nograd(positions, directions, ray_indices)
+
+    def _forward_nograd(self, positions, directions, ray_indices):
         lib = _lib.load()
         h = self._native()
         pos = _lib.f32(positions.reshape(-1, 3))

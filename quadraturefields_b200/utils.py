@@ -32,12 +32,44 @@ def inverse_of_compressed_sigma(alpha):
     return -torch.log(1 - alpha) / 0.005
 
 
-@torch.no_grad()
+class _DerivePropertiesFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, color, density, depths, delta, offsets, N, bg, bk):
+        lib = _lib.load()
+        dev = color.device
+        M = density.shape[0]
+        rgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        out_alpha = torch.empty((N, 1), dtype=torch.float32, device=dev)
+        Depth = torch.empty((N, 1), dtype=torch.float32, device=dev)
+        weights = torch.empty((M, 1), dtype=torch.float32, device=dev)
+        _lib.check(lib.qf_derive_properties(_lib.ptr(color), _lib.ptr(density), _lib.ptr(depths), delta, _lib.ptr(offsets), N, bg,
+                                            _lib.ptr(bk), _lib.ptr(rgb), _lib.ptr(out_alpha), _lib.ptr(Depth), _lib.ptr(weights),
+                                            _lib.stream(dev)), "qf_derive_properties")
+        ctx.save_for_backward(color, density, depths, offsets, bk)
+        ctx.meta = (delta, N, bg)
+        ctx.mark_non_differentiable(weights)
+        return rgb, out_alpha, Depth, weights
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_alpha, g_depth, _gw):
+        lib = _lib.load()
+        color, density, depths, offsets, bk = ctx.saved_tensors
+        delta, N, bg = ctx.meta
+        M = density.shape[0]
+        g_color, g_density = torch.empty_like(color), torch.empty_like(density)
+        c = lambda t: _lib.f32(t) if t is not None else None
+        _lib.check(lib.qf_derive_properties_backward(_lib.ptr(color), _lib.ptr(density), _lib.ptr(depths), delta, _lib.ptr(offsets),
+                                                     N, M, bg, _lib.ptr(bk), _lib.ptr(c(g_rgb)), _lib.ptr(c(g_alpha)),
+                                                     _lib.ptr(c(g_depth)), _lib.ptr(g_color), _lib.ptr(g_density),
+                                                     _lib.stream(color.device)), "qf_derive_properties_backward")
+        return g_color, g_density, None, None, None, None, None, None
+
+
 def derive_properties(color, density, depths, deltas, boundary, index_ray, render_bkgd=None, bg_color="white", N=0):
     """utils.py:863-898 -> (rgb (N,3), out_alpha (N,1), index_ray[boundary], Depth (N,1), weights (M,1)).
 
-    One kernel instead of 2 kaolin pack scans + 3 pack reductions + 3 scatters.  `deltas` is the constant
-    quadrature step (quirk Q4); a non-constant tensor is rejected."""
+    One kernel instead of 2 kaolin pack scans + 3 pack reductions + 3 scatters; differentiable w.r.t. color and
+    density.  `deltas` is the constant quadrature step (quirk Q4); a non-constant tensor is rejected."""
     lib = _lib.load()
     dev = color.device
     color = _lib.f32(color.reshape(-1, 3))
@@ -45,34 +77,30 @@ def derive_properties(color, density, depths, deltas, boundary, index_ray, rende
     depths = _lib.f32(depths.reshape(-1))
     M = density.shape[0]
     index_ray = _lib.i64(index_ray)
-    if isinstance(deltas, torch.Tensor):
-        if M and not bool((deltas == deltas.reshape(-1)[0]).all()):
-            raise NotImplementedError("derive_properties: the quadrature step is constant in every reference caller "
-                                      "(mesh_utils.py:225-231)")
-        delta = float(deltas.reshape(-1)[0]) if M else 0.0
-    else:
-        delta = float(deltas)
-    # packs are runs of equal index_ray; with ascending ids offsets come from a count + scan
-    cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
-    ids = index_ray[boundary]
-    if M:
-        starts = torch.nonzero(boundary).flatten()
-        ends = torch.cat([starts[1:], torch.tensor([M], device=dev)])
-        if bool((ids[1:] <= ids[:-1]).any()):
-            raise NotImplementedError("derive_properties expects ray-major (ascending index_ray) packs")
-        cnt[ids] = (ends - starts).to(torch.int32)
-    offsets = torch.empty((N + 1,), dtype=torch.int64, device=dev)
-    ws = _lib.workspace(dev, lib.qf_scan_workspace_bytes(N), "scan")
-    st = _lib.stream(dev)
-    _lib.check(lib.qf_hits_offsets(_lib.ptr(cnt), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), st), "qf_hits_offsets")
-    rgb = torch.empty((N, 3), dtype=torch.float32, device=dev)
-    out_alpha = torch.empty((N, 1), dtype=torch.float32, device=dev)
-    Depth = torch.empty((N, 1), dtype=torch.float32, device=dev)
-    weights = torch.empty((M, 1), dtype=torch.float32, device=dev)
-    bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else None
-    _lib.check(lib.qf_derive_properties(_lib.ptr(color), _lib.ptr(density), _lib.ptr(depths), delta, _lib.ptr(offsets),
-                                        N, _lib.BG_MODES.get(bg_color, 2), _lib.ptr(bk), _lib.ptr(rgb),
-                                        _lib.ptr(out_alpha), _lib.ptr(Depth), _lib.ptr(weights), st), "qf_derive_properties")
+    with torch.no_grad():
+        if isinstance(deltas, torch.Tensor):
+            if M and not bool((deltas == deltas.reshape(-1)[0]).all()):
+                raise NotImplementedError("derive_properties: the quadrature step is constant in every reference caller "
+                                          "(mesh_utils.py:225-231)")
+            delta = float(deltas.reshape(-1)[0]) if M else 0.0
+        else:
+            delta = float(deltas)
+        # packs are runs of equal index_ray; with ascending ids offsets come from a count + scan
+        cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
+        ids = index_ray[boundary]
+        if M:
+            starts = torch.nonzero(boundary).flatten()
+            ends = torch.cat([starts[1:], torch.tensor([M], device=dev)])
+            if bool((ids[1:] <= ids[:-1]).any()):
+                raise NotImplementedError("derive_properties expects ray-major (ascending index_ray) packs")
+            cnt[ids] = (ends - starts).to(torch.int32)
+        offsets = torch.empty((N + 1,), dtype=torch.int64, device=dev)
+        ws = _lib.workspace(dev, lib.qf_scan_workspace_bytes(N), "scan")
+        _lib.check(lib.qf_hits_offsets(_lib.ptr(cnt), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), _lib.stream(dev)),
+                   "qf_hits_offsets")
+        bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else None
+    rgb, out_alpha, Depth, weights = _DerivePropertiesFn.apply(color, density, depths, delta, offsets, N,
+                                                               _lib.BG_MODES.get(bg_color, 2), bk)
     return rgb, out_alpha, ids, Depth, weights
 
 
@@ -127,6 +155,26 @@ class MeshRenderer:
                        "qf_render_mesh_ngp")
         out["n_hits"] = hits
         return out
+
+
+def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="white", render_bkgd=None):
+    """Differentiable mesh-path render (train_finetune.py:494-509 with scaling=0): intersection (no gradient) ->
+    field at the hits (gradients to the hash table and MLPs) -> derive_properties.  -> (rgb (N,3), opacity (N,1), depth (N,1), n_hits)."""
+    N = origins.shape[0]
+    with torch.no_grad():
+        tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
+    dev = mesh_intersect.device
+    if tup is None:
+        fill = 0.0 if bg_color == "black" else 1.0
+        z = torch.zeros((N, 1), device=dev)
+        return torch.full((N, 3), fill, device=dev), z, z.clone(), 0
+    points, _, index_ray, depth, _, _, _ = tup
+    rgbs, sigmas = radiance_field(points, _lib.f32(viewdirs, dev), ray_indices=index_ray)
+    boundary = torch.ones_like(index_ray, dtype=torch.bool)
+    boundary[1:] = index_ray[1:] != index_ray[:-1]
+    rgb, opacity, _, depth_img, _ = derive_properties(rgbs, sigmas.squeeze(-1), depth, mesh_intersect.render_step_size, boundary,
+                                                      index_ray, render_bkgd=render_bkgd, bg_color=bg_color, N=N)
+    return rgb, opacity, depth_img, points.shape[0]
 
 
 def _flatten_rays(rays: Rays):

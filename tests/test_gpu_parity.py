@@ -482,3 +482,102 @@ def test_full_size_properties_c2(dev):
     sub = torch.randperm(N, generator=torch.Generator().manual_seed(1))[:1500]
     ref = O.render_mesh_ngp(o.cpu().numpy()[sub], d.cpu().numpy()[sub], sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
     assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
+
+
+# ----------------------------------------------------------------------------- training mode (fwd + bwd)
+def _grad_params(sc):
+    p = oracle_params(sc)
+    g = lambda t: t.clone().requires_grad_()
+    return O.NGPParams(p.aabb, p.meta, g(p.table), [g(w) for w in p.base_w], [g(w) for w in p.head_w])
+
+
+def _rel(a, b):
+    a, b = a.detach().cpu().double().flatten(), b.detach().cpu().double().flatten()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)), float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("round_hidden,tol,cos_min", [(True, 2e-3, 0.999999), (False, 4e-2, 0.9998)])
+def test_ngp_backward_matches_oracle_autograd(dev, smoke_scene, round_hidden, tol, cos_min):
+    """dL/d(table, MLP weights) from qf_ngp_backward vs PyTorch autograd through the oracle.
+    round_hidden=True: oracle with tcnn's precision (hidden activations rounded to fp16, straight-through) — the
+    kernel's arithmetic; gradients agree to 2e-3 of the largest entry.  round_hidden=False: strict fp32 oracle; ReLU
+    sign flips of pre-activations within fp16 rounding of zero make the gradient differ by ~2% (it is discontinuous
+    there), so the bar is 4e-2 and cosine 0.9998."""
+    sc = smoke_scene
+    O.ROUND_HIDDEN = round_hidden
+    o, d = _rays_for(sc, 0)
+    tup = O.sampling_raytrace(d, o, sc.vertices_np, sc.faces_np, sc.K)
+    g = torch.Generator().manual_seed(11)
+    x = torch.cat([T(tup[0]), (torch.rand(500, 3, generator=g) * 2 - 1) * 1.6])        # hits + random points, some outside the aabb
+    dirs = torch.cat([T(d)[T(tup[2])], torch.nn.functional.normalize(torch.randn(500, 3, generator=g), dim=-1)])
+    M = x.shape[0]
+    wr, ws = torch.randn(M, 3, generator=g), torch.randn(M, 1, generator=g) * 0.01
+    p = _grad_params(sc)
+    try:
+        rgb_r, den_r = O.ngp_forward(x, dirs, p)
+    finally:
+        O.ROUND_HIDDEN = False
+    ((rgb_r * wr).sum() + (den_r * ws).sum()).backward()
+    rf = sc.radiance_field
+    rf.zero_grad(set_to_none=True)
+    rgb, den = rf(x.to(dev), dirs.to(dev))
+    assert rgb.requires_grad and den.requires_grad
+    ((rgb * wr.to(dev)).sum() + (den * ws.to(dev)).sum()).backward()
+    nb = rf._n_base
+    pairs = {"base_w": (rf.mlp_base.params.grad[:nb], torch.cat([w.grad.flatten() for w in p.base_w])),
+             "table": (rf.mlp_base.params.grad[nb:], p.table.grad.flatten()),
+             "head_w": (rf.mlp_head.params.grad, torch.cat([w.grad.flatten() for w in p.head_w]))}
+    for name, (got, ref) in pairs.items():
+        err, cos = _rel(got, ref)
+        assert float(ref.abs().max()) > 0, name
+        assert err <= tol and cos >= cos_min, (name, err, cos)
+    # inference path is unchanged under no_grad
+    with torch.no_grad():
+        rgb2, den2 = rf(x.to(dev), dirs.to(dev))
+    assert maxabs(rgb2, rgb) == 0.0 and not rgb2.requires_grad
+
+
+def test_derive_properties_backward(dev, golden):
+    from quadraturefields_b200.utils import derive_properties
+    g = golden("derive_properties")
+    N = len(g["counts"])
+    gen = torch.Generator().manual_seed(2)
+    w_rgb, w_a, w_d = torch.randn(N, 3, generator=gen), torch.randn(N, 1, generator=gen), torch.randn(N, 1, generator=gen)
+    for bg in ("white", "black", "random"):
+        c_r, s_r = T(g["color"]).clone().requires_grad_(), T(g["density"]).clone().requires_grad_()
+        rgb, a, _, D, _ = O.derive_properties(c_r, s_r, T(g["depths"]), T(g["deltas"]), T(g["boundary"]), T(g["index_ray"]),
+                                              render_bkgd=T(g["bk"]), bg_color=bg, N=N)
+        ((rgb * w_rgb).sum() + (a * w_a).sum() + (D * w_d).sum()).backward()
+        c_d, s_d = T(g["color"]).to(dev).requires_grad_(), T(g["density"]).to(dev).requires_grad_()
+        rgb, a, _, D, _ = derive_properties(c_d, s_d, T(g["depths"]).to(dev), T(g["deltas"]).to(dev), T(g["boundary"]).to(dev),
+                                            T(g["index_ray"]).to(dev), render_bkgd=T(g["bk"]).to(dev), bg_color=bg, N=N)
+        ((rgb * w_rgb.to(dev)).sum() + (a * w_a.to(dev)).sum() + (D * w_d.to(dev)).sum()).backward()
+        assert maxabs(c_d.grad, c_r.grad) <= 1e-5
+        assert maxabs(s_d.grad, s_r.grad) <= 1e-5 * max(1.0, float(s_r.grad.abs().max()))
+
+
+def test_training_step_end_to_end(dev, smoke_scene):
+    """Mesh-path training step (train_finetune.py:494-531 semantics, no deformation): rays -> hits -> field -> composite
+    -> smooth-L1 loss -> gradients; compared with autograd through the oracle pipeline."""
+    from quadraturefields_b200.utils import render_train
+    sc = smoke_scene
+    o, d = _rays_for(sc, 1)
+    target = torch.rand(o.shape[0], 3, generator=torch.Generator().manual_seed(3))
+    p = _grad_params(sc)
+    O.ROUND_HIDDEN = True           # tcnn precision (see test_ngp_backward_matches_oracle_autograd)
+    try:
+        ref = O.render_mesh_ngp(o, d, sc.vertices_np, sc.faces_np, p, K=sc.K)
+    finally:
+        O.ROUND_HIDDEN = False
+    torch.nn.functional.smooth_l1_loss(ref["rgb"], target).backward()
+    rf = sc.radiance_field
+    rf.zero_grad(set_to_none=True)
+    rgb, opacity, depth, n_hits = render_train(sc.mesh_intersect, rf, T(o).to(dev), T(d).to(dev))
+    assert n_hits == ref["index_ray"].shape[0] and maxabs(rgb, ref["rgb"]) <= TOL_IMG
+    torch.nn.functional.smooth_l1_loss(rgb, target.to(dev)).backward()
+    nb = rf._n_base
+    for name, got, want in (("table", rf.mlp_base.params.grad[nb:], p.table.grad.flatten()),
+                            ("base_w", rf.mlp_base.params.grad[:nb], torch.cat([w.grad.flatten() for w in p.base_w])),
+                            ("head_w", rf.mlp_head.params.grad, torch.cat([w.grad.flatten() for w in p.head_w]))):
+        err, cos = _rel(got, want)
+        assert err <= 5e-3 and cos >= 0.99999, (name, err, cos)
