@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--views", type=int, default=200, help="resident ray sets cycled through (c2: 200 x 15.4 MB)")
     ap.add_argument("--cpu-sample", type=int, default=100, help="cpu_baseline renders a sample x sample sub-grid of one frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd training-step measurement (extra key 'train')")
+    ap.add_argument("--train-rays", type=int, default=1 << 18, help="rays per training batch per GPU (BASELINE configs[2])")
     return ap.parse_args()
 
 
@@ -272,6 +274,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = N * world * args.steps / (float(ms_e.item()) * 1e-3)
+    train = None if args.no_train else run_train_steps(args, sc, dev, rank, world, barrier)
     clk = clocks.stop() if clocks else None
 
     if rank == 0:
@@ -302,6 +305,8 @@ def run_ours(args):
                          "note": "gather is served from L2 (table L2-resident), so 'achieved' is an HBM-equivalent rate"},
             "clocks": clk,
         }
+        if train is not None:
+            line["train"] = train
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rps, detail, sec = cpu_render_sample(args.cpu_sample, threads, args.config)
@@ -313,6 +318,58 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_train_steps(args, sc, dev, rank, world, barrier):
+    """BASELINE configs[2]-shaped step (finetune semantics, train_finetune.py:494-531 without deformation): a batch of
+    random rays over all views -> mesh-path render with gradients -> smooth-L1 -> backward (hash table + MLPs) ->
+    NCCL all-reduce of the flat gradients -> Adam step.  Returns rays/s (fwd+bwd, all ranks) and ms/step."""
+    import torch
+    from quadraturefields_b200 import parallel as P
+    from quadraturefields_b200.utils import render_train
+    n = args.train_rays
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_views = min(32, len(sc.poses))
+    pool = [sc.rays(v) for v in range(n_views)]
+    O_all, D_all = torch.stack([p[0] for p in pool]), torch.stack([p[1] for p in pool])        # (V, N, 3)
+    rf = sc.radiance_field
+    params = [rf.mlp_base.params, rf.mlp_head.params]
+    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15, fused=True)
+    steps, warm = max(5, min(args.steps, 20)), 3
+    batches = []
+    for i in range(steps + warm):
+        vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
+        pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
+        batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous(), torch.rand((n, 3), device=dev, generator=g)))
+
+    def step(i):
+        o, d, target = batches[i]
+        opt.zero_grad(set_to_none=False)
+        rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d)
+        loss = torch.nn.functional.smooth_l1_loss(rgb, target)
+        loss.backward()
+        P.all_reduce_gradients(params, n)
+        opt.step()
+        return n_hits
+
+    for p_ in params:
+        p_.grad = torch.zeros_like(p_)
+    for i in range(warm):
+        step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hits = 0
+    for i in range(steps):
+        hits += step(warm + i)
+    e1.record()
+    barrier()
+    ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
+    n_params = sum(p_.numel() for p_ in params)
+    return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,
+            "steps": steps, "rays_per_step_per_gpu": n, "hits_per_ray": hits / (n * steps), "params": n_params,
+            "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+            "includes": "trace + field fwd + composite + loss + field/composite bwd + grad all-reduce + fused Adam step"}
 
 
 if __name__ == "__main__":

@@ -53,6 +53,7 @@ struct BwdArgs {
   int64_t M;
   const float* g_rgb;       // (M,3)
   const float* g_sigma;     // (M) or NULL
+  const float* g_absmax;    // device scalar: max |g_rgb| (for the fp16 dynamic-range scale)
   float2* g_table;          // (n_entries) float2, atomically accumulated
   __half* act;              // (M, kActRow)
   __half* grd;              // (M, kGrdRow)
@@ -127,6 +128,23 @@ __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __r
   }
 }
 
+// Gradients enter the fp16 tensor-core path scaled by a power of two that brings max|dL/drgb| to [0.5, 1) — what the
+// reference gets from torch GradScaler(2**10) (train_finetune.py) — and are unscaled in fp32 before they are accumulated.
+__device__ __forceinline__ float grad_scale_from(float absmax) {
+  if (!(absmax > 0.f) || !isfinite(absmax)) return 1.0f;
+  int e;
+  frexpf(absmax, &e);            // absmax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.0f, -e);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
 constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4 * 32 * 3 * 4;
 
 __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
@@ -146,6 +164,7 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
   }
   __syncthreads();
   const int64_t M = a.M;
+  const float gscale = grad_scale_from(__ldg(a.g_absmax)), ginv = 1.0f / gscale;
   __half* tile = s_tile_all + warp * 32 * kTileStride;
   float* sx = s_x_all + warp * 32 * 3;
   const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
@@ -240,7 +259,7 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
       // dL/d rgb logits = g_rgb * rgb (1 - rgb); lane t owns logit columns 2t, 2t+1 of rows g and g+8
       uint32_t ga[1][4] = {{0u, 0u, 0u, 0u}};
       if (t < 2) {
-        auto dsig = [](float v) { float s = 1.0f / (1.0f + __expf(-v)); return s * (1.0f - s); };
+        auto dsig = [gscale](float v) { float s = 1.0f / (1.0f + __expf(-v)); return gscale * s * (1.0f - s); };
         float gl0 = 0.f, gl1 = 0.f, gh0 = 0.f, gh1 = 0.f;
         if (r_lo < M) { gl0 = a.g_rgb[3 * r_lo + 2 * t] * dsig(acc5[0][0]); if (t == 0) gl1 = a.g_rgb[3 * r_lo + 1] * dsig(acc5[0][1]); }
         if (r_hi < M) { gh0 = a.g_rgb[3 * r_hi + 2 * t] * dsig(acc5[0][2]); if (t == 0) gh1 = a.g_rgb[3 * r_hi + 1] * dsig(acc5[0][3]); }
@@ -269,8 +288,8 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
       layer<4, 2>(gin, af, s_wt + kT3 + 16 * kS64, kS64, g, t);
       if (t == 0) {  // column 0 of the base output is the density logit: dL/dh0 = dL/dsigma * exp(min(h0-1, 15)) * selector
         float gs_lo = (a.g_sigma && r_lo < M) ? a.g_sigma[r_lo] : 0.f, gs_hi = (a.g_sigma && r_hi < M) ? a.g_sigma[r_hi] : 0.f;
-        gin[0][0] = ((selmask >> (mt * 16 + g)) & 1u) ? gs_lo * expf(fminf(h0_lo - 1.0f, 15.0f)) : 0.f;
-        gin[0][2] = ((selmask >> (mt * 16 + g + 8)) & 1u) ? gs_hi * expf(fminf(h0_hi - 1.0f, 15.0f)) : 0.f;
+        gin[0][0] = ((selmask >> (mt * 16 + g)) & 1u) ? gscale * gs_lo * expf(fminf(h0_lo - 1.0f, 15.0f)) : 0.f;
+        gin[0][2] = ((selmask >> (mt * 16 + g + 8)) & 1u) ? gscale * gs_hi * expf(fminf(h0_hi - 1.0f, 15.0f)) : 0.f;
       }
       store_c<2>(a.grd, kGrdRow, 64, r_lo, r_hi, M, gin, t);
       uint32_t g2[1][4];
@@ -293,8 +312,8 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         const int l = n * 4 + t;   // accumulator columns n*8 + 2t, +1 are the two features of level n*4 + t
-        if (r_lo < M) scatter_level(a.desc, a.g_table, l, xl[0], xl[1], xl[2], ge[n][0], ge[n][1]);
-        if (r_hi < M) scatter_level(a.desc, a.g_table, l, xh[0], xh[1], xh[2], ge[n][2], ge[n][3]);
+        if (r_lo < M) scatter_level(a.desc, a.g_table, l, xl[0], xl[1], xl[2], ge[n][0] * ginv, ge[n][1] * ginv);
+        if (r_hi < M) scatter_level(a.desc, a.g_table, l, xh[0], xh[1], xh[2], ge[n][2] * ginv, ge[n][3] * ginv);
       }
     }
     __syncwarp();
@@ -380,14 +399,16 @@ __global__ void __launch_bounds__(128) weight_grad_kernel(const __half* __restri
 }
 
 // kernel image (fp32) -> tinycudann flat layouts, accumulated into the caller's gradient buffers
-__global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, float* __restrict__ g_base, float* __restrict__ g_head) {
+__global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, const float* __restrict__ g_absmax,
+                                           float* __restrict__ g_base, float* __restrict__ g_head) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float ginv = 1.0f / grad_scale_from(__ldg(g_absmax));
   const int n_base = 64 * 32 + 16 * 64, n_head = 64 * 32 + 64 * 64 + 16 * 64;
   if (i < n_base) {
     float v;
     if (i < 2048) v = stage[kW1 + (i / 32) * kS32 + (i % 32)];
     else { int j = i - 2048; v = stage[kW2 + (j / 64) * kS64 + (j % 64)]; }
-    g_base[i] += v;
+    g_base[i] += v * ginv;
   } else if (i < n_base + n_head) {
     int j = i - n_base;
     float v;
@@ -397,7 +418,7 @@ __global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, floa
       v = stage[kW3 + r * kS32 + kc];
     } else if (j < 2048 + 4096) { int q = j - 2048; v = stage[kW4 + (q / 64) * kS64 + (q % 64)]; }
     else { int q = j - 2048 - 4096; v = stage[kW5 + (q / 64) * kS64 + (q % 64)]; }
-    g_head[j] += v;
+    g_head[j] += v * ginv;
   }
 }
 
@@ -408,7 +429,7 @@ using namespace qf;
 static size_t align256b(size_t x) { return (x + 255) / 256 * 256; }
 
 extern "C" size_t qf_ngp_backward_workspace_bytes(int64_t M) {
-  return align256b(sizeof(__half) * kTTotal) + align256b(sizeof(float) * kWTotal) + align256b(sizeof(__half) * (size_t)M * kActRow) +
+  return 256 + align256b(sizeof(__half) * kTTotal) + align256b(sizeof(float) * kWTotal) + align256b(sizeof(__half) * (size_t)M * kActRow) +
          align256b(sizeof(__half) * (size_t)M * kGrdRow) + 1024;
 }
 
@@ -421,6 +442,9 @@ extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const 
   QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)d_workspace;
+  float* gmax = (float*)ws; ws += 256;
+  QF_CUDA_CHECK(cudaMemsetAsync(gmax, 0, sizeof(float), st));
+  absmax_kernel<<<kNumSMs * 2, 256, 0, st>>>(d_grad_rgb, 3 * M, gmax);
   __half* wt = (__half*)ws; ws += align256b(sizeof(__half) * kTTotal);
   float* stage = (float*)ws; ws += align256b(sizeof(float) * kWTotal);
   __half* act = (__half*)ws; ws += align256b(sizeof(__half) * (size_t)M * kActRow);
@@ -430,7 +454,7 @@ extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const 
   BwdArgs a = {};
   a.desc = f->desc; a.table = f->d_table; a.weights = f->d_weights; a.weights_t = wt;
   a.pos = d_positions; a.pos_stride = 3; a.dirs = d_directions; a.ray64 = d_ray_index; a.M = M;
-  a.g_rgb = d_grad_rgb; a.g_sigma = d_grad_density; a.g_table = reinterpret_cast<float2*>(d_grad_table);
+  a.g_rgb = d_grad_rgb; a.g_sigma = d_grad_density; a.g_absmax = gmax; a.g_table = reinterpret_cast<float2*>(d_grad_table);
   a.act = act; a.grd = grd;
   static bool attr_set = false;
   if (!attr_set) {
@@ -444,7 +468,7 @@ extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const 
   dim3 grid((unsigned)ceil_div(M, kGemmChunk), 14);
   weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
   QF_LAUNCH_CHECK();
-  unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, d_grad_base_w, d_grad_head_w);
+  unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, d_grad_head_w);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }
