@@ -243,6 +243,42 @@ def intersect_firstk(origins, dirs, vertices, faces, K: int, pair_budget: int = 
     return tri, tt, count, total
 
 
+_C_LIB = None
+
+
+def _c_oracle():
+    """oracle/_ref/libqf_oracle.so (oracle/bruteforce.c, built by __graft_entry__.build()) or None."""
+    global _C_LIB
+    if _C_LIB is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "libqf_oracle.so")
+        _C_LIB = ctypes.CDLL(path) if os.path.exists(path) else False
+    return _C_LIB or None
+
+
+def intersect_firstk_c(origins, dirs, vertices, faces, K: int):
+    """Same contract and bit-identical results as `intersect_firstk`, through the C restatement (OpenMP)."""
+    import ctypes as C
+    lib = _c_oracle()
+    if lib is None:
+        raise RuntimeError("oracle/_ref/libqf_oracle.so missing: run __graft_entry__.build()")
+    o = np.ascontiguousarray(origins, dtype=np.float32)
+    d = np.ascontiguousarray(dirs, dtype=np.float32)
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    f = np.ascontiguousarray(faces, dtype=np.int32)
+    N, Fn = o.shape[0], f.shape[0]
+    tri = np.empty((N, K), dtype=np.int32)
+    tt = np.empty((N, K), dtype=np.float32)
+    count = np.empty(N, dtype=np.int32)
+    total = np.empty(N, dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.qf_oracle_intersect_firstk.restype = None
+    lib.qf_oracle_intersect_firstk(P(o), P(d), C.c_int64(N), P(v), P(f), C.c_int64(Fn), C.c_int(K),
+                                   C.c_float(float(mesh_box_pad(v))), P(tri), P(tt), P(count), P(total))
+    return tri, tt, count, total
+
+
 def plane_hit_points(o, r, n, v):
     """mesh_utils.py:33-40 ``ray_triangle_intersection``: d=−(n·v); t=−((n·o)+d)/(n·r); t←|t|; ψ=o+t r.  fp32."""
     o, r, n, v = (np.asarray(a, dtype=np.float32) for a in (o, r, n, v))
@@ -257,7 +293,10 @@ def plane_hit_points(o, r, n, v):
 def intersects_id(origins, vectors, vertices, faces, max_hits: int, threads: int = 1):
     """The `RayIntersector.intersects_id` contract (mesh_utils.py:87-109): flat
     (triangle_indices, ray_indices, psi) over all kept hits, ray-major in slot order."""
-    tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits, threads=threads)
+    if np.asarray(faces).shape[0] > 100000 and _c_oracle() is not None:   # big meshes: the C restatement (identical results)
+        tri, _, count, _ = intersect_firstk_c(origins, vectors, vertices, faces, max_hits)
+    else:
+        tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits, threads=threads)
     slot = np.arange(max_hits)[None, :] < count[:, None]
     ray_indices, _ = np.nonzero(slot)
     triangle_indices = tri[slot].astype(np.int64)

@@ -164,8 +164,8 @@ class Scene:
         return self.renderer.render(origins, viewdirs, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out,
                                     image_width=image_width)
 
-    def render_baked(self, origins, viewdirs, bg_color="white", out=None):
-        return self.baked_renderer.render(origins, viewdirs, bg_color=bg_color, out=out)
+    def render_baked(self, origins, viewdirs, bg_color="white", out=None, image_width=None):
+        return self.baked_renderer.render(origins, viewdirs, bg_color=bg_color, out=out, image_width=image_width)
 
 
 def make_scene(name: str = "c2", device="cuda", seed: int = 42, build_field: bool = True, **overrides) -> Scene:

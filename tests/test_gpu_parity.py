@@ -581,3 +581,45 @@ def test_training_step_end_to_end(dev, smoke_scene):
                             ("head_w", rf.mlp_head.params.grad, torch.cat([w.grad.flatten() for w in p.head_w]))):
         err, cos = _rel(got, want)
         assert err <= 5e-3 and cos >= 0.99999, (name, err, cos)
+
+
+# ----------------------------------------------------------------------------- full-size BASELINE configs[3] and [4]
+def test_full_size_c4_shelly_shaped(dev):
+    """BASELINE configs[3]: 1920x1080, 1.15 M-triangle shell mesh, K<=32, T=2^21.  Properties at full size + a ray
+    subsample against the oracle (C brute force over all 1.15 M triangles, bit-exact ids; images within 1e-3)."""
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c4", device=dev)
+    assert sc.faces_np.shape[0] == 14 * 81920 and sc.n_rays == 1920 * 1080 and sc.K == 32
+    o, d = sc.rays(1)
+    out = {k: v.clone() for k, v in sc.render(o.reshape(sc.H, sc.W, 3), d.reshape(sc.H, sc.W, 3)).items()}
+    N = sc.n_rays
+    assert bool(((out["opacity"] >= 0) & (out["opacity"] <= 1 + 1e-5)).all()) and bool(torch.isfinite(out["rgb"]).all())
+    tri, t, count = sc.mesh_intersect.rayintersector.trace(o, d, sc.K)
+    assert int(count.sum()) == int(out["n_hits"]) and int(count.max()) >= 24
+    tri16, _, count16 = sc.mesh_intersect.rayintersector.trace(o, d, 16)            # K truncation at full size
+    assert torch.equal(tri[:, :16], tri16) and torch.equal(torch.clamp(count, max=16), count16)
+    flat = sc.render(o, d)                                                          # untiled ray list == tiled image
+    assert torch.equal(flat["rgb"], out["rgb"]) and torch.equal(flat["opacity"], out["opacity"])
+    sub = torch.randperm(N, generator=torch.Generator().manual_seed(2))[:1200]
+    o_s, d_s = o.cpu().numpy()[sub], d.cpu().numpy()[sub]
+    tri_ref, _, count_ref, _ = O.intersect_firstk_c(o_s, d_s, sc.vertices_np, sc.faces_np, sc.K)
+    assert np.array_equal(tri.cpu().numpy()[sub], tri_ref) and np.array_equal(count.cpu().numpy()[sub], count_ref)
+    ref = O.render_mesh_ngp(o_s, d_s, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
+    assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
+
+
+def test_full_size_c5_baked_4k(dev):
+    """BASELINE configs[4]: 3840x2160 baked spherical-Gaussian render, 8192^2 texture set (L=3), 1.15 M triangles —
+    exercises the >2 M-ray chunking; a ray subsample is checked against the oracle."""
+    from quadraturefields_b200 import scene
+    sc = scene.make_scene("c5", device=dev, build_field=False)
+    assert sc.n_rays == 3840 * 2160 and sc.compressor.texture_size == 8192
+    o, d = sc.rays(0)
+    out = {k: v.clone() for k, v in sc.render_baked(o.reshape(sc.H, sc.W, 3), d.reshape(sc.H, sc.W, 3)).items()}
+    assert bool(((out["opacity"] >= 0) & (out["opacity"] <= 1 + 1e-5)).all()) and bool(torch.isfinite(out["rgb"]).all())
+    assert int(out["n_hits"]) > 4 * sc.n_rays
+    sub = torch.randperm(sc.n_rays, generator=torch.Generator().manual_seed(3))[:800]
+    ref = O.render_mesh_baked(o.cpu().numpy()[sub], d.cpu().numpy()[sub], sc.vertices_np, sc.faces_np, sc.uv_scaled,
+                              oracle_texture(sc), sc.K)
+    assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
+    assert maxabs(out["depth"].cpu()[sub], ref["depth"]) <= 2e-3

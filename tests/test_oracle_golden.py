@@ -137,3 +137,24 @@ def test_grid_meta_matches_survey():
     assert m.hashed.tolist() == [False] * 5 + [True] * 11
     m = O.make_grid_meta(log2_hashmap_size=21)
     assert m.n_entries == 22565520 and m.hashed.tolist() == [False] * 6 + [True] * 10
+
+
+def test_c_bruteforce_matches_numpy():
+    """oracle/bruteforce.c (used for the 1M-triangle parity tests) is bit-identical to the numpy oracle."""
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    verts, faces = O.shell_mesh([0.5, 0.8, 1.0], 3, seed=4)
+    f, cx, cy, W, H = O.pinhole_intrinsics(40, 40, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((2.0, -2.5, 1.5)), W, H, f, cx, cy)
+    rng = np.random.RandomState(0)
+    o2 = rng.uniform(-0.3, 0.3, size=(300, 3)).astype(np.float32)
+    d2 = np.zeros((300, 3), dtype=np.float32)
+    d2[np.arange(300), np.arange(300) % 3] = 1.0            # axis-aligned rays: infinities in the slab test
+    d2[150:] = rng.normal(size=(150, 3)).astype(np.float32)
+    o, d = np.concatenate([o, o2]), np.concatenate([d, d2])
+    for K in (1, 4, 32):
+        a = O.intersect_firstk(o, d, verts, faces, K)
+        b = O.intersect_firstk_c(o, d, verts, faces, K)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert a[3].max() >= 6
