@@ -62,7 +62,8 @@ struct qf_ngp {
   qf_grid_desc desc;
   int64_t n_entries = 0;
   __half2* d_table = nullptr;     // fp16 working copy, 2 features per entry
-  __half* d_weights = nullptr;    // fp16 working copy of all five matrices, smem-ready layout
+  __half* d_weights = nullptr;    // fp16 working copy of all five matrices, smem-ready layout (mma.sync kernels)
+  unsigned char* d_weights_tc = nullptr;  // the same matrices as UMMA K-major canonical images (tcgen05 kernel)
 };
 
 struct qf_texture {

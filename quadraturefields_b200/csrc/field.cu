@@ -10,6 +10,8 @@
 // n+1 (mma.sync m16n8k16, fp32 accumulate), so activations never touch shared or global memory.
 // The density logit uses a hi+lo fp16 split of the hidden activations, which keeps sigma within
 // ~1e-6 of the fp32 oracle.
+#include <stdlib.h>
+
 #include "field_common.cuh"
 
 namespace qf {
@@ -236,7 +238,27 @@ __global__ void hashgrid_forward_kernel(const qf_grid_desc desc, const __half2* 
   });
 }
 
+// field_tc.cu
+struct FieldTcArgs {
+  qf_grid_desc desc; const __half2* table; const unsigned char* weights_tc; const float* pos; int pos_stride; const float* dirs;
+  const int64_t* ray64; const int32_t* ray32; int ray32_stride; int64_t M; const int32_t* d_M; float4* out4; float* rgb; float* density;
+};
+int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st);
+int prep_weights_tc(qf_ngp* f, cudaStream_t st);
+
+// QF_FIELD_TC=0 selects the mma.sync kernel, 1 the tcgen05/TMEM kernel for the full forward
+static int field_tc_mode() {
+  static const int m = getenv("QF_FIELD_TC") ? atoi(getenv("QF_FIELD_TC")) : 0;
+  return m;
+}
+
 int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {
+  if (mode == 0 && field_tc_mode() == 1) {
+    FieldTcArgs t = {};
+    t.pos = a.pos; t.pos_stride = a.pos_stride; t.dirs = a.dirs; t.ray64 = a.ray64; t.ray32 = a.ray32; t.ray32_stride = a.ray32_stride;
+    t.M = a.M; t.d_M = a.d_M; t.out4 = a.out4; t.rgb = a.rgb; t.density = a.density;
+    return launch_ngp_forward_tc(f, t, st);
+  }
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights = f->d_weights;
@@ -262,7 +284,11 @@ int launch_ngp_forward_hits(const qf_ngp* f, const float4* hit_pd, const int2* h
 
 static int upload(qf_ngp* f, const float* d_table, const float* d_base_w, const float* d_head_w, cudaStream_t st) {
   if (d_table) prep_table_kernel<<<kNumSMs * 8, 256, 0, st>>>(d_table, f->n_entries, f->d_table);
-  if (d_base_w && d_head_w) prep_weights_kernel<<<(int)ceil_div(kWTotal, 256), 256, 0, st>>>(d_base_w, d_head_w, f->d_weights);
+  if (d_base_w && d_head_w) {
+    prep_weights_kernel<<<(int)ceil_div(kWTotal, 256), 256, 0, st>>>(d_base_w, d_head_w, f->d_weights);
+    QF_LAUNCH_CHECK();
+    return prep_weights_tc(f, st);
+  }
   QF_LAUNCH_CHECK();
   return QF_OK;
 }
@@ -283,7 +309,8 @@ extern "C" int qf_ngp_create(const qf_grid_desc* desc, const float* d_table, int
   f->desc = *desc;
   f->n_entries = n_entries;
   if (cudaMalloc((void**)&f->d_table, sizeof(__half2) * (size_t)n_entries) != cudaSuccess ||
-      cudaMalloc((void**)&f->d_weights, sizeof(__half) * kWTotal) != cudaSuccess) {
+      cudaMalloc((void**)&f->d_weights, sizeof(__half) * kWTotal) != cudaSuccess ||
+      cudaMalloc((void**)&f->d_weights_tc, 20480) != cudaSuccess) {
     set_error("qf_ngp_create: device allocation failed");
     qf_ngp_destroy(f);
     return QF_ERR_CUDA;
@@ -305,6 +332,7 @@ extern "C" void qf_ngp_destroy(qf_ngp* f) {
   if (!f) return;
   if (f->d_table) cudaFree(f->d_table);
   if (f->d_weights) cudaFree(f->d_weights);
+  if (f->d_weights_tc) cudaFree(f->d_weights_tc);
   delete f;
 }
 

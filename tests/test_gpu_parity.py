@@ -195,6 +195,44 @@ def test_ngp_forward_matches_oracle(dev, smoke_scene):
     assert maxabs(r, r2) == 0.0 and maxabs(s, s2) == 0.0
 
 
+def test_ngp_forward_tcgen05_variant(dev):
+    """The tcgen05 / TMEM variant of the fused field kernel (csrc/field_tc.cu, selected with QF_FIELD_TC=1) against the
+    oracle and against the default mma.sync kernel.  Runs in a subprocess because the selection is read once per process."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import os, sys, torch, numpy as np
+        sys.path.insert(0, os.getcwd())
+        from oracle import quadfield_oracle as O
+        from quadraturefields_b200 import scene
+        from tests.helpers import oracle_params, maxabs
+        dev = torch.device("cuda:0")
+        sc = scene.make_scene("smoke", device=dev)
+        p = oracle_params(sc)
+        g = torch.Generator().manual_seed(4)
+        x = (torch.rand(20011, 3, generator=g) * 2 - 1) * 1.2
+        x[:300] *= 1.4
+        d = torch.nn.functional.normalize(torch.randn(20011, 3, generator=g), dim=-1)
+        rgb_ref, dens_ref = O.ngp_forward(x, d, p)
+        with torch.no_grad():
+            rgb, dens = sc.radiance_field(x.to(dev), d.to(dev))
+            for n in (1, 127, 128, 129):
+                r, s = sc.radiance_field(x[:n].to(dev), d[:n].to(dev))
+                assert maxabs(r, rgb[:n]) == 0.0 and maxabs(s, dens[:n]) == 0.0
+        a_ref, a = 1 - torch.exp(-dens_ref * 0.005), 1 - torch.exp(-dens.cpu() * 0.005)
+        assert maxabs(rgb, rgb_ref) <= 1e-3 and maxabs(a, a_ref) <= 2e-4, (maxabs(rgb, rgb_ref), maxabs(a, a_ref))
+        o, dd = O.generate_rays(sc.poses[0], sc.W, sc.H, np.float32(sc.focal), np.float32(sc.cx), np.float32(sc.cy))
+        ref = O.render_mesh_ngp(o, dd, sc.vertices_np, sc.faces_np, p, K=sc.K)
+        out = sc.render(torch.from_numpy(o).to(dev), torch.from_numpy(dd).to(dev))
+        assert int(out["n_hits"]) == ref["index_ray"].shape[0]
+        assert maxabs(out["rgb"], ref["rgb"]) <= 1e-3 and maxabs(out["opacity"], ref["opacity"]) <= 1e-3
+        print("TC_OK")
+    """)
+    env = dict(os.environ, QF_FIELD_TC="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=280)
+    assert res.returncode == 0 and "TC_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
+
+
 def test_ngp_golden_fixture(dev, golden):
     """tests/golden/ngp.npz: the reference's NGPRadianceField module run over the tinycudann stand-in."""
     from quadraturefields_b200.radiance_fields.ngp import NGPRadianceField
