@@ -133,7 +133,7 @@ _workspaces = {}
 
 def workspace(device, nbytes: int, tag: str = "default") -> torch.Tensor:
     """Grow-only uint8 scratch buffer per (device, tag); the C ABI never allocates caller-visible memory."""
-    key = (str(device), tag)
+    key = (str(device), tag, torch.cuda.current_stream(device).cuda_stream)   # streams must not share scratch
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

@@ -262,8 +262,9 @@ int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st)
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights = f->d_weights;
-  int64_t tiles = a.d_M ? (int64_t)kNumSMs * 3 * 4 : ceil_div(a.M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 * 4 ? tiles : (int64_t)kNumSMs * 3 * 4);
+  static const int per_sm = getenv("QF_SHADE_BLOCKS_PER_SM") ? atoi(getenv("QF_SHADE_BLOCKS_PER_SM")) : 5;   // one resident wave: 5 CTAs/SM at 96 registers
+  int64_t tiles = a.d_M ? (int64_t)kNumSMs * per_sm : ceil_div(a.M, 128);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
   if (blocks < 1) blocks = 1;
   if (mode == 0) ngp_forward_kernel<0><<<blocks, 128, 0, st>>>(a);
   else ngp_forward_kernel<1><<<blocks, 128, 0, st>>>(a);
