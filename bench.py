@@ -307,6 +307,12 @@ def run_ours(args):
         hits_per_launch = float(iso_hits.sum().item()) / max(nch.value, 1)
         shade_ms_overlapped = ms3o[1] / max(ncho.value, 1)
         achieved = 512.0 * hits_per_launch / (shade_ms * 1e-3) / 1e9 if shade_ms > 0 else 0.0
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+            traffic = next((v for k, v in tj["dram_bytes_per_launch"].items() if "ngp_forward_kernel<0>" in k), None)
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -324,7 +330,7 @@ def run_ours(args):
                                                   "composite": ms3o[2] / max(ncho.value, 1),
                                                   "note": "frames alternate on 2 streams, so kernels of neighbouring frames overlap"},
             "roofline": {"bound": "hbm", "kernel": "ngp_forward_kernel<0> (hash-grid gather + fused MLPs)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_hit": 512, "hits_per_launch": hits_per_launch, "peak_source": peak_src,
                          "achieved_in_timed_region": (512.0 * hits_per_launch / (shade_ms_overlapped * 1e-3) / 1e9) if shade_ms_overlapped > 0 else 0.0,
                          "note": "kernel timed alone with CUDA events on its stream in the same process (in the timed region it overlaps the "

@@ -19,8 +19,15 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 lines = [f"# ncu summary `{tag}`", "",
          "Source: `ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --views 8 "
          "--no-cpu-baseline` (B200, one GPU).  Per-launch values; cold-cache, serialised — compare shares, not absolutes.", ""]
+import os
 raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
+if os.path.exists(f"gpurun_out/prof_train_{tag}.ncu-rep"):
+    raw2 = subprocess.run(["ncu", "-i", f"gpurun_out/prof_train_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows2 = list(csv.reader(io.StringIO(raw2)))
+    if rows2 and rows and rows2[0] == rows[0]:
+        rows += rows2[2:]
+traffic = {}
 if rows:
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -30,6 +37,12 @@ if rows:
         if name in seen:
             continue
         seen.add(name)
+        try:
+            scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = idx["dram__bytes_read.sum"], idx["dram__bytes_write.sum"]
+            traffic[name.replace("void ", "").replace("qf::", "")] = float(r[rd]) * scale.get(units[rd], 1) + float(r[wr]) * scale.get(units[wr], 1)
+        except Exception:
+            pass
         lines += [f"## `{name}`", "", "| metric | value | unit |", "|---|---|---|"]
         for w in WANT:
             if w in idx:
@@ -54,5 +67,8 @@ try:
         f.write(open(f"gpurun_out/launches_{tag}.csv").read())
 except FileNotFoundError:
     pass
+import json
+json.dump({"tag": tag, "dram_bytes_per_launch": traffic, "source": "ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum"},
+          open("profiles/roofline_traffic.json", "w"), indent=1)
 open(out_md, "w").write("\n".join(lines))
 print("wrote", out_md)
