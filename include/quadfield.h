@@ -61,8 +61,12 @@ int qf_mesh_info(const qf_mesh* mesh, int64_t* info4, float* box_pad);
 /* `find_intersections`: first K hits of every ray ordered by (t, triangle id); d_tri is the
  * reference's int[N*max_hits] with -1 padding (mesh_utils.py:91-96).  d_t (may be NULL) gets the
  * Möller–Trumbore t (+inf padded), d_count min(total,K), d_total (may be NULL) the untruncated count. */
+/* d_workspace (>= qf_trace_workspace_bytes(n_rays), may be NULL): scratch for the incoherent-ray path — rays that miss
+ * the scene box are dropped up front and persistent warps refill finished lanes; results are identical without it. */
+size_t qf_trace_workspace_bytes(int64_t n_rays);
 int qf_trace_firstk(const qf_mesh* mesh, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
-                    int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* stream);
+                    int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* d_workspace,
+                    size_t workspace_bytes, void* stream);
 
 /* Exclusive scan of d_count into d_offsets[n_rays+1] (ray-major hit layout).  workspace >= qf_scan_workspace_bytes. */
 size_t qf_scan_workspace_bytes(int64_t n);

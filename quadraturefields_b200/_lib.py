@@ -33,7 +33,8 @@ _SIGS = {
     "qf_mesh_update_vertices": (_I, [_P, _P, _P]),
     "qf_mesh_destroy": (None, [_P]),
     "qf_mesh_info": (_I, [_P, C.POINTER(_L), C.POINTER(_F)]),
-    "qf_trace_firstk": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _P]),
+    "qf_trace_workspace_bytes": (_SZ, [_L]),
+    "qf_trace_firstk": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_scan_workspace_bytes": (_SZ, [_L]),
     "qf_hits_offsets": (_I, [_P, _L, _P, _P, _SZ, _P]),
     "qf_hits_total": (_I, [_P, _L, C.POINTER(_L), _P]),
@@ -133,6 +134,8 @@ _workspaces = {}
 
 def workspace(device, nbytes: int, tag: str = "default") -> torch.Tensor:
     """Grow-only uint8 scratch buffer per (device, tag); the C ABI never allocates caller-visible memory."""
+    if torch.device(device).type != "cuda":
+        raise RuntimeError("quadraturefields_b200 ops take CUDA tensors only (no CPU path)")
     key = (str(device), tag, torch.cuda.current_stream(device).cuda_stream)   # streams must not share scratch
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:

@@ -237,20 +237,43 @@ __global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, const flo
   nodes[3] = make_float4(__int_as_float(~0), __int_as_float(kEmptyRef), 0.f, 0.f);
 }
 
-template <int KMAX, bool COUNT_ALL>
-__global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
-                                                    const float* __restrict__ origins, const float* __restrict__ dirs,
-                                                    int64_t N, int K, int32_t* __restrict__ out_tri,
-                                                    float* __restrict__ out_t, int32_t* __restrict__ out_count,
-                                                    int32_t* __restrict__ out_total) {
-  __shared__ int s_stack[4][kStackDepth];
+// Pre-pass over a ray list.  slot[0] += warps (32 consecutive rays) that would traverse as a packet, slot[1] += warps,
+// slot[3] = number of rays whose slab test against the whole scene box passes; their ids are compacted into `list`.
+// The outputs are pre-filled with "no hit" (memsets), so the refill kernel only writes rays that have hits.
+__global__ void classify_rays_kernel(const float* __restrict__ scene, const float* __restrict__ origins,
+                                     const float* __restrict__ dirs, int64_t N, int32_t* __restrict__ slot,
+                                     int32_t* __restrict__ list) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const bool valid = i < N;
   Ray r = make_ray(origins, dirs, valid ? i : N - 1);
-  HitBuf<KMAX> hb;
-  int total;
-  trace_ray<KMAX, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
-  if (!valid) return;
+  const bool coh = warp_is_coherent(r, valid);
+  // all padded triangle boxes lie inside [scene_lo - pad, scene_hi + pad]: by monotonicity a ray that fails this slab
+  // test fails every triangle's own box test
+  const float pad = __ldg(scene + 6);
+  float tn, tf;
+  const bool in_scene = valid && slab(r, __fsub_rn(__ldg(scene), pad), __fsub_rn(__ldg(scene + 1), pad), __fsub_rn(__ldg(scene + 2), pad),
+                                      __fadd_rn(__ldg(scene + 3), pad), __fadd_rn(__ldg(scene + 4), pad), __fadd_rn(__ldg(scene + 5), pad), tn, tf);
+  const unsigned m = __ballot_sync(0xffffffffu, in_scene);
+  int base = 0;
+  if (lane == 0 && valid) {
+    atomicAdd(slot + 1, 1);
+    if (coh) atomicAdd(slot, 1);
+    if (m && list) base = atomicAdd(slot + 3, __popc(m));
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (in_scene && list) list[base + __popc(m & ((1u << lane) - 1u))] = (int32_t)i;
+}
+
+__global__ void fill_inf_kernel(float* __restrict__ p, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = __int_as_float(0x7f800000);
+}
+__device__ __forceinline__ bool mostly_coherent(const int32_t* slot) { return 2 * __ldg(slot) >= __ldg(slot + 1); }
+
+template <int KMAX>
+__device__ __forceinline__ void write_hits(const HitBuf<KMAX>& hb, int total, int64_t i, int K, int32_t* __restrict__ out_tri,
+                                           float* __restrict__ out_t, int32_t* __restrict__ out_count,
+                                           int32_t* __restrict__ out_total) {
 #pragma unroll
   for (int s = 0; s < KMAX; ++s) {
     if (s >= KMAX - K) {
@@ -261,6 +284,82 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
   }
   out_count[i] = hb.count(K);
   if (out_total) out_total[i] = total;
+}
+
+// Incoherent ray lists (training batches of random pixels): persistent warps whose lanes fetch a new ray as soon as
+// enough of them have finished, so one long ray no longer idles the other 31 lanes (thread efficiency was 3.4 / 32
+// with one ray per thread, profiles/r1c).  Runs only when classify_rays_kernel found the list mostly incoherent.
+template <int KMAX, bool COUNT_ALL>
+__global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                           const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                           int64_t N, int K, int32_t* __restrict__ out_tri,
+                                                           float* __restrict__ out_t, int32_t* __restrict__ out_count,
+                                                           int32_t* __restrict__ out_total, int32_t* __restrict__ slot,
+                                                           const int32_t* __restrict__ list) {
+  if (mostly_coherent(slot)) return;
+  N = __ldg(slot + 3);   // rays that reach the scene box; the rest keep the pre-filled "no hit"
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int sref[kStackDepth];
+  float stn[kStackDepth];
+  HitBuf<KMAX> hb;
+  Ray r;
+  int64_t ri = -1;
+  int sp = 0, cur = kDoneRef, total = 0;
+  float cur_tn = 0.f;
+  bool exhausted = false;
+  hb.init(K);
+  while (true) {
+    const unsigned idle = __ballot_sync(0xffffffffu, ri < 0);
+    if (!exhausted && __popc(idle) >= 12) {
+      const int n = __popc(idle);
+      int base = 0;
+      if (lane == 0) base = atomicAdd(slot + 2, n);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int64_t mine = (int64_t)base + __popc(idle & lt);
+      if (ri < 0 && mine < N) {
+        ri = __ldg(list + mine);
+        r = make_ray(origins, dirs, ri);
+        hb.init(K);
+        total = 0; sp = 0; cur = 0; cur_tn = 0.f;
+      }
+      exhausted = (int64_t)base + n >= N;
+    }
+    if (__all_sync(0xffffffffu, ri < 0)) { if (exhausted) break; else continue; }
+    int steps = 0;
+    while (ri >= 0 && cur >= 0 && cur != kDoneRef && steps < 24) {
+      single_node_step<KMAX, !COUNT_ALL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
+      ++steps;
+    }
+    while (ri >= 0 && cur < 0) {
+      const float tcull = COUNT_ALL ? __int_as_float(0x7f800000) : hb.cull_distance();
+      if (cur_tn <= tcull) leaf_intersect<KMAX>(r, tris, cur, cur_tn, hb, total);
+      if (sp) { cur = sref[--sp]; cur_tn = stn[sp]; }
+      else cur = kDoneRef;
+    }
+    if (ri >= 0 && cur == kDoneRef) {
+      if (total > 0) write_hits<KMAX>(hb, total, ri, K, out_tri, out_t, out_count, out_total);
+      ri = -1;
+    }
+  }
+}
+
+template <int KMAX, bool COUNT_ALL>
+__global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+                                                    const float* __restrict__ origins, const float* __restrict__ dirs,
+                                                    int64_t N, int K, int32_t* __restrict__ out_tri,
+                                                    float* __restrict__ out_t, int32_t* __restrict__ out_count,
+                                                    int32_t* __restrict__ out_total, const int32_t* __restrict__ slot) {
+  if (!mostly_coherent(slot)) return;   // trace_refill_kernel handles this list
+  __shared__ int s_stack[4][kStackDepth];
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const bool valid = i < N;
+  Ray r = make_ray(origins, dirs, valid ? i : N - 1);
+  HitBuf<KMAX> hb;
+  int total;
+  trace_ray<KMAX, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
+  if (!valid) return;
+  write_hits<KMAX>(hb, total, i, K, out_tri, out_t, out_count, out_total);
 }
 
 // ---------------------------------------------------------------- tuple packing (a3)
@@ -396,6 +495,7 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
   QF_A(dev_alloc(&m->d_last, F, &m->bytes));
   QF_A(dev_alloc(&m->d_flags, F + 8, &m->bytes));
   QF_A(dev_alloc(&m->d_ibox, 2 * F, &m->bytes));
+  QF_A(dev_alloc(&m->d_call_slots, 4 * kCallSlots, &m->bytes));
 #undef QF_A
   if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
   size_t tmp = 0;
@@ -431,7 +531,7 @@ extern "C" void qf_mesh_destroy(qf_mesh* m) {
   if (!m) return;
   void* ptrs[] = {m->d_vertices, m->d_faces, m->d_tris, m->d_planes, m->d_nodes, m->d_scene, m->d_keys, m->d_keys_sorted,
                   m->d_idx, m->d_idx_sorted, m->d_left, m->d_right, m->d_parent, m->d_leaf_parent, m->d_first, m->d_last,
-                  m->d_flags, m->d_ibox, m->d_sort_tmp};
+                  m->d_flags, m->d_ibox, m->d_sort_tmp, m->d_call_slots};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
 }
@@ -443,14 +543,35 @@ extern "C" int qf_mesh_info(const qf_mesh* m, int64_t* info4, float* box_pad) {
   return QF_OK;
 }
 
+extern "C" size_t qf_trace_workspace_bytes(int64_t n_rays) { return 256 + sizeof(int32_t) * (size_t)(n_rays > 0 ? n_rays : 0) + 256; }
+
 extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
-                               int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* stream) {
+                               int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* d_workspace,
+                               size_t workspace_bytes, void* stream) {
   QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count, "qf_trace_firstk: NULL argument");
   QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_trace_firstk: K=%d outside [1,%d]", K, QF_MAX_HITS);
   if (n_rays == 0) return QF_OK;
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)ceil_div(n_rays, 128);
-#define QF_TRACE(KM, ALL) trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total)
+  // caller scratch: [slot: 4 ints | compacted ray ids]; without it the list always takes the thread-per-ray kernel
+  const bool have_ws = d_workspace && workspace_bytes >= qf_trace_workspace_bytes(n_rays);
+  int32_t* slot = have_ws ? (int32_t*)d_workspace : m->d_call_slots + 4 * (m->call_id++ % kCallSlots);
+  int32_t* list = have_ws ? (int32_t*)d_workspace + 64 : nullptr;
+  QF_CUDA_CHECK(cudaMemsetAsync(slot, 0, 4 * sizeof(int32_t), st));
+  if (have_ws) {   // without scratch slot[0] = slot[1] = 0 reads as "coherent" (2*0 >= 0): thread-per-ray kernel only
+    classify_rays_kernel<<<blocks, 128, 0, st>>>(m->d_scene, d_origins, d_dirs, n_rays, slot, list);
+    // "no hit" defaults for the rays the refill kernel never writes: tri = -1, count = total = 0, t = +inf
+    QF_CUDA_CHECK(cudaMemsetAsync(d_tri, 0xFF, sizeof(int32_t) * n_rays * K, st));
+    QF_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(int32_t) * n_rays, st));
+    if (d_total) QF_CUDA_CHECK(cudaMemsetAsync(d_total, 0, sizeof(int32_t) * n_rays, st));
+    if (d_t) fill_inf_kernel<<<kNumSMs * 4, 256, 0, st>>>(d_t, n_rays * K);
+  }
+  const int pblocks = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;   // persistent grid of the refill kernel
+#define QF_TRACE(KM, ALL)                                                                                                         \
+  do {                                                                                                                            \
+    trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot); \
+    if (have_ws) trace_refill_kernel<KM, ALL><<<pblocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, list); \
+  } while (0)
   // the untruncated total needs a traversal without distance culling
   if (d_total) { if (K <= 8) QF_TRACE(8, true); else if (K <= 16) QF_TRACE(16, true); else QF_TRACE(32, true); }
   else { if (K <= 8) QF_TRACE(8, false); else if (K <= 16) QF_TRACE(16, false); else QF_TRACE(32, false); }

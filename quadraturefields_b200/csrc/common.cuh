@@ -54,9 +54,12 @@ struct qf_mesh {
   float4* d_ibox = nullptr;       // 2 x float4 per internal node (lo, hi)
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
+  int32_t* d_call_slots = nullptr;  // ring of per-call scratch: [coherent chunks, total chunks, ray counter, pad]
+  mutable unsigned call_id = 0;
   size_t bytes = 0;
   float h_pad = 0.f;
 };
+constexpr int kCallSlots = 64;
 
 struct qf_ngp {
   qf_grid_desc desc;

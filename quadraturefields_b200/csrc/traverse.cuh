@@ -71,6 +71,30 @@ __device__ __forceinline__ void leaf_intersect(const Ray& r, const float4* __res
 constexpr int kDoneRef = 0x7fffffff;
 constexpr int kStackDepth = 96;   // LBVH depth <= 64 Morton bits + 32 index bits
 
+// One internal-node step of the per-lane traversal (shared by traverse_single and the refill kernel).
+template <int KMAX, bool CULL>
+__device__ __forceinline__ void single_node_step(const Ray& r, const float4* __restrict__ nodes, const HitBuf<KMAX>& hb,
+                                                 int* sref, float* stn, int& sp, int& cur, float& cur_tn) {
+  const float inf = __int_as_float(0x7f800000);
+  const float4* np = nodes + 4 * (int64_t)cur;
+  float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
+  int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
+  float tn0, tf0, tn1, tf1;
+  const float tcull = CULL ? hb.cull_distance() : inf;
+  bool h0 = (r0 != kEmptyRef) && slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0) && (tn0 <= tcull);
+  bool h1 = (r1 != kEmptyRef) && slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1) && (tn1 <= tcull);
+  if (h0 && h1) {
+    const bool swap = tn1 < tn0;
+    sref[sp] = swap ? r0 : r1;
+    stn[sp++] = swap ? tn0 : tn1;
+    cur = swap ? r1 : r0;
+    cur_tn = swap ? tn1 : tn0;
+  } else if (h0) { cur = r0; cur_tn = tn0; }
+  else if (h1) { cur = r1; cur_tn = tn1; }
+  else if (sp) { cur = sref[--sp]; cur_tn = stn[sp]; }
+  else cur = kDoneRef;
+}
+
 // ---------------------------------------------------------------- per-lane while-while traversal
 template <int KMAX, bool CULL = true>
 __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __restrict__ nodes,
@@ -84,25 +108,8 @@ __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __re
   hb.init(K);
   const float inf = __int_as_float(0x7f800000);
   while (cur != kDoneRef) {
-    while (cur >= 0 && cur != kDoneRef) {   // ---- internal nodes, until this lane holds a leaf
-      const float4* np = nodes + 4 * (int64_t)cur;
-      float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3);
-      int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
-      float tn0, tf0, tn1, tf1;
-      const float tcull = CULL ? hb.cull_distance() : inf;
-      bool h0 = (r0 != kEmptyRef) && slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0) && (tn0 <= tcull);
-      bool h1 = (r1 != kEmptyRef) && slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1) && (tn1 <= tcull);
-      if (h0 && h1) {
-        const bool swap = tn1 < tn0;         // nearer child first so the cull distance tightens early
-        sref[sp] = swap ? r0 : r1;
-        stn[sp++] = swap ? tn0 : tn1;
-        cur = swap ? r1 : r0;
-        cur_tn = swap ? tn1 : tn0;
-      } else if (h0) { cur = r0; cur_tn = tn0; }
-      else if (h1) { cur = r1; cur_tn = tn1; }
-      else if (sp) { cur = sref[--sp]; cur_tn = stn[sp]; }
-      else cur = kDoneRef;
-    }
+    while (cur >= 0 && cur != kDoneRef)     // ---- internal nodes, until this lane holds a leaf
+      single_node_step<KMAX, CULL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
     while (cur < 0) {                        // ---- leaves, warp reconverged (kDoneRef is positive)
       const float tcull = CULL ? hb.cull_distance() : inf;
       if (cur_tn <= tcull) leaf_intersect<KMAX>(r, tris, cur, cur_tn, hb, total);

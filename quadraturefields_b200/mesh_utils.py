@@ -117,8 +117,10 @@ class RayIntersector:
         t = torch.empty((N, K), dtype=torch.float32, device=self.device)
         count = torch.empty((N,), dtype=torch.int32, device=self.device)
         total = torch.empty((N,), dtype=torch.int32, device=self.device) if with_total else None
+        ws = _lib.workspace(self.device, lib.qf_trace_workspace_bytes(N), "trace")
         _lib.check(lib.qf_trace_firstk(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(t),
-                                       _lib.ptr(count), _lib.ptr(total), _lib.stream(self.device)), "qf_trace_firstk")
+                                       _lib.ptr(count), _lib.ptr(total), _lib.ptr(ws), ws.numel(), _lib.stream(self.device)),
+                   "qf_trace_firstk")
         return (tri, t, count, total) if with_total else (tri, t, count)
 
     @torch.no_grad()

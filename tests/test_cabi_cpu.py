@@ -45,7 +45,7 @@ def test_argument_validation_without_gpu(lib):
     h = ctypes.c_void_p()
     assert L.qf_mesh_create(None, 0, None, 0, None, ctypes.byref(h)) == 1
     assert b"empty mesh" in L.qf_last_error()
-    assert L.qf_trace_firstk(None, None, None, 10, 8, None, None, None, None, None) == 1
+    assert L.qf_trace_firstk(None, None, None, 10, 8, None, None, None, None, None, 0, None) == 1
     assert L.qf_render_weights(7, None, None, None, None, 1, 1, None, None, None, None, None) == 1
     assert b"mode=7" in L.qf_last_error()
 
