@@ -119,6 +119,9 @@ void qf_ngp_destroy(qf_ngp* f);
 
 /* tcnn HashGrid forward alone: x01 (M,3) in [0,1] -> (M, 2*n_levels) fp32 holding fp16-rounded features. */
 int qf_hashgrid_forward(const qf_ngp* f, const float* d_x01, int64_t M, float* d_enc, void* stream);
+/* tcnn HashGrid backward alone: ACCUMULATES dL/dtable (n_entries,2) from dL/denc (M, 2*n_levels) at x01 (M,3). */
+int qf_hashgrid_backward(const qf_ngp* f, const float* d_x01, const float* d_grad_enc, int64_t M, float* d_grad_table,
+                         void* stream);
 /* `NGPRadianceField.query_density(x, return_feat)` (ngp.py:757-779): d_feat (M,15) may be NULL. */
 int qf_ngp_query_density(const qf_ngp* f, const float* d_positions, int64_t M, float* d_density, float* d_feat,
                          void* stream);
@@ -151,6 +154,11 @@ int qf_texture_create(int size, int num_lobes, const uint8_t* d_alpha, const uin
 void qf_texture_destroy(qf_texture* t);
 /* get_features_from_texture_map: indices (M,2) int64 -> features (M, 3+7L+1) fp32 */
 int qf_texture_decode(const qf_texture* t, const int64_t* d_indices, int64_t M, float* d_features, void* stream);
+/* The bake writer `FeatureCompression.compress` / `assign_values_to_texture_map` (texture_utils.py:67-106):
+ * quantise feature rows (M, 3+7L+1) into the uint8 planes, at row i (d_indices NULL) or at texel d_indices[i] of SxS planes. */
+int qf_texture_compress(const float* d_features, int64_t M, int num_lobes, int colour_logit, float lambda_thres,
+                        const int64_t* d_indices, int texture_size, uint8_t* d_alpha, uint8_t* d_diffuse,
+                        uint8_t* const* h_d_colors, uint8_t* const* h_d_lambdas, void* stream);
 /* features_to_rgb: features (M, 3+7L[+1]) with row stride `stride` floats, dirs (M,3) -> rgb (M,3) */
 int qf_sg_features_to_rgb(const float* d_features, int64_t stride, int num_lobes, const float* d_dirs, int64_t M,
                           float* d_rgb, void* stream);

@@ -140,6 +140,20 @@ def golden_sg_decode():
         out[k + "_alpha"], out[k + "_diffuse"] = tex.alpha, tex.diffuse
         for i in range(L):
             out[k + f"_color{i}"], out[k + f"_lambda{i}"] = tex.sg_colors[i], tex.lambdas[i]
+    # f-4: the bake writer, FeatureCompression.compress (texture_utils.py:67-98) on random features
+    for L, ctype, lam in ((3, "linear", 5.0), (2, "sigma", 7.5)):
+        g = torch.Generator().manual_seed(50 + L)
+        M = 400
+        feats = torch.randn(M, 3 + 7 * L + 1, generator=g) * 3.0
+        feats[:, -1] = torch.rand(M, generator=g) * 600          # sigma >= 0
+        feats[:5, -1] = torch.tensor([0.0, 1e-3, 50.0, 5000.0, 1e6])
+        fc = object.__new__(FeatureCompression)
+        fc.num_lobes, fc.compression_type, fc.lambda_thres = L, ctype, lam
+        data = fc.compress(feats)
+        k = f"cmp_L{L}_{ctype}"
+        out[k + "_feats"], out[k + "_alpha"], out[k + "_diffuse"] = feats, data["alpha"], data["diffuse"]
+        for i in range(L):
+            out[k + f"_lambda{i}"], out[k + f"_color{i}"] = data["lambdas"][i], data["colors"][i]
     x = torch.tensor([-3.0, -1.0, 0.0, 0.5, 2.0, 14.0, 16.0, 20.0], requires_grad=True)
     y = NGP.trunc_exp(x)
     y.backward(torch.ones_like(y))

@@ -632,6 +632,30 @@ def texture_decode(indices: torch.Tensor, tex: TextureSet) -> torch.Tensor:
     return torch.cat(cols, dim=-1)
 
 
+def texture_compress(features: torch.Tensor, num_lobes: int, compression_type: str = "linear", lambda_thres: float = 7.5):
+    """SURVEY §8 row f-4 — the bake writer `FeatureCompression.compress` (texture_utils.py:67-98) with the quantisers
+    of ngp.py:239-273 and texture_utils.py:51-55.  features (M, 3+7L+1) -> dict(alpha (M), diffuse (M,3),
+    lambdas L x (M,3) [lambda, azimuth, elevation], colors L x (M,3)) uint8."""
+    def colors(c):
+        if compression_type == "sigma":
+            c = torch.sigmoid(c)
+        else:
+            c = (torch.clip(c, -12, 12) + 12) / 2 / 12
+        return (c * 255).to(torch.uint8)
+    M = features.shape[0]
+    sigma = features[:, -1]
+    alpha = torch.clip((1 - torch.exp(-sigma * 0.005)) * 255, 0, 255).to(torch.uint8)
+    lobes = features[:, 3:-1].reshape(M, num_lobes, 7)
+    v = lobes[..., :3] / (torch.norm(lobes[..., :3], dim=-1, keepdim=True) + 1e-6)
+    az = (torch.atan2(v[..., 1], v[..., 0]) * 128 / np.pi + 128).to(torch.uint8)
+    el = (torch.acos(v[..., 2]) * 256 / np.pi).to(torch.uint8)
+    lam = torch.clamp((torch.log(torch.clamp(torch.abs(lobes[..., 3]), 1e-5, np.inf)) + 2.5) / lambda_thres, 0.0, 1.0)
+    lam = (255 * lam).to(torch.uint8)
+    return dict(alpha=alpha, diffuse=colors(features[:, :3]),
+                lambdas=[torch.stack([lam[:, i], az[:, i], el[:, i]], dim=-1) for i in range(num_lobes)],
+                colors=[colors(lobes[:, i, 4:]) for i in range(num_lobes)])
+
+
 # --------------------------------------------------------------------------------------
 # a10  barycentric → texel — utils.py:1055-1063 (trimesh.triangles.points_to_barycentric, fp64)
 # --------------------------------------------------------------------------------------

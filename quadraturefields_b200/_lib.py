@@ -44,6 +44,7 @@ _SIGS = {
     "qf_ngp_update": (_I, [_P, _P, _P, _P, _P]),
     "qf_ngp_destroy": (None, [_P]),
     "qf_hashgrid_forward": (_I, [_P, _P, _L, _P, _P]),
+    "qf_hashgrid_backward": (_I, [_P, _P, _P, _L, _P, _P]),
     "qf_ngp_query_density": (_I, [_P, _P, _L, _P, _P, _P]),
     "qf_ngp_forward": (_I, [_P, _P, _P, _P, _L, _P, _P, _P]),
     "qf_ngp_backward_workspace_bytes": (_SZ, [_L]),
@@ -51,6 +52,7 @@ _SIGS = {
     "qf_texture_create": (_I, [_I, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _I, _F, _P, C.POINTER(_P)]),
     "qf_texture_destroy": (None, [_P]),
     "qf_texture_decode": (_I, [_P, _P, _L, _P, _P]),
+    "qf_texture_compress": (_I, [_P, _L, _I, _I, _F, _P, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "qf_sg_features_to_rgb": (_I, [_P, _L, _I, _P, _L, _P, _P]),
     "qf_hit_texels": (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
     "qf_derive_properties": (_I, [_P, _P, _P, _F, _P, _L, _I, _P, _P, _P, _P, _P, _P]),

@@ -149,6 +149,43 @@ __global__ void hit_texels_kernel(const float* __restrict__ verts, const int32_t
   out[2 * i] = t0; out[2 * i + 1] = t1;
 }
 
+// SURVEY §8 row f-4 — the bake writer FeatureCompression.compress (texture_utils.py:67-98): quantise feature rows
+// [diffuse(3), L x (axis3, lambda, c3), sigma] into the uint8 planes, at row i or at texel (idx[i,0], idx[i,1]).
+struct PlaneOut {
+  uint8_t* alpha;
+  uint8_t* diffuse;
+  uint8_t* colors[QF_MAX_LOBES];
+  uint8_t* lambdas[QF_MAX_LOBES];
+};
+__device__ __forceinline__ uint8_t to_u8(float v) { return (uint8_t)(int)v; }   // torch .to(uint8): truncate, low 8 bits
+__device__ __forceinline__ uint8_t quant_colour(float c, int logit) {
+  if (logit) c = 1.0f / (1.0f + expf(-c));                                   // ngp.py:264-273
+  else c = (fminf(fmaxf(c, -12.0f), 12.0f) + 12.0f) / 2.0f / 12.0f;
+  return to_u8(c * 255.0f);
+}
+__global__ void texture_compress_kernel(const float* __restrict__ feats, int64_t M, int L, int colour_logit, float lambda_thres,
+                                        const int64_t* __restrict__ idx, int S, PlaneOut p) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const int W = 3 + 7 * L + 1;
+  const float* f = feats + i * W;
+  const int64_t o = idx ? idx[2 * i] * S + idx[2 * i + 1] : i;
+  const float a = (1.0f - expf(-f[W - 1] * 0.005f)) * 255.0f;                 // texture_utils.py:51-55
+  p.alpha[o] = to_u8(fminf(fmaxf(a, 0.0f), 255.0f));
+  for (int c = 0; c < 3; ++c) p.diffuse[3 * o + c] = quant_colour(f[c], colour_logit);
+  for (int l = 0; l < L; ++l) {
+    const float* q = f + 3 + 7 * l;
+    float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]) + 1e-6f;           // ngp.py:239-243
+    float vx = q[0] / n, vy = q[1] / n, vz = q[2] / n;
+    float az = atan2f(vy, vx) * 128.0f / 3.14159265358979323846f + 128.0f;
+    float el = acosf(vz) * 256.0f / 3.14159265358979323846f;
+    float lam = (logf(fmaxf(fabsf(q[3]), 1e-5f)) + 2.5f) / lambda_thres;       // ngp.py:254-258
+    lam = 255.0f * fminf(fmaxf(lam, 0.0f), 1.0f);
+    p.lambdas[l][3 * o] = to_u8(lam); p.lambdas[l][3 * o + 1] = to_u8(az); p.lambdas[l][3 * o + 2] = to_u8(el);
+    for (int c = 0; c < 3; ++c) p.colors[l][3 * o + c] = quant_colour(q[4 + c], colour_logit);
+  }
+}
+
 // fused shading of compact hit records for qf_render_mesh_baked (render.cu): texel lookup + decode + SG
 __global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const float* __restrict__ verts,
                                                           const int32_t* __restrict__ faces, const float* __restrict__ uv,
@@ -222,6 +259,21 @@ extern "C" int qf_texture_decode(const qf_texture* t, const int64_t* d_indices, 
   if (M == 0) return QF_OK;
   TexParams p{t->d_records, t->size, t->num_lobes, t->record_bytes, t->colour_logit, t->lambda_thres};
   texture_decode_kernel<<<(int)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(p, d_indices, M, d_features);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_texture_compress(const float* d_features, int64_t M, int num_lobes, int colour_logit, float lambda_thres,
+                                   const int64_t* d_indices, int texture_size, uint8_t* d_alpha, uint8_t* d_diffuse,
+                                   uint8_t* const* h_d_colors, uint8_t* const* h_d_lambdas, void* stream) {
+  if (M == 0) return QF_OK;
+  QF_REQUIRE(d_features && d_alpha && d_diffuse && h_d_colors && h_d_lambdas, "qf_texture_compress: NULL argument");
+  QF_REQUIRE(num_lobes >= 0 && num_lobes <= QF_MAX_LOBES, "qf_texture_compress: lobes=%d", num_lobes);
+  PlaneOut p{};
+  p.alpha = d_alpha; p.diffuse = d_diffuse;
+  for (int l = 0; l < num_lobes; ++l) { p.colors[l] = h_d_colors[l]; p.lambdas[l] = h_d_lambdas[l]; }
+  texture_compress_kernel<<<(int)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(d_features, M, num_lobes, colour_logit, lambda_thres,
+                                                                                   d_indices, texture_size, p);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

@@ -320,6 +320,17 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
   }
 }
 
+// tcnn grid backward alone: dL/dtable += scatter of dL/denc (M, 2L) at x01 (M,3); thread per (sample, level)
+__global__ void hashgrid_backward_kernel(const qf_grid_desc d, const float* __restrict__ x01, const float* __restrict__ g_enc,
+                                         int64_t M, float2* __restrict__ g_table) {
+  const int L = d.n_levels;
+  const int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (id >= M * L) return;
+  const int64_t i = id / L;
+  const int l = (int)(id % L);
+  scatter_level(d, g_table, l, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], g_enc[i * 2 * L + 2 * l], g_enc[i * 2 * L + 2 * l + 1]);
+}
+
 // ---------------------------------------------------------------- dW_l = G_l^T A_l
 struct LayerGemm { int N, K, act_off, grd_off, img_off, img_stride; };
 __constant__ LayerGemm c_layers[5] = {
@@ -427,6 +438,17 @@ __global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, cons
 using namespace qf;
 
 static size_t align256b(size_t x) { return (x + 255) / 256 * 256; }
+
+extern "C" int qf_hashgrid_backward(const qf_ngp* f, const float* d_x01, const float* d_grad_enc, int64_t M, float* d_grad_table,
+                                    void* stream) {
+  if (M == 0) return QF_OK;
+  QF_REQUIRE(f && d_x01 && d_grad_enc && d_grad_table, "qf_hashgrid_backward: NULL argument");
+  const int64_t n = M * f->desc.n_levels;
+  hashgrid_backward_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(f->desc, d_x01, d_grad_enc, M,
+                                                                                       reinterpret_cast<float2*>(d_grad_table));
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
 
 extern "C" size_t qf_ngp_backward_workspace_bytes(int64_t M) {
   return 256 + align256b(sizeof(__half) * kTTotal) + align256b(sizeof(float) * kWTotal) + align256b(sizeof(__half) * (size_t)M * kActRow) +

@@ -223,6 +223,18 @@ class NGPRadianceField(nn.Module):
         return rgb, density
 
     @torch.no_grad()
+    def encode_backward(self, x01: torch.Tensor, grad_enc: torch.Tensor) -> torch.Tensor:
+        """tcnn HashGrid backward alone: dL/dtable (n_entries, 2) for dL/denc (M, 32) at x in [0,1]^3."""
+        lib = _lib.load()
+        h = self._native()
+        x01 = _lib.f32(x01.reshape(-1, 3))
+        g = _lib.f32(grad_enc.reshape(x01.shape[0], 2 * self.n_levels))
+        out = torch.zeros((self._n_entries, 2), dtype=torch.float32, device=x01.device)
+        _lib.check(lib.qf_hashgrid_backward(h, _lib.ptr(x01), _lib.ptr(g), x01.shape[0], _lib.ptr(out), _lib.stream(x01.device)),
+                   "qf_hashgrid_backward")
+        return out
+
+    @torch.no_grad()
     def encode(self, x01: torch.Tensor) -> torch.Tensor:
         """tcnn HashGrid forward alone (for tests / profiling): x in [0,1]^3 -> (M, 32)."""
         lib = _lib.load()

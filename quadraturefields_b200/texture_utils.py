@@ -77,6 +77,45 @@ class FeatureCompression:
                    "qf_texture_decode")
         return out
 
+    def _compress_into(self, features, indices, alpha, diffuse, colors, lambdas, size):
+        lib = _lib.load()
+        L = self.num_lobes
+        f = _lib.f32(features.reshape(-1, 3 + 7 * L + 1), self.device)
+        idx = _lib.i64(indices.to(self.device)) if indices is not None else None
+        cols = (C.c_void_p * max(L, 1))(*[colors[i].data_ptr() for i in range(L)])
+        lams = (C.c_void_p * max(L, 1))(*[lambdas[i].data_ptr() for i in range(L)])
+        _lib.check(lib.qf_texture_compress(_lib.ptr(f), f.shape[0], L, 1 if self.compression_type == "sigma" else 0,
+                                           float(self.lambda_thres), _lib.ptr(idx), int(size), _lib.ptr(alpha), _lib.ptr(diffuse),
+                                           cols, lams, _lib.stream(self.device)), "qf_texture_compress")
+
+    @torch.no_grad()
+    def compress(self, features):
+        """texture_utils.py:67-98: features (N, 3+7L+1) -> dict(alpha (N,), diffuse (N,3), lambdas [L x (N,3)], colors [L x (N,3)]) uint8."""
+        N = features.shape[0]
+        z = lambda *s: torch.empty(s, dtype=torch.uint8, device=self.device)
+        data = dict(alpha=z(N), diffuse=z(N, 3), lambdas=[z(N, 3) for _ in range(self.num_lobes)],
+                    colors=[z(N, 3) for _ in range(self.num_lobes)])
+        self._compress_into(features, None, data["alpha"], data["diffuse"], data["colors"], data["lambdas"], 0)
+        return data
+
+    @torch.no_grad()
+    def assign_values_to_texture_map(self, features, indices):
+        """texture_utils.py:100-106: quantise and scatter into the atlas planes at texel `indices` (M,2)."""
+        self._compress_into(features, indices, self.alpha, self.diffuse, self.sg_colors, self.lambdas, self.texture_size)
+        if self._handle is not None:
+            self.repack()
+
+    load_features_into_maps = assign_values_to_texture_map            # texture_utils.py:197-203
+
+    def save_to_file(self, path):
+        """texture_utils.py:119-124 (PNG set: alpha.png, diffuse.png, color_i.png, lambda_axis_i.png)."""
+        from PIL import Image
+        Image.fromarray(self.alpha.cpu().numpy()).save(path + "alpha.png")
+        Image.fromarray(self.diffuse.cpu().numpy()).save(path + "diffuse.png")
+        for i in range(self.num_lobes):
+            Image.fromarray(self.sg_colors[i].cpu().numpy()).save(path + "color_{}.png".format(i))
+            Image.fromarray(self.lambdas[i].cpu().numpy()).save(path + "lambda_axis_{}.png".format(i))
+
     @torch.no_grad()
     def features_to_rgb(self, features, dir):
         """texture_utils.py:144-147."""

@@ -164,6 +164,18 @@ def test_hashgrid_encode(dev, smoke_scene):
     assert float((diff > 0).float().mean()) < 1e-4
 
 
+def test_hashgrid_backward(dev, smoke_scene):
+    sc = smoke_scene
+    p = oracle_params(sc)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(5000, 3, generator=g)
+    ge = torch.randn(5000, 32, generator=g)
+    table = p.table.clone().requires_grad_()
+    (O.hashgrid_encode(x, table, p.meta) * ge).sum().backward()
+    got = sc.radiance_field.encode_backward(x.to(dev), ge.to(dev)).cpu()
+    assert float((got - table.grad).abs().max()) <= 1e-4 * float(table.grad.abs().max())
+
+
 def test_ngp_forward_matches_oracle(dev, smoke_scene):
     sc = smoke_scene
     p = oracle_params(sc)
@@ -271,6 +283,37 @@ def test_texture_decode_and_sg_golden(dev, golden):
         rgb = NGPRadianceFieldSGNew(num_g_lobes=L).features_to_rgb(T(g[k + "_feats"])[:, :-1].to(dev), T(g[k + "_dirs"]).to(dev))
         assert maxabs(rgb, g[k + "_rgb"]) <= 2e-6
         assert maxabs(fc.features_to_rgb(feats[:, :-1], T(g[k + "_dirs"]).to(dev)), g[k + "_rgb"]) <= 1e-5
+
+
+def test_texture_compress_and_roundtrip(dev, golden, tmp_path):
+    """f-4 bake writer vs the reference's FeatureCompression.compress fixture, then write PNGs -> load -> decode."""
+    from quadraturefields_b200.texture_utils import FeatureCompression
+    g = golden("sg_decode")
+    for L, ctype, lam in ((3, "linear", 5.0), (2, "sigma", 7.5)):
+        k = f"cmp_L{L}_{ctype}"
+        fc = FeatureCompression(L, initialize=True, texture_size=20, compression_type=ctype, lambda_thres=lam, device=dev)
+        feats = T(g[k + "_feats"]).to(dev)
+        d = fc.compress(feats)
+        pairs = [(d["alpha"], g[k + "_alpha"]), (d["diffuse"], g[k + "_diffuse"])]
+        pairs += [(d["lambdas"][i], g[k + f"_lambda{i}"]) for i in range(L)] + [(d["colors"][i], g[k + f"_color{i}"]) for i in range(L)]
+        n_bad = n_all = 0
+        for got, ref in pairs:
+            diff = (got.cpu().numpy().astype(np.int16) - ref.astype(np.int16)) % 256
+            diff = np.minimum(diff, 256 - diff)                                  # azimuth wraps mod 256
+            assert diff.max() <= 1                                              # transcendental functions differ by an ulp at most
+            n_bad += int((diff != 0).sum()); n_all += diff.size
+        assert n_bad <= 2e-3 * n_all
+        # scatter into the atlas, write the PNG set, load it back, decode
+        idx = torch.stack([torch.arange(400) // 20, torch.arange(400) % 20], dim=1)
+        fc.assign_values_to_texture_map(feats, idx.to(dev))
+        fc.save_to_file(str(tmp_path) + "/")
+        fc2 = FeatureCompression(L, path=str(tmp_path) + "/", compression_type=ctype, lambda_thres=lam, device=dev)
+        assert torch.equal(fc2.alpha, fc.alpha) and torch.equal(fc2.lambdas[L - 1], fc.lambdas[L - 1])
+        dec = fc2.get_features_from_texture_map(idx.to(dev)).cpu()
+        tex = O.TextureSet(fc.alpha.cpu(), fc.diffuse.cpu(), [fc.sg_colors[i].cpu() for i in range(L)],
+                           [fc.lambdas[i].cpu() for i in range(L)], ctype, lam)
+        ref_dec = O.texture_decode(idx, tex)
+        assert float(((dec - ref_dec).abs() / ref_dec.abs().clamp_min(1.0)).max()) <= 2e-6
 
 
 def test_hit_texels_bit_exact(dev):

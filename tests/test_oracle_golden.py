@@ -83,6 +83,19 @@ def test_sg_decode_golden(golden):
     close(torch.exp(torch.clamp(T(g["trunc_exp_x"]), max=15)), g["trunc_exp_g"], 0.0)
 
 
+def test_texture_compress_golden(golden):
+    """f-4 bake writer: oracle restatement vs the reference's FeatureCompression.compress, byte for byte."""
+    g = golden("sg_decode")
+    for L, ctype, lam in ((3, "linear", 5.0), (2, "sigma", 7.5)):
+        k = f"cmp_L{L}_{ctype}"
+        d = O.texture_compress(T(g[k + "_feats"]), L, ctype, lam)
+        assert np.array_equal(d["alpha"].numpy(), g[k + "_alpha"]) and np.array_equal(d["diffuse"].numpy(), g[k + "_diffuse"])
+        for i in range(L):
+            assert np.array_equal(d["lambdas"][i].numpy(), g[k + f"_lambda{i}"])
+            assert np.array_equal(d["colors"][i].numpy(), g[k + f"_color{i}"])
+        assert g[k + "_alpha"].max() == 255 and g[k + "_alpha"].min() == 0
+
+
 def test_geometry_golden(golden):
     g = golden("geometry")
     K = int(g["K"])
