@@ -270,26 +270,27 @@ __global__ void fill_inf_kernel(float* __restrict__ p, int64_t n) {
 }
 __device__ __forceinline__ bool mostly_coherent(const int32_t* slot) { return 2 * __ldg(slot) >= __ldg(slot + 1); }
 
-template <int KMAX>
-__device__ __forceinline__ void write_hits(const HitBuf<KMAX>& hb, int total, int64_t i, int K, int32_t* __restrict__ out_tri,
+template <class HB>
+__device__ __forceinline__ void write_hits(HB& hb, int total, int64_t i, int K, int32_t* __restrict__ out_tri,
                                            float* __restrict__ out_t, int32_t* __restrict__ out_count,
                                            int32_t* __restrict__ out_total) {
-#pragma unroll
-  for (int s = 0; s < KMAX; ++s) {
-    if (s >= KMAX - K) {
-      const bool hit = hb.t[s] != __int_as_float(0x7f800000);
-      out_tri[i * K + s - (KMAX - K)] = hit ? hb.id[s] : -1;
-      if (out_t) out_t[i * K + s - (KMAX - K)] = hb.t[s];
-    }
+  const int c = hb.count(K);
+  hb.for_each(K, [&](int j, float t, int id) {
+    out_tri[i * K + j] = id;
+    if (out_t) out_t[i * K + j] = t;
+  });
+  for (int j = c; j < K; ++j) {
+    out_tri[i * K + j] = -1;
+    if (out_t) out_t[i * K + j] = __int_as_float(0x7f800000);
   }
-  out_count[i] = hb.count(K);
+  out_count[i] = c;
   if (out_total) out_total[i] = total;
 }
 
 // Incoherent ray lists (training batches of random pixels): persistent warps whose lanes fetch a new ray as soon as
 // enough of them have finished, so one long ray no longer idles the other 31 lanes (thread efficiency was 3.4 / 32
 // with one ray per thread, profiles/r1c).  Runs only when classify_rays_kernel found the list mostly incoherent.
-template <int KMAX, bool COUNT_ALL>
+template <class HB, bool COUNT_ALL>
 __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                            const float* __restrict__ origins, const float* __restrict__ dirs,
                                                            int64_t N, int K, int32_t* __restrict__ out_tri,
@@ -300,9 +301,11 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
   N = __ldg(slot + 3);   // rays that reach the scene box; the rest keep the pre-filled "no hit"
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
+  __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
+  __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   int sref[kStackDepth];
   float stn[kStackDepth];
-  HitBuf<KMAX> hb;
+  HB hb(s_ht, s_hi, threadIdx.x);
   Ray r;
   int64_t ri = -1;
   int sp = 0, cur = kDoneRef, total = 0;
@@ -328,23 +331,23 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
     if (__all_sync(0xffffffffu, ri < 0)) { if (exhausted) break; else continue; }
     int steps = 0;
     while (ri >= 0 && cur >= 0 && cur != kDoneRef && steps < 24) {
-      single_node_step<KMAX, !COUNT_ALL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
+      single_node_step<HB, !COUNT_ALL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
       ++steps;
     }
     while (ri >= 0 && cur < 0) {
       const float tcull = COUNT_ALL ? __int_as_float(0x7f800000) : hb.cull_distance();
-      if (cur_tn <= tcull) leaf_intersect<KMAX>(r, tris, cur, cur_tn, hb, total);
+      if (cur_tn <= tcull) leaf_intersect<HB>(r, tris, cur, cur_tn, hb, total);
       if (sp) { cur = sref[--sp]; cur_tn = stn[sp]; }
       else cur = kDoneRef;
     }
     if (ri >= 0 && cur == kDoneRef) {
-      if (total > 0) write_hits<KMAX>(hb, total, ri, K, out_tri, out_t, out_count, out_total);
+      if (total > 0) write_hits<HB>(hb, total, ri, K, out_tri, out_t, out_count, out_total);
       ri = -1;
     }
   }
 }
 
-template <int KMAX, bool COUNT_ALL>
+template <class HB, bool COUNT_ALL>
 __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                     const float* __restrict__ origins, const float* __restrict__ dirs,
                                                     int64_t N, int K, int32_t* __restrict__ out_tri,
@@ -352,14 +355,16 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
                                                     int32_t* __restrict__ out_total, const int32_t* __restrict__ slot) {
   if (!mostly_coherent(slot)) return;   // trace_refill_kernel handles this list
   __shared__ int s_stack[4][kStackDepth];
+  __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
+  __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const bool valid = i < N;
   Ray r = make_ray(origins, dirs, valid ? i : N - 1);
-  HitBuf<KMAX> hb;
+  HB hb(s_ht, s_hi, threadIdx.x);
   int total;
-  trace_ray<KMAX, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
+  trace_ray<HB, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
   if (!valid) return;
-  write_hits<KMAX>(hb, total, i, K, out_tri, out_t, out_count, out_total);
+  write_hits<HB>(hb, total, i, K, out_tri, out_t, out_count, out_total);
 }
 
 // ---------------------------------------------------------------- tuple packing (a3)
@@ -573,8 +578,8 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
     if (have_ws) trace_refill_kernel<KM, ALL><<<pblocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, list); \
   } while (0)
   // the untruncated total needs a traversal without distance culling
-  if (d_total) { if (K <= 8) QF_TRACE(8, true); else if (K <= 16) QF_TRACE(16, true); else QF_TRACE(32, true); }
-  else { if (K <= 8) QF_TRACE(8, false); else if (K <= 16) QF_TRACE(16, false); else QF_TRACE(32, false); }
+  if (d_total) { if (K <= 8) QF_TRACE(HitBufReg<8>, true); else QF_TRACE(HitBufSmem, true); }
+  else { if (K <= 8) QF_TRACE(HitBufReg<8>, false); else QF_TRACE(HitBufSmem, false); }
 #undef QF_TRACE
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -252,6 +252,19 @@ static int field_tc_mode() {
   return m;
 }
 
+// diagnostic (tools/diag_shade.py): the gather alone — every level encoded, 4 bytes written per sample
+__global__ void __launch_bounds__(128) encode_sum_kernel(const qf_grid_desc desc, const __half2* __restrict__ table,
+                                                         const float* __restrict__ x01, int64_t M, float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float acc = 0.f;
+  encode_point(desc, table, x01[3 * i], x01[3 * i + 1], x01[3 * i + 2], [&](int l, uint32_t h2) {
+    float2 f = __half22float2(*reinterpret_cast<__half2*>(&h2));
+    acc += f.x + f.y;
+  });
+  out[i] = acc;
+}
+
 int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {
   if (mode == 0 && field_tc_mode() == 1) {
     FieldTcArgs t = {};
@@ -335,6 +348,13 @@ extern "C" void qf_ngp_destroy(qf_ngp* f) {
   if (f->d_weights) cudaFree(f->d_weights);
   if (f->d_weights_tc) cudaFree(f->d_weights_tc);
   delete f;
+}
+
+extern "C" int qf_debug_encode_sum(const qf_ngp* f, const float* d_x01, int64_t M, float* d_out, void* stream) {
+  if (M == 0) return QF_OK;
+  encode_sum_kernel<<<(int)ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(f->desc, f->d_table, d_x01, M, d_out);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
 }
 
 extern "C" int qf_hashgrid_forward(const qf_ngp* f, const float* d_x01, int64_t M, float* d_enc, void* stream) {

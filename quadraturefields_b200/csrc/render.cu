@@ -51,7 +51,7 @@ static size_t workspace_layout(int64_t n_rays, int K, Workspace* w, char* base) 
   return off;
 }
 
-template <int KMAX>
+template <class HB>
 __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                             const float4* __restrict__ planes, const float* __restrict__ scene,
                                                             const float* __restrict__ origins, const float* __restrict__ dirs,
@@ -71,11 +71,13 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
     const int tiles = img_w >> 3;
     li = ((gw / tiles) * 4 + (lane >> 3)) * img_w + (gw % tiles) * 8 + (lane & 7);
   }
+  __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
+  __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   const bool valid = li < n;
-  HitBuf<KMAX> hb;
+  HB hb(s_ht, s_hi, tid);
   int total = 0;
   Ray r = make_ray(origins, dirs, ray0 + (valid ? li : n - 1));
-  trace_ray<KMAX>(r, valid, nodes, tris, K, hb, total, s_stack[warp], mode);
+  trace_ray<HB>(r, valid, nodes, tris, K, hb, total, s_stack[warp], mode);
   // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
   int c = valid ? hb.count(K) : 0, inc = c;
 #pragma unroll
@@ -94,19 +96,15 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   ray_count[li] = c;
   float prev = -1.f;
   bool unsorted = false;
-#pragma unroll
-  for (int s = 0; s < KMAX; ++s) {
-    if (s >= KMAX - K && hb.t[s] != __int_as_float(0x7f800000)) {   // real slots are [KMAX-K, KMAX), filled in order
-      float px, py, pz;
-      plane_hit(r, __ldg(planes + hb.id[s]), px, py, pz);
-      float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
-      unsorted |= d < prev;
-      prev = d;
-      const int j = start + s - (KMAX - K);
-      hit_pd[j] = make_float4(px, py, pz, d);
-      hit_rt[j] = make_int2((int)(ray0 + li), hb.id[s]);
-    }
-  }
+  hb.for_each(K, [&](int j, float, int id) {
+    float px, py, pz;
+    plane_hit(r, __ldg(planes + id), px, py, pz);
+    float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
+    unsorted |= d < prev;
+    prev = d;
+    hit_pd[start + j] = make_float4(px, py, pz, d);
+    hit_rt[start + j] = make_int2((int)(ray0 + li), id);
+  });
   if (unsorted) {  // rare: plane-hit depth order differs from Möller–Trumbore t order; stable insertion sort
     for (int s = 1; s < c; ++s) {
       float4 pd = hit_pd[start + s];
@@ -219,13 +217,10 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
     if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
     if (K <= 8)
-      trace_compact_kernel<8><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
+      trace_compact_kernel<HitBufReg<8>><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
-    else if (K <= 16)
-      trace_compact_kernel<16><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
     else
-      trace_compact_kernel<32><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
+      trace_compact_kernel<HitBufSmem><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
                                                        d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) cudaEventRecord(pe[1], st);

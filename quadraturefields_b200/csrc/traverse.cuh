@@ -12,15 +12,19 @@
 
 namespace qf {
 
-// Per-ray sorted K-buffer kept entirely in registers: every access uses a compile-time slot index (any
-// `slot == runtime value` guard lets the compiler fold the access into a dynamically indexed one and the
-// arrays fall back to local memory).  The buffer always has KMAX slots; when K < KMAX the first KMAX-K slots
-// hold -inf sentinels that sort before every real hit, so the K real slots are [KMAX-K, KMAX) and
-// t[KMAX-1] is the K-th smallest hit (+inf until K hits were found) — the culling distance.
+// ---- per-ray K-buffers.  Both keep the K smallest hits by (t, id) and expose the same interface:
+//   init(K) | insert(t,id) | cull_distance() (K-th smallest t, +inf until K hits) | count(K) | for_each(K, f(j,t,id)) in order.
+//
+// HitBufReg<KMAX> (K <= 8): sorted, entirely in registers.  Every access uses a compile-time slot index (any
+// `slot == runtime value` guard lets the compiler fold the access into a dynamically indexed one and the arrays fall
+// back to local memory).  The buffer always has KMAX slots; when K < KMAX the first KMAX-K slots hold -inf sentinels
+// that sort before every real hit, so the K real slots are [KMAX-K, KMAX) and t[KMAX-1] is the K-th smallest hit.
 template <int KMAX>
-struct HitBuf {
+struct HitBufReg {
+  static constexpr int kSmemSlots = 0;
   float t[KMAX];
   int id[KMAX];
+  __device__ __forceinline__ HitBufReg(float*, int*, int) {}
   __device__ __forceinline__ void init(int K) {
 #pragma unroll
     for (int s = 0; s < KMAX; ++s) {
@@ -36,35 +40,85 @@ struct HitBuf {
     for (int s = 0; s < KMAX; ++s) c += (s >= KMAX - K && t[s] != __int_as_float(0x7f800000)) ? 1 : 0;
     return c;
   }
+  // carry-insertion: the largest element falls off the end
+  __device__ __forceinline__ void insert(float nt, int nid) {
+    float ct = nt;
+    int ci = nid;
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s) {
+      const bool less = (ct < t[s]) || (ct == t[s] && ci < id[s]);
+      const float tt = t[s];
+      const int ti = id[s];
+      t[s] = less ? ct : tt;
+      id[s] = less ? ci : ti;
+      ct = less ? tt : ct;
+      ci = less ? ti : ci;
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each(int K, F f) {
+#pragma unroll
+    for (int s = 0; s < KMAX; ++s)
+      if (s >= KMAX - K && t[s] != __int_as_float(0x7f800000)) f(s - (KMAX - K), t[s], id[s]);
+  }
 };
 
-// carry-insertion: order key is (t, id); the largest element falls off the end
-template <int KMAX>
-__device__ __forceinline__ void insert_hit(HitBuf<KMAX>& hb, float t, int id) {
-  float ct = t;
-  int ci = id;
-#pragma unroll
-  for (int s = 0; s < KMAX; ++s) {
-    const bool less = (ct < hb.t[s]) || (ct == hb.t[s] && ci < hb.id[s]);
-    const float tt = hb.t[s];
-    const int ti = hb.id[s];
-    hb.t[s] = less ? ct : tt;
-    hb.id[s] = less ? ci : ti;
-    ct = less ? tt : ct;
-    ci = less ? ti : ci;
+// HitBufSmem (8 < K <= 32): unsorted in shared memory (slot-major, 128 threads per CTA, conflict free), O(1) append
+// while fewer than K hits are known — the common case, since K is chosen above the deepest ray — and replace-the-maximum
+// once full; sorted once at the end.  Keeps the traversal kernels at ~60 registers instead of 115 for a 32-slot
+// register buffer whose insertion costs 32 compare-exchange steps per hit.
+struct HitBufSmem {
+  static constexpr int kSmemSlots = QF_MAX_HITS;
+  float* st;
+  int* si;
+  int cnt, K, imax, idmax;
+  float tmax;
+  __device__ __forceinline__ HitBufSmem(float* t, int* i, int tid) : st(t + tid), si(i + tid) {}
+  __device__ __forceinline__ void init(int K_) { cnt = 0; K = K_; imax = 0; idmax = 0x7fffffff; tmax = __int_as_float(0x7f800000); }
+  __device__ __forceinline__ float cull_distance() const { return cnt == K ? tmax : __int_as_float(0x7f800000); }
+  __device__ __forceinline__ int count(int) const { return cnt; }
+  __device__ __forceinline__ void find_max() {
+    tmax = st[0]; idmax = si[0]; imax = 0;
+    for (int s = 1; s < K; ++s) {
+      const float a = st[s * 128];
+      const int b = si[s * 128];
+      if (a > tmax || (a == tmax && b > idmax)) { tmax = a; idmax = b; imax = s; }
+    }
   }
-}
+  __device__ __forceinline__ void insert(float nt, int nid) {
+    if (cnt < K) {
+      st[cnt * 128] = nt; si[cnt * 128] = nid;
+      if (++cnt == K) find_max();
+    } else if (nt < tmax || (nt == tmax && nid < idmax)) {
+      st[imax * 128] = nt; si[imax * 128] = nid;
+      find_max();
+    }
+  }
+  template <typename F>
+  __device__ __forceinline__ void for_each(int, F f) {
+    for (int s = 1; s < cnt; ++s) {   // insertion sort by (t, id)
+      const float a = st[s * 128];
+      const int b = si[s * 128];
+      int q = s;
+      while (q > 0 && (st[(q - 1) * 128] > a || (st[(q - 1) * 128] == a && si[(q - 1) * 128] > b))) {
+        st[q * 128] = st[(q - 1) * 128]; si[q * 128] = si[(q - 1) * 128];
+        --q;
+      }
+      st[q * 128] = a; si[q * 128] = b;
+    }
+    for (int s = 0; s < cnt; ++s) f(s, st[s * 128], si[s * 128]);
+  }
+};
 
 // one triangle (leaf reference) whose padded box passed the slab test with entry distance tn
-template <int KMAX>
-__device__ __forceinline__ void leaf_intersect(const Ray& r, const float4* __restrict__ tris, int ref, float tn,
-                                               HitBuf<KMAX>& hb, int& total) {
+template <class HB>
+__device__ __forceinline__ void leaf_intersect(const Ray& r, const float4* __restrict__ tris, int ref, float tn, HB& hb, int& total) {
   const float4* p = tris + 3 * (int64_t)(~ref);
   float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
   float t;
   if (ray_triangle_mt(r, a.x, a.y, a.z, b.x, b.y, b.z, c.x, c.y, c.z, tn, t)) {
     ++total;
-    insert_hit<KMAX>(hb, t, __float_as_int(a.w));
+    hb.insert(t, __float_as_int(a.w));
   }
 }
 
@@ -72,8 +126,8 @@ constexpr int kDoneRef = 0x7fffffff;
 constexpr int kStackDepth = 96;   // LBVH depth <= 64 Morton bits + 32 index bits
 
 // One internal-node step of the per-lane traversal (shared by traverse_single and the refill kernel).
-template <int KMAX, bool CULL>
-__device__ __forceinline__ void single_node_step(const Ray& r, const float4* __restrict__ nodes, const HitBuf<KMAX>& hb,
+template <class HB, bool CULL>
+__device__ __forceinline__ void single_node_step(const Ray& r, const float4* __restrict__ nodes, const HB& hb,
                                                  int* sref, float* stn, int& sp, int& cur, float& cur_tn) {
   const float inf = __int_as_float(0x7f800000);
   const float4* np = nodes + 4 * (int64_t)cur;
@@ -96,9 +150,9 @@ __device__ __forceinline__ void single_node_step(const Ray& r, const float4* __r
 }
 
 // ---------------------------------------------------------------- per-lane while-while traversal
-template <int KMAX, bool CULL = true>
+template <class HB, bool CULL = true>
 __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __restrict__ nodes,
-                                                const float4* __restrict__ tris, int K, HitBuf<KMAX>& hb, int& total) {
+                                                const float4* __restrict__ tris, int K, HB& hb, int& total) {
   int sref[kStackDepth];
   float stn[kStackDepth];
   int sp = 0;
@@ -109,10 +163,10 @@ __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __re
   const float inf = __int_as_float(0x7f800000);
   while (cur != kDoneRef) {
     while (cur >= 0 && cur != kDoneRef)     // ---- internal nodes, until this lane holds a leaf
-      single_node_step<KMAX, CULL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
+      single_node_step<HB, CULL>(r, nodes, hb, sref, stn, sp, cur, cur_tn);
     while (cur < 0) {                        // ---- leaves, warp reconverged (kDoneRef is positive)
       const float tcull = CULL ? hb.cull_distance() : inf;
-      if (cur_tn <= tcull) leaf_intersect<KMAX>(r, tris, cur, cur_tn, hb, total);
+      if (cur_tn <= tcull) leaf_intersect<HB>(r, tris, cur, cur_tn, hb, total);
       if (sp) { cur = sref[--sp]; cur_tn = stn[sp]; }
       else cur = kDoneRef;
     }
@@ -121,9 +175,9 @@ __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __re
 
 // ---------------------------------------------------------------- warp packet traversal
 // `wstack`: kStackDepth ints of shared memory private to the warp.  Lanes with active == false never vote.
-template <int KMAX, bool CULL = true>
+template <class HB, bool CULL = true>
 __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const float4* __restrict__ nodes,
-                                                const float4* __restrict__ tris, int K, HitBuf<KMAX>& hb, int& total,
+                                                const float4* __restrict__ tris, int K, HB& hb, int& total,
                                                 int* __restrict__ wstack) {
   int sp = 0;
   int cur = 0;   // warp-uniform
@@ -139,8 +193,8 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
     bool h0 = active && (r0 != kEmptyRef) && slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0) && (tn0 <= tcull);
     bool h1 = active && (r1 != kEmptyRef) && slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1) && (tn1 <= tcull);
     // leaf children: their box is the triangle's own box, so the lanes that pass go straight to Möller–Trumbore
-    if (r0 < 0) { if (h0) leaf_intersect<KMAX>(r, tris, r0, tn0, hb, total); h0 = false; }
-    if (r1 < 0) { if (h1 && tn1 <= (CULL ? hb.cull_distance() : inf)) leaf_intersect<KMAX>(r, tris, r1, tn1, hb, total); h1 = false; }
+    if (r0 < 0) { if (h0) leaf_intersect<HB>(r, tris, r0, tn0, hb, total); h0 = false; }
+    if (r1 < 0) { if (h1 && tn1 <= (CULL ? hb.cull_distance() : inf)) leaf_intersect<HB>(r, tris, r1, tn1, hb, total); h1 = false; }
     const unsigned b0 = __ballot_sync(0xffffffffu, h0), b1 = __ballot_sync(0xffffffffu, h1);
     if (b0 && b1) {
       // order by majority preference of the lanes that hit both (nearer child first)
@@ -175,15 +229,15 @@ __device__ __forceinline__ bool warp_is_coherent(const Ray& r, bool active) {
 
 // Entry used by the trace kernels.  EVERY lane of the warp must call it (invalid lanes pass valid=false).
 // mode: 0 = choose per warp, 1 = always per-lane, 2 = always packet (tuning knob, results are identical)
-template <int KMAX, bool CULL = true>
+template <class HB, bool CULL = true>
 __device__ __forceinline__ void trace_ray(const Ray& r, bool valid, const float4* __restrict__ nodes,
-                                          const float4* __restrict__ tris, int K, HitBuf<KMAX>& hb, int& total,
+                                          const float4* __restrict__ tris, int K, HB& hb, int& total,
                                           int* __restrict__ wstack, int mode = 0) {
   const bool coherent = warp_is_coherent(r, valid);
   if (mode == 2 || (mode == 0 && coherent)) {
-    traverse_packet<KMAX, CULL>(r, valid, nodes, tris, K, hb, total, wstack);
+    traverse_packet<HB, CULL>(r, valid, nodes, tris, K, hb, total, wstack);
   } else if (valid) {
-    traverse_single<KMAX, CULL>(r, nodes, tris, K, hb, total);
+    traverse_single<HB, CULL>(r, nodes, tris, K, hb, total);
   } else {
     hb.init(K);
     total = 0;

@@ -26,7 +26,7 @@ for name in sys.argv[1:] or ["c4", "c5"]:
     lib.qf_profile_read(ms3, C.byref(n)); lib.qf_profile_enable(0)
     ms = e0.elapsed_time(e1) / steps
     hits = int(r["n_hits"])
-    print(f"{name}: {N} rays, {sc.faces_np.shape[0]} tris, K={sc.K}, hits/ray {hits/N:.2f}: {ms:.3f} ms/frame = {N/ms/1e6:.1f} Mrays/s; "
+    print(f"{name}: {N} rays, {sc.faces_np.shape[0]} tris, K={sc.K}, hits/ray {hits/N:.2f}: {ms:.3f} ms/frame = {N/(ms*1e-3)/1e6:.1f} Mrays/s; "
           f"stages/frame trace {ms3[0]/steps:.3f} shade {ms3[1]/steps:.3f} composite {ms3[2]/steps:.3f} ms; mesh {sc.mesh_intersect.rayintersector.info()}", flush=True)
     del sc, rays, out
     torch.cuda.empty_cache()

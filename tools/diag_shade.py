@@ -22,6 +22,14 @@ def timeit(fn, n=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 print("hits", M)
+import ctypes as C
+from quadraturefields_b200 import _lib
+lib = _lib.load()
+outsum = torch.empty(M, device=dev)
+h = sc.radiance_field._native()
+def enc_sum(xx):
+    lib.qf_debug_encode_sum(h, C.c_void_p(xx.data_ptr()), C.c_int64(M), C.c_void_p(outsum.data_ptr()), _lib.stream(dev))
+print("gather only, 4 B out per sample (ray-major hits): %.3f ms" % timeit(lambda: enc_sum(x01)))
 print("encode only (ray-major hits): %.3f ms" % timeit(lambda: sc.radiance_field.encode(x01)))
 print("fused forward (ray-major hits): %.3f ms" % timeit(lambda: sc.radiance_field(pts, d, ray_indices=idx_ray)))
 perm = torch.randperm(M, device=dev)
