@@ -60,169 +60,299 @@ struct FieldArgs {
   float* feat;               // (M,15)                              [mode 1]
 };
 
-template <int MODE>  // 0: full forward (rgb + sigma); 1: density + geo features only
-__global__ void __launch_bounds__(128, 5) ngp_forward_kernel(const FieldArgs a) {
-  __shared__ __align__(16) __half s_w[kWTotal];
-  __shared__ __align__(16) __half s_tile[4][32 * kTileStride];
+// producer half of one 32-sample tile (one warp, lane = sample): normalise, encode the 16 levels and (MODE 0) the SH
+// basis into the lane's row of `tile`; returns the warp's selector ballot
+template <int MODE>
+__device__ __forceinline__ unsigned produce_tile(const FieldArgs& a, const float* amin, const float* aext, int64_t base,
+                                                 int64_t M, int lane, __half* tile) {
+  const int64_t i = base + lane;
+  const bool valid = i < M;
+  float x = 0.5f, y = 0.5f, z = 0.5f;
+  bool sel = false;
+  if (valid) {
+    const float* p = a.pos + i * a.pos_stride;
+    x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);       // ngp.py:761-763
+    y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
+    z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
+    sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
+  }
+  uint32_t* row32 = reinterpret_cast<uint32_t*>(tile + lane * kTileStride);
+  encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) { row32[l] = h2; });
+  uint4* row = reinterpret_cast<uint4*>(row32);
+  if (MODE == 0) {
+    float dx = 0.f, dy = 0.f, dz = 1.f;
+    if (valid) {
+      int64_t r = a.ray64 ? __ldg(a.ray64 + i) : (a.ray32 ? (int64_t)__ldg(a.ray32 + i * a.ray32_stride) : i);
+      const float* dp = a.dirs + 3 * r;
+      // (d+1)/2 then tcnn maps back with *2-1 (ngp.py:784; tcnn SH kernel)
+      dx = ((__ldg(dp) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+      dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+      dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
+    }
+    float sh[16];
+    sh4(dx, dy, dz, sh);
+    row[4] = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sh[3]), pack_h2(sh[4], sh[5]), pack_h2(sh[6], sh[7]));
+    row[5] = make_uint4(pack_h2(sh[8], sh[9]), pack_h2(sh[10], sh[11]), pack_h2(sh[12], sh[13]), pack_h2(sh[14], sh[15]));
+  }
+  return __ballot_sync(0xffffffffu, sel);
+}
+
+// consumer half: the two 16-row m-tiles of `tile` through the MLPs (mma.sync, fragments chained in registers)
+template <int MODE>
+__device__ __forceinline__ void consume_tile(const FieldArgs& a, const __half* s_w, const __half* tile, unsigned selmask,
+                                             int64_t base, int64_t M, int g, int t) {
+#pragma unroll 1
+  for (int mt = 0; mt < 2; ++mt) {
+    if (base + mt * 16 >= M) break;
+    const __half* ta = tile + (mt * 16 + g) * kTileStride + t * 2;
+    const __half* tb = ta + 8 * kTileStride;
+    // ---- base layer 1: 32 -> 64, ReLU
+    uint32_t a1[2][4];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      a1[k][0] = lds32(ta + k * 16); a1[k][1] = lds32(tb + k * 16);
+      a1[k][2] = lds32(ta + k * 16 + 8); a1[k][3] = lds32(tb + k * 16 + 8);
+    }
+    float acc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    layer<2, 8>(acc, a1, s_w + kW1, kS32, g, t);
+    // ---- base layer 2: 64 -> 16 with hi+lo split of the hidden activations
+    uint32_t ahi[4][4], alo[4][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* c = acc[2 * k + h];
+        float r0 = fmaxf(c[0], 0.f), r1 = fmaxf(c[1], 0.f), r2 = fmaxf(c[2], 0.f), r3 = fmaxf(c[3], 0.f);
+        __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
+        float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        ahi[k][2 * h] = *reinterpret_cast<uint32_t*>(&h01);
+        ahi[k][2 * h + 1] = *reinterpret_cast<uint32_t*>(&h23);
+        alo[k][2 * h] = pack_h2(r0 - f01.x, r1 - f01.y);
+        alo[k][2 * h + 1] = pack_h2(r2 - f23.x, r3 - f23.y);
+      }
+    }
+    float acc2[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
+    layer<4, 2>(acc2, alo, s_w + kW2, kS64, g, t);
+    layer<4, 2>(acc2, ahi, s_w + kW2, kS64, g, t);
+    // sigma = trunc_exp(h0 - 1) * selector   (ngp.py:772-775; _TruncExp forward is plain exp)
+    const int64_t r_lo = base + mt * 16 + g, r_hi = r_lo + 8;
+    const float s_lo = ((selmask >> (mt * 16 + g)) & 1u) ? expf(acc2[0][0] - 1.0f) : 0.f;
+    const float s_hi = ((selmask >> (mt * 16 + g + 8)) & 1u) ? expf(acc2[0][2] - 1.0f) : 0.f;
+    if (MODE == 1) {
+      if (t == 0) {
+        if (r_lo < M) a.density[r_lo] = s_lo;
+        if (r_hi < M) a.density[r_hi] = s_hi;
+      }
+      if (a.feat) {
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            int col = n * 8 + t * 2 + q - 1;  // output column 0 is the density logit
+            if (col >= 0) {
+              if (r_lo < M) a.feat[r_lo * 15 + col] = acc2[n][q];
+              if (r_hi < M) a.feat[r_hi * 15 + col] = acc2[n][2 + q];
+            }
+          }
+        }
+      }
+      continue;
+    }
+    // ---- head layer 1: [SH(16) | pad, feat(15)] -> 64, ReLU
+    uint32_t a3[2][4];
+    a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
+    a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
+    a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
+    a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
+    a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
+    // ---- head layer 2: 64 -> 64, ReLU
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* c = acc[2 * k + h];
+        ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+        ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+    layer<4, 8>(acc, ahi, s_w + kW4, kS64, g, t);
+    // ---- head layer 3: 64 -> 3 (first n-tile only), sigmoid
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* c = acc[2 * k + h];
+        ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
+        ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
+      }
+    }
+    float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    layer<4, 1>(acc5, ahi, s_w + kW5, kS64, g, t);
+    const float b_lo = __shfl_down_sync(0xffffffffu, acc5[0][0], 1);
+    const float b_hi = __shfl_down_sync(0xffffffffu, acc5[0][2], 1);
+    if (t == 0) {
+      auto sig = [](float v) { return 1.0f / (1.0f + __expf(-v)); };
+      float4 o_lo = make_float4(sig(acc5[0][0]), sig(acc5[0][1]), sig(b_lo), s_lo);
+      float4 o_hi = make_float4(sig(acc5[0][2]), sig(acc5[0][3]), sig(b_hi), s_hi);
+      if (a.out4) {
+        if (r_lo < M) a.out4[r_lo] = o_lo;
+        if (r_hi < M) a.out4[r_hi] = o_hi;
+      } else {
+        if (r_lo < M) { a.rgb[3 * r_lo] = o_lo.x; a.rgb[3 * r_lo + 1] = o_lo.y; a.rgb[3 * r_lo + 2] = o_lo.z; a.density[r_lo] = o_lo.w; }
+        if (r_hi < M) { a.rgb[3 * r_hi] = o_hi.x; a.rgb[3 * r_hi + 1] = o_hi.y; a.rgb[3 * r_hi + 2] = o_hi.z; a.density[r_hi] = o_hi.w; }
+      }
+    }
+  }
+}
+
+// WARPS warps per CTA share one weight image; CTAs per SM are chosen so that 20 warps are resident (96 registers each).
+// Fewer, larger CTAs replicate the 24 KB weight image less often, which leaves more of the 256 KB L1/shared array as
+// L1 for the table gathers.
+template <int MODE, int WARPS>  // MODE 0: full forward (rgb + sigma); 1: density + geo features only
+__global__ void __launch_bounds__(WARPS * 32, 20 / WARPS) ngp_forward_kernel(const FieldArgs a) {
+  extern __shared__ __align__(16) unsigned char fused_smem[];
+  __half* s_w = reinterpret_cast<__half*>(fused_smem);
+  __half* s_tiles = s_w + kWTotal;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.weights);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
     constexpr int n16 = (MODE == 0 ? kWTotal : kW3) / 8;
-    for (int i = tid; i < n16; i += 128) dst[i] = __ldg(src + i);
+    for (int i = tid; i < n16; i += WARPS * 32) dst[i] = __ldg(src + i);
   }
   __syncthreads();
   const int64_t M = a.d_M ? (int64_t)__ldg(a.d_M) : a.M;
-  __half* tile = s_tile[warp];
+  __half* tile = s_tiles + warp * (32 * kTileStride);
   const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
   const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
 
-  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < M; base += (int64_t)gridDim.x * 128) {
-    const int64_t i = base + lane;
-    const bool valid = i < M;
-    float x = 0.5f, y = 0.5f, z = 0.5f;
-    bool sel = false;
-    if (valid) {
-      const float* p = a.pos + i * a.pos_stride;
-      x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);       // ngp.py:761-763
-      y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
-      z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
-      sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
-    }
-    uint32_t* row32 = reinterpret_cast<uint32_t*>(tile + lane * kTileStride);
-    encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) { row32[l] = h2; });
-    uint4* row = reinterpret_cast<uint4*>(row32);
-    if (MODE == 0) {
-      float dx = 0.f, dy = 0.f, dz = 1.f;
-      if (valid) {
-        int64_t r = a.ray64 ? __ldg(a.ray64 + i) : (a.ray32 ? (int64_t)__ldg(a.ray32 + i * a.ray32_stride) : i);
-        const float* dp = a.dirs + 3 * r;
-        // (d+1)/2 then tcnn maps back with *2-1 (ngp.py:784; tcnn SH kernel)
-        dx = ((__ldg(dp) + 1.0f) / 2.0f) * 2.0f - 1.0f;
-        dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
-        dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
-      }
-      float sh[16];
-      sh4(dx, dy, dz, sh);
-      row[4] = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sh[3]), pack_h2(sh[4], sh[5]), pack_h2(sh[6], sh[7]));
-      row[5] = make_uint4(pack_h2(sh[8], sh[9]), pack_h2(sh[10], sh[11]), pack_h2(sh[12], sh[13]), pack_h2(sh[14], sh[15]));
-    }
-    const unsigned selmask = __ballot_sync(0xffffffffu, sel);
+  for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * 32; base < M; base += (int64_t)gridDim.x * (WARPS * 32)) {
+    const unsigned selmask = produce_tile<MODE>(a, amin, aext, base, M, lane, tile);
     __syncwarp();
-
-#pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
-      if (base + mt * 16 >= M) break;
-      const __half* ta = tile + (mt * 16 + g) * kTileStride + t * 2;
-      const __half* tb = ta + 8 * kTileStride;
-      // ---- base layer 1: 32 -> 64, ReLU
-      uint32_t a1[2][4];
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        a1[k][0] = lds32(ta + k * 16); a1[k][1] = lds32(tb + k * 16);
-        a1[k][2] = lds32(ta + k * 16 + 8); a1[k][3] = lds32(tb + k * 16 + 8);
-      }
-      float acc[8][4];
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<2, 8>(acc, a1, s_w + kW1, kS32, g, t);
-      // ---- base layer 2: 64 -> 16 with hi+lo split of the hidden activations
-      uint32_t ahi[4][4], alo[4][4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float* c = acc[2 * k + h];
-          float r0 = fmaxf(c[0], 0.f), r1 = fmaxf(c[1], 0.f), r2 = fmaxf(c[2], 0.f), r3 = fmaxf(c[3], 0.f);
-          __half2 h01 = __floats2half2_rn(r0, r1), h23 = __floats2half2_rn(r2, r3);
-          float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          ahi[k][2 * h] = *reinterpret_cast<uint32_t*>(&h01);
-          ahi[k][2 * h + 1] = *reinterpret_cast<uint32_t*>(&h23);
-          alo[k][2 * h] = pack_h2(r0 - f01.x, r1 - f01.y);
-          alo[k][2 * h + 1] = pack_h2(r2 - f23.x, r3 - f23.y);
-        }
-      }
-      float acc2[2][4];
-#pragma unroll
-      for (int n = 0; n < 2; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
-      layer<4, 2>(acc2, alo, s_w + kW2, kS64, g, t);
-      layer<4, 2>(acc2, ahi, s_w + kW2, kS64, g, t);
-      // sigma = trunc_exp(h0 - 1) * selector   (ngp.py:772-775; _TruncExp forward is plain exp)
-      const int64_t r_lo = base + mt * 16 + g, r_hi = r_lo + 8;
-      const float s_lo = ((selmask >> (mt * 16 + g)) & 1u) ? expf(acc2[0][0] - 1.0f) : 0.f;
-      const float s_hi = ((selmask >> (mt * 16 + g + 8)) & 1u) ? expf(acc2[0][2] - 1.0f) : 0.f;
-      if (MODE == 1) {
-        if (t == 0) {
-          if (r_lo < M) a.density[r_lo] = s_lo;
-          if (r_hi < M) a.density[r_hi] = s_hi;
-        }
-        if (a.feat) {
-#pragma unroll
-          for (int n = 0; n < 2; ++n) {
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              int col = n * 8 + t * 2 + q - 1;  // output column 0 is the density logit
-              if (col >= 0) {
-                if (r_lo < M) a.feat[r_lo * 15 + col] = acc2[n][q];
-                if (r_hi < M) a.feat[r_hi * 15 + col] = acc2[n][2 + q];
-              }
-            }
-          }
-        }
-        continue;
-      }
-      // ---- head layer 1: [SH(16) | pad, feat(15)] -> 64, ReLU
-      uint32_t a3[2][4];
-      a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
-      a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
-      a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
-      a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
-      a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
-      // ---- head layer 2: 64 -> 64, ReLU
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float* c = acc[2 * k + h];
-          ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
-          ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
-        }
-      }
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<4, 8>(acc, ahi, s_w + kW4, kS64, g, t);
-      // ---- head layer 3: 64 -> 3 (first n-tile only), sigmoid
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float* c = acc[2 * k + h];
-          ahi[k][2 * h] = pack_h2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f));
-          ahi[k][2 * h + 1] = pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f));
-        }
-      }
-      float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-      layer<4, 1>(acc5, ahi, s_w + kW5, kS64, g, t);
-      const float b_lo = __shfl_down_sync(0xffffffffu, acc5[0][0], 1);
-      const float b_hi = __shfl_down_sync(0xffffffffu, acc5[0][2], 1);
-      if (t == 0) {
-        auto sig = [](float v) { return 1.0f / (1.0f + __expf(-v)); };
-        float4 o_lo = make_float4(sig(acc5[0][0]), sig(acc5[0][1]), sig(b_lo), s_lo);
-        float4 o_hi = make_float4(sig(acc5[0][2]), sig(acc5[0][3]), sig(b_hi), s_hi);
-        if (a.out4) {
-          if (r_lo < M) a.out4[r_lo] = o_lo;
-          if (r_hi < M) a.out4[r_hi] = o_hi;
-        } else {
-          if (r_lo < M) { a.rgb[3 * r_lo] = o_lo.x; a.rgb[3 * r_lo + 1] = o_lo.y; a.rgb[3 * r_lo + 2] = o_lo.z; a.density[r_lo] = o_lo.w; }
-          if (r_hi < M) { a.rgb[3 * r_hi] = o_hi.x; a.rgb[3 * r_hi + 1] = o_hi.y; a.rgb[3 * r_hi + 2] = o_hi.z; a.density[r_hi] = o_hi.w; }
-        }
-      }
-    }
+    consume_tile<MODE>(a, s_w, tile, selmask, base, M, g, t);
     __syncwarp();
   }
+}
+
+// ---- warp-specialised variant of the full forward (QF_FIELD_TC=2) ------------------------------------------------------
+// One persistent CTA per SM: PROD producer warps only gather (48 registers each after setmaxnreg.dec) and CONS consumer
+// warps only run the MLPs (setmaxnreg.inc).  Producer p owns two tile slots in shared memory; a full/empty mbarrier
+// pair per slot hands tiles over.  Consumer c serves producers p = c (mod CONS).  Same arithmetic as the fused kernel
+// (produce_tile / consume_tile), so results are bit-identical.  Measured (16 producers + 4 consumers): c2 0.255 ms,
+// c4 3.54 ms against 0.251 / 3.87 ms for the fused kernel: the gather is bound by L1TEX wavefronts, not by the MLP
+// phases sharing its warps, so the split only pays where the larger L1 share (less shared memory) does.
+constexpr int kWsSlots = 2;
+constexpr int kWsTileHalfs = 32 * kTileStride;
+constexpr int kWsProdRegs = 48;
+template <int PROD, int CONS>
+struct WsCfg {
+  static constexpr int kThreads = (PROD + CONS) * 32;
+  // ptxas allocates the launch_bounds maximum per thread; setmaxnreg.inc blocks forever if the CTA's pool
+  // (threads x launch registers) cannot cover producers x 48 + consumers x kConsRegs
+  static constexpr int kLaunchRegs = 65536 / kThreads / 8 * 8;
+  static constexpr int kConsRegsRaw = (kThreads * kLaunchRegs - PROD * 32 * kWsProdRegs) / (CONS * 32) / 8 * 8;
+  static constexpr int kConsRegs = kConsRegsRaw > 200 ? 200 : kConsRegsRaw;
+  static constexpr int kSmTiles = kWTotal * 2;
+  static constexpr int kSmSel = kSmTiles + PROD * kWsSlots * kWsTileHalfs * 2;
+  static constexpr int kSmBar = (kSmSel + PROD * kWsSlots * 4 + 7) / 8 * 8;
+  static constexpr int kSmemBytes = kSmBar + 2 * PROD * kWsSlots * 8;
+  static_assert(PROD % 4 == 0 && CONS % 4 == 0 && PROD % CONS == 0 && kThreads <= 1024, "warpgroup-aligned roles");
+  static_assert(kSmTiles % 16 == 0 && kSmemBytes <= 227 * 1024 && kConsRegs >= 96, "warp-specialised smem / register budget");
+};
+
+__device__ __forceinline__ uint32_t ws_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ws_mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void ws_mbar_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(mbar) : "memory");
+}
+
+template <int PROD, int CONS>
+__global__ void __launch_bounds__((PROD + CONS) * 32, 1) ngp_forward_ws_kernel(const FieldArgs a) {
+  using Cfg = WsCfg<PROD, CONS>;
+  extern __shared__ __align__(16) unsigned char ws_smem[];
+  __half* s_w = reinterpret_cast<__half*>(ws_smem);
+  __half* s_tiles = reinterpret_cast<__half*>(ws_smem + Cfg::kSmTiles);
+  uint32_t* s_sel = reinterpret_cast<uint32_t*>(ws_smem + Cfg::kSmSel);
+  const uint32_t bar_full = ws_smem_u32(ws_smem + Cfg::kSmBar), bar_empty = bar_full + PROD * kWsSlots * 8;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(a.weights);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = tid; i < kWTotal / 8; i += Cfg::kThreads) dst[i] = __ldg(src + i);
+    if (tid < 2 * PROD * kWsSlots)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(bar_full + tid * 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  const int64_t M = a.d_M ? (int64_t)__ldg(a.d_M) : a.M;
+  const int64_t n_tiles = (M + 31) >> 5;
+  // round `it` of this CTA takes PROD consecutive tiles, one per producer warp
+  const int64_t round_stride = (int64_t)gridDim.x * PROD;
+
+  if (warp < PROD) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"(kWsProdRegs));
+    const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
+    const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
+    int it = 0;
+    for (int64_t tile_id = (int64_t)blockIdx.x * PROD + warp; tile_id < n_tiles; tile_id += round_stride, ++it) {
+      const int idx = warp * kWsSlots + (it & 1), use = it >> 1;
+      if (use > 0) ws_mbar_wait(bar_empty + idx * 8, (use - 1) & 1);
+      const unsigned selmask = produce_tile<0>(a, amin, aext, tile_id * 32, M, lane, s_tiles + idx * kWsTileHalfs);
+      if (lane == 0) s_sel[idx] = selmask;
+      __syncwarp();
+      if (lane == 0) ws_mbar_arrive(bar_full + idx * 8);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"(Cfg::kConsRegs));
+    const int c = warp - PROD, g = lane >> 2, t = lane & 3;
+    for (int it = 0;; ++it) {
+      const int64_t round_base = (int64_t)blockIdx.x * PROD + it * round_stride;
+      if (round_base + c >= n_tiles) break;
+      const int use = it >> 1;
+#pragma unroll 1
+      for (int p = c; p < PROD; p += CONS) {
+        const int64_t tile_id = round_base + p;
+        if (tile_id >= n_tiles) break;
+        const int idx = p * kWsSlots + (it & 1);
+        ws_mbar_wait(bar_full + idx * 8, use & 1);
+        const unsigned selmask = s_sel[idx];
+        consume_tile<0>(a, s_w, s_tiles + idx * kWsTileHalfs, selmask, tile_id * 32, M, g, t);
+        __syncwarp();
+        if (lane == 0) ws_mbar_arrive(bar_empty + idx * 8);
+      }
+    }
+  }
+}
+
+template <int PROD, int CONS>
+static int launch_ws(FieldArgs& a, cudaStream_t st) {
+  using Cfg = WsCfg<PROD, CONS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_ws_kernel<PROD, CONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  int64_t rounds = a.d_M ? kNumSMs : ceil_div(a.M, 32 * PROD);
+  int blocks = (int)(rounds < kNumSMs ? (rounds < 1 ? 1 : rounds) : kNumSMs);
+  ngp_forward_ws_kernel<PROD, CONS><<<blocks, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
 }
 
 __global__ void hashgrid_forward_kernel(const qf_grid_desc desc, const __half2* __restrict__ table,
@@ -246,7 +376,7 @@ struct FieldTcArgs {
 int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st);
 int prep_weights_tc(qf_ngp* f, cudaStream_t st);
 
-// QF_FIELD_TC=0 selects the mma.sync kernel, 1 the tcgen05/TMEM kernel for the full forward
+// QF_FIELD_TC=0 selects the fused mma.sync kernel, 1 the tcgen05/TMEM kernel, 2 the warp-specialised mma.sync kernel
 static int field_tc_mode() {
   static const int m = getenv("QF_FIELD_TC") ? atoi(getenv("QF_FIELD_TC")) : 0;
   return m;
@@ -265,6 +395,24 @@ __global__ void __launch_bounds__(128) encode_sum_kernel(const qf_grid_desc desc
   out[i] = acc;
 }
 
+template <int WARPS>
+static int launch_fused(FieldArgs& a, int mode, cudaStream_t st) {
+  constexpr int smem = kWTotal * 2 + WARPS * 32 * kTileStride * 2, per_sm = 20 / WARPS;   // one resident wave
+  static bool attr_set = false;
+  if (!attr_set) {
+    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_kernel<0, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_kernel<1, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  int64_t tiles = a.d_M ? (int64_t)kNumSMs * per_sm : ceil_div(a.M, WARPS * 32);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
+  if (blocks < 1) blocks = 1;
+  if (mode == 0) ngp_forward_kernel<0, WARPS><<<blocks, WARPS * 32, smem, st>>>(a);
+  else ngp_forward_kernel<1, WARPS><<<blocks, WARPS * 32, smem, st>>>(a);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
 int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {
   if (mode == 0 && field_tc_mode() == 1) {
     FieldTcArgs t = {};
@@ -275,17 +423,16 @@ int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st)
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights = f->d_weights;
-  static const int per_sm = getenv("QF_SHADE_BLOCKS_PER_SM") ? atoi(getenv("QF_SHADE_BLOCKS_PER_SM")) : 5;   // one resident wave: 5 CTAs/SM at 96 registers
-  int64_t tiles = a.d_M ? (int64_t)kNumSMs * per_sm : ceil_div(a.M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
-  if (blocks < 1) blocks = 1;
-  if (mode == 0) ngp_forward_kernel<0><<<blocks, 128, 0, st>>>(a);
-  else ngp_forward_kernel<1><<<blocks, 128, 0, st>>>(a);
-  QF_LAUNCH_CHECK();
-  return QF_OK;
+  if (mode == 0 && field_tc_mode() == 2) return launch_ws<16, 4>(a, st);
+  // 10 warps per CTA, 2 CTAs per SM measured best (c2 0.251 ms, c4 3.87 ms; 4 warps x 5 CTAs: 0.252 / 4.67 ms)
+  static const int warps = getenv("QF_SHADE_WARPS") ? atoi(getenv("QF_SHADE_WARPS")) : 10;
+  switch (warps) {
+    case 4: return launch_fused<4>(a, mode, st);
+    case 20: return launch_fused<20>(a, mode, st);
+    default: return launch_fused<10>(a, mode, st);
+  }
 }
 
-// shading entry for the fused render (render.cu): compact hit records in, (rgb, sigma) out
 int launch_ngp_forward_hits(const qf_ngp* f, const float4* hit_pd, const int2* hit_rt, const float* d_viewdirs,
                             const int32_t* d_M, float4* out4, cudaStream_t st) {
   FieldArgs a = {};

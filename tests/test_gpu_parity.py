@@ -207,9 +207,11 @@ def test_ngp_forward_matches_oracle(dev, smoke_scene):
     assert maxabs(r, r2) == 0.0 and maxabs(s, s2) == 0.0
 
 
-def test_ngp_forward_tcgen05_variant(dev):
-    """The tcgen05 / TMEM variant of the fused field kernel (csrc/field_tc.cu, selected with QF_FIELD_TC=1) against the
-    oracle and against the default mma.sync kernel.  Runs in a subprocess because the selection is read once per process."""
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_ngp_forward_kernel_variants(dev, variant):
+    """The alternative full-forward kernels against the oracle: QF_FIELD_TC=1 is the tcgen05 / TMEM kernel
+    (csrc/field_tc.cu), QF_FIELD_TC=2 the warp-specialised producer/consumer kernel (csrc/field.cu).  Runs in a
+    subprocess because the selection is read once per process."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent("""
         import os, sys, torch, numpy as np
@@ -227,7 +229,7 @@ def test_ngp_forward_tcgen05_variant(dev):
         rgb_ref, dens_ref = O.ngp_forward(x, d, p)
         with torch.no_grad():
             rgb, dens = sc.radiance_field(x.to(dev), d.to(dev))
-            for n in (1, 127, 128, 129):
+            for n in (1, 127, 128, 129, 32 * 24 * 2 + 5):
                 r, s = sc.radiance_field(x[:n].to(dev), d[:n].to(dev))
                 assert maxabs(r, rgb[:n]) == 0.0 and maxabs(s, dens[:n]) == 0.0
         a_ref, a = 1 - torch.exp(-dens_ref * 0.005), 1 - torch.exp(-dens.cpu() * 0.005)
@@ -239,7 +241,7 @@ def test_ngp_forward_tcgen05_variant(dev):
         assert maxabs(out["rgb"], ref["rgb"]) <= 1e-3 and maxabs(out["opacity"], ref["opacity"]) <= 1e-3
         print("TC_OK")
     """)
-    env = dict(os.environ, QF_FIELD_TC="1")
+    env = dict(os.environ, QF_FIELD_TC=variant)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     res = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0 and "TC_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
