@@ -310,7 +310,7 @@ def run_ours(args):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = next((v for k, v in tj["dram_bytes_per_launch"].items() if "ngp_forward_kernel<0>" in k), None)
+            traffic = next((v for k, v in tj["dram_bytes_per_launch"].items() if k.startswith("ngp_forward_kernel<0")), None)
         except Exception:
             pass
         line = {
@@ -329,7 +329,7 @@ def run_ours(args):
             "stage_ms_per_step_in_timed_region": {"trace": ms3o[0] / max(ncho.value, 1), "shade": shade_ms_overlapped,
                                                   "composite": ms3o[2] / max(ncho.value, 1),
                                                   "note": "frames alternate on 2 streams, so kernels of neighbouring frames overlap"},
-            "roofline": {"bound": "hbm", "kernel": "ngp_forward_kernel<0> (hash-grid gather + fused MLPs)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "ngp_forward_kernel<0, 10> (hash-grid gather + fused MLPs)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_hit": 512, "hits_per_launch": hits_per_launch, "peak_source": peak_src,
                          "achieved_in_timed_region": (512.0 * hits_per_launch / (shade_ms_overlapped * 1e-3) / 1e9) if shade_ms_overlapped > 0 else 0.0,

@@ -40,3 +40,19 @@ key = ((x01[:, 2] * 64).long() * 4096 + (x01[:, 1] * 64).long() * 64 + (x01[:, 0
 xm = x01[torch.argsort(key)].contiguous()
 print("encode only (grid-sorted hits): %.3f ms" % timeit(lambda: sc.radiance_field.encode(xm)))
 print("density only (ray-major): %.3f ms" % timeit(lambda: sc.radiance_field.query_density(pts)))
+# slot-major inside 8x4 pixel tiles: the 32 lanes of a warp hold the j-th hits of 32 neighbouring pixels
+W = sc.W
+r = idx_ray.long()
+px, py = r % W, r // W
+tile = (py // 4) * (W // 8) + px // 8
+intile = (py % 4) * 8 + px % 8
+first = torch.ones_like(r, dtype=torch.bool); first[1:] = r[1:] != r[:-1]
+start = torch.cummax(torch.where(first, torch.arange(M, device=dev), torch.zeros_like(r)), 0).values
+slot = torch.arange(M, device=dev) - start
+key2 = (tile * 64 + slot) * 32 + intile
+xt = x01[torch.argsort(key2)].contiguous()
+print("encode only (slot-major in 8x4 pixel tiles): %.3f ms" % timeit(lambda: sc.radiance_field.encode(xt)))
+print("gather only (slot-major in 8x4 pixel tiles): %.3f ms" % timeit(lambda: enc_sum(xt)))
+print("gather only (grid-sorted): %.3f ms" % timeit(lambda: enc_sum(xm)))
+pt = pts[torch.argsort(key2)].contiguous(); dt = d[r[torch.argsort(key2)]].contiguous()
+print("fused forward (slot-major in 8x4 pixel tiles): %.3f ms" % timeit(lambda: sc.radiance_field(pt, dt)))
