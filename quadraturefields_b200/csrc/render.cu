@@ -5,8 +5,10 @@
 //
 //   trace_compact_kernel : one thread per ray; traversal (traverse.cuh), plane-hit point + depth per hit
 //                          (mesh_utils.py:33-40,371), stable depth order (:375), then the CTA reserves a
-//                          contiguous run of the compact hit array with ONE atomicAdd, so samples of
-//                          neighbouring pixels stay adjacent for the gather-bound shading kernel.
+//                          contiguous run of the compact hit array with ONE atomicAdd.  Inside a warp's run the
+//                          records are slot-major: all first hits of the 32 rays, then all second hits, ... so
+//                          the 32 samples of a shading warp are same-depth-order hits of neighbouring pixels and
+//                          share hash-grid cells (fused field kernel -8 % at c2, -22 % at c4 against ray-major).
 //   shading              : ngp_forward_kernel (field.cu) or baked_shade_kernel (baked.cu) over the M live
 //                          samples only (M is read from device memory; persistent grid of 148 x k CTAs).
 //   composite_rays_kernel: derive_properties (utils.py:863-898) per ray.
@@ -26,7 +28,7 @@ int launch_baked_shade(const qf_texture* tex, const qf_mesh* mesh, const float* 
 
 struct Workspace {
   int32_t* cursor;     // [0] live hit samples of the current chunk
-  int32_t* ray_start;  // (CH)
+  int32_t* ray_start;  // (CH) first record of the ray's WARP run (slot-major inside the run, see warp_slot_layout)
   int32_t* ray_count;  // (CH)
   float4* hit_pd;      // (CH*K) psi.xyz, depth
   int2* hit_rt;        // (CH*K) ray id (global), triangle id
@@ -51,6 +53,16 @@ static size_t workspace_layout(int64_t n_rays, int K, Workspace* w, char* base) 
   return off;
 }
 
+// Ray handled by a thread: linear, or an 8x4 pixel tile per warp for image-ordered rays (tighter packets, and the
+// compacted hit samples of a warp stay close in space for the gather-bound shading kernel).  trace and composite
+// must agree on it: the slot-major record layout is defined per warp.
+__device__ __forceinline__ int64_t ray_of_thread(int64_t linear, int lane, int img_w) {
+  if (img_w <= 0) return linear;
+  const int64_t gw = linear >> 5;
+  const int tiles = img_w >> 3;
+  return ((gw / tiles) * 4 + (lane >> 3)) * img_w + (gw % tiles) * 8 + (lane & 7);
+}
+
 template <class HB>
 __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                             const float4* __restrict__ planes, const float* __restrict__ scene,
@@ -63,14 +75,9 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   __shared__ int s_base;
   __shared__ int s_stack[4][kStackDepth];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int64_t li = blockIdx.x * (int64_t)blockDim.x + tid;  // ray inside the chunk
-  if (img_w > 0) {
-    // image-ordered rays: a warp takes an 8x4 pixel tile instead of a 32x1 strip (tighter packets, and the
-    // compacted hit samples of a CTA stay close in space for the gather-bound shading kernel)
-    const int64_t gw = li >> 5;
-    const int tiles = img_w >> 3;
-    li = ((gw / tiles) * 4 + (lane >> 3)) * img_w + (gw % tiles) * 8 + (lane & 7);
-  }
+  __shared__ int s_slot_off[4][QF_MAX_HITS];        // records of the warp's run before slot j
+  __shared__ unsigned s_slot_mask[4][QF_MAX_HITS];  // lanes that have a j-th hit
+  const int64_t li = ray_of_thread(blockIdx.x * (int64_t)blockDim.x + tid, lane, img_w);  // ray inside the chunk
   __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   const bool valid = li < n;
@@ -90,9 +97,19 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
     s_base = t ? atomicAdd(cursor, t) : 0;
   }
   __syncthreads();
+  // slot-major layout of the warp's run: record (lane, j) sits at warp_start + off[j] + rank of lane among mask[j]
+  const int warp_start = s_base + s_warp[warp];
+  const int cmax = __reduce_max_sync(0xffffffffu, c);
+  for (int j = 0, off = 0; j < cmax; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, c > j);
+    if (lane == 0) { s_slot_off[warp][j] = off; s_slot_mask[warp][j] = m; }
+    off += __popc(m);
+  }
+  __syncwarp();
   if (!valid) return;
-  const int start = s_base + s_warp[warp] + inc - c;
-  ray_start[li] = start;
+  const unsigned lt = (1u << lane) - 1u;
+  auto pos = [&](int j) { return warp_start + s_slot_off[warp][j] + __popc(s_slot_mask[warp][j] & lt); };
+  ray_start[li] = warp_start;
   ray_count[li] = c;
   float prev = -1.f;
   bool unsorted = false;
@@ -102,23 +119,24 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
     float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
     unsorted |= d < prev;
     prev = d;
-    hit_pd[start + j] = make_float4(px, py, pz, d);
-    hit_rt[start + j] = make_int2((int)(ray0 + li), id);
+    const int p = pos(j);
+    hit_pd[p] = make_float4(px, py, pz, d);
+    hit_rt[p] = make_int2((int)(ray0 + li), id);
   });
   if (unsorted) {  // rare: plane-hit depth order differs from Möller–Trumbore t order; stable insertion sort
     for (int s = 1; s < c; ++s) {
-      float4 pd = hit_pd[start + s];
-      int2 rt = hit_rt[start + s];
+      float4 pd = hit_pd[pos(s)];
+      int2 rt = hit_rt[pos(s)];
       int q = s;
       while (q > 0) {
-        float4 o = hit_pd[start + q - 1];
+        float4 o = hit_pd[pos(q - 1)];
         if (!(o.w > pd.w)) break;
-        hit_pd[start + q] = o;
-        hit_rt[start + q] = hit_rt[start + q - 1];
+        hit_pd[pos(q)] = o;
+        hit_rt[pos(q)] = hit_rt[pos(q - 1)];
         --q;
       }
-      hit_pd[start + q] = pd;
-      hit_rt[start + q] = rt;
+      hit_pd[pos(q)] = pd;
+      hit_rt[pos(q)] = rt;
     }
   }
 }
@@ -127,24 +145,35 @@ __global__ void composite_rays_kernel(const int32_t* __restrict__ ray_start, con
                                       const float4* __restrict__ hit_pd, const float4* __restrict__ hit_out, float delta,
                                       int64_t ray0, int64_t n, int bg_mode, const float* __restrict__ bkgd,
                                       float* __restrict__ rgb, float* __restrict__ alpha_out, float* __restrict__ depth_out,
-                                      const int32_t* __restrict__ cursor, int32_t* __restrict__ hits_total) {
-  int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (li == 0 && hits_total) atomicAdd(hits_total, *cursor);
-  if (li >= n) return;
-  const int s = ray_start[li], c = ray_count[li];
+                                      const int32_t* __restrict__ cursor, int32_t* __restrict__ hits_total, int img_w) {
+  const int64_t linear = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  if (linear == 0 && hits_total) atomicAdd(hits_total, *cursor);
+  const int64_t li = ray_of_thread(linear, lane, img_w);  // same warp <-> rays mapping as trace_compact_kernel
+  const bool valid = li < n;
+  const int s = valid ? ray_start[li] : 0, c = valid ? ray_count[li] : 0;
   float fill = bg_mode == QF_BG_BLACK ? 0.f : 1.f;
   float r = fill, g = fill, b = fill, A = 0.f, D = 0.f;
-  if (c > 0) {
-    float cum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-    for (int j = s; j < s + c; ++j) {
-      float4 o = hit_out[j];
+  float cum = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+  // walk the warp's slot-major run: the j-th hits of the 32 rays are adjacent records
+  const int cmax = __reduce_max_sync(0xffffffffu, c);
+  const unsigned lt = (1u << lane) - 1u;
+  for (int j = 0, off = 0; j < cmax; ++j) {
+    const unsigned m = __ballot_sync(0xffffffffu, c > j);
+    if (c > j) {
+      const int p = s + off + __popc(m & lt);
+      float4 o = hit_out[p];
       float tau = o.w * delta;
       float w = expf(-cum) * (1.0f - expf(-tau));
       cum += tau;
       cr += w * o.x; cg += w * o.y; cb += w * o.z;
-      D += w * hit_pd[j].w;
+      D += w * hit_pd[p].w;
       A += w;
     }
+    off += __popc(m);
+  }
+  if (!valid) return;
+  if (c > 0) {
     if (bg_mode == QF_BG_WHITE) { r = (1.f - A) + A * cr; g = (1.f - A) + A * cg; b = (1.f - A) + A * cb; }
     else if (bg_mode == QF_BG_BLACK) { r = A * cr; g = A * cg; b = A * cb; }
     else { r = A * cr + (1.f - A) * bkgd[0]; g = A * cg + (1.f - A) * bkgd[1]; b = A * cb + (1.f - A) * bkgd[2]; }
@@ -229,7 +258,7 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     if (rc != QF_OK) return rc;
     if (g_prof.enabled) cudaEventRecord(pe[2], st);
     composite_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(w.ray_start, w.ray_count, w.hit_pd, w.hit_out, delta, ray0, n,
-                                                                 bg_mode, d_bkgd, d_rgb, d_alpha, d_depth, w.cursor, d_hits_total);
+                                                                 bg_mode, d_bkgd, d_rgb, d_alpha, d_depth, w.cursor, d_hits_total, img_w);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) { cudaEventRecord(pe[3], st); for (auto e : pe) g_prof.ev.push_back(e); }
   }

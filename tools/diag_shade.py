@@ -6,7 +6,7 @@ import __graft_entry__ as entry
 entry.build()
 from quadraturefields_b200 import scene as S
 dev = torch.device("cuda:0")
-sc = S.make_scene("c2", device=dev)
+sc = S.make_scene(sys.argv[1] if len(sys.argv) > 1 else "c2", device=dev)
 o, d = sc.rays(3)
 tup = sc.mesh_intersect.sampling_raytrace(d, o)
 pts, idx_ray = tup[0], tup[2]
