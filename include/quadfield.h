@@ -227,6 +227,24 @@ int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float
                          int bg_mode, const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth,
                          int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (6) Mesh finetuning accumulators: replace the torch_scatter calls of
+ * MeshFinetune (mesh_utils.py:112-156) and of the prune pass (prune_mesh_after_finetuning.py:354-357).
+ * ------------------------------------------------------------------------------------------ */
+/* MeshFinetune.update_d (mesh_utils.py:126-133): cache_d[tri] += d*w (F,3), cache_w[tri] += w (F,) over M samples. */
+int qf_triangle_accumulate(const float* d_disp, const float* d_w, const int64_t* d_index_tri, int64_t M,
+                           int64_t n_faces, float* d_cache_d, float* d_cache_w, void* stream);
+/* MeshFinetune.update_faces (mesh_utils.py:135-144): per-triangle clip(cache_d / cache_w, +-scaling), scatter_mean over
+ * the face corners onto the vertices, d_vertices (V,3) += mean (in place; pass the result to qf_mesh_update_vertices). */
+size_t qf_vertex_displace_workspace_bytes(int64_t n_vertices);
+int qf_vertex_displace(const float* d_cache_d, const float* d_cache_w, const int32_t* d_faces, int64_t n_faces,
+                       int64_t n_vertices, float scaling, float* d_vertices, void* d_workspace, size_t workspace_bytes,
+                       void* stream);
+/* prune pass: tri_w[tri] = max(tri_w[tri], w) with the running maximum starting at 0
+ * (scatter_max into zeros + torch.maximum, prune_mesh_after_finetuning.py:354-357); weights read `stride` floats apart. */
+int qf_triangle_weight_max(const float* d_weights, int64_t stride, const int64_t* d_index_tri, int64_t M,
+                           int64_t n_faces, float* d_tri_w, void* stream);
+
 /* Optional per-stage CUDA-event timing of the fused render on its own stream (off by default).
  * qf_profile_read sums {trace, shade, composite} milliseconds recorded since the last read (synchronises). */
 int qf_profile_enable(int on);

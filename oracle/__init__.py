@@ -14,6 +14,10 @@ Parity status:
     ``NGPRadianceField`` module glue (a5/a6): PINNED to outputs of the unmodified
     reference python, run on CPU behind stand-ins for its absent third-party
     imports (``oracle/shims``; generator ``oracle/make_golden.py``).
+  * the bake writer ``FeatureCompression.compress`` (f-4) and the mesh finetuning
+    accumulators ``MeshFinetune`` / prune ``scatter_max`` (f-3): PINNED the same way
+    (``tests/golden/sg_decode.npz``, ``tests/golden/mesh_finetune.npz``; torch_scatter
+    is a stand-in with its documented semantics).
   * the arithmetic that lives in absent third-party native code — Embree/OptiX
     ray-mesh intersection, tinycudann hash grid / fully fused MLP / SH, kaolin
     pack scans — is PARITY UNPINNED: it is restated from the published algorithms

@@ -248,6 +248,41 @@ def golden_ngp():
                 rgb=rgb.detach(), density=density.detach(), feat=feat.detach(), selector=sel, xn=xn)
 
 
+def golden_mesh_finetune():
+    """f-3: the reference's MeshFinetune (update_d x2, update_faces, reset_d) and the prune pass's scatter_max,
+    executed over the torch_scatter stand-in."""
+    import mesh_utils as MU
+    from torch_scatter import scatter_max
+    from oracle import quadfield_oracle as O
+    verts, faces = O.shell_mesh([0.5, 0.8], subdivisions=2, jitter=1e-3, seed=11)
+    g = torch.Generator().manual_seed(12)
+    F, M = faces.shape[0], 5000
+    mf = MU.MeshFinetune(verts.copy(), faces.astype(np.int64), 0.01)
+    out = dict(verts=verts, faces=faces, scaling=np.float32(0.01))
+    for it in range(2):
+        d = 0.02 * torch.randn(M, 3, generator=g)
+        w = torch.rand(M, generator=g)
+        idx = torch.randint(0, F - 7, (M,), generator=g)          # the last 7 triangles never get a sample
+        mf.update_d(d, w, idx)
+        out.update({f"d{it}": d, f"w{it}": w, f"idx{it}": idx})
+    out["cache_d"], out["cache_w"] = mf.cache_d.clone(), mf.cache_w.clone()
+    mf.update_faces()
+    out["verts_after"] = np.asarray(mf.vertices, np.float32)
+    mf.reset_d()
+    out["cache_w_reset"] = mf.cache_w.clone()
+    # prune pass: two frames of scatter_max + maximum
+    tri_w = torch.zeros(F)
+    for it in range(2):
+        wts = torch.rand(M, 1, generator=g) - 0.1                   # a few negative entries
+        idx = torch.randint(0, F - 7, (M,), generator=g)
+        cur = torch.zeros_like(tri_w)
+        scatter_max(wts[:, 0], idx, out=cur)
+        tri_w = torch.maximum(tri_w, cur)
+        out.update({f"pw{it}": wts, f"pidx{it}": idx})
+    out["tri_w"] = tri_w
+    return out
+
+
 def _np(v):
     if isinstance(v, torch.Tensor):
         return v.detach().cpu().numpy()
@@ -259,7 +294,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
                      ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
-                     ("ngp", golden_ngp)):
+                     ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune)):
         data = {k: _np(v) for k, v in fn().items()}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

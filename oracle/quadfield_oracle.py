@@ -956,3 +956,38 @@ def render_mesh_baked(origins, viewdirs, vertices, faces, uv_scaled, tex: Textur
                                                         bg_color=bg_color, N=N)
     return dict(rgb=rgb, opacity=opacity, depth=Depth, index_ray=index_ray_t, index_tri=index_tri_t,
                 weights=weights, texels=texels, rgbs=rgbs, sigmas=sigmas, points=points_t)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f-3: mesh finetuning accumulators (mesh_utils.py:112-156; prune_mesh_after_finetuning.py:354-357)
+# ---------------------------------------------------------------------------------------------------------------------
+def mesh_finetune_update_d(cache_d, cache_w, d, w, index_tri):
+    """MeshFinetune.update_d (mesh_utils.py:126-133): scatter d*w and w per triangle, add to the caches (fp64 sums so the
+    oracle does not depend on accumulation order; the kernel's fp32 atomics are compared with a tolerance)."""
+    cache_d, cache_w = np.asarray(cache_d, np.float32), np.asarray(cache_w, np.float32)
+    d, w, index_tri = np.asarray(d, np.float32), np.asarray(w, np.float32), np.asarray(index_tri, np.int64)
+    acc_d = np.zeros(cache_d.shape, np.float64)
+    acc_w = np.zeros(cache_w.shape, np.float64)
+    np.add.at(acc_d, index_tri, (d * w[:, None]).astype(np.float64))
+    np.add.at(acc_w, index_tri, w.astype(np.float64))
+    return (cache_d + acc_d).astype(np.float32), (cache_w + acc_w).astype(np.float32)
+
+
+def mesh_finetune_update_faces(vertices, faces, cache_d, cache_w, scaling):
+    """MeshFinetune.update_faces (mesh_utils.py:135-144): clip(cache_d / cache_w, +-scaling) per triangle, scatter_mean over
+    the face corners (count clamped to >= 1), vertices += mean."""
+    vertices, faces = np.asarray(vertices, np.float32), np.asarray(faces, np.int64)
+    deform = np.clip(np.asarray(cache_d, np.float32) / np.asarray(cache_w, np.float32)[:, None], -np.float32(scaling), np.float32(scaling))
+    sums = np.zeros(vertices.shape, np.float64)
+    cnt = np.zeros(vertices.shape[0], np.float64)
+    np.add.at(sums, faces.reshape(-1), np.repeat(deform, 3, axis=0).astype(np.float64))
+    np.add.at(cnt, faces.reshape(-1), 1.0)
+    dv = (sums / np.maximum(cnt, 1.0)[:, None]).astype(np.float32)
+    return vertices + dv
+
+
+def triangle_weight_max(tri_w, weights, index_tri):
+    """prune pass (prune_mesh_after_finetuning.py:354-357): scatter_max into zeros, then the running torch.maximum."""
+    cur = np.zeros_like(np.asarray(tri_w, np.float32))
+    np.maximum.at(cur, np.asarray(index_tri, np.int64), np.asarray(weights, np.float32))
+    return np.maximum(np.asarray(tri_w, np.float32), cur)

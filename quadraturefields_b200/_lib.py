@@ -54,6 +54,10 @@ _SIGS = {
     "qf_texture_decode": (_I, [_P, _P, _L, _P, _P]),
     "qf_texture_compress": (_I, [_P, _L, _I, _I, _F, _P, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "qf_sg_features_to_rgb": (_I, [_P, _L, _I, _P, _L, _P, _P]),
+    "qf_triangle_accumulate": (_I, [_P, _P, _P, _L, _L, _P, _P, _P]),
+    "qf_vertex_displace_workspace_bytes": (C.c_size_t, [_L]),
+    "qf_vertex_displace": (_I, [_P, _P, _P, _L, _L, _F, _P, _P, C.c_size_t, _P]),
+    "qf_triangle_weight_max": (_I, [_P, _L, _P, _L, _L, _P, _P]),
     "qf_hit_texels": (_I, [_P, _P, _P, _L, _P, _I, _P, _P]),
     "qf_derive_properties": (_I, [_P, _P, _P, _F, _P, _L, _I, _P, _P, _P, _P, _P, _P]),
     "qf_derive_properties_backward": (_I, [_P, _P, _P, _F, _P, _L, _L, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -167,6 +167,77 @@ class RayIntersector:
             pass
 
 
+class MeshFinetune:
+    """mesh_utils.py:112-156: accumulates the weight-averaged per-triangle displacement of the quadrature points and
+    applies it to the vertices.  The caches, the vertices and the scatters stay on the device (`vertices_t`); the
+    `vertices` property gives the reference's numpy view.  After `update_faces()` pass `vertices_t` to
+    `RayIntersector.update_intersector` to refit the BVH (train_finetune.py:709-718)."""
+
+    def __init__(self, vertices, faces, scaling, device="cuda") -> None:
+        self.device = torch.device(device)
+        self.vertices_t = torch.as_tensor(np.asarray(vertices, dtype=np.float32)).to(self.device).contiguous().clone()
+        f = faces if isinstance(faces, torch.Tensor) else torch.as_tensor(np.asarray(faces))
+        self.faces = f.to(self.device).long()
+        self._faces32 = self.faces.to(torch.int32).contiguous()
+        n = self.faces.shape[0]
+        self.cache_d = torch.zeros((n, 3), device=self.device)
+        self.cache_w = torch.ones(n, device=self.device) * 1e-8
+        self.scaling = scaling
+
+    @property
+    def vertices(self) -> np.ndarray:
+        return self.vertices_t.cpu().numpy()
+
+    @torch.no_grad()
+    def update_d(self, d, w, index_tri):
+        lib = _lib.load()
+        d = d.detach().to(self.device, torch.float32).contiguous()
+        w = w.detach().to(self.device, torch.float32).contiguous()
+        idx = index_tri.to(self.device, torch.int64).contiguous()
+        if d.shape[0] != w.shape[0] or d.shape[0] != idx.shape[0] or d.dim() != 2 or d.shape[1] != 3:
+            raise ValueError("update_d expects d (M,3), w (M,), index_tri (M,)")
+        _lib.check(lib.qf_triangle_accumulate(_lib.ptr(d), _lib.ptr(w), _lib.ptr(idx), d.shape[0], self.cache_w.shape[0],
+                                              _lib.ptr(self.cache_d), _lib.ptr(self.cache_w), _lib.stream(self.device)),
+                   "qf_triangle_accumulate")
+
+    @torch.no_grad()
+    def update_faces(self):
+        lib = _lib.load()
+        V = self.vertices_t.shape[0]
+        ws = _lib.workspace(self.device, lib.qf_vertex_displace_workspace_bytes(V))
+        _lib.check(lib.qf_vertex_displace(_lib.ptr(self.cache_d), _lib.ptr(self.cache_w), _lib.ptr(self._faces32),
+                                          self._faces32.shape[0], V, float(self.scaling), _lib.ptr(self.vertices_t),
+                                          _lib.ptr(ws), ws.numel() * ws.element_size(), _lib.stream(self.device)),
+                   "qf_vertex_displace")
+
+    @torch.no_grad()
+    def reset_d(self):
+        self.cache_d[:] = 0
+        self.cache_w[:] = 1e-8
+
+    def sum_of_seq(self, gamma, epochs):
+        s = 0
+        for i in range(1, epochs):
+            s += gamma ** i
+        return s
+
+
+@torch.no_grad()
+def triangle_weight_max(triangles_weights: torch.Tensor, weights: torch.Tensor, index_tri: torch.Tensor) -> torch.Tensor:
+    """The prune pass's `scatter_max(weights[:, 0], index_tri, out=zeros)` + `torch.maximum`
+    (prune_mesh_after_finetuning.py:354-357), in place on `triangles_weights` (F,)."""
+    lib = _lib.load()
+    dev = triangles_weights.device
+    if triangles_weights.dtype != torch.float32 or not triangles_weights.is_contiguous():
+        raise ValueError("triangles_weights must be a contiguous float32 tensor")
+    w = weights.detach().to(dev, torch.float32)
+    w = (w[:, 0] if w.dim() == 2 else w).contiguous()
+    idx = index_tri.to(dev, torch.int64).contiguous()
+    _lib.check(lib.qf_triangle_weight_max(_lib.ptr(w), 1, _lib.ptr(idx), w.shape[0], triangles_weights.shape[0],
+                                          _lib.ptr(triangles_weights), _lib.stream(dev)), "qf_triangle_weight_max")
+    return triangles_weights
+
+
 class MeshIntersection:
     """mesh_utils.py:180-412.  `mesh_path` may also be a `(vertices, faces)` pair."""
 

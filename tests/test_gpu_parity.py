@@ -706,3 +706,36 @@ def test_full_size_c5_baked_4k(dev):
                               oracle_texture(sc), sc.K)
     assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
     assert maxabs(out["depth"].cpu()[sub], ref["depth"]) <= 2e-3
+
+
+def test_mesh_finetune_and_prune_golden(dev, golden):
+    """f-3: MeshFinetune.update_d / update_faces / reset_d and the prune pass's running per-triangle maximum against the
+    reference classes' outputs (tests/golden/mesh_finetune.npz), then the BVH refit on the moved vertices."""
+    from quadraturefields_b200.mesh_utils import MeshFinetune, RayIntersector, triangle_weight_max, _Mesh
+    g = golden("mesh_finetune")
+    F = g["faces"].shape[0]
+    mf = MeshFinetune(g["verts"], g["faces"], float(g["scaling"]), device=dev)
+    for it in range(2):
+        mf.update_d(T(g[f"d{it}"]).to(dev), T(g[f"w{it}"]).to(dev), T(g[f"idx{it}"]).to(dev))
+    assert np.allclose(mf.cache_d.cpu().numpy(), g["cache_d"], rtol=2e-5, atol=1e-6)       # fp32 atomics: order-dependent
+    assert np.allclose(mf.cache_w.cpu().numpy(), g["cache_w"], rtol=2e-5, atol=1e-8)
+    mf.cache_d.copy_(T(g["cache_d"])); mf.cache_w.copy_(T(g["cache_w"]))
+    mf.update_faces()
+    assert np.abs(mf.vertices - g["verts_after"]).max() <= 2e-7
+    mf.reset_d()
+    assert np.array_equal(mf.cache_w.cpu().numpy(), g["cache_w_reset"]) and float(mf.cache_d.abs().max()) == 0.0
+    mf.update_d(torch.zeros((0, 3), device=dev), torch.zeros(0, device=dev), torch.zeros(0, dtype=torch.int64, device=dev))
+    # prune pass: bit-exact (max does not depend on order)
+    tw = torch.zeros(F, device=dev)
+    for it in range(2):
+        triangle_weight_max(tw, T(g[f"pw{it}"]).to(dev), T(g[f"pidx{it}"]).to(dev))
+    assert np.array_equal(tw.cpu().numpy(), g["tri_w"])
+    # the moved vertices drive the BVH refit and the refit mesh traces like a freshly built one
+    ri = RayIntersector(_Mesh(g["verts"], g["faces"]), max_hits=8, device=dev)
+    ri.update_intersector(mf.vertices_t)
+    fresh = RayIntersector(_Mesh(g["verts_after"], g["faces"]), max_hits=8, device=dev)
+    gen = torch.Generator().manual_seed(2)
+    o = torch.nn.functional.normalize(torch.randn(4096, 3, generator=gen), dim=-1) * 3.0
+    d = torch.nn.functional.normalize(-o + 0.3 * torch.randn(4096, 3, generator=gen), dim=-1)
+    a, b = ri.trace(o.to(dev), d.to(dev)), fresh.trace(o.to(dev), d.to(dev))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and int(a[2].sum()) > 4096

@@ -143,6 +143,25 @@ def test_ngp_golden(golden):
     assert g["rgb"].std() > 0.01 and g["density"].std() > 0.01, "fixture must not be degenerate"
 
 
+def test_mesh_finetune_golden(golden):
+    """f-3: oracle restatement of MeshFinetune / the prune scatter_max against the reference classes executed over the
+    torch_scatter stand-in (oracle/make_golden.py::golden_mesh_finetune)."""
+    g = golden("mesh_finetune")
+    F = g["faces"].shape[0]
+    cd, cw = np.zeros((F, 3), np.float32), np.full(F, 1e-8, np.float32)
+    for it in range(2):
+        cd, cw = O.mesh_finetune_update_d(cd, cw, g[f"d{it}"], g[f"w{it}"], g[f"idx{it}"])
+    assert np.allclose(cd, g["cache_d"], rtol=1e-5, atol=1e-7) and np.allclose(cw, g["cache_w"], rtol=1e-5, atol=1e-9)
+    v = O.mesh_finetune_update_faces(g["verts"], g["faces"], g["cache_d"], g["cache_w"], g["scaling"])
+    assert np.abs(v - g["verts_after"]).max() <= 1e-7
+    assert np.abs(v - g["verts"]).max() > 1e-4                    # the update moved something
+    assert np.abs(v - g["verts"]).max() <= float(g["scaling"]) * (1 + 1e-6)
+    tw = np.zeros(F, np.float32)
+    for it in range(2):
+        tw = O.triangle_weight_max(tw, g[f"pw{it}"][:, 0], g[f"pidx{it}"])
+    assert np.array_equal(tw, g["tri_w"]) and tw.min() == 0.0
+
+
 def test_grid_meta_matches_survey():
     """6 299 960 entries at T=2^19 (levels 0-4 dense), 22 565 520 at T=2^21 (0-5 dense)."""
     m = O.make_grid_meta(log2_hashmap_size=19)
