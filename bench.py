@@ -295,6 +295,7 @@ def run_ours(args):
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = N * world * args.steps / (float(ms_e.item()) * 1e-3)
     train = None if args.no_train else run_train_steps(args, sc, dev, rank, world, barrier)
+    field_train = None if args.no_train else run_field_train_steps(args, sc, dev, rank, world, barrier)
     clk = clocks.stop() if clocks else None
 
     if rank == 0:
@@ -339,6 +340,7 @@ def run_ours(args):
         }
         if train is not None:
             line["train"] = train
+            line["field_train"] = field_train
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rps, detail, sec = cpu_render_sample(args.cpu_sample, threads, args.config)
@@ -350,6 +352,51 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_field_train_steps(args, sc, dev, rank, world, barrier):
+    """BASELINE configs[2] with train_field.py semantics (:313-368): frozen radiance field -> weights / reversed weights at
+    the samples of a 2^18-ray batch (sampler = the quadrature mesh, the occupancy marcher is out of scope) -> quadrature
+    Field forward + field_grad -> field loss -> double backward -> gradient all-reduce -> Adam."""
+    import torch
+    from quadraturefields_b200 import parallel as P
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.utils import train_field_step
+    n = args.train_rays
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    n_views = min(32, len(sc.poses))
+    pool = [sc.rays(v) for v in range(n_views)]
+    O_all, D_all = torch.stack([p[0] for p in pool]), torch.stack([p[1] for p in pool])
+    net = Field(scale=0.5, precision=16, log2_T=19, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=16,
+                num_features=2, back_prop=False, nl="elu").to(dev)                  # train_field.py:238-252 (T reduced to 2^19)
+    params = list(net.parameters())
+    opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15)
+    steps, warm = max(5, min(args.steps, 20)), 3
+    batches = []
+    for i in range(steps + warm):
+        vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
+        pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
+        batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous()))
+    for p_ in params:
+        p_.grad = torch.zeros_like(p_)
+    reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
+    for i in range(warm):
+        train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[i], opt, all_reduce=reduce)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    samples = 0
+    for i in range(steps):
+        samples += train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[warm + i], opt, all_reduce=reduce)[1]
+    e1.record()
+    barrier()
+    ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
+    n_params = sum(p_.numel() for p_ in params)
+    return {"metric": "rays_per_sec_field_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n, "samples_per_ray": samples / (n * steps),
+            "params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+            "includes": "trace + frozen field fwd + weights/reversed weights + Field fwd with field_grad + loss + double backward + "
+                        "grad all-reduce + Adam step"}
 
 
 def run_train_steps(args, sc, dev, rank, world, barrier):
@@ -380,7 +427,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
         rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d)
         loss = torch.nn.functional.smooth_l1_loss(rgb, target)
         loss.backward()
-        P.all_reduce_gradients(params, n)
+        P.all_reduce_gradients(params, n, n * world)
         opt.step()
         return n_hits
 

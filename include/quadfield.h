@@ -228,6 +228,37 @@ int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float
                          int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * (5b) The quadrature `Field` net (field.py:130-259) with back_prop=False (both reference
+ * call sites): out = MLP([x01, grid(x01)]) with a 16-level fp16 hash grid (tcnn.Encoding "Grid"/"Hash") and a
+ * torch fp32 BasicDecoder (2 hidden layers of 16 or 32 units, ELU or ReLU, output_dim <= 3);
+ * field_grad = d(sum out)/dx through the raw-xyz inputs of the MLP only (field.py:196-199, 229-238).
+ * Weights are torch nn.Linear layouts: w1 (H,35), w2 (H,H), w3 (out_dim,H); biases may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+enum { QF_ACT_ELU = 0, QF_ACT_RELU = 1 };
+typedef struct {
+  int32_t hidden;      /* 16 or 32 */
+  int32_t out_dim;     /* 1..3 */
+  int32_t activation;  /* QF_ACT_* */
+  float xyz_min[3];    /* field.py:141-142: -scale, +scale */
+  float xyz_max[3];
+} qf_field_desc;
+/* A grid-only field handle (no NGP MLPs): usable with qf_hashgrid_forward/backward and qf_field_*; free with qf_ngp_destroy,
+ * refresh the table with qf_ngp_update(f, d_table, NULL, NULL, stream). */
+int qf_grid_create(const qf_grid_desc* desc, const float* d_table, int64_t n_entries, void* stream, qf_ngp** out);
+/* Field.forward (field.py:203-221): field (M,out_dim); field_grad (M,3) or NULL (return_grad=False). */
+int qf_field_forward(const qf_ngp* grid, const qf_field_desc* fd, const float* d_w1, const float* d_b1,
+                     const float* d_w2, const float* d_b2, const float* d_w3, const float* d_b3, const float* d_x,
+                     int64_t M, float* d_field, float* d_field_grad, void* stream);
+/* Backward of BOTH outputs (the field_grad part is the reference's double backward through the torch MLP plus the
+ * first-order grid backward).  Upstream gradients may be NULL (= zero); parameter gradients are ACCUMULATED
+ * (d_grad_table (n_entries,2) fp32 may be NULL to skip the grid; bias gradients may be NULL). */
+int qf_field_backward(const qf_ngp* grid, const qf_field_desc* fd, const float* d_w1, const float* d_b1,
+                      const float* d_w2, const float* d_b2, const float* d_w3, const float* d_b3, const float* d_x,
+                      int64_t M, const float* d_grad_field, const float* d_grad_field_grad, float* d_grad_table,
+                      float* d_grad_w1, float* d_grad_b1, float* d_grad_w2, float* d_grad_b2, float* d_grad_w3,
+                      float* d_grad_b3, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * (6) Mesh finetuning accumulators: replace the torch_scatter calls of
  * MeshFinetune (mesh_utils.py:112-156) and of the prune pass (prune_mesh_after_finetuning.py:354-357).
  * ------------------------------------------------------------------------------------------ */

@@ -18,6 +18,10 @@ Parity status:
     accumulators ``MeshFinetune`` / prune ``scatter_max`` (f-3): PINNED the same way
     (``tests/golden/sg_decode.npz``, ``tests/golden/mesh_finetune.npz``; torch_scatter
     is a stand-in with its documented semantics).
+  * the quadrature ``Field`` net (f-2): its torch part (``BasicDecoder``, ``field_grad`` with
+    ``create_graph=True``, ``compute_field_loss`` and the autograd double backward) is PINNED
+    by executing the reference class (``tests/golden/field_net.npz``); its tcnn grid encoder
+    is the stand-in (unpinned, like a5).
   * the arithmetic that lives in absent third-party native code — Embree/OptiX
     ray-mesh intersection, tinycudann hash grid / fully fused MLP / SH, kaolin
     pack scans — is PARITY UNPINNED: it is restated from the published algorithms

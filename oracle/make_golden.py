@@ -283,6 +283,42 @@ def golden_mesh_finetune():
     return out
 
 
+def golden_field_net():
+    """f-2: the reference's quadrature `Field` (train_field.py:238-252 configuration, smaller table) executed over the
+    tinycudann stand-in: forward, field_grad (create_graph), compute_field_loss and loss.backward()."""
+    import field as FM
+    out = {}
+    # small tables keep the fixture small: (a) 3 dense + 13 hashed levels, (b) all levels hashed
+    for tag, hidden, nl, log2_T, min_res in (("a", 16, "elu", 10, 4), ("b", 32, "relu", 11, 16)):
+        torch.manual_seed(21 + hidden)
+        net = FM.Field(scale=0.5, precision=16, log2_T=log2_T, L=16, max_res=512, min_res=min_res, output_dim=1,
+                       hidden_size=hidden, num_features=2, back_prop=False, nl=nl, bias=True, bias_last=True)
+        g = torch.Generator().manual_seed(22)
+        with torch.no_grad():                                 # features large enough to matter next to the xyz inputs
+            net.xyz_encoder.params.copy_(((torch.rand(net.xyz_encoder.params.shape, generator=g) * 2 - 1) * 0.5).half().float())
+        M = 800
+        x = (torch.rand(M, 3, generator=g) - 0.5) * 0.98
+        w, wr = torch.rand(M, generator=g), torch.rand(M, generator=g)
+        dirs = torch.randn(M, 3, generator=g)
+        xin = x.clone().requires_grad_(True)
+        fld, fgrad = net(xin)
+        loss = net.compute_field_loss(w, weights_rev=wr, field_norm=fgrad, view_dirs=dirs)
+        (loss + 0.5 * fld.pow(2).mean()).backward()          # exercise the plain output path too
+        sd = net.state_dict()
+        for k, v in sd.items():
+            out[f"{tag}_p_{k}"] = v
+        for k, p in net.named_parameters():
+            out[f"{tag}_g_{k}"] = p.grad
+        out.update({f"{tag}_x": x, f"{tag}_w": w, f"{tag}_wr": wr, f"{tag}_dirs": dirs, f"{tag}_field": fld, f"{tag}_field_grad": fgrad,
+                    f"{tag}_loss": loss, f"{tag}_hidden": np.int64(hidden), f"{tag}_nl": np.array(nl),
+                    f"{tag}_log2_T": np.int64(log2_T), f"{tag}_min_res": np.int64(min_res)})
+        out[f"{tag}_p_xyz_encoder.params"] = sd["xyz_encoder.params"].half()      # fp16-representable by construction
+        fld2, none = net(x.clone(), return_grad=False)
+        assert none is None
+        out[f"{tag}_field_nograd"] = fld2
+    return out
+
+
 def _np(v):
     if isinstance(v, torch.Tensor):
         return v.detach().cpu().numpy()
@@ -294,7 +330,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
                      ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
-                     ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune)):
+                     ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune),
+                     ("field_net", golden_field_net)):
         data = {k: _np(v) for k, v in fn().items()}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

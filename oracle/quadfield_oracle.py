@@ -991,3 +991,47 @@ def triangle_weight_max(tri_w, weights, index_tri):
     cur = np.zeros_like(np.asarray(tri_w, np.float32))
     np.maximum.at(cur, np.asarray(index_tri, np.int64), np.asarray(weights, np.float32))
     return np.maximum(np.asarray(tri_w, np.float32), cur)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# f-2: the quadrature Field net (field.py:130-259), back_prop=False
+# ---------------------------------------------------------------------------------------------------------------------
+class _HalfBoundary(torch.autograd.Function):
+    """A tensor handed over as `__half`: values AND the gradient coming back are rounded to fp16 (the cast that
+    torch.cat([x, h]) inserts for the half encoder output, field.py:193, rounds the incoming gradient the same way)."""
+
+    @staticmethod
+    def forward(ctx, v):
+        return v.half().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.half().float()
+
+
+def field_net_forward(x, table, meta, w1, b1, w2, b2, w3, b3, xyz_min, xyz_max, activation="elu", return_grad=True):
+    """Field.forward (field.py:203-221): x (M,3) -> field (M,out_dim), field_grad (M,3).  The grid sees x.detach()
+    (field.py:196-199), so field_grad = d(sum field)/dx flows through the raw-xyz inputs of the MLP only; it is built with
+    create_graph=True like the reference, so losses on it back-propagate into every parameter passed with requires_grad.
+    `table` (n_entries,2) fp32 master parameters (rounded to fp16 with a straight-through gradient, tcnn's working copy)."""
+    act = torch.nn.functional.elu if activation == "elu" else torch.relu
+    x = x.detach().clone().requires_grad_(True)
+    lo, hi = torch.as_tensor(xyz_min, dtype=torch.float32), torch.as_tensor(xyz_max, dtype=torch.float32)
+    x01 = (x - lo) / (hi - lo)
+    h = _HalfBoundary.apply(hashgrid_encode(x01.detach(), _round_h(table), meta))     # tcnn emits / receives __half
+    inp = torch.cat([x01, h], dim=1)
+    a1 = act(torch.nn.functional.linear(inp, w1, b1))
+    a2 = act(torch.nn.functional.linear(a1, w2, b2))
+    field = torch.nn.functional.linear(a2, w3, b3)
+    if not return_grad:
+        return field, None
+    grad = torch.autograd.grad(field.flatten(), [x], grad_outputs=torch.ones_like(field.flatten()), create_graph=True,
+                               retain_graph=True)[0]
+    return field, grad
+
+
+def compute_field_loss(weights, weights_rev, field_norm, view_dirs):
+    """Field.compute_field_loss (field.py:253-259)."""
+    view_dirs = view_dirs / torch.norm(view_dirs, dim=1, keepdim=True)
+    loss = torch.abs(torch.maximum(weights.detach(), weights_rev.detach()) - torch.abs(torch.sum(field_norm * view_dirs.detach(), 1)))
+    return loss.mean()

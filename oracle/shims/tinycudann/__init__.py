@@ -65,16 +65,35 @@ class Network(torch.nn.Module):
 
 
 class Encoding(torch.nn.Module):
+    """Two configurations are used by the reference: the SH(4) direction encoding (ngp.py:724-737, no parameters) and
+    the "Grid"/"Hash" position encoding of the quadrature Field net (field.py:158-172; trainable, half output)."""
+
     def __init__(self, n_input_dims, encoding_config, seed=1337, dtype=None):
         super().__init__()
-        nested = encoding_config["nested"]
-        assert encoding_config["otype"] == "Composite" and len(nested) == 1
-        assert nested[0]["otype"] == "SphericalHarmonics" and nested[0]["degree"] == 4
         self.n_input_dims = n_input_dims
+        self.dtype = dtype
+        e = encoding_config
+        if e["otype"] == "Grid":
+            assert e["type"] == "Hash" and e["interpolation"] == "Linear" and e["n_features_per_level"] == 2 and n_input_dims == 3
+            self.kind = "grid"
+            self.meta = O.make_grid_meta(n_levels=e["n_levels"], base_resolution=e["base_resolution"],
+                                         log2_hashmap_size=e["log2_hashmap_size"], per_level_scale=float(e["per_level_scale"]))
+            g = torch.Generator().manual_seed(seed)
+            self.params = torch.nn.Parameter((torch.rand(self.meta.n_entries * 2, generator=g) * 2 - 1) * 1e-4)
+            self.n_output_dims = e["n_levels"] * 2
+            return
+        nested = e["nested"]
+        assert e["otype"] == "Composite" and len(nested) == 1
+        assert nested[0]["otype"] == "SphericalHarmonics" and nested[0]["degree"] == 4
+        self.kind = "sh"
         self.n_output_dims = 16
 
     def forward(self, x):
         x = x.float()
+        if self.kind == "grid":
+            table = O._round_h(self.params.view(-1, 2))           # fp16 working copy of the fp32 master parameters
+            enc = O.hashgrid_encode(x, table, self.meta)
+            return enc.to(self.dtype) if self.dtype is not None else enc.half()
         return O.sh4(x * 2.0 - 1.0).half().float()
 
 

@@ -54,6 +54,9 @@ _SIGS = {
     "qf_texture_decode": (_I, [_P, _P, _L, _P, _P]),
     "qf_texture_compress": (_I, [_P, _L, _I, _I, _F, _P, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "qf_sg_features_to_rgb": (_I, [_P, _L, _I, _P, _L, _P, _P]),
+    "qf_grid_create": (_I, [_P, _P, _L, _P, C.POINTER(_P)]),
+    "qf_field_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "qf_field_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "qf_triangle_accumulate": (_I, [_P, _P, _P, _L, _L, _P, _P, _P]),
     "qf_vertex_displace_workspace_bytes": (C.c_size_t, [_L]),
     "qf_vertex_displace": (_I, [_P, _P, _P, _L, _L, _F, _P, _P, C.c_size_t, _P]),

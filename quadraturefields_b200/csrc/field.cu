@@ -414,6 +414,7 @@ static int launch_fused(FieldArgs& a, int mode, cudaStream_t st) {
 }
 
 int launch_ngp_forward(const qf_ngp* f, FieldArgs& a, int mode, cudaStream_t st) {
+  QF_REQUIRE(f->d_weights, "this field handle holds a grid only (qf_grid_create); the NGP MLPs need qf_ngp_create");
   if (mode == 0 && field_tc_mode() == 1) {
     FieldTcArgs t = {};
     t.pos = a.pos; t.pos_stride = a.pos_stride; t.dirs = a.dirs; t.ray64 = a.ray64; t.ray32 = a.ray32; t.ray32_stride = a.ray32_stride;

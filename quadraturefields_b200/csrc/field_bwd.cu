@@ -114,20 +114,6 @@ __device__ __forceinline__ void store_c(__half* __restrict__ base, int row_len, 
   }
 }
 
-__device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
-                                              float z, float g0, float g1) {
-  if (g0 == 0.f && g1 == 0.f) return;
-  Corner8 c;
-  level_indices(d, l, x, y, z, c);
-  float2* lvl = g_table + d.offset[l];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
-    w *= (k & 4) ? c.fz : 1.f - c.fz;
-    atomicAdd(lvl + c.idx[k], make_float2(w * g0, w * g1));
-  }
-}
-
 // Gradients enter the fp16 tensor-core path scaled by a power of two that brings max|dL/drgb| to [0.5, 1) — what the
 // reference gets from torch GradScaler(2**10) (train_finetune.py) — and are unscaled in fp32 before they are accumulated.
 __device__ __forceinline__ float grad_scale_from(float absmax) {
@@ -461,6 +447,7 @@ extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const 
   if (M == 0) return QF_OK;
   QF_REQUIRE(f && d_positions && d_directions && d_grad_rgb && d_grad_table && d_grad_base_w && d_grad_head_w && d_workspace,
              "qf_ngp_backward: NULL argument");
+  QF_REQUIRE(f->d_weights, "qf_ngp_backward: this field handle holds a grid only (qf_grid_create)");
   QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)d_workspace;

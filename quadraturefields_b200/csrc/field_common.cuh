@@ -87,6 +87,20 @@ __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half
     if (two) store(l + 1, level_blend(c1, v1));
   }
 }
+// backward of one level: scatter the gradient of its two features to the 8 corners (fp32 atomics)
+__device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
+                                              float z, float g0, float g1) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  Corner8 c;
+  level_indices(d, l, x, y, z, c);
+  float2* lvl = g_table + d.offset[l];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
+    w *= (k & 4) ? c.fz : 1.f - c.fz;
+    atomicAdd(lvl + c.idx[k], make_float2(w * g0, w * g1));
+  }
+}
 
 __device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
   float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;

@@ -211,6 +211,50 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
     return rgb, opacity, depth_img, points.shape[0]
 
 
+def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs):
+    """The no-grad half of a quadrature-field training step (train_field.py:313-344): sample positions along the rays,
+    the frozen radiance field's near-to-far and far-to-near weights at them (`rendering_field`, utils.py:431-446) and the
+    normalised positions.  The reference takes its samples from nerfacc's occupancy-grid marcher (out
+    of scope); here the sampler is the quadrature mesh: one interval of width render_step_size centred on every hit.
+    -> (positions - 0.5 (M,3), dirs (M,3), weights (M,), weights_rev (M,)) or None when nothing is hit."""
+    from .field_rendering import rendering_field
+    with torch.no_grad():
+        tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
+        if tup is None:
+            return None
+        points, _, index_ray, depth, _, _, _ = tup
+        dev = points.device
+        vd = _lib.f32(viewdirs, dev)
+        half = 0.5 * float(mesh_intersect.render_step_size)
+        t_starts, t_ends = depth - half, depth + half
+
+        def rgb_sigma_fn(ts, te, ray_indices):
+            rgbs, sigmas = radiance_field(points, vd, ray_indices=ray_indices)
+            return rgbs, sigmas.squeeze(-1)
+
+        _, _, _, weights, weights_rev = rendering_field(t_starts, t_ends, index_ray, n_rays=origins.shape[0], rgb_sigma_fn=rgb_sigma_fn)
+        _, positions = radiance_field.normalize(points)                    # train_field.py:344
+        return positions - 0.5, vd[index_ray], weights, weights_rev
+
+
+def train_field_step(field_net, radiance_field, mesh_intersect, origins, viewdirs, optimizer, all_reduce=None):
+    """One optimiser step of the quadrature field (train_field.py:345-368): Field forward + analytic field_grad ->
+    compute_field_loss -> backward (double backward through the MLP, first-order grid backward) -> optional gradient
+    all-reduce -> optimizer.step().  -> (loss tensor, number of samples)."""
+    batch = field_training_batch(mesh_intersect, radiance_field, origins, viewdirs)
+    if batch is None:
+        return None, 0
+    positions, dirs, weights, weights_rev = batch
+    _, field_grad = field_net(positions)
+    loss = field_net.compute_field_loss(weights, weights_rev=weights_rev, field_norm=field_grad, view_dirs=dirs)
+    optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    if all_reduce is not None:
+        all_reduce()
+    optimizer.step()
+    return loss.detach(), positions.shape[0]
+
+
 def _flatten_rays(rays: Rays):
     rays_shape = rays.origins.shape
     if len(rays_shape) == 3:

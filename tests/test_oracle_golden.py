@@ -1,6 +1,7 @@
 """Pin oracle/quadfield_oracle.py against fixtures produced from the unmodified reference
 (oracle/make_golden.py) and against the reference's docstring known-answer vectors."""
 import numpy as np
+import pytest
 import torch
 
 from oracle import quadfield_oracle as O
@@ -160,6 +161,36 @@ def test_mesh_finetune_golden(golden):
     for it in range(2):
         tw = O.triangle_weight_max(tw, g[f"pw{it}"][:, 0], g[f"pidx{it}"])
     assert np.array_equal(tw, g["tri_w"]) and tw.min() == 0.0
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_field_net_golden(golden, tag):
+    """f-2: oracle restatement of the quadrature Field net (forward, field_grad with create_graph, compute_field_loss,
+    parameter gradients incl. the double backward) against the reference `Field` executed over the tinycudann stand-in."""
+    g = golden("field_net")
+    P = lambda k: torch.from_numpy(np.asarray(g[f"{tag}_p_{k}"], dtype=np.float32)).requires_grad_(True)
+    meta = O.make_grid_meta(n_levels=16, base_resolution=int(g[f"{tag}_min_res"]), log2_hashmap_size=int(g[f"{tag}_log2_T"]),
+                            per_level_scale=float(np.exp(np.log(512 * 0.5 / int(g[f"{tag}_min_res"])) / 15)))
+    table = P("xyz_encoder.params")
+    tab2 = table.view(-1, 2)
+    ws = [P("decoder_field.layers.0.weight"), P("decoder_field.layers.0.bias"), P("decoder_field.layers.1.weight"),
+          P("decoder_field.layers.1.bias"), P("decoder_field.lout.weight"), P("decoder_field.lout.bias")]
+    fld, fgrad = O.field_net_forward(torch.from_numpy(g[f"{tag}_x"]), tab2, meta, *ws, g[f"{tag}_p_xyz_min"][0], g[f"{tag}_p_xyz_max"][0],
+                                     activation=str(g[f"{tag}_nl"]))
+    assert np.abs(fld.detach().numpy() - g[f"{tag}_field"]).max() <= 1e-6
+    assert np.abs(fgrad.detach().numpy() - g[f"{tag}_field_grad"]).max() <= 1e-5
+    loss = O.compute_field_loss(torch.from_numpy(g[f"{tag}_w"]), torch.from_numpy(g[f"{tag}_wr"]), fgrad, torch.from_numpy(g[f"{tag}_dirs"]))
+    assert abs(float(loss) - float(g[f"{tag}_loss"])) <= 1e-6
+    (loss + 0.5 * fld.pow(2).mean()).backward()
+    names = ["decoder_field.layers.0.weight", "decoder_field.layers.0.bias", "decoder_field.layers.1.weight",
+             "decoder_field.layers.1.bias", "decoder_field.lout.weight", "decoder_field.lout.bias"]
+    for n, w in zip(names, ws):
+        ref = g[f"{tag}_g_{n}"]
+        assert np.abs(w.grad.numpy() - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), n
+    gt = g[f"{tag}_g_xyz_encoder.params"]
+    assert np.abs(gt).max() > 1e-6                                         # the grid really receives a gradient
+    assert np.abs(table.grad.numpy() - gt).max() <= 1e-5 * np.abs(gt).max()
+    assert np.abs(g[f"{tag}_field_nograd"] - g[f"{tag}_field"]).max() == 0.0
 
 
 def test_grid_meta_matches_survey():
