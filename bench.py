@@ -172,6 +172,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from quadraturefields_b200.parallel import bind_to_gpu_numa
+        bind_to_gpu_numa(local)                      # host buffers of the e2e leg land on the GPU's NUMA node
         dist.init_process_group("nccl", device_id=dev)
     entry.build()
     from quadraturefields_b200 import _lib, scene as S

@@ -553,9 +553,11 @@ extern "C" size_t qf_trace_workspace_bytes(int64_t n_rays) { return 256 + sizeof
 extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
                                int32_t* d_tri, float* d_t, int32_t* d_count, int32_t* d_total, void* d_workspace,
                                size_t workspace_bytes, void* stream) {
-  QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count, "qf_trace_firstk: NULL argument");
+  QF_REQUIRE(m, "qf_trace_firstk: NULL mesh");
   QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_trace_firstk: K=%d outside [1,%d]", K, QF_MAX_HITS);
-  if (n_rays == 0) return QF_OK;
+  QF_REQUIRE(n_rays >= 0, "qf_trace_firstk: n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) return QF_OK;   // empty tensors carry NULL data pointers
+  QF_REQUIRE(d_origins && d_dirs && d_tri && d_count, "qf_trace_firstk: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   int blocks = (int)ceil_div(n_rays, 128);
   // caller scratch: [slot: 4 ints | compacted ray ids]; without it the list always takes the thread-per-ray kernel
@@ -593,9 +595,14 @@ extern "C" size_t qf_scan_workspace_bytes(int64_t n) {
 
 extern "C" int qf_hits_offsets(const int32_t* d_count, int64_t n_rays, int64_t* d_offsets, void* d_workspace,
                                size_t workspace_bytes, void* stream) {
-  QF_REQUIRE(d_count && d_offsets && d_workspace, "qf_hits_offsets: NULL argument");
-  QF_REQUIRE(workspace_bytes >= qf_scan_workspace_bytes(n_rays), "qf_hits_offsets: workspace too small");
+  QF_REQUIRE(n_rays >= 0 && d_offsets, "qf_hits_offsets: NULL offsets / negative size");
   cudaStream_t st = (cudaStream_t)stream;
+  if (n_rays == 0) {   // empty count tensor (NULL pointer): offsets = [0]
+    QF_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(int64_t), st));
+    return QF_OK;
+  }
+  QF_REQUIRE(d_count && d_workspace, "qf_hits_offsets: NULL argument");
+  QF_REQUIRE(workspace_bytes >= qf_scan_workspace_bytes(n_rays), "qf_hits_offsets: workspace too small");
   int64_t* wide = (int64_t*)d_workspace;
   size_t wide_bytes = (sizeof(int64_t) * (size_t)(n_rays + 1) + 255) / 256 * 256;
   void* tmp = (char*)d_workspace + wide_bytes;
@@ -618,10 +625,10 @@ extern "C" int qf_hits_pack(const qf_mesh* m, const float* d_origins, const floa
                             const int32_t* d_tri, const int32_t* d_count, const int64_t* d_offsets, float* d_points,
                             float* d_vectors, int64_t* d_index_ray, float* d_depth, int64_t* d_index_tri,
                             float* d_origins_out, void* stream) {
-  QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count && d_offsets, "qf_hits_pack: NULL input");
-  QF_REQUIRE(d_points && d_vectors && d_index_ray && d_depth && d_index_tri && d_origins_out, "qf_hits_pack: NULL output");
   QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_hits_pack: K=%d outside [1,%d]", K, QF_MAX_HITS);
   if (n_rays == 0) return QF_OK;
+  QF_REQUIRE(m && d_origins && d_dirs && d_tri && d_count && d_offsets, "qf_hits_pack: NULL input");
+  QF_REQUIRE(d_points && d_vectors && d_index_ray && d_depth && d_index_tri && d_origins_out, "qf_hits_pack: NULL output");
   hits_pack_kernel<<<(int)ceil_div(n_rays, 128), 128, 0, (cudaStream_t)stream>>>(
       m->d_planes, d_origins, d_dirs, n_rays, K, d_tri, d_count, d_offsets, d_points, d_vectors, d_index_ray, d_depth,
       d_index_tri, d_origins_out);
@@ -631,8 +638,8 @@ extern "C" int qf_hits_pack(const qf_mesh* m, const float* d_origins, const floa
 
 extern "C" int qf_hits_resort(const int64_t* d_index_ray, const float* d_depth, int64_t n_hits, int64_t* d_perm,
                               uint8_t* d_boundary, void* stream) {
-  QF_REQUIRE(d_index_ray && d_depth && d_perm && d_boundary, "qf_hits_resort: NULL argument");
   if (n_hits == 0) return QF_OK;
+  QF_REQUIRE(d_index_ray && d_depth && d_perm && d_boundary, "qf_hits_resort: NULL argument");
   hits_resort_kernel<<<(int)ceil_div(n_hits, 256), 256, 0, (cudaStream_t)stream>>>(d_index_ray, d_depth, n_hits, d_perm, d_boundary);
   QF_LAUNCH_CHECK();
   return QF_OK;

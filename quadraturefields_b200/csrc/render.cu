@@ -222,7 +222,13 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
                          const float* d_origins, const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta, int bg_mode,
                          const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total,
                          void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
-  QF_REQUIRE(mesh && d_origins && d_viewdirs && d_rgb && d_alpha && d_depth && d_workspace, "qf_render: NULL argument");
+  QF_REQUIRE(mesh, "qf_render: NULL mesh");
+  QF_REQUIRE(n_rays >= 0, "qf_render: n_rays=%lld", (long long)n_rays);
+  if (n_rays == 0) {   // empty tensors carry NULL data pointers
+    if (d_hits_total) QF_CUDA_CHECK(cudaMemsetAsync(d_hits_total, 0, sizeof(int32_t), st));
+    return QF_OK;
+  }
+  QF_REQUIRE(d_origins && d_viewdirs && d_rgb && d_alpha && d_depth && d_workspace, "qf_render: NULL argument");
   QF_REQUIRE(K >= 1 && K <= QF_MAX_HITS, "qf_render: K=%d outside [1,%d]", K, QF_MAX_HITS);
   QF_REQUIRE(bg_mode >= 0 && bg_mode <= 2, "qf_render: bg_mode=%d", bg_mode);
   QF_REQUIRE(bg_mode != QF_BG_RANDOM || d_bkgd, "qf_render: bg 'random' needs render_bkgd");

@@ -12,6 +12,32 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[List[int]]:
+    """Pin this process to the CPUs NVML reports as local to the GPU, so the pinned host buffers of the end-to-end path are
+    first-touched on the GPU's NUMA node (8 ranks streaming rays in and images out otherwise cross the socket link).
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber devices: go through the UUID
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [w * 64 + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def world() -> Tuple[int, int]:
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()

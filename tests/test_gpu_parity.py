@@ -802,3 +802,46 @@ def test_train_field_step_learns(dev):
         losses.append(float(loss))
     assert n == pos.shape[0] and abs(losses[0] - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
     assert losses[-1] < 0.9 * losses[0], losses[::6]
+
+
+def test_trace_and_render_edge_cases(dev, smoke_scene):
+    """Empty ray sets, frames that miss the mesh, degenerate / duplicated triangles and non-finite rays."""
+    from quadraturefields_b200.mesh_utils import RayIntersector, _Mesh
+    sc = smoke_scene
+    ri = sc.mesh_intersect.rayintersector
+    # (1) zero rays
+    e = torch.zeros((0, 3), device=dev)
+    tri, t, count = ri.trace(e, e, 8)
+    assert tri.shape == (0, 8) and t.shape == (0, 8) and count.shape == (0,)
+    out = sc.render(e, e)
+    assert out["rgb"].shape == (0, 3) and int(out["n_hits"]) == 0
+    assert sc.mesh_intersect.sampling_raytrace(e, e) is None and ri.trace_tuple(e, e)[0].shape == (0, 3)
+    # (2) a frame looking away from the mesh: background everywhere, None from the tuple API (quirk Q9)
+    o = torch.tensor([[0.0, 0.0, 5.0]], device=dev).repeat(4096, 1)
+    d = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 1.0]], device=dev) + 0.1 * torch.rand(4096, 3, device=dev), dim=-1)
+    for bg, fill in (("white", 1.0), ("black", 0.0)):
+        out = sc.render(o, d, bg_color=bg)
+        assert int(out["n_hits"]) == 0 and float(out["opacity"].abs().max()) == 0.0
+        assert float((out["rgb"] - fill).abs().max()) == 0.0
+    assert sc.mesh_intersect.sampling_raytrace(d, o) is None
+    # (3) degenerate triangles (zero area, repeated vertex), an exact duplicate, and non-finite rays: same hit set as the oracle
+    rng = np.random.RandomState(7)
+    verts, faces = O.shell_mesh([0.6, 1.0], subdivisions=1, jitter=1e-3, seed=5)
+    nv = verts.shape[0]
+    verts = np.concatenate([verts, np.array([[0.2, 0.2, 0.2], [0.4, 0.4, 0.4], [0.6, 0.6, 0.6]], np.float32)])
+    faces = np.concatenate([faces, np.array([[nv, nv + 1, nv + 2],            # collinear
+                                             [nv, nv, nv + 1],                # repeated vertex
+                                             faces[3], faces[3]], faces.dtype)])   # two exact duplicates of face 3
+    origins = rng.uniform(-1.5, 1.5, size=(3000, 3)).astype(np.float32)
+    dirs = rng.normal(size=(3000, 3)).astype(np.float32)
+    dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dirs[0] = np.nan; dirs[1, 0] = np.inf; origins[2] = np.nan; dirs[3] = 0.0; origins[4, 1] = np.inf
+    with np.errstate(all="ignore"):
+        tri_ref, t_ref, count_ref, total_ref = O.intersect_firstk(origins, dirs, verts, faces, 6)
+    r2 = RayIntersector(_Mesh(verts, faces), max_hits=6, device=dev)
+    tri, t, count, total = r2.trace(T(origins).to(dev), T(dirs).to(dev), 6, with_total=True)
+    assert np.array_equal(count.cpu().numpy(), count_ref) and np.array_equal(total.cpu().numpy(), total_ref)
+    assert np.array_equal(tri.cpu().numpy(), tri_ref) and np.array_equal(t.cpu().numpy(), t_ref)
+    assert count_ref[:5].sum() == 0 and count_ref.max() >= 4
+    dup = (tri_ref == faces.shape[0] - 1).any(axis=1).sum()
+    assert dup > 0                                            # the duplicated face is reported once per copy, id order on equal t
