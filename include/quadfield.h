@@ -138,6 +138,15 @@ size_t qf_ngp_backward_workspace_bytes(int64_t M);
 int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const float* d_directions, const int64_t* d_ray_index,
                     int64_t M, const float* d_grad_rgb, const float* d_grad_density, float* d_grad_table,
                     float* d_grad_base_w, float* d_grad_head_w, void* d_workspace, size_t workspace_bytes, void* stream);
+/* The same, plus dL/dpositions (M,3) — tinycudann's grid input gradient, which the finetune step relies on when the
+ * deformation field moves the quadrature points (utils.py:566-583: points = xyzs + dh feed radiance_field). The
+ * gradient flows through the trilinear weights of the hash grid and the 1/(aabb_max-aabb_min) normalisation
+ * (ngp.py:761-763); directions get no gradient. d_grad_positions may be NULL. */
+int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions, const float* d_directions,
+                           const int64_t* d_ray_index, int64_t M, const float* d_grad_rgb,
+                           const float* d_grad_density, float* d_grad_table, float* d_grad_base_w,
+                           float* d_grad_head_w, float* d_grad_positions, void* d_workspace, size_t workspace_bytes,
+                           void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (4) Baked spherical-Gaussian texture path.

@@ -319,6 +319,81 @@ def golden_field_net():
     return out
 
 
+def golden_finetune_step():
+    """f-3 end to end: the reference's `render_image_finetune_with_occgrid` (utils.py:465-607) in TRAINING mode —
+    deformation field on the quadrature points and on random points of their triangles, re-sort, radiance field at the
+    moved points, derive_properties, regulariser, MeshFinetune.update_d — followed by loss.backward(), with the
+    reference Field / NGPRadianceField / MeshFinetune / MeshIntersection classes over the stand-ins."""
+    import field as FM
+    import mesh_utils as MU
+    import radiance_fields.ngp as NGP
+    import trimesh
+    import utils as U
+    from datasets.utils import Rays
+    from oracle import quadfield_oracle as O
+    verts, faces = O.shell_mesh([0.5, 0.8, 1.0], subdivisions=2, jitter=1e-3, seed=3)
+    f, cx, cy, W, H = O.pinhole_intrinsics(20, 20, 0.6911)
+    origins, viewdirs = O.generate_rays(O.look_at_c2w((2.4, 1.9, 1.3)), W, H, f, cx, cy)
+    K, step, scaling = 6, 0.005, 1.0 / 128
+    mesh = trimesh.Trimesh(vertices=verts, faces=faces, process=False)
+
+    class FakeIntersector:
+        def intersects_id(self, o, v, multiple_hits=True, return_locations=True, max_hits=10):
+            return O.intersects_id(o, v, verts, faces, max_hits)
+
+    mi = object.__new__(MU.MeshIntersection)
+    mi.mesh, mi.num_intersections, mi.render_step_size = mesh, K, step
+    mi.rayintersector = FakeIntersector()
+    mi.vertices = torch.from_numpy(verts.astype(np.float32))
+    points, vectors, index_ray, depth, index_tri, _, org = mi.sampling_raytrace_numpy(viewdirs, origins)
+    data = tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in
+                 (points.astype(np.float32), vectors.astype(np.float32), index_ray, depth.astype(np.float32), index_tri,
+                  org.astype(np.float32)))
+    log2_T = 12
+    p = O.make_ngp_params(seed=42, log2_hashmap_size=log2_T, table_scale=1e4)
+    p.base_w[1][0] = (p.base_w[1][0].abs() * 8.0).half().float()          # opacity spans (0,1), colours vary (scene.py)
+    p.head_w[2][:3] = (p.head_w[2][:3] * 4.0).half().float()
+    rf = NGP.NGPRadianceField(aabb=p.aabb.tolist(), log2_hashmap_size=log2_T)
+    with torch.no_grad():
+        rf.mlp_base.params.copy_(torch.cat([w.flatten() for w in p.base_w] + [p.table.flatten()]))
+        rf.mlp_head.params.copy_(torch.cat([w.flatten() for w in p.head_w]))
+    rf_base0, rf_head0 = rf.mlp_base.params.detach().clone(), rf.mlp_head.params.detach().clone()
+    torch.manual_seed(31)
+    net = FM.Field(scale=1.5, precision=16, log2_T=10, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=32,
+                   num_features=2, back_prop=False, nl="relu")                         # train_finetune.py:387-399
+    g = torch.Generator().manual_seed(32)
+    with torch.no_grad():
+        net.xyz_encoder.params.copy_(((torch.rand(net.xyz_encoder.params.shape, generator=g) * 2 - 1) * 0.5).half().float())
+    mf = MU.MeshFinetune(verts.copy(), faces.astype(np.int64), scaling)
+    rays = Rays(origins=torch.from_numpy(origins), viewdirs=torch.from_numpy(viewdirs))
+    pixels = torch.rand(origins.shape[0], 3, generator=g)
+    M = data[0].shape[0]
+    torch.manual_seed(33)
+    bary = torch.rand((M, 3))
+    torch.manual_seed(33)                                     # the function's first RNG call draws the same numbers
+    prev = O.ROUND_HIDDEN
+    O.ROUND_HIDDEN = True                                     # tcnn precision: fp16 hidden activations
+    try:
+        rgb, opacity, depth_img, n, weights, positions, index_ray_s, loss_reg, index_tri_o = U.render_image_finetune_with_occgrid(
+            rf, net, None, rays, data, render_step_size=step, render_bkgd=None, mesh_intersect=mi, mesh_finetune=mf,
+            scaling=scaling, bg_color="white")
+        loss = torch.nn.functional.smooth_l1_loss(rgb.squeeze(), pixels) + loss_reg
+        loss.sum().backward()
+    finally:
+        O.ROUND_HIDDEN = prev
+    out = dict(verts=verts, faces=faces, origins=origins, viewdirs=viewdirs, K=np.int64(K), step=np.float32(step),
+               scaling=np.float32(scaling), log2_T=np.int64(log2_T), pixels=pixels, bary=bary,
+               data_xyzs=data[0], data_dirs=data[1], data_index_ray=data[2], data_ts=data[3], data_index_tri=data[4], data_origins=data[5],
+               rgb=rgb, opacity=opacity, depth=depth_img, n=np.int64(n), weights=weights, positions=positions,
+               index_ray=index_ray_s, loss_reg=loss_reg, index_tri=index_tri_o, cache_d=mf.cache_d, cache_w=mf.cache_w,
+               g_base=rf.mlp_base.params.grad, g_head=rf.mlp_head.params.grad, rf_base=rf_base0.half(), rf_head=rf_head0.half())
+    for k, v in net.state_dict().items():
+        out[f"p_{k}"] = v.half() if k == "xyz_encoder.params" else v
+    for k, v in net.named_parameters():
+        out[f"g_{k}"] = v.grad
+    return out
+
+
 def _np(v):
     if isinstance(v, torch.Tensor):
         return v.detach().cpu().numpy()
@@ -331,7 +406,7 @@ def main():
     for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
                      ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
                      ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune),
-                     ("field_net", golden_field_net)):
+                     ("field_net", golden_field_net), ("finetune_step", golden_finetune_step)):
         data = {k: _np(v) for k, v in fn().items()}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

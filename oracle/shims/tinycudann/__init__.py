@@ -4,7 +4,8 @@
 (HashGrid + FullyFusedMLP) restated on CPU through `oracle.quadfield_oracle`.  Parameters live in ONE
 flat fp32 tensor `params`, MLP weights first then the grid table, each matrix (out,in) row-major —
 tcnn's layout as recalled (SURVEY §5 checkpoint row).  Values are cast to fp16 each forward like tcnn;
-unlike tcnn the MLP *output* is returned un-rounded in fp32.
+unlike tcnn the MLP *output* is returned un-rounded in fp32.  The stand-ins are differentiable
+(parameters and inputs), with straight-through gradients at the fp16 roundings.
 """
 import math
 
@@ -41,12 +42,12 @@ class _MLP:
     def split(self, flat):
         ws, off = [], 0
         for o, i in self.shapes:
-            ws.append(flat[off:off + o * i].view(o, i).half().float())
+            ws.append(O._round_h(flat[off:off + o * i].view(o, i)))       # fp16 working copy, straight-through gradient
             off += o * i
         return ws
 
     def forward(self, x, flat):
-        x = x.half().float()
+        x = O._round_h(x)
         if self.in_pad != self.n_in:
             pad = torch.full((x.shape[0], self.in_pad - self.n_in), O.HEAD_PAD_VALUE, dtype=torch.float32)
             x = torch.cat([x, pad], dim=-1)
@@ -61,7 +62,7 @@ class Network(torch.nn.Module):
         self.params = torch.nn.Parameter(self._mlp.init(torch.Generator().manual_seed(seed)))
 
     def forward(self, x):
-        return self._mlp.forward(x.float(), self.params.detach())
+        return self._mlp.forward(x.float(), self.params)
 
 
 class Encoding(torch.nn.Module):
@@ -112,7 +113,7 @@ class NetworkWithInputEncoding(torch.nn.Module):
         self.n_input_dims, self.n_output_dims = n_input_dims, n_output_dims
 
     def forward(self, x):
-        p = self.params.detach()
-        table = p[self._mlp.n_params:].view(-1, 2).half().float()
+        p = self.params
+        table = O._round_h(p[self._mlp.n_params:].view(-1, 2))
         enc = O.hashgrid_encode(x.float(), table, self.meta)
         return self._mlp.forward(enc, p[:self._mlp.n_params])

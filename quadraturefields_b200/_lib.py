@@ -49,6 +49,7 @@ _SIGS = {
     "qf_ngp_forward": (_I, [_P, _P, _P, _P, _L, _P, _P, _P]),
     "qf_ngp_backward_workspace_bytes": (_SZ, [_L]),
     "qf_ngp_backward": (_I, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_ngp_backward_inputs": (_I, [_P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_texture_create": (_I, [_I, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _I, _F, _P, C.POINTER(_P)]),
     "qf_texture_destroy": (None, [_P]),
     "qf_texture_decode": (_I, [_P, _P, _L, _P, _P]),

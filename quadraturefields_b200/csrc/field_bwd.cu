@@ -57,6 +57,8 @@ struct BwdArgs {
   float2* g_table;          // (n_entries) float2, atomically accumulated
   __half* act;              // (M, kActRow)
   __half* grd;              // (M, kGrdRow)
+  float* g_pos;             // (M,3) dL/dposition or NULL
+  float inv_ext[3];         // 1 / (aabb_max - aabb_min)
 };
 
 __device__ __forceinline__ unsigned relu_mask8(float (*acc)[4]) {
@@ -295,11 +297,34 @@ __global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
       layer<4, 4>(ge, af, s_wt + kT1, kS64, g, t);
       const float* xl = sx + (mt * 16 + g) * 3;
       const float* xh = xl + 24;
+      if (a.g_pos == nullptr) {
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int l = n * 4 + t;   // accumulator columns n*8 + 2t, +1 are the two features of level n*4 + t
-        if (r_lo < M) scatter_level(a.desc, a.g_table, l, xl[0], xl[1], xl[2], ge[n][0] * ginv, ge[n][1] * ginv);
-        if (r_hi < M) scatter_level(a.desc, a.g_table, l, xh[0], xh[1], xh[2], ge[n][2] * ginv, ge[n][3] * ginv);
+        for (int n = 0; n < 4; ++n) {
+          const int l = n * 4 + t;   // accumulator columns n*8 + 2t, +1 are the two features of level n*4 + t
+          if (r_lo < M) scatter_level(a.desc, a.g_table, l, xl[0], xl[1], xl[2], ge[n][0] * ginv, ge[n][1] * ginv);
+          if (r_hi < M) scatter_level(a.desc, a.g_table, l, xh[0], xh[1], xh[2], ge[n][2] * ginv, ge[n][3] * ginv);
+        }
+      } else {
+        // also dL/dposition (tcnn input gradient): each lane sums its 4 levels, the 4 lanes of a row are reduced
+        float gp_lo[3] = {0.f, 0.f, 0.f}, gp_hi[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int n = 0; n < 4; ++n) {
+          const int l = n * 4 + t;
+          if (r_lo < M) scatter_level_pos(a.desc, a.g_table, a.table, l, xl[0], xl[1], xl[2], ge[n][0] * ginv, ge[n][1] * ginv, gp_lo);
+          if (r_hi < M) scatter_level_pos(a.desc, a.g_table, a.table, l, xh[0], xh[1], xh[2], ge[n][2] * ginv, ge[n][3] * ginv, gp_hi);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          gp_lo[c] += __shfl_xor_sync(0xffffffffu, gp_lo[c], 1); gp_lo[c] += __shfl_xor_sync(0xffffffffu, gp_lo[c], 2);
+          gp_hi[c] += __shfl_xor_sync(0xffffffffu, gp_hi[c], 1); gp_hi[c] += __shfl_xor_sync(0xffffffffu, gp_hi[c], 2);
+        }
+        if (t == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (r_lo < M) a.g_pos[3 * r_lo + c] = gp_lo[c] * a.inv_ext[c];
+            if (r_hi < M) a.g_pos[3 * r_hi + c] = gp_hi[c] * a.inv_ext[c];
+          }
+        }
       }
     }
     __syncwarp();
@@ -444,6 +469,15 @@ extern "C" size_t qf_ngp_backward_workspace_bytes(int64_t M) {
 extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const float* d_directions, const int64_t* d_ray_index,
                                int64_t M, const float* d_grad_rgb, const float* d_grad_density, float* d_grad_table,
                                float* d_grad_base_w, float* d_grad_head_w, void* d_workspace, size_t workspace_bytes, void* stream) {
+  return qf_ngp_backward_inputs(f, d_positions, d_directions, d_ray_index, M, d_grad_rgb, d_grad_density, d_grad_table,
+                                d_grad_base_w, d_grad_head_w, nullptr, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions, const float* d_directions,
+                                      const int64_t* d_ray_index, int64_t M, const float* d_grad_rgb,
+                                      const float* d_grad_density, float* d_grad_table, float* d_grad_base_w,
+                                      float* d_grad_head_w, float* d_grad_positions, void* d_workspace, size_t workspace_bytes,
+                                      void* stream) {
   if (M == 0) return QF_OK;
   QF_REQUIRE(f && d_positions && d_directions && d_grad_rgb && d_grad_table && d_grad_base_w && d_grad_head_w && d_workspace,
              "qf_ngp_backward: NULL argument");
@@ -465,6 +499,8 @@ extern "C" int qf_ngp_backward(const qf_ngp* f, const float* d_positions, const 
   a.pos = d_positions; a.pos_stride = 3; a.dirs = d_directions; a.ray64 = d_ray_index; a.M = M;
   a.g_rgb = d_grad_rgb; a.g_sigma = d_grad_density; a.g_absmax = gmax; a.g_table = reinterpret_cast<float2*>(d_grad_table);
   a.act = act; a.grd = grd;
+  a.g_pos = d_grad_positions;
+  for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
   static bool attr_set = false;
   if (!attr_set) {
     QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));

@@ -102,6 +102,32 @@ __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __r
   }
 }
 
+// scatter_level plus the gradient with respect to the normalised position (tcnn's grid input gradient): with
+// enc_f = sum_k w_k v_k[f] and w_k the trilinear weight, d enc_f / d x = scale * sum_k (+-1)(w_y w_z)_k v_k[f], etc.
+__device__ __forceinline__ void scatter_level_pos(const qf_grid_desc& d, float2* __restrict__ g_table,
+                                                  const __half2* __restrict__ table, int l, float x, float y, float z, float g0,
+                                                  float g1, float* gx) {
+  if (g0 == 0.f && g1 == 0.f) return;
+  Corner8 c;
+  level_indices(d, l, x, y, z, c);
+  float2* lvl = g_table + d.offset[l];
+  const __half2* tl = table + d.offset[l];
+  float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float wx = (k & 1) ? c.fx : 1.f - c.fx, wy = (k & 2) ? c.fy : 1.f - c.fy, wz = (k & 4) ? c.fz : 1.f - c.fz;
+    const float w = (wx * wy) * wz;
+    atomicAdd(lvl + c.idx[k], make_float2(w * g0, w * g1));
+    const float2 v = __half22float2(__ldg(tl + c.idx[k]));
+    const float gv = g0 * v.x + g1 * v.y;
+    ax += ((k & 1) ? gv : -gv) * (wy * wz);
+    ay += ((k & 2) ? gv : -gv) * (wx * wz);
+    az += ((k & 4) ? gv : -gv) * (wx * wy);
+  }
+  const float sc = d.scale[l];
+  gx[0] += sc * ax; gx[1] += sc * ay; gx[2] += sc * az;
+}
+
 __device__ __forceinline__ void sh4(float x, float y, float z, float* o) {
   float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
   o[0] = 0.28209479177387814f;

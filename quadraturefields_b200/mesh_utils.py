@@ -278,13 +278,23 @@ class MeshIntersection:
         return (points.cpu().numpy(), vecs.cpu().numpy(), index_ray.cpu().numpy(), depth.cpu().numpy(),
                 index_tri.cpu().numpy(), 0, org.cpu().numpy())
 
-    @torch.no_grad()
     def sampling_indexing(self, points, origins, vectors, index_ray, depth, index_tri, random=0):
-        """mesh_utils.py:389-412: per-ray re-sort by depth, pack boundaries, constant deltas — all on the device."""
-        lib = _lib.load()
+        """mesh_utils.py:389-412: per-ray re-sort by depth, pack boundaries, constant deltas — all on the device.  The
+        permutation is found without gradient; the gathers that apply it are differentiable like the reference's
+        `points[new_indices]` (the finetune step back-propagates through the re-sorted points)."""
         dev = self.device
         index_ray = _lib.i64(index_ray.to(dev))
-        depth = _lib.f32(depth, dev)
+        depth_in = depth.to(dev, torch.float32)
+        with torch.no_grad():
+            perm, boundary = self._resort(index_ray, _lib.f32(depth_in.detach(), dev))
+        g = lambda t: t.to(dev)[perm]
+        depth = depth_in[perm]
+        deltas = self.find_deltas(boundary, depth)
+        return g(points), deltas, boundary, g(vectors), index_ray[perm], depth, g(index_tri), g(origins)
+
+    def _resort(self, index_ray, depth):
+        lib = _lib.load()
+        dev = self.device
         M = index_ray.shape[0]
         if M > 1 and bool((index_ray[1:] < index_ray[:-1]).any()):
             # arbitrary order: full lexsort((depth, index_ray)) with device sorts (stable)
@@ -298,7 +308,5 @@ class MeshIntersection:
             _lib.check(lib.qf_hits_resort(_lib.ptr(index_ray), _lib.ptr(depth), M, _lib.ptr(perm), _lib.ptr(b8),
                                           _lib.stream(dev)), "qf_hits_resort")
             boundary = b8.bool()
-        g = lambda t: t.to(dev)[perm]
-        depth = depth[perm]
-        deltas = self.find_deltas(boundary, depth)
-        return g(points), deltas, boundary, g(vectors), index_ray[perm], depth, g(index_tri), g(origins)
+        return perm, boundary
+

@@ -51,7 +51,9 @@ class _DirectionEncoding(nn.Module):
 
 class _NGPForwardFn(torch.autograd.Function):
     """NGPRadianceField.forward under autograd: gradients for the flat tinycudann parameter tensors
-    (`mlp_base.params` = [MLP weights | grid table], `mlp_head.params`).  Positions / directions get no gradient."""
+    (`mlp_base.params` = [MLP weights | grid table], `mlp_head.params`) and, when `positions` requires grad, for the
+    positions (tinycudann's grid input gradient; the finetune step moves the sample points with the deformation field).
+    Directions get no gradient."""
 
     @staticmethod
     def forward(ctx, field, positions, directions, ray_indices, base_params, head_params):
@@ -66,6 +68,7 @@ class _NGPForwardFn(torch.autograd.Function):
         _lib.check(lib.qf_ngp_forward(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(rgb), _lib.ptr(density),
                                       _lib.stream(pos.device)), "qf_ngp_forward")
         ctx.field = field
+        ctx.pos_shape = positions.shape
         ctx.save_for_backward(pos, dirs, ri)
         return rgb, density
 
@@ -79,15 +82,18 @@ class _NGPForwardFn(torch.autograd.Function):
         h = field._native()
         g_base = torch.zeros_like(field.mlp_base.params)
         g_head = torch.zeros_like(field.mlp_head.params)
+        g_pos = torch.zeros((M, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         if M:
             g_rgb = _lib.f32(g_rgb) if g_rgb is not None else torch.zeros((M, 3), device=dev)
             g_den = _lib.f32(g_density.reshape(-1)) if g_density is not None else None
             nb = field._n_base
             ws = _lib.workspace(dev, lib.qf_ngp_backward_workspace_bytes(M), "ngp_bwd")
-            _lib.check(lib.qf_ngp_backward(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(g_rgb), _lib.ptr(g_den),
-                                           _lib.ptr(g_base[nb:]), _lib.ptr(g_base[:nb]), _lib.ptr(g_head), _lib.ptr(ws), ws.numel(),
-                                           _lib.stream(dev)), "qf_ngp_backward")
-        return None, None, None, None, g_base, g_head
+            _lib.check(lib.qf_ngp_backward_inputs(h, _lib.ptr(pos), _lib.ptr(dirs), _lib.ptr(ri), M, _lib.ptr(g_rgb), _lib.ptr(g_den),
+                                                  _lib.ptr(g_base[nb:]), _lib.ptr(g_base[:nb]), _lib.ptr(g_head), _lib.ptr(g_pos),
+                                                  _lib.ptr(ws), ws.numel(), _lib.stream(dev)), "qf_ngp_backward_inputs")
+        if g_pos is not None:
+            g_pos = g_pos.view(ctx.pos_shape)
+        return None, g_pos, None, None, g_base, g_head
 
 
 _BASE_SHAPES = [(64, 32), (16, 64)]
@@ -204,7 +210,8 @@ class NGPRadianceField(nn.Module):
             raise NameError("name 'rgb' is not defined")  # what the reference does (quirk Q8, ngp.py:803-809)
         if ray_indices is None:
             assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
-        if torch.is_grad_enabled() and (self.mlp_base.params.requires_grad or self.mlp_head.params.requires_grad):
+        if torch.is_grad_enabled() and (self.mlp_base.params.requires_grad or self.mlp_head.params.requires_grad
+                                        or positions.requires_grad):
             return _NGPForwardFn.apply(self, positions, directions, ray_indices, self.mlp_base.params, self.mlp_head.params)
         with torch.no_grad():
             return self._forward_nograd(positions, directions, ray_indices)

@@ -266,27 +266,58 @@ def _flatten_rays(rays: Rays):
     return rays, rays_shape, num_rays
 
 
-@torch.no_grad()
+def _field_vector(field_net, x):
+    """`del_vector[b:b+batch] = field_net(x, return_grad=False)[0]` (utils.py:557-565): the reference writes the
+    (M, output_dim) output into an (M,3) buffer, so a scalar field is broadcast to the three components."""
+    out = field_net(x, return_grad=False)[0]
+    return out.expand(-1, 3) if out.shape[1] == 1 else out
+
+
 def render_image_finetune_with_occgrid(radiance_field, field_net, estimator, rays: Rays, data, near_plane=0.0,
                                        far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
                                        alpha_thre=0.0, test_chunk_size=8192, timestamps=None, mesh_intersect=None,
-                                       mesh_finetune=None, scaling=0.0, bg_color="white"):
-    """utils.py:465-607, inference semantics (`scaling == 0`, as in the eval "after" pass train_finetune.py:726):
-    the deformation field multiplies to zero (quirk Q10), so `field_net` is not evaluated.
-    `data` is the reference tuple (xyzs, dirs, index_ray, ts, index_tri, origins).  Returns the 9-tuple."""
-    if scaling != 0 or mesh_finetune is not None:
-        raise NotImplementedError("training-time deformation (SURVEY §8 row f-3) is not part of the render path")
+                                       mesh_finetune=None, scaling=1 / 128, bg_color="white"):
+    """utils.py:465-607.  `data` is the reference tuple (xyzs, dirs, index_ray, ts, index_tri, origins).  Returns the
+    9-tuple (rgb, opacity, depth, n_samples, weights, points, index_ray, loss, index_tri).
+
+    Training mode (scaling != 0): the deformation field moves every quadrature point along its ray by
+    tanh(field_net)·scaling (`dh`), the samples are re-sorted per ray, the radiance field is queried at the moved points
+    (gradients reach `field_net` through the radiance field's POSITION gradient) and `mesh_finetune.update_d` accumulates
+    the weighted displacement per triangle.  Reference quirks kept: `update_d` pairs the re-sorted `weights` with the
+    un-sorted `dh` / `index_tri` (:588), and the vertex regulariser samples random points of the hit triangles (:543-546).
+    With scaling == 0 (the evaluation passes, train_finetune.py:726) the displacement is exactly zero (quirk Q10) and
+    `field_net` is not evaluated."""
     rays, rays_shape, num_rays = _flatten_rays(rays)
     dev = mesh_intersect.device
     xyzs, dirs, index_ray, ts, index_tri, origins = [t.to(dev) for t in data]
-    points, deltas, boundary, dirs, index_ray, depth, index_tri, _ = mesh_intersect.sampling_indexing(
-        xyzs, origins, dirs, index_ray.long(), ts, index_tri.long())
-    rgbs, sigmas = radiance_field(points, rays.viewdirs.to(dev), ray_indices=index_ray)      # quirk Q7
-    loss = torch.zeros(1, device=dev)
-    rgb, opacity, _, depth_img, weights = derive_properties(rgbs, sigmas.squeeze(-1), depth, deltas, boundary, index_ray,
+    index_ray, index_tri = index_ray.long(), index_tri.long()
+    viewdirs = rays.viewdirs.to(dev)
+    if scaling == 0:
+        points, deltas, boundary, _, index_ray_s, depth, _, _ = mesh_intersect.sampling_indexing(xyzs, origins, dirs, index_ray, ts, index_tri)
+        dh = torch.zeros_like(xyzs)
+        loss = torch.zeros(1, device=dev)
+    else:
+        faces = torch.as_tensor(np.asarray(mesh_intersect.mesh.faces), device=dev).long()
+        tri_v = mesh_intersect.vertices[faces[index_tri]][:, :, 0:3]                       # (M,3,3)   utils.py:543-544
+        w = torch.rand((xyzs.shape[0], 3), device=xyzs.device)[..., None]
+        vertices = torch.sum(tri_v * w, dim=1) / (torch.sum(w, dim=1) + 1e-6)
+        del_vector_v = torch.tanh(_field_vector(field_net, vertices)) * scaling
+        del_vector = torch.tanh(_field_vector(field_net, xyzs)) * scaling
+        del_delta = (del_vector * dirs).sum(-1, keepdim=True)
+        dh = del_delta * dirs
+        xyzs = xyzs + dh
+        ts = ts + del_delta.view(-1)
+        # re-sorting the quadrature points based on the added dh
+        points, deltas, boundary, _, index_ray_s, depth, _, _ = mesh_intersect.sampling_indexing(xyzs, origins, dirs, index_ray, ts, index_tri)
+        loss = ((del_vector) ** 2).mean() + ((del_vector_v - del_vector.detach()) ** 2).mean()
+        loss = loss.reshape(1)
+    rgbs, sigmas = radiance_field(points, viewdirs, ray_indices=index_ray_s)                 # quirk Q7: original viewdirs
+    rgb, opacity, _, depth_img, weights = derive_properties(rgbs, sigmas.squeeze(-1), depth, deltas, boundary, index_ray_s,
                                                             bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays)
+    if mesh_finetune is not None:
+        mesh_finetune.update_d(dh, weights[:, 0], index_tri)
     return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth_img.view((*rays_shape[:-1], -1)),
-            xyzs.shape[0], weights, points, index_ray, loss, index_tri)
+            xyzs.shape[0], weights, points, index_ray_s, loss, index_tri)
 
 
 @torch.no_grad()

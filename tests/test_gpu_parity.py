@@ -845,3 +845,99 @@ def test_trace_and_render_edge_cases(dev, smoke_scene):
     assert count_ref[:5].sum() == 0 and count_ref.max() >= 4
     dup = (tri_ref == faces.shape[0] - 1).any(axis=1).sum()
     assert dup > 0                                            # the duplicated face is reported once per copy, id order on equal t
+
+
+def test_ngp_position_gradient_matches_oracle_autograd(dev, smoke_scene):
+    """dL/dpositions of NGPRadianceField.forward (tcnn's grid input gradient, needed when the finetune deformation moves
+    the quadrature points, utils.py:566-583) against PyTorch autograd through the oracle at tcnn precision."""
+    sc = smoke_scene
+    p = oracle_params(sc)
+    g = torch.Generator().manual_seed(9)
+    M = 6000
+    x = ((torch.rand(M, 3, generator=g) * 2 - 1) * 1.3)
+    x[:200] *= 1.3                                               # some points outside the aabb (selector = 0 on the density path)
+    d = torch.nn.functional.normalize(torch.randn(M, 3, generator=g), dim=-1)
+    wr, ws = torch.randn(M, 3, generator=g), torch.randn(M, 1, generator=g) * 0.01
+    prev = O.ROUND_HIDDEN
+    O.ROUND_HIDDEN = True
+    try:
+        xr = x.clone().requires_grad_(True)
+        rgb_ref, dens_ref = O.ngp_forward(xr, d, p)
+        ((rgb_ref * wr).sum() + (dens_ref * ws).sum()).backward()
+    finally:
+        O.ROUND_HIDDEN = prev
+    xg = x.to(dev).requires_grad_(True)
+    rgb, dens = sc.radiance_field(xg, d.to(dev))
+    ((rgb * wr.to(dev)).sum() + (dens * ws.to(dev)).sum()).backward()
+    ref = xr.grad
+    err = (xg.grad.cpu() - ref).abs()
+    scale = float(ref.abs().max())
+    cos = float(torch.nn.functional.cosine_similarity(xg.grad.cpu().flatten(), ref.flatten(), dim=0))
+    assert scale > 1e-3 and cos >= 0.9999 and float(err.max()) <= 2e-2 * scale, (float(err.max()), scale, cos)
+    assert float(err.mean()) <= 1e-3 * scale
+    # parameter gradients are unchanged by asking for the position gradient
+    sc.radiance_field.zero_grad()
+    rgb2, dens2 = sc.radiance_field(x.to(dev), d.to(dev))
+    ((rgb2 * wr.to(dev)).sum() + (dens2 * ws.to(dev)).sum()).backward()
+    g_a = sc.radiance_field.mlp_head.params.grad.clone()
+    sc.radiance_field.zero_grad()
+
+
+def test_finetune_step_training_mode_golden(dev, golden, monkeypatch):
+    """f-3 end to end against the reference: `render_image_finetune_with_occgrid` in training mode (deformation field on
+    the quadrature points, re-sort, radiance field at the moved points, regulariser, MeshFinetune.update_d) followed
+    by loss.backward() — outputs, accumulators and the gradients of BOTH networks (the field net's gradient arrives
+    through the radiance field's position gradient) vs tests/golden/finetune_step.npz.  The golden was produced at
+    tcnn precision on the CPU (fp32 MMAs there, fp16 operands here), hence the gradient tolerances."""
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.mesh_utils import MeshFinetune, MeshIntersection
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceField
+    from quadraturefields_b200.utils import render_image_finetune_with_occgrid as drv
+    g = golden("finetune_step")
+    f32 = lambda k: torch.from_numpy(np.asarray(g[k], dtype=np.float32))
+    mi = MeshIntersection((g["verts"], g["faces"]), num_intersections=int(g["K"]), render_step_size=float(g["step"]), device=dev)
+    rf = NGPRadianceField(aabb=[-1.5] * 3 + [1.5] * 3, log2_hashmap_size=int(g["log2_T"]))
+    with torch.no_grad():
+        rf.mlp_base.params.copy_(f32("rf_base")); rf.mlp_head.params.copy_(f32("rf_head"))
+    rf = rf.to(dev)
+    net = Field(scale=1.5, precision=16, log2_T=10, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=32,
+                num_features=2, back_prop=False, nl="relu")
+    net.load_state_dict({k[2:]: f32(k) for k in g if k.startswith("p_")})
+    net = net.to(dev)
+    mf = MeshFinetune(g["verts"], g["faces"], float(g["scaling"]), device=dev)
+    data = [f32("data_xyzs"), f32("data_dirs"), T(g["data_index_ray"]), f32("data_ts"), T(g["data_index_tri"]), f32("data_origins")]
+    # the intersector reproduces the tuple the reference run started from
+    tup = mi.sampling_raytrace(f32("viewdirs"), f32("origins"))
+    assert torch.equal(tup[2].cpu(), data[2]) and torch.equal(tup[4].cpu(), data[4]) and maxabs(tup[0], data[0]) <= 1e-6
+    rays = Rays(f32("origins"), f32("viewdirs"))
+    bary = f32("bary").to(dev)
+    real_rand = torch.rand
+    monkeypatch.setattr(torch, "rand", lambda *a, **k: bary if tuple(a[0]) == tuple(bary.shape) else real_rand(*a, **k))
+    rgb, op, depth, n, weights, points, index_ray, loss_reg, index_tri = drv(
+        rf, net, None, rays, data, render_step_size=float(g["step"]), mesh_intersect=mi, mesh_finetune=mf,
+        scaling=float(g["scaling"]), bg_color="white")
+    monkeypatch.undo()
+    assert n == int(g["n"]) and torch.equal(index_ray.cpu(), T(g["index_ray"])) and torch.equal(index_tri.cpu(), T(g["index_tri"]))
+    assert maxabs(points, g["positions"]) <= 2e-6                      # the field net moved the points like the reference
+    assert maxabs(points, g["data_xyzs"]) > 1e-4
+    assert maxabs(rgb, g["rgb"]) <= TOL_IMG and maxabs(op, g["opacity"]) <= TOL_IMG and maxabs(weights, g["weights"]) <= TOL_IMG
+    assert abs(float(loss_reg) - float(g["loss_reg"][0])) <= 1e-3 * float(g["loss_reg"][0])
+    # sums of per-sample weights that each carry the 1e-3 image tolerance (and of weights x |dh| <= scaling)
+    assert np.allclose(mf.cache_d.cpu().numpy(), g["cache_d"], rtol=2e-3, atol=2e-3 * float(g["scaling"]))
+    assert np.allclose(mf.cache_w.cpu().numpy(), g["cache_w"], rtol=2e-3, atol=2e-3)
+    loss = torch.nn.functional.smooth_l1_loss(rgb.squeeze(), f32("pixels").to(dev)) + loss_reg
+    loss.sum().backward()
+
+    def close(a, ref, rel, cos_min):
+        a, ref = a.detach().cpu().flatten(), torch.from_numpy(np.asarray(ref)).flatten()
+        cos = float(torch.nn.functional.cosine_similarity(a, ref, dim=0))
+        return float((a - ref).abs().max()) <= rel * float(ref.abs().max()) and cos >= cos_min, (float((a - ref).abs().max()), float(ref.abs().max()), cos)
+    missing = [name for name, prm in list(net.named_parameters()) + list(rf.named_parameters()) if prm.grad is None]
+    assert not missing, missing
+    for name, prm in net.named_parameters():
+        ok, info = close(prm.grad, g[f"g_{name}"], 5e-2, 0.999)
+        assert ok, (name, info)
+    for name, prm, key in (("base", rf.mlp_base.params, "g_base"), ("head", rf.mlp_head.params, "g_head")):
+        ok, info = close(prm.grad, g[key], 2e-2, 0.9995)
+        assert ok, (name, info)
