@@ -363,7 +363,7 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     import torch
     from quadraturefields_b200 import parallel as P
     from quadraturefields_b200.field import Field
-    from quadraturefields_b200.utils import train_field_step
+    from quadraturefields_b200.utils import HitTuplePrefetcher, train_field_step
     n = args.train_rays
     g = torch.Generator(device=dev).manual_seed(4321 + rank)
     n_views = min(32, len(sc.poses))
@@ -375,21 +375,32 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15)
     steps, warm = max(5, min(args.steps, 20)), 3
     batches = []
-    for i in range(steps + warm):
+    for i in range(steps + warm + 1):
         vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
         pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous()))
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
     reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
+    # every step trains on the tuple traced during the previous step and traces the next batch on a side stream
+    # (the reference's DataLoader worker does the intersection ahead of the step, too): one trace per step
+    pf = HitTuplePrefetcher(sc.mesh_intersect)
+
+    def step(i):
+        tup = pf.get()
+        m = train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[i], opt, all_reduce=reduce, tup=tup)[1]
+        pf.submit(*batches[i + 1], rays_ready=True)
+        return m
+
+    pf.submit(*batches[0], rays_ready=True)
     for i in range(warm):
-        train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[i], opt, all_reduce=reduce)
+        step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     samples = 0
     for i in range(steps):
-        samples += train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[warm + i], opt, all_reduce=reduce)[1]
+        samples += step(warm + i)
     e1.record()
     barrier()
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
@@ -397,8 +408,8 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     return {"metric": "rays_per_sec_field_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s",
             "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n, "samples_per_ray": samples / (n * steps),
             "params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "includes": "trace + frozen field fwd + weights/reversed weights + Field fwd with field_grad + loss + double backward + "
-                        "grad all-reduce + Adam step"}
+            "includes": "trace (of the next batch, side stream) + frozen field fwd + weights/reversed weights + Field fwd with "
+                        "field_grad + loss + double backward + grad all-reduce + Adam step"}
 
 
 def run_train_steps(args, sc, dev, rank, world, barrier):
@@ -407,7 +418,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     NCCL all-reduce of the flat gradients -> Adam step.  Returns rays/s (fwd+bwd, all ranks) and ms/step."""
     import torch
     from quadraturefields_b200 import parallel as P
-    from quadraturefields_b200.utils import render_train
+    from quadraturefields_b200.utils import HitTuplePrefetcher, render_train
     n = args.train_rays
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_views = min(32, len(sc.poses))
@@ -418,23 +429,29 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15, fused=True)
     steps, warm = max(5, min(args.steps, 20)), 3
     batches = []
-    for i in range(steps + warm):
+    for i in range(steps + warm + 1):
         vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
         pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous(), torch.rand((n, 3), device=dev, generator=g)))
+    # the tuple of batch i was traced on a side stream during step i-1 (as the reference's DataLoader worker does); every
+    # step still performs exactly one trace (of the next batch)
+    pf = HitTuplePrefetcher(sc.mesh_intersect)
 
     def step(i):
         o, d, target = batches[i]
+        tup = pf.get()
         opt.zero_grad(set_to_none=False)
-        rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d)
+        rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d, tup=tup)
         loss = torch.nn.functional.smooth_l1_loss(rgb, target)
         loss.backward()
         P.all_reduce_gradients(params, n, n * world)
         opt.step()
+        pf.submit(batches[i + 1][0], batches[i + 1][1], rays_ready=True)
         return n_hits
 
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
+    pf.submit(batches[0][0], batches[0][1], rays_ready=True)
     for i in range(warm):
         step(i)
     barrier()
@@ -450,7 +467,8 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,
             "steps": steps, "rays_per_step_per_gpu": n, "hits_per_ray": hits / (n * steps), "params": n_params,
             "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "includes": "trace + field fwd + composite + loss + field/composite bwd + grad all-reduce + fused Adam step"}
+            "includes": "trace (of the next batch, side stream) + field fwd + composite + loss + field/composite bwd + grad all-reduce "
+                        "+ fused Adam step"}
 
 
 if __name__ == "__main__":

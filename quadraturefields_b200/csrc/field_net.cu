@@ -422,7 +422,8 @@ extern "C" int qf_field_backward(const qf_ngp* grid, const qf_field_desc* fd, co
   a.g_table = reinterpret_cast<float2*>(d_grad_table);
   a.g_w1 = d_grad_w1; a.g_b1 = d_grad_b1; a.g_w2 = d_grad_w2; a.g_b2 = d_grad_b2; a.g_w3 = d_grad_w3; a.g_b3 = d_grad_b3;
   int64_t want = ceil_div(M, 128);
-  const int blocks = (int)(want < (int64_t)kNumSMs * 2 ? want : (int64_t)kNumSMs * 2);
+  // 4 CTAs per SM fit (44-55 KB of shared memory each); the per-CTA flush costs ~2 k atomics, so no more than that
+  const int blocks = (int)(want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4);
   cudaStream_t st = (cudaStream_t)stream;
   const int key = fd->hidden * 2 + fd->activation;
   switch (key) {

@@ -123,9 +123,12 @@ class Field(nn.Module):
         p = self.xyz_encoder.params
         if not p.is_cuda:
             raise RuntimeError("Field runs on CUDA only: call .cuda() first (no CPU path)")
-        lo, hi = self.xyz_min.detach().cpu().reshape(-1).tolist(), self.xyz_max.detach().cpu().reshape(-1).tolist()
-        for c in range(3):
-            self._fdesc.xyz_min[c], self._fdesc.xyz_max[c] = lo[c], hi[c]
+        box_key = (self.xyz_min.data_ptr(), self.xyz_min._version, self.xyz_max.data_ptr(), self.xyz_max._version)
+        if getattr(self, "_box_key", None) != box_key:        # a device->host copy synchronises: only when the box changed
+            lo, hi = self.xyz_min.detach().cpu().reshape(-1).tolist(), self.xyz_max.detach().cpu().reshape(-1).tolist()
+            for c in range(3):
+                self._fdesc.xyz_min[c], self._fdesc.xyz_max[c] = lo[c], hi[c]
+            self._box_key = box_key
         key = (p.data_ptr(), p._version)
         if self._handle is not None and key == self._handle_key:
             return self._handle

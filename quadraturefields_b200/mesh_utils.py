@@ -238,6 +238,11 @@ def triangle_weight_max(triangles_weights: torch.Tensor, weights: torch.Tensor, 
     return triangles_weights
 
 
+class HitTuple(tuple):
+    """The reference's 7-tuple (points, vectors, index_ray, depth, index_tri, 0, origins) plus `.offsets`."""
+    offsets = None
+
+
 class MeshIntersection:
     """mesh_utils.py:180-412.  `mesh_path` may also be a `(vertices, faces)` pair."""
 
@@ -263,11 +268,13 @@ class MeshIntersection:
     @torch.no_grad()
     def sampling_raytrace(self, vectors: torch.Tensor, origins: torch.Tensor):
         """Device-resident `sampling_raytrace_numpy`: returns the 7-tuple as CUDA tensors, or None on zero hits."""
-        points, vecs, index_ray, depth, index_tri, org, _ = self.rayintersector.trace_tuple(origins, vectors,
-                                                                                          self.num_intersections)
+        points, vecs, index_ray, depth, index_tri, org, offsets = self.rayintersector.trace_tuple(origins, vectors,
+                                                                                                self.num_intersections)
         if index_tri.shape[0] == 0:
             return None
-        return points, vecs, index_ray, depth, index_tri, 0, org
+        tup = HitTuple((points, vecs, index_ray, depth, index_tri, 0, org))
+        tup.offsets = offsets          # (N+1,) int64 start of every ray's run: lets callers skip re-deriving the packs
+        return tup
 
     def sampling_raytrace_numpy(self, vectors, origins, random=0):
         """mesh_utils.py:343-387 (numpy in, numpy out, `None` when nothing is hit)."""

@@ -149,9 +149,12 @@ class NGPRadianceField(nn.Module):
         if self._handle is not None and key == self._handle_key:
             return self._handle
         lib = _lib.load()
-        aabb = self.aabb.detach().cpu().tolist()
-        for i in range(6):
-            self._desc.aabb[i] = float(aabb[i])
+        aabb_key = (self.aabb.data_ptr(), self.aabb._version)
+        if getattr(self, "_aabb_key", None) != aabb_key:      # a device->host copy synchronises: only when the box changed
+            aabb = self.aabb.detach().cpu().tolist()
+            for i in range(6):
+                self._desc.aabb[i] = float(aabb[i])
+            self._aabb_key = aabb_key
         base = p_base.detach()
         table, base_w, head_w = base[self._n_base:], base[: self._n_base], p_head.detach()
         st = _lib.stream(p_base.device)

@@ -191,12 +191,57 @@ class FramePipeline:
             cur.wait_stream(st)
 
 
-def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="white", render_bkgd=None):
+class HitTuplePrefetcher:
+    """Intersection of the NEXT training batch while the current one trains.  The reference does the same thing with a
+    DataLoader worker: `SubjectLoader.fetch_data` calls `mesh_intersect.sampling_raytrace_numpy` on the CPU (Embree) and
+    hands the tuple over as `data["data"]` (train_finetune.py:494-509).  Here the trace runs on a side CUDA stream, so the
+    host-side wait for the hit count (the tuple's size) does not drain the training stream.  Call `submit` AFTER the
+    current step's work has been launched: the host then waits for the side stream while the GPU trains.  (A worker
+    thread for the wait was measured slower: the step is bound by Python launch overhead and the thread competes for
+    the GIL.)  The intersection does not depend on the networks' parameters, so the result is identical to tracing
+    inside the step."""
+
+    def __init__(self, mesh_intersect):
+        self.mesh_intersect = mesh_intersect
+        self.stream = torch.cuda.Stream(device=mesh_intersect.device)
+        self._pending = None
+
+    @torch.no_grad()
+    def submit(self, origins, viewdirs, rays_ready: bool = False):
+        """`rays_ready=True`: the ray tensors were completed earlier (a data-loader batch), so the trace need not wait
+        for the work queued on the training stream — that wait would serialise it behind the whole current step."""
+        main = torch.cuda.current_stream(self.mesh_intersect.device)
+        if not rays_ready:
+            self.stream.wait_stream(main)                   # the rays may still be in flight on the training stream
+        with torch.cuda.stream(self.stream):
+            tup = self.mesh_intersect.sampling_raytrace(viewdirs, origins)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._pending = (tup, ev, origins, viewdirs)
+
+    def get(self):
+        """-> the 7-tuple (or None when nothing was hit), safe to use on the current stream."""
+        tup, ev, origins, viewdirs = self._pending
+        self._pending = None
+        main = torch.cuda.current_stream(self.mesh_intersect.device)
+        main.wait_event(ev)
+        if tup is not None:
+            for t in tup:
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
+        return tup
+
+
+_NO_TUPLE = object()
+
+
+def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="white", render_bkgd=None, tup=_NO_TUPLE):
     """Differentiable mesh-path render (train_finetune.py:494-509 with scaling=0): intersection (no gradient) ->
     field at the hits (gradients to the hash table and MLPs) -> derive_properties.  -> (rgb (N,3), opacity (N,1), depth (N,1), n_hits)."""
     N = origins.shape[0]
-    with torch.no_grad():
-        tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
+    if tup is _NO_TUPLE:                                    # otherwise: a tuple prefetched with HitTuplePrefetcher
+        with torch.no_grad():
+            tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
     dev = mesh_intersect.device
     if tup is None:
         fill = 0.0 if bg_color == "black" else 1.0
@@ -204,6 +249,14 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
         return torch.full((N, 3), fill, device=dev), z, z.clone(), 0
     points, _, index_ray, depth, _, _, _ = tup
     rgbs, sigmas = radiance_field(points, _lib.f32(viewdirs, dev), ray_indices=index_ray)
+    offsets = getattr(tup, "offsets", None)
+    if offsets is not None:
+        # the intersector already knows where every ray's run starts: no boundary scan, no host synchronisation
+        bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else None
+        rgb, opacity, depth_img, _ = _DerivePropertiesFn.apply(_lib.f32(rgbs), _lib.f32(sigmas.reshape(-1)), _lib.f32(depth),
+                                                               float(mesh_intersect.render_step_size), offsets, N,
+                                                               _lib.BG_MODES.get(bg_color, 2), bk)
+        return rgb, opacity, depth_img, points.shape[0]
     boundary = torch.ones_like(index_ray, dtype=torch.bool)
     boundary[1:] = index_ray[1:] != index_ray[:-1]
     rgb, opacity, _, depth_img, _ = derive_properties(rgbs, sigmas.squeeze(-1), depth, mesh_intersect.render_step_size, boundary,
@@ -211,7 +264,7 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
     return rgb, opacity, depth_img, points.shape[0]
 
 
-def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs):
+def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs, tup=_NO_TUPLE):
     """The no-grad half of a quadrature-field training step (train_field.py:313-344): sample positions along the rays,
     the frozen radiance field's near-to-far and far-to-near weights at them (`rendering_field`, utils.py:431-446) and the
     normalised positions.  The reference takes its samples from nerfacc's occupancy-grid marcher (out
@@ -219,7 +272,8 @@ def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs):
     -> (positions - 0.5 (M,3), dirs (M,3), weights (M,), weights_rev (M,)) or None when nothing is hit."""
     from .field_rendering import rendering_field
     with torch.no_grad():
-        tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
+        if tup is _NO_TUPLE:
+            tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
         if tup is None:
             return None
         points, _, index_ray, depth, _, _, _ = tup
@@ -237,11 +291,11 @@ def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs):
         return positions - 0.5, vd[index_ray], weights, weights_rev
 
 
-def train_field_step(field_net, radiance_field, mesh_intersect, origins, viewdirs, optimizer, all_reduce=None):
+def train_field_step(field_net, radiance_field, mesh_intersect, origins, viewdirs, optimizer, all_reduce=None, tup=_NO_TUPLE):
     """One optimiser step of the quadrature field (train_field.py:345-368): Field forward + analytic field_grad ->
     compute_field_loss -> backward (double backward through the MLP, first-order grid backward) -> optional gradient
     all-reduce -> optimizer.step().  -> (loss tensor, number of samples)."""
-    batch = field_training_batch(mesh_intersect, radiance_field, origins, viewdirs)
+    batch = field_training_batch(mesh_intersect, radiance_field, origins, viewdirs, tup=tup)
     if batch is None:
         return None, 0
     positions, dirs, weights, weights_rev = batch
