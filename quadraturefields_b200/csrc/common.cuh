@@ -1,5 +1,6 @@
 // Shared host/device helpers for libquadfield.so (sm_100a only).
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -35,6 +36,19 @@ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
   } while (0)
 
 #define QF_LAUNCH_CHECK() QF_CUDA_CHECK(cudaGetLastError())
+// Opt a kernel into more than 48 KB of dynamic shared memory.  The attribute is per device, so it is set once per
+// (call site, device); a bit mask per call site remembers which devices are done (thread-safe, devices 0..63).
+#define QF_ENSURE_DYNAMIC_SMEM(kernel, bytes)                                                                      \
+  do {                                                                                                             \
+    static std::atomic<unsigned long long> qf_smem_done_{0};                                                       \
+    int qf_dev_ = 0;                                                                                               \
+    QF_CUDA_CHECK(cudaGetDevice(&qf_dev_));                                                                        \
+    const unsigned long long qf_bit_ = 1ull << (qf_dev_ & 63);                                                     \
+    if (!(qf_smem_done_.load(std::memory_order_acquire) & qf_bit_)) {                                              \
+      QF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      qf_smem_done_.fetch_or(qf_bit_, std::memory_order_release);                                                  \
+    }                                                                                                              \
+  } while (0)
 
 // ---- opaque handle layouts (shared between translation units) --------------------------------
 
@@ -55,7 +69,7 @@ struct qf_mesh {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int32_t* d_call_slots = nullptr;  // ring of per-call scratch: [coherent chunks, total chunks, ray counter, pad]
-  mutable unsigned call_id = 0;
+  mutable std::atomic<unsigned> call_id{0};   // concurrent qf_trace_firstk calls on one mesh take distinct slots
   size_t bytes = 0;
   float h_pad = 0.f;
 };

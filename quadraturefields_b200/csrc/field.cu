@@ -343,11 +343,7 @@ __global__ void __launch_bounds__((PROD + CONS) * 32, 1) ngp_forward_ws_kernel(c
 template <int PROD, int CONS>
 static int launch_ws(FieldArgs& a, cudaStream_t st) {
   using Cfg = WsCfg<PROD, CONS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_ws_kernel<PROD, CONS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
+  QF_ENSURE_DYNAMIC_SMEM((ngp_forward_ws_kernel<PROD, CONS>), Cfg::kSmemBytes);
   int64_t rounds = a.d_M ? kNumSMs : ceil_div(a.M, 32 * PROD);
   int blocks = (int)(rounds < kNumSMs ? (rounds < 1 ? 1 : rounds) : kNumSMs);
   ngp_forward_ws_kernel<PROD, CONS><<<blocks, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
@@ -398,12 +394,8 @@ __global__ void __launch_bounds__(128) encode_sum_kernel(const qf_grid_desc desc
 template <int WARPS>
 static int launch_fused(FieldArgs& a, int mode, cudaStream_t st) {
   constexpr int smem = kWTotal * 2 + WARPS * 32 * kTileStride * 2, per_sm = 20 / WARPS;   // one resident wave
-  static bool attr_set = false;
-  if (!attr_set) {
-    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_kernel<0, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_kernel<1, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  QF_ENSURE_DYNAMIC_SMEM((ngp_forward_kernel<0, WARPS>), smem);
+  QF_ENSURE_DYNAMIC_SMEM((ngp_forward_kernel<1, WARPS>), smem);
   int64_t tiles = a.d_M ? (int64_t)kNumSMs * per_sm : ceil_div(a.M, WARPS * 32);
   int blocks = (int)(tiles < (int64_t)kNumSMs * per_sm ? tiles : (int64_t)kNumSMs * per_sm);
   if (blocks < 1) blocks = 1;

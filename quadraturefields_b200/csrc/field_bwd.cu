@@ -501,11 +501,7 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
   a.act = act; a.grd = grd;
   a.g_pos = d_grad_positions;
   for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
-  static bool attr_set = false;
-  if (!attr_set) {
-    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
-    attr_set = true;
-  }
+  QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel, kBwdSmemBytes);
   int64_t tiles = ceil_div(M, 128);
   int blocks = (int)(tiles < (int64_t)kNumSMs * 2 ? tiles : (int64_t)kNumSMs * 2);
   ngp_backward_kernel<<<blocks, 128, kBwdSmemBytes, st>>>(a);

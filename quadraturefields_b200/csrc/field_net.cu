@@ -328,11 +328,7 @@ __global__ void __launch_bounds__(128) field_net_backward_kernel(const FieldNetA
 template <int H, int ACT>
 static int launch_bwd(const FieldNetArgs& a, int blocks, cudaStream_t st) {
   constexpr int smem = (2 * FnSmem<H>::kTotal + 2 * 4 * 32 * kFnPanel) * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    QF_CUDA_CHECK(cudaFuncSetAttribute(field_net_backward_kernel<H, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
+  QF_ENSURE_DYNAMIC_SMEM((field_net_backward_kernel<H, ACT>), smem);
   field_net_backward_kernel<H, ACT><<<blocks, 128, smem, st>>>(a);
   QF_LAUNCH_CHECK();
   return QF_OK;

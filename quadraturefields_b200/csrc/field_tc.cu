@@ -306,11 +306,7 @@ int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st) {
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights_tc = f->d_weights_tc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QF_CUDA_CHECK(cudaFuncSetAttribute(ngp_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    attr_set = true;
-  }
+  QF_ENSURE_DYNAMIC_SMEM(ngp_forward_tc_kernel, kTcSmemBytes);
   int64_t tiles = a.d_M ? (int64_t)kNumSMs * 4 : ceil_div(a.M, 128);
   int blocks = (int)(tiles < (int64_t)kNumSMs * 4 ? tiles : (int64_t)kNumSMs * 4);
   if (blocks < 1) blocks = 1;

@@ -76,24 +76,35 @@ def gather_frame(parts: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Opt
 
 
 def all_reduce_gradients(params: Sequence[torch.Tensor], n_local: int, n_global: Optional[int] = None) -> None:
-    """Training mode: sum the per-rank gradients of the (replicated) hash table and MLPs in ONE flat bucket and
-    rescale a per-rank mean loss to the global sample count (`n_local` samples here, `n_global` overall)."""
+    """Training mode: sum the per-rank gradients of the (replicated) hash table and MLPs — large tensors in place,
+    the small ones in one flat bucket — and rescale a per-rank mean loss to the global sample count (`n_local`
+    samples here, `n_global` overall)."""
     rank, ws = world()
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
     if ws == 1:
         return
-    counts = torch.tensor([float(n_local)], device=grads[0].device)
     if n_global is None:
+        counts = torch.tensor([float(n_local)], device=grads[0].device)
         dist.all_reduce(counts)
         n_global = float(counts.item())
-    flat = torch.cat([g.reshape(-1) for g in grads]) * (float(n_local) / float(n_global))
-    dist.all_reduce(flat)
-    off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+    scale = float(n_local) / float(n_global)
+    big = [g for g in grads if g.numel() >= (1 << 20) and g.is_contiguous()]
+    small = [g for g in grads if not (g.numel() >= (1 << 20) and g.is_contiguous())]
+    for g in big:                       # the hash table: reduced in place, no flatten / copy-back of tens of MB
+        if scale != 1.0:
+            g.mul_(scale)
+        dist.all_reduce(g)
+    if small:                           # MLP matrices and biases: one bucket, one launch-latency-bound collective
+        flat = torch.cat([g.reshape(-1) for g in small])
+        if scale != 1.0:
+            flat.mul_(scale)
+        dist.all_reduce(flat)
+        off = 0
+        for g in small:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -941,3 +941,36 @@ def test_finetune_step_training_mode_golden(dev, golden, monkeypatch):
     for name, prm, key in (("base", rf.mlp_base.params, "g_base"), ("head", rf.mlp_head.params, "g_head")):
         ok, info = close(prm.grad, g[key], 2e-2, 0.9995)
         assert ok, (name, info)
+
+
+def test_hit_tuple_prefetcher_matches_inline_trace(dev, smoke_scene):
+    """HitTuplePrefetcher (next batch traced on a side stream, as the reference's DataLoader worker does on the CPU) gives
+    the same tuples, images and gradients as tracing inside the step; the packed fast path of render_train (ray offsets
+    carried by the tuple) equals the boundary-scan path."""
+    from quadraturefields_b200.utils import HitTuplePrefetcher, render_train
+    sc = smoke_scene
+    rf = sc.radiance_field
+    batches = [sc.rays(v) for v in range(2)]
+    pf = HitTuplePrefetcher(sc.mesh_intersect)
+    pf.submit(*batches[0], rays_ready=True)
+    outs = []
+    for i in range(2):
+        tup = pf.get()
+        if i == 0:
+            pf.submit(*batches[1])
+        ref_tup = sc.mesh_intersect.sampling_raytrace(batches[i][1], batches[i][0])
+        for a, b in zip(tup, ref_tup):
+            assert (a == b) if not isinstance(a, torch.Tensor) else torch.equal(a, b)
+        assert torch.equal(tup.offsets, ref_tup.offsets) and int(tup.offsets[-1]) == tup[0].shape[0]
+        rf.zero_grad()
+        rgb_a, op_a, d_a, n_a = render_train(sc.mesh_intersect, rf, *batches[i], tup=tup)
+        rgb_a.square().mean().backward()
+        g_a = rf.mlp_head.params.grad.clone()
+        rf.zero_grad()
+        rgb_b, op_b, d_b, n_b = render_train(sc.mesh_intersect, rf, *batches[i], tup=tuple(ref_tup))      # plain tuple: boundary-scan path
+        rgb_b.square().mean().backward()
+        assert n_a == n_b and torch.equal(rgb_a, rgb_b) and torch.equal(op_a, op_b) and torch.equal(d_a, d_b)
+        assert maxabs(g_a, rf.mlp_head.params.grad) <= 1e-6 * float(g_a.abs().max())
+        outs.append(rgb_a)
+    rf.zero_grad()
+    assert maxabs(outs[0], outs[1]) > 1e-3
