@@ -372,7 +372,7 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     net = Field(scale=0.5, precision=16, log2_T=19, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=16,
                 num_features=2, back_prop=False, nl="elu").to(dev)                  # train_field.py:238-252 (T reduced to 2^19)
     params = list(net.parameters())
-    opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15)
+    opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15, fused=True)
     steps, warm = max(5, min(args.steps, 20)), 3
     batches = []
     for i in range(steps + warm + 1):

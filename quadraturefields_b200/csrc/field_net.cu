@@ -72,17 +72,18 @@ __device__ __forceinline__ void fn_act(float z, float& a, float& d) {
 template <int ACT>
 __device__ __forceinline__ float fn_dd(float a, float d) { return (ACT == 0 && !(a > 0.f)) ? d : 0.f; }
 
-// Per-sample vectors (H floats each) live in local memory: the outer loop of every matrix-vector product is rolled
-// (dynamic index), the inner one unrolled by 8 with the weight row read from shared memory (broadcast).  The work per
-// sample is ~8 k FMA (H=32), small next to what the render path does per ray, so the kernel favours compact code.
+// H = 16 (train_field.py) is fully unrolled: the per-sample vectors stay in registers (255 registers, 2 CTAs per SM;
+// measured 0.76 ms against 1.05 ms for the rolled form on 442 k samples, forcing 3 CTAs/SM: 1.01 ms).  H = 32 keeps
+// the outer loop of every matrix-vector product rolled with the vectors in local memory (fully unrolled it needs
+// ~500 live floats and ptxas falls back to a 10 KB stack frame); weight rows are read from shared memory (broadcast).
 template <int H>
 __device__ __forceinline__ void fn_hidden(const float* s, const float* inp, float* z1) {
   using S = FnSmem<H>;
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
   for (int j = 0; j < H; ++j) {
     const float* w = s + S::kW1 + j * kFnIn;
     float acc = s[S::kB1 + j];
-#pragma unroll 7
+#pragma unroll (H <= 16 ? kFnIn : 7)
     for (int i = 0; i < kFnIn; ++i) acc = fmaf(w[i], inp[i], acc);
     z1[j] = acc;
   }
@@ -91,11 +92,11 @@ __device__ __forceinline__ void fn_hidden(const float* s, const float* inp, floa
 // out[j] = bias[j] + sum_k W[j][k] v[k]      (W row-major H x H)
 template <int H>
 __device__ __forceinline__ void fn_matvec(const float* W, const float* bias, const float* v, float* out) {
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
   for (int j = 0; j < H; ++j) {
     const float* w = W + j * H;
     float acc = bias ? bias[j] : 0.f;
-#pragma unroll 8
+#pragma unroll (H <= 16 ? H : 8)
     for (int k = 0; k < H; ++k) acc = fmaf(w[k], v[k], acc);
     out[j] = acc;
   }
@@ -104,10 +105,10 @@ __device__ __forceinline__ void fn_matvec(const float* W, const float* bias, con
 // out[k] = sum_j W[j][k] v[j]                (transposed product)
 template <int H>
 __device__ __forceinline__ void fn_matvec_t(const float* W, const float* v, float* out) {
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
   for (int k = 0; k < H; ++k) {
     float acc = 0.f;
-#pragma unroll 8
+#pragma unroll (H <= 16 ? H : 8)
     for (int j = 0; j < H; ++j) acc = fmaf(W[j * H + k], v[j], acc);
     out[k] = acc;
   }
@@ -139,10 +140,10 @@ __global__ void __launch_bounds__(128) field_net_forward_kernel(const FieldNetAr
     fn_encode<H>(a, i, true, inp);
     float z[H], a1[H], d1[H], a2[H], q2[H];
     fn_hidden<H>(s, inp, z);
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) fn_act<ACT>(z[j], a1[j], d1[j]);
     fn_matvec<H>(s + S::kW2, s + S::kB2, a1, z);
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) {
       float d2;
       fn_act<ACT>(z[j], a2[j], d2);
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(128) field_net_forward_kernel(const FieldNetAr
     if (a.field_grad) {
       fn_matvec_t<H>(s + S::kW2, q2, z);          // p1
       float g[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
       for (int k = 0; k < H; ++k) {
         const float q1 = d1[k] * z[k];
 #pragma unroll
@@ -183,7 +184,7 @@ __device__ __forceinline__ void fn_outer(const float* U, const float* V, int R, 
 
 template <int H>
 __device__ __forceinline__ void fn_stage(float* row, const float* v) {
-#pragma unroll 8
+#pragma unroll (H <= 16 ? H : 8)
   for (int j = 0; j < H; ++j) row[j] = v[j];
 }
 
@@ -211,10 +212,10 @@ __global__ void __launch_bounds__(128) field_net_backward_kernel(const FieldNetA
     fn_encode<H>(a, i, valid, inp);
     float t[H], a1[H], d1[H], a2[H], d2[H];
     fn_hidden<H>(s, inp, t);
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) fn_act<ACT>(t[j], a1[j], d1[j]);
     fn_matvec<H>(s + S::kW2, s + S::kB2, a1, t);
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) fn_act<ACT>(t[j], a2[j], d2[j]);
     // upstream gradients (zero for padding lanes)
     float gF[3] = {0.f, 0.f, 0.f}, g01[3] = {0.f, 0.f, 0.f};
@@ -227,10 +228,10 @@ __global__ void __launch_bounds__(128) field_net_backward_kernel(const FieldNetA
     }
     // ---- reverse sweep that produced field_grad (q2, p1, q1), and its adjoint (q1b, p1b, q2b)
     float q2[H], p1[H], p1b[H], q1b[H];
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) q2[j] = d2[j] * (s[S::kW3 + j] + s[S::kW3 + H + j] + s[S::kW3 + 2 * H + j]);
     fn_matvec_t<H>(s + S::kW2, q2, p1);
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) {
       const float* w = s + S::kW1 + j * kFnIn;
       q1b[j] = w[0] * g01[0] + w[1] * g01[1] + w[2] * g01[2];
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(128) field_net_backward_kernel(const FieldNetA
     }
     float z2b[H], w3sb[H];
     fn_matvec<H>(s + S::kW2, nullptr, p1b, t);    // q2b
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int j = 0; j < H; ++j) {
       const float w3s = s[S::kW3 + j] + s[S::kW3 + H + j] + s[S::kW3 + 2 * H + j];
       const float a2b = gF[0] * s[S::kW3 + j] + gF[1] * s[S::kW3 + H + j] + gF[2] * s[S::kW3 + 2 * H + j];
@@ -247,14 +248,14 @@ __global__ void __launch_bounds__(128) field_net_backward_kernel(const FieldNetA
     }
     float z1b[H];
     fn_matvec_t<H>(s + S::kW2, z2b, t);           // a1b
-#pragma unroll 1
+#pragma unroll (H <= 16 ? H : 1)
     for (int k = 0; k < H; ++k) z1b[k] = t[k] * d1[k] + (q1b[k] * p1[k]) * fn_dd<ACT>(a1[k], d1[k]);
     // ---- grid: d loss / d encoding -> table scatter (first-order grid backward)
     if (valid && a.g_table) {
 #pragma unroll 1
       for (int l = 0; l < 16; ++l) {
         float g0 = 0.f, g1 = 0.f;
-#pragma unroll 8
+#pragma unroll (H <= 16 ? H : 8)
         for (int j = 0; j < H; ++j) {
           g0 = fmaf(s[S::kW1 + j * kFnIn + 3 + 2 * l], z1b[j], g0);
           g1 = fmaf(s[S::kW1 + j * kFnIn + 4 + 2 * l], z1b[j], g1);
