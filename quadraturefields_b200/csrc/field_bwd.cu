@@ -135,7 +135,7 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
 
 constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4 * 32 * 3 * 4;
 
-__global__ void __launch_bounds__(128, 2) ngp_backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(128, 3) ngp_backward_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* s_w = reinterpret_cast<__half*>(smem_raw);
   __half* s_wt = s_w + kWTotal;
@@ -503,7 +503,7 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
   for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
   QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel, kBwdSmemBytes);
   int64_t tiles = ceil_div(M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 2 ? tiles : (int64_t)kNumSMs * 2);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);   // 3 CTAs/SM: 64.5 KB smem, <= 168 registers
   ngp_backward_kernel<<<blocks, 128, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   dim3 grid((unsigned)ceil_div(M, kGemmChunk), 14);
