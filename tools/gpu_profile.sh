@@ -22,7 +22,7 @@ full)
 train)
   TCMD="python tools/diag_train.py 3"
   $TCMD > gpurun_out/plain_train_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'ngp_backward_kernel|weight_grad_kernel|trace_kernel' -s 9 -c 3 -o gpurun_out/prof_train_$TAG $TCMD > gpurun_out/ncu_train_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'ngp_backward_kernel|weight_grad_kernel|trace_refill_kernel' -s 9 -c 3 -o gpurun_out/prof_train_$TAG $TCMD > gpurun_out/ncu_train_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_train_$TAG.log ;;
 esac
 ls -la gpurun_out/ | tail -12
