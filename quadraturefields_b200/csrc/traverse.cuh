@@ -175,7 +175,8 @@ __device__ __forceinline__ void traverse_single(const Ray& r, const float4* __re
 
 // ---------------------------------------------------------------- warp packet traversal
 // `wstack`: kStackDepth ints of shared memory private to the warp.  Lanes with active == false never vote.
-template <class HB, bool CULL = true>
+// SIGN >= 0: every active lane's direction has finite non-zero components with the sign pattern SIGN (see slab_signed).
+template <class HB, bool CULL = true, int SIGN = -1>
 __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const float4* __restrict__ nodes,
                                                 const float4* __restrict__ tris, int K, HB& hb, int& total,
                                                 int* __restrict__ wstack) {
@@ -190,8 +191,18 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
     const int r0 = __float_as_int(n3.x), r1 = __float_as_int(n3.y);
     float tn0, tf0, tn1, tf1;
     const float tcull = CULL ? hb.cull_distance() : inf;
-    bool h0 = active && (r0 != kEmptyRef) && slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0) && (tn0 <= tcull);
-    bool h1 = active && (r1 != kEmptyRef) && slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1) && (tn1 <= tcull);
+    // both slab tests are evaluated unconditionally (the warp issues them anyway) and masked afterwards: no
+    // divergence regions around them
+    bool s0, s1;
+    if (SIGN < 0) {
+      s0 = slab(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0);
+      s1 = slab(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1);
+    } else {
+      s0 = slab_signed<SIGN & 7>(r, n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, tn0, tf0);
+      s1 = slab_signed<SIGN & 7>(r, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, tn1, tf1);
+    }
+    bool h0 = s0 & active & (r0 != kEmptyRef) & (tn0 <= tcull);
+    bool h1 = s1 & active & (r1 != kEmptyRef) & (tn1 <= tcull);
     // leaf children: their box is the triangle's own box, so the lanes that pass go straight to Möller–Trumbore
     if (r0 < 0) { if (h0) leaf_intersect<HB>(r, tris, r0, tn0, hb, total); h0 = false; }
     if (r1 < 0) { if (h1 && tn1 <= (CULL ? hb.cull_distance() : inf)) leaf_intersect<HB>(r, tris, r1, tn1, hb, total); h1 = false; }
@@ -210,6 +221,18 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
       cur = wstack[--sp];
     }
   }
+}
+
+// Warp-uniform sign pattern of the direction components (bit k: component k negative) when every active lane has
+// finite, non-zero components of the same signs; -1 otherwise.
+__device__ __forceinline__ int warp_sign_pattern(const Ray& r, bool active) {
+  const unsigned m = __ballot_sync(0xffffffffu, active);
+  if (m == 0) return -1;
+  const bool fin = isfinite(r.ix) && isfinite(r.iy) && isfinite(r.iz) && r.ix != 0.f && r.iy != 0.f && r.iz != 0.f;
+  const int code = (r.ix < 0.f ? 1 : 0) | (r.iy < 0.f ? 2 : 0) | (r.iz < 0.f ? 4 : 0);
+  const int first = __shfl_sync(0xffffffffu, code, __ffs(m) - 1);
+  const bool ok = !active || (fin && code == first);
+  return __all_sync(0xffffffffu, ok) ? first : -1;
 }
 
 // All lanes of the warp share one origin and their directions lie within ~2.2 degrees of the first lane's (a
@@ -235,7 +258,17 @@ __device__ __forceinline__ void trace_ray(const Ray& r, bool valid, const float4
                                           int* __restrict__ wstack, int mode = 0) {
   const bool coherent = warp_is_coherent(r, valid);
   if (mode == 2 || (mode == 0 && coherent)) {
-    traverse_packet<HB, CULL>(r, valid, nodes, tris, K, hb, total, wstack);
+    switch (warp_sign_pattern(r, valid)) {   // warp-uniform: one specialisation per octant, the generic test otherwise
+      case 0: traverse_packet<HB, CULL, 0>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 1: traverse_packet<HB, CULL, 1>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 2: traverse_packet<HB, CULL, 2>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 3: traverse_packet<HB, CULL, 3>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 4: traverse_packet<HB, CULL, 4>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 5: traverse_packet<HB, CULL, 5>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 6: traverse_packet<HB, CULL, 6>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      case 7: traverse_packet<HB, CULL, 7>(r, valid, nodes, tris, K, hb, total, wstack); break;
+      default: traverse_packet<HB, CULL, -1>(r, valid, nodes, tris, K, hb, total, wstack); break;
+    }
   } else if (valid) {
     traverse_single<HB, CULL>(r, nodes, tris, K, hb, total);
   } else {
