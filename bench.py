@@ -105,6 +105,7 @@ def cpu_render_sample(sample: int, threads: int, config: str = "c2", steps: int 
     from oracle import quadfield_oracle as O
     from quadraturefields_b200 import scene as S
     torch.set_num_threads(threads)
+    O.PREFER_C = True       # OpenMP C brute force (oracle/bruteforce.c, all host threads) instead of the numpy one
     cfg = S.CONFIGS[config]
     vertices, faces = O.shell_mesh(cfg["radii"], cfg["sub"], jitter=1e-3, seed=42)
     f, cx, cy, W, H = O.pinhole_intrinsics(cfg["W"], cfg["H"], S.CAMERA_ANGLE_X)
@@ -136,16 +137,16 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 32
+    sample = 128
     rps, detail, sec = cpu_render_sample(sample, threads, args.config, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     desc = (f"{sample}x{sample} sub-grid of one {args.config} frame per step; intersect {detail.get('intersect_s', 0):.2f}s "
-            f"(brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite {detail.get('composite_s', 0):.3f}s; "
+            f"(OpenMP brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite {detail.get('composite_s', 0):.3f}s; "
             f"{detail.get('hits', 0)} hits")
     line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "note": "reference path is CUDA-only with un-installable native "
-                       "dependencies; timed here as its pure numpy/PyTorch CPU port (oracle/)"},
+                       "dependencies; timed here as its CPU port in oracle/ (OpenMP C intersector + PyTorch field and compositing)"},
             "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -349,7 +350,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_sample}x{args.cpu_sample} sub-grid of one frame ({detail.get('rays')} rays, "
                                               f"{detail.get('hits')} hits) in {sec:.1f}s: intersect {detail.get('intersect_s', 0):.1f}s "
-                                              f"(brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite "
+                                              f"(OpenMP brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite "
                                               f"{detail.get('composite_s', 0):.3f}s"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -290,10 +290,13 @@ def plane_hit_points(o, r, n, v):
     return o + t[:, None] * r
 
 
+PREFER_C = False   # bench.py's CPU legs set this: the OpenMP C restatement (identical results) is the faster CPU path
+
+
 def intersects_id(origins, vectors, vertices, faces, max_hits: int, threads: int = 1):
     """The `RayIntersector.intersects_id` contract (mesh_utils.py:87-109): flat
     (triangle_indices, ray_indices, psi) over all kept hits, ray-major in slot order."""
-    if np.asarray(faces).shape[0] > 100000 and _c_oracle() is not None:   # big meshes: the C restatement (identical results)
+    if (PREFER_C or np.asarray(faces).shape[0] > 100000) and _c_oracle() is not None:   # the C restatement (identical results)
         tri, _, count, _ = intersect_firstk_c(origins, vectors, vertices, faces, max_hits)
     else:
         tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits, threads=threads)
