@@ -285,6 +285,25 @@ int qf_vertex_displace(const float* d_cache_d, const float* d_cache_w, const int
 int qf_triangle_weight_max(const float* d_weights, int64_t stride, const int64_t* d_index_tri, int64_t M,
                            int64_t n_faces, float* d_tri_w, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (7) Occupancy-grid ray marcher: nerfacc 0.5.3 `OccGridEstimator.sampling` ->
+ * `traverse_grids` as called at utils.py:137-148, 241-285, 422-433.  Two passes over the same march:
+ * pass 0 writes the per-ray sample counts, the caller scans them (qf_hits_offsets) and allocates,
+ * pass 1 writes (ray_indices int64, t_starts, t_ends) ray-major.  binaries: (levels, rx, ry, rz) bytes.
+ * d_near_planes (N) overrides near_plane per ray (stratified sampling jitters it).
+ * ------------------------------------------------------------------------------------------ */
+#define QF_OCC_MAX_LEVELS 8
+typedef struct {
+  int32_t levels;
+  int32_t resolution[3];
+  float aabbs[QF_OCC_MAX_LEVELS][6]; /* level l: xmin ymin zmin xmax ymax zmax */
+} qf_occgrid_desc;
+int qf_occgrid_march(const qf_occgrid_desc* grid, const uint8_t* d_binaries, const float* d_origins,
+                     const float* d_dirs, int64_t n_rays, const float* d_near_planes, float near_plane,
+                     float far_plane, float step_size, float cone_angle, int pass, int32_t* d_counts,
+                     const int64_t* d_offsets, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends,
+                     void* stream);
+
 /* Optional per-stage CUDA-event timing of the fused render on its own stream (off by default).
  * qf_profile_read sums {trace, shade, composite} milliseconds recorded since the last read (synchronises). */
 int qf_profile_enable(int on);

@@ -22,6 +22,9 @@ Parity status:
     ``create_graph=True``, ``compute_field_loss`` and the autograd double backward) is PINNED
     by executing the reference class (``tests/golden/field_net.npz``); its tcnn grid encoder
     is the stand-in (unpinned, like a5).
+  * the occupancy-grid ray marcher (f-1, nerfacc 0.5.3 ``traverse_grids`` /
+    ``OccGridEstimator``): PARITY UNPINNED — restated from the published algorithm as
+    recalled (``occgrid_march``); the kernel is bit-exact against that restatement only.
   * the arithmetic that lives in absent third-party native code — Embree/OptiX
     ray-mesh intersection, tinycudann hash grid / fully fused MLP / SH, kaolin
     pack scans — is PARITY UNPINNED: it is restated from the published algorithms

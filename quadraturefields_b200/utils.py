@@ -309,6 +309,101 @@ def train_field_step(field_net, radiance_field, mesh_intersect, origins, viewdir
     return loss.detach(), positions.shape[0]
 
 
+def _occgrid_fns(radiance_field, origins, viewdirs):
+    """sigma_fn / rgb_sigma_fn of the reference's volumetric drivers (utils.py:93-122, 380-411): sample position =
+    origin + dir * (t_start + t_end) / 2."""
+    def positions(t_starts, t_ends, ray_indices):
+        return origins[ray_indices] + viewdirs[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+
+    def sigma_fn(t_starts, t_ends, ray_indices):
+        return radiance_field.query_density(positions(t_starts, t_ends, ray_indices)).squeeze(-1)
+
+    def rgb_sigma_fn(t_starts, t_ends, ray_indices):
+        rgbs, sigmas = radiance_field(positions(t_starts, t_ends, ray_indices), viewdirs, ray_indices=ray_indices)
+        return rgbs, sigmas.squeeze(-1)
+    return sigma_fn, rgb_sigma_fn
+
+
+def render_image_with_occgrid(radiance_field, estimator, rays: Rays, near_plane: float = 0.0, far_plane: float = 1e10,
+                              render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None, cone_angle: float = 0.0,
+                              alpha_thre: float = 0.0, test_chunk_size: int = 8192, timestamps=None, use_eps_loss: bool = False):
+    """utils.py:65-172: the volumetric (ray-marched) render of the NeRF stage and of the finetune step's second pass:
+    `estimator.sampling` (occupancy-grid marcher) -> `rendering` (nerfacc-style compositing).  -> (rgb, opacity, depth,
+    n_rendering_samples, extras)."""
+    from .field_rendering import rendering
+    if timestamps is not None:
+        raise NotImplementedError("dnerf timestamps are not part of the Quadfield scripts")
+    rays, rays_shape, num_rays = _flatten_rays(rays)
+    dev = estimator.binaries.device
+    chunk = torch.iinfo(torch.int32).max if radiance_field.training else test_chunk_size
+    results, extras = [], {}
+    for i in range(0, num_rays, chunk):
+        origins, viewdirs = _lib.f32(rays.origins[i:i + chunk], dev), _lib.f32(rays.viewdirs[i:i + chunk], dev)
+        sigma_fn, rgb_sigma_fn = _occgrid_fns(radiance_field, origins, viewdirs)
+        ray_indices, t_starts, t_ends = estimator.sampling(origins, viewdirs, sigma_fn=sigma_fn, near_plane=near_plane,
+                                                           far_plane=far_plane, render_step_size=render_step_size,
+                                                           stratified=radiance_field.training, cone_angle=cone_angle,
+                                                           alpha_thre=alpha_thre)
+        rgb, opacity, depth, extras = rendering(t_starts, t_ends, ray_indices, n_rays=origins.shape[0], rgb_sigma_fn=rgb_sigma_fn,
+                                                render_bkgd=render_bkgd)
+        extras["t_starts"], extras["t_ends"], extras["ray_indices"], extras["t_origins"] = t_starts, t_ends, ray_indices, origins
+        results.append([rgb, opacity, depth, len(t_starts)])
+    colors, opacities, depths, n_rendering_samples = [torch.cat(r, dim=0) if isinstance(r[0], torch.Tensor) else r
+                                                      for r in zip(*results)]
+    return (colors.view((*rays_shape[:-1], -1)), opacities.view((*rays_shape[:-1], -1)), depths.view((*rays_shape[:-1], -1)),
+            sum(n_rendering_samples), extras)
+
+
+def render_image_field_with_occgrid(radiance_field, estimator, rays: Rays, near_plane: float = 0.0, far_plane: float = 1e10,
+                                    render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
+                                    cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192, timestamps=None):
+    """utils.py:353-462 (the no-grad half of train_field.py's step): marcher samples, `rendering_field` -> near-to-far and
+    far-to-near weights, sample positions and directions.  -> (rgb, opacity, depth, n_samples, weights, weights_rev,
+    positions, dirs)."""
+    from .field_rendering import rendering_field
+    if timestamps is not None:
+        raise NotImplementedError("dnerf timestamps are not part of the Quadfield scripts")
+    rays, rays_shape, num_rays = _flatten_rays(rays)
+    dev = estimator.binaries.device
+    chunk = torch.iinfo(torch.int32).max if radiance_field.training else test_chunk_size
+    results = []
+    for i in range(0, num_rays, chunk):
+        origins, viewdirs = _lib.f32(rays.origins[i:i + chunk], dev), _lib.f32(rays.viewdirs[i:i + chunk], dev)
+        sigma_fn, rgb_sigma_fn = _occgrid_fns(radiance_field, origins, viewdirs)
+        ray_indices, t_starts, t_ends = estimator.sampling(origins, viewdirs, sigma_fn=sigma_fn, near_plane=near_plane,
+                                                           far_plane=far_plane, render_step_size=render_step_size,
+                                                           stratified=radiance_field.training, cone_angle=cone_angle,
+                                                           alpha_thre=alpha_thre, early_stop_eps=1e-4)   # utils.py:432
+        rgb, opacity, depth, weights, weights_rev = rendering_field(t_starts, t_ends, ray_indices, n_rays=origins.shape[0],
+                                                                    rgb_sigma_fn=rgb_sigma_fn, render_bkgd=render_bkgd)
+        positions = origins[ray_indices] + viewdirs[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+        results.append([rgb, opacity, depth, len(t_starts), weights, weights_rev, positions, viewdirs[ray_indices]])
+    colors, opacities, depths, n_rendering_samples, weights, weights_rev, positions, dirs = [
+        torch.cat(r, dim=0) if isinstance(r[0], torch.Tensor) else r for r in zip(*results)]
+    return (colors.view((*rays_shape[:-1], -1)), opacities.view((*rays_shape[:-1], -1)), depths.view((*rays_shape[:-1], -1)),
+            sum(n_rendering_samples), weights, weights_rev, positions, dirs)
+
+
+def train_field_step_occgrid(field_net, radiance_field, estimator, rays: Rays, optimizer, near_plane=0.0, render_step_size=5e-3,
+                             cone_angle=0.0, alpha_thre=0.0, render_bkgd=None):
+    """train_field.py:320-368 with the reference's own sampler: frozen radiance field + occupancy-grid marcher ->
+    weights / reversed weights -> quadrature Field forward with field_grad -> field loss -> backward -> optimizer step."""
+    with torch.no_grad():
+        _, _, _, n, weights, weights_rev, positions, dirs = render_image_field_with_occgrid(
+            radiance_field, estimator, rays, near_plane=near_plane, render_step_size=render_step_size, render_bkgd=render_bkgd,
+            cone_angle=cone_angle, alpha_thre=alpha_thre)
+        if n == 0:
+            return None, 0
+        _, positions = radiance_field.normalize(positions)                 # train_field.py:344
+    positions = positions - 0.5
+    _, field_grad = field_net(positions)
+    loss = field_net.compute_field_loss(weights, weights_rev=weights_rev, field_norm=field_grad, view_dirs=dirs)
+    optimizer.zero_grad(set_to_none=False)
+    loss.backward()
+    optimizer.step()
+    return loss.detach(), n
+
+
 def _flatten_rays(rays: Rays):
     rays_shape = rays.origins.shape
     if len(rays_shape) == 3:

@@ -974,3 +974,85 @@ def test_hit_tuple_prefetcher_matches_inline_trace(dev, smoke_scene):
         outs.append(rgb_a)
     rf.zero_grad()
     assert maxabs(outs[0], outs[1]) > 1e-3
+
+
+@pytest.mark.parametrize("levels,cone,near", [(1, 0.0, 0.0), (2, 0.004, 0.2), (4, 0.002, 0.05)])
+def test_occgrid_marcher_matches_oracle(dev, levels, cone, near):
+    """f-1: the occupancy-grid marcher kernel against the restated nerfacc algorithm (oracle.occgrid_march): sample
+    counts, ray indices and interval end points bit-exact (parity unpinned against nerfacc itself, which is absent)."""
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    rng = np.random.RandomState(5 + levels)
+    R = 24
+    est = OccGridEstimator([-1, -1, -1, 1, 1, 1], resolution=R, levels=levels).to(dev)
+    B = rng.rand(levels, R, R, R) < 0.15
+    est.binaries.copy_(torch.from_numpy(B))
+    assert np.array_equal(est.aabbs.cpu().numpy(), O.occgrid_aabbs([-1, -1, -1, 1, 1, 1], levels))
+    f, cx, cy, W, H = O.pinhole_intrinsics(40, 40, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((2.4, 1.9, 1.3)), W, H, f, cx, cy)
+    o2 = rng.uniform(-0.5, 0.5, size=(300, 3)).astype(np.float32)                      # rays that start inside the grid
+    d2 = rng.normal(size=(300, 3)).astype(np.float32); d2 /= np.linalg.norm(d2, axis=1, keepdims=True)
+    d2[:3] = [[1, 0, 0], [0, -1, 0], [0, 0, 1]]                                        # axis-aligned directions
+    o, d = np.concatenate([o, o2]), np.concatenate([d, d2])
+    step = 0.02
+    with np.errstate(all="ignore"):
+        r_ref, ts_ref, te_ref, cnt_ref = O.occgrid_march(o, d, B, est.aabbs.cpu().numpy(), near, 1e10, step, cone)
+    r, ts, te, offsets = est.march(T(o).to(dev), T(d).to(dev), None, near, 1e10, step, cone)
+    assert np.array_equal(np.diff(offsets.cpu().numpy()), cnt_ref) and cnt_ref.sum() > 2000
+    assert np.array_equal(r.cpu().numpy(), r_ref) and np.array_equal(ts.cpu().numpy(), ts_ref) and np.array_equal(te.cpu().numpy(), te_ref)
+    # per-ray near planes (stratified sampling jitters them)
+    nears = (near + rng.rand(o.shape[0]) * step).astype(np.float32)
+    with np.errstate(all="ignore"):
+        r_ref, ts_ref, te_ref, _ = O.occgrid_march(o, d, B, est.aabbs.cpu().numpy(), nears, 1e10, step, cone)
+    r, ts, te, _ = est.march(T(o).to(dev), T(d).to(dev), T(nears).to(dev), near, 1e10, step, cone)
+    assert np.array_equal(r.cpu().numpy(), r_ref) and np.array_equal(ts.cpu().numpy(), ts_ref)
+    e = torch.zeros((0, 3), device=dev)
+    assert est.march(e, e, None, 0.0, 1e10, step, 0.0)[0].shape == (0,)
+
+
+def test_volumetric_render_and_field_training_with_occgrid(dev, smoke_scene):
+    """f-1 end to end: occupancy grid built from the radiance field (`update_every_n_steps`), `render_image_with_occgrid`
+    (sampling with visibility culling + nerfacc-style `rendering`) against the oracle's restatement of the same pipeline,
+    and quadrature-field training steps with the reference's own sampler (train_field.py:313-368)."""
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.utils import render_image_with_occgrid, train_field_step_occgrid
+    sc = smoke_scene
+    rf = sc.radiance_field
+    step = 0.01
+    est = OccGridEstimator([-1.2, -1.2, -1.2, 1.2, 1.2, 1.2], resolution=32, levels=1).to(dev)
+    est.train()
+    torch.manual_seed(0)
+    for it in range(0, 48, 16):
+        est.update_every_n_steps(step=it, occ_eval_fn=lambda x: rf.query_density(x) * step, occ_thre=1e10)  # dense random field: threshold = mean occupancy
+    frac = float(est.binaries.float().mean())
+    assert 0.0 < frac < 1.0 and float(est.occs.max()) > 0
+    with pytest.raises(RuntimeError):
+        est.eval().update_every_n_steps(step=0, occ_eval_fn=lambda x: rf.query_density(x))
+    o, d = sc.rays(0)
+    rf.eval()
+    rgb, opacity, depth, n, extras = render_image_with_occgrid(rf, est, Rays(o, d), render_step_size=step, test_chunk_size=1 << 20)
+    # oracle: same grid, same pipeline
+    p = oracle_params(sc)
+    on, dn = o.cpu().numpy(), d.cpu().numpy()
+    r_ref, ts_ref, te_ref, _ = O.occgrid_march(on, dn, est.binaries.cpu().numpy(), est.aabbs.cpu().numpy(), 0.0, 1e10, step)
+    rr, tsr, ter = torch.from_numpy(r_ref), torch.from_numpy(ts_ref), torch.from_numpy(te_ref)
+    pos = o.cpu()[rr] + d.cpu()[rr] * (tsr + ter)[:, None] / 2.0
+    sig = O.ngp_query_density(pos, p)[0].squeeze(-1)
+    vis = O.render_visibility_from_density(tsr, ter, sig, ray_indices=rr, n_rays=on.shape[0], early_stop_eps=1e-4, alpha_thre=0.0)
+    rr, tsr, ter, pos = rr[vis], tsr[vis], ter[vis], pos[vis]
+    rgbs, sigmas = O.ngp_forward(pos, d.cpu()[rr], p)
+    c_ref, a_ref, d_ref, _ = O.rendering(tsr, ter, rr, n_rays=on.shape[0], rgbs=rgbs, sigmas=sigmas.squeeze(-1))
+    same = extras["ray_indices"].shape[0] == rr.shape[0]
+    assert abs(n - rr.shape[0]) <= max(2, rr.shape[0] // 2000)        # a sample at the 1e-4 transmittance threshold may flip
+    assert maxabs(rgb, c_ref) <= 2e-3 and maxabs(opacity, a_ref) <= 2e-3
+    if same:
+        assert torch.equal(extras["ray_indices"].cpu(), rr) and torch.equal(extras["t_starts"].cpu(), tsr)
+    # quadrature-field training with the marcher as the sampler
+    net = Field(scale=0.5, precision=16, log2_T=14, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=16,
+                num_features=2, back_prop=False, nl="elu").to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=2e-2)
+    rf.train()
+    losses = [float(train_field_step_occgrid(net, rf, est, Rays(o, d), opt, render_step_size=step)[0]) for _ in range(25)]
+    rf.eval()
+    assert losses[-1] < 0.9 * losses[0], losses[::6]

@@ -193,6 +193,33 @@ def test_field_net_golden(golden, tag):
     assert np.abs(g[f"{tag}_field_nograd"] - g[f"{tag}_field"]).max() == 0.0
 
 
+def test_occgrid_march_oracle_properties():
+    """f-1 (parity unpinned: nerfacc is absent): self-consistency of the restated marcher — every kept sample's midpoint
+    lies in an occupied cell of the finest containing level, samples of a ray sit on one regular grid, a full grid keeps
+    every sample between entry and exit, an empty grid keeps none."""
+    rng = np.random.RandomState(3)
+    aabbs = O.occgrid_aabbs([-1, -1, -1, 1, 1, 1], 2)
+    assert np.array_equal(aabbs[1], np.array([-2, -2, -2, 2, 2, 2], np.float32))
+    B = rng.rand(2, 12, 12, 12) < 0.25
+    f, cx, cy, W, H = O.pinhole_intrinsics(12, 12, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((2.4, 1.9, 1.3)), W, H, f, cx, cy)
+    step = np.float32(0.03)
+    r, ts, te, cnt = O.occgrid_march(o, d, B, aabbs, 0.0, 1e10, step)
+    assert cnt.sum() == r.shape[0] > 100 and np.all(np.diff(r) >= 0)
+    mid = o[r] + ((ts + te) / 2)[:, None] * d[r]
+    lvl = np.where(np.all(np.abs(mid) < 1, axis=1), 0, 1)
+    cell = np.clip(np.floor((mid - aabbs[lvl, :3]) / (aabbs[lvl, 3:] - aabbs[lvl, :3]) * 12).astype(int), 0, 11)
+    assert B[lvl, cell[:, 0], cell[:, 1], cell[:, 2]].mean() > 0.995           # fp32 ties at cell faces aside
+    same = r[1:] == r[:-1]
+    k = (ts[1:] - ts[:-1])[same] / step
+    assert np.abs(k - np.round(k)).max() < 1e-2 and np.allclose(te - ts, step, rtol=1e-5)
+    r_full, ts_full, te_full, cnt_full = O.occgrid_march(o, d, np.ones_like(B), aabbs, 0.0, 1e10, step)
+    assert cnt_full.min() > 0 and np.all(cnt_full >= cnt)
+    assert O.occgrid_march(o, d, np.zeros_like(B), aabbs, 0.0, 1e10, step)[0].shape[0] == 0
+    r_c, ts_c, te_c, _ = O.occgrid_march(o, d, B, aabbs, 0.2, 1e10, 0.01, cone_angle=0.004)
+    assert ts_c.min() >= 0.2 and (te_c - ts_c).max() > 0.0101 and (te_c - ts_c).min() >= 0.01 - 1e-7
+
+
 def test_grid_meta_matches_survey():
     """6 299 960 entries at T=2^19 (levels 0-4 dense), 22 565 520 at T=2^21 (0-5 dense)."""
     m = O.make_grid_meta(log2_hashmap_size=19)
