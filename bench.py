@@ -299,6 +299,7 @@ def run_ours(args):
     e2e_value = N * world * args.steps / (float(ms_e.item()) * 1e-3)
     train = None if args.no_train else run_train_steps(args, sc, dev, rank, world, barrier)
     field_train = None if args.no_train else run_field_train_steps(args, sc, dev, rank, world, barrier)
+    field_train_occ = None if args.no_train else run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier)
     clk = clocks.stop() if clocks else None
 
     if rank == 0:
@@ -344,6 +345,7 @@ def run_ours(args):
         if train is not None:
             line["train"] = train
             line["field_train"] = field_train
+            line["field_train_occgrid"] = field_train_occ
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             rps, detail, sec = cpu_render_sample(args.cpu_sample, threads, args.config)
@@ -355,6 +357,57 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier):
+    """train_field.py:297-368 with the reference's own sampler: occupancy grid built from the frozen radiance field,
+    marcher samples (~2^18 per step, the reference's target_sample_batch_size), weights / reversed weights, quadrature Field
+    forward + field_grad, field loss, double backward, Adam.  Reported per SAMPLE (the ray count follows the grid)."""
+    import torch
+    from quadraturefields_b200 import parallel as P
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.utils import train_field_step_occgrid
+    rf = sc.radiance_field
+    step_size = 5e-3                                                  # train_field.py:195
+    est = OccGridEstimator([-1.5] * 3 + [1.5] * 3, resolution=128, levels=1).to(dev)
+    est.train()
+    torch.manual_seed(7 + rank)
+    for it in range(0, 64, 16):                                       # the synthetic field is dense: threshold = mean occupancy
+        est.update_every_n_steps(step=it, occ_eval_fn=lambda x: rf.query_density(x) * step_size, occ_thre=1e10)
+    net = Field(scale=0.5, precision=16, log2_T=19, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=16,
+                num_features=2, back_prop=False, nl="elu").to(dev)
+    params = list(net.parameters())
+    opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15, fused=True)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    o_all, d_all = sc.rays(0)
+    n_rays = 1 << 16
+    steps, warm = max(5, min(args.steps, 10)), 2
+    batches = []
+    for i in range(steps + warm):
+        pi = torch.randint(0, sc.n_rays, (n_rays,), device=dev, generator=g)
+        batches.append(Rays(o_all[pi].contiguous(), d_all[pi].contiguous()))
+    for p_ in params:
+        p_.grad = torch.zeros_like(p_)
+    rf.train()
+    for i in range(warm):
+        train_field_step_occgrid(net, rf, est, batches[i], opt, render_step_size=step_size)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    samples = 0
+    for i in range(steps):
+        samples += train_field_step_occgrid(net, rf, est, batches[warm + i], opt, render_step_size=step_size)[1]
+    e1.record()
+    barrier()
+    rf.eval()
+    ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
+    return {"metric": "samples_per_sec_field_train_occgrid", "value": samples * world / (ms * 1e-3), "unit": "samples/s",
+            "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n_rays, "samples_per_step": samples / steps,
+            "occupied_fraction": float(est.binaries.float().mean()),
+            "includes": "occupancy-grid march + density for visibility culling + frozen field fwd + weights/reversed weights + "
+                        "Field fwd with field_grad + loss + double backward + Adam step (no gradient all-reduce in this leg)"}
 
 
 def run_field_train_steps(args, sc, dev, rank, world, barrier):
