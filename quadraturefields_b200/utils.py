@@ -404,6 +404,35 @@ def train_field_step_occgrid(field_net, radiance_field, estimator, rays: Rays, o
     return loss.detach(), n
 
 
+def train_finetune_step(radiance_field, field_net, estimator, mesh_intersect, mesh_finetune, rays: Rays, data, pixels, optimizer,
+                        scaling=1 / 128, near_plane=0.0, render_step_size=5e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0,
+                        bg_color="white", all_reduce=None):
+    """One step of the finetune loop (train_finetune.py:494-533): the mesh-path render with the deformation field
+    (discrete loss + regulariser, MeshFinetune accumulation), the volumetric render through the occupancy grid (smooth
+    loss), both smooth-L1 against the pixels, backward into the radiance field AND the deformation field, optimizer step.
+    `data` is the hit tuple of the batch (xyzs, dirs, index_ray, ts, index_tri, origins).
+    -> dict(loss, rgb_discrete_loss, rgb_smooth_loss, loss_reg, n_mesh_samples, n_volume_samples)."""
+    F = torch.nn.functional
+    rgb, _, _, n_mesh, _, _, _, loss_reg, _ = render_image_finetune_with_occgrid(
+        radiance_field, field_net, estimator, rays, data, near_plane=near_plane, render_step_size=render_step_size,
+        render_bkgd=render_bkgd, cone_angle=cone_angle, alpha_thre=alpha_thre, mesh_intersect=mesh_intersect,
+        mesh_finetune=mesh_finetune, scaling=scaling, bg_color=bg_color)
+    rgb_full, _, _, n_vol, _ = render_image_with_occgrid(radiance_field, estimator, rays, near_plane=near_plane,
+                                                       render_step_size=render_step_size, render_bkgd=render_bkgd,
+                                                       cone_angle=cone_angle, alpha_thre=alpha_thre)
+    pixels = pixels.to(rgb.device)
+    rgb_discrete_loss = F.smooth_l1_loss(rgb.reshape(-1, 3), pixels.reshape(-1, 3))
+    rgb_smooth_loss = F.smooth_l1_loss(rgb_full.reshape(-1, 3), pixels.reshape(-1, 3))
+    loss = (rgb_discrete_loss + rgb_smooth_loss) / 2 + loss_reg
+    optimizer.zero_grad(set_to_none=False)
+    loss.sum().backward()
+    if all_reduce is not None:
+        all_reduce()
+    optimizer.step()
+    return dict(loss=loss.detach(), rgb_discrete_loss=rgb_discrete_loss.detach(), rgb_smooth_loss=rgb_smooth_loss.detach(),
+                loss_reg=loss_reg.detach(), n_mesh_samples=n_mesh, n_volume_samples=n_vol)
+
+
 def _flatten_rays(rays: Rays):
     rays_shape = rays.origins.shape
     if len(rays_shape) == 3:

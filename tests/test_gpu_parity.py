@@ -1056,3 +1056,48 @@ def test_volumetric_render_and_field_training_with_occgrid(dev, smoke_scene):
     losses = [float(train_field_step_occgrid(net, rf, est, Rays(o, d), opt, render_step_size=step)[0]) for _ in range(25)]
     rf.eval()
     assert losses[-1] < 0.9 * losses[0], losses[::6]
+
+
+def test_finetune_loop_end_to_end(dev):
+    """train_finetune.py:494-533 + :708-718 assembled from the pieces: mesh-path render with the deformation field,
+    volumetric render through the occupancy grid, both losses, backward into both networks, optimizer step, MeshFinetune
+    accumulation, vertex update and BVH refit — the loss against a fixed target goes down and the mesh moves."""
+    from quadraturefields_b200 import scene
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.mesh_utils import MeshFinetune
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.utils import train_finetune_step
+    sc = scene.make_scene("smoke", device=dev)
+    rf, mi = sc.radiance_field, sc.mesh_intersect
+    step = float(mi.render_step_size)
+    est = OccGridEstimator([-1.2] * 3 + [1.2] * 3, resolution=32, levels=1).to(dev)
+    est.train()
+    torch.manual_seed(1)
+    for it in range(0, 48, 16):
+        est.update_every_n_steps(step=it, occ_eval_fn=lambda x: rf.query_density(x) * step, occ_thre=1e10)
+    net = Field(scale=1.5, precision=16, log2_T=14, L=16, max_res=512, min_res=16, output_dim=1, hidden_size=32,
+                num_features=2, back_prop=False, nl="relu").to(dev)                    # train_finetune.py:387-399
+    scaling = 1.0 / 128
+    mf = MeshFinetune(sc.vertices_np, sc.faces_np, scaling, device=dev)
+    opt = torch.optim.Adam([{"params": net.parameters(), "lr": 2e-2}, {"params": rf.parameters(), "lr": 1e-3}], eps=1e-15)
+    o, d = sc.rays(0)
+    tup = mi.sampling_raytrace(d, o)
+    data = [tup[0], tup[1], tup[2], tup[3], tup[4], tup[6]]
+    g = torch.Generator(device=dev).manual_seed(3)
+    pixels = torch.rand((o.shape[0], 3), device=dev, generator=g) * 0.5 + 0.25
+    rf.train()
+    hist = [train_finetune_step(rf, net, est, mi, mf, Rays(o, d), data, pixels, opt, scaling=scaling, render_step_size=step)
+            for _ in range(12)]
+    rf.eval()
+    losses = [float(h["loss"].sum()) for h in hist]
+    assert hist[0]["n_mesh_samples"] == tup[0].shape[0] and hist[0]["n_volume_samples"] > 0
+    assert losses[-1] < 0.95 * losses[0] and losses[5] < losses[0], losses      # random target colours: only the mean can be fitted
+    assert float(mf.cache_w.max()) > 1e-3 and float(mf.cache_d.abs().max()) > 0
+    v0 = mf.vertices_t.clone()
+    mf.update_faces(); mf.reset_d()
+    moved = float((mf.vertices_t - v0).abs().max())
+    assert 0 < moved <= scaling * (1 + 1e-6)
+    mi.rayintersector.update_intersector(mf.vertices_t)
+    tup2 = mi.sampling_raytrace(d, o)
+    assert abs(tup2[0].shape[0] - tup[0].shape[0]) < 0.05 * tup[0].shape[0] and maxabs(tup2[3][:100], tup[3][:100]) < 0.1
