@@ -226,7 +226,9 @@ class HitTuplePrefetcher:
         main = torch.cuda.current_stream(self.mesh_intersect.device)
         main.wait_event(ev)
         if tup is not None:
-            for t in tup:
+            # the tensors were allocated on the side stream: tell the allocator they are now in use on this one, or their
+            # memory could be handed to the next prefetch while this step's backward still reads it
+            for t in list(tup) + [getattr(tup, "offsets", None)]:
                 if isinstance(t, torch.Tensor):
                     t.record_stream(main)
         return tup
