@@ -166,6 +166,7 @@ class FramePipeline:
         self.renderer = renderer
         self.device = renderer.device
         self.streams = [torch.cuda.Stream(self.device) for _ in range(n_streams)]
+        self._hits = [torch.zeros((1,), dtype=torch.int32, device=self.device) for _ in range(n_streams)]   # one counter per stream
         self._i = 0
 
     def begin(self):
@@ -176,12 +177,20 @@ class FramePipeline:
 
     def submit(self, origins, viewdirs, out=None, after: Optional[torch.cuda.Event] = None, **kw):
         """Queue one frame; returns (out dict, stream it runs on)."""
-        st = self.streams[self._i % len(self.streams)]
+        k = self._i % len(self.streams)
+        st = self.streams[k]
         self._i += 1
+        kw.setdefault("hits_out", self._hits[k])
+        cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(st):
             if after is not None:
                 st.wait_event(after)
             res = self.renderer.render(origins, viewdirs, out=out, **kw)
+        if out is None:
+            # allocated on the pipeline stream but consumed by the caller's stream after join(): tell the allocator
+            for t in res.values():
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)
         return res, st
 
     def join(self):
