@@ -1,9 +1,16 @@
-"""`Rays` namedtuple of the reference (examples/datasets/utils.py:7)."""
-import collections
+"""Ray container of the drivers (the reference keeps the same two-field tuple in `datasets/utils.py`)."""
+from typing import Callable, NamedTuple
 
-Rays = collections.namedtuple("Rays", ("origins", "viewdirs"))
+import torch
 
 
-def namedtuple_map(fn, tup):
-    """Apply `fn` to each element of `tup` and cast to `tup`'s namedtuple."""
-    return type(tup)(*(None if x is None else fn(x) for x in tup))
+class Rays(NamedTuple):
+    """A bundle of rays: `origins` and unit `viewdirs`, both (..., 3)."""
+    origins: torch.Tensor
+    viewdirs: torch.Tensor
+
+
+def namedtuple_map(fn: Callable, tup):
+    """Rebuild `tup` (any namedtuple) with `fn` applied to every non-None field."""
+    fields = (None if field is None else fn(field) for field in tup)
+    return tup.__class__(*fields)
