@@ -186,7 +186,9 @@ def run_ours(args):
     # resident inputs: precomputed ray sets for n_views poses (rank r starts at view r so ranks render different frames)
     rays = [sc.rays(v) for v in range(n_views)]
     from quadraturefields_b200.utils import FramePipeline
-    NS = 2   # frames alternate between two streams: trace (ALU bound) of one overlaps shading (L1-gather bound) of the other
+    # frames rotate over three streams: the trace (ALU bound) of one frame overlaps the shading (L1-gather bound) of another;
+    # measured 1 / 2 / 3 / 4 streams: 0.446 / 0.376 / 0.370 / 0.370 ms per frame
+    NS = int(os.environ.get("QF_BENCH_STREAMS", "3"))
     pipe = FramePipeline(sc.renderer, NS)
     outs = [dict(rgb=torch.empty((N, 3), device=dev), opacity=torch.empty((N, 1), device=dev), depth=torch.empty((N, 1), device=dev))
             for _ in range(NS)]
