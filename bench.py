@@ -335,7 +335,7 @@ def run_ours(args):
                                   "note": "each kernel timed alone (single stream)"},
             "stage_ms_per_step_in_timed_region": {"trace": ms3o[0] / max(ncho.value, 1), "shade": shade_ms_overlapped,
                                                   "composite": ms3o[2] / max(ncho.value, 1),
-                                                  "note": "frames alternate on 2 streams, so kernels of neighbouring frames overlap"},
+                                                  "note": "frames rotate over the pipeline streams, so kernels of neighbouring frames overlap"},
             "roofline": {"bound": "hbm", "kernel": "ngp_forward_kernel<0, 10> (hash-grid gather + fused MLPs)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_hit": 512, "hits_per_launch": hits_per_launch, "peak_source": peak_src,
