@@ -394,6 +394,34 @@ def golden_finetune_step():
     return out
 
 
+def golden_sg_field():
+    """a8: the reference's `NGPRadianceFieldSGNew` (use_viewdirs=False, as every script builds it): `features`, `forward`
+    and `features_to_rgb` over the tinycudann stand-in."""
+    import radiance_fields.ngp as NGP
+    from oracle import quadfield_oracle as O
+    log2_T, L = 12, 3
+    p = O.make_ngp_params(seed=7, log2_hashmap_size=log2_T, table_scale=1e4)
+    p.base_w[1][0] = (p.base_w[1][0].abs() * 4.0).half().float()
+    torch.manual_seed(41)
+    rf = NGP.NGPRadianceFieldSGNew(aabb=p.aabb.tolist(), use_viewdirs=False, num_g_lobes=L, log2_hashmap_size=log2_T)
+    with torch.no_grad():
+        rf.mlp_base.params.copy_(torch.cat([w.flatten() for w in p.base_w] + [p.table.flatten()]))
+        for prm in rf.mlp_head.parameters():                     # larger than the default init so that the lobes matter
+            prm.mul_(3.0)
+    g = torch.Generator().manual_seed(42)
+    x = (torch.rand(500, 3, generator=g) * 2 - 1) * 1.45
+    x[:8] *= 1.2
+    d = torch.nn.functional.normalize(torch.randn(500, 3, generator=g), dim=-1)
+    with torch.no_grad():
+        feats = rf.features(x)
+        rgb, density = rf(x, d)
+        rgb2 = rf.features_to_rgb(feats[:, :-1], d)              # callers strip the density column
+    out = dict(log2_T=np.int64(log2_T), L=np.int64(L), x=x, d=d, features=feats, rgb=rgb, density=density, rgb_from_features=rgb2)
+    for k, v in rf.state_dict().items():
+        out["p_" + k] = v.half() if k == "mlp_base.params" else v
+    return out
+
+
 def _np(v):
     if isinstance(v, torch.Tensor):
         return v.detach().cpu().numpy()
@@ -406,7 +434,8 @@ def main():
     for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
                      ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
                      ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune),
-                     ("field_net", golden_field_net), ("finetune_step", golden_finetune_step)):
+                     ("field_net", golden_field_net), ("finetune_step", golden_finetune_step),
+                     ("sg_field", golden_sg_field)):
         data = {k: _np(v) for k, v in fn().items()}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

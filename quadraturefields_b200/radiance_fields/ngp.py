@@ -276,18 +276,96 @@ def spherical_gaussian_features_to_rgb(features: torch.Tensor, dirs: torch.Tenso
     return rgb
 
 
-class NGPRadianceFieldSGNew(nn.Module):
-    """The stateless part of ngp.py:284-470 the baked path uses (test_baking_texture_images.py:297-305 builds it
-    but never loads weights — SURVEY fact 5): `features_to_rgb`."""
+class _DecoderHead(nn.Module):
+    """Parameter layout of the reference's `BasicDecoder` (ngp.py:35-143): `layers.{i}` hidden `nn.Linear` + `lout`."""
 
-    def __init__(self, aabb=None, use_viewdirs: bool = False, num_g_lobes: int = 3, num_layers: int = 2,
-                 discretize: bool = False, log2_hashmap_size: int = 19, **kwargs) -> None:
+    def __init__(self, input_dim: int, output_dim: int, num_layers: int, hidden_dim: int, bias: bool = True):
         super().__init__()
+        self.layers = nn.ModuleList([nn.Linear(input_dim if i == 0 else hidden_dim, hidden_dim, bias=bias) for i in range(num_layers)])
+        self.lout = nn.Linear(hidden_dim, output_dim, bias=True)
+
+    def forward(self, x):
+        for layer in self.layers:
+            x = torch.relu(layer(x))
+        return self.lout(x)
+
+
+class NGPRadianceFieldSGNew(NGPRadianceField):
+    """The spherical-Gaussian radiance field (ngp.py:284-470) as every Quadfield script builds it (`use_viewdirs=False`):
+    hash grid + 64-wide base MLP -> (sigma, 15 features) on the fused kernel, a torch fp32 `BasicDecoder` head
+    15 -> 64 x num_layers -> 3 + 7 L (plain library GEMMs, as in the reference), and the SG mixture
+    rgb = sigmoid(diffuse + sum_l c_l exp(|lambda_l| (a_l . d - 1))) on `qf_sg_features_to_rgb`.
+    State-dict keys: `aabb`, `mlp_base.params`, `mlp_head.layers.{i}.weight/bias`, `mlp_head.lout.weight/bias`.
+    Inference only: `features`, `features_to_rgb`, `query_density`, `forward` run without autograd (fitting the SG
+    field, train_fit_sg.py, needs the base MLP's feature gradient — not built)."""
+
+    def __init__(self, aabb=None, num_dim: int = 3, use_viewdirs: bool = False, density_activation=None, unbounded: bool = False,
+                 base_resolution: int = 16, max_resolution: int = 4096, geo_feat_dim: int = 15, n_levels: int = 16,
+                 log2_hashmap_size: int = 19, num_g_lobes: int = 3, hidden_size: int = 64, num_layers: int = 2,
+                 output_activation: str = "sigmoid", discretize: bool = False, seed: int = 1337) -> None:
+        if use_viewdirs:
+            raise NotImplementedError("every Quadfield script builds the SG field with use_viewdirs=False")
         if discretize:
             raise NotImplementedError("discretize=True (fake quantisation during SG fitting) is outside the render path")
-        self.num_g_lobes = num_g_lobes
-        self.discretize = discretize
+        if aabb is None:
+            aabb = [-1.5, -1.5, -1.5, 1.5, 1.5, 1.5]
+        super().__init__(aabb=aabb, num_dim=num_dim, use_viewdirs=True, unbounded=unbounded, base_resolution=base_resolution,
+                         max_resolution=max_resolution, geo_feat_dim=geo_feat_dim, n_levels=n_levels,
+                         log2_hashmap_size=log2_hashmap_size, seed=seed)
+        self.use_viewdirs = False
+        self.num_g_lobes, self.discretize, self.output_activation = num_g_lobes, discretize, output_activation
+        # the tcnn head of the parent is replaced by the reference's torch decoder; the fused kernel only needs the base
+        # matrices, so the native handle is fed zeros for the (unused) tcnn head image
+        del self.mlp_head
+        del self.direction_encoding
+        torch.manual_seed(seed)
+        self.mlp_head = _DecoderHead(geo_feat_dim, 3 + num_g_lobes * 7, num_layers, hidden_size)
+        self.register_buffer("_zero_head", torch.zeros(sum(o * i for o, i in _HEAD_SHAPES)), persistent=False)
+
+    def _native(self):
+        p_base = self.mlp_base.params
+        if not p_base.is_cuda:
+            raise RuntimeError("NGPRadianceFieldSGNew runs on CUDA only: call .to('cuda') first (no CPU path)")
+        key = (p_base.data_ptr(), p_base._version, self.aabb._version)
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        lib = _lib.load()
+        aabb = self.aabb.detach().cpu().tolist()
+        for i in range(6):
+            self._desc.aabb[i] = float(aabb[i])
+        base = p_base.detach()
+        table, base_w = base[self._n_base:], base[: self._n_base]
+        st = _lib.stream(p_base.device)
+        if self._handle is None or key[0] != self._handle_key[0]:
+            self._free()
+            h = C.c_void_p()
+            _lib.check(lib.qf_ngp_create(C.byref(self._desc), _lib.ptr(table), self._n_entries, _lib.ptr(base_w),
+                                         _lib.ptr(self._zero_head), st, C.byref(h)), "qf_ngp_create")
+            self._handle = h
+        else:
+            _lib.check(lib.qf_ngp_update(self._handle, _lib.ptr(table), _lib.ptr(base_w), _lib.ptr(self._zero_head), st), "qf_ngp_update")
+        self._handle_key = key
+        return self._handle
+
+    @torch.no_grad()
+    def features(self, x):
+        """ngp.py:445-454 -> (M, 3 + 7 L + 1): decoder output, then the density."""
+        density, embedding = self.query_density(x, return_feat=True)
+        feats = self.mlp_head(embedding.reshape(-1, self.geo_feat_dim))
+        return torch.cat([feats.reshape(list(embedding.shape[:-1]) + [self.num_g_lobes * 7 + 3]), density], dim=-1)
 
     @torch.no_grad()
     def features_to_rgb(self, features, dir):
+        """ngp.py:456-461 (discretize=False)."""
         return spherical_gaussian_features_to_rgb(features, dir, self.num_g_lobes)
+
+    @torch.no_grad()
+    def forward(self, positions: torch.Tensor, directions: torch.Tensor = None, ray_indices: torch.Tensor = None):
+        """ngp.py:463-470 -> (rgb (M,3), density (M,1)).  `ray_indices` (extension): directions are per ray."""
+        density, embedding = self.query_density(positions, return_feat=True)
+        feats = self.mlp_head(embedding.reshape(-1, self.geo_feat_dim))
+        d = directions.reshape(-1, 3)
+        if ray_indices is not None:
+            d = d[ray_indices]
+        rgb = spherical_gaussian_features_to_rgb(feats, d, self.num_g_lobes)
+        return rgb, density

@@ -196,6 +196,6 @@ def make_scene(name: str = "c2", device="cuda", seed: int = 42, build_field: boo
                                            lambda_thres=cfg.get("lambda_thres", 7.5), device=dev)
         sc.extras["uv"] = random_uv(vertices.shape[0], seed + 2)
         sc.uv_scaled = scale_uv(sc.extras["uv"], S)
-        sc.extras["sg_field"] = NGPRadianceFieldSGNew(num_g_lobes=L)
+        sc.extras["sg_field"] = NGPRadianceFieldSGNew(num_g_lobes=L, log2_hashmap_size=12)
         sc.baked_renderer = MeshRenderer(sc.mesh_intersect, compressor=sc.compressor, uv=sc.uv_scaled)
     return sc

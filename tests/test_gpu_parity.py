@@ -282,7 +282,7 @@ def test_texture_decode_and_sg_golden(dev, golden):
         ref = T(g[k + "_feats"])
         assert feats.shape == ref.shape
         assert float(((feats.cpu() - ref).abs() / ref.abs().clamp_min(1.0)).max()) <= 2e-6
-        rgb = NGPRadianceFieldSGNew(num_g_lobes=L).features_to_rgb(T(g[k + "_feats"])[:, :-1].to(dev), T(g[k + "_dirs"]).to(dev))
+        rgb = NGPRadianceFieldSGNew(num_g_lobes=L, log2_hashmap_size=12).features_to_rgb(T(g[k + "_feats"])[:, :-1].to(dev), T(g[k + "_dirs"]).to(dev))
         assert maxabs(rgb, g[k + "_rgb"]) <= 2e-6
         assert maxabs(fc.features_to_rgb(feats[:, :-1], T(g[k + "_dirs"]).to(dev)), g[k + "_rgb"]) <= 1e-5
 
@@ -1101,3 +1101,29 @@ def test_finetune_loop_end_to_end(dev):
     mi.rayintersector.update_intersector(mf.vertices_t)
     tup2 = mi.sampling_raytrace(d, o)
     assert abs(tup2[0].shape[0] - tup[0].shape[0]) < 0.05 * tup[0].shape[0] and maxabs(tup2[3][:100], tup[3][:100]) < 0.1
+
+
+def test_sg_field_golden(dev, golden):
+    """a8: the full spherical-Gaussian radiance field (hash grid + base MLP on the fused kernel, fp32 decoder head, SG
+    mixture kernel) against the reference `NGPRadianceFieldSGNew` executed over the tinycudann stand-in: `features`,
+    `forward`, `features_to_rgb`, and the reference's state-dict keys."""
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceFieldSGNew
+    g = golden("sg_field")
+    rf = NGPRadianceFieldSGNew(aabb=[-1.5] * 3 + [1.5] * 3, use_viewdirs=False, num_g_lobes=int(g["L"]), log2_hashmap_size=int(g["log2_T"]))
+    sd = {k[2:]: torch.from_numpy(np.asarray(v, dtype=np.float32)) for k, v in g.items() if k.startswith("p_")}
+    assert set(sd) == set(rf.state_dict())
+    rf.load_state_dict(sd)
+    rf = rf.to(dev)
+    x, d = T(g["x"]).to(dev), T(g["d"]).to(dev)
+    feats = rf.features(x)
+    assert feats.shape == g["features"].shape
+    # decoder outputs: fp16 grid/MLP features in, fp32 decoder; density column relative
+    assert maxabs(feats[:, :-1], g["features"][:, :-1]) <= 5e-3 * float(np.abs(g["features"][:, :-1]).max())
+    dens_ref = T(g["density"])
+    assert float(((feats[:, -1:].cpu() - dens_ref).abs() / dens_ref.clamp_min(1e-3)).max()) <= 2e-4
+    rgb, density = rf(x, d)
+    assert maxabs(rgb, g["rgb"]) <= TOL_IMG
+    assert float(((density.cpu() - dens_ref).abs() / dens_ref.clamp_min(1e-3)).max()) <= 2e-4
+    assert maxabs(rf.features_to_rgb(T(g["features"])[:, :-1].to(dev), d), g["rgb_from_features"]) <= 1e-6
+    ridx = torch.arange(x.shape[0], device=dev)
+    assert maxabs(rf(x, d, ray_indices=ridx)[0], rgb) == 0.0
