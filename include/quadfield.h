@@ -147,6 +147,12 @@ int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions, const floa
                            const float* d_grad_density, float* d_grad_table, float* d_grad_base_w,
                            float* d_grad_head_w, float* d_grad_positions, void* d_workspace, size_t workspace_bytes,
                            void* stream);
+/* Backward of `query_density(x, return_feat=True)` (ngp.py:402-428): upstream gradients of sigma (M, may be NULL) and of
+ * the 15 geo features (M,15) into the hash table and the base MLP (d_grad_base_w: 64x32 + 16x64), optionally the
+ * positions.  Workspace as qf_ngp_backward.  The spherical-Gaussian field (ngp.py:284-470) trains through this. */
+int qf_ngp_backward_features(const qf_ngp* f, const float* d_positions, int64_t M, const float* d_grad_density,
+                             const float* d_grad_feat, float* d_grad_table, float* d_grad_base_w,
+                             float* d_grad_positions, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (4) Baked spherical-Gaussian texture path.
@@ -171,6 +177,11 @@ int qf_texture_compress(const float* d_features, int64_t M, int num_lobes, int c
 /* features_to_rgb: features (M, 3+7L[+1]) with row stride `stride` floats, dirs (M,3) -> rgb (M,3) */
 int qf_sg_features_to_rgb(const float* d_features, int64_t stride, int num_lobes, const float* d_dirs, int64_t M,
                           float* d_rgb, void* stream);
+/* its backward with respect to the feature rows (the SG field is fitted through it, train_fit_sg.py):
+ * grad_features (M, >= 3+7L) with row stride `grad_stride`; directions get no gradient. */
+int qf_sg_features_to_rgb_backward(const float* d_features, int64_t stride, int num_lobes, const float* d_dirs,
+                                   int64_t M, const float* d_grad_rgb, float* d_grad_features, int64_t grad_stride,
+                                   void* stream);
 /* utils.py:1055-1063: hit points + triangle ids -> texel (M,2) int64; uv_scaled (V,2) fp32 */
 int qf_hit_texels(const qf_mesh* mesh, const float* d_points, const int64_t* d_index_tri, int64_t M,
                   const float* d_uv_scaled, int texture_size, int64_t* d_texels, void* stream);

@@ -55,6 +55,8 @@ _SIGS = {
     "qf_texture_decode": (_I, [_P, _P, _L, _P, _P]),
     "qf_texture_compress": (_I, [_P, _L, _I, _I, _F, _P, _I, _P, _P, C.POINTER(_P), C.POINTER(_P), _P]),
     "qf_sg_features_to_rgb": (_I, [_P, _L, _I, _P, _L, _P, _P]),
+    "qf_sg_features_to_rgb_backward": (_I, [_P, _L, _I, _P, _L, _P, _P, _L, _P]),
+    "qf_ngp_backward_features": (_I, [_P, _P, _L, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_grid_create": (_I, [_P, _P, _L, _P, C.POINTER(_P)]),
     "qf_field_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "qf_field_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

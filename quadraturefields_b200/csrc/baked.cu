@@ -139,6 +139,45 @@ __global__ void sg_rgb_kernel(const float* __restrict__ feats, int64_t stride, i
   rgb[3 * i] = o[0]; rgb[3 * i + 1] = o[1]; rgb[3 * i + 2] = o[2];
 }
 
+// backward of sg_rgb with respect to the feature row (diffuse, per lobe axis / lambda / colour); thread per sample
+__global__ void sg_rgb_backward_kernel(const float* __restrict__ feats, int64_t stride, int L, const float* __restrict__ dirs,
+                                       int64_t M, const float* __restrict__ g_rgb, float* __restrict__ g_feats, int64_t g_stride) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float* f = feats + i * stride;
+  const float dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
+  float u[3] = {f[0], f[1], f[2]};
+  for (int l = 0; l < L; ++l) {
+    const float* o = f + 3 + 7 * l;
+    const float n = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+    const float e = expf(fabsf(o[3]) * ((o[0] * dx + o[1] * dy + o[2] * dz) / n - 1.0f));
+    u[0] += o[4] * e; u[1] += o[5] * e; u[2] += o[6] * e;
+  }
+  float gu[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float sgm = 1.0f / (1.0f + expf(-u[c]));
+    gu[c] = g_rgb[3 * i + c] * sgm * (1.0f - sgm);
+  }
+  float* go = g_feats + i * g_stride;
+  go[0] = gu[0]; go[1] = gu[1]; go[2] = gu[2];
+  for (int l = 0; l < L; ++l) {
+    const float* o = f + 3 + 7 * l;
+    float* g = go + 3 + 7 * l;
+    const float n = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+    const float ax = o[0] / n, ay = o[1] / n, az = o[2] / n;
+    const float cosv = ax * dx + ay * dy + az * dz;
+    const float lam = fabsf(o[3]);
+    const float e = expf(lam * (cosv - 1.0f));
+    g[4] = gu[0] * e; g[5] = gu[1] * e; g[6] = gu[2] * e;                    // d colour
+    const float se = (gu[0] * o[4] + gu[1] * o[5] + gu[2] * o[6]) * e;         // dL/d(exponent)
+    g[3] = se * (cosv - 1.0f) * (o[3] > 0.f ? 1.0f : (o[3] < 0.f ? -1.0f : 0.0f));   // d lambda through |.|
+    const float gc = se * lam;                                                  // dL/d(cos)
+    // d(a/|a| . d)/da = (d - a_hat (a_hat . d)) / |a|
+    g[0] = gc * (dx - ax * cosv) / n; g[1] = gc * (dy - ay * cosv) / n; g[2] = gc * (dz - az * cosv) / n;
+  }
+}
+
 __global__ void hit_texels_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces,
                                   const float* __restrict__ uv, const float* __restrict__ points,
                                   const int64_t* __restrict__ tri, int64_t M, int S, int64_t* __restrict__ out) {
@@ -295,6 +334,20 @@ extern "C" int qf_hit_texels(const qf_mesh* mesh, const float* d_points, const i
   if (M == 0) return QF_OK;
   hit_texels_kernel<<<(int)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(mesh->d_vertices, mesh->d_faces, d_uv_scaled,
                                                                              d_points, d_index_tri, M, texture_size, d_texels);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+
+extern "C" int qf_sg_features_to_rgb_backward(const float* d_features, int64_t stride, int num_lobes, const float* d_dirs,
+                                              int64_t M, const float* d_grad_rgb, float* d_grad_features, int64_t grad_stride,
+                                              void* stream) {
+  QF_REQUIRE(num_lobes >= 0 && num_lobes <= QF_MAX_LOBES && stride >= 3 + 7 * num_lobes && grad_stride >= 3 + 7 * num_lobes,
+             "qf_sg_features_to_rgb_backward: lobes=%d stride=%lld grad_stride=%lld", num_lobes, (long long)stride, (long long)grad_stride);
+  if (M == 0) return QF_OK;
+  QF_REQUIRE(d_features && d_dirs && d_grad_rgb && d_grad_features, "qf_sg_features_to_rgb_backward: NULL argument");
+  sg_rgb_backward_kernel<<<(int)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(d_features, stride, num_lobes, d_dirs, M, d_grad_rgb,
+                                                                                  d_grad_features, grad_stride);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

@@ -53,6 +53,7 @@ struct BwdArgs {
   int64_t M;
   const float* g_rgb;       // (M,3)
   const float* g_sigma;     // (M) or NULL
+  const float* g_feat;      // (M,15) dL/d(geo features), FEAT mode only
   const float* g_absmax;    // device scalar: max |g_rgb| (for the fp16 dynamic-range scale)
   float2* g_table;          // (n_entries) float2, atomically accumulated
   __half* act;              // (M, kActRow)
@@ -135,6 +136,10 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
 
 constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4 * 32 * 3 * 4;
 
+// FEAT = false: backward of the full forward (rgb, sigma).  FEAT = true: backward of `query_density(return_feat=True)`
+// — the upstream gradient arrives at the 16 outputs of the base MLP (sigma and the 15 geo features), the tcnn head is
+// not part of the graph (the spherical-Gaussian field feeds the features to a torch decoder instead).
+template <bool FEAT>
 __global__ void __launch_bounds__(128, 3) ngp_backward_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* s_w = reinterpret_cast<__half*>(smem_raw);
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(128, 3) ngp_backward_kernel(const BwdArgs a) {
     uint32_t* row32 = reinterpret_cast<uint32_t*>(tile + lane * kTileStride);
     encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) { row32[l] = h2; });
     uint4* row = reinterpret_cast<uint4*>(row32);
-    {
+    if (!FEAT) {
       float dx = 0.f, dy = 0.f, dz = 1.f;
       if (valid) {
         int64_t r = a.ray64 ? __ldg(a.ray64 + i) : i;
@@ -222,58 +227,73 @@ __global__ void __launch_bounds__(128, 3) ngp_backward_kernel(const BwdArgs a) {
       for (int n = 0; n < 2; ++n) acc2[n][0] = acc2[n][1] = acc2[n][2] = acc2[n][3] = 0.f;
       layer<4, 2>(acc2, af, s_w + kW2, kS64, g, t);
       const float h0_lo = acc2[0][0], h0_hi = acc2[0][2];   // meaningful on t == 0
-      uint32_t a3[2][4];
-      a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
-      a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
-      a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
-      a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
-      a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
-      store_a<2>(a.act, kActRow, 96, r_lo, r_hi, M, a3, t);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
-      const unsigned mask3 = relu_mask8(acc);
-      c_to_a<true>(af, acc);
-      store_a<4>(a.act, kActRow, 128, r_lo, r_hi, M, af, t);
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<4, 8>(acc, af, s_w + kW4, kS64, g, t);
-      const unsigned mask4 = relu_mask8(acc);
-      c_to_a<true>(af, acc);
-      store_a<4>(a.act, kActRow, 192, r_lo, r_hi, M, af, t);
-      float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-      layer<4, 1>(acc5, af, s_w + kW5, kS64, g, t);
-      // ================= backward =================
-      // dL/d rgb logits = g_rgb * rgb (1 - rgb); lane t owns logit columns 2t, 2t+1 of rows g and g+8
-      uint32_t ga[1][4] = {{0u, 0u, 0u, 0u}};
-      if (t < 2) {
-        auto dsig = [gscale](float v) { float s = 1.0f / (1.0f + __expf(-v)); return gscale * s * (1.0f - s); };
-        float gl0 = 0.f, gl1 = 0.f, gh0 = 0.f, gh1 = 0.f;
-        if (r_lo < M) { gl0 = a.g_rgb[3 * r_lo + 2 * t] * dsig(acc5[0][0]); if (t == 0) gl1 = a.g_rgb[3 * r_lo + 1] * dsig(acc5[0][1]); }
-        if (r_hi < M) { gh0 = a.g_rgb[3 * r_hi + 2 * t] * dsig(acc5[0][2]); if (t == 0) gh1 = a.g_rgb[3 * r_hi + 1] * dsig(acc5[0][3]); }
-        ga[0][0] = pack_h2(gl0, gl1);
-        ga[0][1] = pack_h2(gh0, gh1);
-      }
-      store_a<1>(a.grd, kGrdRow, 208, r_lo, r_hi, M, ga, t);
-      // head L3:  dL/dh3 = g_o W5, masked
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<1, 8>(acc, ga, s_wt + kT5, kT24, g, t);
-      apply_mask8(acc, mask4);
-      store_c<8>(a.grd, kGrdRow, 144, r_lo, r_hi, M, acc, t);
-      c_to_a<false>(af, acc);
-      // head L2:  dL/dh2 = g_h3 W4, masked
-#pragma unroll
-      for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-      layer<4, 8>(acc, af, s_wt + kT4, kS64, g, t);
-      apply_mask8(acc, mask3);
-      store_c<8>(a.grd, kGrdRow, 80, r_lo, r_hi, M, acc, t);
-      c_to_a<false>(af, acc);
-      // head L1: only the [pad | feat] half of the input carries gradient on to the base MLP
       float gin[2][4];
 #pragma unroll
       for (int n = 0; n < 2; ++n) gin[n][0] = gin[n][1] = gin[n][2] = gin[n][3] = 0.f;
-      layer<4, 2>(gin, af, s_wt + kT3 + 16 * kS64, kS64, g, t);
+      if (!FEAT) {
+        uint32_t a3[2][4];
+        a3[0][0] = lds32(ta + 32); a3[0][1] = lds32(tb + 32); a3[0][2] = lds32(ta + 40); a3[0][3] = lds32(tb + 40);
+        a3[1][0] = pack_h2(t == 0 ? 1.0f : acc2[0][0], acc2[0][1]);
+        a3[1][1] = pack_h2(t == 0 ? 1.0f : acc2[0][2], acc2[0][3]);
+        a3[1][2] = pack_h2(acc2[1][0], acc2[1][1]);
+        a3[1][3] = pack_h2(acc2[1][2], acc2[1][3]);
+        store_a<2>(a.act, kActRow, 96, r_lo, r_hi, M, a3, t);
+  #pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        layer<2, 8>(acc, a3, s_w + kW3, kS32, g, t);
+        const unsigned mask3 = relu_mask8(acc);
+        c_to_a<true>(af, acc);
+        store_a<4>(a.act, kActRow, 128, r_lo, r_hi, M, af, t);
+  #pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        layer<4, 8>(acc, af, s_w + kW4, kS64, g, t);
+        const unsigned mask4 = relu_mask8(acc);
+        c_to_a<true>(af, acc);
+        store_a<4>(a.act, kActRow, 192, r_lo, r_hi, M, af, t);
+        float acc5[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+        layer<4, 1>(acc5, af, s_w + kW5, kS64, g, t);
+        // ================= backward =================
+        // dL/d rgb logits = g_rgb * rgb (1 - rgb); lane t owns logit columns 2t, 2t+1 of rows g and g+8
+        uint32_t ga[1][4] = {{0u, 0u, 0u, 0u}};
+        if (t < 2) {
+          auto dsig = [gscale](float v) { float s = 1.0f / (1.0f + __expf(-v)); return gscale * s * (1.0f - s); };
+          float gl0 = 0.f, gl1 = 0.f, gh0 = 0.f, gh1 = 0.f;
+          if (r_lo < M) { gl0 = a.g_rgb[3 * r_lo + 2 * t] * dsig(acc5[0][0]); if (t == 0) gl1 = a.g_rgb[3 * r_lo + 1] * dsig(acc5[0][1]); }
+          if (r_hi < M) { gh0 = a.g_rgb[3 * r_hi + 2 * t] * dsig(acc5[0][2]); if (t == 0) gh1 = a.g_rgb[3 * r_hi + 1] * dsig(acc5[0][3]); }
+          ga[0][0] = pack_h2(gl0, gl1);
+          ga[0][1] = pack_h2(gh0, gh1);
+        }
+        store_a<1>(a.grd, kGrdRow, 208, r_lo, r_hi, M, ga, t);
+        // head L3:  dL/dh3 = g_o W5, masked
+  #pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        layer<1, 8>(acc, ga, s_wt + kT5, kT24, g, t);
+        apply_mask8(acc, mask4);
+        store_c<8>(a.grd, kGrdRow, 144, r_lo, r_hi, M, acc, t);
+        c_to_a<false>(af, acc);
+        // head L2:  dL/dh2 = g_h3 W4, masked
+  #pragma unroll
+        for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        layer<4, 8>(acc, af, s_wt + kT4, kS64, g, t);
+        apply_mask8(acc, mask3);
+        store_c<8>(a.grd, kGrdRow, 80, r_lo, r_hi, M, acc, t);
+        c_to_a<false>(af, acc);
+        // head L1: only the [pad | feat] half of the input carries gradient on to the base MLP
+        layer<4, 2>(gin, af, s_wt + kT3 + 16 * kS64, kS64, g, t);
+      } else {
+        // upstream gradient of the 15 geo features: output column c = n*8 + 2t + q holds feature c-1 (column 0 = logit)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int col = n * 8 + 2 * t + q;
+            if (col >= 1) {
+              if (r_lo < M) gin[n][q] = gscale * a.g_feat[r_lo * 15 + col - 1];
+              if (r_hi < M) gin[n][2 + q] = gscale * a.g_feat[r_hi * 15 + col - 1];
+            }
+          }
+        }
+      }
       if (t == 0) {  // column 0 of the base output is the density logit: dL/dh0 = dL/dsigma * exp(min(h0-1, 15)) * selector
         float gs_lo = (a.g_sigma && r_lo < M) ? a.g_sigma[r_lo] : 0.f, gs_hi = (a.g_sigma && r_hi < M) ? a.g_sigma[r_hi] : 0.f;
         gin[0][0] = ((selmask >> (mt * 16 + g)) & 1u) ? gscale * gs_lo * expf(fminf(h0_lo - 1.0f, 15.0f)) : 0.f;
@@ -440,7 +460,7 @@ __global__ void unpack_weight_grads_kernel(const float* __restrict__ stage, cons
       v = stage[kW3 + r * kS32 + kc];
     } else if (j < 2048 + 4096) { int q = j - 2048; v = stage[kW4 + (q / 64) * kS64 + (q % 64)]; }
     else { int q = j - 2048 - 4096; v = stage[kW5 + (q / 64) * kS64 + (q % 64)]; }
-    g_head[j] += v * ginv;
+    if (g_head) g_head[j] += v * ginv;
   }
 }
 
@@ -501,15 +521,56 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
   a.act = act; a.grd = grd;
   a.g_pos = d_grad_positions;
   for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
-  QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel, kBwdSmemBytes);
+  QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel<false>, kBwdSmemBytes);
   int64_t tiles = ceil_div(M, 128);
   int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);   // 3 CTAs/SM: 64.5 KB smem, <= 168 registers
-  ngp_backward_kernel<<<blocks, 128, kBwdSmemBytes, st>>>(a);
+  ngp_backward_kernel<false><<<blocks, 128, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   dim3 grid((unsigned)ceil_div(M, kGemmChunk), 14);
   weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
   QF_LAUNCH_CHECK();
   unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, d_grad_head_w);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+
+// Backward of `query_density(x, return_feat=True)` (ngp.py:402-428): gradients of sigma (M) and of the 15 geo features
+// (M,15) into the hash table and the base MLP (and optionally the positions).  The spherical-Gaussian field trains through
+// this (train_fit_sg.py: features -> torch decoder -> SG mixture -> composite).  Same workspace as qf_ngp_backward.
+extern "C" int qf_ngp_backward_features(const qf_ngp* f, const float* d_positions, int64_t M, const float* d_grad_density,
+                                        const float* d_grad_feat, float* d_grad_table, float* d_grad_base_w,
+                                        float* d_grad_positions, void* d_workspace, size_t workspace_bytes, void* stream) {
+  if (M == 0) return QF_OK;
+  QF_REQUIRE(f && d_positions && d_grad_feat && d_grad_table && d_grad_base_w && d_workspace, "qf_ngp_backward_features: NULL argument");
+  QF_REQUIRE(f->d_weights, "qf_ngp_backward_features: this field handle holds a grid only (qf_grid_create)");
+  QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward_features: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)d_workspace;
+  float* gmax = (float*)ws; ws += 256;
+  QF_CUDA_CHECK(cudaMemsetAsync(gmax, 0, sizeof(float), st));
+  absmax_kernel<<<kNumSMs * 2, 256, 0, st>>>(d_grad_feat, 15 * M, gmax);
+  __half* wt = (__half*)ws; ws += align256b(sizeof(__half) * kTTotal);
+  float* stage = (float*)ws; ws += align256b(sizeof(float) * kWTotal);
+  __half* act = (__half*)ws; ws += align256b(sizeof(__half) * (size_t)M * kActRow);
+  __half* grd = (__half*)ws;
+  transpose_weights_kernel<<<(int)ceil_div(kTTotal, 256), 256, 0, st>>>(f->d_weights, wt);
+  QF_CUDA_CHECK(cudaMemsetAsync(stage, 0, sizeof(float) * kWTotal, st));
+  BwdArgs a = {};
+  a.desc = f->desc; a.table = f->d_table; a.weights = f->d_weights; a.weights_t = wt;
+  a.pos = d_positions; a.pos_stride = 3; a.M = M;
+  a.g_sigma = d_grad_density; a.g_feat = d_grad_feat; a.g_absmax = gmax; a.g_table = reinterpret_cast<float2*>(d_grad_table);
+  a.act = act; a.grd = grd; a.g_pos = d_grad_positions;
+  for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
+  QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel<true>, kBwdSmemBytes);
+  int64_t tiles = ceil_div(M, 128);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);
+  ngp_backward_kernel<true><<<blocks, 128, kBwdSmemBytes, st>>>(a);
+  QF_LAUNCH_CHECK();
+  dim3 grid((unsigned)ceil_div(M, kGemmChunk), 5);        // items 0..4: the two base layers
+  weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
+  QF_LAUNCH_CHECK();
+  unpack_weight_grads_kernel<<<(int)ceil_div(3072, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, nullptr);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

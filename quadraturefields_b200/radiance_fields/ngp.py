@@ -96,6 +96,46 @@ class _NGPForwardFn(torch.autograd.Function):
         return None, g_pos, None, None, g_base, g_head
 
 
+class _NGPDensityFeatFn(torch.autograd.Function):
+    """`query_density(x, return_feat=True)` under autograd: gradients of sigma and of the 15 geo features reach the flat
+    `mlp_base.params` tensor ([MLP weights | grid table]) and, when requested, the positions."""
+
+    @staticmethod
+    def forward(ctx, field, positions, base_params):
+        lib = _lib.load()
+        h = field._native()
+        pos = _lib.f32(positions.detach().reshape(-1, 3))
+        M = pos.shape[0]
+        density = torch.empty((M, 1), dtype=torch.float32, device=pos.device)
+        feat = torch.empty((M, 15), dtype=torch.float32, device=pos.device)
+        _lib.check(lib.qf_ngp_query_density(h, _lib.ptr(pos), M, _lib.ptr(density), _lib.ptr(feat), _lib.stream(pos.device)),
+                   "qf_ngp_query_density")
+        ctx.field, ctx.pos_shape = field, positions.shape
+        ctx.save_for_backward(pos)
+        return density, feat
+
+    @staticmethod
+    def backward(ctx, g_density, g_feat):
+        lib = _lib.load()
+        field = ctx.field
+        (pos,) = ctx.saved_tensors
+        M, dev = pos.shape[0], pos.device
+        h = field._native()
+        g_base = torch.zeros_like(field.mlp_base.params)
+        g_pos = torch.zeros((M, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        if M:
+            gf = _lib.f32(g_feat) if g_feat is not None else torch.zeros((M, 15), device=dev)
+            gd = _lib.f32(g_density.reshape(-1)) if g_density is not None else None
+            nb = field._n_base
+            ws = _lib.workspace(dev, lib.qf_ngp_backward_workspace_bytes(M), "ngp_bwd")
+            _lib.check(lib.qf_ngp_backward_features(h, _lib.ptr(pos), M, _lib.ptr(gd), _lib.ptr(gf), _lib.ptr(g_base[nb:]),
+                                                    _lib.ptr(g_base[:nb]), _lib.ptr(g_pos), _lib.ptr(ws), ws.numel(),
+                                                    _lib.stream(dev)), "qf_ngp_backward_features")
+        if g_pos is not None:
+            g_pos = g_pos.view(ctx.pos_shape)
+        return None, g_pos, g_base
+
+
 _BASE_SHAPES = [(64, 32), (16, 64)]
 _HEAD_SHAPES = [(64, 32), (64, 64), (16, 64)]
 
@@ -264,16 +304,39 @@ class NGPRadianceField(nn.Module):
         self.mlp_head.params.copy_(torch.cat([w.reshape(-1) for w in head_w]).to(dev))
 
 
+class _SGMixtureFn(torch.autograd.Function):
+    """rgb = sigmoid(diffuse + sum_l c_l exp(|lambda_l| (a_l/|a_l| . d - 1))), differentiable in the feature rows."""
+
+    @staticmethod
+    def forward(ctx, features, dirs, num_lobes):
+        lib = _lib.load()
+        f = _lib.f32(features.detach())
+        d = _lib.f32(dirs.detach())
+        M = f.shape[0]
+        rgb = torch.empty((M, 3), dtype=torch.float32, device=f.device)
+        _lib.check(lib.qf_sg_features_to_rgb(_lib.ptr(f), f.shape[1], num_lobes, _lib.ptr(d), M, _lib.ptr(rgb),
+                                             _lib.stream(f.device)), "qf_sg_features_to_rgb")
+        ctx.save_for_backward(f, d)
+        ctx.num_lobes = num_lobes
+        return rgb
+
+    @staticmethod
+    def backward(ctx, g_rgb):
+        lib = _lib.load()
+        f, d = ctx.saved_tensors
+        M = f.shape[0]
+        g_f = torch.zeros_like(f)                       # columns beyond 3+7L (e.g. a trailing density) get no gradient
+        if M:
+            _lib.check(lib.qf_sg_features_to_rgb_backward(_lib.ptr(f), f.shape[1], ctx.num_lobes, _lib.ptr(d), M,
+                                                          _lib.ptr(_lib.f32(g_rgb)), _lib.ptr(g_f), g_f.shape[1],
+                                                          _lib.stream(f.device)), "qf_sg_features_to_rgb_backward")
+        return g_f, None, None
+
+
 def spherical_gaussian_features_to_rgb(features: torch.Tensor, dirs: torch.Tensor, num_lobes: int) -> torch.Tensor:
-    """`NGPRadianceFieldSGNew.features_to_rgb` (ngp.py:456-461, 371-393) with discretize=False."""
-    lib = _lib.load()
-    f = _lib.f32(features)
-    d = _lib.f32(dirs)
-    M = f.shape[0]
-    rgb = torch.empty((M, 3), dtype=torch.float32, device=f.device)
-    _lib.check(lib.qf_sg_features_to_rgb(_lib.ptr(f), f.shape[1], num_lobes, _lib.ptr(d), M, _lib.ptr(rgb),
-                                         _lib.stream(f.device)), "qf_sg_features_to_rgb")
-    return rgb
+    """`NGPRadianceFieldSGNew.features_to_rgb` (ngp.py:456-461, 371-393) with discretize=False; differentiable with
+    respect to `features`."""
+    return _SGMixtureFn.apply(features, dirs, num_lobes)
 
 
 class _DecoderHead(nn.Module):
@@ -296,8 +359,9 @@ class NGPRadianceFieldSGNew(NGPRadianceField):
     15 -> 64 x num_layers -> 3 + 7 L (plain library GEMMs, as in the reference), and the SG mixture
     rgb = sigmoid(diffuse + sum_l c_l exp(|lambda_l| (a_l . d - 1))) on `qf_sg_features_to_rgb`.
     State-dict keys: `aabb`, `mlp_base.params`, `mlp_head.layers.{i}.weight/bias`, `mlp_head.lout.weight/bias`.
-    Inference only: `features`, `features_to_rgb`, `query_density`, `forward` run without autograd (fitting the SG
-    field, train_fit_sg.py, needs the base MLP's feature gradient — not built)."""
+    Trainable (train_fit_sg.py:439-452): with autograd enabled the gradient flows through the SG mixture
+    (`qf_sg_features_to_rgb_backward`), the torch decoder and the geo features into the base MLP and the hash table
+    (`qf_ngp_backward_features`)."""
 
     def __init__(self, aabb=None, num_dim: int = 3, use_viewdirs: bool = False, density_activation=None, unbounded: bool = False,
                  base_resolution: int = 16, max_resolution: int = 4096, geo_feat_dim: int = 15, n_levels: int = 16,
@@ -347,19 +411,25 @@ class NGPRadianceFieldSGNew(NGPRadianceField):
         self._handle_key = key
         return self._handle
 
-    @torch.no_grad()
+    def query_density(self, x, return_feat: bool = False):
+        """ngp.py:402-428; differentiable when autograd is on and the parameters (or x) require grad."""
+        if torch.is_grad_enabled() and (self.mlp_base.params.requires_grad or x.requires_grad):
+            shape = list(x.shape[:-1])
+            density, feat = _NGPDensityFeatFn.apply(self, x, self.mlp_base.params)
+            density, feat = density.view(shape + [1]), feat.view(shape + [15])
+            return (density, feat) if return_feat else density
+        return super().query_density(x, return_feat=return_feat)
+
     def features(self, x):
         """ngp.py:445-454 -> (M, 3 + 7 L + 1): decoder output, then the density."""
         density, embedding = self.query_density(x, return_feat=True)
         feats = self.mlp_head(embedding.reshape(-1, self.geo_feat_dim))
         return torch.cat([feats.reshape(list(embedding.shape[:-1]) + [self.num_g_lobes * 7 + 3]), density], dim=-1)
 
-    @torch.no_grad()
     def features_to_rgb(self, features, dir):
         """ngp.py:456-461 (discretize=False)."""
         return spherical_gaussian_features_to_rgb(features, dir, self.num_g_lobes)
 
-    @torch.no_grad()
     def forward(self, positions: torch.Tensor, directions: torch.Tensor = None, ray_indices: torch.Tensor = None):
         """ngp.py:463-470 -> (rgb (M,3), density (M,1)).  `ray_indices` (extension): directions are per ray."""
         density, embedding = self.query_density(positions, return_feat=True)
