@@ -15,52 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-
-
-class _Mesh:
-    """Minimal stand-in for the `trimesh.Trimesh` attributes the reference touches (`vertices`, `faces`)."""
-
-    def __init__(self, vertices: np.ndarray, faces: np.ndarray):
-        self.vertices = np.asarray(vertices, dtype=np.float64)
-        self.faces = np.asarray(faces, dtype=np.int64)
-
-
-def load_mesh(path: str) -> _Mesh:
-    """Tiny OBJ / ASCII-PLY reader (`trimesh.load(path, force='mesh', process=False)`, mesh_utils.py:193)."""
-    verts, faces = [], []
-    if path.endswith(".obj"):
-        with open(path) as f:
-            for line in f:
-                p = line.split()
-                if not p:
-                    continue
-                if p[0] == "v":
-                    verts.append([float(p[1]), float(p[2]), float(p[3])])
-                elif p[0] == "f":
-                    idx = [int(q.split("/")[0]) - 1 for q in p[1:]]
-                    for k in range(1, len(idx) - 1):
-                        faces.append([idx[0], idx[k], idx[k + 1]])
-    elif path.endswith(".ply"):
-        with open(path, "rb") as f:
-            header = []
-            while True:
-                line = f.readline().decode("ascii", "replace").strip()
-                header.append(line)
-                if line == "end_header":
-                    break
-            if not any(h.startswith("format ascii") for h in header):
-                raise NotImplementedError("only ASCII PLY is supported")
-            nv = next(int(h.split()[-1]) for h in header if h.startswith("element vertex"))
-            nf = next(int(h.split()[-1]) for h in header if h.startswith("element face"))
-            for _ in range(nv):
-                verts.append([float(x) for x in f.readline().split()[:3]])
-            for _ in range(nf):
-                p = [int(x) for x in f.readline().split()]
-                for k in range(2, p[0]):
-                    faces.append([p[1], p[k], p[k + 1]])
-    else:
-        raise NotImplementedError(f"unsupported mesh format: {path}")
-    return _Mesh(np.array(verts), np.array(faces))
+from .mesh_io import Mesh as _Mesh, load_mesh  # noqa: F401  (OBJ with uv, ASCII / binary PLY)
 
 
 class RayIntersector:

@@ -1,0 +1,189 @@
+"""SURVEY §8 row f-4, host side: mesh files (OBJ with uv, ASCII / binary PLY) and the reference's checkpoint dicts.
+
+No GPU: these are the readers / writers either side of the hot path."""
+import numpy as np
+import pytest
+import torch
+
+from quadraturefields_b200 import mesh_io
+from quadraturefields_b200.checkpoint import load_checkpoint, save_checkpoint
+from quadraturefields_b200.scene import icosphere, scale_uv
+
+
+@pytest.fixture()
+def sphere():
+    v, f = icosphere(2)
+    return np.asarray(v, dtype=np.float64), np.asarray(f, dtype=np.int64)
+
+
+@pytest.mark.parametrize("binary", [True, False])
+def test_ply_round_trip(tmp_path, sphere, binary):
+    v, f = sphere
+    p = str(tmp_path / "m.ply")
+    mesh_io.save_ply(p, v, f, binary=binary)
+    m = mesh_io.load_mesh(p)
+    assert m.faces.dtype == np.int64 and m.vertices.dtype == np.float64
+    assert np.array_equal(m.faces, f)
+    assert np.array_equal(m.vertices.astype(np.float32), v.astype(np.float32))     # PLY stores fp32 (trimesh export)
+    assert m.visual.uv is None
+
+
+def test_ply_big_endian_extra_properties_and_quads(tmp_path):
+    """Vertex normals / colours are skipped, `s`/`t` become uv, mixed triangle / quad faces are fan-triangulated."""
+    v = np.array([[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0], [0.5, 0.5, 1]], dtype=">f4")
+    vt = np.dtype([("x", ">f4"), ("y", ">f4"), ("z", ">f4"), ("nx", ">f4"), ("red", "u1"), ("s", ">f8"), ("t", ">f8")])
+    rec = np.zeros(5, dtype=vt)
+    rec["x"], rec["y"], rec["z"] = v[:, 0], v[:, 1], v[:, 2]
+    rec["s"], rec["t"] = np.linspace(0, 1, 5), np.linspace(1, 0, 5)
+    header = ("ply\nformat binary_big_endian 1.0\ncomment made by hand\nelement vertex 5\nproperty float x\nproperty float y\n"
+              "property float z\nproperty float nx\nproperty uchar red\nproperty double s\nproperty double t\n"
+              "element face 2\nproperty list uchar uint vertex_indices\nend_header\n")
+    body = rec.tobytes() + bytes([4]) + np.array([0, 1, 2, 3], dtype=">u4").tobytes() + bytes([3]) + np.array([0, 1, 4], dtype=">u4").tobytes()
+    p = tmp_path / "q.ply"
+    p.write_bytes(header.encode() + body)
+    m = mesh_io.load_ply(str(p))
+    assert np.array_equal(m.faces, [[0, 1, 2], [0, 2, 3], [0, 1, 4]])
+    assert np.allclose(m.vertices, v.astype(np.float64))
+    assert np.allclose(m.visual.uv[:, 0], np.linspace(0, 1, 5)) and np.allclose(m.visual.uv[:, 1], np.linspace(1, 0, 5))
+
+
+def test_obj_per_vertex_uv_round_trip_and_scaling(tmp_path, sphere):
+    """The xatlas layout (`f a/a b/b c/c`): uv[i] belongs to vertex i, bit-exact through the text file; then the
+    reference's texel scaling (test_baking_texture_images.py:325-328)."""
+    v, f = sphere
+    uv = np.random.RandomState(3).uniform(0, 1, size=(len(v), 2))
+    p = str(tmp_path / "m.obj")
+    mesh_io.save_obj(p, v, f, uv)
+    m = mesh_io.load_mesh(p)
+    assert np.array_equal(m.vertices, v) and np.array_equal(m.faces, f) and np.array_equal(m.visual.uv, uv)
+    S = 512
+    ref = np.clip(np.array(uv - 1e-7).astype(np.float32) * S, 0, S - 1)
+    assert np.array_equal(scale_uv(m.visual.uv, S).numpy(), ref)
+
+
+def test_obj_split_vertices_negative_indices_and_polygons(tmp_path):
+    """A seam: the same position with two texture coordinates becomes two vertices; relative indices; a quad."""
+    txt = """
+v 0 0 0
+v 1 0 0
+v 1 1 0
+v 0 1 0
+vt 0 0
+vt 1 0
+vt 1 1
+vt 0 1
+vt 0.5 0.5
+f 1/1 2/2 3/3 4/4
+f -4/5 -3/2 -2//
+"""
+    p = tmp_path / "s.obj"
+    p.write_text(txt)
+    m = mesh_io.load_obj(str(p))
+    # corners in order: (0,0) (1,1) (2,2) (3,3) | (0,4) (1,1) (2,-)
+    assert len(m.vertices) == 6
+    assert np.array_equal(m.faces, [[0, 1, 2], [0, 2, 3], [4, 1, 5]])
+    assert np.array_equal(m.vertices[4], [0, 0, 0]) and np.array_equal(m.visual.uv[4], [0.5, 0.5])
+    assert np.array_equal(m.vertices[5], [1, 1, 0]) and np.array_equal(m.visual.uv[5], [0, 0])     # no vt -> zero
+    # positions only
+    (tmp_path / "t.obj").write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n")
+    m2 = mesh_io.load_obj(str(tmp_path / "t.obj"))
+    assert m2.visual.uv is None and np.array_equal(m2.faces, [[0, 1, 2]])
+
+
+def test_mesh_attributes_match_the_definitions(sphere):
+    v, f = sphere
+    m = mesh_io.Mesh(v, f)
+    n = m.face_normals
+    assert n.dtype == np.float64 and np.allclose(np.linalg.norm(n, axis=1), 1.0)
+    c = m.triangles.mean(axis=1)
+    assert np.all(np.einsum("ij,ij->i", n, c) > 0)                         # icosphere faces wind outwards
+    assert m.triangles.shape == (len(f), 3, 3)
+    assert np.isclose(m.scale, np.linalg.norm(v.max(0) - v.min(0)))
+    deg = mesh_io.Mesh([[0, 0, 0], [1, 0, 0], [2, 0, 0]], [[0, 1, 2]])
+    assert np.array_equal(deg.face_normals, [[0, 0, 0]])
+    with pytest.raises(ValueError):
+        mesh_io.Mesh(v, [[0, 1, len(v)]])
+    with pytest.raises(NotImplementedError):
+        mesh_io.load_mesh("mesh.stl")
+
+
+def _modules():
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceField, NGPRadianceFieldSGNew
+    aabb = [-1.5] * 3 + [1.5] * 3
+    return dict(
+        rf=lambda **k: NGPRadianceField(aabb=aabb, log2_hashmap_size=k.get("log2_T", 12)),
+        sg=lambda **k: NGPRadianceFieldSGNew(aabb=aabb, use_viewdirs=False, num_g_lobes=3, log2_hashmap_size=12),
+        field=lambda **k: Field(scale=0.5, log2_T=12, L=16, max_res=64, min_res=16, hidden_size=16),
+        est=lambda **k: OccGridEstimator(roi_aabb=aabb, resolution=k.get("res", 16), levels=1),
+    )
+
+
+def test_checkpoint_dicts_follow_the_reference_stages(tmp_path):
+    """Keys per stage (train_ngp_nerf_sg_occ.py:357-362, train_field.py:413-416, train_finetune.py:563-567,
+    train_fit_sg.py:486-489) and a bit-exact round trip of every tensor."""
+    mk = _modules()
+    g = torch.Generator().manual_seed(0)
+    rf, sg, field, est = mk["rf"](), mk["sg"](), mk["field"](), mk["est"]()
+    with torch.no_grad():
+        for mod in (rf, sg, field):
+            for prm in mod.parameters():
+                prm.copy_(torch.randn(prm.shape, generator=g))
+        est.occs.copy_(torch.rand(est.occs.shape, generator=g))
+        est.binaries.copy_(torch.rand(est.binaries.shape, generator=g) > 0.5)
+    assert set(rf.state_dict()) == {"aabb", "mlp_base.params", "mlp_head.params"}             # tinycudann's keys
+    assert {"resolution", "aabbs", "occs", "binaries"} <= set(est.state_dict())                 # nerfacc's buffers
+
+    def same(a, b):
+        sa, sb = a.state_dict(), b.state_dict()
+        return set(sa) == set(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+    # NeRF stage -> field / finetune stage: {"estimator", "model"}
+    p = str(tmp_path / "ngp.pth")
+    save_checkpoint(p, estimator=est, radiance_field=rf, radiance_key="model")
+    assert set(torch.load(p, weights_only=True)) == {"estimator", "model"}
+    rf2, est2 = mk["rf"](), mk["est"]()
+    load_checkpoint(p, estimator=est2, radiance_field=rf2)
+    assert same(rf, rf2) and same(est, est2)
+    # field stage: "model" is the Field net
+    p = str(tmp_path / "field.pth")
+    save_checkpoint(p, estimator=est, field_net=field, field_key="model")
+    f2 = mk["field"]()
+    load_checkpoint(p, field_net=f2)
+    assert same(field, f2)
+    # finetune stage: all three
+    p = str(tmp_path / "finetune.pth")
+    save_checkpoint(p, estimator=est, radiance_field=rf, field_net=field)
+    assert set(torch.load(p, weights_only=True)) == {"estimator", "field_model", "radiance_field"}
+    rf3, f3 = mk["rf"](), mk["field"]()
+    ck = load_checkpoint(p, radiance_field=rf3, field_net=f3)
+    assert same(rf, rf3) and same(field, f3) and "estimator" in ck
+    # SG stage
+    p = str(tmp_path / "sg.pth")
+    save_checkpoint(p, estimator=est, radiance_field=sg)
+    sg2 = mk["sg"]()
+    load_checkpoint(p, radiance_field=sg2)
+    assert same(sg, sg2)
+    # a half-precision checkpoint is widened, a dict is accepted in place of a path
+    half = {"model": {k: (v.half() if v.is_floating_point() else v) for k, v in rf.state_dict().items()}}
+    rf4 = mk["rf"]()
+    load_checkpoint(half, radiance_field=rf4)
+    assert rf4.mlp_base.params.dtype == torch.float32
+    assert torch.equal(rf4.mlp_base.params, rf.mlp_base.params.half().float())
+
+
+def test_checkpoint_errors_name_the_mismatch(tmp_path):
+    mk = _modules()
+    p = str(tmp_path / "m.pth")
+    save_checkpoint(p, estimator=mk["est"](), radiance_field=mk["rf"](), radiance_key="model")
+    with pytest.raises(ValueError, match="log2_hashmap_size"):
+        load_checkpoint(p, radiance_field=mk["rf"](log2_T=13))
+    with pytest.raises(ValueError, match="grid resolution"):
+        load_checkpoint(p, estimator=mk["est"](res=8))
+    with pytest.raises(KeyError):
+        load_checkpoint({"estimator": {}}, radiance_field=mk["rf"]())
+    with pytest.raises(ValueError):
+        save_checkpoint(p, radiance_field=mk["rf"](), field_net=mk["field"](), radiance_key="model", field_key="model")
+    with pytest.raises(ValueError):
+        save_checkpoint(p, radiance_field=mk["rf"](), radiance_key="weights")
