@@ -429,26 +429,27 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
                 num_features=2, back_prop=False, nl="elu").to(dev)                  # train_field.py:238-252 (T reduced to 2^19)
     params = list(net.parameters())
     opt = torch.optim.Adam(params, lr=2e-2, eps=1e-15, fused=True)
-    steps, warm = max(5, min(args.steps, 20)), 3
+    steps, warm = max(5, min(args.steps, 20)), 8      # warm-up also fills the side stream's allocator pool
     batches = []
-    for i in range(steps + warm + 1):
+    for i in range(steps + warm + 2):
         vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
         pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous()))
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
     reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
-    # every step trains on the tuple traced during the previous step and traces the next batch on a side stream
-    # (the reference's DataLoader worker does the intersection ahead of the step, too): one trace per step
+    # every step trains on a tuple traced two steps earlier and launches the trace of the batch after next on a side stream
+    # (the reference's DataLoader workers do the intersection ahead of the step, too): one trace per step, no host wait
     pf = HitTuplePrefetcher(sc.mesh_intersect)
 
     def step(i):
         tup = pf.get()
         m = train_field_step(net, sc.radiance_field, sc.mesh_intersect, *batches[i], opt, all_reduce=reduce, tup=tup)[1]
-        pf.submit(*batches[i + 1], rays_ready=True)
+        pf.submit(*batches[i + 2], rays_ready=True)
         return m
 
     pf.submit(*batches[0], rays_ready=True)
+    pf.submit(*batches[1], rays_ready=True)
     for i in range(warm):
         step(i)
     barrier()
@@ -464,7 +465,7 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     return {"metric": "rays_per_sec_field_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s",
             "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n, "samples_per_ray": samples / (n * steps),
             "params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "includes": "trace (of the next batch, side stream) + frozen field fwd + weights/reversed weights + Field fwd with "
+            "includes": "trace (of the batch after next, side stream) + frozen field fwd + weights/reversed weights + Field fwd with "
                         "field_grad + loss + double backward + grad all-reduce + Adam step"}
 
 
@@ -483,14 +484,14 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     rf = sc.radiance_field
     params = [rf.mlp_base.params, rf.mlp_head.params]
     opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15, fused=True)
-    steps, warm = max(5, min(args.steps, 20)), 3
+    steps, warm = max(5, min(args.steps, 20)), 8      # warm-up also fills the side stream's allocator pool
     batches = []
-    for i in range(steps + warm + 1):
+    for i in range(steps + warm + 2):
         vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
         pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous(), torch.rand((n, 3), device=dev, generator=g)))
-    # the tuple of batch i was traced on a side stream during step i-1 (as the reference's DataLoader worker does); every
-    # step still performs exactly one trace (of the next batch)
+    # the tuple of batch i was traced on a side stream during step i-2 and packed during step i-1 (the reference's
+    # DataLoader workers run ahead the same way); every step still performs exactly one trace (of the batch after next)
     pf = HitTuplePrefetcher(sc.mesh_intersect)
 
     def step(i):
@@ -502,12 +503,13 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
         loss.backward()
         P.all_reduce_gradients(params, n, n * world)
         opt.step()
-        pf.submit(batches[i + 1][0], batches[i + 1][1], rays_ready=True)
+        pf.submit(batches[i + 2][0], batches[i + 2][1], rays_ready=True)
         return n_hits
 
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
     pf.submit(batches[0][0], batches[0][1], rays_ready=True)
+    pf.submit(batches[1][0], batches[1][1], rays_ready=True)
     for i in range(warm):
         step(i)
     barrier()
@@ -523,7 +525,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,
             "steps": steps, "rays_per_step_per_gpu": n, "hits_per_ray": hits / (n * steps), "params": n_params,
             "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
-            "includes": "trace (of the next batch, side stream) + field fwd + composite + loss + field/composite bwd + grad all-reduce "
+            "includes": "trace (of the batch after next, side stream) + field fwd + composite + loss + field/composite bwd + grad all-reduce "
                         "+ fused Adam step"}
 
 

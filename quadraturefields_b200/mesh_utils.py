@@ -18,6 +18,14 @@ from . import _lib
 from .mesh_io import Mesh as _Mesh, load_mesh  # noqa: F401  (OBJ with uv, ASCII / binary PLY)
 
 
+class _DoneEvent:
+    """Stands in for a CUDA event whose work the host has already waited for."""
+
+    @staticmethod
+    def synchronize():
+        return None
+
+
 class RayIntersector:
     """mesh_utils.py:75-109.  `intersects_id` returns (triangle_indices, ray_indices, psi) as numpy arrays."""
 
@@ -79,6 +87,48 @@ class RayIntersector:
         return (tri, t, count, total) if with_total else (tri, t, count)
 
     @torch.no_grad()
+    def trace_tuple_begin(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None):
+        """First half of `trace_tuple`: launch the traversal and the per-ray offset scan on the current stream and start
+        an asynchronous copy of the hit total into pinned host memory.  No host synchronisation; hand the result to
+        `trace_tuple_end` (on the same stream) once the size is wanted."""
+        lib = _lib.load()
+        K = int(max_hits or self.max_hits)
+        o = _lib.f32(origins, self.device)
+        d = _lib.f32(vectors, self.device)
+        N = o.shape[0]
+        tri, _, count = self.trace(o, d, K)
+        offsets = torch.empty((N + 1,), dtype=torch.int64, device=self.device)
+        ws = _lib.workspace(self.device, lib.qf_scan_workspace_bytes(N), "scan")
+        st = _lib.stream(self.device)
+        _lib.check(lib.qf_hits_offsets(_lib.ptr(count), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), st), "qf_hits_offsets")
+        total = torch.empty((1,), dtype=torch.int64, pin_memory=True)
+        total.copy_(offsets[N:], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return o, d, N, K, tri, count, offsets, total, ev
+
+    @torch.no_grad()
+    def trace_tuple_end(self, pending):
+        """Second half: wait (host) for the hit total only, size the tuple and pack it on the current stream."""
+        lib = _lib.load()
+        o, d, N, K, tri, count, offsets, total, ev = pending
+        ev.synchronize()
+        M = int(total[0])
+        st = _lib.stream(self.device)
+        # M changes from batch to batch: allocating in steps of 32 Ki hits lets the caching allocator hand the previous
+        # batch's blocks straight back instead of growing the pool (cudaMalloc stalls the host for milliseconds)
+        cap = (M + 32767) // 32768 * 32768
+        f = lambda *s: torch.empty((cap,) + s, dtype=torch.float32, device=self.device)[:M]
+        points, vecs, org, depth = f(3), f(3), f(3), f()
+        index_ray = torch.empty((cap,), dtype=torch.int64, device=self.device)[:M]
+        index_tri = torch.empty((cap,), dtype=torch.int64, device=self.device)[:M]
+        if M:
+            _lib.check(lib.qf_hits_pack(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(count),
+                                        _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(vecs), _lib.ptr(index_ray),
+                                        _lib.ptr(depth), _lib.ptr(index_tri), _lib.ptr(org), st), "qf_hits_pack")
+        return points, vecs, index_ray, depth, index_tri, org, offsets
+
+    @torch.no_grad()
     def trace_tuple(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None):
         """The reference data tuple on the device, ray-major and depth-sorted:
         (points (M,3), vectors (M,3), index_ray (M,), depth (M,), index_tri (M,), origins (M,3)); M may be 0."""
@@ -94,16 +144,8 @@ class RayIntersector:
         _lib.check(lib.qf_hits_offsets(_lib.ptr(count), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), st), "qf_hits_offsets")
         total = C.c_int64()
         _lib.check(lib.qf_hits_total(_lib.ptr(offsets), N, C.byref(total), st), "qf_hits_total")
-        M = total.value
-        f = lambda *s: torch.empty(s, dtype=torch.float32, device=self.device)
-        points, vecs, org, depth = f(M, 3), f(M, 3), f(M, 3), f(M)
-        index_ray = torch.empty((M,), dtype=torch.int64, device=self.device)
-        index_tri = torch.empty((M,), dtype=torch.int64, device=self.device)
-        if M:
-            _lib.check(lib.qf_hits_pack(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(count),
-                                        _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(vecs), _lib.ptr(index_ray),
-                                        _lib.ptr(depth), _lib.ptr(index_tri), _lib.ptr(org), st), "qf_hits_pack")
-        return points, vecs, index_ray, depth, index_tri, org, offsets
+        pinned = torch.tensor([total.value], dtype=torch.int64)
+        return self.trace_tuple_end((o, d, N, K, tri, count, offsets, pinned, _DoneEvent))
 
     # ---- reference surface ------------------------------------------------------------------------
     @torch.no_grad()
@@ -229,6 +271,21 @@ class MeshIntersection:
             return None
         tup = HitTuple((points, vecs, index_ray, depth, index_tri, 0, org))
         tup.offsets = offsets          # (N+1,) int64 start of every ray's run: lets callers skip re-deriving the packs
+        return tup
+
+    @torch.no_grad()
+    def sampling_raytrace_begin(self, vectors: torch.Tensor, origins: torch.Tensor):
+        """`sampling_raytrace` in two halves for prefetching: this one launches the intersection without waiting for it."""
+        return self.rayintersector.trace_tuple_begin(origins, vectors, self.num_intersections)
+
+    @torch.no_grad()
+    def sampling_raytrace_end(self, pending):
+        """Second half of `sampling_raytrace_begin`: the 7-tuple (or None), packed on the current stream."""
+        points, vecs, index_ray, depth, index_tri, org, offsets = self.rayintersector.trace_tuple_end(pending)
+        if index_tri.shape[0] == 0:
+            return None
+        tup = HitTuple((points, vecs, index_ray, depth, index_tri, 0, org))
+        tup.offsets = offsets
         return tup
 
     def sampling_raytrace_numpy(self, vectors, origins, random=0):

@@ -201,37 +201,51 @@ class FramePipeline:
 
 
 class HitTuplePrefetcher:
-    """Intersection of the NEXT training batch while the current one trains.  The reference does the same thing with a
-    DataLoader worker: `SubjectLoader.fetch_data` calls `mesh_intersect.sampling_raytrace_numpy` on the CPU (Embree) and
-    hands the tuple over as `data["data"]` (train_finetune.py:494-509).  Here the trace runs on a side CUDA stream, so the
-    host-side wait for the hit count (the tuple's size) does not drain the training stream.  Call `submit` AFTER the
-    current step's work has been launched: the host then waits for the side stream while the GPU trains.  (A worker
-    thread for the wait was measured slower: the step is bound by Python launch overhead and the thread competes for
-    the GIL.)  The intersection does not depend on the networks' parameters, so the result is identical to tracing
-    inside the step."""
+    """Intersection of the NEXT training batches while the current one trains.  The reference does the same thing with
+    DataLoader workers: `SubjectLoader.fetch_data` calls `mesh_intersect.sampling_raytrace_numpy` on the CPU (Embree) and
+    hands the tuple over as `data["data"]` (train_finetune.py:494-509), a few batches ahead (torch's `prefetch_factor`).
+    Here the trace runs on a side CUDA stream in two halves (`sampling_raytrace_begin/_end`): `submit` launches the
+    traversal of the new batch WITHOUT waiting for it, after it has sized and packed the tuple of the batch submitted
+    before — whose traversal was launched a whole training step earlier, so the host-side wait for the hit count (the
+    tuple's size) is over by then.  `get` hands the tuples back in submission order.  Submit two batches before the first
+    step and one more after each step's work has been launched: neither the host nor the training stream then ever waits
+    for a traversal.  With a single batch in flight `get` completes it on the spot (the one-deep behaviour).  The
+    intersection does not depend on the networks' parameters, so the result is identical to tracing inside the step."""
 
     def __init__(self, mesh_intersect):
         self.mesh_intersect = mesh_intersect
         self.stream = torch.cuda.Stream(device=mesh_intersect.device)
-        self._pending = None
+        self._inflight = None            # (pending trace, origins, viewdirs): launched, tuple not sized yet
+        self._ready = []                 # [(tuple, event, origins, viewdirs)] in submission order
+
+    def _complete(self):
+        if self._inflight is None:
+            return
+        pending, origins, viewdirs = self._inflight
+        self._inflight = None
+        with torch.cuda.stream(self.stream):
+            tup = self.mesh_intersect.sampling_raytrace_end(pending)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self._ready.append((tup, ev, origins, viewdirs))
 
     @torch.no_grad()
     def submit(self, origins, viewdirs, rays_ready: bool = False):
         """`rays_ready=True`: the ray tensors were completed earlier (a data-loader batch), so the trace need not wait
         for the work queued on the training stream — that wait would serialise it behind the whole current step."""
+        self._complete()                                    # pack the previous batch first: it must not queue behind this trace
         main = torch.cuda.current_stream(self.mesh_intersect.device)
         if not rays_ready:
             self.stream.wait_stream(main)                   # the rays may still be in flight on the training stream
         with torch.cuda.stream(self.stream):
-            tup = self.mesh_intersect.sampling_raytrace(viewdirs, origins)
-            ev = torch.cuda.Event()
-            ev.record(self.stream)
-        self._pending = (tup, ev, origins, viewdirs)
+            pending = self.mesh_intersect.sampling_raytrace_begin(viewdirs, origins)
+        self._inflight = (pending, origins, viewdirs)
 
     def get(self):
-        """-> the 7-tuple (or None when nothing was hit), safe to use on the current stream."""
-        tup, ev, origins, viewdirs = self._pending
-        self._pending = None
+        """-> the 7-tuple (or None when nothing was hit) of the oldest submitted batch, safe to use on the current stream."""
+        if not self._ready:
+            self._complete()
+        tup, ev, origins, viewdirs = self._ready.pop(0)
         main = torch.cuda.current_stream(self.mesh_intersect.device)
         main.wait_event(ev)
         if tup is not None:

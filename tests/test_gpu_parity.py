@@ -976,6 +976,38 @@ def test_hit_tuple_prefetcher_matches_inline_trace(dev, smoke_scene):
     assert maxabs(outs[0], outs[1]) > 1e-3
 
 
+def test_hit_tuple_prefetcher_two_deep_pipeline(dev, smoke_scene):
+    """Two batches ahead (`submit, submit, get, submit, get, ...`): the traversal of batch i+2 is launched without a host
+    wait while batch i trains; tuples come back in submission order and equal the inline trace, including an all-miss
+    batch (None) in the middle of the queue, and `trace_tuple_begin/_end` equal `trace_tuple`."""
+    from quadraturefields_b200.utils import HitTuplePrefetcher
+    sc = smoke_scene
+    mi = sc.mesh_intersect
+    o0, d0 = sc.rays(0)
+    o1, d1 = sc.rays(1)
+    away = (o0 + 100.0, d0)                                             # every ray misses the mesh
+    mid = o0.shape[0] // 2
+    batches = [(o0, d0), away, (o1, d1), (o0[mid - 50:mid + 50], d0[mid - 50:mid + 50]), (o1, d1)]
+    pf = HitTuplePrefetcher(mi)
+    pf.submit(*batches[0], rays_ready=True)
+    pf.submit(*batches[1], rays_ready=True)
+    for i in range(len(batches)):
+        tup = pf.get()
+        if i + 2 < len(batches):
+            pf.submit(*batches[i + 2])
+        ref = mi.sampling_raytrace(batches[i][1], batches[i][0])
+        if ref is None:
+            assert tup is None and i == 1
+            continue
+        for a, b in zip(tup, ref):
+            assert (a == b) if not isinstance(a, torch.Tensor) else torch.equal(a, b)
+        assert torch.equal(tup.offsets, ref.offsets)
+    ri = mi.rayintersector
+    a = ri.trace_tuple_end(ri.trace_tuple_begin(o0, d0, 3))
+    b = ri.trace_tuple(o0, d0, 3)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
 @pytest.mark.parametrize("levels,cone,near", [(1, 0.0, 0.0), (2, 0.004, 0.2), (4, 0.002, 0.05)])
 def test_occgrid_marcher_matches_oracle(dev, levels, cone, near):
     """f-1: the occupancy-grid marcher kernel against the restated nerfacc algorithm (oracle.occgrid_march): sample
