@@ -18,7 +18,7 @@ constexpr int kTileStride = 56;           // per-sample staging row: 32 enc + 16
 // ---- hash-grid encode of one point: 16 levels, trilinear, fp32 interpolation, fp16 result
 // The level loop is kept ROLLED (two levels per trip, the gathers of both issued before either is consumed):
 // fully unrolled it is ~13k instructions and the kernel stalls on instruction fetch.
-struct Corner8 { uint32_t idx[8]; float fx, fy, fz; };
+struct Corner8 { uint32_t idx[8]; float fx, fy, fz; uint32_t odd; };   // odd: low bit of the cell's x index (hashed levels)
 
 __device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, float x, float y, float z, Corner8& c) {
   const float scale = d.scale[l];
@@ -27,6 +27,7 @@ __device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, floa
   const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
   const uint32_t cx = (uint32_t)(int)flx, cy = (uint32_t)(int)fly, cz = (uint32_t)(int)flz;
   c.fx = px - flx; c.fy = py - fly; c.fz = pz - flz;
+  c.odd = cx & 1u;
   if (d.hashed[l]) {   // hashed levels always have size == 2^log2_hashmap_size
     const uint32_t mask = size - 1;
     const uint32_t y0 = cy * 2654435761u, y1 = (cy + 1) * 2654435761u, z0 = cz * 805459861u, z1 = (cz + 1) * 805459861u;
@@ -64,6 +65,54 @@ __device__ __forceinline__ uint32_t level_blend(const Corner8& c, const __half2*
 // x, y, z factors in turn; (1*wx)*wy*wz == (wx*wy)*wz exactly.
 
 // writes 2 halves per level to out[2*l] (shared-memory row of the sample, or a local array)
+// The 8 corner entries of one level: eight 4-byte gathers.
+// QF_PAIRED_GATHER (off; measured and rejected): the hash leaves x un-multiplied, so for an EVEN cell x
+// the two x-neighbours of a hashed level differ only in index bit 0 and sit in one aligned 8-byte pair.  Variant 1: even
+// lanes one 8-byte load, odd lanes two 4-byte loads (three predicated instructions into the same two registers);
+// variant 2: every lane loads the pair around its first corner, odd lanes add a 4-byte load.  Both touch 1.5 instead of
+// 2 lines per lane and x-pair, both are bit-identical, neither is faster (c2 shade 0.242 -> 0.252 / 0.246 ms).
+#ifndef QF_PAIRED_GATHER
+#define QF_PAIRED_GATHER 0
+#endif
+__device__ __forceinline__ void load_corners(const qf_grid_desc& d, int l, const __half2* __restrict__ table, const Corner8& c,
+                                             __half2* v) {
+  const __half2* t = table + d.offset[l];
+#if QF_PAIRED_GATHER
+  if (d.hashed[l]) {
+    const uint32_t odd = c.odd;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t i0 = c.idx[2 * j], i1 = c.idx[2 * j + 1];
+#if QF_PAIRED_GATHER == 1
+      const __half2* pa = t + (odd ? i0 : (i0 & ~1u));
+      const __half2* pb = t + i1;
+      uint32_t e0, e1;
+      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
+          "@p ld.global.nc.b32 %0, [%2];\n\t"
+          "@p ld.global.nc.b32 %1, [%3];\n\t"
+          "@!p ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+          : "=&r"(e0), "=&r"(e1)
+          : "l"(pa), "l"(pb), "r"(odd));
+      const bool swap = !odd && (i0 & 1u);          // even cell: entry i0 sits in the half given by its low bit
+      const uint32_t a = swap ? e1 : e0, b = swap ? e0 : e1;
+#else
+      // every lane loads the aligned pair around i0; odd cells add one 4-byte load for the far x-neighbour
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(t + (i0 & ~1u)));
+      uint32_t lone = 0u;
+      if (odd) lone = __ldg(reinterpret_cast<const uint32_t*>(t + i1));
+      const uint32_t a = (i0 & 1u) ? w.y : w.x;
+      const uint32_t b = odd ? lone : ((i0 & 1u) ? w.x : w.y);
+#endif
+      v[2 * j] = *reinterpret_cast<const __half2*>(&a);
+      v[2 * j + 1] = *reinterpret_cast<const __half2*>(&b);
+    }
+    return;
+  }
+#endif
+#pragma unroll
+  for (int k = 0; k < 8; ++k) v[k] = __ldg(t + c.idx[k]);
+}
+
 template <typename Store>
 __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
                                              float z, Store store) {
@@ -73,15 +122,11 @@ __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half
     Corner8 c0, c1;
     __half2 v0[8], v1[8];
     level_indices(d, l, x, y, z, c0);
-    const __half2* t0 = table + d.offset[l];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v0[k] = __ldg(t0 + c0.idx[k]);
+    load_corners(d, l, table, c0, v0);
     const bool two = l + 1 < L;
     if (two) {
       level_indices(d, l + 1, x, y, z, c1);
-      const __half2* t1 = table + d.offset[l + 1];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v1[k] = __ldg(t1 + c1.idx[k]);
+      load_corners(d, l + 1, table, c1, v1);
     }
     store(l, level_blend(c0, v0));
     if (two) store(l + 1, level_blend(c1, v1));
