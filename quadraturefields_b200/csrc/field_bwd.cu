@@ -9,7 +9,8 @@
 //                         exactly the fragment layout where lane (g,t) owns levels {t, t+4, t+8, t+12} of samples
 //                         g and g+8, so the table scatter (8 float2 atomics per level) needs no shuffles.
 //                         Layer inputs and output-gradients are written once as fp16 rows (960 B / sample).
-//   weight_grad_kernel    dW_l = G_l^T A_l as a split-K tensor-core GEMM over the sample dimension
+//   weight_grad_kernel    dW_l = G_l^T A_l as a split-K tensor-core GEMM over the sample dimension, all five layers in
+//                         one pass over the rows (cp.async ring, accumulators in registers)
 //                         (ldmatrix.trans fragments, fp32 accumulate, one atomicAdd per element per chunk).
 //   unpack_weight_grads   padded kernel image -> tinycudann flat layout (row-major (out,in), head columns un-permuted).
 #include "field_common.cuh"
@@ -367,8 +368,6 @@ struct LayerGemm { int N, K, act_off, grd_off, img_off, img_stride; };
 __constant__ LayerGemm c_layers[5] = {
     {64, 32, 0, 0, kW1, kS32}, {16, 64, 32, 64, kW2, kS64}, {64, 32, 96, 80, kW3, kS32},
     {64, 64, 128, 144, kW4, kS64}, {16, 64, 192, 208, kW5, kS64}};
-__constant__ int c_item_layer[14] = {0, 0, 0, 0, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4};
-__constant__ int c_item_mtile[14] = {0, 1, 2, 3, 0, 0, 1, 2, 3, 0, 1, 2, 3, 0};
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const void* p) {
   unsigned addr = (unsigned)__cvta_generic_to_shared(p);
@@ -380,64 +379,156 @@ __device__ __forceinline__ void ldmatrix_x2_trans(uint32_t& r0, uint32_t& r1, co
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 
-constexpr int kGemmChunk = 4096;  // samples per CTA
+// One CTA streams whole sample rows (activations 512 B + gradients 448 B, read exactly once, fully coalesced) through a
+// 3-stage cp.async ring of 16-sample tiles; its four warps own disjoint sets of the 14 (layer, 16-row m-tile) items and
+// keep their fp32 accumulators in registers for the CTA's whole share of the samples:
+//   warp 0: base L1 (4 m-tiles, K=32) + base L2 (K=64)     96 accumulators, 24 MMAs per tile
+//   warp 1: head L1 (4 m-tiles, K=32) + head L3 (K=64)     96 accumulators, 24 MMAs per tile
+//   warp 2: head L2 m-tiles 0,1 (K=64)                     64 accumulators, 16 MMAs per tile
+//   warp 3: head L2 m-tiles 2,3 (K=64)                     64 accumulators, 16 MMAs per tile
+// (The first version launched one CTA per item and re-read every row once per item through un-pipelined loads: 0.27 ms
+// for 442 K samples, 1.2 KB of DRAM reads per sample.)
+constexpr int kWgTile = 16;          // samples per pipeline stage
+constexpr int kWgStages = 3;
+constexpr int kWgActStride = 264;    // halves; 528 B rows -> the 8 rows of an ldmatrix hit 8 distinct 16-byte bank groups
+constexpr int kWgGrdStride = 232;    // halves; 464 B rows, same property
+constexpr int kWgStageHalves = kWgTile * (kWgActStride + kWgGrdStride);
+constexpr int kWgSmemBytes = kWgStages * kWgStageHalves * 2;   // 47616 B
 
-__global__ void __launch_bounds__(128) weight_grad_kernel(const __half* __restrict__ act, const __half* __restrict__ grd,
-                                                          int64_t M, float* __restrict__ stage) {
-  __shared__ __align__(16) __half s_g[4][16 * kT24];
-  __shared__ __align__(16) __half s_a[4][16 * kS64];
-  const int item = blockIdx.y;
-  const LayerGemm L = c_layers[c_item_layer[item]];
-  const int mtile = c_item_mtile[item];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  __half* sg = s_g[warp];
-  __half* sa = s_a[warp];
-  const int KT8 = L.K / 8;
-  float acc[8][4];
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gmem_src, bool valid) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// acc[KT8][4] += G^T (16 gradient columns at grd_col) x A (KT8*8 input columns at act_col) over the 16 samples of a stage
+template <int KT8>
+__device__ __forceinline__ void wg_item(float (&acc)[KT8][4], const __half* sa, const __half* sg, int act_col, int grd_col, int lane) {
+  uint32_t af[4];
+  {
+    const int j = lane >> 3, r = lane & 7;
+    ldmatrix_x4_trans(af, sg + ((j >> 1) * 8 + r) * kWgGrdStride + grd_col + (j & 1) * 8);
+  }
 #pragma unroll
-  for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-  const int64_t c0 = (int64_t)blockIdx.x * kGemmChunk + warp * (kGemmChunk / 4);
-  const int64_t c1 = min(c0 + kGemmChunk / 4, M);
-  for (int64_t s0 = c0; s0 < c1; s0 += 16) {
-    {  // G block: 16 samples x 16 gradient columns of this m-tile
-      const int r = lane >> 1, seg = lane & 1;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (s0 + r < M) v = __ldg(reinterpret_cast<const uint4*>(grd + (s0 + r) * kGrdRow + L.grd_off + mtile * 16 + seg * 8));
-      *reinterpret_cast<uint4*>(sg + r * kT24 + seg * 8) = v;
-    }
-    for (int q = lane; q < 16 * KT8; q += 32) {  // A block: 16 samples x K layer inputs
-      const int r = q / KT8, seg = q % KT8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (s0 + r < M) v = __ldg(reinterpret_cast<const uint4*>(act + (s0 + r) * kActRow + L.act_off + seg * 8));
-      *reinterpret_cast<uint4*>(sa + r * kS64 + seg * 8) = v;
-    }
-    __syncwarp();
-    uint32_t af[4];
-    {
-      const int j = lane >> 3, r = lane & 7;
-      ldmatrix_x4_trans(af, sg + ((j >> 1) * 8 + r) * kT24 + (j & 1) * 8);
-    }
+  for (int n = 0; n < KT8; ++n) {
+    uint32_t b0, b1;
+    ldmatrix_x2_trans(b0, b1, sa + (lane & 15) * kWgActStride + act_col + n * 8);
+    mma16816(acc[n], af, b0, b1);
+  }
+}
+
+template <int KT8>
+__device__ __forceinline__ void wg_flush(const float (&acc)[KT8][4], float* __restrict__ stage, int layer, int mtile, int lane,
+                                         int col0 = 0) {
+  const LayerGemm L = c_layers[layer];
+  const int g = lane >> 2, t = lane & 3;
+  float* out = stage + L.img_off + (mtile * 16) * L.img_stride + col0;
 #pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (n < KT8) {
-        uint32_t b0, b1;
-        ldmatrix_x2_trans(b0, b1, sa + (lane & 15) * kS64 + n * 8);
-        mma16816(acc[n], af, b0, b1);
+  for (int n = 0; n < KT8; ++n) {
+    const int c = n * 8 + t * 2;
+    atomicAdd(out + g * L.img_stride + c, acc[n][0]);
+    atomicAdd(out + g * L.img_stride + c + 1, acc[n][1]);
+    atomicAdd(out + (g + 8) * L.img_stride + c, acc[n][2]);
+    atomicAdd(out + (g + 8) * L.img_stride + c + 1, acc[n][3]);
+  }
+}
+
+template <int KT8, int NI>
+__device__ __forceinline__ void wg_zero(float (&acc)[NI][KT8][4]) {
+#pragma unroll
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int n = 0; n < KT8; ++n) acc[i][n][0] = acc[i][n][1] = acc[i][n][2] = acc[i][n][3] = 0.f;
+}
+
+// base_only: the geo-feature backward (qf_ngp_backward_features) wrote only the base MLP's columns
+__global__ void __launch_bounds__(128, 3) weight_grad_kernel(const __half* __restrict__ act, const __half* __restrict__ grd,
+                                                             int64_t M, float* __restrict__ stage, int base_only) {
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  __half* smem = reinterpret_cast<__half*>(wg_smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (M + kWgTile - 1) / kWgTile;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  auto issue = [&](int64_t it) {          // tile `it` of this CTA -> stage it % kWgStages (an empty group past the end)
+    if (it < my_tiles) {
+      const int64_t s0 = ((int64_t)blockIdx.x + it * gridDim.x) * kWgTile;
+      __half* sa = smem + (it % kWgStages) * kWgStageHalves;
+      __half* sg = sa + kWgTile * kWgActStride;
+      constexpr int kA = kWgTile * (kActRow / 8), kG = kWgTile * (kGrdRow / 8);     // 16-byte pieces: 512 + 448
+      for (int q = tid; q < kA + kG; q += 128) {
+        if (q < kA) {
+          const int r = q / (kActRow / 8), c = q % (kActRow / 8);
+          const bool ok = s0 + r < M;
+          cp_async16_zfill(sa + r * kWgActStride + c * 8, act + (ok ? (s0 + r) : 0) * kActRow + c * 8, ok);
+        } else {
+          const int q2 = q - kA, r = q2 / (kGrdRow / 8), c = q2 % (kGrdRow / 8);
+          const bool ok = s0 + r < M;
+          cp_async16_zfill(sg + r * kWgGrdStride + c * 8, grd + (ok ? (s0 + r) : 0) * kGrdRow + c * 8, ok);
+        }
       }
     }
-    __syncwarp();
-  }
-  float* out = stage + L.img_off + (mtile * 16) * L.img_stride;
+    cp_async_commit();
+  };
+
+  float acc32[4][4][4];      // warps 0,1: four K=32 m-tiles; warps 2,3: [0],[1] = the two column halves of their second K=64 m-tile
+  float acc64[1][8][4];      // warps 0,1: the 16-row K=64 layer; warps 2,3: their first K=64 m-tile of head L2
+  wg_zero<4, 4>(acc32);
+  wg_zero<8, 1>(acc64);
+  for (int i = 0; i < kWgStages - 1; ++i) issue(i);
+  for (int64_t it = 0; it < my_tiles; ++it) {
+    cp_async_wait<kWgStages - 2>();
+    __syncthreads();                       // tile `it` has landed for every thread; everyone is done with tile it-1
+    issue(it + kWgStages - 1);             // refills the stage of tile it-1
+    const __half* sa = smem + (it % kWgStages) * kWgStageHalves;
+    const __half* sg = sa + kWgTile * kWgActStride;
+    if (warp == 0) {
 #pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    if (n < KT8) {
-      const int c = n * 8 + t * 2;
-      atomicAdd(out + g * L.img_stride + c, acc[n][0]);
-      atomicAdd(out + g * L.img_stride + c + 1, acc[n][1]);
-      atomicAdd(out + (g + 8) * L.img_stride + c, acc[n][2]);
-      atomicAdd(out + (g + 8) * L.img_stride + c + 1, acc[n][3]);
+      for (int m = 0; m < 4; ++m) wg_item<4>(acc32[m], sa, sg, 0, m * 16, lane);            // base L1: enc -> dL/dh1pre
+      wg_item<8>(acc64[0], sa, sg, 32, 64, lane);                                           // base L2: relu(h1) -> dL/d base out
+    } else if (!base_only) {
+      if (warp == 1) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) wg_item<4>(acc32[m], sa, sg, 96, 80 + m * 16, lane);    // head L1: head input -> dL/dh2pre
+        wg_item<8>(acc64[0], sa, sg, 192, 208, lane);                                       // head L3: relu(h3) -> dL/d logits
+      } else {
+        const int m0 = (warp - 2) * 2;
+        wg_item<8>(acc64[0], sa, sg, 128, 144 + m0 * 16, lane);                             // head L2: relu(h2) -> dL/dh3pre
+        wg_item<4>(acc32[0], sa, sg, 128, 144 + (m0 + 1) * 16, lane);
+        wg_item<4>(acc32[1], sa, sg, 160, 144 + (m0 + 1) * 16, lane);
+      }
     }
   }
+  cp_async_wait<0>();
+  if (my_tiles == 0) return;
+  if (warp == 0) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) wg_flush<4>(acc32[m], stage, 0, m, lane);
+    wg_flush<8>(acc64[0], stage, 1, 0, lane);
+  } else if (!base_only) {
+    if (warp == 1) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) wg_flush<4>(acc32[m], stage, 2, m, lane);
+      wg_flush<8>(acc64[0], stage, 4, 0, lane);
+    } else {
+      const int m0 = (warp - 2) * 2;
+      wg_flush<8>(acc64[0], stage, 3, m0, lane);
+      wg_flush<4>(acc32[0], stage, 3, m0 + 1, lane);
+      wg_flush<4>(acc32[1], stage, 3, m0 + 1, lane, 32);
+    }
+  }
+}
+
+static int launch_weight_grad(const __half* act, const __half* grd, int64_t M, float* stage, bool base_only, cudaStream_t st) {
+  QF_ENSURE_DYNAMIC_SMEM(weight_grad_kernel, kWgSmemBytes);
+  const int64_t tiles = ceil_div(M, kWgTile);
+  const int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);
+  weight_grad_kernel<<<blocks, 128, kWgSmemBytes, st>>>(act, grd, M, stage, base_only ? 1 : 0);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
 }
 
 // kernel image (fp32) -> tinycudann flat layouts, accumulated into the caller's gradient buffers
@@ -526,9 +617,7 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
   int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);   // 3 CTAs/SM: 64.5 KB smem, <= 168 registers
   ngp_backward_kernel<false><<<blocks, 128, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
-  dim3 grid((unsigned)ceil_div(M, kGemmChunk), 14);
-  weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
-  QF_LAUNCH_CHECK();
+  { int rc = launch_weight_grad(act, grd, M, stage, false, st); if (rc != QF_OK) return rc; }
   unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, d_grad_head_w);
   QF_LAUNCH_CHECK();
   return QF_OK;
@@ -567,9 +656,7 @@ extern "C" int qf_ngp_backward_features(const qf_ngp* f, const float* d_position
   int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);
   ngp_backward_kernel<true><<<blocks, 128, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
-  dim3 grid((unsigned)ceil_div(M, kGemmChunk), 5);        // items 0..4: the two base layers
-  weight_grad_kernel<<<grid, 128, 0, st>>>(act, grd, M, stage);
-  QF_LAUNCH_CHECK();
+  { int rc = launch_weight_grad(act, grd, M, stage, true, st); if (rc != QF_OK) return rc; }      // the two base layers only
   unpack_weight_grads_kernel<<<(int)ceil_div(3072, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, nullptr);
   QF_LAUNCH_CHECK();
   return QF_OK;

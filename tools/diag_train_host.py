@@ -10,7 +10,7 @@ dev = torch.device("cuda:0")
 sc = S.make_scene("c2", device=dev)
 args = argparse.Namespace(train_rays=1 << 18, steps=int(sys.argv[1]) if len(sys.argv) > 1 else 20)
 def barrier(): torch.cuda.synchronize()
-for fn in (bench.run_train_steps, bench.run_field_train_steps):
+for fn in (bench.run_train_steps,):
     print(fn.__name__, "plain:", {k: v for k, v in fn(args, sc, dev, 0, 1, barrier).items() if k in ("value", "ms_per_step")})
     pr = cProfile.Profile()
     pr.enable()
@@ -18,5 +18,5 @@ for fn in (bench.run_train_steps, bench.run_field_train_steps):
     pr.disable()
     print(fn.__name__, "under cProfile:", r["ms_per_step"], "ms/step")
     s = io.StringIO()
-    pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28)
+    pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(45)
     print("\n".join(l[:150] for l in s.getvalue().splitlines()[4:]))
