@@ -69,15 +69,17 @@ class RayIntersector:
 
     # ---- device-resident API --------------------------------------------------------------------
     @torch.no_grad()
-    def trace(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None, with_total=False):
-        """First-K hits per ray: tri (N,K) int32 (-1 padded), t (N,K), count (N,) [, total (N,)]."""
+    def trace(self, origins: torch.Tensor, vectors: torch.Tensor, max_hits: Optional[int] = None, with_total=False,
+              with_t: bool = True):
+        """First-K hits per ray: tri (N,K) int32 (-1 padded), t (N,K) (None with `with_t=False`: the tuple path recomputes
+        the depth from the plane hit and skips the N*K floats), count (N,) [, total (N,)]."""
         lib = _lib.load()
         K = int(max_hits or self.max_hits)
         o = _lib.f32(origins, self.device)
         d = _lib.f32(vectors, self.device)
         N = o.shape[0]
         tri = torch.empty((N, K), dtype=torch.int32, device=self.device)
-        t = torch.empty((N, K), dtype=torch.float32, device=self.device)
+        t = torch.empty((N, K), dtype=torch.float32, device=self.device) if with_t else None
         count = torch.empty((N,), dtype=torch.int32, device=self.device)
         total = torch.empty((N,), dtype=torch.int32, device=self.device) if with_total else None
         ws = _lib.workspace(self.device, lib.qf_trace_workspace_bytes(N), "trace")
@@ -96,7 +98,7 @@ class RayIntersector:
         o = _lib.f32(origins, self.device)
         d = _lib.f32(vectors, self.device)
         N = o.shape[0]
-        tri, _, count = self.trace(o, d, K)
+        tri, _, count = self.trace(o, d, K, with_t=False)
         offsets = torch.empty((N + 1,), dtype=torch.int64, device=self.device)
         ws = _lib.workspace(self.device, lib.qf_scan_workspace_bytes(N), "scan")
         st = _lib.stream(self.device)
@@ -137,7 +139,7 @@ class RayIntersector:
         o = _lib.f32(origins, self.device)
         d = _lib.f32(vectors, self.device)
         N = o.shape[0]
-        tri, _, count = self.trace(o, d, K)
+        tri, _, count = self.trace(o, d, K, with_t=False)
         offsets = torch.empty((N + 1,), dtype=torch.int64, device=self.device)
         ws = _lib.workspace(self.device, lib.qf_scan_workspace_bytes(N), "scan")
         st = _lib.stream(self.device)
