@@ -385,7 +385,7 @@ def run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier):
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     o_all, d_all = sc.rays(0)
     n_rays = 1 << 16
-    steps, warm = max(5, min(args.steps, 10)), 2
+    steps, warm = max(5, min(args.steps, 10)), 5
     batches = []
     for i in range(steps + warm):
         pi = torch.randint(0, sc.n_rays, (n_rays,), device=dev, generator=g)
@@ -397,17 +397,19 @@ def run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier):
         train_field_step_occgrid(net, rf, est, batches[i], opt, render_step_size=step_size)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0.record()
     samples = 0
     for i in range(steps):
         samples += train_field_step_occgrid(net, rf, est, batches[warm + i], opt, render_step_size=step_size)[1]
     e1.record()
     barrier()
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs
     rf.eval()
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
     return {"metric": "samples_per_sec_field_train_occgrid", "value": samples * world / (ms * 1e-3), "unit": "samples/s",
             "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n_rays, "samples_per_step": samples / steps,
-            "occupied_fraction": float(est.binaries.float().mean()),
+            "occupied_fraction": float(est.binaries.float().mean()), "cuda_mallocs_in_timed_region": mallocs,
             "includes": "occupancy-grid march + density for visibility culling + frozen field fwd + weights/reversed weights + "
                         "Field fwd with field_grad + loss + double backward + Adam step (no gradient all-reduce in this leg)"}
 
@@ -440,7 +442,7 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
     reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
     # every step trains on a tuple traced two steps earlier and launches the trace of the batch after next on a side stream
     # (the reference's DataLoader workers do the intersection ahead of the step, too): one trace per step, no host wait
-    pf = HitTuplePrefetcher(sc.mesh_intersect)
+    pf = HitTuplePrefetcher(sc.mesh_intersect, ring=4)       # tuples in 4 recycled buffer sets: no allocator calls per step
 
     def step(i):
         tup = pf.get()
@@ -454,16 +456,19 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0.record()
     samples = 0
     for i in range(steps):
         samples += step(warm + i)
     e1.record()
     barrier()
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
     n_params = sum(p_.numel() for p_ in params)
     return {"metric": "rays_per_sec_field_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s",
             "ms_per_step": ms / steps, "steps": steps, "rays_per_step_per_gpu": n, "samples_per_ray": samples / (n * steps),
+            "cuda_mallocs_in_timed_region": mallocs,
             "params": n_params, "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
             "includes": "trace (of the batch after next, side stream) + frozen field fwd + weights/reversed weights + Field fwd with "
                         "field_grad + loss + double backward + grad all-reduce + Adam step"}
@@ -492,7 +497,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous(), torch.rand((n, 3), device=dev, generator=g)))
     # the tuple of batch i was traced on a side stream during step i-2 and packed during step i-1 (the reference's
     # DataLoader workers run ahead the same way); every step still performs exactly one trace (of the batch after next)
-    pf = HitTuplePrefetcher(sc.mesh_intersect)
+    pf = HitTuplePrefetcher(sc.mesh_intersect, ring=4)       # tuples in 4 recycled buffer sets: no allocator calls per step
 
     def step(i):
         o, d, target = batches[i]
@@ -514,15 +519,18 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
         step(i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0.record()
     hits = 0
     for i in range(steps):
         hits += step(warm + i)
     e1.record()
     barrier()
+    mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
     n_params = sum(p_.numel() for p_ in params)
     return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,
+            "cuda_mallocs_in_timed_region": mallocs,
             "steps": steps, "rays_per_step_per_gpu": n, "hits_per_ray": hits / (n * steps), "params": n_params,
             "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
             "includes": "trace (of the batch after next, side stream) + field fwd + composite + loss + field/composite bwd + grad all-reduce "

@@ -110,8 +110,17 @@ class RayIntersector:
         return o, d, N, K, tri, count, offsets, total, ev
 
     @torch.no_grad()
-    def trace_tuple_end(self, pending):
-        """Second half: wait (host) for the hit total only, size the tuple and pack it on the current stream."""
+    def tuple_buffers(self, capacity: int):
+        """The six tensors of a hit tuple with room for `capacity` hits: (points, vectors, origins (cap,3) f32, depth (cap,)
+        f32, index_ray, index_tri (cap,) i64)."""
+        f = lambda *s: torch.empty((capacity,) + s, dtype=torch.float32, device=self.device)
+        g = lambda: torch.empty((capacity,), dtype=torch.int64, device=self.device)
+        return f(3), f(3), f(3), f(), g(), g()
+
+    @torch.no_grad()
+    def trace_tuple_end(self, pending, alloc=None):
+        """Second half: wait (host) for the hit total only, size the tuple and pack it on the current stream.
+        `alloc(M)` may supply `tuple_buffers` of capacity >= M (a prefetcher's ring); the tuple then aliases them."""
         lib = _lib.load()
         o, d, N, K, tri, count, offsets, total, ev = pending
         ev.synchronize()
@@ -119,11 +128,8 @@ class RayIntersector:
         st = _lib.stream(self.device)
         # M changes from batch to batch: allocating in steps of 32 Ki hits lets the caching allocator hand the previous
         # batch's blocks straight back instead of growing the pool (cudaMalloc stalls the host for milliseconds)
-        cap = (M + 32767) // 32768 * 32768
-        f = lambda *s: torch.empty((cap,) + s, dtype=torch.float32, device=self.device)[:M]
-        points, vecs, org, depth = f(3), f(3), f(3), f()
-        index_ray = torch.empty((cap,), dtype=torch.int64, device=self.device)[:M]
-        index_tri = torch.empty((cap,), dtype=torch.int64, device=self.device)[:M]
+        bufs = alloc(M) if alloc is not None else self.tuple_buffers((M + 32767) // 32768 * 32768)
+        points, vecs, org, depth, index_ray, index_tri = (b[:M] for b in bufs)
         if M:
             _lib.check(lib.qf_hits_pack(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(count),
                                         _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(vecs), _lib.ptr(index_ray),
@@ -281,9 +287,9 @@ class MeshIntersection:
         return self.rayintersector.trace_tuple_begin(origins, vectors, self.num_intersections)
 
     @torch.no_grad()
-    def sampling_raytrace_end(self, pending):
+    def sampling_raytrace_end(self, pending, alloc=None):
         """Second half of `sampling_raytrace_begin`: the 7-tuple (or None), packed on the current stream."""
-        points, vecs, index_ray, depth, index_tri, org, offsets = self.rayintersector.trace_tuple_end(pending)
+        points, vecs, index_ray, depth, index_tri, org, offsets = self.rayintersector.trace_tuple_end(pending, alloc)
         if index_tri.shape[0] == 0:
             return None
         tup = HitTuple((points, vecs, index_ray, depth, index_tri, 0, org))

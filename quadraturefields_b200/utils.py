@@ -212,22 +212,54 @@ class HitTuplePrefetcher:
     for a traversal.  With a single batch in flight `get` completes it on the spot (the one-deep behaviour).  The
     intersection does not depend on the networks' parameters, so the result is identical to tracing inside the step."""
 
-    def __init__(self, mesh_intersect):
+    def __init__(self, mesh_intersect, ring: int = 0):
+        """`ring` > 0: the tuples live in `ring` buffer sets owned by the prefetcher instead of fresh allocations, so a
+        steady-state training loop makes no allocator calls for them (blocks that crossed streams are handed back late by
+        the caching allocator, the pool keeps growing for a while and every `cudaMalloc` stalls the host for
+        milliseconds).  A tuple is then valid until `ring - 1` further `get()` calls; 4 suits the two-deep schedule."""
         self.mesh_intersect = mesh_intersect
         self.stream = torch.cuda.Stream(device=mesh_intersect.device)
         self._inflight = None            # (pending trace, origins, viewdirs): launched, tuple not sized yet
-        self._ready = []                 # [(tuple, event, origins, viewdirs)] in submission order
+        self._ready = []                 # [(tuple, event, origins, viewdirs, ringed)] in submission order
+        self.ring = int(ring)
+        self._sets = [None] * self.ring          # buffer sets, slot = tuple number % ring
+        self._got = [None] * self.ring           # main-stream event recorded by get() number g, at g % ring
+        self._n_completed = 0
+        self._n_got = 0
+
+    def _ring_alloc(self, n):
+        """alloc callback for tuple number n, or None when its slot's previous tuple may still be in use."""
+        R = self.ring
+        if R < 2 or (n >= R and self._n_got < n - R + 2):      # get(n-R+1) not called yet: tuple n-R is not retired
+            return None
+        if n >= R:
+            self.stream.wait_event(self._got[(n - R + 1) % R])  # everything that consumed tuple n-R has been submitted before it
+        main = torch.cuda.current_stream(self.mesh_intersect.device)     # (alloc itself runs under the side stream)
+
+        def alloc(M):
+            cur = self._sets[n % R]
+            if cur is None or cur[0].shape[0] < M:
+                if cur is not None:
+                    for t in cur:
+                        t.record_stream(main)
+                cap = (int(M * 1.25) + 32767) // 32768 * 32768
+                cur = self._sets[n % R] = self.mesh_intersect.rayintersector.tuple_buffers(max(cap, 32768))
+            return cur
+        return alloc
 
     def _complete(self):
         if self._inflight is None:
             return
         pending, origins, viewdirs = self._inflight
         self._inflight = None
+        n = self._n_completed
+        self._n_completed += 1
+        alloc = self._ring_alloc(n) if self.ring else None
         with torch.cuda.stream(self.stream):
-            tup = self.mesh_intersect.sampling_raytrace_end(pending)
+            tup = self.mesh_intersect.sampling_raytrace_end(pending, alloc)
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        self._ready.append((tup, ev, origins, viewdirs))
+        self._ready.append((tup, ev, origins, viewdirs, alloc is not None))
 
     @torch.no_grad()
     def submit(self, origins, viewdirs, rays_ready: bool = False):
@@ -245,13 +277,19 @@ class HitTuplePrefetcher:
         """-> the 7-tuple (or None when nothing was hit) of the oldest submitted batch, safe to use on the current stream."""
         if not self._ready:
             self._complete()
-        tup, ev, origins, viewdirs = self._ready.pop(0)
+        tup, ev, origins, viewdirs, ringed = self._ready.pop(0)
         main = torch.cuda.current_stream(self.mesh_intersect.device)
+        if self.ring:
+            g = torch.cuda.Event()
+            g.record(main)                                  # the consumers of all earlier tuples were submitted before this point
+            self._got[self._n_got % self.ring] = g
+        self._n_got += 1
         main.wait_event(ev)
         if tup is not None:
-            # the tensors were allocated on the side stream: tell the allocator they are now in use on this one, or their
-            # memory could be handed to the next prefetch while this step's backward still reads it
-            for t in list(tup) + [getattr(tup, "offsets", None)]:
+            # tensors allocated on the side stream: tell the allocator they are now in use on this one, or their memory
+            # could be handed to the next prefetch while this step's backward still reads it (ring buffers are never freed;
+            # the ray offsets always come from the allocator)
+            for t in ([] if ringed else list(tup)) + [getattr(tup, "offsets", None)]:
                 if isinstance(t, torch.Tensor):
                     t.record_stream(main)
         return tup

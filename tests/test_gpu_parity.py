@@ -976,10 +976,12 @@ def test_hit_tuple_prefetcher_matches_inline_trace(dev, smoke_scene):
     assert maxabs(outs[0], outs[1]) > 1e-3
 
 
-def test_hit_tuple_prefetcher_two_deep_pipeline(dev, smoke_scene):
+@pytest.mark.parametrize("ring", [0, 3])
+def test_hit_tuple_prefetcher_two_deep_pipeline(dev, smoke_scene, ring):
     """Two batches ahead (`submit, submit, get, submit, get, ...`): the traversal of batch i+2 is launched without a host
     wait while batch i trains; tuples come back in submission order and equal the inline trace, including an all-miss
-    batch (None) in the middle of the queue, and `trace_tuple_begin/_end` equal `trace_tuple`."""
+    batch (None) in the middle of the queue, and `trace_tuple_begin/_end` equal `trace_tuple`; the same with the tuples
+    living in a ring of recycled buffer sets."""
     from quadraturefields_b200.utils import HitTuplePrefetcher
     sc = smoke_scene
     mi = sc.mesh_intersect
@@ -987,8 +989,8 @@ def test_hit_tuple_prefetcher_two_deep_pipeline(dev, smoke_scene):
     o1, d1 = sc.rays(1)
     away = (o0 + 100.0, d0)                                             # every ray misses the mesh
     mid = o0.shape[0] // 2
-    batches = [(o0, d0), away, (o1, d1), (o0[mid - 50:mid + 50], d0[mid - 50:mid + 50]), (o1, d1)]
-    pf = HitTuplePrefetcher(mi)
+    batches = [(o0, d0), away, (o1, d1), (o0[mid - 50:mid + 50], d0[mid - 50:mid + 50]), (o1, d1), (o0, d0), (o1, d1), (o0, d0)]
+    pf = HitTuplePrefetcher(mi, ring=ring)       # ring=3: the buffer sets are recycled twice in this sequence
     pf.submit(*batches[0], rays_ready=True)
     pf.submit(*batches[1], rays_ready=True)
     for i in range(len(batches)):
