@@ -1233,3 +1233,66 @@ def test_sg_field_training_gradients_and_fit(dev, golden, smoke_scene):
         opt.zero_grad(); loss.backward(); opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.9 * losses[0], losses[::3]
+
+
+def test_on_disk_formats_drive_the_kernels(dev, smoke_scene, tmp_path):
+    """f-4 end to end: the quadrature mesh read back from binary PLY and from OBJ-with-uv, the radiance field and the
+    estimator read back from a reference-layout checkpoint and the atlas read back from its PNG set give bit-identical
+    hits, images and decoded features to the in-memory objects they were written from."""
+    from quadraturefields_b200 import mesh_io
+    from quadraturefields_b200.checkpoint import load_checkpoint, save_checkpoint
+    from quadraturefields_b200.mesh_utils import MeshIntersection
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceField
+    from quadraturefields_b200.scene import random_uv, scale_uv
+    from quadraturefields_b200.texture_utils import FeatureCompression
+    from quadraturefields_b200.utils import MeshRenderer
+    sc = smoke_scene
+    o, d = sc.rays(1)
+    ref_tup = sc.mesh_intersect.sampling_raytrace(d, o)
+    uv = random_uv(sc.vertices_np.shape[0], 11).astype(np.float64)
+    ply, obj = str(tmp_path / "mesh.ply"), str(tmp_path / "mesh_uv.obj")
+    mesh_io.save_ply(ply, sc.vertices_np, sc.faces_np, binary=True)
+    mesh_io.save_obj(obj, sc.vertices_np, sc.faces_np, uv)
+    intersectors = {}
+    for path in (ply, obj):
+        mi = MeshIntersection(path, simplify_mesh=False, num_intersections=sc.K, device=dev)
+        assert np.array_equal(mi.mesh.faces, sc.faces_np) and np.array_equal(mi.mesh.vertices.astype(np.float32), sc.vertices_np.astype(np.float32))
+        tup = mi.sampling_raytrace(d, o)
+        for a, b in zip(tup, ref_tup):
+            assert (a == b) if not isinstance(a, torch.Tensor) else torch.equal(a, b)
+        intersectors[path] = mi
+    # checkpoint: NeRF-stage dict -> fresh modules -> identical image
+    rf = sc.radiance_field
+    est = OccGridEstimator(roi_aabb=sc.aabb, resolution=16, levels=1).to(dev)
+    est.occs.uniform_(0, 1); est.binaries.copy_(est.occs.view(est.binaries.shape) > 0.5)
+    ck = str(tmp_path / "model.pth")
+    save_checkpoint(ck, estimator=est, radiance_field=rf, radiance_key="model")
+    rf2 = NGPRadianceField(aabb=sc.aabb, log2_hashmap_size=sc.cfg["log2_T"]).to(dev)
+    est2 = OccGridEstimator(roi_aabb=sc.aabb, resolution=16, levels=1).to(dev)
+    load_checkpoint(ck, estimator=est2, radiance_field=rf2, map_location=dev)
+    assert torch.equal(est2.binaries, est.binaries) and torch.equal(est2.occs, est.occs)
+    img_ref = sc.renderer.render(o, d)
+    img = MeshRenderer(intersectors[ply], radiance_field=rf2).render(o, d)
+    for k in ("rgb", "opacity", "depth"):
+        assert torch.equal(img[k], img_ref[k]), k
+    # atlas: PNG set + uv from the OBJ -> baked frame identical to the in-memory atlas / uv
+    L, S = 2, 64
+    gen = torch.Generator().manual_seed(5)
+    planes = dict(alpha=torch.randint(0, 256, (S, S), dtype=torch.uint8, generator=gen),
+                  diffuse=torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=gen),
+                  sg_colors=[torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=gen) for _ in range(L)],
+                  lambdas=[torch.randint(0, 256, (S, S, 3), dtype=torch.uint8, generator=gen) for _ in range(L)])
+    fc = FeatureCompression(L, planes=planes, compression_type="linear", lambda_thres=5.0, device=dev)
+    tex_dir = str(tmp_path / "texture_64") + "/"
+    import os
+    os.makedirs(tex_dir)
+    fc.save_to_file(tex_dir)
+    fc2 = FeatureCompression(L, path=tex_dir, compression_type="linear", lambda_thres=5.0, device=dev)
+    uv_file = scale_uv(mesh_io.load_mesh(obj).visual.uv, S)                 # test_baking_texture_images.py:323-328
+    assert torch.equal(uv_file, scale_uv(uv, S))
+    baked_ref = MeshRenderer(sc.mesh_intersect, compressor=fc, uv=scale_uv(uv, S)).render(o, d)
+    baked = MeshRenderer(intersectors[obj], compressor=fc2, uv=uv_file).render(o, d)
+    for k in ("rgb", "opacity", "depth"):
+        assert torch.equal(baked[k], baked_ref[k]), k
+    assert float(baked["opacity"].max()) > 0.1
