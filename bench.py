@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
     ap.add_argument("--views", type=int, default=200, help="resident ray sets cycled through (c2: 200 x 15.4 MB)")
-    ap.add_argument("--cpu-sample", type=int, default=100, help="cpu_baseline renders a sample x sample sub-grid of one frame")
+    ap.add_argument("--cpu-sample", type=int, default=800, help="cpu_baseline renders a sample x sample sub-grid of one frame "
+                    "(800 = every ray of a c2 frame, 3-6 s on 8-16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd training-step measurement (extra key 'train')")
     ap.add_argument("--train-rays", type=int, default=1 << 18, help="rays per training batch per GPU (BASELINE configs[2])")
@@ -105,7 +106,8 @@ def cpu_render_sample(sample: int, threads: int, config: str = "c2", steps: int 
     from oracle import quadfield_oracle as O
     from quadraturefields_b200 import scene as S
     torch.set_num_threads(threads)
-    O.PREFER_C = True       # OpenMP C brute force (oracle/bruteforce.c, all host threads) instead of the numpy one
+    O.PREFER_C = True       # the C restatement (oracle/bruteforce.c, all host threads) instead of the numpy one ...
+    O.PREFER_BVH = True     # ... through its CPU BVH (bit-identical to the brute force; the reference's Embree shape)
     cfg = S.CONFIGS[config]
     vertices, faces = O.shell_mesh(cfg["radii"], cfg["sub"], jitter=1e-3, seed=42)
     f, cx, cy, W, H = O.pinhole_intrinsics(cfg["W"], cfg["H"], S.CAMERA_ANGLE_X)
@@ -137,16 +139,16 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 128
+    sample = 256
     rps, detail, sec = cpu_render_sample(sample, threads, args.config, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     desc = (f"{sample}x{sample} sub-grid of one {args.config} frame per step; intersect {detail.get('intersect_s', 0):.2f}s "
-            f"(OpenMP brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite {detail.get('composite_s', 0):.3f}s; "
+            f"(OpenMP CPU BVH traversal), field {detail.get('field_s', 0):.2f}s, composite {detail.get('composite_s', 0):.3f}s; "
             f"{detail.get('hits', 0)} hits")
     line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "note": "reference path is CUDA-only with un-installable native "
-                       "dependencies; timed here as its CPU port in oracle/ (OpenMP C intersector + PyTorch field and compositing)"},
+                       "dependencies; timed here as its CPU port in oracle/ (OpenMP C BVH intersector + PyTorch field and compositing)"},
             "cpu_baseline": {"value": rps, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
             "e2e": {"value": rps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -354,7 +356,7 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
                                     "sample": f"{args.cpu_sample}x{args.cpu_sample} sub-grid of one frame ({detail.get('rays')} rays, "
                                               f"{detail.get('hits')} hits) in {sec:.1f}s: intersect {detail.get('intersect_s', 0):.1f}s "
-                                              f"(OpenMP brute force O(N*F)), field {detail.get('field_s', 0):.2f}s, composite "
+                                              f"(OpenMP CPU BVH traversal), field {detail.get('field_s', 0):.2f}s, composite "
                                               f"{detail.get('composite_s', 0):.3f}s"}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -279,6 +279,32 @@ def intersect_firstk_c(origins, dirs, vertices, faces, K: int):
     return tri, tt, count, total
 
 
+def intersect_firstk_bvh_c(origins, dirs, vertices, faces, K: int, want_total: bool = True):
+    """`intersect_firstk` through a CPU bounding-volume hierarchy (oracle/bruteforce.c: qf_oracle_intersect_firstk_bvh):
+    the shape of the reference's shipped CPU path (Embree behind trimesh, mesh_utils.py:223,350-354), bit-identical to
+    the brute force (tests/test_oracle_golden.py::test_c_bvh_matches_bruteforce).  `want_total=False` lets the traversal
+    cull behind the K-th hit (total = -1)."""
+    import ctypes as C
+    lib = _c_oracle()
+    if lib is None or not hasattr(lib, "qf_oracle_intersect_firstk_bvh"):
+        raise RuntimeError("oracle/_ref/libqf_oracle.so missing or stale: run __graft_entry__.build()")
+    o = np.ascontiguousarray(origins, dtype=np.float32)
+    d = np.ascontiguousarray(dirs, dtype=np.float32)
+    v = np.ascontiguousarray(vertices, dtype=np.float32)
+    f = np.ascontiguousarray(faces, dtype=np.int32)
+    N, Fn = o.shape[0], f.shape[0]
+    tri = np.empty((N, K), dtype=np.int32)
+    tt = np.empty((N, K), dtype=np.float32)
+    count = np.empty(N, dtype=np.int32)
+    total = np.empty(N, dtype=np.int32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.qf_oracle_intersect_firstk_bvh.restype = None
+    lib.qf_oracle_intersect_firstk_bvh(P(o), P(d), C.c_int64(N), P(v), P(f), C.c_int64(Fn), C.c_int(K),
+                                       C.c_float(float(mesh_box_pad(v))), C.c_int(1 if want_total else 0), P(tri), P(tt),
+                                       P(count), P(total))
+    return tri, tt, count, total
+
+
 def plane_hit_points(o, r, n, v):
     """mesh_utils.py:33-40 ``ray_triangle_intersection``: d=−(n·v); t=−((n·o)+d)/(n·r); t←|t|; ψ=o+t r.  fp32."""
     o, r, n, v = (np.asarray(a, dtype=np.float32) for a in (o, r, n, v))
@@ -291,12 +317,15 @@ def plane_hit_points(o, r, n, v):
 
 
 PREFER_C = False   # bench.py's CPU legs set this: the OpenMP C restatement (identical results) is the faster CPU path
+PREFER_BVH = False  # bench.py's CPU legs set this too: CPU BVH traversal (identical results), the reference's Embree shape
 
 
 def intersects_id(origins, vectors, vertices, faces, max_hits: int, threads: int = 1):
     """The `RayIntersector.intersects_id` contract (mesh_utils.py:87-109): flat
     (triangle_indices, ray_indices, psi) over all kept hits, ray-major in slot order."""
-    if (PREFER_C or np.asarray(faces).shape[0] > 100000) and _c_oracle() is not None:   # the C restatement (identical results)
+    if PREFER_BVH and _c_oracle() is not None and hasattr(_c_oracle(), "qf_oracle_intersect_firstk_bvh"):
+        tri, _, count, _ = intersect_firstk_bvh_c(origins, vectors, vertices, faces, max_hits, want_total=False)
+    elif (PREFER_C or np.asarray(faces).shape[0] > 100000) and _c_oracle() is not None:   # the C restatement (identical results)
         tri, _, count, _ = intersect_firstk_c(origins, vectors, vertices, faces, max_hits)
     else:
         tri, _, count, _ = intersect_firstk(origins, vectors, vertices, faces, max_hits, threads=threads)

@@ -248,3 +248,35 @@ def test_c_bruteforce_matches_numpy():
         for x, y in zip(a, b):
             assert np.array_equal(x, y)
     assert a[3].max() >= 6
+
+
+def test_c_bvh_matches_bruteforce():
+    """The CPU BVH traversal of oracle/bruteforce.c (bench.py's CPU baseline, the shape of the reference's Embree path) is
+    bit-identical to the brute force: ids, distances, counts and totals, with and without culling behind the K-th hit,
+    including axis-aligned rays, rays starting inside the mesh, duplicated triangles (equal t, order by id) and K > hits."""
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    verts, faces = O.shell_mesh([0.5, 0.8, 1.0], 3, seed=4)
+    faces = np.concatenate([faces, faces[:40]])                        # duplicates: ties in t resolved by triangle id
+    f, cx, cy, W, H = O.pinhole_intrinsics(48, 48, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((2.0, -2.5, 1.5)), W, H, f, cx, cy)
+    rng = np.random.RandomState(1)
+    o2 = rng.uniform(-0.9, 0.9, size=(600, 3)).astype(np.float32)
+    d2 = np.zeros((600, 3), dtype=np.float32)
+    d2[np.arange(600), np.arange(600) % 3] = 1.0
+    d2[300:] = rng.normal(size=(300, 3)).astype(np.float32)
+    o, d = np.concatenate([o, o2]), np.concatenate([d, d2])
+    for K in (1, 3, 8, 32):
+        a = O.intersect_firstk_c(o, d, verts, faces, K)
+        b = O.intersect_firstk_bvh_c(o, d, verts, faces, K, want_total=True)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        c = O.intersect_firstk_bvh_c(o, d, verts, faces, K, want_total=False)
+        for x, y in zip(a[:3], c[:3]):
+            assert np.array_equal(x, y)
+    assert a[3].max() >= 6 and (a[2] == 0).any()
+    # single triangle, empty ray set
+    one = O.intersect_firstk_bvh_c(o[:5], d[:5], verts, faces[:1], 2)
+    ref = O.intersect_firstk_c(o[:5], d[:5], verts, faces[:1], 2)
+    assert all(np.array_equal(x, y) for x, y in zip(one, ref))
+    assert O.intersect_firstk_bvh_c(o[:0], d[:0], verts, faces, 2)[0].shape == (0, 2)
