@@ -350,7 +350,7 @@ def run_ours(args):
             line["train"] = train
             line["field_train"] = field_train
             line["field_train_occgrid"] = field_train_occ
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # rank 0 at N=1 only (torchrun pins OMP_NUM_THREADS=1 anyway)
             threads = os.cpu_count() or 1
             rps, detail, sec = cpu_render_sample(args.cpu_sample, threads, args.config)
             line["cpu_baseline"] = {"value": rps, "unit": UNIT, "cores": threads, "kind": "port",
