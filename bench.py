@@ -441,6 +441,7 @@ def run_field_train_steps(args, sc, dev, rank, world, barrier):
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous()))
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
+    net.accumulate_grad_in_place = True         # the grid scatter adds into .grad directly
     reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
     # every step trains on a tuple traced two steps earlier and launches the trace of the batch after next on a side stream
     # (the reference's DataLoader workers do the intersection ahead of the step, too): one trace per step, no host wait
@@ -515,6 +516,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
 
     for p_ in params:
         p_.grad = torch.zeros_like(p_)
+    rf.accumulate_grad_in_place = True          # backward adds into .grad directly (no 50 MB zero buffer + autograd add per step)
     pf.submit(batches[0][0], batches[0][1], rays_ready=True)
     pf.submit(batches[1][0], batches[1][1], rays_ready=True)
     for i in range(warm):
@@ -529,6 +531,7 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     e1.record()
     barrier()
     mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs
+    rf.accumulate_grad_in_place = False
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
     n_params = sum(p_.numel() for p_ in params)
     return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,

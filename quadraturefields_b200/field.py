@@ -81,14 +81,17 @@ class _FieldFn(torch.autograd.Function):
         h = net._native()
         gf = None if g_field is None else _lib.f32(g_field)
         gg = None if g_fgrad is None else _lib.f32(g_fgrad)
-        g_table = torch.zeros_like(net.xyz_encoder.params)
+        # `accumulate_grad_in_place` (see NGPRadianceField): the grid scatter adds into `xyz_encoder.params.grad` directly
+        pt = net.xyz_encoder.params
+        inplace = getattr(net, "accumulate_grad_in_place", False) and pt.grad is not None and pt.grad.is_contiguous()
+        g_table = pt.grad if inplace else torch.zeros_like(pt)
         grads = [None if t is None else torch.zeros_like(t) for t in ws]
         if M > 0 and (gf is not None or gg is not None):
             _lib.check(lib.qf_field_backward(h, C.byref(net._fdesc), *[_opt_ptr(t) for t in ws], _lib.ptr(x), M, _opt_ptr(gf),
                                              _opt_ptr(gg), _lib.ptr(g_table), _lib.ptr(grads[0]), _opt_ptr(grads[1]),
                                              _lib.ptr(grads[2]), _opt_ptr(grads[3]), _lib.ptr(grads[4]), _opt_ptr(grads[5]),
                                              _lib.stream(dev)), "qf_field_backward")
-        return (None, None, None, g_table, *grads)
+        return (None, None, None, None if inplace else g_table, *grads)
 
 
 class Field(nn.Module):

@@ -80,8 +80,14 @@ class _NGPForwardFn(torch.autograd.Function):
         M = pos.shape[0]
         dev = pos.device
         h = field._native()
-        g_base = torch.zeros_like(field.mlp_base.params)
-        g_head = torch.zeros_like(field.mlp_head.params)
+        # `accumulate_grad_in_place`: the kernels add into `.grad` directly (they accumulate anyway: atomics into the table
+        # gradient, `+=` for the matrices) instead of into fresh zero buffers that autograd then adds to `.grad` — saves a
+        # 50 MB memset and a 150 MB read-modify-write per step at T=2^19; needs preallocated `.grad` tensors
+        pb, ph = field.mlp_base.params, field.mlp_head.params
+        inplace = (getattr(field, "accumulate_grad_in_place", False) and pb.grad is not None and ph.grad is not None
+                   and pb.grad.is_contiguous() and ph.grad.is_contiguous())
+        g_base = pb.grad if inplace else torch.zeros_like(pb)
+        g_head = ph.grad if inplace else torch.zeros_like(ph)
         g_pos = torch.zeros((M, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         if M:
             g_rgb = _lib.f32(g_rgb) if g_rgb is not None else torch.zeros((M, 3), device=dev)
@@ -93,6 +99,8 @@ class _NGPForwardFn(torch.autograd.Function):
                                                   _lib.ptr(ws), ws.numel(), _lib.stream(dev)), "qf_ngp_backward_inputs")
         if g_pos is not None:
             g_pos = g_pos.view(ctx.pos_shape)
+        if inplace:
+            return None, g_pos, None, None, None, None
         return None, g_pos, None, None, g_base, g_head
 
 

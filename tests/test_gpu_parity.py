@@ -1296,3 +1296,51 @@ def test_on_disk_formats_drive_the_kernels(dev, smoke_scene, tmp_path):
     for k in ("rgb", "opacity", "depth"):
         assert torch.equal(baked[k], baked_ref[k]), k
     assert float(baked["opacity"].max()) > 0.1
+
+
+def test_gradients_accumulated_in_place_equal_autograd_accumulation(dev, smoke_scene):
+    """`accumulate_grad_in_place`: the backward kernels add into `.grad` directly; same gradients as fresh buffers +
+    autograd's accumulation (fp32 atomics are order-dependent, hence the 1e-5 band), also on top of a non-zero `.grad`,
+    for the radiance field and for the quadrature Field net."""
+    from quadraturefields_b200.field import Field
+    from quadraturefields_b200.utils import render_train
+    sc = smoke_scene
+    rf = sc.radiance_field
+    o, d = sc.rays(0)
+    tgt = torch.rand((o.shape[0], 3), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    params = [rf.mlp_base.params, rf.mlp_head.params]
+
+    def grads(inplace, seed_grad):
+        rf.accumulate_grad_in_place = inplace
+        for p_ in params:
+            p_.grad = torch.full_like(p_, seed_grad)
+        rgb, _, _, _ = render_train(sc.mesh_intersect, rf, o, d)
+        torch.nn.functional.smooth_l1_loss(rgb, tgt).backward()
+        out = [p_.grad.clone() for p_ in params]
+        rf.accumulate_grad_in_place = False
+        rf.zero_grad()
+        return out
+
+    scale = max(float(g.abs().max()) for g in grads(False, 0.0))
+    assert scale > 0
+    for seed_grad in (0.0, 0.5 * scale):          # the second pass accumulates on top of a non-zero .grad of the same magnitude
+        a, b = grads(False, seed_grad), grads(True, seed_grad)
+        for x, y in zip(a, b):
+            # a wrong accumulation (twice, or not at all) is an O(1) relative error; summation order is ~1e-6
+            assert maxabs(x, y) <= 2e-4 * float((x - seed_grad).abs().max()), (seed_grad, maxabs(x, y), float((x - seed_grad).abs().max()))
+    net = Field(scale=0.5, precision=16, log2_T=14, L=16, max_res=128, min_res=16, output_dim=1, hidden_size=16,
+                num_features=2, back_prop=False, nl="elu").to(dev)
+    with torch.no_grad():
+        net.xyz_encoder.params.mul_(1e3)
+    x = (torch.rand((5000, 3), device=dev, generator=torch.Generator(device=dev).manual_seed(9)) - 0.5) * 0.9
+    res = []
+    for inplace in (False, True):
+        net.accumulate_grad_in_place = inplace
+        for p_ in net.parameters():
+            p_.grad = torch.zeros_like(p_)
+        f, fg = net(x)
+        (f.square().mean() + fg.square().mean()).backward()
+        res.append([p_.grad.clone() for p_ in net.parameters()])
+    net.accumulate_grad_in_place = False
+    for x_, y_ in zip(*res):
+        assert maxabs(x_, y_) <= 2e-4 * float(x_.abs().max()) + 1e-12, (maxabs(x_, y_), float(x_.abs().max()))
