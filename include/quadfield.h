@@ -323,6 +323,12 @@ int qf_profile_read(double* ms3, int64_t* n_chunks);
 /* a1: eval-mode pinhole rays of one camera (datasets/nerf_synthetic.py:310-360), c2w (3,4) row-major on host */
 int qf_generate_rays(const float* h_c2w, int W, int H, float focal, float cx, float cy, int opengl,
                      float* d_origins, float* d_viewdirs, void* stream);
+/* a1, training branch (datasets/nerf_synthetic.py:293-309, 341-370): ray i looks through pixel (x[i], y[i]) of camera
+ * image_id[i] (NULL = camera 0 for all).  c2w (n_views,3,4) row-major ON THE DEVICE; x, y fp32 (pixel indices, or index +
+ * U[0,1) for add_ray_direction_noise).  An id outside [0, n_views) yields a NaN ray. */
+int qf_generate_rays_indexed(const float* d_c2w, int64_t n_views, const int64_t* d_image_id, const float* d_x,
+                             const float* d_y, int64_t n, float focal, float cx, float cy, int opengl,
+                             float* d_origins, float* d_viewdirs, void* stream);
 
 #ifdef __cplusplus
 }

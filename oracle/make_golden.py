@@ -428,14 +428,82 @@ def _np(v):
     return np.asarray(v)
 
 
+def golden_ray_generation():
+    """a1: the reference's `SubjectLoader` (datasets/nerf_synthetic.py:157-378) executed on a tiny NeRF-synthetic-shaped
+    dataset written to a temporary directory (transforms_*.json + RGBA PNGs, non-square so that a W/H swap shows): file
+    loading, the eval branch (row-major rays of a whole image, upsample 1 and 2, white background) and the training
+    branch (random images / pixels, random background colour, `add_ray_direction_noise`).  The random draws are
+    replayed with the same seed and the same call order to record which (image, x, y) each training ray belongs to."""
+    import json
+    import tempfile
+    from PIL import Image
+    import datasets.nerf_synthetic as NS
+    rng = np.random.RandomState(17)
+    W, H, n_img = 12, 10, 3
+    out = {}
+    with tempfile.TemporaryDirectory() as root:
+        os.makedirs(os.path.join(root, "toy", "train"))
+        os.makedirs(os.path.join(root, "toy", "test"))
+        for split in ("train", "test"):
+            frames = []
+            for i in range(n_img):
+                img = rng.randint(0, 256, size=(H, W, 4)).astype(np.uint8)
+                Image.fromarray(img, mode="RGBA").save(os.path.join(root, "toy", split, f"r_{i}.png"))
+                ang = 0.7 * i + (0.3 if split == "test" else 0.0)
+                eye = np.array([4.0 * np.cos(ang), 4.0 * np.sin(ang), 1.0 + 0.5 * i])
+                fwd = -eye / np.linalg.norm(eye)
+                right = np.cross(fwd, [0.0, 0.0, 1.0]); right /= np.linalg.norm(right)
+                up = np.cross(right, fwd)
+                m = np.eye(4)
+                m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, eye
+                frames.append({"file_path": f"./{split}/r_{i}", "transform_matrix": m.tolist()})
+            with open(os.path.join(root, "toy", f"transforms_{split}.json"), "w") as f:
+                json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, f)
+        for up in (1, 2):
+            ds = NS.SubjectLoader("toy", root, "test", num_rays=None, upsample=up)
+            d = ds[1]
+            out[f"eval{up}_origins"], out[f"eval{up}_viewdirs"] = d["rays"].origins, d["rays"].viewdirs
+            out[f"eval{up}_pixels"], out[f"eval{up}_color_bkgd"] = d["pixels"], d["color_bkgd"]
+            out[f"eval{up}_K"] = ds.K
+        out["images_test"], out["camtoworlds_test"], out["focal"] = ds.images, ds.camtoworlds, np.float64(ds.focal / 2)
+        for tag, kw in (("train", {}), ("train_noise", {"add_ray_direction_noise": True}), ("train_single", {"batch_over_images": False})):
+            n = 40
+            ds = NS.SubjectLoader("toy", root, "train", color_bkgd_aug="random", num_rays=n, upsample=2, **kw)
+            torch.manual_seed(123)
+            d = ds[2]
+            torch.manual_seed(123)                       # replay the draws of fetch_data (:293-309) in the same order
+            image_id = torch.randint(0, n_img, (n,)) if kw.get("batch_over_images", True) else torch.full((n,), 2)
+            x = torch.randint(0, ds.WIDTH, (n,))
+            y = torch.randint(0, ds.HEIGHT, (n,))
+            if kw.get("add_ray_direction_noise"):
+                xf = x.float() + torch.rand_like(x.float())
+                yf = y.float() + torch.rand_like(y.float())
+                out[tag + "_xf"], out[tag + "_yf"] = xf, yf
+            out[tag + "_color_bkgd_replayed"] = torch.rand(3)
+            out[tag + "_image_id"], out[tag + "_x"], out[tag + "_y"] = image_id, x, y
+            out[tag + "_origins"], out[tag + "_viewdirs"] = d["rays"].origins, d["rays"].viewdirs
+            out[tag + "_pixels"], out[tag + "_color_bkgd"] = d["pixels"], d["color_bkgd"]
+        out["images_train"], out["camtoworlds_train"] = ds.images, ds.camtoworlds
+        out["train_K"] = ds.K
+        # the dataset itself (PNG bytes + json), so the product's reader is tested on the very files the reference read
+        for split in ("train", "test"):
+            out[f"json_{split}"] = np.frombuffer(open(os.path.join(root, "toy", f"transforms_{split}.json"), "rb").read(), dtype=np.uint8)
+            for i in range(n_img):
+                out[f"png_{split}_{i}"] = np.frombuffer(open(os.path.join(root, "toy", split, f"r_{i}.png"), "rb").read(), dtype=np.uint8)
+    return out
+
+
 def main():
     _install()
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
     for name, fn in (("field_rendering", golden_field_rendering), ("sg_decode", golden_sg_decode),
                      ("geometry", golden_geometry), ("derive_properties", golden_derive_properties),
                      ("ngp", golden_ngp), ("mesh_finetune", golden_mesh_finetune),
                      ("field_net", golden_field_net), ("finetune_step", golden_finetune_step),
-                     ("sg_field", golden_sg_field)):
+                     ("sg_field", golden_sg_field), ("ray_generation", golden_ray_generation)):
+        if only and name not in only:
+            continue
         data = {k: _np(v) for k, v in fn().items()}
         path = os.path.join(OUT, name + ".npz")
         np.savez_compressed(path, **data)

@@ -58,6 +58,34 @@ def generate_rays(c2w: np.ndarray, W: int, H: int, focal, cx, cy, opengl: bool =
     return origins.contiguous().numpy().copy(), viewdirs.contiguous().numpy().copy()
 
 
+def generate_rays_indexed(camtoworlds, image_id, x, y, focal, cx, cy, opengl: bool = True):
+    """Training-branch rays: nerf_synthetic.py:341-370 with one camera matrix per ray (`c2w = camtoworlds[image_id]`,
+    :337).  x, y: pixel indices (int) or index + noise (float).  -> origins (n,3), viewdirs (n,3) fp32."""
+    c2w = torch.as_tensor(np.asarray(camtoworlds, dtype=np.float32))[torch.as_tensor(np.asarray(image_id, dtype=np.int64))]
+    x, y = torch.as_tensor(np.asarray(x)), torch.as_tensor(np.asarray(y))
+    K00, cxt, cyt = (torch.tensor(v, dtype=torch.float32) for v in (focal, cx, cy))
+    sgn = -1.0 if opengl else 1.0
+    camera_dirs = torch.nn.functional.pad(
+        torch.stack([(x - cxt + 0.5) / K00, (y - cyt + 0.5) / K00 * sgn], dim=-1), (0, 1), value=sgn
+    )
+    directions = (camera_dirs[:, None, :] * c2w[:, :3, :3]).sum(dim=-1)
+    origins = torch.broadcast_to(c2w[:, :3, -1], directions.shape)
+    viewdirs = directions / torch.linalg.norm(directions, dim=-1, keepdims=True)
+    return origins.contiguous().numpy().copy(), viewdirs.contiguous().numpy().copy()
+
+
+def subject_pixels(images, image_id, x, y, upsample: int, color_bkgd):
+    """Target colours of a batch: nerf_synthetic.py:331 (rgba at floor(y/upsample), floor(x/upsample)) and :266-281
+    (alpha-composite over the background colour).  images (n,h,w,4) uint8 -> (n_rays,3) fp32."""
+    img = torch.as_tensor(np.asarray(images))
+    iid = torch.as_tensor(np.asarray(image_id, dtype=np.int64))
+    xi, yi = torch.as_tensor(np.asarray(x)), torch.as_tensor(np.asarray(y))
+    rgba = img[iid, torch.floor(yi / upsample).long(), torch.floor(xi / upsample).long()] / 255.0
+    pixels, alpha = torch.split(rgba, [3, 1], dim=-1)
+    bk = torch.as_tensor(np.asarray(color_bkgd, dtype=np.float32))
+    return (pixels * alpha + bk * (1.0 - alpha)).numpy()
+
+
 def look_at_c2w(eye, target=(0.0, 0.0, 0.0), up=(0.0, 0.0, 1.0)) -> np.ndarray:
     """OpenGL-convention camera-to-world (camera looks down −z), used only to make synthetic poses."""
     eye = np.asarray(eye, dtype=np.float64)

@@ -201,6 +201,33 @@ __global__ void generate_rays_kernel(float r00, float r01, float r02, float r10,
   origins[3 * i] = tx; origins[3 * i + 1] = ty; origins[3 * i + 2] = tz;
 }
 
+// Training-mode rays (nerf_synthetic.py:293-309, 341-370): ray i looks through pixel (x[i], y[i]) of camera image_id[i];
+// x / y arrive as floats (integer pixel indices, or index + U[0,1) with add_ray_direction_noise).  Same operation order
+// as generate_rays_kernel, per-ray camera matrix.
+__global__ void generate_rays_indexed_kernel(const float* __restrict__ c2w, int64_t n_views, const int64_t* __restrict__ image_id,
+                                             const float* __restrict__ xs, const float* __restrict__ ys, int64_t n, float focal,
+                                             float cx, float cy, float sgn, float* __restrict__ origins,
+                                             float* __restrict__ viewdirs) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t v = image_id ? image_id[i] : 0;
+  if (v < 0 || v >= n_views) {   // an id outside the camera array: poison the ray instead of reading out of bounds
+    const float q = __int_as_float(0x7fc00000);
+    for (int k = 0; k < 3; ++k) { origins[3 * i + k] = q; viewdirs[3 * i + k] = q; }
+    return;
+  }
+  const float* m = c2w + 12 * v;
+  float cxd = __fdiv_rn(__fadd_rn(__fsub_rn(xs[i], cx), 0.5f), focal);
+  float cyd = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn(ys[i], cy), 0.5f), focal), sgn);
+  float czd = sgn;
+  float dx = __fadd_rn(__fadd_rn(__fmul_rn(cxd, m[0]), __fmul_rn(cyd, m[1])), __fmul_rn(czd, m[2]));
+  float dy = __fadd_rn(__fadd_rn(__fmul_rn(cxd, m[4]), __fmul_rn(cyd, m[5])), __fmul_rn(czd, m[6]));
+  float dz = __fadd_rn(__fadd_rn(__fmul_rn(cxd, m[8]), __fmul_rn(cyd, m[9])), __fmul_rn(czd, m[10]));
+  float nrm = norm3(dx, dy, dz);
+  viewdirs[3 * i] = __fdiv_rn(dx, nrm); viewdirs[3 * i + 1] = __fdiv_rn(dy, nrm); viewdirs[3 * i + 2] = __fdiv_rn(dz, nrm);
+  origins[3 * i] = m[3]; origins[3 * i + 1] = m[7]; origins[3 * i + 2] = m[11];
+}
+
 enum class Shade { NGP, BAKED };
 
 // Optional per-stage CUDA-event timing of the fused render (bench.py's roofline uses it): events are recorded on
@@ -302,6 +329,19 @@ extern "C" int qf_generate_rays(const float* c, int W, int H, float focal, float
   generate_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10],
                                                                                 c[3], c[7], c[11], W, H, focal, cx, cy,
                                                                                 opengl ? -1.0f : 1.0f, d_origins, d_viewdirs);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int qf_generate_rays_indexed(const float* d_c2w, int64_t n_views, const int64_t* d_image_id, const float* d_x,
+                                        const float* d_y, int64_t n, float focal, float cx, float cy, int opengl,
+                                        float* d_origins, float* d_viewdirs, void* stream) {
+  QF_REQUIRE(n >= 0 && n_views >= 1 && focal > 0.f, "qf_generate_rays_indexed: n=%lld views=%lld focal=%f", (long long)n,
+             (long long)n_views, focal);
+  if (n == 0) return QF_OK;
+  QF_REQUIRE(d_c2w && d_x && d_y && d_origins && d_viewdirs, "qf_generate_rays_indexed: NULL argument");
+  generate_rays_indexed_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      d_c2w, n_views, d_image_id, d_x, d_y, n, focal, cx, cy, opengl ? -1.0f : 1.0f, d_origins, d_viewdirs);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

@@ -1344,3 +1344,62 @@ def test_gradients_accumulated_in_place_equal_autograd_accumulation(dev, smoke_s
     net.accumulate_grad_in_place = False
     for x_, y_ in zip(*res):
         assert maxabs(x_, y_) <= 2e-4 * float(x_.abs().max()) + 1e-12, (maxabs(x_, y_), float(x_.abs().max()))
+
+
+def test_subject_loader_matches_reference_fixture(dev, golden, smoke_scene, tmp_path):
+    """a1 through the product's `SubjectLoader` on the GPU, against the reference's loader executed on the same toy dataset
+    (`tests/golden/ray_generation.npz`): evaluation images at upsample 1 and 2 and training batches with the reference's
+    random draws replayed (plain, with direction noise, single-image batches) — origins bit for bit, unit directions and
+    target colours to an ulp or two; the
+    `mesh_intersect=` hook hands over the GPU hit tuple; camera ids outside the array poison the ray."""
+    import os
+    from quadraturefields_b200.datasets.nerf_synthetic import SubjectLoader
+    from quadraturefields_b200.datasets.ray_gen import generate_rays_indexed
+    g = golden("ray_generation")
+    root = tmp_path / "toy"
+    for split in ("train", "test"):
+        os.makedirs(root / split)
+        (root / f"transforms_{split}.json").write_bytes(g[f"json_{split}"].tobytes())
+        for i in range(3):
+            (root / split / f"r_{i}.png").write_bytes(g[f"png_{split}_{i}"].tobytes())
+    eq = lambda a, ref: torch.equal(a.cpu(), T(ref))
+    # unit directions: 1 ulp.  The un-normalised directions agree bit for bit; torch's CPU `linalg.norm` reduction is
+    # neither the fp32 operation sequence nor a double-precision accumulation (it differs from both on ~5 % of the rays)
+    ulp = lambda a, ref: maxabs(a, ref) <= 2e-7
+    # target colours: torch's CUDA `x / 255.0` multiplies by the reciprocal (1 ulp off the IEEE quotient the CPU computes),
+    # which the reference's own loader would do as well when it is given a CUDA device
+    col = lambda a, ref: maxabs(a, ref) <= 5e-7
+    for up in (1, 2):
+        ds = SubjectLoader("toy", str(tmp_path), "test", num_rays=None, upsample=up, device=dev)
+        assert not ds.training and (ds.WIDTH, ds.HEIGHT) == (12 * up, 10 * up) and eq(ds.K, g[f"eval{up}_K"])
+        d = ds[1 + 3 * up]                                              # index wraps modulo the number of images
+        assert eq(d["rays"].origins, g[f"eval{up}_origins"]) and ulp(d["rays"].viewdirs, g[f"eval{up}_viewdirs"])
+        assert col(d["pixels"], g[f"eval{up}_pixels"]) and eq(d["color_bkgd"], g[f"eval{up}_color_bkgd"])
+    for tag, kw in (("train", {}), ("train_noise", {"add_ray_direction_noise": True}), ("train_single", {"batch_over_images": False})):
+        ds = SubjectLoader("toy", str(tmp_path), "train", color_bkgd_aug="white", num_rays=40, upsample=2, device=dev, **kw)
+        assert ds.training and eq(ds.images, g["images_train"]) and eq(ds.camtoworlds, g["camtoworlds_train"])
+        x = T(g[tag + "_xf"] if tag == "train_noise" else g[tag + "_x"])
+        y = T(g[tag + "_yf"] if tag == "train_noise" else g[tag + "_y"])
+        iid = None if tag == "train_single" else T(g[tag + "_image_id"])
+        raw = ds.fetch_data(2, image_id=iid, x=x, y=y)
+        assert eq(raw["rays"].origins, g[tag + "_origins"]) and ulp(raw["rays"].viewdirs, g[tag + "_viewdirs"]), tag
+        if tag != "train_noise":        # (with noise the target pixel comes from the integer index drawn before the noise)
+            out = ds.preprocess(raw)
+            ref = O.subject_pixels(g["images_train"], g[tag + "_image_id"], g[tag + "_x"], g[tag + "_y"], 2, [1.0, 1.0, 1.0])
+            assert col(out["pixels"], ref), tag
+        d = ds[0]                                                        # own random draws: shapes, ranges, unit directions
+        assert d["rays"].origins.shape == (40, 3) and d["pixels"].shape == (40, 3)
+        assert float((d["rays"].viewdirs.norm(dim=-1) - 1).abs().max()) < 1e-6
+    # random background, hit-tuple hook
+    sc = smoke_scene
+    ds = SubjectLoader("toy", str(tmp_path), "train", color_bkgd_aug="random", num_rays=256, device=dev, mesh_intersect=sc.mesh_intersect)
+    d = ds[1]
+    ref = sc.mesh_intersect.sampling_raytrace(d["rays"].viewdirs, d["rays"].origins)
+    assert ref is not None and len(d["data"]) == 6
+    for a, b in zip(d["data"], [ref[0], ref[1], ref[2], ref[3], ref[4], ref[6]]):
+        assert torch.equal(a, b)
+    assert torch.equal(d["data"].offsets, ref.offsets) and 0.0 <= float(d["color_bkgd"].min()) <= float(d["color_bkgd"].max()) <= 1.0
+    bad = generate_rays_indexed(ds.camtoworlds, torch.tensor([0, 3, -1], device=dev), torch.zeros(3), torch.zeros(3), 10.0, 6.0, 5.0)
+    assert bool(torch.isfinite(bad.viewdirs[0]).all()) and bool(torch.isnan(bad.viewdirs[1:]).all()) and bool(torch.isnan(bad.origins[1:]).all())
+    with pytest.raises(RuntimeError):
+        SubjectLoader("toy", str(tmp_path), "train", num_rays=8, device="cpu")

@@ -280,3 +280,42 @@ def test_c_bvh_matches_bruteforce():
     ref = O.intersect_firstk_c(o[:5], d[:5], verts, faces[:1], 2)
     assert all(np.array_equal(x, y) for x, y in zip(one, ref))
     assert O.intersect_firstk_bvh_c(o[:0], d[:0], verts, faces, 2)[0].shape == (0, 2)
+
+
+def test_ray_generation_golden(golden, tmp_path):
+    """a1 pinned: the oracle's ray generation and target colours against the reference's `SubjectLoader` executed on a toy
+    dataset (eval branch at upsample 1 and 2, training branch with replayed random draws, direction noise, single-image
+    batches), bit for bit; and the product's file reader on the very files the reference read."""
+    g = golden("ray_generation")
+    W0, H0 = 12, 10
+    for up in (1, 2):
+        K = g[f"eval{up}_K"]
+        o, d = O.generate_rays(g["camtoworlds_test"][1], W0 * up, H0 * up, K[0, 0], K[0, 2], K[1, 2])
+        assert np.array_equal(o, g[f"eval{up}_origins"]) and np.array_equal(d, g[f"eval{up}_viewdirs"])
+        f32, cx, cy, W, H = O.pinhole_intrinsics(W0, H0, 0.6911112070083618, upsample=up)
+        assert (f32, cx, cy, W, H) == (K[0, 0], K[0, 2], K[1, 2], W0 * up, H0 * up)
+        x, y = np.meshgrid(np.arange(W0), np.arange(H0), indexing="xy")
+        px = O.subject_pixels(g["images_test"], np.full(W0 * H0, 1), x.flatten(), y.flatten(), 1, [1.0, 1.0, 1.0])
+        assert np.array_equal(px, g[f"eval{up}_pixels"]) and np.array_equal(g[f"eval{up}_color_bkgd"], [1, 1, 1])
+    K = g["train_K"]
+    for tag in ("train", "train_noise", "train_single"):
+        x = g[tag + "_xf"] if tag == "train_noise" else g[tag + "_x"]
+        y = g[tag + "_yf"] if tag == "train_noise" else g[tag + "_y"]
+        o, d = O.generate_rays_indexed(g["camtoworlds_train"], g[tag + "_image_id"], x, y, K[0, 0], K[0, 2], K[1, 2])
+        assert np.array_equal(o, g[tag + "_origins"]) and np.array_equal(d, g[tag + "_viewdirs"]), tag
+        px = O.subject_pixels(g["images_train"], g[tag + "_image_id"], g[tag + "_x"], g[tag + "_y"], 2, g[tag + "_color_bkgd"])
+        assert np.array_equal(px, g[tag + "_pixels"]), tag
+    # the reader: same files -> same arrays and focal as the reference's _load_renderings
+    import os
+    from quadraturefields_b200.datasets.nerf_synthetic import _load_renderings
+    root = tmp_path / "toy"
+    for split in ("train", "test"):
+        os.makedirs(root / split)
+        (root / f"transforms_{split}.json").write_bytes(g[f"json_{split}"].tobytes())
+        for i in range(3):
+            (root / split / f"r_{i}.png").write_bytes(g[f"png_{split}_{i}"].tobytes())
+    for split in ("train", "test"):
+        imgs, c2w, focal = _load_renderings(str(tmp_path), "toy", split)
+        assert np.array_equal(imgs, g[f"images_{split}"]) and imgs.dtype == np.uint8
+        assert np.array_equal(c2w.astype(np.float32), g[f"camtoworlds_{split}"])
+        assert focal == float(g["focal"])
