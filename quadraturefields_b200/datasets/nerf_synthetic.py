@@ -121,22 +121,19 @@ class SubjectLoader(torch.utils.data.Dataset):
         return data
 
     def preprocess(self, data):
-        """nerf_synthetic.py:264-287."""
-        rgba, rays = data["rgba"], data["rays"]
-        pixels, alpha = torch.split(rgba, [3, 1], dim=-1)
+        """nerf_synthetic.py:264-287: alpha-composite the target colours over the batch's background colour (white at
+        evaluation; white / black / one random colour per batch in training)."""
         dev = self.images.device
-        if self.training:
-            if self.color_bkgd_aug == "random":
-                color_bkgd = torch.rand(3, device=dev)
-            elif self.color_bkgd_aug == "white":
-                color_bkgd = torch.ones(3, device=dev)
-            else:
-                color_bkgd = torch.zeros(3, device=dev)
+        if self.training and self.color_bkgd_aug == "random":
+            color_bkgd = torch.rand(3, device=dev)
         else:
-            color_bkgd = torch.ones(3, device=dev)
-        pixels = pixels * alpha + color_bkgd * (1.0 - alpha)
-        return {"pixels": pixels, "rays": rays, "color_bkgd": color_bkgd,
-                **{k: v for k, v in data.items() if k not in ["rgba", "rays"]}}
+            level = 0.0 if (self.training and self.color_bkgd_aug == "black") else 1.0
+            color_bkgd = torch.full((3,), level, dtype=torch.float32, device=dev)
+        rgb, alpha = data["rgba"][..., :3], data["rgba"][..., 3:]
+        out = {k: v for k, v in data.items() if k != "rgba"}          # "rays" and anything a caller attached
+        out["pixels"] = rgb * alpha + color_bkgd * (1.0 - alpha)      # [n_rays, 3]
+        out["color_bkgd"] = color_bkgd                                 # [3]
+        return out
 
     def update_num_rays(self, num_rays):
         self.num_rays = num_rays

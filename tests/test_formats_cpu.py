@@ -187,3 +187,29 @@ def test_checkpoint_errors_name_the_mismatch(tmp_path):
         save_checkpoint(p, radiance_field=mk["rf"](), field_net=mk["field"](), radiance_key="model", field_key="model")
     with pytest.raises(ValueError):
         save_checkpoint(p, radiance_field=mk["rf"](), radiance_key="weights")
+
+
+def test_subject_loader_preprocess_on_cpu():
+    """The host half of the loader that needs no kernel: background selection and alpha compositing
+    (nerf_synthetic.py:264-287) against the formula, for evaluation and the three training modes."""
+    from quadraturefields_b200.datasets.nerf_synthetic import SubjectLoader
+    from quadraturefields_b200.datasets.utils import Rays
+    ds = SubjectLoader.__new__(SubjectLoader)                     # no CUDA here: attributes set by hand
+    ds.images = torch.zeros((1, 2, 2, 4), dtype=torch.uint8)
+    g = torch.Generator().manual_seed(0)
+    rgba = torch.rand((7, 4), generator=g)
+    rays = Rays(torch.zeros(7, 3), torch.ones(7, 3))
+    for training, aug, want in ((False, "black", 1.0), (True, "white", 1.0), (True, "black", 0.0), (True, "random", None)):
+        ds.training, ds.color_bkgd_aug = training, aug
+        torch.manual_seed(5)
+        out = ds.preprocess({"rgba": rgba, "rays": rays, "extra": 3})
+        bk = out["color_bkgd"]
+        if want is None:
+            torch.manual_seed(5)
+            assert torch.equal(bk, torch.rand(3))                  # one draw of three numbers, like the reference
+        else:
+            assert torch.equal(bk, torch.full((3,), want))
+        assert torch.equal(out["pixels"], rgba[:, :3] * rgba[:, 3:] + bk * (1.0 - rgba[:, 3:]))
+        assert out["rays"] is rays and out["extra"] == 3 and "rgba" not in out and bk.dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        SubjectLoader("toy", "/nonexistent", "train", num_rays=4, device="cpu")
