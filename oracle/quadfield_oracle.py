@@ -333,6 +333,30 @@ def intersect_firstk_bvh_c(origins, dirs, vertices, faces, K: int, want_total: b
     return tri, tt, count, total
 
 
+def embree_restart_firstk(t_all, tri_all, count_all, K: int, eps: float):
+    """What the reference's SHIPPED intersector would keep (SURVEY §8 row a2', recalled trimesh 3.23.5
+    `ray_pyembree.intersects_id(multiple_hits=True, max_hits=K)`): a first-hit query repeated up to K times, each time
+    restarted `eps` beyond the previous hit along the ray — so hits come out front to back and a hit closer than `eps`
+    to the previously KEPT one is never returned.  Input: all hits per ray sorted by (t, id) (`intersect_firstk` with a
+    large K).  -> tri (N,K) int32 (-1 padded), count (N,).  Used only to quantify how far the two definitions differ."""
+    t_all, tri_all = np.asarray(t_all), np.asarray(tri_all)
+    N = t_all.shape[0]
+    tri = np.full((N, K), -1, dtype=np.int32)
+    count = np.zeros(N, dtype=np.int32)
+    for i in range(N):
+        last = -np.inf
+        c = 0
+        for j in range(int(count_all[i])):
+            if c == K:
+                break
+            if t_all[i, j] - last > eps:
+                tri[i, c] = tri_all[i, j]
+                last = t_all[i, j]
+                c += 1
+        count[i] = c
+    return tri, count
+
+
 def plane_hit_points(o, r, n, v):
     """mesh_utils.py:33-40 ``ray_triangle_intersection``: d=−(n·v); t=−((n·o)+d)/(n·r); t←|t|; ψ=o+t r.  fp32."""
     o, r, n, v = (np.asarray(a, dtype=np.float32) for a in (o, r, n, v))
