@@ -48,6 +48,20 @@ def test_argument_validation_without_gpu(lib):
     assert L.qf_trace_firstk(None, None, None, 10, 8, None, None, None, None, None, 0, None) == 1
     assert L.qf_render_weights(7, None, None, None, None, 1, 1, None, None, None, None, None) == 1
     assert b"mode=7" in L.qf_last_error()
+    # entry points added in round 1h: empty inputs are a no-op, bad arguments are reported before any CUDA call
+    assert L.qf_generate_rays_indexed(None, 3, None, None, None, 0, 10.0, 5.0, 5.0, 1, None, None, None) == 0
+    assert L.qf_generate_rays_indexed(None, 3, None, None, None, 4, 10.0, 5.0, 5.0, 1, None, None, None) == 1
+    assert b"qf_generate_rays_indexed: NULL" in L.qf_last_error()
+    assert L.qf_generate_rays_indexed(None, 0, None, None, None, 4, 10.0, 5.0, 5.0, 1, None, None, None) == 1
+    assert b"views=0" in L.qf_last_error()
+    assert L.qf_sg_features_to_rgb_backward(None, 24, 3, None, 0, None, None, 24, None) == 0
+    assert L.qf_sg_features_to_rgb_backward(None, 10, 3, None, 5, None, None, 24, None) == 1
+    assert b"stride=10" in L.qf_last_error()
+    assert L.qf_sg_features_to_rgb_backward(None, 24, 3, None, 5, None, None, 24, None) == 1
+    assert b"NULL argument" in L.qf_last_error()
+    assert L.qf_ngp_backward_features(None, None, 0, None, None, None, None, None, None, 0, None) == 0
+    assert L.qf_ngp_backward_features(None, None, 5, None, None, None, None, None, None, 0, None) == 1
+    assert b"qf_ngp_backward_features: NULL" in L.qf_last_error()
 
 
 def test_ops_fail_loudly_on_cpu_tensors(lib):
