@@ -108,6 +108,7 @@ def cpu_render_sample(sample: int, threads: int, config: str = "c2", steps: int 
     torch.set_num_threads(threads)
     O.PREFER_C = True       # the C restatement (oracle/bruteforce.c, all host threads) instead of the numpy one ...
     O.PREFER_BVH = True     # ... through its CPU BVH (bit-identical to the brute force; the reference's Embree shape)
+    O.set_c_threads(threads)   # torchrun exports OMP_NUM_THREADS=1; `cores` in the JSON line is what really runs
     cfg = S.CONFIGS[config]
     vertices, faces = O.shell_mesh(cfg["radii"], cfg["sub"], jitter=1e-3, seed=42)
     f, cx, cy, W, H = O.pinhole_intrinsics(cfg["W"], cfg["H"], S.CAMERA_ANGLE_X)
@@ -139,6 +140,10 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm is rank 0 alone and uses all host threads (the
+    # variable is read when the OpenMP runtimes start, i.e. before torch is imported below, and also seeds worker threads)
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ["MKL_NUM_THREADS"] = str(threads)
     sample = 256
     rps, detail, sec = cpu_render_sample(sample, threads, args.config, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     desc = (f"{sample}x{sample} sub-grid of one {args.config} frame per step; intersect {detail.get('intersect_s', 0):.2f}s "

@@ -11,6 +11,19 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; bench.py's reference arm asks for all host threads explicitly */
+void qf_oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 static inline float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
 static inline float max3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 

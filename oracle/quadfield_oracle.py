@@ -285,6 +285,13 @@ def _c_oracle():
     return _C_LIB or None
 
 
+def set_c_threads(n: int) -> None:
+    """OpenMP thread count of the C restatement (torchrun pins OMP_NUM_THREADS=1 in every rank's environment)."""
+    lib = _c_oracle()
+    if lib is not None and hasattr(lib, "qf_oracle_set_threads"):
+        lib.qf_oracle_set_threads(int(n))
+
+
 def intersect_firstk_c(origins, dirs, vertices, faces, K: int):
     """Same contract and bit-identical results as `intersect_firstk`, through the C restatement (OpenMP)."""
     import ctypes as C

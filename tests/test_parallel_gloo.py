@@ -65,3 +65,24 @@ def test_sharding_covers_every_ray_once():
             assert max(b - a for a, b in cuts) - min(b - a for a, b in cuts) <= (4 * w if w else 1)
     views = sorted(P.view_for_step(s, r, 4, 200) for s in range(50) for r in range(4))
     assert views == list(range(200))
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """`bench.py --impl reference` launched the way the driver launches N>1 arms: rank 0 alone measures and prints the
+    JSON line (impl, metric, cpu_baseline, e2e with zero copy bytes), the other rank exits 0 without work."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rays_per_sec_render_fwd" and d["unit"] == "rays/s" and d["n_gpus"] == 2
+    assert d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "BVH" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
