@@ -562,6 +562,32 @@ def render_image_finetune_with_occgrid(radiance_field, field_net, estimator, ray
 
 
 @torch.no_grad()
+def render_image_fit_sg_with_occgrid(radiance_field, radiance_field_sg, estimator, rays: Rays, data, near_plane=0.0,
+                                     far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
+                                     alpha_thre=0.0, test_chunk_size=8192, timestamps=None, mesh_intersect=None,
+                                     mesh_finetune=None, scaling=1 / 128, bg_color="white"):
+    """utils.py:610-731 (the render of train_fit_sg.py:439-452) -> the reference's 8-tuple
+    (colors, opacities, depths, n_samples, weights, xyzs, index_ray, index_tri).  Colours come from the
+    spherical-Gaussian field (with gradient), densities from the frozen radiance field (no gradient), both evaluated at the
+    quadrature points with the ORIGINAL ray directions `rays.viewdirs[index_ray]` (:686, :663); constant quadrature step
+    (quirk Q4, :709-710).  The reference's 32768-row loops are single kernel launches here."""
+    rays, rays_shape, num_rays = _flatten_rays(rays)
+    xyzs, dirs, index_ray, ts, index_tri, origins = data
+    dev = radiance_field_sg.aabb.device
+    xyzs, ts, index_ray = xyzs.to(dev), ts.to(dev), index_ray.to(dev).long()
+    viewdirs = _lib.f32(rays.viewdirs, dev)
+    rgbs, _ = radiance_field_sg(xyzs, viewdirs, ray_indices=index_ray)
+    with torch.no_grad():
+        _, sigmas = radiance_field(xyzs, viewdirs, ray_indices=index_ray)
+        sigmas = sigmas.squeeze(-1)
+        boundary = torch.ones_like(index_ray, dtype=torch.bool)
+        boundary[1:] = index_ray[1:] != index_ray[:-1]                       # spc_render.mark_pack_boundaries (:708)
+    rgb, opacity, _, depth, weights = derive_properties(rgbs, sigmas, ts, float(render_step_size), boundary, index_ray,
+                                                        bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays)
+    return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth.view((*rays_shape[:-1], -1)),
+            xyzs.shape[0], weights, xyzs, index_ray, index_tri)
+
+
 def render_image_bake_texture_images_with_occgrid(radiance_field, rays: Rays, data, texture=None, uv=None, near_plane=0.0,
                                                   far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
                                                   alpha_thre=0.0, test_chunk_size=8192, timestamps=None,

@@ -1403,3 +1403,42 @@ def test_subject_loader_matches_reference_fixture(dev, golden, smoke_scene, tmp_
     assert bool(torch.isfinite(bad.viewdirs[0]).all()) and bool(torch.isnan(bad.viewdirs[1:]).all()) and bool(torch.isnan(bad.origins[1:]).all())
     with pytest.raises(RuntimeError):
         SubjectLoader("toy", str(tmp_path), "train", num_rays=8, device="cpu")
+
+
+def test_fit_sg_render_driver(dev, smoke_scene):
+    """`render_image_fit_sg_with_occgrid` (utils.py:610-731, the render of train_fit_sg.py): colours from the SG field at the
+    quadrature points with the original ray directions, densities from the frozen radiance field, constant quadrature step,
+    `derive_properties`; checked against the oracle's derive_properties on the two fields' own outputs, (H,W,3) ray input,
+    and the gradient reaches the SG field only."""
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.radiance_fields.ngp import NGPRadianceFieldSGNew
+    from quadraturefields_b200.utils import render_image_fit_sg_with_occgrid
+    sc = smoke_scene
+    rf = sc.radiance_field
+    sg = NGPRadianceFieldSGNew(aabb=sc.aabb, use_viewdirs=False, num_g_lobes=3, log2_hashmap_size=14).to(dev)
+    with torch.no_grad():
+        sg.mlp_base.params[sg._n_base:].mul_(1e3)
+    o, d = sc.rays(1)
+    tup = sc.mesh_intersect.sampling_raytrace(d, o)
+    data = [tup[0], tup[1], tup[2], tup[3], tup[4], tup[6]]
+    rays = Rays(o.view(sc.H, sc.W, 3), d.view(sc.H, sc.W, 3))
+    step = sc.mesh_intersect.render_step_size
+    rf.zero_grad(); sg.zero_grad()
+    rgb, opacity, depth, n, weights, xyzs, index_ray, index_tri = render_image_fit_sg_with_occgrid(
+        rf, sg, None, rays, data, render_step_size=step, mesh_intersect=sc.mesh_intersect, bg_color="white")
+    assert rgb.shape == (sc.H, sc.W, 3) and opacity.shape == (sc.H, sc.W, 1) and depth.shape == (sc.H, sc.W, 1)
+    assert n == tup[0].shape[0] and torch.equal(index_ray, tup[2]) and torch.equal(index_tri, tup[4]) and torch.equal(xyzs, tup[0])
+    with torch.no_grad():
+        rgbs_ref, _ = sg(tup[0], d, ray_indices=tup[2])
+        _, sig_ref = rf(tup[0], d, ray_indices=tup[2])
+    ir = tup[2].cpu()
+    boundary = torch.ones_like(ir, dtype=torch.bool); boundary[1:] = ir[1:] != ir[:-1]
+    ref = O.derive_properties(rgbs_ref.cpu(), sig_ref.squeeze(-1).cpu(), tup[3].cpu(), torch.full((ir.shape[0],), step), boundary, ir,
+                              bg_color="white", N=o.shape[0])
+    assert maxabs(rgb.reshape(-1, 3), ref[0]) <= 1e-5 and maxabs(opacity.reshape(-1, 1), ref[1]) <= 1e-5
+    assert maxabs(weights, ref[4]) <= 1e-5
+    rgb.square().mean().backward()
+    assert sg.mlp_base.params.grad is not None and float(sg.mlp_base.params.grad.abs().max()) > 0
+    assert all(p_.grad is not None and float(p_.grad.abs().max()) > 0 for p_ in sg.mlp_head.parameters())
+    assert rf.mlp_base.params.grad is None or float(rf.mlp_base.params.grad.abs().max()) == 0.0      # sigma is frozen
+    sg.zero_grad()
