@@ -213,3 +213,30 @@ def test_subject_loader_preprocess_on_cpu():
         assert out["rays"] is rays and out["extra"] == 3 and "rgba" not in out and bk.dtype == torch.float32
     with pytest.raises(RuntimeError):
         SubjectLoader("toy", "/nonexistent", "train", num_rays=4, device="cpu")
+
+
+def test_mesh_files_round_trip_random_meshes(tmp_path):
+    """Property: any triangle soup written by the writers comes back identical (PLY at fp32, OBJ at fp64 precision),
+    including an empty face list, a single triangle and vertex indices that need all 32 bits of the PLY int field."""
+    rng = np.random.RandomState(0)
+    for case, (nv, nf) in enumerate(((3, 1), (4, 0), (50, 97), (1000, 3000))):
+        v = rng.normal(size=(nv, 3)) * 10.0 ** rng.randint(-3, 4)
+        f = rng.randint(0, nv, size=(nf, 3))
+        uv = rng.uniform(size=(nv, 2))
+        for binary in (True, False):
+            p = str(tmp_path / f"m{case}_{int(binary)}.ply")
+            mesh_io.save_ply(p, v, f, binary=binary)
+            m = mesh_io.load_mesh(p)
+            assert m.faces.shape == (nf, 3) and np.array_equal(m.faces, f.reshape(-1, 3))
+            if binary:
+                assert np.array_equal(m.vertices.astype(np.float32), v.astype(np.float32))
+            else:
+                assert np.allclose(m.vertices, v.astype(np.float32), rtol=1e-7, atol=0)
+        if nf:
+            p = str(tmp_path / f"m{case}.obj")
+            mesh_io.save_obj(p, v, f, uv)
+            m = mesh_io.load_mesh(p)
+            assert np.array_equal(m.vertices, v) and np.array_equal(m.faces, f) and np.array_equal(m.visual.uv, uv)
+            mesh_io.save_obj(p, v, f)
+            m = mesh_io.load_mesh(p)
+            assert np.array_equal(m.vertices, v) and np.array_equal(m.faces, f) and m.visual.uv is None
