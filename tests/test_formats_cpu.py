@@ -240,3 +240,98 @@ def test_mesh_files_round_trip_random_meshes(tmp_path):
             mesh_io.save_obj(p, v, f)
             m = mesh_io.load_mesh(p)
             assert np.array_equal(m.vertices, v) and np.array_equal(m.faces, f) and m.visual.uv is None
+
+
+def test_prefetcher_ring_logic_with_fake_streams(monkeypatch):
+    """Host logic of `HitTuplePrefetcher(ring=R)` without a GPU (streams / events replaced by recorders): tuples come back
+    in submission order; tuple n re-uses the buffers of tuple n-R only after `get()` number n-R+1 was called, waiting on
+    that call's event; when a caller runs further ahead than the ring allows, the tuple falls back to fresh allocations
+    instead of overwriting buffers that may still be in use."""
+    from quadraturefields_b200 import utils as U
+    log = []
+
+    class FakeEvent:
+        n = 0
+
+        def __init__(self, *a, **k):
+            FakeEvent.n += 1
+            self.id = FakeEvent.n
+
+        def record(self, stream=None):
+            log.append(("record", self.id, getattr(stream, "name", "main")))
+
+        def synchronize(self):
+            pass
+
+    class FakeStream:
+        def __init__(self, name="side", **k):
+            self.name = name
+
+        def wait_event(self, ev):
+            log.append(("wait", self.name, ev.id))
+
+        def wait_stream(self, other):
+            log.append(("wait_stream", self.name, other.name))
+
+    main = FakeStream("main")
+
+    class Ctx:
+        def __init__(self, s): pass
+        def __enter__(self): return self
+        def __exit__(self, *a): return False
+
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: FakeStream("side"))
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "stream", Ctx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda device=None: main)
+    monkeypatch.setattr(torch.Tensor, "record_stream", lambda self, s: None, raising=False)
+
+    class FakeIntersector:
+        allocs = 0
+
+        def tuple_buffers(self, cap):
+            FakeIntersector.allocs += 1
+            return tuple(torch.zeros((cap, 3)) if k < 3 else torch.zeros((cap,)) for k in range(6))
+
+    class FakeMesh:
+        device = torch.device("cpu")
+        rayintersector = FakeIntersector()
+        used = []                                   # (batch id, "ring" | "fresh", id of the first buffer)
+
+        def sampling_raytrace_begin(self, viewdirs, origins):
+            return int(origins[0, 0])
+
+        def sampling_raytrace_end(self, pending, alloc=None):
+            M = 10 + pending
+            bufs = alloc(M) if alloc is not None else self.rayintersector.tuple_buffers(M)
+            self.used.append((pending, "ring" if alloc is not None else "fresh", id(bufs[0])))
+            return tuple(b[:M] for b in bufs) + (pending,)
+
+    batch = lambda i: (torch.full((4, 3), float(i)), torch.zeros((4, 3)))
+    fm = FakeMesh()
+    pf = U.HitTuplePrefetcher(fm, ring=3)
+    pf.submit(*batch(0), rays_ready=True)
+    pf.submit(*batch(1), rays_ready=True)
+    got = []
+    for i in range(8):                               # the two-deep schedule
+        got.append(pf.get()[-1])
+        pf.submit(*batch(i + 2), rays_ready=True)
+    assert got == list(range(8))
+    kinds = [k for _, k, _ in fm.used]
+    assert kinds == ["ring"] * len(kinds)
+    ids = [b for _, _, b in fm.used]
+    assert all(ids[n] == ids[n - 3] for n in range(3, len(ids))) and len(set(ids[:3])) == 3      # three sets, recycled in turn
+    assert FakeIntersector.allocs == 3
+    # every recycled tuple n >= 3 made the side stream wait for the event get() number n-2 recorded on the main stream
+    get_events = [e for op, e, s in log if op == "record" and s == "main"]
+    waits = [e for op, s, e in [(l[0], l[1], l[2]) for l in log if l[0] == "wait"] if s == "side"]
+    assert waits[:len(ids) - 3] == get_events[1:1 + len(ids) - 3]
+    # running ahead: five submits without a get -> the tuples whose slot is not yet retired are freshly allocated
+    fm2 = FakeMesh(); fm2.used = []
+    pf2 = U.HitTuplePrefetcher(fm2, ring=3)
+    for i in range(6):
+        pf2.submit(*batch(i), rays_ready=True)
+    assert [pf2.get()[-1] for _ in range(6)] == list(range(6))
+    # tuples 3 and 4 are sized while tuples 0 and 1 have not been handed out yet; tuple 5 is sized by the last get(), after
+    # get() number 3 retired tuple 2, whose buffers it may take over
+    assert [k for _, k, _ in fm2.used] == ["ring", "ring", "ring", "fresh", "fresh", "ring"]
