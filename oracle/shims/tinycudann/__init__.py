@@ -88,6 +88,8 @@ class Encoding(torch.nn.Module):
         assert nested[0]["otype"] == "SphericalHarmonics" and nested[0]["degree"] == 4
         self.kind = "sh"
         self.n_output_dims = 16
+        # tcnn.Module registers `params` for every module, empty when the encoding has no parameters (recalled)
+        self.params = torch.nn.Parameter(torch.zeros(0))
 
     def forward(self, x):
         x = x.float()

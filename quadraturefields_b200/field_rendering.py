@@ -62,23 +62,29 @@ class _RenderWeights(torch.autograd.Function):
                                          packed_info.shape[0], n, _lib.ptr(pf), _lib.ptr(w), _lib.ptr(T), _lib.ptr(a),
                                          _lib.stream(x.device)), "qf_render_weights")
         ctx.mode = mode
+        ctx.set_materialize_grads(False)
         ctx.save_for_backward(x, ts, te, packed_info, pf)
         if mode == 1:
-            ctx.mark_non_differentiable(a)
             return w, T, a
         return w, T
 
     @staticmethod
-    def backward(ctx, gw, gT, *unused):
+    def backward(ctx, gw, gT, ga=None):
         lib = _lib.load()
         x, ts, te, packed_info, pf = ctx.saved_tensors
         gw = _lib.f32(gw) if gw is not None else None
         gT = _lib.f32(gT) if gT is not None else None
+        if gw is None and gT is None and ga is None:
+            return None, None, None, None, None, None
         gin = torch.empty_like(x)
         _lib.check(lib.qf_render_weights_backward(ctx.mode, _lib.ptr(x), _lib.ptr(ts), _lib.ptr(te),
                                                   _lib.ptr(packed_info), packed_info.shape[0], x.numel(), _lib.ptr(pf),
                                                   _lib.ptr(gw), _lib.ptr(gT), _lib.ptr(gin), _lib.stream(x.device)),
                    "qf_render_weights_backward")
+        if ga is not None:
+            # alphas = 1 - exp(-sigma * dt) is an ordinary autograd output in the reference (field_rendering.py:257-261)
+            dt = te - ts
+            gin = gin + _lib.f32(ga) * dt * torch.exp(-x * dt)
         return None, gin, None, None, None, None
 
 

@@ -134,6 +134,7 @@ class RayIntersector:
             _lib.check(lib.qf_hits_pack(self._handle, _lib.ptr(o), _lib.ptr(d), N, K, _lib.ptr(tri), _lib.ptr(count),
                                         _lib.ptr(offsets), _lib.ptr(points), _lib.ptr(vecs), _lib.ptr(index_ray),
                                         _lib.ptr(depth), _lib.ptr(index_tri), _lib.ptr(org), st), "qf_hits_pack")
+        index_ray.qf_ray_major = True      # ascending by construction: `sampling_indexing` then skips its (host-synchronising) order check
         return points, vecs, index_ray, depth, index_tri, org, offsets
 
     @torch.no_grad()
@@ -243,6 +244,11 @@ def triangle_weight_max(triangles_weights: torch.Tensor, weights: torch.Tensor, 
     return triangles_weights
 
 
+def _tag_ray_major(t: torch.Tensor) -> torch.Tensor:
+    t.qf_ray_major = True
+    return t
+
+
 class HitTuple(tuple):
     """The reference's 7-tuple (points, vectors, index_ray, depth, index_tri, 0, origins) plus `.offsets`."""
     offsets = None
@@ -268,7 +274,9 @@ class MeshIntersection:
 
     def find_deltas(self, boundary, depth):
         """mesh_utils.py:225-231: the constant quadrature step (quirk Q4)."""
-        return torch.full((depth.shape[0],), self.render_step_size, dtype=torch.float32, device=depth.device)
+        deltas = torch.full((depth.shape[0],), self.render_step_size, dtype=torch.float32, device=depth.device)
+        deltas.qf_const = float(self.render_step_size)      # read by utils.derive_properties instead of a device->host copy
+        return deltas
 
     @torch.no_grad()
     def sampling_raytrace(self, vectors: torch.Tensor, origins: torch.Tensor):
@@ -310,20 +318,23 @@ class MeshIntersection:
         permutation is found without gradient; the gathers that apply it are differentiable like the reference's
         `points[new_indices]` (the finetune step back-propagates through the re-sorted points)."""
         dev = self.device
+        ray_major = bool(getattr(index_ray, "qf_ray_major", False))
         index_ray = _lib.i64(index_ray.to(dev))
         depth_in = depth.to(dev, torch.float32)
         with torch.no_grad():
-            perm, boundary = self._resort(index_ray, _lib.f32(depth_in.detach(), dev))
+            perm, boundary = self._resort(index_ray, _lib.f32(depth_in.detach(), dev), ray_major)
         g = lambda t: t.to(dev)[perm]
         depth = depth_in[perm]
         deltas = self.find_deltas(boundary, depth)
-        return g(points), deltas, boundary, g(vectors), index_ray[perm], depth, g(index_tri), g(origins)
+        return g(points), deltas, boundary, g(vectors), _tag_ray_major(index_ray[perm]), depth, g(index_tri), g(origins)
 
-    def _resort(self, index_ray, depth):
+    def _resort(self, index_ray, depth, ray_major=False):
+        """`ray_major=True` (index_ray produced by this package's tracer, tagged `qf_ray_major`) promises ascending ray ids
+        and skips the order test, which is the only device->host read of the re-sort."""
         lib = _lib.load()
         dev = self.device
         M = index_ray.shape[0]
-        if M > 1 and bool((index_ray[1:] < index_ray[:-1]).any()):
+        if not ray_major and M > 1 and bool((index_ray[1:] < index_ray[:-1]).any()):
             # arbitrary order: full lexsort((depth, index_ray)) with device sorts (stable)
             o1 = torch.sort(depth, stable=True).indices
             perm = o1[torch.sort(index_ray[o1], stable=True).indices]

@@ -75,36 +75,49 @@ def gather_frame(parts: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Opt
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0) if rank == dst else None
 
 
-def all_reduce_gradients(params: Sequence[torch.Tensor], n_local: int, n_global: Optional[int] = None) -> None:
+def all_reduce_gradients(params: Sequence[torch.Tensor], n_local, n_global=None) -> None:
     """Training mode: sum the per-rank gradients of the (replicated) hash table and MLPs — large tensors in place,
-    the small ones in one flat bucket — and rescale a per-rank mean loss to the global sample count (`n_local`
-    samples here, `n_global` overall)."""
+    the small ones in one flat bucket — and rescale a per-rank MEAN loss to the global sample count: every rank's
+    gradient is weighted by n_local / n_global, so the result is the gradient of the mean over all ranks' samples
+    (pass the number of samples the rank's loss averaged over, not its ray count, when the two differ).
+
+    `n_local` / `n_global` may be Python numbers or 0-d device tensors; with `n_global=None` the counts are all-reduced
+    on the device and the scale stays a device scalar (no host synchronisation).
+
+    Every rank ALWAYS enters the same collectives in the same order: a parameter without `.grad` on this rank (zero-hit
+    batch, unused branch) contributes zeros — an early return here would leave the peers blocked in NCCL."""
     rank, ws = world()
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
     if ws == 1:
         return
+    params = [p for p in params if p.requires_grad and p.numel()]
+    if not params:
+        return
+    dev = params[0].device
+    for p in params:
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
+    grads = [p.grad for p in params]
     if n_global is None:
-        counts = torch.tensor([float(n_local)], device=grads[0].device)
-        dist.all_reduce(counts)
-        n_global = float(counts.item())
-    scale = float(n_local) / float(n_global)
+        n_loc = n_local.detach().to(device=dev, dtype=torch.float32).reshape(1) if isinstance(n_local, torch.Tensor) \
+            else torch.tensor([float(n_local)], dtype=torch.float32, device=dev)
+        total = n_loc.clone()
+        dist.all_reduce(total)
+        scale = n_loc / total.clamp_min(1.0)                 # device scalar; a rank with no samples scales its zeros by 0
+    else:
+        scale = float(n_local) / float(n_global)
+    unit = isinstance(scale, float) and scale == 1.0
     big = [g for g in grads if g.numel() >= (1 << 20) and g.is_contiguous()]
     small = [g for g in grads if not (g.numel() >= (1 << 20) and g.is_contiguous())]
     for g in big:                       # the hash table: reduced in place, no flatten / copy-back of tens of MB
-        if scale != 1.0:
+        if not unit:
             g.mul_(scale)
         dist.all_reduce(g)
     if small:                           # MLP matrices and biases: one bucket, one launch-latency-bound collective
         flat = torch.cat([g.reshape(-1) for g in small])
-        if scale != 1.0:
+        if not unit:
             flat.mul_(scale)
         dist.all_reduce(flat)
-        off = 0
-        for g in small:
-            g.copy_(flat[off:off + g.numel()].view_as(g))
-            off += g.numel()
+        torch._foreach_copy_(small, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in small]), small)])
 
 
 def max_over_ranks(value: float, device=None) -> float:

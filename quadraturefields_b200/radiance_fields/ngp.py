@@ -46,7 +46,14 @@ class _TcnnParams(nn.Module):
 
 
 class _DirectionEncoding(nn.Module):
-    n_output_dims = 16  # SphericalHarmonics degree 4 (ngp.py:694-707)
+    """SphericalHarmonics degree 4 (ngp.py:694-707).  A tinycudann module always registers a flat `params` Parameter, empty
+    for a parameter-free encoding, so the reference's NeRF-stage state dicts carry `direction_encoding.params` of shape (0,);
+    the same key is kept here so that `load_state_dict(strict=True)` works in both directions."""
+    n_output_dims = 16
+
+    def __init__(self):
+        super().__init__()
+        self.params = nn.Parameter(torch.zeros(0, dtype=torch.float32))
 
 
 class _NGPForwardFn(torch.autograd.Function):

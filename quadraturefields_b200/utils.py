@@ -10,6 +10,7 @@ Two levels are offered:
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -47,29 +48,54 @@ class _DerivePropertiesFn(torch.autograd.Function):
                                             _lib.stream(dev)), "qf_derive_properties")
         ctx.save_for_backward(color, density, depths, offsets, bk)
         ctx.meta = (delta, N, bg)
-        ctx.mark_non_differentiable(weights)
+        ctx.set_materialize_grads(False)
         return rgb, out_alpha, Depth, weights
 
     @staticmethod
-    def backward(ctx, g_rgb, g_alpha, g_depth, _gw):
+    def backward(ctx, g_rgb, g_alpha, g_depth, g_w):
         lib = _lib.load()
         color, density, depths, offsets, bk = ctx.saved_tensors
         delta, N, bg = ctx.meta
         M = density.shape[0]
+        dev = color.device
         g_color, g_density = torch.empty_like(color), torch.empty_like(density)
         c = lambda t: _lib.f32(t) if t is not None else None
+        if g_rgb is None and g_alpha is None and g_depth is None:
+            g_rgb = torch.zeros((N, 3), dtype=torch.float32, device=dev)
         _lib.check(lib.qf_derive_properties_backward(_lib.ptr(color), _lib.ptr(density), _lib.ptr(depths), delta, _lib.ptr(offsets),
                                                      N, M, bg, _lib.ptr(bk), _lib.ptr(c(g_rgb)), _lib.ptr(c(g_alpha)),
                                                      _lib.ptr(c(g_depth)), _lib.ptr(g_color), _lib.ptr(g_density),
                                                      _lib.stream(color.device)), "qf_derive_properties_backward")
+        if g_w is not None and M:
+            # the per-sample weights w_i = T_i (1 - e^{-sigma_i delta}) are an ordinary autograd output in the reference
+            # (kaolin exponential_integration, utils.py:869-879): their gradient w.r.t. the densities is the nerfacc-style
+            # weights backward with t_ends - t_starts = delta
+            packed = torch.stack([offsets[:-1], offsets[1:] - offsets[:-1]], dim=1).contiguous()
+            ts, te = torch.zeros_like(density), torch.full_like(density, float(delta))
+            gin = torch.empty_like(density)
+            _lib.check(lib.qf_render_weights_backward(1, _lib.ptr(density), _lib.ptr(ts), _lib.ptr(te), _lib.ptr(packed), N, M, None,
+                                                      _lib.ptr(c(g_w.reshape(-1))), None, _lib.ptr(gin), _lib.stream(dev)),
+                       "qf_render_weights_backward")
+            g_density = g_density + gin
         return g_color, g_density, None, None, None, None, None, None
 
 
-def derive_properties(color, density, depths, deltas, boundary, index_ray, render_bkgd=None, bg_color="white", N=0):
+VALIDATE_INPUTS = bool(int(os.environ.get("QF_VALIDATE", "0")))   # debug: re-enable the input checks that synchronise the host
+
+
+def derive_properties(color, density, depths, deltas, boundary, index_ray, render_bkgd=None, bg_color="white", N=0,
+                      return_ray_ids=True):
     """utils.py:863-898 -> (rgb (N,3), out_alpha (N,1), index_ray[boundary], Depth (N,1), weights (M,1)).
 
     One kernel instead of 2 kaolin pack scans + 3 pack reductions + 3 scatters; differentiable w.r.t. color and
-    density.  `deltas` is the constant quadrature step (quirk Q4); a non-constant tensor is rejected."""
+    density (all four float outputs, `weights` included).  `deltas` is the constant quadrature step (quirk Q4): a float, or
+    the tensor `MeshIntersection.find_deltas` returns.  Packs are the runs of equal `index_ray`, ascending (the layout
+    `sampling_indexing` produces); `boundary` is implied by `index_ray` and only used for the third return value.
+
+    No device->host synchronisation happens here when `deltas` is a float / tagged tensor and `return_ray_ids=False`
+    (the third return value `index_ray[boundary]` has a data-dependent length, so producing it must wait for the device —
+    as it does in the reference; the package's own drivers do not ask for it).  `QF_VALIDATE=1` (or
+    `utils.VALIDATE_INPUTS = True`) re-enables the checks that the step is constant and the packs ascend."""
     lib = _lib.load()
     dev = color.device
     color = _lib.f32(color.reshape(-1, 3))
@@ -79,25 +105,25 @@ def derive_properties(color, density, depths, deltas, boundary, index_ray, rende
     index_ray = _lib.i64(index_ray)
     with torch.no_grad():
         if isinstance(deltas, torch.Tensor):
-            if M and not bool((deltas == deltas.reshape(-1)[0]).all()):
+            const = getattr(deltas, "qf_const", None)
+            if VALIDATE_INPUTS and M and not bool((deltas == deltas.reshape(-1)[0]).all()):
                 raise NotImplementedError("derive_properties: the quadrature step is constant in every reference caller "
                                           "(mesh_utils.py:225-231)")
-            delta = float(deltas.reshape(-1)[0]) if M else 0.0
+            delta = float(const) if const is not None else (float(deltas.reshape(-1)[0]) if M else 0.0)
         else:
             delta = float(deltas)
-        # packs are runs of equal index_ray; with ascending ids offsets come from a count + scan
-        cnt = torch.zeros((N,), dtype=torch.int32, device=dev)
-        ids = index_ray[boundary]
-        if M:
-            starts = torch.nonzero(boundary).flatten()
-            ends = torch.cat([starts[1:], torch.tensor([M], device=dev)])
-            if bool((ids[1:] <= ids[:-1]).any()):
-                raise NotImplementedError("derive_properties expects ray-major (ascending index_ray) packs")
-            cnt[ids] = (ends - starts).to(torch.int32)
+        if VALIDATE_INPUTS and M > 1 and bool((index_ray[1:] < index_ray[:-1]).any()):
+            raise NotImplementedError("derive_properties expects ray-major (ascending index_ray) packs")
+        # packs are runs of equal, ascending index_ray: per-ray counts + scan on the device (qf_pack_info), no host round trip
         offsets = torch.empty((N + 1,), dtype=torch.int64, device=dev)
-        ws = _lib.workspace(dev, lib.qf_scan_workspace_bytes(N), "scan")
-        _lib.check(lib.qf_hits_offsets(_lib.ptr(cnt), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), _lib.stream(dev)),
-                   "qf_hits_offsets")
+        if N:
+            packed = torch.empty((N, 2), dtype=torch.int64, device=dev)
+            ws = _lib.workspace(dev, lib.qf_pack_info_workspace_bytes(N), "pack")
+            _lib.check(lib.qf_pack_info(_lib.ptr(index_ray), M, N, _lib.ptr(packed), _lib.ptr(ws), ws.numel(), _lib.stream(dev)),
+                       "qf_pack_info")
+            offsets[:N] = packed[:, 0]
+        offsets[N:] = M
+        ids = index_ray[boundary] if return_ray_ids else None
         bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else None
     rgb, out_alpha, Depth, weights = _DerivePropertiesFn.apply(color, density, depths, delta, offsets, N,
                                                                _lib.BG_MODES.get(bg_color, 2), bk)
@@ -307,9 +333,13 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
             tup = mesh_intersect.sampling_raytrace(viewdirs, origins)
     dev = mesh_intersect.device
     if tup is None:
+        # nothing hit: the quirk-Q2 fill, still connected to the parameters (zero gradient) so that `loss.backward()` and
+        # the gradient all-reduce run on this rank exactly as on its peers
         fill = 0.0 if bg_color == "black" else 1.0
-        z = torch.zeros((N, 1), device=dev)
-        return torch.full((N, 3), fill, device=dev), z, z.clone(), 0
+        tie = sum((p.reshape(-1)[:1].sum() * 0.0 for p in radiance_field.parameters() if p.requires_grad and p.numel()),
+                  torch.zeros((), device=dev))
+        z = torch.zeros((N, 1), device=dev) + tie
+        return torch.full((N, 3), fill, device=dev) + tie, z, z.clone(), 0
     points, _, index_ray, depth, _, _, _ = tup
     rgbs, sigmas = radiance_field(points, _lib.f32(viewdirs, dev), ray_indices=index_ray)
     offsets = getattr(tup, "offsets", None)
@@ -323,7 +353,7 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
     boundary = torch.ones_like(index_ray, dtype=torch.bool)
     boundary[1:] = index_ray[1:] != index_ray[:-1]
     rgb, opacity, _, depth_img, _ = derive_properties(rgbs, sigmas.squeeze(-1), depth, mesh_intersect.render_step_size, boundary,
-                                                      index_ray, render_bkgd=render_bkgd, bg_color=bg_color, N=N)
+                                                      index_ray, render_bkgd=render_bkgd, bg_color=bg_color, N=N, return_ray_ids=False)
     return rgb, opacity, depth_img, points.shape[0]
 
 
@@ -360,6 +390,12 @@ def train_field_step(field_net, radiance_field, mesh_intersect, origins, viewdir
     all-reduce -> optimizer.step().  -> (loss tensor, number of samples)."""
     batch = field_training_batch(mesh_intersect, radiance_field, origins, viewdirs, tup=tup)
     if batch is None:
+        # a zero-hit batch still takes part in the step: with several ranks the peers are inside the gradient all-reduce,
+        # so this rank contributes zero gradients instead of returning early (which would dead-lock NCCL)
+        optimizer.zero_grad(set_to_none=False)
+        if all_reduce is not None:
+            all_reduce()
+            optimizer.step()
         return None, 0
     positions, dirs, weights, weights_rev = batch
     _, field_grad = field_net(positions)
@@ -554,14 +590,13 @@ def render_image_finetune_with_occgrid(radiance_field, field_net, estimator, ray
         loss = loss.reshape(1)
     rgbs, sigmas = radiance_field(points, viewdirs, ray_indices=index_ray_s)                 # quirk Q7: original viewdirs
     rgb, opacity, _, depth_img, weights = derive_properties(rgbs, sigmas.squeeze(-1), depth, deltas, boundary, index_ray_s,
-                                                            bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays)
+                                                            bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays, return_ray_ids=False)
     if mesh_finetune is not None:
         mesh_finetune.update_d(dh, weights[:, 0], index_tri)
     return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth_img.view((*rays_shape[:-1], -1)),
             xyzs.shape[0], weights, points, index_ray_s, loss, index_tri)
 
 
-@torch.no_grad()
 def render_image_fit_sg_with_occgrid(radiance_field, radiance_field_sg, estimator, rays: Rays, data, near_plane=0.0,
                                      far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
                                      alpha_thre=0.0, test_chunk_size=8192, timestamps=None, mesh_intersect=None,
@@ -583,11 +618,12 @@ def render_image_fit_sg_with_occgrid(radiance_field, radiance_field_sg, estimato
         boundary = torch.ones_like(index_ray, dtype=torch.bool)
         boundary[1:] = index_ray[1:] != index_ray[:-1]                       # spc_render.mark_pack_boundaries (:708)
     rgb, opacity, _, depth, weights = derive_properties(rgbs, sigmas, ts, float(render_step_size), boundary, index_ray,
-                                                        bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays)
+                                                        bg_color=bg_color, render_bkgd=render_bkgd, N=num_rays, return_ray_ids=False)
     return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth.view((*rays_shape[:-1], -1)),
             xyzs.shape[0], weights, xyzs, index_ray, index_tri)
 
 
+@torch.no_grad()
 def render_image_bake_texture_images_with_occgrid(radiance_field, rays: Rays, data, texture=None, uv=None, near_plane=0.0,
                                                   far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0,
                                                   alpha_thre=0.0, test_chunk_size=8192, timestamps=None,
@@ -613,6 +649,6 @@ def render_image_bake_texture_images_with_occgrid(radiance_field, rays: Rays, da
         sigmas = texture_points[:, -1]
     rgbs = radiance_field.features_to_rgb(texture_points[:, :-1], dirs)
     rgb, opacity, _, depth_img, weights = derive_properties(rgbs, sigmas, depth, deltas, boundary, index_ray,
-                                                            bg_color=bg_color, render_bkgd=None, N=num_rays)
+                                                            bg_color=bg_color, render_bkgd=None, N=num_rays, return_ray_ids=False)
     return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth_img.view((*rays_shape[:-1], -1)),
             xyzs.shape[0], weights, points, rays, 0)

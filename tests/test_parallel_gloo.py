@@ -41,6 +41,15 @@ def _worker(rank, ws, port, ret):
         P.all_reduce_gradients([p], n_local)
         expect = sum((10 + 30 * r) * (r + 1) for r in range(ws)) / sum(10 + 30 * r for r in range(ws))
         ok &= bool(torch.allclose(p.grad, torch.full((7,), expect)))
+        # a rank whose batch hit nothing has no .grad at all: it must still enter the collectives (zeros), not return early
+        big = torch.nn.Parameter(torch.zeros(1 << 20))
+        small, unused = torch.nn.Parameter(torch.zeros(5)), torch.nn.Parameter(torch.zeros(0))
+        if rank == 1:
+            big.grad, small.grad = torch.full_like(big, 3.0), torch.full_like(small, 5.0)
+        n_loc = torch.tensor(0.0 if rank == 0 else 8.0)                 # device-side count: no host read of the total
+        P.all_reduce_gradients([big, small, unused], n_loc)
+        ok &= bool(torch.allclose(big.grad, torch.full_like(big, 3.0))) and bool(torch.allclose(small.grad, torch.full_like(small, 5.0)))
+        ok &= unused.grad is None
         ok &= P.max_over_ranks(1.0 + rank) == float(ws)
         ret[rank] = bool(ok)
     finally:
