@@ -372,9 +372,10 @@ struct FieldTcArgs {
 int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st);
 int prep_weights_tc(qf_ngp* f, cudaStream_t st);
 
-// QF_FIELD_TC=0 selects the fused mma.sync kernel, 1 the tcgen05/TMEM kernel, 2 the warp-specialised mma.sync kernel
+// The full forward runs on the warp-specialised tcgen05 / TMEM kernel (field_tc.cu) by default.  QF_FIELD_TC=0 selects the
+// fused mma.sync kernel (kept as the comparison baseline and for the density-only mode), 2 the warp-specialised mma.sync one.
 static int field_tc_mode() {
-  static const int m = getenv("QF_FIELD_TC") ? atoi(getenv("QF_FIELD_TC")) : 0;
+  static const int m = getenv("QF_FIELD_TC") ? atoi(getenv("QF_FIELD_TC")) : 1;
   return m;
 }
 

@@ -1,19 +1,35 @@
-// (3) Blackwell-native variant of the fused field kernel: the five MLP layers run on the 5th-generation tensor
-// cores with tcgen05.mma (operands in shared memory through UMMA descriptors, accumulators in TMEM), one CTA of
-// 128 threads per 128-sample tile.
+// (2)+(3) Blackwell-native fused field kernel — the DEFAULT full forward (radiance_fields/ngp.py:757-809):
+// warp-specialised CTA, hash-grid gathers on 12 producer warps, the five MLP layers on the 5th-generation tensor
+// cores (tcgen05.mma, SASS UTCHMMA) with every activation living in tensor memory.
 //
-//   thread i  <->  sample i of the tile  <->  TMEM lane i
+//   CTA = 512 threads, 2 CTAs per SM (persistent grid of 2 x 148), TMEM 256 columns per CTA.
 //
-// Each thread gathers the hash-grid features of ITS sample and stores them as one row of the layer-1 A operand
-// (K-major, no-swizzle canonical layout: 8-row x 16-byte core matrices).  One elected thread issues
-// tcgen05.mma (M=128, N=64 or 16, K=16 per instruction, fp16 operands, fp32 accumulate) and commits to an
-// mbarrier; every thread then reads its own accumulator row back with tcgen05.ld (32x32b: lane = row), applies
-// ReLU / exp / sigmoid in fp32 and writes the next layer's A row.  Compared with the mma.sync kernel (field.cu) the
-// weight fragments are never loaded through the LSU — the tensor core reads them from shared memory through the
-// async proxy — which leaves the L1TEX pipe, the limiter of this gather-bound kernel, to the table gathers.
+//   warps 0..11   GATHER: three "quads" of four warps.  A quad owns one 128-sample tile at a time; lane = sample,
+//                 warp w of the quad = rows 32w..32w+31 = TMEM lanes 32w..  (a warp can only touch the TMEM lane quarter
+//                 warp_id % 4, which is why roles are quad-aligned).  Each lane gathers its 16 levels x 8 corners from the
+//                 table and writes the 32 encoded features (16 packed columns) and the 16 SH values (8 columns) of its
+//                 sample STRAIGHT INTO TENSOR MEMORY with tcgen05.st — the layer-1 / layer-3 A operands never exist in
+//                 shared memory.  Two A-operand slots per quad, full/empty mbarriers.
+//   warps 12..15  MLP warpgroup: thread r <-> row r of the tile <-> TMEM lane r.  Its first thread issues the
+//                 tcgen05.mma chain (A from TMEM, B = weight images in shared memory through UMMA descriptors, fp32
+//                 accumulators in TMEM) and commits to an mbarrier; all 128 threads then read their accumulator row
+//                 back with tcgen05.ld (LDTM), apply ReLU / exp / sigmoid in fp32 and write the next layer's A row back
+//                 to TMEM (tcgen05.st): no LDS / STS at all in the steady state, no CTA-wide barrier — a 128-thread named
+//                 barrier orders the warpgroup's TMEM writes before its leader issues the next layer.
+//
+// Why: the mma.sync kernel (field.cu) is bound by the L1TEX data pipe (67 % busy, profiles/r1h): 204 K wavefronts per SM
+// of table gathers plus 93 K wavefronts of shared-memory fragment loads / tile stores for the MLPs, issued from the same
+// warps that gather.  Here the tensor core reads A from TMEM and only the 20 KB weight image from shared memory, the
+// gather warps never run MLP code, and the 20 KB of shared memory per CTA leave ~200 KB of the SM's array as L1.
+//
+// TMEM columns per CTA (32-bit cells, lane = tile row):
+//   [  0, 64)  R   D1 -> (in place) A2 hi|lo interleaved per 16-wide k-chunk -> D3 -> D4
+//   [ 64, 96)  X   [1, feat] chunk of A3 (8 cols) -> A4 -> A5 (packed fp16 pairs, 32 cols = K 64)
+//   [ 96,112)  S   D2 (density logit + 15 geo features), D5 (rgb logits)
+//   [112,256)  3 quads x 2 slots x 24 cols: A1 (16 cols = 32 encoded features) | SH (8 cols = 16 values)
 //
 // Numerics are those of field.cu: fp16 operands, fp32 accumulation, hi+lo split of the hidden activations for the
-// density logit.
+// density logit; the encoding is bit-identical (same encode_point).
 #include "field_common.cuh"
 
 namespace qf {
@@ -56,17 +72,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
 // InstrDescriptor for kind::f16: D=F32 (bits 4-5 = 1), A=B=F16 (0), both K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) { return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
 
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is read from tensor memory (row i = lane i, two K-consecutive halves per cell)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" :: "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" :: "r"(mbar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
@@ -75,14 +95,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
         : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 24)) __trap();   // never hang the GPU on a protocol error
+    if (!done && ++spins > (1u << 26)) __trap();   // never hang the GPU on a protocol error
   }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;\n" :: "r"(id), "r"(threads) : "memory"); }
 
-// 16 consecutive accumulator columns of this thread's TMEM lane
+// 16 consecutive 32-bit columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
@@ -93,6 +115,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};\n" :: "r"(taddr), "r"(r0), "r"(r1) : "memory");
 }
 
 struct FieldTcArgs {
@@ -112,44 +141,40 @@ struct FieldTcArgs {
   float* density;
 };
 
+// ---- roles and resources
+constexpr int kGatherWarps = 12, kQuads = kGatherWarps / 4, kSlots = 2;
+constexpr int kMlpWarp0 = kGatherWarps;                 // warps 12..15 (12 % 4 == 0: TMEM lane quarters line up)
+constexpr int kTcThreads = (kGatherWarps + 4) * 32;     // 512
+constexpr int kColR = 0, kColX = 64, kColS = 96, kColSlot0 = 112, kSlotCols = 24, kTmemCols = 256;
+static_assert(kColSlot0 + kQuads * kSlots * kSlotCols <= kTmemCols, "TMEM column budget");
 // shared memory map (bytes)
-constexpr int kSmW = 0;                        // weights, 20480
-constexpr int kSmX = kSmW + kTcWBytes;         // region X, 16 KB: A1 (128x32) -> A2lo (128x64) -> A3 (128x32)
-constexpr int kSmY = kSmX + 128 * 64 * 2;      // region Y, 16 KB: A2hi -> A4 -> A5 (128x64)
-constexpr int kSmBar = kSmY + 128 * 64 * 2;    // mbarrier (8 B) + tmem base (4 B)
-constexpr int kTcSmemBytes = kSmBar + 64;
-constexpr int kTmemCols = 128;                 // D wide at columns [0,64), D narrow at [64,80)
+constexpr int kSmW = 0;                                            // weights, 20480
+constexpr int kSmFull = kSmW + kTcWBytes;                          // full[quad][slot]  mbarriers (count 4: one per gather warp)
+constexpr int kSmEmpty = kSmFull + kQuads * kSlots * 8;            // empty[quad][slot] mbarriers (count 1: tcgen05.commit)
+constexpr int kSmMma = kSmEmpty + kQuads * kSlots * 8;             // MLP chain mbarrier
+constexpr int kSmTmem = kSmMma + 8;                                // TMEM base address
+constexpr int kSmSel = kSmTmem + 8;                                // selector ballots [quad][slot][4 warps]
+constexpr int kTcSmemBytes = kSmSel + kQuads * kSlots * 4 * 4;
 
-// store 8 halves (one 16-byte k-chunk) of this thread's row
-__device__ __forceinline__ void st_chunk(unsigned char* tile, int row, int chunk, int K, uint4 v) {
-  *reinterpret_cast<uint4*>(tile + (row >> 3) * (K >> 3) * 128 + chunk * 128 + (row & 7) * 16) = v;
-}
+__device__ __forceinline__ uint32_t slot_col(int quad, int slot) { return kColSlot0 + (quad * kSlots + slot) * kSlotCols; }
 
-// D[128 x N] (+)= A[128 x K] * W[N x K]^T, K/16 instructions
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, int K_a, uint32_t w_addr, int K, int N, bool accumulate) {
-  const uint32_t idesc = umma_idesc(128, N);
-  for (int j = 0; j < K / 16; ++j) {
-    const uint64_t da = umma_desc(a_addr + j * 256, 128, (K_a >> 3) * 128);
-    const uint64_t db = umma_desc(w_addr + j * 256, 128, (K >> 3) * 128);
-    umma_f16(tmem_d, da, db, idesc, (accumulate || j > 0) ? 1u : 0u);
-  }
-}
-
-__global__ void __launch_bounds__(128, 4) ngp_forward_tc_kernel(const FieldTcArgs a) {
+__global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const FieldTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
-  uint64_t* mbar_ptr = reinterpret_cast<uint64_t*>(smem + kSmBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 8);
-  const uint32_t mbar = smem_u32(mbar_ptr);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmTmem);
+  uint32_t* s_sel = reinterpret_cast<uint32_t*>(smem + kSmSel);
+  const uint32_t bar_full = smem_u32(smem + kSmFull), bar_empty = smem_u32(smem + kSmEmpty), bar_mma = smem_u32(smem + kSmMma);
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.weights_tc);
     uint4* dst = reinterpret_cast<uint4*>(smem + kSmW);
-    for (int i = tid; i < kTcWBytes / 16; i += 128) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kTcWBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
   }
-  if (tid == 0) {
-    mbar_init(mbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  if (tid < kQuads * kSlots) {
+    mbar_init(bar_full + tid * 8, 4);
+    mbar_init(bar_empty + tid * 8, 1);
   }
+  if (tid == 0) mbar_init(bar_mma, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
@@ -159,143 +184,191 @@ __global__ void __launch_bounds__(128, 4) ngp_forward_tc_kernel(const FieldTcArg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
-  const uint32_t sW = smem_u32(smem + kSmW), sX = smem_u32(smem + kSmX), sY = smem_u32(smem + kSmY);
-  unsigned char* X = smem + kSmX;
-  unsigned char* Y = smem + kSmY;
-  uint32_t phase = 0;
-
   const int64_t M = a.d_M ? (int64_t)__ldg(a.d_M) : a.M;
-  const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
-  const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
+  const int64_t n_tiles = (M + 127) >> 7;
+  // the CTA's n-th tile is tile (blockIdx.x + n * gridDim.x); quad (n % kQuads) gathers it into slot ((n / kQuads) % kSlots)
+  const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
 
-  for (int64_t base = (int64_t)blockIdx.x * 128; base < M; base += (int64_t)gridDim.x * 128) {
-    const int64_t i = base + tid;
-    const bool valid = i < M;
-    float x = 0.5f, y = 0.5f, z = 0.5f;
-    bool sel = false;
-    if (valid) {
-      const float* p = a.pos + i * a.pos_stride;
-      x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);
-      y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
-      z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
-      sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
-    }
-    // ---- encode: 32 features = 4 k-chunks of the layer-1 A row
-    {
-      unsigned char* xrow = X + (tid >> 3) * 512 + (tid & 7) * 16;   // K=32 canonical row: chunk c at +128*c, level l at chunk l/4
-      encode_point(a.desc, a.table, x, y, z,
-                   [&](int l, uint32_t h2) { *reinterpret_cast<uint32_t*>(xrow + (l >> 2) * 128 + (l & 3) * 4) = h2; });
-    }
-    uint32_t shp[8];
-    {
+  if (warp < kGatherWarps) {
+    // ===================== GATHER =====================
+    const int quad = warp >> 2, sub = warp & 3;
+    const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
+    const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
+    int k = 0;   // this quad's k-th tile
+    for (int64_t tile = blockIdx.x + (int64_t)quad * gridDim.x; tile < n_tiles; tile += (int64_t)kQuads * gridDim.x, ++k) {
+      const int slot = k & 1, use = k >> 1, idx = quad * kSlots + slot;
+      if (use > 0) {
+        mbar_wait(bar_empty + idx * 8, (use - 1) & 1);     // layer 3 of the slot's previous tile has read A1 and SH
+        tc_fence_after();
+      }
+      const uint32_t t_a1 = tmem_base + lane_bits + slot_col(quad, slot);
+      const int64_t i = tile * 128 + sub * 32 + lane;
+      const bool valid = i < M;
+      float x = 0.5f, y = 0.5f, z = 0.5f;
+      bool sel = false;
+      if (valid) {
+        const float* p = a.pos + i * a.pos_stride;
+        x = __fdiv_rn(__ldg(p) - amin[0], aext[0]);       // ngp.py:761-763
+        y = __fdiv_rn(__ldg(p + 1) - amin[1], aext[1]);
+        z = __fdiv_rn(__ldg(p + 2) - amin[2], aext[2]);
+        sel = (x > 0.f) && (x < 1.f) && (y > 0.f) && (y < 1.f) && (z > 0.f) && (z < 1.f);
+      }
       float dx = 0.f, dy = 0.f, dz = 1.f;
       if (valid) {
         int64_t r = a.ray64 ? __ldg(a.ray64 + i) : (a.ray32 ? (int64_t)__ldg(a.ray32 + i * a.ray32_stride) : i);
         const float* dp = a.dirs + 3 * r;
+        // (d+1)/2 then tcnn maps back with *2-1 (ngp.py:784; tcnn SH kernel)
         dx = ((__ldg(dp) + 1.0f) / 2.0f) * 2.0f - 1.0f;
         dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
         dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
       }
-      float sh[16];
-      sh4(dx, dy, dz, sh);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) shp[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- base L1: D[.,0:64) = A1 (X, K=32) * W1^T
-    if (tid == 0) { tc_fence_after(); issue_layer(tmem_base, sX, 32, sW + kTcW1, 32, 64, false); umma_commit(mbar); }
-    mbar_wait(mbar, phase); phase ^= 1;
-    tc_fence_after();
-    {
-      float v[16];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {   // 64 hidden units: ReLU, hi -> Y, lo -> X
-        tmem_ld16(t_row + q * 16, v);
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float r0 = fmaxf(v[2 * e], 0.f), r1 = fmaxf(v[2 * e + 1], 0.f);
-          __half2 h = __floats2half2_rn(r0, r1);
-          float2 f = __half22float2(h);
-          hi[e] = *reinterpret_cast<uint32_t*>(&h);
-          lo[e] = pack_h2(r0 - f.x, r1 - f.y);
-        }
-        st_chunk(Y, tid, 2 * q, 64, make_uint4(hi[0], hi[1], hi[2], hi[3]));
-        st_chunk(Y, tid, 2 * q + 1, 64, make_uint4(hi[4], hi[5], hi[6], hi[7]));
-        st_chunk(X, tid, 2 * q, 64, make_uint4(lo[0], lo[1], lo[2], lo[3]));
-        st_chunk(X, tid, 2 * q + 1, 64, make_uint4(lo[4], lo[5], lo[6], lo[7]));
+      // 16 levels, two per trip: the pair's 16 gathers are in flight together; each trip writes 2 TMEM columns of the row
+      {
+        uint32_t even = 0;
+        encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) {
+          if (l & 1) tmem_st2(t_a1 + (l - 1), even, h2);
+          else even = h2;
+        });
       }
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- base L2: D[.,64:80) = A2lo (X) * W2^T + A2hi (Y) * W2^T
-    if (tid == 0) {
-      tc_fence_after();
-      issue_layer(tmem_base + 64, sX, 64, sW + kTcW2, 64, 16, false);
-      issue_layer(tmem_base + 64, sY, 64, sW + kTcW2, 64, 16, true);
-      umma_commit(mbar);
-    }
-    mbar_wait(mbar, phase); phase ^= 1;
-    tc_fence_after();
-    float sigma;
-    {
-      float v[16];
-      tmem_ld16(t_row + 64, v);
-      sigma = sel ? expf(v[0] - 1.0f) : 0.f;                                  // ngp.py:772-775
-      // head input row (kernel order): [SH(16) | 1 | feat(15)]
-      st_chunk(X, tid, 0, 32, make_uint4(shp[0], shp[1], shp[2], shp[3]));
-      st_chunk(X, tid, 1, 32, make_uint4(shp[4], shp[5], shp[6], shp[7]));
-      st_chunk(X, tid, 2, 32, make_uint4(pack_h2(1.0f, v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7])));
-      st_chunk(X, tid, 3, 32, make_uint4(pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15])));
-    }
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    // ---- head L1: D[.,0:64) = A3 (X, K=32) * W3p^T
-    if (tid == 0) { tc_fence_after(); issue_layer(tmem_base, sX, 32, sW + kTcW3, 32, 64, false); umma_commit(mbar); }
-    mbar_wait(mbar, phase); phase ^= 1;
-    tc_fence_after();
-#pragma unroll 1
-    for (int stage = 0; stage < 2; ++stage) {
-      // ReLU(D) -> Y (A4 / A5)
-      float v[16];
+      {
+        float sh[16];
+        sh4(dx, dy, dz, sh);
+        uint32_t shp[8];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        tmem_ld16(t_row + q * 16, v);
-        uint32_t h[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) h[e] = pack_h2(fmaxf(v[2 * e], 0.f), fmaxf(v[2 * e + 1], 0.f));
-        st_chunk(Y, tid, 2 * q, 64, make_uint4(h[0], h[1], h[2], h[3]));
-        st_chunk(Y, tid, 2 * q + 1, 64, make_uint4(h[4], h[5], h[6], h[7]));
+        for (int q = 0; q < 8; ++q) shp[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
+        tmem_st8(t_a1 + 16, shp);
       }
-      fence_async_smem();
+      const unsigned selmask = __ballot_sync(0xffffffffu, sel);
+      if (lane == 0) s_sel[idx * 4 + sub] = selmask;
+      tmem_wait_st();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        if (stage == 0) issue_layer(tmem_base, sY, 64, sW + kTcW4, 64, 64, false);        // head L2 -> D[.,0:64)
-        else issue_layer(tmem_base + 64, sY, 64, sW + kTcW5, 64, 16, false);              // head L3 -> D[.,64:80)
-        umma_commit(mbar);
-      }
-      mbar_wait(mbar, phase); phase ^= 1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + idx * 8);
+    }
+  } else {
+    // ===================== MLP warpgroup =====================
+    const int row = tid - kMlpWarp0 * 32;                          // 0..127 = TMEM lane
+    const bool leader = row == 0;
+    const uint32_t t_row = tmem_base + lane_bits;                  // this warp's lane quarter, column 0
+    const uint32_t sW = smem_u32(smem + kSmW);
+    const uint32_t id64 = umma_idesc(128, 64), id16 = umma_idesc(128, 16);
+    // B descriptors: chunk j (16 k-values = two 8x8 core matrices) of a (N x K) K-major canonical image
+    auto bdesc = [&](int w_off, int K, int j) { return umma_desc(sW + w_off + j * 256, 128, (K >> 3) * 128); };
+    uint32_t phase = 0;
+    int n = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
+      const int quad = n % kQuads, kq = n / kQuads, slot = kq & 1, idx = quad * kSlots + slot;
+      mbar_wait(bar_full + idx * 8, (kq >> 1) & 1);
       tc_fence_after();
-    }
-    {
-      float v[16];
-      tmem_ld16(t_row + 64, v);
-      auto sig = [](float q) { return 1.0f / (1.0f + __expf(-q)); };
-      if (valid) {
-        float4 o = make_float4(sig(v[0]), sig(v[1]), sig(v[2]), sigma);
-        if (a.out4) a.out4[i] = o;
-        else { a.rgb[3 * i] = o.x; a.rgb[3 * i + 1] = o.y; a.rgb[3 * i + 2] = o.z; a.density[i] = o.w; }
+      const bool sel = (s_sel[idx * 4 + (row >> 5)] >> (row & 31)) & 1u;
+      const uint32_t c_a1 = tmem_base + slot_col(quad, slot);
+      // ---- base L1: R = A1 (K=32) * W1^T
+      if (leader) {
+        umma_f16_ts(tmem_base + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u);
+        umma_f16_ts(tmem_base + kColR, c_a1 + 8, bdesc(kTcW1, 32, 1), id64, 1u);
+        umma_commit(bar_mma);
       }
+      mbar_wait(bar_mma, phase); phase ^= 1;
+      tc_fence_after();
+      {
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {   // 64 hidden units: ReLU, hi | lo written in place over the 16 accumulator columns
+          tmem_ld16(t_row + kColR + q * 16, v);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float r0 = fmaxf(v[2 * e], 0.f), r1 = fmaxf(v[2 * e + 1], 0.f);
+            __half2 h = __floats2half2_rn(r0, r1);
+            float2 f = __half22float2(h);
+            hi[e] = *reinterpret_cast<uint32_t*>(&h);
+            lo[e] = pack_h2(r0 - f.x, r1 - f.y);
+          }
+          tmem_st8(t_row + kColR + q * 16, hi);
+          tmem_st8(t_row + kColR + q * 16 + 8, lo);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      named_bar(1, 128);
+      // ---- base L2: S = A2lo * W2^T + A2hi * W2^T  (K = 64 each)
+      if (leader) {
+        tc_fence_after();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColR + j * 16 + 8, bdesc(kTcW2, 64, j), id16, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColR + j * 16, bdesc(kTcW2, 64, j), id16, 1u);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, phase); phase ^= 1;
+      tc_fence_after();
+      float sigma;
+      {
+        float v[16];
+        tmem_ld16(t_row + kColS, v);
+        sigma = sel ? expf(v[0] - 1.0f) : 0.f;                                  // ngp.py:772-775
+        // second k-chunk of the head input row (kernel order [SH(16) | 1 | feat(15)])
+        uint32_t f[8] = {pack_h2(1.0f, v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]),
+                         pack_h2(v[8], v[9]), pack_h2(v[10], v[11]), pack_h2(v[12], v[13]), pack_h2(v[14], v[15])};
+        tmem_st8(t_row + kColX, f);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      named_bar(1, 128);
+      // ---- head L1: R = [SH | 1, feat] (K=32) * W3p^T ; its completion also frees the gather slot
+      if (leader) {
+        tc_fence_after();
+        umma_f16_ts(tmem_base + kColR, c_a1 + 16, bdesc(kTcW3, 32, 0), id64, 0u);
+        umma_f16_ts(tmem_base + kColR, tmem_base + kColX, bdesc(kTcW3, 32, 1), id64, 1u);
+        umma_commit(bar_empty + idx * 8);
+        umma_commit(bar_mma);
+      }
+      mbar_wait(bar_mma, phase); phase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int stage = 0; stage < 2; ++stage) {
+        // ReLU(R) -> X (A4 / A5)
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          tmem_ld16(t_row + kColR + q * 16, v);
+          uint32_t h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = pack_h2(fmaxf(v[2 * e], 0.f), fmaxf(v[2 * e + 1], 0.f));
+          tmem_st8(t_row + kColX + q * 8, h);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        named_bar(1, 128);
+        if (leader) {
+          tc_fence_after();
+          if (stage == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColR, tmem_base + kColX + j * 8, bdesc(kTcW4, 64, j), id64, j > 0 ? 1u : 0u);   // head L2
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColX + j * 8, bdesc(kTcW5, 64, j), id16, j > 0 ? 1u : 0u);   // head L3
+          }
+          umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase); phase ^= 1;
+        tc_fence_after();
+      }
+      {
+        float v[16];
+        tmem_ld16(t_row + kColS, v);
+        auto sig = [](float q) { return 1.0f / (1.0f + __expf(-q)); };
+        const int64_t i = tile * 128 + row;
+        if (i < M) {
+          float4 o = make_float4(sig(v[0]), sig(v[1]), sig(v[2]), sigma);
+          if (a.out4) a.out4[i] = o;
+          else { a.rgb[3 * i] = o.x; a.rgb[3 * i + 1] = o.y; a.rgb[3 * i + 2] = o.z; a.density[i] = o.w; }
+        }
+      }
+      // the next tile's L1 overwrites R (last read before the L5 barrier) and its L2 overwrites S only after the
+      // next named barrier, which every thread reaches after this tcgen05.ld has completed
+      tc_fence_before();
     }
-    tc_fence_before();
-    __syncthreads();   // region X is rewritten by the next tile's encode; its last reader (head L1) has completed
   }
   tc_fence_before();
   __syncthreads();
@@ -306,11 +379,10 @@ int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st) {
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights_tc = f->d_weights_tc;
-  QF_ENSURE_DYNAMIC_SMEM(ngp_forward_tc_kernel, kTcSmemBytes);
-  int64_t tiles = a.d_M ? (int64_t)kNumSMs * 4 : ceil_div(a.M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 4 ? tiles : (int64_t)kNumSMs * 4);
+  int64_t tiles = a.d_M ? (int64_t)kNumSMs * 2 : ceil_div(a.M, 128);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * 2 ? tiles : (int64_t)kNumSMs * 2);
   if (blocks < 1) blocks = 1;
-  ngp_forward_tc_kernel<<<blocks, 128, kTcSmemBytes, st>>>(a);
+  ngp_forward_tc_kernel<<<blocks, kTcThreads, kTcSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

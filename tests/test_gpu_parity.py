@@ -207,11 +207,11 @@ def test_ngp_forward_matches_oracle(dev, smoke_scene):
     assert maxabs(r, r2) == 0.0 and maxabs(s, s2) == 0.0
 
 
-@pytest.mark.parametrize("variant", ["1", "2"])
+@pytest.mark.parametrize("variant", ["0", "1", "2"])
 def test_ngp_forward_kernel_variants(dev, variant):
-    """The alternative full-forward kernels against the oracle: QF_FIELD_TC=1 is the tcgen05 / TMEM kernel
-    (csrc/field_tc.cu), QF_FIELD_TC=2 the warp-specialised producer/consumer kernel (csrc/field.cu).  Runs in a
-    subprocess because the selection is read once per process."""
+    """Every full-forward kernel against the oracle: QF_FIELD_TC=1 is the default, the warp-specialised tcgen05 / TMEM
+    kernel (csrc/field_tc.cu); 0 the fused mma.sync kernel and 2 the warp-specialised mma.sync producer/consumer kernel
+    (csrc/field.cu), kept as baselines.  Runs in a subprocess because the selection is read once per process."""
     import os, subprocess, sys, textwrap
     code = textwrap.dedent("""
         import os, sys, torch, numpy as np
@@ -229,7 +229,7 @@ def test_ngp_forward_kernel_variants(dev, variant):
         rgb_ref, dens_ref = O.ngp_forward(x, d, p)
         with torch.no_grad():
             rgb, dens = sc.radiance_field(x.to(dev), d.to(dev))
-            for n in (1, 127, 128, 129, 32 * 24 * 2 + 5):
+            for n in (1, 127, 128, 129, 32 * 24 * 2 + 5, 128 * 7 + 3):
                 r, s = sc.radiance_field(x[:n].to(dev), d[:n].to(dev))
                 assert maxabs(r, rgb[:n]) == 0.0 and maxabs(s, dens[:n]) == 0.0
         a_ref, a = 1 - torch.exp(-dens_ref * 0.005), 1 - torch.exp(-dens.cpu() * 0.005)
@@ -261,7 +261,7 @@ def test_ngp_golden_fixture(dev, golden):
     sel, xn = rf.normalize(T(g["x"]).to(dev))
     assert np.array_equal(sel.cpu().numpy(), g["selector"]) and maxabs(xn, g["xn"]) <= 1e-7
     sd = rf.state_dict()
-    assert set(sd) == {"aabb", "mlp_base.params", "mlp_head.params"}            # tinycudann checkpoint keys
+    assert set(sd) == {"aabb", "mlp_base.params", "mlp_head.params", "direction_encoding.params"}   # tinycudann checkpoint keys
     with pytest.raises(NameError):
         rf(T(g["x"]).to(dev), None)                                              # quirk Q8
     with pytest.raises(AssertionError):

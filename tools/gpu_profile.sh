@@ -17,7 +17,7 @@ list)
   tail -2 gpurun_out/ncu_list_$TAG.log ;;
 full)
   $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'trace_compact_kernel|ngp_forward_kernel' -s 8 -c 4 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'trace_compact_kernel|ngp_forward' -s 8 -c 4 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_full_$TAG.log ;;
 train)
   TCMD="python tools/diag_train.py 3"
