@@ -12,7 +12,8 @@ Numeric conventions shared with the CUDA kernels:
     order spelled out below (numpy evaluates ``a*b-c*d`` as three separately rounded ops;
     the kernel uses ``__fmul_rn/__fadd_rn``), so hit ids / counts are bit-exact;
   * tcnn module boundaries round to fp16 (hash-grid output, SH output, head input) because
-    tinycudann's encodings emit ``__half``; MLP arithmetic itself is restated in fp32.
+    tinycudann's encodings emit ``__half``; the hash-grid interpolation accumulates in half like
+    tcnn's ``kernel_grid`` (one half FMA per corner); MLP arithmetic itself is restated in fp32.
 """
 from __future__ import annotations
 
@@ -507,8 +508,15 @@ _U32 = 0xFFFFFFFF
 
 
 def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> torch.Tensor:
-    """tcnn `kernel_grid` forward restated.  x01 (M,3) fp32, table (n_entries, F) fp32 holding
-    fp16-representable values.  Output (M, L·F) fp32 holding fp16-rounded values, level-major."""
+    """tcnn `kernel_grid` forward restated (recalled from tiny-cuda-nn `encodings/grid.h`, the un-pinned master the
+    reference installs, ngp.py:17-21).  x01 (M,3) fp32, table (n_entries, F) fp32 holding fp16-representable values.
+    Output (M, L·F) fp32 holding fp16 values, level-major.
+
+    Interpolation arithmetic is tcnn's: the grid and the result are `T = __half`; per corner the weight
+    ((1·wx)·wy)·wz is formed in fp32, cast to half, and `result = fma((T)weight, grid_val, result)` accumulates with one
+    fused half multiply-add (single rounding) in corner order 0..7.  The chain is evaluated exactly here (float64
+    product + sum of half values, one correctly rounded conversion to half per corner — numpy's double->half).
+    Gradients (table, positions) follow the un-rounded trilinear form, straight through the half roundings."""
     M = x01.shape[0]
     Fdim = meta.n_features
     outs = []
@@ -521,7 +529,8 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
         cell = torch.floor(pos)
         frac = pos - cell
         cu = cell.to(torch.int64) & _U32              # (uint32_t)(int)floorf(pos)
-        acc = torch.zeros((M, Fdim), dtype=torch.float32)
+        lin = torch.zeros((M, Fdim), dtype=torch.float32)
+        acc16 = np.zeros((M, Fdim), dtype=np.float16)
         for corner in range(8):
             w = torch.ones(M, dtype=torch.float32)
             g = []
@@ -537,8 +546,12 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
             else:
                 idx = (g[0] + ((g[1] * res) & _U32) + ((g[2] * ((res * res) & _U32)) & _U32)) & _U32
             idx = idx % size + int(meta.offset[l])
-            acc = acc + w[:, None] * table[idx]
-        outs.append(_round_h(acc))
+            tv = table[idx]
+            lin = lin + w[:, None] * tv
+            w16 = w.detach().numpy().astype(np.float16).astype(np.float64)
+            acc16 = (w16[:, None] * tv.detach().numpy().astype(np.float64) + acc16.astype(np.float64)).astype(np.float16)
+        exact = torch.from_numpy(acc16.astype(np.float32))
+        outs.append(lin + (exact - lin).detach())
     return torch.cat(outs, dim=1)
 
 
@@ -646,6 +659,23 @@ def ngp_forward(positions: torch.Tensor, directions: torch.Tensor, p: NGPParams)
     assert positions.shape == directions.shape, f"{positions.shape} v.s. {directions.shape}"
     density, emb = ngp_query_density(positions, p)
     return ngp_query_rgb(directions, emb, p), density
+
+
+def ngp_relu_margin(positions: torch.Tensor, directions: torch.Tensor, p: NGPParams) -> torch.Tensor:
+    """Per sample, the smallest |pre-activation| over the 192 hidden units of `ngp_forward` (tcnn precision: hidden
+    activations rounded to half).  The gradient of the field is discontinuous where a pre-activation crosses zero, so two
+    correct implementations whose accumulation orders differ disagree by a whole unit's gradient on samples with a
+    margin below their rounding noise; gradient parity tests leave those samples out."""
+    with torch.no_grad():
+        _, x01 = ngp_normalize(positions, p.aabb)
+        enc = hashgrid_encode(x01, p.table, p.meta)
+        pre1 = enc @ p.base_w[0].t()
+        out = _round_h(torch.relu(pre1)) @ p.base_w[1].t()
+        sh = sh4((directions + 1.0) / 2.0 * 2.0 - 1.0).half().float()
+        pad = torch.full((directions.shape[0], 1), HEAD_PAD_VALUE, dtype=torch.float32)
+        pre3 = torch.cat([sh, _round_h(out[:, 1:16]), pad], dim=-1) @ p.head_w[0].t()
+        pre4 = _round_h(torch.relu(pre3)) @ p.head_w[1].t()
+        return torch.minimum(torch.minimum(pre1.abs().min(dim=1).values, pre3.abs().min(dim=1).values), pre4.abs().min(dim=1).values)
 
 
 # --------------------------------------------------------------------------------------

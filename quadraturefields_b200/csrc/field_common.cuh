@@ -18,7 +18,7 @@ constexpr int kTileStride = 56;           // per-sample staging row: 32 enc + 16
 // ---- hash-grid encode of one point: 16 levels, trilinear, fp32 interpolation, fp16 result
 // The level loop is kept ROLLED (two levels per trip, the gathers of both issued before either is consumed):
 // fully unrolled it is ~13k instructions and the kernel stalls on instruction fetch.
-struct Corner8 { uint32_t idx[8]; float fx, fy, fz; uint32_t odd; };   // odd: low bit of the cell's x index (hashed levels)
+struct Corner8 { uint32_t idx[8]; float fx, fy, fz; };
 
 __device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, float x, float y, float z, Corner8& c) {
   const float scale = d.scale[l];
@@ -27,7 +27,6 @@ __device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, floa
   const float flx = floorf(px), fly = floorf(py), flz = floorf(pz);
   const uint32_t cx = (uint32_t)(int)flx, cy = (uint32_t)(int)fly, cz = (uint32_t)(int)flz;
   c.fx = px - flx; c.fy = py - fly; c.fz = pz - flz;
-  c.odd = cx & 1u;
   if (d.hashed[l]) {   // hashed levels always have size == 2^log2_hashmap_size
     const uint32_t mask = size - 1;
     const uint32_t y0 = cy * 2654435761u, y1 = (cy + 1) * 2654435761u, z0 = cz * 805459861u, z1 = (cz + 1) * 805459861u;
@@ -48,69 +47,31 @@ __device__ __forceinline__ void level_indices(const qf_grid_desc& d, int l, floa
   }
 }
 
+// Trilinear blend of one level, tcnn's arithmetic (kernel_grid, recalled: `result = fma((T)weight, grid_val(...), result)`
+// with T = __half): the corner weight ((wx*wy)*wz) is formed in fp32, rounded to half and accumulated with one half2 FMA
+// per corner, corners in tcnn's order (bit d of k selects the upper neighbour along dimension d).  The oracle
+// (quadfield_oracle.hashgrid_encode) restates exactly this, so the 32 encoded features agree bit for bit.
 __device__ __forceinline__ uint32_t level_blend(const Corner8& c, const __half2* v) {
-  float r0 = 0.f, r1 = 0.f;
+  const float wx[2] = {1.f - c.fx, c.fx}, wy[2] = {1.f - c.fy, c.fy}, wz[2] = {1.f - c.fz, c.fz};
+  __half2 acc = __float2half2_rn(0.f);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
-    w *= (k & 4) ? c.fz : 1.f - c.fz;
-    float2 f = __half22float2(v[k]);
-    r0 = __fadd_rn(r0, __fmul_rn(w, f.x));   // separately rounded like the oracle: the encoding is bit-exact
-    r1 = __fadd_rn(r1, __fmul_rn(w, f.y));
+    const float w = __fmul_rn(__fmul_rn(wx[k & 1], wy[(k >> 1) & 1]), wz[k >> 2]);
+    acc = __hfma2(__float2half2_rn(w), v[k], acc);
   }
-  __half2 hv = __floats2half2_rn(r0, r1);
-  return *reinterpret_cast<uint32_t*>(&hv);
+  return *reinterpret_cast<uint32_t*>(&acc);
 }
-// The weight of corner k is ((wx*wy)*wz) in the oracle's order: w starts at 1 and is multiplied by the
-// x, y, z factors in turn; (1*wx)*wy*wz == (wx*wy)*wz exactly.
 
-// writes 2 halves per level to out[2*l] (shared-memory row of the sample, or a local array)
-// The 8 corner entries of one level: eight 4-byte gathers.
-// QF_PAIRED_GATHER (off; measured and rejected): the hash leaves x un-multiplied, so for an EVEN cell x
-// the two x-neighbours of a hashed level differ only in index bit 0 and sit in one aligned 8-byte pair.  Variant 1: even
-// lanes one 8-byte load, odd lanes two 4-byte loads (three predicated instructions into the same two registers);
-// variant 2: every lane loads the pair around its first corner, odd lanes add a 4-byte load.  Both touch 1.5 instead of
-// 2 lines per lane and x-pair, both are bit-identical, neither is faster (c2 shade 0.242 -> 0.252 / 0.246 ms).
-#ifndef QF_PAIRED_GATHER
-#define QF_PAIRED_GATHER 0
-#endif
+// The 8 corner entries of one level: eight 4-byte gathers, each address formed with one 32x32->64 multiply-add.
 __device__ __forceinline__ void load_corners(const qf_grid_desc& d, int l, const __half2* __restrict__ table, const Corner8& c,
                                              __half2* v) {
   const __half2* t = table + d.offset[l];
-#if QF_PAIRED_GATHER
-  if (d.hashed[l]) {
-    const uint32_t odd = c.odd;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t i0 = c.idx[2 * j], i1 = c.idx[2 * j + 1];
-#if QF_PAIRED_GATHER == 1
-      const __half2* pa = t + (odd ? i0 : (i0 & ~1u));
-      const __half2* pb = t + i1;
-      uint32_t e0, e1;
-      asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t"
-          "@p ld.global.nc.b32 %0, [%2];\n\t"
-          "@p ld.global.nc.b32 %1, [%3];\n\t"
-          "@!p ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
-          : "=&r"(e0), "=&r"(e1)
-          : "l"(pa), "l"(pb), "r"(odd));
-      const bool swap = !odd && (i0 & 1u);          // even cell: entry i0 sits in the half given by its low bit
-      const uint32_t a = swap ? e1 : e0, b = swap ? e0 : e1;
-#else
-      // every lane loads the aligned pair around i0; odd cells add one 4-byte load for the far x-neighbour
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(t + (i0 & ~1u)));
-      uint32_t lone = 0u;
-      if (odd) lone = __ldg(reinterpret_cast<const uint32_t*>(t + i1));
-      const uint32_t a = (i0 & 1u) ? w.y : w.x;
-      const uint32_t b = odd ? lone : ((i0 & 1u) ? w.x : w.y);
-#endif
-      v[2 * j] = *reinterpret_cast<const __half2*>(&a);
-      v[2 * j + 1] = *reinterpret_cast<const __half2*>(&b);
-    }
-    return;
+  for (int k = 0; k < 8; ++k) {
+    uint32_t r;
+    asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %2;\n\tld.global.nc.b32 %0, [a];\n\t}" : "=r"(r) : "r"(c.idx[k]), "l"(t));
+    v[k] = *reinterpret_cast<__half2*>(&r);
   }
-#endif
-#pragma unroll
-  for (int k = 0; k < 8; ++k) v[k] = __ldg(t + c.idx[k]);
 }
 
 template <typename Store>

@@ -1,16 +1,16 @@
 // (2)+(3) Blackwell-native fused field kernel — the DEFAULT full forward (radiance_fields/ngp.py:757-809):
-// warp-specialised CTA, hash-grid gathers on 12 producer warps, the five MLP layers on the 5th-generation tensor
+// warp-specialised CTA, hash-grid gathers on 16 producer warps, the five MLP layers on the 5th-generation tensor
 // cores (tcgen05.mma, SASS UTCHMMA) with every activation living in tensor memory.
 //
-//   CTA = 512 threads, 2 CTAs per SM (persistent grid of 2 x 148), TMEM 256 columns per CTA.
+//   CTA = 640 threads, 2 CTAs per SM (persistent grid of 2 x 148), TMEM 256 columns per CTA.
 //
-//   warps 0..11   GATHER: three "quads" of four warps.  A quad owns one 128-sample tile at a time; lane = sample,
+//   warps 0..15   GATHER: four "quads" of four warps.  A quad owns one 128-sample tile at a time; lane = sample,
 //                 warp w of the quad = rows 32w..32w+31 = TMEM lanes 32w..  (a warp can only touch the TMEM lane quarter
 //                 warp_id % 4, which is why roles are quad-aligned).  Each lane gathers its 16 levels x 8 corners from the
 //                 table and writes the 32 encoded features (16 packed columns) and the 16 SH values (8 columns) of its
 //                 sample STRAIGHT INTO TENSOR MEMORY with tcgen05.st — the layer-1 / layer-3 A operands never exist in
-//                 shared memory.  Two A-operand slots per quad, full/empty mbarriers.
-//   warps 12..15  MLP warpgroup: thread r <-> row r of the tile <-> TMEM lane r.  Its first thread issues the
+//                 shared memory.  Two A1 slots and one SH slot per quad, full/empty mbarriers.
+//   warps 16..19  MLP warpgroup: thread r <-> row r of the tile <-> TMEM lane r.  Its first thread issues the
 //                 tcgen05.mma chain (A from TMEM, B = weight images in shared memory through UMMA descriptors, fp32
 //                 accumulators in TMEM) and commits to an mbarrier; all 128 threads then read their accumulator row
 //                 back with tcgen05.ld (LDTM), apply ReLU / exp / sigmoid in fp32 and write the next layer's A row back
@@ -23,10 +23,10 @@
 // gather warps never run MLP code, and the 20 KB of shared memory per CTA leave ~200 KB of the SM's array as L1.
 //
 // TMEM columns per CTA (32-bit cells, lane = tile row):
-//   [  0, 64)  R   D1 -> (in place) A2 hi|lo interleaved per 16-wide k-chunk -> D3 -> D4
-//   [ 64, 96)  X   [1, feat] chunk of A3 (8 cols) -> A4 -> A5 (packed fp16 pairs, 32 cols = K 64)
-//   [ 96,112)  S   D2 (density logit + 15 geo features), D5 (rgb logits)
-//   [112,256)  3 quads x 2 slots x 24 cols: A1 (16 cols = 32 encoded features) | SH (8 cols = 16 values)
+//   [  0, 64)  R   D1 -> (in place) A2 hi|lo interleaved per 16-wide k-chunk -> D3 -> D4 -> D5 (rgb logits, 16 cols)
+//   [ 64, 96)  X   D2 (density logit + 15 geo features) in [80,96) -> [1, feat] chunk of A3 in [64,72) -> A4 -> A5
+//                  (packed fp16 pairs, 32 cols = K 64)
+//   [ 96,256)  4 quads x 40 cols: A1 slot 0 | A1 slot 1 (16 cols each = 32 encoded features) | SH (8 cols = 16 values)
 //
 // Numerics are those of field.cu: fp16 operands, fp32 accumulation, hi+lo split of the hidden activations for the
 // density logit; the encoding is bit-identical (same encode_point).
@@ -142,21 +142,22 @@ struct FieldTcArgs {
 };
 
 // ---- roles and resources
-constexpr int kGatherWarps = 12, kQuads = kGatherWarps / 4, kSlots = 2;
-constexpr int kMlpWarp0 = kGatherWarps;                 // warps 12..15 (12 % 4 == 0: TMEM lane quarters line up)
-constexpr int kTcThreads = (kGatherWarps + 4) * 32;     // 512
-constexpr int kColR = 0, kColX = 64, kColS = 96, kColSlot0 = 112, kSlotCols = 24, kTmemCols = 256;
-static_assert(kColSlot0 + kQuads * kSlots * kSlotCols <= kTmemCols, "TMEM column budget");
+constexpr int kGatherWarps = 16, kQuads = kGatherWarps / 4, kSlots = 2;
+constexpr int kMlpWarp0 = kGatherWarps;                 // warps 16..19 (16 % 4 == 0: TMEM lane quarters line up)
+constexpr int kTcThreads = (kGatherWarps + 4) * 32;     // 640
+constexpr int kColR = 0, kColX = 64, kColS = 80, kColSlot0 = 96, kQuadCols = 40, kTmemCols = 256;
+static_assert(kColSlot0 + kQuads * kQuadCols <= kTmemCols, "TMEM column budget");
 // shared memory map (bytes)
 constexpr int kSmW = 0;                                            // weights, 20480
 constexpr int kSmFull = kSmW + kTcWBytes;                          // full[quad][slot]  mbarriers (count 4: one per gather warp)
-constexpr int kSmEmpty = kSmFull + kQuads * kSlots * 8;            // empty[quad][slot] mbarriers (count 1: tcgen05.commit)
-constexpr int kSmMma = kSmEmpty + kQuads * kSlots * 8;             // MLP chain mbarrier
+constexpr int kSmEmpty = kSmFull + kQuads * kSlots * 8;            // empty[quad] mbarriers (count 1: tcgen05.commit of layer 3)
+constexpr int kSmMma = kSmEmpty + kQuads * 8;                      // MLP chain mbarrier
 constexpr int kSmTmem = kSmMma + 8;                                // TMEM base address
 constexpr int kSmSel = kSmTmem + 8;                                // selector ballots [quad][slot][4 warps]
 constexpr int kTcSmemBytes = kSmSel + kQuads * kSlots * 4 * 4;
 
-__device__ __forceinline__ uint32_t slot_col(int quad, int slot) { return kColSlot0 + (quad * kSlots + slot) * kSlotCols; }
+__device__ __forceinline__ uint32_t a1_col(int quad, int slot) { return kColSlot0 + quad * kQuadCols + slot * 16; }
+__device__ __forceinline__ uint32_t sh_col(int quad) { return kColSlot0 + quad * kQuadCols + 32; }
 
 __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const FieldTcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -169,10 +170,8 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
     uint4* dst = reinterpret_cast<uint4*>(smem + kSmW);
     for (int i = tid; i < kTcWBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
   }
-  if (tid < kQuads * kSlots) {
-    mbar_init(bar_full + tid * 8, 4);
-    mbar_init(bar_empty + tid * 8, 1);
-  }
+  if (tid < kQuads * kSlots) mbar_init(bar_full + tid * 8, 4);
+  if (tid < kQuads) mbar_init(bar_empty + tid * 8, 1);
   if (tid == 0) mbar_init(bar_mma, 1);
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
@@ -196,12 +195,10 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
     const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
     int k = 0;   // this quad's k-th tile
     for (int64_t tile = blockIdx.x + (int64_t)quad * gridDim.x; tile < n_tiles; tile += (int64_t)kQuads * gridDim.x, ++k) {
-      const int slot = k & 1, use = k >> 1, idx = quad * kSlots + slot;
-      if (use > 0) {
-        mbar_wait(bar_empty + idx * 8, (use - 1) & 1);     // layer 3 of the slot's previous tile has read A1 and SH
-        tc_fence_after();
-      }
-      const uint32_t t_a1 = tmem_base + lane_bits + slot_col(quad, slot);
+      const int slot = k & 1, idx = quad * kSlots + slot;
+      // A1 slot `slot` was last read by layer 1 of this quad's tile k-2: complete, because before writing tile k-1's SH
+      // this warp waited for layer 3 of tile k-2 (below)
+      const uint32_t t_a1 = tmem_base + lane_bits + a1_col(quad, slot);
       const int64_t i = tile * 128 + sub * 32 + lane;
       const bool valid = i < M;
       float x = 0.5f, y = 0.5f, z = 0.5f;
@@ -236,7 +233,11 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
         uint32_t shp[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) shp[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
-        tmem_st8(t_a1 + 16, shp);
+        if (k > 0) {
+          mbar_wait(bar_empty + quad * 8, (k - 1) & 1);     // layer 3 of this quad's previous tile has read the SH columns
+          tc_fence_after();
+        }
+        tmem_st8(tmem_base + lane_bits + sh_col(quad), shp);
       }
       const unsigned selmask = __ballot_sync(0xffffffffu, sel);
       if (lane == 0) s_sel[idx * 4 + sub] = selmask;
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       mbar_wait(bar_full + idx * 8, (kq >> 1) & 1);
       tc_fence_after();
       const bool sel = (s_sel[idx * 4 + (row >> 5)] >> (row & 31)) & 1u;
-      const uint32_t c_a1 = tmem_base + slot_col(quad, slot);
+      const uint32_t c_a1 = tmem_base + a1_col(quad, slot), c_sh = tmem_base + sh_col(quad);
       // ---- base L1: R = A1 (K=32) * W1^T
       if (leader) {
         umma_f16_ts(tmem_base + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u);
@@ -318,9 +319,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       // ---- head L1: R = [SH | 1, feat] (K=32) * W3p^T ; its completion also frees the gather slot
       if (leader) {
         tc_fence_after();
-        umma_f16_ts(tmem_base + kColR, c_a1 + 16, bdesc(kTcW3, 32, 0), id64, 0u);
+        umma_f16_ts(tmem_base + kColR, c_sh, bdesc(kTcW3, 32, 0), id64, 0u);
         umma_f16_ts(tmem_base + kColR, tmem_base + kColX, bdesc(kTcW3, 32, 1), id64, 1u);
-        umma_commit(bar_empty + idx * 8);
+        umma_commit(bar_empty + quad * 8);
         umma_commit(bar_mma);
       }
       mbar_wait(bar_mma, phase); phase ^= 1;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
             for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColR, tmem_base + kColX + j * 8, bdesc(kTcW4, 64, j), id64, j > 0 ? 1u : 0u);   // head L2
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColX + j * 8, bdesc(kTcW5, 64, j), id16, j > 0 ? 1u : 0u);   // head L3
+            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColR, tmem_base + kColX + j * 8, bdesc(kTcW5, 64, j), id16, j > 0 ? 1u : 0u);   // head L3 -> R[0,16)
           }
           umma_commit(bar_mma);
         }
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       }
       {
         float v[16];
-        tmem_ld16(t_row + kColS, v);
+        tmem_ld16(t_row + kColR, v);
         auto sig = [](float q) { return 1.0f / (1.0f + __expf(-q)); };
         const int64_t i = tile * 128 + row;
         if (i < M) {
@@ -365,9 +366,9 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
           else { a.rgb[3 * i] = o.x; a.rgb[3 * i + 1] = o.y; a.rgb[3 * i + 2] = o.z; a.density[i] = o.w; }
         }
       }
-      // the next tile's L1 overwrites R (last read before the L5 barrier) and its L2 overwrites S only after the
-      // next named barrier, which every thread reaches after this tcgen05.ld has completed
+      // the next tile's L1 overwrites R, which every thread of the warpgroup must have finished reading
       tc_fence_before();
+      named_bar(1, 128);
     }
   }
   tc_fence_before();

@@ -583,7 +583,10 @@ def _rel(a, b):
 def test_ngp_backward_matches_oracle_autograd(dev, smoke_scene, round_hidden, tol, cos_min):
     """dL/d(table, MLP weights) from qf_ngp_backward vs PyTorch autograd through the oracle.
     round_hidden=True: oracle with tcnn's precision (hidden activations rounded to fp16, straight-through) — the
-    kernel's arithmetic; gradients agree to 2e-3 of the largest entry.  round_hidden=False: strict fp32 oracle; ReLU
+    kernel's arithmetic; gradients agree to 2e-3 of the largest entry on the samples whose ReLU pattern is unambiguous
+    (every hidden pre-activation further than 3e-4 from zero — `O.ngp_relu_margin`; a sample with a pre-activation inside
+    the accumulation-order noise flips one unit's whole gradient, a 1e-2 effect that is not an error of either side:
+    measured r2, one such hit sample moved head L1 by 8e-3).  round_hidden=False: strict fp32 oracle; ReLU
     sign flips of pre-activations within fp16 rounding of zero make the gradient differ by ~2% (it is discontinuous
     there), so the bar is 4e-2 and cosine 0.9998."""
     sc = smoke_scene
@@ -593,6 +596,10 @@ def test_ngp_backward_matches_oracle_autograd(dev, smoke_scene, round_hidden, to
     g = torch.Generator().manual_seed(11)
     x = torch.cat([T(tup[0]), (torch.rand(500, 3, generator=g) * 2 - 1) * 1.6])        # hits + random points, some outside the aabb
     dirs = torch.cat([T(d)[T(tup[2])], torch.nn.functional.normalize(torch.randn(500, 3, generator=g), dim=-1)])
+    if round_hidden:
+        keep = O.ngp_relu_margin(x, dirs, oracle_params(sc)) > 3e-4
+        assert int(keep.sum()) > 0.6 * x.shape[0]
+        x, dirs = x[keep], dirs[keep]
     M = x.shape[0]
     wr, ws = torch.randn(M, 3, generator=g), torch.randn(M, 1, generator=g) * 0.01
     p = _grad_params(sc)
