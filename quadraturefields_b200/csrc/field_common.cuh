@@ -62,15 +62,48 @@ __device__ __forceinline__ uint32_t level_blend(const Corner8& c, const __half2*
   return *reinterpret_cast<uint32_t*>(&acc);
 }
 
-// The 8 corner entries of one level: eight 4-byte gathers, each address formed with one 32x32->64 multiply-add.
+// The 8 corner entries of one level.
+// Dense levels: eight 4-byte gathers.  Hashed levels: the hash leaves x un-multiplied (prime 1), so the two x-neighbours
+// of a (y,z) corner pair are entries i0 = (cx ^ h) & mask and i1 = ((cx+1) ^ h) & mask; for an EVEN cell x they differ
+// in bit 0 only and sit in one aligned 8-byte word.  Every lane fetches the aligned pair around i0 with one 8-byte load;
+// lanes with an odd cell x add a predicated 4-byte load for i1.  An L1TEX wavefront is spent per distinct 128-byte line
+// per instruction, so at the fine levels (32 lanes, 32 lines) the x-pair costs 1.5 instead of 2 instructions' worth of
+// wavefronts; the gather warps of the field kernel are bound by exactly that pipe (profiles/r2c).  Bit-identical output.
+#ifndef QF_PAIRED_GATHER
+#define QF_PAIRED_GATHER 1
+#endif
+__device__ __forceinline__ uint32_t ldg_entry(const __half2* t, uint32_t idx) {
+  uint32_t r;
+  asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %2;\n\tld.global.nc.b32 %0, [a];\n\t}" : "=r"(r) : "r"(idx), "l"(t));
+  return r;
+}
 __device__ __forceinline__ void load_corners(const qf_grid_desc& d, int l, const __half2* __restrict__ table, const Corner8& c,
                                              __half2* v) {
   const __half2* t = table + d.offset[l];
+#if QF_PAIRED_GATHER
+  if (d.hashed[l]) {
+    // x-corner parity: idx[0] and idx[1] differ in bit 0 only  <=>  the cell's x is even (all four pairs alike)
+    const bool even = ((c.idx[0] ^ c.idx[1]) == 1u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t i0 = c.idx[2 * j], i1 = c.idx[2 * j + 1];
+      uint32_t wx, wy, lone = 0u;
+      asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %2, 8, %3;\n\tld.global.nc.v2.b32 {%0, %1}, [a];\n\t}"
+          : "=r"(wx), "=r"(wy) : "r"(i0 >> 1), "l"(t));
+      if (!even) lone = ldg_entry(t, i1);
+      const bool hi0 = i0 & 1u;
+      const uint32_t e0 = hi0 ? wy : wx;
+      const uint32_t e1 = even ? (hi0 ? wx : wy) : lone;
+      v[2 * j] = *reinterpret_cast<const __half2*>(&e0);
+      v[2 * j + 1] = *reinterpret_cast<const __half2*>(&e1);
+    }
+    return;
+  }
+#endif
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    uint32_t r;
-    asm("{\n\t.reg .u64 a;\n\tmad.wide.u32 a, %1, 4, %2;\n\tld.global.nc.b32 %0, [a];\n\t}" : "=r"(r) : "r"(c.idx[k]), "l"(t));
-    v[k] = *reinterpret_cast<__half2*>(&r);
+    const uint32_t r = ldg_entry(t, c.idx[k]);
+    v[k] = *reinterpret_cast<const __half2*>(&r);
   }
 }
 
@@ -93,6 +126,41 @@ __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half
     if (two) store(l + 1, level_blend(c1, v1));
   }
 }
+// Software-pipelined variant for gather-only warps (field_tc.cu): the 8 gathers of level l+1 are issued BEFORE
+// level l is blended, so a warp always has loads queued in the L1TEX pipe while it does its index / blend arithmetic (with
+// encode_point the two phases alternate, and warps fall into a convoy: ncu r2c showed issue 53 % + L1 wavefront pipe 63 %
+// busy, i.e. almost no overlap).  Same arithmetic, bit-identical output; costs 11 more live registers.
+struct LevelLoad { __half2 v[8]; float fx, fy, fz; };
+
+__device__ __forceinline__ void level_issue(const qf_grid_desc& d, int l, const __half2* __restrict__ table, float x, float y,
+                                            float z, LevelLoad& o) {
+  Corner8 c;
+  level_indices(d, l, x, y, z, c);
+  load_corners(d, l, table, c, o.v);
+  o.fx = c.fx; o.fy = c.fy; o.fz = c.fz;
+}
+__device__ __forceinline__ uint32_t level_finish(const LevelLoad& o) {
+  Corner8 c;
+  c.fx = o.fx; c.fy = o.fy; c.fz = o.fz;
+  return level_blend(c, o.v);
+}
+
+template <typename Store2>   // store2(l_even, h2_even, h2_odd) once per level pair; n_levels must be even
+__device__ __forceinline__ void encode_point_pipelined(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
+                                                       float z, Store2 store2) {
+  const int L = d.n_levels;
+  LevelLoad a, b;
+  level_issue(d, 0, table, x, y, z, a);
+#pragma unroll 1
+  for (int l = 0; l < L; l += 2) {
+    level_issue(d, l + 1, table, x, y, z, b);
+    const uint32_t e = level_finish(a);
+    if (l + 2 < L) level_issue(d, l + 2, table, x, y, z, a);
+    const uint32_t o = level_finish(b);
+    store2(l, e, o);
+  }
+}
+
 // backward of one level: scatter the gradient of its two features to the 8 corners (fp32 atomics)
 __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
                                               float z, float g0, float g1) {

@@ -1,35 +1,37 @@
 // (2)+(3) Blackwell-native fused field kernel — the DEFAULT full forward (radiance_fields/ngp.py:757-809):
-// warp-specialised CTA, hash-grid gathers on 16 producer warps, the five MLP layers on the 5th-generation tensor
-// cores (tcgen05.mma, SASS UTCHMMA) with every activation living in tensor memory.
+// warp-specialised CTA, hash-grid gathers on producer warps, the five MLP layers on the 5th-generation tensor cores
+// (tcgen05.mma, SASS UTCHMMA) with every activation living in tensor memory.
 //
-//   CTA = 640 threads, 2 CTAs per SM (persistent grid of 2 x 148), TMEM 256 columns per CTA.
+//   CTA = Q gather "quads" (4 warps each) + G MLP warpgroups; CPS CTAs per SM, persistent grid of CPS x 148.
+//   Default Q=3, G=1, CPS=2 (512 threads, 256 TMEM columns per CTA); the A/B of r2 is in DESIGN §4a.
 //
-//   warps 0..15   GATHER: four "quads" of four warps.  A quad owns one 128-sample tile at a time; lane = sample,
-//                 warp w of the quad = rows 32w..32w+31 = TMEM lanes 32w..  (a warp can only touch the TMEM lane quarter
-//                 warp_id % 4, which is why roles are quad-aligned).  Each lane gathers its 16 levels x 8 corners from the
-//                 table and writes the 32 encoded features (16 packed columns) and the 16 SH values (8 columns) of its
-//                 sample STRAIGHT INTO TENSOR MEMORY with tcgen05.st — the layer-1 / layer-3 A operands never exist in
-//                 shared memory.  Two A1 slots and one SH slot per quad, full/empty mbarriers.
-//   warps 16..19  MLP warpgroup: thread r <-> row r of the tile <-> TMEM lane r.  Its first thread issues the
-//                 tcgen05.mma chain (A from TMEM, B = weight images in shared memory through UMMA descriptors, fp32
-//                 accumulators in TMEM) and commits to an mbarrier; all 128 threads then read their accumulator row
-//                 back with tcgen05.ld (LDTM), apply ReLU / exp / sigmoid in fp32 and write the next layer's A row back
-//                 to TMEM (tcgen05.st): no LDS / STS at all in the steady state, no CTA-wide barrier — a 128-thread named
-//                 barrier orders the warpgroup's TMEM writes before its leader issues the next layer.
+//   GATHER quads: a quad owns one 128-sample tile at a time; lane = sample, warp w of the quad = rows 32w..32w+31 = TMEM
+//                 lanes 32w..  (a warp can only touch the TMEM lane quarter warp_id % 4, which is why roles are
+//                 quad-aligned).  Each lane gathers its 16 levels x 8 corners from the table and writes the 32 encoded
+//                 features (16 packed columns) and the 16 SH values (8 columns) of its sample STRAIGHT INTO TENSOR MEMORY
+//                 with tcgen05.st — the layer-1 / layer-3 A operands never exist in shared memory.  Two A1 slots and one
+//                 SH slot per quad, full/empty mbarriers.
+//   MLP warpgroup: thread r <-> row r of the tile <-> TMEM lane r.  Its first thread issues the tcgen05.mma chain (A from
+//                 TMEM, B = weight images in shared memory through UMMA descriptors, fp32 accumulators in TMEM) and
+//                 commits to an mbarrier; all 128 threads then read their accumulator row back with tcgen05.ld (LDTM),
+//                 apply ReLU / exp / sigmoid in fp32 and write the next layer's A row back to TMEM (tcgen05.st): no LDS /
+//                 STS at all in the steady state, no CTA-wide barrier — a 128-thread named barrier orders the warpgroup's
+//                 TMEM writes before its leader issues the next layer.  With G > 1 the warpgroups take alternate tiles.
 //
 // Why: the mma.sync kernel (field.cu) is bound by the L1TEX data pipe (67 % busy, profiles/r1h): 204 K wavefronts per SM
 // of table gathers plus 93 K wavefronts of shared-memory fragment loads / tile stores for the MLPs, issued from the same
 // warps that gather.  Here the tensor core reads A from TMEM and only the 20 KB weight image from shared memory, the
 // gather warps never run MLP code, and the 20 KB of shared memory per CTA leave ~200 KB of the SM's array as L1.
 //
-// TMEM columns per CTA (32-bit cells, lane = tile row):
+// TMEM columns per CTA (32-bit cells, lane = tile row); per MLP warpgroup 96 columns:
 //   [  0, 64)  R   D1 -> (in place) A2 hi|lo interleaved per 16-wide k-chunk -> D3 -> D4 -> D5 (rgb logits, 16 cols)
 //   [ 64, 96)  X   D2 (density logit + 15 geo features) in [80,96) -> [1, feat] chunk of A3 in [64,72) -> A4 -> A5
 //                  (packed fp16 pairs, 32 cols = K 64)
-//   [ 96,256)  4 quads x 40 cols: A1 slot 0 | A1 slot 1 (16 cols each = 32 encoded features) | SH (8 cols = 16 values)
+// then per gather quad 40 columns: A1 slot 0 | A1 slot 1 (16 cols each = 32 encoded features) | SH (8 cols = 16 values)
 //
 // Numerics are those of field.cu: fp16 operands, fp32 accumulation, hi+lo split of the hidden activations for the
-// density logit; the encoding is bit-identical (same encode_point).
+// density logit (here hi = the activation truncated to fp16's mantissa, lo = the exact remainder); the
+// encoding is bit-identical (same encode_point).
 #include "field_common.cuh"
 
 namespace qf {
@@ -142,40 +144,68 @@ struct FieldTcArgs {
 };
 
 // ---- roles and resources
-constexpr int kGatherWarps = 16, kQuads = kGatherWarps / 4, kSlots = 2;
-constexpr int kMlpWarp0 = kGatherWarps;                 // warps 16..19 (16 % 4 == 0: TMEM lane quarters line up)
-constexpr int kTcThreads = (kGatherWarps + 4) * 32;     // 640
-constexpr int kColR = 0, kColX = 64, kColS = 80, kColSlot0 = 96, kQuadCols = 40, kTmemCols = 256;
-static_assert(kColSlot0 + kQuads * kQuadCols <= kTmemCols, "TMEM column budget");
-// shared memory map (bytes)
-constexpr int kSmW = 0;                                            // weights, 20480
-constexpr int kSmFull = kSmW + kTcWBytes;                          // full[quad][slot]  mbarriers (count 4: one per gather warp)
-constexpr int kSmEmpty = kSmFull + kQuads * kSlots * 8;            // empty[quad] mbarriers (count 1: tcgen05.commit of layer 3)
-constexpr int kSmMma = kSmEmpty + kQuads * 8;                      // MLP chain mbarrier
-constexpr int kSmTmem = kSmMma + 8;                                // TMEM base address
-constexpr int kSmSel = kSmTmem + 8;                                // selector ballots [quad][slot][4 warps]
-constexpr int kTcSmemBytes = kSmSel + kQuads * kSlots * 4 * 4;
+// Q gather quads (4 warps each) + G MLP warpgroups per CTA, CPS CTAs per SM.  TMEM: G x 96 pipeline columns, then Q x 40.
+#ifndef QF_TC_PIPELINED
+#define QF_TC_PIPELINED 0
+#endif
+#ifndef QF_TC_DEBUG
+#define QF_TC_DEBUG 0
+#endif
+#ifndef QF_TC_QUADS
+#define QF_TC_QUADS 3
+#endif
+#ifndef QF_TC_GROUPS
+#define QF_TC_GROUPS 1
+#endif
+#ifndef QF_TC_CTAS_PER_SM
+#define QF_TC_CTAS_PER_SM 2
+#endif
+template <int Q, int G, int CPS>
+struct TcCfg {
+  static constexpr int kGatherWarps = 4 * Q, kThreads = (4 * Q + 4 * G) * 32;
+  static constexpr int kPipeCols = 96, kQuadCols = 40, kColSlot0 = G * kPipeCols;
+  static constexpr int kColsNeeded = kColSlot0 + Q * kQuadCols;
+  static constexpr int kTmemCols = kColsNeeded <= 128 ? 128 : (kColsNeeded <= 256 ? 256 : 512);
+  // shared memory map (bytes)
+  static constexpr int kSmW = 0;                                   // weights, 20480
+  static constexpr int kSmFull = kSmW + kTcWBytes;                 // full[quad][slot] mbarriers (count 4: one per gather warp)
+  static constexpr int kSmEmpty = kSmFull + Q * 2 * 8;             // empty[quad] mbarriers (count 1: tcgen05.commit of layer 3)
+  static constexpr int kSmMma = kSmEmpty + Q * 8;                  // one MLP chain mbarrier per warpgroup
+  static constexpr int kSmTmem = kSmMma + G * 8;                   // TMEM base address
+  static constexpr int kSmSel = kSmTmem + 8;                       // selector ballots [quad][slot][4 warps]
+  static constexpr int kSmemBytes = kSmSel + Q * 2 * 4 * 4;
+  static_assert(kColsNeeded <= 512 && kTmemCols * CPS <= 512, "TMEM column budget");
+  static_assert(kThreads <= 1024 && kThreads * CPS <= 2048, "thread budget");
+};
+// pipeline-relative TMEM columns
+constexpr int kColR = 0, kColX = 64, kColS = 80;
 
-__device__ __forceinline__ uint32_t a1_col(int quad, int slot) { return kColSlot0 + quad * kQuadCols + slot * 16; }
-__device__ __forceinline__ uint32_t sh_col(int quad) { return kColSlot0 + quad * kQuadCols + 32; }
+// two floats -> packed halves with ReLU folded into the conversion (lo -> low half)
+__device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 
-__global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const FieldTcArgs a) {
+template <int Q, int G, int CPS>
+__global__ void __launch_bounds__(TcCfg<Q, G, CPS>::kThreads, CPS) ngp_forward_tc_kernel(const FieldTcArgs a) {
+  using Cfg = TcCfg<Q, G, CPS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmTmem);
-  uint32_t* s_sel = reinterpret_cast<uint32_t*>(smem + kSmSel);
-  const uint32_t bar_full = smem_u32(smem + kSmFull), bar_empty = smem_u32(smem + kSmEmpty), bar_mma = smem_u32(smem + kSmMma);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Cfg::kSmTmem);
+  uint32_t* s_sel = reinterpret_cast<uint32_t*>(smem + Cfg::kSmSel);
+  const uint32_t bar_full = smem_u32(smem + Cfg::kSmFull), bar_empty = smem_u32(smem + Cfg::kSmEmpty);
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.weights_tc);
-    uint4* dst = reinterpret_cast<uint4*>(smem + kSmW);
-    for (int i = tid; i < kTcWBytes / 16; i += kTcThreads) dst[i] = __ldg(src + i);
+    uint4* dst = reinterpret_cast<uint4*>(smem + Cfg::kSmW);
+    for (int i = tid; i < kTcWBytes / 16; i += Cfg::kThreads) dst[i] = __ldg(src + i);
   }
-  if (tid < kQuads * kSlots) mbar_init(bar_full + tid * 8, 4);
-  if (tid < kQuads) mbar_init(bar_empty + tid * 8, 1);
-  if (tid == 0) mbar_init(bar_mma, 1);
+  if (tid < Q * 2) mbar_init(bar_full + tid * 8, 4);
+  if (tid < Q) mbar_init(bar_empty + tid * 8, 1);
+  if (tid < G) mbar_init(smem_u32(smem + Cfg::kSmMma) + tid * 8, 1);
   asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" :: "r"(smem_u32(tmem_slot)), "n"(Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   fence_async_smem();          // weights written through the generic proxy, read by the tensor core
@@ -185,17 +215,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
   const uint32_t tmem_base = *tmem_slot;
   const int64_t M = a.d_M ? (int64_t)__ldg(a.d_M) : a.M;
   const int64_t n_tiles = (M + 127) >> 7;
-  // the CTA's n-th tile is tile (blockIdx.x + n * gridDim.x); quad (n % kQuads) gathers it into slot ((n / kQuads) % kSlots)
+  // the CTA's n-th tile is tile (blockIdx.x + n * gridDim.x); quad (n % Q) gathers it — its k-th tile, k = n / Q, into A1
+  // slot (k % 2) — and MLP warpgroup (n % G) consumes it
   const uint32_t lane_bits = (uint32_t)((warp & 3) * 32) << 16;
+  auto a1_col = [](int quad, int slot) { return (uint32_t)(Cfg::kColSlot0 + quad * Cfg::kQuadCols + slot * 16); };
+  auto sh_col = [](int quad) { return (uint32_t)(Cfg::kColSlot0 + quad * Cfg::kQuadCols + 32); };
 
-  if (warp < kGatherWarps) {
+  if (warp < Cfg::kGatherWarps) {
     // ===================== GATHER =====================
     const int quad = warp >> 2, sub = warp & 3;
     const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
     const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
     int k = 0;   // this quad's k-th tile
-    for (int64_t tile = blockIdx.x + (int64_t)quad * gridDim.x; tile < n_tiles; tile += (int64_t)kQuads * gridDim.x, ++k) {
-      const int slot = k & 1, idx = quad * kSlots + slot;
+    for (int64_t tile = blockIdx.x + (int64_t)quad * gridDim.x; tile < n_tiles; tile += (int64_t)Q * gridDim.x, ++k) {
+      const int slot = k & 1, idx = quad * 2 + slot;
       // A1 slot `slot` was last read by layer 1 of this quad's tile k-2: complete, because before writing tile k-1's SH
       // this warp waited for layer 3 of tile k-2 (below)
       const uint32_t t_a1 = tmem_base + lane_bits + a1_col(quad, slot);
@@ -219,7 +252,19 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
         dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
         dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
       }
-      // 16 levels, two per trip: the pair's 16 gathers are in flight together; each trip writes 2 TMEM columns of the row
+      // 16 levels in pairs, software-pipelined: the next level's 8 gathers are issued before this one is blended; each
+      // pair writes 2 TMEM columns of the row
+#if QF_TC_DEBUG == 2   // timing experiment: no table gathers (MLP side alone)
+#pragma unroll 1
+      for (int l = 0; l < 16; l += 2) tmem_st2(t_a1 + l, __float_as_uint(x) + l, __float_as_uint(y));
+#elif QF_TC_DEBUG == 4   // timing experiment: DEBUG 3 without the TMEM stores
+      uint32_t dbg_acc = 0;
+      encode_point_pipelined(a.desc, a.table, x, y, z, [&](int l, uint32_t even, uint32_t odd) { dbg_acc += even ^ odd; });
+      if (a.out4 && valid) reinterpret_cast<uint32_t*>(a.out4)[4 * i] = dbg_acc;
+#else
+#if QF_TC_PIPELINED
+      encode_point_pipelined(a.desc, a.table, x, y, z, [&](int l, uint32_t even, uint32_t odd) { tmem_st2(t_a1 + l, even, odd); });
+#else
       {
         uint32_t even = 0;
         encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) {
@@ -227,17 +272,25 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
           else even = h2;
         });
       }
+#endif
+#endif
       {
         float sh[16];
         sh4(dx, dy, dz, sh);
         uint32_t shp[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) shp[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
+#if QF_TC_DEBUG < 3   // 3: timing experiment, gather warps alone with no hand-over at all
         if (k > 0) {
           mbar_wait(bar_empty + quad * 8, (k - 1) & 1);     // layer 3 of this quad's previous tile has read the SH columns
           tc_fence_after();
         }
+#endif
+#if QF_TC_DEBUG == 4
+        if (a.out4 && valid) reinterpret_cast<uint32_t*>(a.out4)[4 * i + 1] = shp[0] ^ shp[1] ^ shp[2] ^ shp[3] ^ shp[4] ^ shp[5] ^ shp[6] ^ shp[7];
+#else
         tmem_st8(tmem_base + lane_bits + sh_col(quad), shp);
+#endif
       }
       const unsigned selmask = __ballot_sync(0xffffffffu, sel);
       if (lane == 0) s_sel[idx * 4 + sub] = selmask;
@@ -247,43 +300,59 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       if (lane == 0) mbar_arrive(bar_full + idx * 8);
     }
   } else {
-    // ===================== MLP warpgroup =====================
-    const int row = tid - kMlpWarp0 * 32;                          // 0..127 = TMEM lane
+    // ===================== MLP warpgroups =====================
+    const int group = (warp - Cfg::kGatherWarps) >> 2;
+    const int row = (tid - Cfg::kGatherWarps * 32) & 127;          // 0..127 = TMEM lane
     const bool leader = row == 0;
-    const uint32_t t_row = tmem_base + lane_bits;                  // this warp's lane quarter, column 0
-    const uint32_t sW = smem_u32(smem + kSmW);
+    const uint32_t pipe = tmem_base + group * Cfg::kPipeCols;      // this warpgroup's R | X columns
+    const uint32_t t_row = pipe + lane_bits;                       // this warp's lane quarter
+    const uint32_t bar_mma = smem_u32(smem + Cfg::kSmMma) + group * 8;
+    const int bar_id = 1 + group;
+    const uint32_t sW = smem_u32(smem + Cfg::kSmW);
     const uint32_t id64 = umma_idesc(128, 64), id16 = umma_idesc(128, 16);
     // B descriptors: chunk j (16 k-values = two 8x8 core matrices) of a (N x K) K-major canonical image
     auto bdesc = [&](int w_off, int K, int j) { return umma_desc(sW + w_off + j * 256, 128, (K >> 3) * 128); };
     uint32_t phase = 0;
-    int n = 0;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++n) {
-      const int quad = n % kQuads, kq = n / kQuads, slot = kq & 1, idx = quad * kSlots + slot;
+#if QF_TC_DEBUG >= 3
+    if (a.out4 && blockIdx.x == 0 && row == 0) a.out4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t n = group; false; n += G) {
+#else
+    for (int64_t n = group; ; n += G) {
+#endif
+      const int64_t tile = blockIdx.x + n * gridDim.x;
+      if (tile >= n_tiles) break;
+      const int quad = (int)(n % Q), kq = (int)(n / Q), slot = kq & 1, idx = quad * 2 + slot;
       mbar_wait(bar_full + idx * 8, (kq >> 1) & 1);
       tc_fence_after();
       const bool sel = (s_sel[idx * 4 + (row >> 5)] >> (row & 31)) & 1u;
       const uint32_t c_a1 = tmem_base + a1_col(quad, slot), c_sh = tmem_base + sh_col(quad);
+#if QF_TC_DEBUG == 1   // timing experiment: no MLP (gather side alone): free the slot at once
+      if (leader) { umma_f16_ts(pipe + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u); umma_commit(bar_empty + quad * 8); }
+      { const int64_t i = tile * 128 + row; if (i < M && a.out4) a.out4[i] = make_float4(0.f, 0.f, 0.f, sel ? 1.f : 0.f); }
+      continue;
+#endif
       // ---- base L1: R = A1 (K=32) * W1^T
       if (leader) {
-        umma_f16_ts(tmem_base + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u);
-        umma_f16_ts(tmem_base + kColR, c_a1 + 8, bdesc(kTcW1, 32, 1), id64, 1u);
+        umma_f16_ts(pipe + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u);
+        umma_f16_ts(pipe + kColR, c_a1 + 8, bdesc(kTcW1, 32, 1), id64, 1u);
         umma_commit(bar_mma);
       }
       mbar_wait(bar_mma, phase); phase ^= 1;
       tc_fence_after();
       {
+        // 64 hidden units: ReLU and hi | lo split, written in place over the 16 accumulator columns of each k-chunk.
+        // hi = the value truncated to fp16's 10 mantissa bits (exactly representable), lo = the exact remainder (same sign
+        // as the value), both converted with ReLU folded in: no max, no unpack.
         float v[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {   // 64 hidden units: ReLU, hi | lo written in place over the 16 accumulator columns
+        for (int q = 0; q < 4; ++q) {
           tmem_ld16(t_row + kColR + q * 16, v);
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float r0 = fmaxf(v[2 * e], 0.f), r1 = fmaxf(v[2 * e + 1], 0.f);
-            __half2 h = __floats2half2_rn(r0, r1);
-            float2 f = __half22float2(h);
-            hi[e] = *reinterpret_cast<uint32_t*>(&h);
-            lo[e] = pack_h2(r0 - f.x, r1 - f.y);
+            const float t0 = __uint_as_float(__float_as_uint(v[2 * e]) & 0xFFFFE000u), t1 = __uint_as_float(__float_as_uint(v[2 * e + 1]) & 0xFFFFE000u);
+            hi[e] = pack_relu_h2(t0, t1);
+            lo[e] = pack_relu_h2(v[2 * e] - t0, v[2 * e + 1] - t1);
           }
           tmem_st8(t_row + kColR + q * 16, hi);
           tmem_st8(t_row + kColR + q * 16 + 8, lo);
@@ -291,14 +360,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       }
       tmem_wait_st();
       tc_fence_before();
-      named_bar(1, 128);
+      named_bar(bar_id, 128);
       // ---- base L2: S = A2lo * W2^T + A2hi * W2^T  (K = 64 each)
       if (leader) {
         tc_fence_after();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColR + j * 16 + 8, bdesc(kTcW2, 64, j), id16, j > 0 ? 1u : 0u);
+        for (int j = 0; j < 4; ++j) umma_f16_ts(pipe + kColS, pipe + kColR + j * 16 + 8, bdesc(kTcW2, 64, j), id16, j > 0 ? 1u : 0u);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColS, tmem_base + kColR + j * 16, bdesc(kTcW2, 64, j), id16, 1u);
+        for (int j = 0; j < 4; ++j) umma_f16_ts(pipe + kColS, pipe + kColR + j * 16, bdesc(kTcW2, 64, j), id16, 1u);
         umma_commit(bar_mma);
       }
       mbar_wait(bar_mma, phase); phase ^= 1;
@@ -315,12 +384,12 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       }
       tmem_wait_st();
       tc_fence_before();
-      named_bar(1, 128);
-      // ---- head L1: R = [SH | 1, feat] (K=32) * W3p^T ; its completion also frees the gather slot
+      named_bar(bar_id, 128);
+      // ---- head L1: R = [SH | 1, feat] (K=32) * W3p^T ; its completion also frees the quad's SH columns
       if (leader) {
         tc_fence_after();
-        umma_f16_ts(tmem_base + kColR, c_sh, bdesc(kTcW3, 32, 0), id64, 0u);
-        umma_f16_ts(tmem_base + kColR, tmem_base + kColX, bdesc(kTcW3, 32, 1), id64, 1u);
+        umma_f16_ts(pipe + kColR, c_sh, bdesc(kTcW3, 32, 0), id64, 0u);
+        umma_f16_ts(pipe + kColR, pipe + kColX, bdesc(kTcW3, 32, 1), id64, 1u);
         umma_commit(bar_empty + quad * 8);
         umma_commit(bar_mma);
       }
@@ -335,20 +404,20 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
           tmem_ld16(t_row + kColR + q * 16, v);
           uint32_t h[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) h[e] = pack_h2(fmaxf(v[2 * e], 0.f), fmaxf(v[2 * e + 1], 0.f));
+          for (int e = 0; e < 8; ++e) h[e] = pack_relu_h2(v[2 * e], v[2 * e + 1]);
           tmem_st8(t_row + kColX + q * 8, h);
         }
         tmem_wait_st();
         tc_fence_before();
-        named_bar(1, 128);
+        named_bar(bar_id, 128);
         if (leader) {
           tc_fence_after();
           if (stage == 0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColR, tmem_base + kColX + j * 8, bdesc(kTcW4, 64, j), id64, j > 0 ? 1u : 0u);   // head L2
+            for (int j = 0; j < 4; ++j) umma_f16_ts(pipe + kColR, pipe + kColX + j * 8, bdesc(kTcW4, 64, j), id64, j > 0 ? 1u : 0u);   // head L2
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) umma_f16_ts(tmem_base + kColR, tmem_base + kColX + j * 8, bdesc(kTcW5, 64, j), id16, j > 0 ? 1u : 0u);   // head L3 -> R[0,16)
+            for (int j = 0; j < 4; ++j) umma_f16_ts(pipe + kColR, pipe + kColX + j * 8, bdesc(kTcW5, 64, j), id16, j > 0 ? 1u : 0u);   // head L3 -> R[0,16)
           }
           umma_commit(bar_mma);
         }
@@ -368,22 +437,24 @@ __global__ void __launch_bounds__(kTcThreads, 2) ngp_forward_tc_kernel(const Fie
       }
       // the next tile's L1 overwrites R, which every thread of the warpgroup must have finished reading
       tc_fence_before();
-      named_bar(1, 128);
+      named_bar(bar_id, 128);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "r"(kTmemCols) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(tmem_base), "n"(Cfg::kTmemCols) : "memory");
 }
 
 int launch_ngp_forward_tc(const qf_ngp* f, FieldTcArgs& a, cudaStream_t st) {
+  using Cfg = TcCfg<QF_TC_QUADS, QF_TC_GROUPS, QF_TC_CTAS_PER_SM>;
   a.desc = f->desc;
   a.table = f->d_table;
   a.weights_tc = f->d_weights_tc;
-  int64_t tiles = a.d_M ? (int64_t)kNumSMs * 2 : ceil_div(a.M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 2 ? tiles : (int64_t)kNumSMs * 2);
+  constexpr int max_blocks = kNumSMs * QF_TC_CTAS_PER_SM;
+  int64_t tiles = a.d_M ? (int64_t)max_blocks : ceil_div(a.M, 128);
+  int blocks = (int)(tiles < max_blocks ? tiles : max_blocks);
   if (blocks < 1) blocks = 1;
-  ngp_forward_tc_kernel<<<blocks, kTcThreads, kTcSmemBytes, st>>>(a);
+  ngp_forward_tc_kernel<QF_TC_QUADS, QF_TC_GROUPS, QF_TC_CTAS_PER_SM><<<blocks, Cfg::kThreads, Cfg::kSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

@@ -195,7 +195,8 @@ def test_ngp_forward_matches_oracle(dev, smoke_scene):
     # query_density surface
     dens2, feat = sc.radiance_field.query_density(x.to(dev), return_feat=True)
     dref, fref = O.ngp_query_density(x, p)
-    assert maxabs(dens2, dens) == 0.0 and maxabs(feat, fref) <= 1e-3
+    # query_density runs the mma.sync kernel, forward the tcgen05 one: the same arithmetic up to the hi+lo split's last bit
+    assert float(((dens2 - dens).abs() / dens.clamp_min(1e-3)).max()) <= 2e-4 and maxabs(feat, fref) <= 1e-3
     assert sc.radiance_field.query_density(x[:7].to(dev)).shape == (7, 1)
     # ragged sizes around the 32-sample warp tile and the in-kernel direction gather
     for n in (1, 15, 16, 17, 31, 33, 129):
