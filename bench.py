@@ -48,6 +48,7 @@ def parse():
                     "(800 = every ray of a c2 frame, 3-6 s on 8-16 host cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the fwd+bwd training-step measurement (extra key 'train')")
+    ap.add_argument("--no-big", action="store_true", help="skip the ray-sharded configs[3] / configs[4] legs (extra keys 'c4', 'c5')")
     ap.add_argument("--train-rays", type=int, default=1 << 18, help="rays per training batch per GPU (BASELINE configs[2])")
     return ap.parse_args()
 
@@ -144,13 +145,19 @@ def run_reference(args):
     # variable is read when the OpenMP runtimes start, i.e. before torch is imported below, and also seeds worker threads)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ["MKL_NUM_THREADS"] = str(threads)
-    sample = 256
-    rps, detail, sec = cpu_render_sample(sample, threads, args.config, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
-    desc = (f"{sample}x{sample} sub-grid of one {args.config} frame per step; intersect {detail.get('intersect_s', 0):.2f}s "
+    # every step renders EVERY ray of one frame of the workload the line names (800x800 for c2: 1.4-6 s per step on 8-16 host
+    # cores); steps / warm-up are capped so that the whole arm stays within a few minutes
+    import quadraturefields_b200.scene as S_
+    sample = max(S_.CONFIGS[args.config]["W"], S_.CONFIGS[args.config]["H"]) if args.config in ("c1", "c2") else 256
+    requested = args.steps
+    _, _, probe = cpu_render_sample(sample, threads, args.config, steps=1, warmup=0)           # also the (single) warm-up step
+    args.steps = max(1, min(args.steps, int(200.0 / max(probe, 1e-3))))                        # the whole arm stays under ~4 minutes
+    rps, detail, sec = cpu_render_sample(sample, threads, args.config, steps=args.steps, warmup=0)
+    desc = (f"{sample}x{sample} rays (the whole frame) of one {args.config} frame per step; intersect {detail.get('intersect_s', 0):.2f}s "
             f"(OpenMP CPU BVH traversal), field {detail.get('field_s', 0):.2f}s, composite {detail.get('composite_s', 0):.3f}s; "
             f"{detail.get('hits', 0)} hits")
     line = {"impl": "reference", "metric": METRIC, "value": rps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "steps_requested": requested, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.config), "note": "reference path is CUDA-only with un-installable native "
                        "dependencies; timed here as its CPU port in oracle/ (OpenMP C BVH intersector + PyTorch field and compositing)"},
@@ -306,11 +313,51 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = N * world * args.steps / (float(ms_e.item()) * 1e-3)
+    # ---- e2e, the reference's real eval input: a 48-byte camera pose on the HOST per frame (its loader builds the rays on
+    # the device, nerf_synthetic.py:289-378), image (rgb + depth, what the eval loop takes back, train_finetune.py:620-626)
+    # device->host into pinned memory every step.  Two compute streams so the D2H of frame i overlaps frame i+1.
+    pose_host = [dict(rgb=torch.empty((N, 3)).pin_memory(), depth=torch.empty((N, 1)).pin_memory()) for _ in range(NB)]
+    from quadraturefields_b200.utils import MeshRenderer
+    pose_renderers = [MeshRenderer(sc.mesh_intersect, radiance_field=sc.radiance_field) for _ in range(NB)]   # private ray scratch per slot
+
+    def run_e2e_pose(n_steps, first):
+        for j in range(n_steps):
+            i, b = first + j, j % NB
+            s_cmp = s_cmps[b]
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_out[b])               # previous D2H from this slot finished
+                pose_renderers[b].render_pose(sc.poses[view_of(i) % len(sc.poses)], sc.W, sc.H, sc.focal, sc.cx, sc.cy, out=d_out[b])
+                ev_cmp[b].record(s_cmp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_cmp[b])
+                for k in ("rgb", "depth"):
+                    pose_host[b][k].copy_(d_out[b][k], non_blocking=True)
+                ev_out[b].record(s_d2h)
+        for st in (s_d2h, *s_cmps):
+            torch.cuda.current_stream(dev).wait_stream(st)
+
+    run_e2e_pose(max(args.warmup, 3), 0)
+    barrier()
+    ev0.record()
+    run_e2e_pose(args.steps, args.warmup)
+    ev1.record()
+    barrier()
+    ms_p = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_p, op=dist.ReduceOp.MAX)
+    e2e_pose_value = N * world * args.steps / (float(ms_p.item()) * 1e-3)
+    del pose_renderers
     train = None if args.no_train else run_train_steps(args, sc, dev, rank, world, barrier)
     field_train = None if args.no_train else run_field_train_steps(args, sc, dev, rank, world, barrier)
     field_train_occ = None if args.no_train else run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier)
     up2 = run_upsample2_frames(args, sc, dev) if args.config == "c2" else None
     clk = clocks.stop() if clocks else None
+    dense = run_dense_c2(args, dev) if (args.config == "c2" and world == 1 and not args.no_big) else None
+    # free the c2 scene's resident ray sets (3 GB) before the large configs are built
+    del rays, host_rays, pipe, outs, d_in, d_out, host_out
+    torch.cuda.empty_cache()
+    c4 = None if args.no_big else run_sharded_frame_leg("c4", args, dev, rank, world, barrier, baked=False)
+    c5 = None if args.no_big else run_sharded_frame_leg("c5", args, dev, rank, world, barrier, baked=True)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -325,7 +372,7 @@ def run_ours(args):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = next((v for k, v in tj["dram_bytes_per_launch"].items() if k.startswith("ngp_forward_kernel<0")), None)
+            traffic = next((v for k, v in tj["dram_bytes_per_launch"].items() if k.startswith("ngp_forward")), None)
         except Exception:
             pass
         line = {
@@ -337,14 +384,19 @@ def run_ours(args):
                        "l2_policy": f"inputs larger than L2: {n_views} resident ray sets ({n_views * N * 24 / 1e9:.2f} GB) cycled; "
                                     "25 MB table + 2.6 MB BVH are L2-resident by design", "parallelism": f"frames over {world} GPU(s)"},
             "ms_per_frame_800x800": ms_total / args.steps if args.config == "c2" else None,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 24, "d2h_bytes_per_step": N * 20},
+            # headline e2e = the reference's real per-frame input (a host pose; rays are generated on the device as its loader
+            # does); the rays-from-host flavour of round 1 stays as `e2e_rays_from_host`
+            "e2e": {"value": e2e_pose_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": N * 16,
+                    "input": "3x4 camera-to-world pose in host memory (48 B, passed as kernel arguments of the ray generator)",
+                    "output": "rgb (N,3) + depth (N,1) copied device->pinned host every step"},
+            "e2e_rays_from_host": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 24, "d2h_bytes_per_step": N * 20},
             "gpu_launches": 3 * args.steps,
             "stage_ms_per_step": {"trace": ms3[0] / max(nch.value, 1), "shade": shade_ms, "composite": ms3[2] / max(nch.value, 1),
                                   "note": "each kernel timed alone (single stream)"},
             "stage_ms_per_step_in_timed_region": {"trace": ms3o[0] / max(ncho.value, 1), "shade": shade_ms_overlapped,
                                                   "composite": ms3o[2] / max(ncho.value, 1),
                                                   "note": "frames rotate over the pipeline streams, so kernels of neighbouring frames overlap"},
-            "roofline": {"bound": "hbm", "kernel": "ngp_forward_kernel<0, 10> (hash-grid gather + fused MLPs)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": "ngp_forward_tc_kernel (hash-grid gather + tcgen05 MLPs)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "algorithmic_bytes_per_hit": 512, "hits_per_launch": hits_per_launch, "peak_source": peak_src,
                          "achieved_in_timed_region": (512.0 * hits_per_launch / (shade_ms_overlapped * 1e-3) / 1e9) if shade_ms_overlapped > 0 else 0.0,
@@ -352,8 +404,15 @@ def run_ours(args):
                                  "next frame's trace kernel); the table is L2-resident, so 'achieved' is an HBM-equivalent gather rate"},
             "clocks": clk,
         }
+        line["samples_per_sec"] = total_hits.item() / (ms_total * 1e-3)
         if up2 is not None:
             line["frame_800x800_up_sample2"] = up2
+        if dense is not None:
+            line["c2_dense"] = dense
+        if c4 is not None:
+            line["c4"] = c4
+        if c5 is not None:
+            line["c5"] = c5
         if train is not None:
             line["train"] = train
             line["field_train"] = field_train
@@ -369,6 +428,137 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
+    """BASELINE configs[3] (`c4`: Shelly-shaped 1080p, 1.15 M triangles, K=32, T=2^21, neural field) and configs[4] (`c5`:
+    baked spherical-Gaussian textures, 4K): ONE frame per step, its rays sharded over the ranks in 4-row bands
+    (`parallel.shard_rays`; the reference renders such frames in 160 000-ray splits on one GPU, train_finetune.py:590-617,
+    test_baking_texture_images.py:355-371), every rank renders its band from the HOST pose (`render_pose`), and the
+    (rgb, opacity, depth) bands are gathered to rank 0 with one NCCL gather per frame INSIDE the timed region.  Strong
+    scaling: the frame is fixed, N grows.  Never fails the main line."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from quadraturefields_b200 import _lib, parallel as P, scene as S
+    try:
+        lib = _lib.load()
+        sc = S.make_scene(name, device=dev, build_field=not baked)
+        renderer = sc.baked_renderer if baked else sc.renderer
+        N, W, H = sc.n_rays, sc.W, sc.H
+        lo, hi = P.shard_rays(N, rank, world, W)
+        sizes = [b - a for a, b in (P.shard_rays(N, r, world, W) for r in range(world))]
+        rows = (lo // W, hi // W)
+        n = hi - lo
+        out = dict(rgb=torch.empty((n, 3), device=dev), opacity=torch.empty((n, 1), device=dev), depth=torch.empty((n, 1), device=dev))
+        band = torch.empty((n, 5), device=dev)
+        frame = torch.empty((N, 5), device=dev) if rank == 0 else None
+        recv = ([torch.empty((sz, 5), device=dev) for sz in sizes] if rank == 0 else None) if world > 1 else None
+        if world > 1 and len(set(sizes)) != 1:
+            recv = None                                   # ragged bands: the padding path of parallel.gather_frame
+        hits = torch.zeros((1,), dtype=torch.int32, device=dev)
+        steps, warm = max(3, min(args.steps, 10)), 3
+        hit_slots = torch.zeros((warm + steps, 1), dtype=torch.int32, device=dev)
+
+        def step(i):
+            renderer.render_pose(sc.poses[i % len(sc.poses)], W, H, sc.focal, sc.cx, sc.cy, out=out, hits_out=hit_slots[i], rows=rows)
+            if world > 1:
+                torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1, out=band)
+                if recv is not None or rank != 0:
+                    if len(set(sizes)) == 1:
+                        dist.gather(band, recv, dst=0)
+                    else:
+                        P.gather_frame(band, sizes, dst=0)
+                else:
+                    P.gather_frame(band, sizes, dst=0)
+
+        for i in range(warm):
+            step(i)
+        barrier()
+        lib.qf_profile_enable(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            step(warm + i)
+        e1.record()
+        barrier()
+        ms3 = (C.c_double * 3)()
+        nch = C.c_int64()
+        _lib.check(lib.qf_profile_read(ms3, C.byref(nch)), "qf_profile_read")
+        lib.qf_profile_enable(0)
+        ms = P.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+        h = hit_slots[warm:].to(torch.int64).sum().reshape(1)
+        if world > 1:
+            dist.all_reduce(h)
+        hits_per_frame = float(h.item()) / steps
+        st = [ms3[k] / steps for k in range(3)]            # this rank's band: trace / shade / composite ms per frame
+        peak, peak_src = _hbm_peak()
+        L = sc.cfg.get("lobes", 0)
+        bytes_per_hit = (4 + 6 * L + 36) if baked else 512
+        rank_hits = float(hit_slots[warm:].to(torch.int64).sum().item()) / steps
+        shade_gbs = bytes_per_hit * rank_hits / (st[1] * 1e-3) / 1e9 if st[1] > 0 else 0.0
+        res = {"config": workload_name(name), "n_gpus": world, "scaling": "strong (one frame, ray bands over the ranks)",
+               "ms_per_frame": ms, "rays_per_frame": N, "rays_per_sec": N / (ms * 1e-3), "hits_per_ray": hits_per_frame / N,
+               "samples_per_sec": hits_per_frame / (ms * 1e-3), "steps": steps, "triangles": int(sc.faces_np.shape[0]), "K": sc.K,
+               "bvh_bytes": int(sc.mesh_intersect.rayintersector.info()["device_bytes"]),
+               "gather_bytes_per_frame": (N - sizes[0]) * 20 if world > 1 else 0,
+               "rank0_stage_ms_per_frame": {"trace": st[0], "shade": st[1], "composite": st[2]},
+               "roofline_shade": {"bound": "hbm", "kernel": "baked_shade_kernel" if baked else "ngp_forward_tc_kernel",
+                                  "algorithmic_bytes_per_hit": bytes_per_hit, "achieved": shade_gbs, "peak": peak, "unit": "GB/s",
+                                  "frac": shade_gbs / peak, "peak_source": peak_src},
+               "includes": "pose on the host -> ray generation -> BVH first-K trace -> shade -> composite on every rank's band"
+                           + (" -> NCCL gather of the bands to rank 0" if world > 1 else "")}
+        del sc, renderer
+        torch.cuda.empty_cache()
+        return res
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def run_dense_c2(args, dev):
+    """configs[1] with the camera at radius 2.2 instead of 4.03: every ray crosses the shells (h ~ 6 hits / ray instead of
+    1.7), the regime SURVEY §8(d) reasons about (512 B and 18.7 kflop per hit sample).  Secondary number, N=1 only."""
+    import torch
+    from quadraturefields_b200 import scene as S
+    from quadraturefields_b200.utils import FramePipeline
+    try:
+        sc = S.make_scene("c2", device=dev, cam_radius=2.2, views=16)
+        N = sc.n_rays
+        rays = [sc.rays(v) for v in range(16)]
+        NS = 3
+        pipe = FramePipeline(sc.renderer, NS)
+        outs = [dict(rgb=torch.empty((N, 3), device=dev), opacity=torch.empty((N, 1), device=dev), depth=torch.empty((N, 1), device=dev))
+                for _ in range(NS)]
+        steps, warm = max(5, min(args.steps, 20)), 5
+        hit_slots = torch.zeros((warm + steps, 1), dtype=torch.int32, device=dev)
+
+        def run(n, first):
+            pipe.begin()
+            for j in range(n):
+                o, d = rays[(first + j) % 16]
+                pipe.submit(o, d, out=outs[j % NS], hits_out=hit_slots[first + j], image_width=sc.W)
+            pipe.join()
+
+        run(warm, 0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps, warm)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        hits = float(hit_slots[warm:].to(torch.int64).sum().item()) / steps
+        return {"ms_per_frame": ms, "rays_per_sec": N / (ms * 1e-3), "hits_per_ray": hits / N, "samples_per_sec": hits / (ms * 1e-3),
+                "steps": steps, "camera_radius": 2.2, "l2_policy": "16 resident ray sets (246 MB > L2) cycled"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def run_upsample2_frames(args, sc, dev):

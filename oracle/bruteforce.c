@@ -227,3 +227,49 @@ void qf_oracle_intersect_firstk_bvh(const float* origins, const float* dirs, int
   }
   free(nodes); free(order); free(cen); free(tv);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * C restatement of oracle/quadfield_oracle.py:hashgrid_encode (tcnn kernel_grid forward, recalled): 3-D positions in
+ * [0,1], F = 2 features per entry, trilinear interpolation accumulated in HALF precision with one fused multiply-add per
+ * corner (weight formed in fp32, cast to half).  The fused half FMA is evaluated exactly: the product of two halves and
+ * the sum with a third are exact in double for every non-pathological exponent gap, and the double -> half conversion
+ * rounds once.  table: (n_entries, 2) fp32 holding half values; out: (M, 2 L) fp32 holding half values, level-major.
+ * Pinned to the numpy/torch version by tests/test_oracle_golden.py::test_c_hashgrid_matches_numpy.
+ * ------------------------------------------------------------------------------------------------------------------- */
+void qf_oracle_hashgrid_encode(const float* x01, int64_t M, const float* table, int L, const float* scale,
+                               const uint32_t* resolution, const int64_t* offset, const int64_t* size, const uint8_t* hashed,
+                               float* out) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < M; ++i) {
+    const float x[3] = {x01[3 * i], x01[3 * i + 1], x01[3 * i + 2]};
+    for (int l = 0; l < L; ++l) {
+      uint32_t c[3];
+      float fr[3];
+      for (int d = 0; d < 3; ++d) {
+        const float pos = fmaf(scale[l], x[d], 0.5f);
+        const float fl = floorf(pos);
+        c[d] = (uint32_t)(int32_t)fl;
+        fr[d] = pos - fl;
+      }
+      const uint32_t res = resolution[l];
+      _Float16 acc0 = (_Float16)0.0f, acc1 = (_Float16)0.0f;
+      for (int k = 0; k < 8; ++k) {
+        float w = 1.0f;
+        uint32_t g[3];
+        for (int d = 0; d < 3; ++d) {
+          if ((k >> d) & 1) { w = w * fr[d]; g[d] = c[d] + 1u; }
+          else { w = w * (1.0f - fr[d]); g[d] = c[d]; }
+        }
+        uint32_t idx;
+        if (hashed[l]) idx = (g[0] * 1u) ^ (g[1] * 2654435761u) ^ (g[2] * 805459861u);
+        else idx = g[0] + g[1] * res + g[2] * (res * res);
+        const int64_t e = (int64_t)(idx % (uint64_t)size[l]) + offset[l];
+        const _Float16 wh = (_Float16)w;
+        acc0 = (_Float16)((double)wh * (double)table[2 * e] + (double)acc0);
+        acc1 = (_Float16)((double)wh * (double)table[2 * e + 1] + (double)acc1);
+      }
+      out[(size_t)i * 2 * L + 2 * l] = (float)acc0;
+      out[(size_t)i * 2 * L + 2 * l + 1] = (float)acc1;
+    }
+  }
+}

@@ -519,6 +519,9 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
     Gradients (table, positions) follow the un-rounded trilinear form, straight through the half roundings."""
     M = x01.shape[0]
     Fdim = meta.n_features
+    if (PREFER_C and Fdim == 2 and x01.shape[1] == 3 and not x01.requires_grad and not table.requires_grad
+            and _c_oracle() is not None and hasattr(_c_oracle(), "qf_oracle_hashgrid_encode")):
+        return hashgrid_encode_c(x01, table, meta)       # bench.py's CPU legs: the OpenMP C restatement, identical results
     outs = []
     xd = x01.double()
     for l in range(meta.n_levels):
@@ -551,8 +554,28 @@ def hashgrid_encode(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> t
             w16 = w.detach().numpy().astype(np.float16).astype(np.float64)
             acc16 = (w16[:, None] * tv.detach().numpy().astype(np.float64) + acc16.astype(np.float64)).astype(np.float16)
         exact = torch.from_numpy(acc16.astype(np.float32))
-        outs.append(lin + (exact - lin).detach())
+        # forward value = the half chain; under autograd the un-rounded trilinear form carries the gradient
+        outs.append(lin + (exact - lin).detach() if lin.requires_grad else exact)
     return torch.cat(outs, dim=1)
+
+
+def hashgrid_encode_c(x01: torch.Tensor, table: torch.Tensor, meta: GridMeta) -> torch.Tensor:
+    """`hashgrid_encode` through oracle/bruteforce.c (OpenMP): same arithmetic, same bits, no gradients."""
+    import ctypes as C
+    lib = _c_oracle()
+    x = np.ascontiguousarray(x01.detach().numpy(), dtype=np.float32)
+    t = np.ascontiguousarray(table.detach().numpy(), dtype=np.float32)
+    L = int(meta.n_levels)
+    scale = np.ascontiguousarray(meta.scale, dtype=np.float32)
+    res = np.ascontiguousarray(meta.resolution, dtype=np.uint32)
+    offset = np.ascontiguousarray(meta.offset, dtype=np.int64)
+    size = np.ascontiguousarray(meta.size, dtype=np.int64)
+    hashed = np.ascontiguousarray(meta.hashed, dtype=np.uint8)
+    out = np.empty((x.shape[0], 2 * L), dtype=np.float32)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.qf_oracle_hashgrid_encode.restype = None
+    lib.qf_oracle_hashgrid_encode(P(x), C.c_int64(x.shape[0]), P(t), C.c_int(L), P(scale), P(res), P(offset), P(size), P(hashed), P(out))
+    return torch.from_numpy(out)
 
 
 def sh4(d: torch.Tensor) -> torch.Tensor:

@@ -183,6 +183,31 @@ class MeshRenderer:
         return out
 
 
+    @torch.no_grad()
+    def render_pose(self, c2w, W: int, H: int, focal: float, cx: float, cy: float, bg_color="white", render_bkgd=None, out=None,
+                    hits_out: Optional[torch.Tensor] = None, opengl: bool = True, rows: Optional[tuple] = None):
+        """The evaluation frame of the reference from its real input: a 3x4 camera-to-world pose on the HOST.  The reference's
+        `SubjectLoader.fetch_data` builds the W*H rays on the device from the pose (nerf_synthetic.py:289-378) and the eval
+        loop renders them (train_finetune.py:586-617); here: `qf_generate_rays` (the 48-byte pose travels as kernel
+        arguments, no host->device copy of rays) into resident scratch, then the fused render.
+        `rows=(r0, r1)` renders only image rows [r0, r1) — a rank's band of a ray-sharded frame.  -> the `render` dict."""
+        lib = _lib.load()
+        dev = self.device
+        m = np.ascontiguousarray(np.asarray(c2w.cpu() if isinstance(c2w, torch.Tensor) else c2w, dtype=np.float32)[:3, :4])
+        n = W * H
+        key = ("pose_rays", n)
+        buf = getattr(self, "_pose_rays", None)
+        if buf is None or buf[0] != key:
+            buf = (key, torch.empty((n, 3), dtype=torch.float32, device=dev), torch.empty((n, 3), dtype=torch.float32, device=dev))
+            self._pose_rays = buf
+        _, o, d = buf
+        _lib.check(lib.qf_generate_rays(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
+                                        1 if opengl else 0, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)), "qf_generate_rays")
+        if rows is not None:
+            o, d = o[rows[0] * W:rows[1] * W], d[rows[0] * W:rows[1] * W]
+        return self.render(o, d, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out, image_width=W)
+
+
 class FramePipeline:
     """Renders successive frames on alternating CUDA streams.  The BVH traversal kernel is issue/ALU bound and the
     hash-grid shading kernel is L1-gather bound, so the trace of frame i+1 overlaps the shading of frame i when they

@@ -250,6 +250,32 @@ def test_c_bruteforce_matches_numpy():
     assert a[3].max() >= 6
 
 
+def test_c_hashgrid_matches_numpy():
+    """oracle/bruteforce.c:qf_oracle_hashgrid_encode (bench.py's CPU baseline) is bit-identical to the numpy/torch
+    restatement of tcnn's half-precision interpolation: dense and hashed levels, points outside [0,1] (index wrap),
+    a table scaled into the half denormal range, and the hand-computed value of a point on a cell corner."""
+    import __graft_entry__ as entry
+    entry.build_oracle()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(20000, 3, generator=g) * 1.3 - 0.15
+    x[:8] = torch.tensor([0.0, 0.25, 0.5, 1.0, 0.999999, 1e-7, 0.75, 0.125]).view(8, 1).expand(8, 3)
+    for log2_T, scale in ((12, 1.0), (19, 1e-4), (14, 30.0)):
+        meta = O.make_grid_meta(log2_hashmap_size=log2_T)
+        table = ((torch.rand(int(meta.n_entries), 2, generator=g) * 2 - 1) * scale).half().float()
+        a = O.hashgrid_encode(x, table, meta)
+        b = O.hashgrid_encode_c(x, table, meta)
+        assert torch.equal(a, b)
+        assert torch.equal(a, a.half().float())                     # every output is a half value
+    # level 0 (res 16, scale 15): x01 = 1/30 puts pos = 15/30 + 0.5 = 1.0 exactly on corner (1,1,1) -> the entry itself
+    meta = O.make_grid_meta(log2_hashmap_size=12)
+    table = ((torch.rand(int(meta.n_entries), 2, generator=g) * 2 - 1)).half().float()
+    p = torch.full((1, 3), 1.0 / 30.0)
+    pos = np.float32(15.0) * np.float32(1.0 / 30.0) + np.float32(0.5)
+    if float(pos) == 1.0:
+        idx = 1 + 1 * 16 + 1 * 256
+        assert torch.equal(O.hashgrid_encode(p, table, meta)[0, :2], table[idx])
+
+
 def test_c_bvh_matches_bruteforce():
     """The CPU BVH traversal of oracle/bruteforce.c (bench.py's CPU baseline, the shape of the reference's Embree path) is
     bit-identical to the brute force: ids, distances, counts and totals, with and without culling behind the K-th hit,
