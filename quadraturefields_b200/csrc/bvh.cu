@@ -17,6 +17,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <float.h>
+#include <stdlib.h>
 
 #include "traverse.cuh"
 
@@ -237,6 +238,113 @@ __global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, const flo
   nodes[3] = make_float4(__int_as_float(~0), __int_as_float(kEmptyRef), 0.f, 0.f);
 }
 
+// ---------------------------------------------------------------- wide BVH: collapse of the binary tree
+// One warp per wide node, lane = child slot.  The frontier starts as the two children of the node's binary root and is
+// expanded one binary step at a time:
+//   1. while a frontier entry covers more than 32 triangles, the one with the largest surface area is replaced by its two
+//      children (slots permitting) — the upper levels tile space by area, like a SAH collapse;
+//   2. entries of <= 32 triangles stay whole subtrees (each becomes one well-filled node of the next level), except that
+//      the smallest ones are dissolved into single triangles while the free slots allow, so no node of 2-3 triangles is
+//      ever emitted next to free slots.
+// Children that are still internal get a wide node of the next level; triangle children carry the triangle's own padded
+// box.  Levels are processed by successive launches (kWideLevels of them: the packet stack holds 8 levels of pushes); a
+// tree that needs more, or more nodes than were allocated, clears the ok flag and the traversal keeps to the binary tree.
+constexpr int kWideLevels = 8;
+
+__global__ void wide_init_kernel(int32_t* __restrict__ wstate, int32_t* __restrict__ wqueue) {
+  wstate[0] = 0; wstate[1] = 1; wstate[2] = 1; wstate[3] = 1; wstate[4] = 0;
+  wqueue[0] = 0;
+}
+
+__global__ void wide_advance_kernel(int32_t* __restrict__ wstate, int capacity) {
+  wstate[0] = wstate[1];
+  wstate[1] = wstate[2] < capacity ? wstate[2] : capacity;
+  if (wstate[2] > capacity) wstate[3] = 0;
+  wstate[4] += 1;
+  if (wstate[4] >= kWideLevels && wstate[0] < wstate[1]) wstate[3] = 0;    // deeper than the packet stack allows
+}
+
+__global__ void __launch_bounds__(128) wide_collapse_kernel(const float4* __restrict__ tris, int n_tris, const float* __restrict__ scene,
+                                                            const int* __restrict__ left, const int* __restrict__ right,
+                                                            const int* __restrict__ first, const int* __restrict__ last,
+                                                            const float4* __restrict__ ibox, int32_t* __restrict__ wqueue,
+                                                            int32_t* __restrict__ wstate, int capacity, float4* __restrict__ wnodes) {
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  const int begin = wstate[0], end = wstate[1];
+  const float pad = scene[6];
+  for (int w = begin + gw; w < end; w += nw) {
+    int ref = kEmptyRef;          // binary reference held by this slot
+    int cnt = 0;                  // triangles below it
+    float area = -1.f;
+    auto fill = [&](int r) {
+      ref = r;
+      if (r < 0) { cnt = 1; area = -1.f; }
+      else {
+        cnt = last[r] - first[r] + 1;
+        const float4 a = ibox[2 * (int64_t)r], b = ibox[2 * (int64_t)r + 1];
+        const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+        area = dx * dy + dy * dz + dz * dx;
+      }
+    };
+    int n;
+    if (n_tris == 1) { if (lane == 0) fill(~0); n = 1; }
+    else {
+      const int b = wqueue[w];
+      if (lane == 0) fill(left[b]);
+      if (lane == 1) fill(right[b]);
+      n = 2;
+    }
+    // ---- phase 1: split the largest-area entry that covers more than 32 triangles
+    while (n < 32) {
+      float key = (ref >= 0 && cnt > 32) ? area : -1.f;
+      float best = key;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (best < 0.f) break;
+      const int who = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+      const int r = __shfl_sync(0xffffffffu, ref, who);
+      if (lane == who) fill(left[r]);
+      if (lane == n) fill(right[r]);
+      ++n;
+    }
+    // ---- phase 2: dissolve the smallest remaining subtrees into triangles while the slots allow
+    while (n < 32) {
+      int key = (ref >= 0 && cnt <= 32) ? cnt : 0x7fffffff;
+      int best = key;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+      if (best == 0x7fffffff || n + best - 1 > 32) break;
+      const int who = __ffs(__ballot_sync(0xffffffffu, key == best)) - 1;
+      const int r = __shfl_sync(0xffffffffu, ref, who);
+      if (lane == who) fill(left[r]);
+      if (lane == n) fill(right[r]);
+      ++n;
+    }
+    // ---- emit: internal entries get wide nodes of the next level
+    const bool internal = lane < n && ref >= 0;
+    const unsigned mi = __ballot_sync(0xffffffffu, internal);
+    int base = 0;
+    if (lane == 0 && mi) base = atomicAdd(wstate + 2, __popc(mi));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+    int out_ref = kEmptyRef;
+    if (lane < n) {
+      if (ref < 0) { tri_box(tris, ~ref, pad, lo, hi); out_ref = ref; }
+      else {
+        const float4 a = ibox[2 * (int64_t)ref], b = ibox[2 * (int64_t)ref + 1];
+        lo[0] = a.x; lo[1] = a.y; lo[2] = a.z; hi[0] = b.x; hi[1] = b.y; hi[2] = b.z;
+        const int idx = base + __popc(mi & ((1u << lane) - 1u));
+        if (idx < capacity) { wqueue[idx] = ref; out_ref = idx; }
+        else out_ref = kEmptyRef;      // overflow: the ok flag goes down in wide_advance_kernel, the node is never used
+      }
+    }
+    float4* rec = wnodes + ((int64_t)w * 32 + lane) * 2;
+    rec[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+    rec[1] = make_float4(hi[1], hi[2], __int_as_float(out_ref), 0.f);
+  }
+}
+
 // Pre-pass over a ray list.  slot[0] += warps (32 consecutive rays) that would traverse as a packet, slot[1] += warps,
 // slot[3] = number of rays whose slab test against the whole scene box passes; their ids are compacted into `list`.
 // The outputs are pre-filled with "no hit" (memsets), so the refill kernel only writes rays that have hits.
@@ -352,9 +460,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
                                                     const float* __restrict__ origins, const float* __restrict__ dirs,
                                                     int64_t N, int K, int32_t* __restrict__ out_tri,
                                                     float* __restrict__ out_t, int32_t* __restrict__ out_count,
-                                                    int32_t* __restrict__ out_total, const int32_t* __restrict__ slot) {
+                                                    int32_t* __restrict__ out_total, const int32_t* __restrict__ slot,
+                                                    const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate) {
   if (!mostly_coherent(slot)) return;   // trace_refill_kernel handles this list
-  __shared__ int s_stack[4][kStackDepth];
+  __shared__ int s_stack[4][kWideStack];
+  if (wnodes && !__ldg(wstate + 3)) wnodes = nullptr;    // the collapse gave up on this mesh: binary tree only
   __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -362,7 +472,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
   Ray r = make_ray(origins, dirs, valid ? i : N - 1);
   HB hb(s_ht, s_hi, threadIdx.x);
   int total;
-  trace_ray<HB, !COUNT_ALL>(r, valid, nodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
+  trace_ray<HB, !COUNT_ALL>(r, valid, nodes, wnodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
   if (!valid) return;
   write_hits<HB>(hb, total, i, K, out_tri, out_t, out_count, out_total);
 }
@@ -453,6 +563,16 @@ static int build(qf_mesh* m, cudaStream_t st) {
     QF_LAUNCH_CHECK();
     m->n_nodes = F - 1;
   }
+  // wide BVH for coherent packets: level-synchronous collapse, no host synchronisation
+  if (m->d_wnodes) {
+    wide_init_kernel<<<1, 1, 0, st>>>(m->d_wstate, m->d_wqueue);
+    for (int lvl = 0; lvl < kWideLevels; ++lvl) {
+      wide_collapse_kernel<<<kNumSMs * 4, 128, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_first, m->d_last,
+                                                       m->d_ibox, m->d_wqueue, m->d_wstate, (int)m->wide_capacity, m->d_wnodes);
+      wide_advance_kernel<<<1, 1, 0, st>>>(m->d_wstate, (int)m->wide_capacity);
+    }
+    QF_LAUNCH_CHECK();
+  }
   return QF_OK;
 }
 
@@ -501,6 +621,14 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
   QF_A(dev_alloc(&m->d_flags, F + 8, &m->bytes));
   QF_A(dev_alloc(&m->d_ibox, 2 * F, &m->bytes));
   QF_A(dev_alloc(&m->d_call_slots, 4 * kCallSlots, &m->bytes));
+  // wide nodes: ~F/22 in practice (leaf nodes hold 17-32 triangles); room for F/8 + 64, the collapse falls back to the
+  // binary tree if a pathological mesh needs more.  QF_WIDE_BVH=0 disables the wide tree.
+  if (!(getenv("QF_WIDE_BVH") && atoi(getenv("QF_WIDE_BVH")) == 0)) {
+    m->wide_capacity = (int64_t)(F / 8 + 64);
+    QF_A(dev_alloc(&m->d_wnodes, 64 * (size_t)m->wide_capacity, &m->bytes));
+    QF_A(dev_alloc(&m->d_wqueue, (size_t)m->wide_capacity, &m->bytes));
+    QF_A(dev_alloc(&m->d_wstate, 8, &m->bytes));
+  }
 #undef QF_A
   if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
   size_t tmp = 0;
@@ -536,7 +664,7 @@ extern "C" void qf_mesh_destroy(qf_mesh* m) {
   if (!m) return;
   void* ptrs[] = {m->d_vertices, m->d_faces, m->d_tris, m->d_planes, m->d_nodes, m->d_scene, m->d_keys, m->d_keys_sorted,
                   m->d_idx, m->d_idx_sorted, m->d_left, m->d_right, m->d_parent, m->d_leaf_parent, m->d_first, m->d_last,
-                  m->d_flags, m->d_ibox, m->d_sort_tmp, m->d_call_slots};
+                  m->d_flags, m->d_ibox, m->d_sort_tmp, m->d_call_slots, m->d_wnodes, m->d_wqueue, m->d_wstate};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
 }
@@ -576,7 +704,7 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   const int pblocks = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;   // persistent grid of the refill kernel
 #define QF_TRACE(KM, ALL)                                                                                                         \
   do {                                                                                                                            \
-    trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot); \
+    trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, m->d_wnodes, m->d_wstate); \
     if (have_ws) trace_refill_kernel<KM, ALL><<<pblocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, list); \
   } while (0)
   // the untruncated total needs a traversal without distance culling

@@ -59,6 +59,10 @@ struct qf_mesh {
   float4* d_tris = nullptr;       // Morton-sorted: 3 x float4 per triangle: (v0,id) (v1,0) (v2,0)
   float4* d_planes = nullptr;     // per ORIGINAL triangle id: (n.xyz from fp64, d=-(n.v0))
   float4* d_nodes = nullptr;      // 4 x float4 per node: both children's boxes + refs
+  float4* d_wnodes = nullptr;     // wide BVH: 32 children x 2 float4 per node (traverse.cuh), collapsed from the binary tree
+  int32_t* d_wqueue = nullptr;    // binary node behind every wide node (build scratch)
+  int32_t* d_wstate = nullptr;    // [0] level begin, [1] level end, [2] wide nodes allocated, [3] ok flag, [4] level
+  int64_t wide_capacity = 0;      // wide nodes that fit in d_wnodes
   float* d_scene = nullptr;       // [0..2] lo, [3..5] hi, [6] pad
   // build scratch (kept so update_vertices does not allocate)
   uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;

@@ -70,10 +70,12 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
                                                             int64_t ray0, int64_t n, int K, int img_w, int mode,
                                                             int32_t* __restrict__ cursor,
                                                             int32_t* __restrict__ ray_start, int32_t* __restrict__ ray_count,
-                                                            float4* __restrict__ hit_pd, int2* __restrict__ hit_rt) {
+                                                            float4* __restrict__ hit_pd, int2* __restrict__ hit_rt,
+                                                            const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate) {
   __shared__ int s_warp[4];
   __shared__ int s_base;
-  __shared__ int s_stack[4][kStackDepth];
+  __shared__ int s_stack[4][kWideStack];
+  if (wnodes && !__ldg(wstate + 3)) wnodes = nullptr;    // the collapse gave up on this mesh: binary tree only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ int s_slot_off[4][QF_MAX_HITS];        // records of the warp's run before slot j
   __shared__ unsigned s_slot_mask[4][QF_MAX_HITS];  // lanes that have a j-th hit
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   HB hb(s_ht, s_hi, tid);
   int total = 0;
   Ray r = make_ray(origins, dirs, ray0 + (valid ? li : n - 1));
-  trace_ray<HB>(r, valid, nodes, tris, K, hb, total, s_stack[warp], mode);
+  trace_ray<HB>(r, valid, nodes, wnodes, tris, K, hb, total, s_stack[warp], mode);
   // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
   int c = valid ? hb.count(K) : 0, inc = c;
 #pragma unroll
@@ -280,10 +282,10 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
     if (K <= 8)
       trace_compact_kernel<HitBufReg<8>><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                      d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+                                                      d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate);
     else
       trace_compact_kernel<HitBufSmem><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt);
+                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) cudaEventRecord(pe[1], st);
     int rc = mode == Shade::NGP ? launch_ngp_forward_hits(field, w.hit_pd, w.hit_rt, d_viewdirs, w.cursor, w.hit_out, st)

@@ -223,6 +223,87 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
   }
 }
 
+// ---------------------------------------------------------------- warp packet traversal of the WIDE BVH
+// A wide node has up to 32 children (bvh.cu: collapse of the binary LBVH); child c is the record pair
+//   wnodes[(node * 32 + c) * 2 + 0] = (lo.x, lo.y, lo.z, hi.x)     wnodes[... + 1] = (hi.y, hi.z, ref, -)
+// with ref >= 0 a wide node, ref < 0 ONE triangle (~ref = position in the Morton-sorted array; the box is that triangle's
+// padded box, exactly), kEmptyRef nothing.  The packet's 32 lanes test the 32 children of a node AT ONCE, lane c testing
+// child c against the whole packet: the rays share their origin, so with m = fl(plane - o) (one value for the packet)
+// every ray's fl(m * i_r) lies between fl(m * i_min) and fl(m * i_max) — rounding is monotone and the operation is the
+// very one of the per-ray slab test — hence
+//     tn_lo = max_axes(min(m_near * i_min, m_near * i_max), 0) <= tn_r    and    tf_hi = min_axes(max(m_far * i_min, m_far * i_max)) >= tf_r
+// for every ray r of the packet, with NO epsilon: a child is skipped only if no ray's own test could pass, and by
+// monotonicity in the box no descendant triangle's either.  Triangles are then tested per lane with the exact predicate
+// (slab of the triangle's own box, Möller–Trumbore, t >= tn), so results are bit-identical to the binary traversal and to
+// the brute force.  One node visit replaces ~5 levels of two-box visits in which all 32 lanes did the same test.
+constexpr int kWideStack = 256;   // entries of shared memory per warp (a visit pushes <= 32 children, depth ~ log32 F)
+
+template <class HB, bool CULL, int SIGN>
+__device__ __forceinline__ void traverse_packet_wide(const Ray& r, bool active, const float4* __restrict__ wnodes,
+                                                     const float4* __restrict__ tris, int K, HB& hb, int& total,
+                                                     int* __restrict__ wstack) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const float inf = __int_as_float(0x7f800000);
+  // packet bounds of the reciprocal directions (all active lanes share the sign pattern SIGN and the origin)
+  float ixa = active ? r.ix : inf, ixb = active ? r.ix : -inf;
+  float iya = active ? r.iy : inf, iyb = active ? r.iy : -inf;
+  float iza = active ? r.iz : inf, izb = active ? r.iz : -inf;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ixa = fminf(ixa, __shfl_xor_sync(0xffffffffu, ixa, o)); ixb = fmaxf(ixb, __shfl_xor_sync(0xffffffffu, ixb, o));
+    iya = fminf(iya, __shfl_xor_sync(0xffffffffu, iya, o)); iyb = fmaxf(iyb, __shfl_xor_sync(0xffffffffu, iyb, o));
+    iza = fminf(iza, __shfl_xor_sync(0xffffffffu, iza, o)); izb = fmaxf(izb, __shfl_xor_sync(0xffffffffu, izb, o));
+  }
+  const int src = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
+  const float ox = __shfl_sync(0xffffffffu, r.ox, src), oy = __shfl_sync(0xffffffffu, r.oy, src), oz = __shfl_sync(0xffffffffu, r.oz, src);
+  total = 0;
+  hb.init(K);
+  int sp = 1;
+  if (lane == 0) wstack[0] = 0;
+  __syncwarp();
+  while (sp > 0) {
+    const int node = wstack[--sp];
+    __syncwarp();                      // every lane has read the entry before a push may overwrite it
+    const float4* rec = wnodes + ((int64_t)node * 32 + lane) * 2;
+    const float4 a = __ldg(rec), b = __ldg(rec + 1);
+    const int ref = __float_as_int(b.z);
+    // child `lane` against the packet
+    const float nx = (SIGN & 1) ? a.w : a.x, fx = (SIGN & 1) ? a.x : a.w;
+    const float ny = (SIGN & 2) ? b.x : a.y, fy = (SIGN & 2) ? a.y : b.x;
+    const float nz = (SIGN & 4) ? b.y : a.z, fz = (SIGN & 4) ? a.z : b.y;
+    const float mnx = __fsub_rn(nx, ox), mfx = __fsub_rn(fx, ox);
+    const float mny = __fsub_rn(ny, oy), mfy = __fsub_rn(fy, oy);
+    const float mnz = __fsub_rn(nz, oz), mfz = __fsub_rn(fz, oz);
+    const float tnx = fminf(__fmul_rn(mnx, ixa), __fmul_rn(mnx, ixb)), tfx = fmaxf(__fmul_rn(mfx, ixa), __fmul_rn(mfx, ixb));
+    const float tny = fminf(__fmul_rn(mny, iya), __fmul_rn(mny, iyb)), tfy = fmaxf(__fmul_rn(mfy, iya), __fmul_rn(mfy, iyb));
+    const float tnz = fminf(__fmul_rn(mnz, iza), __fmul_rn(mnz, izb)), tfz = fmaxf(__fmul_rn(mfz, iza), __fmul_rn(mfz, izb));
+    const float tn_lo = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f)), tf_hi = fminf(fminf(tfx, tfy), tfz);
+    bool hit = (ref != kEmptyRef) && (tn_lo <= tf_hi);
+    if (CULL) {
+      // a child further than the K-th hit of EVERY lane cannot contribute (t >= tn_r >= tn_lo > cull distance)
+      const float mine = active ? hb.cull_distance() : 0.0f;
+      const float tcm = __int_as_float(__reduce_max_sync(0xffffffffu, __float_as_int(mine)));   // distances are >= 0: int order
+      hit = hit && (tn_lo <= tcm);
+    }
+    const unsigned m_int = __ballot_sync(0xffffffffu, hit && ref >= 0);
+    unsigned m_tri = __ballot_sync(0xffffffffu, hit && ref < 0);
+    if (hit && ref >= 0) wstack[sp + __popc(m_int & lt)] = ref;
+    sp += __popc(m_int);
+    __syncwarp();
+    while (m_tri) {
+      const int c = __ffs(m_tri) - 1;
+      m_tri &= m_tri - 1;
+      const float lx = __shfl_sync(0xffffffffu, a.x, c), ly = __shfl_sync(0xffffffffu, a.y, c), lz = __shfl_sync(0xffffffffu, a.z, c);
+      const float hx = __shfl_sync(0xffffffffu, a.w, c), hy = __shfl_sync(0xffffffffu, b.x, c), hz = __shfl_sync(0xffffffffu, b.y, c);
+      const int tref = __shfl_sync(0xffffffffu, ref, c);
+      float tn, tf;
+      const bool s = slab_signed<SIGN & 7>(r, lx, ly, lz, hx, hy, hz, tn, tf);
+      if (s && active && tn <= (CULL ? hb.cull_distance() : inf)) leaf_intersect<HB>(r, tris, tref, tn, hb, total);
+    }
+  }
+}
+
 // Warp-uniform sign pattern of the direction components (bit k: component k negative) when every active lane has
 // finite, non-zero components of the same signs; -1 otherwise.
 __device__ __forceinline__ int warp_sign_pattern(const Ray& r, bool active) {
@@ -251,14 +332,30 @@ __device__ __forceinline__ bool warp_is_coherent(const Ray& r, bool active) {
 }
 
 // Entry used by the trace kernels.  EVERY lane of the warp must call it (invalid lanes pass valid=false).
-// mode: 0 = choose per warp, 1 = always per-lane, 2 = always packet (tuning knob, results are identical)
+// mode: 0 = choose per warp, 1 = always per-lane, 2 = always packet, 3 = binary packets only (tuning knobs, results are
+// identical).  `wnodes` (may be NULL): the wide BVH; coherent warps with one sign pattern traverse it, every other warp
+// the binary tree.  `wstack`: kWideStack ints of shared memory private to the warp.
 template <class HB, bool CULL = true>
 __device__ __forceinline__ void trace_ray(const Ray& r, bool valid, const float4* __restrict__ nodes,
-                                          const float4* __restrict__ tris, int K, HB& hb, int& total,
-                                          int* __restrict__ wstack, int mode = 0) {
+                                          const float4* __restrict__ wnodes, const float4* __restrict__ tris, int K, HB& hb,
+                                          int& total, int* __restrict__ wstack, int mode = 0) {
   const bool coherent = warp_is_coherent(r, valid);
-  if (mode == 2 || (mode == 0 && coherent)) {
-    switch (warp_sign_pattern(r, valid)) {   // warp-uniform: one specialisation per octant, the generic test otherwise
+  if (mode == 2 || mode == 3 || (mode == 0 && coherent)) {
+    const int sign = warp_sign_pattern(r, valid);   // warp-uniform: one specialisation per octant, the generic test otherwise
+    if (wnodes != nullptr && coherent && mode != 3 && sign >= 0) {
+      switch (sign) {
+        case 0: traverse_packet_wide<HB, CULL, 0>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 1: traverse_packet_wide<HB, CULL, 1>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 2: traverse_packet_wide<HB, CULL, 2>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 3: traverse_packet_wide<HB, CULL, 3>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 4: traverse_packet_wide<HB, CULL, 4>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 5: traverse_packet_wide<HB, CULL, 5>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        case 6: traverse_packet_wide<HB, CULL, 6>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+        default: traverse_packet_wide<HB, CULL, 7>(r, valid, wnodes, tris, K, hb, total, wstack); break;
+      }
+      return;
+    }
+    switch (sign) {
       case 0: traverse_packet<HB, CULL, 0>(r, valid, nodes, tris, K, hb, total, wstack); break;
       case 1: traverse_packet<HB, CULL, 1>(r, valid, nodes, tris, K, hb, total, wstack); break;
       case 2: traverse_packet<HB, CULL, 2>(r, valid, nodes, tris, K, hb, total, wstack); break;
