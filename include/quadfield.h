@@ -55,6 +55,14 @@ int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const int32_t* d
  * positions; rebuilds the hierarchy on `stream`. */
 int qf_mesh_update_vertices(qf_mesh* mesh, const float* d_vertices, void* stream);
 void qf_mesh_destroy(qf_mesh* mesh);
+/* Hit-set semantics.  eps = 0 (default): ALL hits with t > 0 in (t, triangle id) order, first K — what the reference's
+ * OptiX intersector returns (mesh_utils.py:77-96, `optix=True`).  eps > 0: the SHIPPED default intersector, trimesh +
+ * Embree (`optix=False`; mesh_utils.py:223, 350-354 `intersects_id(multiple_hits=True, max_hits=K)`): a first-hit query
+ * repeated up to K times, each restarted eps beyond the previous hit — of the hits in (t, id) order one is kept iff it lies
+ * more than eps (fp32 difference of t) behind the last kept one, until K are kept.  The reference's eps is
+ * clip(1e-4 * 100 / mesh.scale, 1e-8, inf) world units (mesh.scale = bounding-box diagonal).  The filter sees the
+ * QF_MAX_HITS nearest raw hits of a ray.  Applies to qf_trace_firstk and the fused renders of this mesh. */
+int qf_mesh_set_restart_eps(qf_mesh* mesh, float eps);
 /* info[0]=n_faces, [1]=n_vertices, [2]=n_nodes, [3]=device bytes held */
 int qf_mesh_info(const qf_mesh* mesh, int64_t* info4, float* box_pad);
 

@@ -347,22 +347,30 @@ def embree_restart_firstk(t_all, tri_all, count_all, K: int, eps: float):
     restarted `eps` beyond the previous hit along the ray — so hits come out front to back and a hit closer than `eps`
     to the previously KEPT one is never returned.  Input: all hits per ray sorted by (t, id) (`intersect_firstk` with a
     large K).  -> tri (N,K) int32 (-1 padded), count (N,).  Used only to quantify how far the two definitions differ."""
-    t_all, tri_all = np.asarray(t_all), np.asarray(tri_all)
+    t_all, tri_all = np.asarray(t_all, dtype=np.float32), np.asarray(tri_all)
     N = t_all.shape[0]
     tri = np.full((N, K), -1, dtype=np.int32)
     count = np.zeros(N, dtype=np.int32)
+    eps32 = np.float32(eps)
     for i in range(N):
-        last = -np.inf
+        last = np.float32(-np.inf)
         c = 0
         for j in range(int(count_all[i])):
             if c == K:
                 break
-            if t_all[i, j] - last > eps:
+            if np.float32(t_all[i, j] - last) > eps32:          # fp32 difference against the fp32 epsilon (the kernel's test)
                 tri[i, c] = tri_all[i, j]
                 last = t_all[i, j]
                 c += 1
         count[i] = c
     return tri, count
+
+
+def embree_restart_eps(vertices) -> float:
+    """trimesh 3.23.5 `ray_pyembree` (recalled): offset = clip(1e-4 * 100 / mesh.scale, 1e-8, inf) in world units,
+    mesh.scale = bounding-box diagonal."""
+    v = np.asarray(vertices, dtype=np.float64)
+    return float(np.clip(1e-4 * 100.0 / float(np.linalg.norm(v.max(0) - v.min(0))), 1e-8, np.inf))
 
 
 def plane_hit_points(o, r, n, v):

@@ -33,6 +33,7 @@ _SIGS = {
     "qf_mesh_update_vertices": (_I, [_P, _P, _P]),
     "qf_mesh_destroy": (None, [_P]),
     "qf_mesh_info": (_I, [_P, C.POINTER(_L), C.POINTER(_F)]),
+    "qf_mesh_set_restart_eps": (_I, [_P, _F]),
     "qf_trace_workspace_bytes": (_SZ, [_L]),
     "qf_trace_firstk": (_I, [_P, _P, _P, _L, _I, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_scan_workspace_bytes": (_SZ, [_L]),

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
                                                            int64_t N, int K, int32_t* __restrict__ out_tri,
                                                            float* __restrict__ out_t, int32_t* __restrict__ out_count,
                                                            int32_t* __restrict__ out_total, int32_t* __restrict__ slot,
-                                                           const int32_t* __restrict__ list) {
+                                                           const int32_t* __restrict__ list, int k_trav, float restart_eps) {
   if (mostly_coherent(slot)) return;
   N = __ldg(slot + 3);   // rays that reach the scene box; the rest keep the pre-filled "no hit"
   const int lane = threadIdx.x & 31;
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
   int sp = 0, cur = kDoneRef, total = 0;
   float cur_tn = 0.f;
   bool exhausted = false;
-  hb.init(K);
+  hb.init(k_trav);
   while (true) {
     const unsigned idle = __ballot_sync(0xffffffffu, ri < 0);
     if (!exhausted && __popc(idle) >= 12) {
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
       if (ri < 0 && mine < N) {
         ri = __ldg(list + mine);
         r = make_ray(origins, dirs, ri);
-        hb.init(K);
+        hb.init(k_trav);
         total = 0; sp = 0; cur = 0; cur_tn = 0.f;
       }
       exhausted = (int64_t)base + n >= N;
@@ -449,7 +449,10 @@ __global__ void __launch_bounds__(128) trace_refill_kernel(const float4* __restr
       else cur = kDoneRef;
     }
     if (ri >= 0 && cur == kDoneRef) {
-      if (total > 0) write_hits<HB>(hb, total, ri, K, out_tri, out_t, out_count, out_total);
+      if (total > 0) {
+        if (restart_eps > 0.f) hb.restart_filter(restart_eps, K);
+        write_hits<HB>(hb, total, ri, K, out_tri, out_t, out_count, out_total);
+      }
       ri = -1;
     }
   }
@@ -461,7 +464,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
                                                     int64_t N, int K, int32_t* __restrict__ out_tri,
                                                     float* __restrict__ out_t, int32_t* __restrict__ out_count,
                                                     int32_t* __restrict__ out_total, const int32_t* __restrict__ slot,
-                                                    const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate) {
+                                                    const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate,
+                                                    int k_trav, float restart_eps) {
   if (!mostly_coherent(slot)) return;   // trace_refill_kernel handles this list
   __shared__ int s_stack[4][kWideStack];
   if (wnodes && !__ldg(wstate + 3)) wnodes = nullptr;    // the collapse gave up on this mesh: binary tree only
@@ -472,8 +476,9 @@ __global__ void __launch_bounds__(128) trace_kernel(const float4* __restrict__ n
   Ray r = make_ray(origins, dirs, valid ? i : N - 1);
   HB hb(s_ht, s_hi, threadIdx.x);
   int total;
-  trace_ray<HB, !COUNT_ALL>(r, valid, nodes, wnodes, tris, K, hb, total, s_stack[threadIdx.x >> 5]);
+  trace_ray<HB, !COUNT_ALL>(r, valid, nodes, wnodes, tris, k_trav, hb, total, s_stack[threadIdx.x >> 5]);
   if (!valid) return;
+  if (restart_eps > 0.f) hb.restart_filter(restart_eps, K);
   write_hits<HB>(hb, total, i, K, out_tri, out_t, out_count, out_total);
 }
 
@@ -669,6 +674,13 @@ extern "C" void qf_mesh_destroy(qf_mesh* m) {
   delete m;
 }
 
+extern "C" int qf_mesh_set_restart_eps(qf_mesh* m, float eps) {
+  QF_REQUIRE(m, "qf_mesh_set_restart_eps: NULL mesh");
+  QF_REQUIRE(eps >= 0.f && eps == eps, "qf_mesh_set_restart_eps: eps=%f", eps);
+  m->restart_eps = eps;
+  return QF_OK;
+}
+
 extern "C" int qf_mesh_info(const qf_mesh* m, int64_t* info4, float* box_pad) {
   QF_REQUIRE(m, "qf_mesh_info: NULL mesh");
   if (info4) { info4[0] = m->n_faces; info4[1] = m->n_vertices; info4[2] = m->n_nodes; info4[3] = (int64_t)m->bytes; }
@@ -704,12 +716,15 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   const int pblocks = blocks < kNumSMs * 8 ? blocks : kNumSMs * 8;   // persistent grid of the refill kernel
 #define QF_TRACE(KM, ALL)                                                                                                         \
   do {                                                                                                                            \
-    trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, m->d_wnodes, m->d_wstate); \
-    if (have_ws) trace_refill_kernel<KM, ALL><<<pblocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, list); \
+    trace_kernel<KM, ALL><<<blocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, m->d_wnodes, m->d_wstate, k_trav, eps); \
+    if (have_ws) trace_refill_kernel<KM, ALL><<<pblocks, 128, 0, st>>>(m->d_nodes, m->d_tris, d_origins, d_dirs, n_rays, K, d_tri, d_t, d_count, d_total, slot, list, k_trav, eps); \
   } while (0)
+  // epsilon-restart mode: collect the QF_MAX_HITS nearest raw hits, then keep K of them like the Embree restart loop
+  const float eps = m->restart_eps;
+  const int k_trav = eps > 0.f ? QF_MAX_HITS : K;
   // the untruncated total needs a traversal without distance culling
-  if (d_total) { if (K <= 8) QF_TRACE(HitBufReg<8>, true); else QF_TRACE(HitBufSmem, true); }
-  else { if (K <= 8) QF_TRACE(HitBufReg<8>, false); else QF_TRACE(HitBufSmem, false); }
+  if (d_total) { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, true); else QF_TRACE(HitBufSmem, true); }
+  else { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, false); else QF_TRACE(HitBufSmem, false); }
 #undef QF_TRACE
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -76,6 +76,7 @@ struct qf_mesh {
   mutable std::atomic<unsigned> call_id{0};   // concurrent qf_trace_firstk calls on one mesh take distinct slots
   size_t bytes = 0;
   float h_pad = 0.f;
+  float restart_eps = 0.f;        // > 0: keep hits like the reference's Embree restart loop (qf_mesh_set_restart_eps)
 };
 constexpr int kCallSlots = 64;
 

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
                                                             int32_t* __restrict__ cursor,
                                                             int32_t* __restrict__ ray_start, int32_t* __restrict__ ray_count,
                                                             float4* __restrict__ hit_pd, int2* __restrict__ hit_rt,
-                                                            const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate) {
+                                                            const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate,
+                                                            int k_trav, float restart_eps) {
   __shared__ int s_warp[4];
   __shared__ int s_base;
   __shared__ int s_stack[4][kWideStack];
@@ -86,9 +87,10 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   HB hb(s_ht, s_hi, tid);
   int total = 0;
   Ray r = make_ray(origins, dirs, ray0 + (valid ? li : n - 1));
-  trace_ray<HB>(r, valid, nodes, wnodes, tris, K, hb, total, s_stack[warp], mode);
+  trace_ray<HB>(r, valid, nodes, wnodes, tris, k_trav, hb, total, s_stack[warp], mode);
+  if (restart_eps > 0.f && valid) hb.restart_filter(restart_eps, K);   // k_trav = QF_MAX_HITS raw hits -> K kept (Embree restart loop)
   // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
-  int c = valid ? hb.count(K) : 0, inc = c;
+  int c = valid ? hb.count(k_trav) : 0, inc = c;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
   if (lane == 31) s_warp[warp] = inc;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   ray_count[li] = c;
   float prev = -1.f;
   bool unsorted = false;
-  hb.for_each(K, [&](int j, float, int id) {
+  hb.for_each(k_trav, [&](int j, float, int id) {
     float px, py, pz;
     plane_hit(r, __ldg(planes + id), px, py, pz);
     float d = norm3(__fsub_rn(px, r.ox), __fsub_rn(py, r.oy), __fsub_rn(pz, r.oz));
@@ -280,12 +282,14 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     const int blocks = (int)ceil_div(n, 128);
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
     if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
-    if (K <= 8)
+    const float eps = mesh->restart_eps;
+    const int k_trav = eps > 0.f ? QF_MAX_HITS : K;
+    if (k_trav <= 8)
       trace_compact_kernel<HitBufReg<8>><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                      d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate);
+                                                      d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate, k_trav, eps);
     else
       trace_compact_kernel<HitBufSmem><<<blocks, 128, 0, st>>>(mesh->d_nodes, mesh->d_tris, mesh->d_planes, mesh->d_scene, d_origins,
-                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate);
+                                                       d_viewdirs, ray0, n, K, img_w, trace_mode, w.cursor, w.ray_start, w.ray_count, w.hit_pd, w.hit_rt, mesh->d_wnodes, mesh->d_wstate, k_trav, eps);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) cudaEventRecord(pe[1], st);
     int rc = mode == Shade::NGP ? launch_ngp_forward_hits(field, w.hit_pd, w.hit_rt, d_viewdirs, w.cursor, w.hit_out, st)

@@ -61,6 +61,7 @@ struct HitBufReg {
     for (int s = 0; s < KMAX; ++s)
       if (s >= KMAX - K && t[s] != __int_as_float(0x7f800000)) f(s - (KMAX - K), t[s], id[s]);
   }
+  __device__ __forceinline__ void restart_filter(float, int) {}   // the epsilon-restart mode always runs on HitBufSmem
 };
 
 // HitBufSmem (8 < K <= 32): unsorted in shared memory (slot-major, 128 threads per CTA, conflict free), O(1) append
@@ -107,6 +108,20 @@ struct HitBufSmem {
       st[q * 128] = a; si[q * 128] = b;
     }
     for (int s = 0; s < cnt; ++s) f(s, st[s * 128], si[s * 128]);
+  }
+  // The SHIPPED reference intersector (trimesh + Embree, mesh_utils.py:223,350-354, SURVEY a2'): a first-hit query
+  // repeated up to K times, each restarted eps beyond the previous hit — i.e. of the hits in (t, id) order, one is kept
+  // iff it lies more than eps (fp32 difference) behind the last KEPT one, until k_out are kept.  Applied to the <= 32
+  // nearest raw hits this buffer collected; afterwards count() / for_each() see the kept hits only.
+  __device__ __forceinline__ void restart_filter(float eps, int k_out) {
+    for_each(0, [](int, float, int) {});          // sort
+    float last = __int_as_float(0xff800000);
+    int w = 0;
+    for (int s = 0; s < cnt && w < k_out; ++s) {
+      const float ts = st[s * 128];
+      if (__fsub_rn(ts, last) > eps) { st[w * 128] = ts; si[w * 128] = si[s * 128]; last = ts; ++w; }
+    }
+    cnt = w;
   }
 };
 

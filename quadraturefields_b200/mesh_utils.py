@@ -29,13 +29,20 @@ class _DoneEvent:
 class RayIntersector:
     """mesh_utils.py:75-109.  `intersects_id` returns (triangle_indices, ray_indices, psi) as numpy arrays."""
 
-    def __init__(self, mesh, max_hits: int = 10, device="cuda"):
+    def __init__(self, mesh, max_hits: int = 10, device="cuda", restart_eps: float = 0.0):
         self.mesh = mesh
         self.max_hits = max_hits
         self.device = torch.device(device)
         self._handle = None
         self._create(torch.as_tensor(np.asarray(mesh.vertices), dtype=torch.float32),
                      torch.as_tensor(np.asarray(mesh.faces), dtype=torch.int32))
+        self.set_restart_eps(restart_eps)
+
+    def set_restart_eps(self, eps: float):
+        """0: all hits in (t, id) order, first K (the OptiX intersector's set).  > 0: the shipped trimesh + Embree
+        intersector's set — a hit closer than `eps` to the previously kept one is skipped (include/quadfield.h)."""
+        self.restart_eps = float(eps)
+        _lib.check(_lib.load().qf_mesh_set_restart_eps(self._handle, C.c_float(self.restart_eps)), "qf_mesh_set_restart_eps")
 
     def _create(self, vertices: torch.Tensor, faces: torch.Tensor):
         lib = _lib.load()
@@ -258,7 +265,7 @@ class MeshIntersection:
     """mesh_utils.py:180-412.  `mesh_path` may also be a `(vertices, faces)` pair."""
 
     def __init__(self, mesh_path, simplify_mesh=False, scale=1.0, num_repeat=16, optix=False, voxel_size=512,
-                 num_intersections=20, render_step_size=0.005, device="cuda"):
+                 num_intersections=20, render_step_size=0.005, device="cuda", hit_semantics: Optional[str] = None):
         if simplify_mesh:
             # the reference forces the trimesh loader (mesh_utils.py:186), for which simplification is not
             # available; every shipped script passes simplify_mesh=False
@@ -270,7 +277,21 @@ class MeshIntersection:
         self.mesh.vertices = self.mesh.vertices * scale                                   # mesh_utils.py:212
         self.device = torch.device(device)
         self.vertices = torch.from_numpy(self.mesh.vertices.astype(np.float32)).to(self.device)   # :214
-        self.rayintersector = RayIntersector(self.mesh, max_hits=self.num_intersections, device=device)
+        # Which hits a ray keeps.  The reference has two intersectors that disagree on closely spaced sheets:
+        # `optix=True` (mesh_utils.py:203-221) returns all hits; `optix=False`, the shipped default (:223, :350-354), runs
+        # trimesh's Embree loop, which restarts eps = clip(1e-4 * 100 / mesh.scale, 1e-8, inf) beyond every hit and so
+        # never reports two hits closer than eps.  hit_semantics "all" | "embree"; None reads QF_HIT_SEMANTICS, default
+        # "all": the set with a closed-form definition the oracle can brute-force; the two agree wherever consecutive
+        # sheets are further than eps apart (every BASELINE config), and "embree" costs a 32-slot hit buffer per ray.
+        import os
+        if hit_semantics is None:
+            hit_semantics = os.environ.get("QF_HIT_SEMANTICS", "all")
+        if hit_semantics not in ("all", "embree"):
+            raise ValueError("hit_semantics must be 'all' or 'embree'")
+        self.hit_semantics = hit_semantics
+        self.restart_eps = float(np.clip(1e-4 * 100.0 / float(self.mesh.scale), 1e-8, np.inf)) if hit_semantics == "embree" else 0.0
+        self.rayintersector = RayIntersector(self.mesh, max_hits=self.num_intersections, device=device,
+                                             restart_eps=self.restart_eps)
 
     def find_deltas(self, boundary, depth):
         """mesh_utils.py:225-231: the constant quadrature step (quirk Q4)."""
