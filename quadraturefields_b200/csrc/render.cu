@@ -73,8 +73,6 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
                                                             float4* __restrict__ hit_pd, int2* __restrict__ hit_rt,
                                                             const float4* __restrict__ wnodes, const int32_t* __restrict__ wstate,
                                                             int k_trav, float restart_eps) {
-  __shared__ int s_warp[4];
-  __shared__ int s_base;
   __shared__ int s_stack[4][kWideStack];
   if (wnodes && !__ldg(wstate + 3)) wnodes = nullptr;    // the collapse gave up on this mesh: binary tree only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -89,20 +87,15 @@ __global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __rest
   Ray r = make_ray(origins, dirs, ray0 + (valid ? li : n - 1));
   trace_ray<HB>(r, valid, nodes, wnodes, tris, k_trav, hb, total, s_stack[warp], mode);
   if (restart_eps > 0.f && valid) hb.restart_filter(restart_eps, K);   // k_trav = QF_MAX_HITS raw hits -> K kept (Embree restart loop)
-  // CTA-wide exclusive scan of the hit counts, one atomicAdd per CTA
-  int c = valid ? hb.count(k_trav) : 0, inc = c;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-  if (lane == 31) s_warp[warp] = inc;
-  __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int w = 0; w < 4; ++w) { int v = s_warp[w]; s_warp[w] = t; t += v; }
-    s_base = t ? atomicAdd(cursor, t) : 0;
-  }
-  __syncthreads();
+  // the warp reserves a contiguous run of the compact hit array with ONE atomicAdd (no CTA barrier: packets differ a lot in
+  // cost, and a __syncthreads here made every warp wait for the slowest of its CTA — 15 % of the stall samples in r2f)
+  int c = valid ? hb.count(k_trav) : 0;
+  const int wsum = __reduce_add_sync(0xffffffffu, c);
+  int wbase = 0;
+  if (lane == 0 && wsum) wbase = atomicAdd(cursor, wsum);
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
   // slot-major layout of the warp's run: record (lane, j) sits at warp_start + off[j] + rank of lane among mask[j]
-  const int warp_start = s_base + s_warp[warp];
+  const int warp_start = wbase;
   const int cmax = __reduce_max_sync(0xffffffffu, c);
   for (int j = 0, off = 0; j < cmax; ++j) {
     const unsigned m = __ballot_sync(0xffffffffu, c > j);

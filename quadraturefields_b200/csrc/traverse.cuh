@@ -370,17 +370,9 @@ __device__ __forceinline__ void trace_ray(const Ray& r, bool valid, const float4
       }
       return;
     }
-    switch (sign) {
-      case 0: traverse_packet<HB, CULL, 0>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 1: traverse_packet<HB, CULL, 1>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 2: traverse_packet<HB, CULL, 2>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 3: traverse_packet<HB, CULL, 3>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 4: traverse_packet<HB, CULL, 4>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 5: traverse_packet<HB, CULL, 5>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 6: traverse_packet<HB, CULL, 6>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      case 7: traverse_packet<HB, CULL, 7>(r, valid, nodes, tris, K, hb, total, wstack); break;
-      default: traverse_packet<HB, CULL, -1>(r, valid, nodes, tris, K, hb, total, wstack); break;
-    }
+    // binary packets: the generic slab test only (the octant-specialised instantiations were worth -16 % while this was the
+    // main path; now it is the fallback and eight more copies of the loop only cost instruction-cache misses)
+    traverse_packet<HB, CULL, -1>(r, valid, nodes, tris, K, hb, total, wstack);
   } else if (valid) {
     traverse_single<HB, CULL>(r, nodes, tris, K, hb, total);
   } else {

@@ -19,6 +19,12 @@ full)
   $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'trace_compact_kernel|ngp_forward' -s 8 -c 4 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_full_$TAG.log ;;
+extra)
+  # the other kernels of the north star: baked shading + K=32 traversal on configs[4] (4K, 1.15 M triangles)
+  XCMD="python tools/run_leg.py c5 3"
+  $XCMD > gpurun_out/plain_extra_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'baked_shade_kernel|HitBufSmem' -s 8 -c 4 -o gpurun_out/prof_extra_$TAG $XCMD > gpurun_out/ncu_extra_$TAG.log 2>&1
+  tail -3 gpurun_out/ncu_extra_$TAG.log ;;
 train)
   TCMD="python tools/diag_train.py 3"
   $TCMD > gpurun_out/plain_train_$TAG.log 2>&1 &&
