@@ -38,6 +38,7 @@ struct TexParams {
   const uint8_t* records;
   int size, L, rec, colour_logit;
   float lambda_thres;
+  const float* tables;   // kTexTables x 256 floats: every dequantiser evaluated once per uint8 code (decode_tables_kernel)
 };
 
 // ngp.py:275-281 (quirk Q5: logit only for compress_type == "sigma")
@@ -47,34 +48,77 @@ __device__ __forceinline__ float inv_colour(uint8_t q, int logit) {
   return c * 2.0f * 12.0f - 12.0f;
 }
 
-// texel record -> reference feature row [diffuse(3), L x (axis3, lambda, c3), sigma]
-__device__ __forceinline__ void decode_record(const TexParams& t, int64_t texel, float* __restrict__ f) {
+// The dequantisers are pure functions of one uint8 code: sigma(alpha), colour(c), lambda(q), and the four trigonometric
+// factors of the lobe axis.  Evaluating them inline cost ~450 of the ~900 instructions per hit (precise expf / logf / sinf /
+// cosf, 12 of them at L=3; ncu r2f: baked_shade_kernel issue-bound at 68 %, XU pipe 42 %, DRAM 37 %).  They are tabulated
+// once per texture set with these very expressions, so a lookup returns the same bits as the inline evaluation.
+enum { kTabSigma = 0, kTabColour, kTabLambda, kTabCosAz, kTabSinAz, kTabSinEl, kTabCosEl, kTexTables };
+
+__global__ void decode_tables_kernel(int colour_logit, float lambda_thres, float* __restrict__ tab) {
+  const int q = threadIdx.x;   // 256 threads
+  const uint8_t b = (uint8_t)q;
+  const float a = (float)b / 255.0f;
+  tab[kTabSigma * 256 + q] = -logf(fmaxf(1.0f - a, 1e-6f)) / 0.005f;                    // texture_utils.py:61-65
+  tab[kTabColour * 256 + q] = inv_colour(b, colour_logit);
+  tab[kTabLambda * 256 + q] = expf((float)b * lambda_thres / 255.0f - 2.5f);            // ngp.py:260-262
+  const float az = (float)(uint8_t)(b - 128) / 128.0f * 3.14159265358979323846f;         // ngp.py:245-246, uint8 wrap (Q6)
+  const float el = (float)b / 256.0f * 3.14159265358979323846f;
+  tab[kTabCosAz * 256 + q] = cosf(az);
+  tab[kTabSinAz * 256 + q] = sinf(az);
+  tab[kTabSinEl * 256 + q] = sinf(el);
+  tab[kTabCosEl * 256 + q] = cosf(el);
+}
+
+// texel record -> reference feature row [diffuse(3), L x (axis3, lambda, c3), sigma]; `tab`: the tables (global or shared)
+__device__ __forceinline__ void decode_record(const TexParams& t, const float* __restrict__ tab, int64_t texel, float* __restrict__ f) {
   const uint4* rp = reinterpret_cast<const uint4*>(t.records + texel * t.rec);
   uint4 raw[4];
   const int nq = t.rec / 16;
 #pragma unroll
   for (int q = 0; q < 4; ++q) if (q < nq) raw[q] = __ldg(rp + q);
   const uint8_t* b = reinterpret_cast<const uint8_t*>(raw);
-  float a = (float)b[0] / 255.0f;
-  float sigma = -logf(fmaxf(1.0f - a, 1e-6f)) / 0.005f;                          // texture_utils.py:61-65
-  f[0] = inv_colour(b[1], t.colour_logit); f[1] = inv_colour(b[2], t.colour_logit); f[2] = inv_colour(b[3], t.colour_logit);
+  const float* col = tab + kTabColour * 256;
+  f[0] = col[b[1]]; f[1] = col[b[2]]; f[2] = col[b[3]];
   for (int l = 0; l < t.L; ++l) {
     const uint8_t* r = b + 4 + 6 * l;
-    float lam = expf((float)r[0] * t.lambda_thres / 255.0f - 2.5f);              // ngp.py:260-262
-    float az = (float)(uint8_t)(r[1] - 128) / 128.0f * 3.14159265358979323846f;   // ngp.py:245-246, uint8 wrap (Q6)
-    float el = (float)r[2] / 256.0f * 3.14159265358979323846f;
-    float se = sinf(el);
+    const float se = tab[kTabSinEl * 256 + r[2]];
     float* o = f + 3 + 7 * l;
-    o[0] = cosf(az) * se; o[1] = sinf(az) * se; o[2] = cosf(el);
-    o[3] = lam;
-    o[4] = inv_colour(r[3], t.colour_logit); o[5] = inv_colour(r[4], t.colour_logit); o[6] = inv_colour(r[5], t.colour_logit);
+    o[0] = tab[kTabCosAz * 256 + r[1]] * se; o[1] = tab[kTabSinAz * 256 + r[1]] * se; o[2] = tab[kTabCosEl * 256 + r[2]];
+    o[3] = tab[kTabLambda * 256 + r[0]];
+    o[4] = col[r[3]]; o[5] = col[r[4]]; o[6] = col[r[5]];
   }
-  f[3 + 7 * t.L] = sigma;
+  f[3 + 7 * t.L] = tab[kTabSigma * 256 + b[0]];
+}
+
+// Compile-time lobe count: the record bytes are picked out of registers with constant shifts and the feature row stays
+// in registers (with a run-time L both live in local memory: 304 bytes of stack per thread in the shading kernel).
+template <int L>
+__device__ __forceinline__ void decode_record_static(const TexParams& t, const float* __restrict__ tab, int64_t texel,
+                                                     float* __restrict__ f) {
+  constexpr int NQ = (4 + 6 * L + 15) / 16;
+  const uint4* rp = reinterpret_cast<const uint4*>(t.records + texel * (NQ * 16));
+  uint32_t w[NQ * 4];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) { const uint4 v = __ldg(rp + q); w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+  auto byte = [&](int k) { return (w[k >> 2] >> (8 * (k & 3))) & 255u; };
+  const float* col = tab + kTabColour * 256;
+  f[0] = col[byte(1)]; f[1] = col[byte(2)]; f[2] = col[byte(3)];
+#pragma unroll
+  for (int l = 0; l < L; ++l) {
+    const int r = 4 + 6 * l;
+    const float se = tab[kTabSinEl * 256 + byte(r + 2)];
+    float* o = f + 3 + 7 * l;
+    o[0] = tab[kTabCosAz * 256 + byte(r + 1)] * se; o[1] = tab[kTabSinAz * 256 + byte(r + 1)] * se; o[2] = tab[kTabCosEl * 256 + byte(r + 2)];
+    o[3] = tab[kTabLambda * 256 + byte(r)];
+    o[4] = col[byte(r + 3)]; o[5] = col[byte(r + 4)]; o[6] = col[byte(r + 5)];
+  }
+  f[3 + 7 * L] = tab[kTabSigma * 256 + byte(0)];
 }
 
 // ngp.py:371-393,456-461: rgb = sigmoid(diffuse + sum_l c_l exp(|lambda_l| (a_l/|a_l| . d - 1)))
 __device__ __forceinline__ void sg_rgb(const float* __restrict__ f, int L, float dx, float dy, float dz, float* rgb) {
   float r = f[0], g = f[1], b = f[2];
+#pragma unroll
   for (int l = 0; l < L; ++l) {
     const float* o = f + 3 + 7 * l;
     float n = sqrtf(o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
@@ -123,7 +167,7 @@ __global__ void texture_decode_kernel(TexParams t, const int64_t* __restrict__ i
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M) return;
   float f[3 + 7 * QF_MAX_LOBES + 1];
-  decode_record(t, idx[2 * i] * t.size + idx[2 * i + 1], f);
+  decode_record(t, t.tables, idx[2 * i] * t.size + idx[2 * i + 1], f);
   const int W = 3 + 7 * t.L + 1;
   for (int k = 0; k < W; ++k) out[i * W + k] = f[k];
 }
@@ -226,32 +270,42 @@ __global__ void texture_compress_kernel(const float* __restrict__ feats, int64_t
 }
 
 // fused shading of compact hit records for qf_render_mesh_baked (render.cu): texel lookup + decode + SG
+template <int LS>   // LS > 0: lobe count known at compile time; 0: generic
 __global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const float* __restrict__ verts,
                                                           const int32_t* __restrict__ faces, const float* __restrict__ uv,
                                                           const float4* __restrict__ hit_pd, const int2* __restrict__ hit_rt,
                                                           const float* __restrict__ viewdirs, const int32_t* __restrict__ d_M,
                                                           float4* __restrict__ out4) {
+  __shared__ float s_tab[kTexTables * 256];
+  for (int k = threadIdx.x; k < kTexTables * 256; k += blockDim.x) s_tab[k] = __ldg(t.tables + k);
+  __syncthreads();
   const int64_t M = *d_M;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
     float4 pd = hit_pd[i];
     int2 rt = hit_rt[i];
     int64_t t0, t1;
     hit_texel(verts, faces, uv, rt.y, pd.x, pd.y, pd.z, t.size, t0, t1);
-    float f[3 + 7 * QF_MAX_LOBES + 1];
-    decode_record(t, t0 * t.size + t1, f);
+    float f[3 + 7 * (LS ? LS : QF_MAX_LOBES) + 1];
+    if (LS) decode_record_static<LS ? LS : 1>(t, s_tab, t0 * t.size + t1, f);
+    else decode_record(t, s_tab, t0 * t.size + t1, f);
+    const int L = LS ? LS : t.L;
     // tuple dirs: d / (|d| + 1e-7)   (mesh_utils.py:369-370, quirk Q7)
     float dx = viewdirs[3 * (int64_t)rt.x], dy = viewdirs[3 * (int64_t)rt.x + 1], dz = viewdirs[3 * (int64_t)rt.x + 2];
     float n = __fadd_rn(__fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz))), 1e-7f);
     float o[3];
-    sg_rgb(f, t.L, __fdiv_rn(dx, n), __fdiv_rn(dy, n), __fdiv_rn(dz, n), o);
-    out4[i] = make_float4(o[0], o[1], o[2], f[3 + 7 * t.L]);
+    sg_rgb(f, L, __fdiv_rn(dx, n), __fdiv_rn(dy, n), __fdiv_rn(dz, n), o);
+    out4[i] = make_float4(o[0], o[1], o[2], f[3 + 7 * L]);
   }
 }
 
 int launch_baked_shade(const qf_texture* tex, const qf_mesh* mesh, const float* d_uv, const float4* hit_pd,
                        const int2* hit_rt, const float* d_viewdirs, const int32_t* d_M, float4* out4, cudaStream_t st) {
-  TexParams t{tex->d_records, tex->size, tex->num_lobes, tex->record_bytes, tex->colour_logit, tex->lambda_thres};
-  baked_shade_kernel<<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4);
+  TexParams t{tex->d_records, tex->size, tex->num_lobes, tex->record_bytes, tex->colour_logit, tex->lambda_thres, tex->d_tables};
+  switch (tex->num_lobes) {
+    case 3: baked_shade_kernel<3><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+    case 6: baked_shade_kernel<6><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+    default: baked_shade_kernel<0><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+  }
   QF_LAUNCH_CHECK();
   return QF_OK;
 }
@@ -279,6 +333,12 @@ extern "C" int qf_texture_create(int size, int num_lobes, const uint8_t* d_alpha
   p.alpha = d_alpha; p.diffuse = d_diffuse;
   for (int l = 0; l < num_lobes; ++l) { p.colors[l] = h_d_colors[l]; p.lambdas[l] = h_d_lambdas[l]; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMalloc((void**)&t->d_tables, sizeof(float) * kTexTables * 256) != cudaSuccess) {
+    set_error("qf_texture_create: cannot allocate the dequantiser tables");
+    qf_texture_destroy(t);
+    return QF_ERR_CUDA;
+  }
+  decode_tables_kernel<<<1, 256, 0, st>>>(colour_logit, lambda_thres, t->d_tables);
   texture_pack_kernel<<<kNumSMs * 8, 256, 0, st>>>(p, num_lobes, n, t->record_bytes, t->d_records);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -290,13 +350,14 @@ extern "C" int qf_texture_create(int size, int num_lobes, const uint8_t* d_alpha
 extern "C" void qf_texture_destroy(qf_texture* t) {
   if (!t) return;
   if (t->d_records) cudaFree(t->d_records);
+  if (t->d_tables) cudaFree(t->d_tables);
   delete t;
 }
 
 extern "C" int qf_texture_decode(const qf_texture* t, const int64_t* d_indices, int64_t M, float* d_features, void* stream) {
   QF_REQUIRE(t && d_indices && d_features, "qf_texture_decode: NULL argument");
   if (M == 0) return QF_OK;
-  TexParams p{t->d_records, t->size, t->num_lobes, t->record_bytes, t->colour_logit, t->lambda_thres};
+  TexParams p{t->d_records, t->size, t->num_lobes, t->record_bytes, t->colour_logit, t->lambda_thres, t->d_tables};
   texture_decode_kernel<<<(int)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(p, d_indices, M, d_features);
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -92,4 +92,5 @@ struct qf_texture {
   int size = 0, num_lobes = 0, colour_logit = 0, record_bytes = 0;
   float lambda_thres = 7.5f;
   uint8_t* d_records = nullptr;   // interleaved texel records (see baked.cu)
+  float* d_tables = nullptr;      // dequantiser lookup tables, 7 x 256 floats (see baked.cu)
 };
