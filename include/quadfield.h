@@ -250,6 +250,10 @@ int qf_render_mesh_ngp(const qf_mesh* mesh, const qf_ngp* field, const float* d_
                        int64_t n_rays, int image_width, int K, float delta, int bg_mode, const float* d_bkgd, float* d_rgb,
                        float* d_alpha, float* d_depth, int32_t* d_hits_total, void* d_workspace,
                        size_t workspace_bytes, void* stream);
+/* Baked variant.  d_uv_scaled (V,2): the per-vertex atlas coordinates already multiplied by the texture size
+ * (test_baking_texture_images.py:325-328).  The library caches a 128-byte barycentric record per triangle for the uv array
+ * of the last call: the array is taken to be IMMUTABLE while its address is unchanged (pass a new buffer after editing it;
+ * vertex updates through qf_mesh_update_vertices invalidate the cache by themselves). */
 int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled,
                          const float* d_origins, const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta,
                          int bg_mode, const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth,

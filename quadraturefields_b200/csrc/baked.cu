@@ -163,6 +163,65 @@ __device__ __forceinline__ void hit_texel(const float* __restrict__ verts, const
   t1 = i1 < 0 ? 0 : (i1 > S - 1 ? S - 1 : i1);
 }
 
+// The triangle-only half of hit_texel, done once per triangle: 16 doubles = 128 bytes per record
+//   [v0(3) | e0(3) | e1(3) | d00 d01 d11 | 1/(d00 d11 - d01^2) | uv_a, uv_b, uv_c as 6 floats (3 doubles' worth)]
+// One aligned 128-byte gather per hit replaces seven scattered ones (face, 3 vertices, 3 uv pairs) and ~110 of the ~200
+// fp64 instructions; the per-hit half below repeats hit_texel's remaining operations in the same order: same bits.
+__global__ void bary_setup_kernel(const float* __restrict__ verts, const int32_t* __restrict__ faces, const float* __restrict__ uv,
+                                  int64_t F, double* __restrict__ out) {
+  int64_t f = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int ia = faces[3 * f], ib = faces[3 * f + 1], ic = faces[3 * f + 2];
+  double v0[3], e0[3], e1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v0[k] = (double)verts[3 * (int64_t)ia + k];
+    e0[k] = (double)verts[3 * (int64_t)ib + k] - v0[k];
+    e1[k] = (double)verts[3 * (int64_t)ic + k] - v0[k];
+  }
+  auto dot = [](const double* a, const double* b) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+  };
+  const double d00 = dot(e0, e0), d01 = dot(e0, e1), d11 = dot(e1, e1);
+  const double inv = __ddiv_rn(1.0, __dsub_rn(__dmul_rn(d00, d11), __dmul_rn(d01, d01)));
+  double* o = out + 16 * f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { o[k] = v0[k]; o[3 + k] = e0[k]; o[6 + k] = e1[k]; }
+  o[9] = d00; o[10] = d01; o[11] = d11; o[12] = inv;
+  float* u = reinterpret_cast<float*>(o + 13);
+  u[0] = uv[2 * (int64_t)ia]; u[1] = uv[2 * (int64_t)ia + 1]; u[2] = uv[2 * (int64_t)ib]; u[3] = uv[2 * (int64_t)ib + 1];
+  u[4] = uv[2 * (int64_t)ic]; u[5] = uv[2 * (int64_t)ic + 1];
+}
+
+__device__ __forceinline__ void hit_texel_cached(const double* __restrict__ bary, int64_t tri, float px, float py, float pz, int S,
+                                                 int64_t& t0, int64_t& t1) {
+  const double2* rp = reinterpret_cast<const double2*>(bary + 16 * tri);
+  double q[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { const double2 v = __ldg(rp + k); q[2 * k] = v.x; q[2 * k + 1] = v.y; }
+  const double p[3] = {(double)px, (double)py, (double)pz};
+  double w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = p[k] - q[k];
+  auto dot = [](const double* a, const double* b) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a[0], b[0]), __dmul_rn(a[1], b[1])), __dmul_rn(a[2], b[2]));
+  };
+  const double d00 = q[9], d01 = q[10], d11 = q[11], inv = q[12];
+  const double d02 = dot(q + 3, w), d12 = dot(q + 6, w);
+  double b2 = __dmul_rn(__dsub_rn(__dmul_rn(d00, d12), __dmul_rn(d01, d02)), inv);
+  double b1 = __dmul_rn(__dsub_rn(__dmul_rn(d11, d02), __dmul_rn(d01, d12)), inv);
+  double b0 = __dsub_rn(__dsub_rn(1.0, b1), b2);
+  float c0 = fminf(fmaxf((float)b0, 0.f), 1.f), c1 = fminf(fmaxf((float)b1, 0.f), 1.f), c2 = fminf(fmaxf((float)b2, 0.f), 1.f);
+  float s = __fadd_rn(__fadd_rn(c0, c1), c2);
+  c0 = __fdiv_rn(c0, s); c1 = __fdiv_rn(c1, s); c2 = __fdiv_rn(c2, s);
+  const float* uvp = reinterpret_cast<const float*>(q + 13);
+  float u = __fadd_rn(__fadd_rn(__fmul_rn(uvp[0], c0), __fmul_rn(uvp[2], c1)), __fmul_rn(uvp[4], c2));
+  float v = __fadd_rn(__fadd_rn(__fmul_rn(uvp[1], c0), __fmul_rn(uvp[3], c1)), __fmul_rn(uvp[5], c2));
+  int64_t i0 = (int64_t)floorf(u), i1 = (int64_t)floorf(v);
+  t0 = i0 < 0 ? 0 : (i0 > S - 1 ? S - 1 : i0);
+  t1 = i1 < 0 ? 0 : (i1 > S - 1 ? S - 1 : i1);
+}
+
 __global__ void texture_decode_kernel(TexParams t, const int64_t* __restrict__ idx, int64_t M, float* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= M) return;
@@ -271,8 +330,7 @@ __global__ void texture_compress_kernel(const float* __restrict__ feats, int64_t
 
 // fused shading of compact hit records for qf_render_mesh_baked (render.cu): texel lookup + decode + SG
 template <int LS>   // LS > 0: lobe count known at compile time; 0: generic
-__global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const float* __restrict__ verts,
-                                                          const int32_t* __restrict__ faces, const float* __restrict__ uv,
+__global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const double* __restrict__ bary,
                                                           const float4* __restrict__ hit_pd, const int2* __restrict__ hit_rt,
                                                           const float* __restrict__ viewdirs, const int32_t* __restrict__ d_M,
                                                           float4* __restrict__ out4) {
@@ -284,7 +342,7 @@ __global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const flo
     float4 pd = hit_pd[i];
     int2 rt = hit_rt[i];
     int64_t t0, t1;
-    hit_texel(verts, faces, uv, rt.y, pd.x, pd.y, pd.z, t.size, t0, t1);
+    hit_texel_cached(bary, rt.y, pd.x, pd.y, pd.z, t.size, t0, t1);
     float f[3 + 7 * (LS ? LS : QF_MAX_LOBES) + 1];
     if (LS) decode_record_static<LS ? LS : 1>(t, s_tab, t0 * t.size + t1, f);
     else decode_record(t, s_tab, t0 * t.size + t1, f);
@@ -301,10 +359,23 @@ __global__ void __launch_bounds__(256) baked_shade_kernel(TexParams t, const flo
 int launch_baked_shade(const qf_texture* tex, const qf_mesh* mesh, const float* d_uv, const float4* hit_pd,
                        const int2* hit_rt, const float* d_viewdirs, const int32_t* d_M, float4* out4, cudaStream_t st) {
   TexParams t{tex->d_records, tex->size, tex->num_lobes, tex->record_bytes, tex->colour_logit, tex->lambda_thres, tex->d_tables};
+  // per-triangle barycentric records for this uv array (rebuilt when the array or the vertices change)
+  if (mesh->d_bary == nullptr) {
+    if (cudaMalloc((void**)&mesh->d_bary, sizeof(double) * 16 * (size_t)mesh->n_faces) != cudaSuccess) {
+      set_error("qf_render_mesh_baked: cannot allocate %lld bytes of per-triangle records", (long long)(128 * mesh->n_faces));
+      return QF_ERR_CUDA;
+    }
+    mesh->bary_uv = nullptr;
+  }
+  if (mesh->bary_uv != d_uv || mesh->bary_version != mesh->geometry_version) {
+    bary_setup_kernel<<<(int)ceil_div(mesh->n_faces, 256), 256, 0, st>>>(mesh->d_vertices, mesh->d_faces, d_uv, mesh->n_faces, mesh->d_bary);
+    mesh->bary_uv = d_uv;
+    mesh->bary_version = mesh->geometry_version;
+  }
   switch (tex->num_lobes) {
-    case 3: baked_shade_kernel<3><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
-    case 6: baked_shade_kernel<6><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
-    default: baked_shade_kernel<0><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_vertices, mesh->d_faces, d_uv, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+    case 3: baked_shade_kernel<3><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_bary, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+    case 6: baked_shade_kernel<6><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_bary, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
+    default: baked_shade_kernel<0><<<kNumSMs * 8, 256, 0, st>>>(t, mesh->d_bary, hit_pd, hit_rt, d_viewdirs, d_M, out4); break;
   }
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -339,9 +339,11 @@ __global__ void __launch_bounds__(128) wide_collapse_kernel(const float4* __rest
         else out_ref = kEmptyRef;      // overflow: the ok flag goes down in wide_advance_kernel, the node is never used
       }
     }
-    float4* rec = wnodes + ((int64_t)w * 32 + lane) * 2;
-    rec[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
-    rec[1] = make_float4(hi[1], hi[2], __int_as_float(out_ref), 0.f);
+    if (wnodes) {   // NULL: dry run that only counts the nodes (qf_mesh_create sizes the array with it)
+      float4* rec = wnodes + ((int64_t)w * 32 + lane) * 2;
+      rec[0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+      rec[1] = make_float4(hi[1], hi[2], __int_as_float(out_ref), 0.f);
+    }
   }
 }
 
@@ -539,6 +541,18 @@ __global__ void widen_count_kernel(const int32_t* __restrict__ c, int64_t n, int
   if (i == n) out[n] = 0;
 }
 
+// `wnodes` NULL: dry run (counts the wide nodes into d_wstate[2], capacity = the queue's).
+static int collapse_wide(qf_mesh* m, float4* wnodes, int capacity, cudaStream_t st) {
+  wide_init_kernel<<<1, 1, 0, st>>>(m->d_wstate, m->d_wqueue);
+  for (int lvl = 0; lvl < kWideLevels; ++lvl) {
+    wide_collapse_kernel<<<kNumSMs * 4, 128, 0, st>>>(m->d_tris, (int)m->n_faces, m->d_scene, m->d_left, m->d_right, m->d_first,
+                                                     m->d_last, m->d_ibox, m->d_wqueue, m->d_wstate, capacity, wnodes);
+    wide_advance_kernel<<<1, 1, 0, st>>>(m->d_wstate, capacity);
+  }
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
 static int build(qf_mesh* m, cudaStream_t st) {
   const int64_t F = m->n_faces, V = m->n_vertices;
   int* ob = m->d_flags;  // 6 ints of scratch before flags are needed
@@ -569,15 +583,7 @@ static int build(qf_mesh* m, cudaStream_t st) {
     m->n_nodes = F - 1;
   }
   // wide BVH for coherent packets: level-synchronous collapse, no host synchronisation
-  if (m->d_wnodes) {
-    wide_init_kernel<<<1, 1, 0, st>>>(m->d_wstate, m->d_wqueue);
-    for (int lvl = 0; lvl < kWideLevels; ++lvl) {
-      wide_collapse_kernel<<<kNumSMs * 4, 128, 0, st>>>(m->d_tris, (int)F, m->d_scene, m->d_left, m->d_right, m->d_first, m->d_last,
-                                                       m->d_ibox, m->d_wqueue, m->d_wstate, (int)m->wide_capacity, m->d_wnodes);
-      wide_advance_kernel<<<1, 1, 0, st>>>(m->d_wstate, (int)m->wide_capacity);
-    }
-    QF_LAUNCH_CHECK();
-  }
+  if (m->d_wnodes) return collapse_wide(m, m->d_wnodes, (int)m->wide_capacity, st);
   return QF_OK;
 }
 
@@ -628,10 +634,10 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
   QF_A(dev_alloc(&m->d_call_slots, 4 * kCallSlots, &m->bytes));
   // wide nodes: ~F/22 in practice (leaf nodes hold 17-32 triangles); room for F/8 + 64, the collapse falls back to the
   // binary tree if a pathological mesh needs more.  QF_WIDE_BVH=0 disables the wide tree.
-  if (!(getenv("QF_WIDE_BVH") && atoi(getenv("QF_WIDE_BVH")) == 0)) {
-    m->wide_capacity = (int64_t)(F / 8 + 64);
-    QF_A(dev_alloc(&m->d_wnodes, 64 * (size_t)m->wide_capacity, &m->bytes));
-    QF_A(dev_alloc(&m->d_wqueue, (size_t)m->wide_capacity, &m->bytes));
+  const bool want_wide = !(getenv("QF_WIDE_BVH") && atoi(getenv("QF_WIDE_BVH")) == 0);
+  const int64_t queue_capacity = (int64_t)(F / 4 + 64);      // ints only; the node array is sized after a dry run below
+  if (want_wide) {
+    QF_A(dev_alloc(&m->d_wqueue, (size_t)queue_capacity, &m->bytes));
     QF_A(dev_alloc(&m->d_wstate, 8, &m->bytes));
   }
 #undef QF_A
@@ -644,7 +650,24 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
   cudaError_t e = cudaMemcpyAsync(m->d_faces, d_faces, sizeof(int32_t) * 3 * F, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) { set_error("qf_mesh_create: copy failed: %s", cudaGetErrorString(e)); qf_mesh_destroy(m); return QF_ERR_CUDA; }
-  rc = build(m, st);
+  rc = build(m, st);      // binary tree (d_wnodes is still NULL)
+  if (rc == QF_OK && want_wide) {
+    // dry-run collapse: count the wide nodes, then allocate exactly that (+25 % for vertex updates, which re-collapse
+    // into the same array) instead of a worst-case bound — 1 KB per node
+    rc = collapse_wide(m, nullptr, (int)queue_capacity, st);
+    int32_t h_state[8] = {0};
+    if (rc == QF_OK) {
+      e = cudaMemcpyAsync(h_state, m->d_wstate, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) { set_error("qf_mesh_create: wide collapse failed: %s", cudaGetErrorString(e)); rc = QF_ERR_CUDA; }
+    }
+    if (rc == QF_OK && h_state[3] == 1) {
+      m->wide_capacity = (int64_t)h_state[2] + h_state[2] / 4 + 16;
+      if (m->wide_capacity > queue_capacity) m->wide_capacity = queue_capacity;
+      rc = dev_alloc(&m->d_wnodes, 64 * (size_t)m->wide_capacity, &m->bytes);
+      if (rc == QF_OK) rc = collapse_wide(m, m->d_wnodes, (int)m->wide_capacity, st);
+    }
+  }
   if (rc == QF_OK) {
     e = cudaMemcpyAsync(&m->h_pad, m->d_scene + 6, sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -659,6 +682,7 @@ extern "C" int qf_mesh_update_vertices(qf_mesh* m, const float* d_vertices, void
   QF_REQUIRE(m && d_vertices, "qf_mesh_update_vertices: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
   QF_CUDA_CHECK(cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * m->n_vertices, cudaMemcpyDeviceToDevice, st));
+  ++m->geometry_version;      // per-triangle caches derived from the vertices (baked path) are rebuilt on next use
   int rc = build(m, st);
   if (rc != QF_OK) return rc;
   QF_CUDA_CHECK(cudaMemcpyAsync(&m->h_pad, m->d_scene + 6, sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -669,7 +693,7 @@ extern "C" void qf_mesh_destroy(qf_mesh* m) {
   if (!m) return;
   void* ptrs[] = {m->d_vertices, m->d_faces, m->d_tris, m->d_planes, m->d_nodes, m->d_scene, m->d_keys, m->d_keys_sorted,
                   m->d_idx, m->d_idx_sorted, m->d_left, m->d_right, m->d_parent, m->d_leaf_parent, m->d_first, m->d_last,
-                  m->d_flags, m->d_ibox, m->d_sort_tmp, m->d_call_slots, m->d_wnodes, m->d_wqueue, m->d_wstate};
+                  m->d_flags, m->d_ibox, m->d_sort_tmp, m->d_call_slots, m->d_wnodes, m->d_wqueue, m->d_wstate, m->d_bary};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete m;
 }

@@ -77,6 +77,12 @@ struct qf_mesh {
   size_t bytes = 0;
   float h_pad = 0.f;
   float restart_eps = 0.f;        // > 0: keep hits like the reference's Embree restart loop (qf_mesh_set_restart_eps)
+  // baked path: per-triangle barycentric setup (128 B: v0, e0, e1, d00, d01, d11, 1/den as doubles + the three uv pairs),
+  // built lazily for the uv array of the last baked render and rebuilt when that pointer or the vertices change
+  mutable double* d_bary = nullptr;
+  mutable const float* bary_uv = nullptr;
+  mutable unsigned bary_version = 0;
+  unsigned geometry_version = 1;
 };
 constexpr int kCallSlots = 64;
 

@@ -142,7 +142,8 @@ class MeshRenderer:
         self.device = mesh_intersect.device
         self.K = int(max_hits or mesh_intersect.num_intersections)
         self.delta = float(render_step_size if render_step_size is not None else mesh_intersect.render_step_size)
-        self.uv = _lib.f32(uv, self.device) if uv is not None else None
+        # private copy: the library caches per-triangle records keyed by this buffer's address (include/quadfield.h)
+        self.uv = _lib.f32(uv, self.device).clone() if uv is not None else None
         self._hits = torch.zeros((1,), dtype=torch.int32, device=self.device)
 
     @torch.no_grad()
