@@ -63,8 +63,11 @@ __device__ __forceinline__ int64_t ray_of_thread(int64_t linear, int lane, int i
   return ((gw / tiles) * 4 + (lane >> 3)) * img_w + (gw % tiles) * 8 + (lane & 7);
 }
 
+#ifndef QF_TRACE_MIN_CTAS
+#define QF_TRACE_MIN_CTAS 8   // 64 registers: c2 trace 0.124 -> 0.114 ms (r2 A/B); the K=32 variant is shared-memory limited anyway
+#endif
 template <class HB>
-__global__ void __launch_bounds__(128) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
+__global__ void __launch_bounds__(128, QF_TRACE_MIN_CTAS) trace_compact_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris,
                                                             const float4* __restrict__ planes, const float* __restrict__ scene,
                                                             const float* __restrict__ origins, const float* __restrict__ dirs,
                                                             int64_t ray0, int64_t n, int K, int img_w, int mode,
