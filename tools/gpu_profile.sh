@@ -23,7 +23,7 @@ extra)
   # the other kernels of the north star: baked shading + K=32 traversal on configs[4] (4K, 1.15 M triangles)
   XCMD="python tools/run_leg.py c5 3"
   $XCMD > gpurun_out/plain_extra_$TAG.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'baked_shade_kernel|HitBufSmem' -s 8 -c 4 -o gpurun_out/prof_extra_$TAG $XCMD > gpurun_out/ncu_extra_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'baked_shade_kernel|trace_compact_kernel|composite_rays_kernel' -s 12 -c 3 -o gpurun_out/prof_extra_$TAG $XCMD > gpurun_out/ncu_extra_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_extra_$TAG.log ;;
 train)
   TCMD="python tools/diag_train.py 3"

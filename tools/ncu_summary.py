@@ -15,23 +15,33 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
         "smsp__inst_executed.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg", "l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum",
+        "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 lines = [f"# ncu summary `{tag}`", "",
          "Source: `ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --views 8 "
-         "--no-cpu-baseline` (B200, one GPU).  Per-launch values; cold-cache, serialised — compare shares, not absolutes.", ""]
+         "--no-cpu-baseline --no-train` (configs[1] frame: trace_compact<HitBufReg<8>>, ngp_forward_tc_kernel), `python "
+         "tools/run_leg.py c5 3` (configs[4] 4K baked frame: trace_compact<HitBufSmem>, baked_shade_kernel) and `python "
+         "tools/diag_train.py 3` (training step kernels); B200, one GPU, tools/gpu_profile.sh.  Per-launch values; cold-cache, "
+         "serialised — compare shares, not absolutes.", ""]
 import os
-raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw)))
-if os.path.exists(f"gpurun_out/prof_train_{tag}.ncu-rep"):
-    raw2 = subprocess.run(["ncu", "-i", f"gpurun_out/prof_train_{tag}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows2 = list(csv.reader(io.StringIO(raw2)))
-    if rows2 and rows and rows2[0] == rows[0]:
-        rows += rows2[2:]
 traffic = {}
-if rows:
+seen = set()
+for rep in (f"gpurun_out/prof_{tag}.ncu-rep", f"gpurun_out/prof_extra_{tag}.ncu-rep", f"gpurun_out/prof_train_{tag}.ncu-rep"):
+    if not os.path.exists(rep):
+        continue
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    if len(rows) < 3:
+        continue
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
-    seen = set()
     for r in rows[2:]:
         name = r[idx["Kernel Name"]].split("(")[0]
         if name in seen:
