@@ -326,6 +326,15 @@ int qf_occgrid_march(const qf_occgrid_desc* grid, const uint8_t* d_binaries, con
                      float far_plane, float step_size, float cone_angle, int pass, int32_t* d_counts,
                      const int64_t* d_offsets, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends,
                      void* stream);
+/* The chunked marcher of `render_image_with_occgrid_test` (utils.py:175-350; nerfacc `traverse_grids` with a step limit):
+ * a ray emits at most max_samples samples (0 = no limit) and reports in d_termination (N, may be NULL) the plane where it
+ * stopped — the near plane of the caller's next round; rays with d_ray_mask[i] == 0 (N bytes, NULL = all alive) emit
+ * nothing and keep their plane. */
+int qf_occgrid_march_limited(const qf_occgrid_desc* grid, const uint8_t* d_binaries, const float* d_origins,
+                             const float* d_dirs, int64_t n_rays, const float* d_near_planes, float near_plane,
+                             float far_plane, float step_size, float cone_angle, int pass, int32_t* d_counts,
+                             const int64_t* d_offsets, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends,
+                             int max_samples, const uint8_t* d_ray_mask, float* d_termination, void* stream);
 
 /* Optional per-stage CUDA-event timing of the fused render on its own stream (off by default).
  * qf_profile_read sums {trace, shade, composite} milliseconds recorded since the last read (synchronises). */

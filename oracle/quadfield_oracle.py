@@ -1211,9 +1211,12 @@ def occgrid_cell_scale(aabbs: np.ndarray, resolution) -> np.ndarray:
     return (res / (aabbs[:, 3:] - aabbs[:, :3])).astype(np.float32)
 
 
-def occgrid_march(origins, dirs, binaries, aabbs, near_planes, far_plane, step_size, cone_angle=0.0):
+def occgrid_march(origins, dirs, binaries, aabbs, near_planes, far_plane, step_size, cone_angle=0.0, max_samples=0,
+                  ray_mask=None, return_termination=False):
     """-> (ray_indices int64 (M,), t_starts (M,), t_ends (M,), counts int32 (N,)), ray-major.  fp32, one rounding per
-    operation in the order written (the kernel file is compiled without FMA contraction)."""
+    operation in the order written (the kernel file is compiled without FMA contraction).
+    `max_samples` > 0: a ray stops after that many samples; `ray_mask` (N,) bool: retired rays emit nothing;
+    `return_termination`: a fifth value, the plane (N,) where every ray stopped (utils.py:254-330's chunked marching)."""
     o, d = np.asarray(origins, dtype=np.float32), np.asarray(dirs, dtype=np.float32)
     N = o.shape[0]
     B = np.asarray(binaries).astype(bool)
@@ -1231,6 +1234,12 @@ def occgrid_march(origins, dirs, binaries, aabbs, near_planes, far_plane, step_s
     t = np.fmax(tmin, near).astype(np.float32)
     t_exit = np.fmin(tmax, far).astype(np.float32)
     alive = (tmin <= tmax) & (t < t_exit)
+    term_keep = None
+    if ray_mask is not None:
+        m = np.asarray(ray_mask).astype(bool)
+        term_keep = (~m, near.copy())
+        alive &= m
+    emitted = np.zeros(N, dtype=np.int64)
     rays, starts, ends = [], [], []
     ids = np.arange(N)
     while alive.any():
@@ -1253,6 +1262,9 @@ def occgrid_march(origins, dirs, binaries, aabbs, near_planes, far_plane, step_s
             found |= inside
         rays.append(idx[occ]); starts.append(tt[occ]); ends.append((tt[occ] + dt[occ]).astype(np.float32))
         t[idx] = (tt + dt).astype(np.float32)
+        if max_samples > 0:
+            emitted[idx[occ]] += 1
+            alive[idx[occ][emitted[idx[occ]] == max_samples]] = False
     if rays:
         rays, starts, ends = np.concatenate(rays), np.concatenate(starts), np.concatenate(ends)
         order = np.lexsort((starts, rays))
@@ -1260,4 +1272,54 @@ def occgrid_march(origins, dirs, binaries, aabbs, near_planes, far_plane, step_s
     else:
         rays, starts, ends = np.zeros(0, np.int64), np.zeros(0, np.float32), np.zeros(0, np.float32)
     counts = np.bincount(rays, minlength=N).astype(np.int32)
+    if return_termination:
+        term = t.copy()
+        if term_keep is not None:
+            term[term_keep[0]] = term_keep[1][term_keep[0]]
+        return rays.astype(np.int64), starts, ends, counts, term
     return rays.astype(np.int64), starts, ends, counts
+
+
+def render_image_with_occgrid_test(max_samples, origins, viewdirs, binaries, aabbs, params: NGPParams, near_plane=0.0,
+                                   far_plane=1e10, render_step_size=1e-3, render_bkgd=None, cone_angle=0.0, alpha_thre=0.0,
+                                   early_stop_eps=1e-4):
+    """utils.py:175-350 restated over the oracle's marcher / field / compositing (PARITY UNPINNED like the marcher itself):
+    rounds of at most n_samples = max(min(num_rays // n_alive, 64), min_samples) samples per ray, composited on top of the
+    accumulated opacity, rays retired at opacity > 1 - early_stop_eps or when a round returned fewer than n_samples."""
+    o, d = np.asarray(origins, dtype=np.float32), np.asarray(viewdirs, dtype=np.float32)
+    N = o.shape[0]
+    ot, dt_ = torch.from_numpy(o), torch.from_numpy(d)
+    opacity, depth, rgb = torch.zeros(N, 1), torch.zeros(N, 1), torch.zeros(N, 3)
+    ray_mask = np.ones(N, dtype=bool)
+    min_samples = 1 if cone_angle == 0 else 4
+    iter_samples = total = 0
+    near = np.full(N, near_plane, dtype=np.float32)
+    positions_all = []
+    while iter_samples < max_samples:
+        n_alive = int(ray_mask.sum())
+        if n_alive == 0:
+            break
+        n_samples = max(min(N // n_alive, 64), min_samples)
+        iter_samples += n_samples
+        with np.errstate(all="ignore"):
+            ri, ts, te, counts, term = occgrid_march(o, d, binaries, aabbs, near, far_plane, render_step_size, cone_angle,
+                                                     max_samples=n_samples, ray_mask=ray_mask, return_termination=True)
+        ri_t, ts_t, te_t = torch.from_numpy(ri), torch.from_numpy(ts), torch.from_numpy(te)
+        pos = ot[ri_t] + dt_[ri_t] * (ts_t + te_t)[:, None] / 2.0
+        positions_all.append(pos)
+        if pos.shape[0]:
+            rgbs, sig = ngp_forward(pos, dt_[ri_t], params)
+            w, _, al = render_weight_from_density(ts_t, te_t, sig.squeeze(-1), ray_indices=ri_t, n_rays=N,
+                                                  prefix_trans=1 - opacity[ri_t].squeeze(-1))
+            if alpha_thre > 0:
+                vis = al >= alpha_thre
+                ri_t, rgbs, w, ts_t, te_t = ri_t[vis], rgbs[vis], w[vis], ts_t[vis], te_t[vis]
+            rgb = rgb + accumulate_along_rays(w, rgbs, ri_t, N)
+            opacity = opacity + accumulate_along_rays(w, None, ri_t, N)
+            depth = depth + accumulate_along_rays(w, (ts_t + te_t)[..., None] / 2.0, ri_t, N)
+            total += int(ri_t.shape[0])
+        near = term
+        ray_mask = (opacity.view(-1).numpy() <= 1 - early_stop_eps) & (counts == n_samples)
+    bk = torch.zeros(3) if render_bkgd is None else torch.as_tensor(render_bkgd, dtype=torch.float32)
+    rgb = rgb + bk * (1.0 - opacity)
+    return rgb, opacity, depth, total, (torch.cat(positions_all) if positions_all else torch.zeros(0, 3))

@@ -62,6 +62,7 @@ _SIGS = {
     "qf_field_forward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
     "qf_field_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "qf_occgrid_march": (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P]),
+    "qf_occgrid_march_limited": (_I, [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "qf_triangle_accumulate": (_I, [_P, _P, _P, _L, _L, _P, _P, _P]),
     "qf_vertex_displace_workspace_bytes": (C.c_size_t, [_L]),
     "qf_vertex_displace": (_I, [_P, _P, _P, _L, _L, _F, _P, _P, C.c_size_t, _P]),

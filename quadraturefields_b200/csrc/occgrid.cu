@@ -25,9 +25,16 @@ __global__ void __launch_bounds__(128) occgrid_march_kernel(const OccGrid g, con
                                                             int64_t n, const float* __restrict__ near_planes, float near_plane,
                                                             float far_plane, float step, float cone, int32_t* __restrict__ counts,
                                                             const int64_t* __restrict__ offsets, int64_t* __restrict__ ray_indices,
-                                                            float* __restrict__ t_starts, float* __restrict__ t_ends) {
+                                                            float* __restrict__ t_starts, float* __restrict__ t_ends,
+                                                            int max_samples, const uint8_t* __restrict__ ray_mask,
+                                                            float* __restrict__ termination) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (ray_mask && !ray_mask[i]) {       // a ray the caller has retired: no samples, its plane stays where it was
+    if (!WRITE) counts[i] = 0;
+    if (termination) termination[i] = near_planes ? near_planes[i] : near_plane;
+    return;
+  }
   const float ox = origins[3 * i], oy = origins[3 * i + 1], oz = origins[3 * i + 2];
   const float dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
   const float ix = __fdiv_rn(1.0f, dx), iy = __fdiv_rn(1.0f, dy), iz = __fdiv_rn(1.0f, dz);
@@ -65,9 +72,11 @@ __global__ void __launch_bounds__(128) occgrid_march_kernel(const OccGrid g, con
         ++c;
       }
       t = te;
+      if (max_samples > 0 && c == max_samples) break;     // the caller continues from `termination` in its next round
     }
   }
   if (!WRITE) counts[i] = c;
+  if (termination) termination[i] = t;
 }
 
 }  // namespace qf
@@ -79,6 +88,17 @@ extern "C" int qf_occgrid_march(const qf_occgrid_desc* grid, const uint8_t* d_bi
                                 float far_plane, float step_size, float cone_angle, int pass, int32_t* d_counts,
                                 const int64_t* d_offsets, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends,
                                 void* stream) {
+  return qf_occgrid_march_limited(grid, d_binaries, d_origins, d_dirs, n_rays, d_near_planes, near_plane, far_plane, step_size,
+                                  cone_angle, pass, d_counts, d_offsets, d_ray_indices, d_t_starts, d_t_ends, 0, nullptr, nullptr,
+                                  stream);
+}
+
+extern "C" int qf_occgrid_march_limited(const qf_occgrid_desc* grid, const uint8_t* d_binaries, const float* d_origins,
+                                        const float* d_dirs, int64_t n_rays, const float* d_near_planes, float near_plane,
+                                        float far_plane, float step_size, float cone_angle, int pass, int32_t* d_counts,
+                                        const int64_t* d_offsets, int64_t* d_ray_indices, float* d_t_starts, float* d_t_ends,
+                                        int max_samples, const uint8_t* d_ray_mask, float* d_termination, void* stream) {
+  QF_REQUIRE(max_samples >= 0, "qf_occgrid_march_limited: max_samples=%d", max_samples);
   QF_REQUIRE(grid, "qf_occgrid_march: NULL grid");
   QF_REQUIRE(grid->levels >= 1 && grid->levels <= QF_OCC_MAX_LEVELS, "qf_occgrid_march: levels=%d outside [1,%d]", grid->levels,
              QF_OCC_MAX_LEVELS);
@@ -103,11 +123,13 @@ extern "C" int qf_occgrid_march(const qf_occgrid_desc* grid, const uint8_t* d_bi
   if (pass == 0) {
     QF_REQUIRE(d_counts, "qf_occgrid_march: pass 0 needs d_counts");
     occgrid_march_kernel<false><<<blocks, 128, 0, st>>>(g, d_binaries, d_origins, d_dirs, n_rays, d_near_planes, near_plane, far_plane,
-                                                        step_size, cone_angle, d_counts, nullptr, nullptr, nullptr, nullptr);
+                                                        step_size, cone_angle, d_counts, nullptr, nullptr, nullptr, nullptr, max_samples,
+                                                        d_ray_mask, d_termination);
   } else {
     QF_REQUIRE(d_offsets, "qf_occgrid_march: pass 1 needs d_offsets");
     occgrid_march_kernel<true><<<blocks, 128, 0, st>>>(g, d_binaries, d_origins, d_dirs, n_rays, d_near_planes, near_plane, far_plane,
-                                                       step_size, cone_angle, nullptr, d_offsets, d_ray_indices, d_t_starts, d_t_ends);
+                                                       step_size, cone_angle, nullptr, d_offsets, d_ray_indices, d_t_starts, d_t_ends,
+                                                       max_samples, d_ray_mask, d_termination);
   }
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -72,8 +72,11 @@ class OccGridEstimator(torch.nn.Module):
     # ---- marching -----------------------------------------------------------------------------------------------
     @torch.no_grad()
     def march(self, rays_o: Tensor, rays_d: Tensor, near_planes: Optional[Tensor], near_plane: float, far_plane: float,
-              step_size: float, cone_angle: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
-        """`traverse_grids`: -> (ray_indices (M,), t_starts (M,), t_ends (M,), offsets (N+1,)) ray-major."""
+              step_size: float, cone_angle: float, max_samples: int = 0, ray_mask: Optional[Tensor] = None,
+              return_termination: bool = False):
+        """`traverse_grids`: -> (ray_indices (M,), t_starts (M,), t_ends (M,), offsets (N+1,)) ray-major.
+        `max_samples` > 0 caps the samples per ray, `ray_mask` (N,) bool retires rays, and with `return_termination` a fifth
+        value gives the plane (N,) where every ray stopped (the chunked marching of `render_image_with_occgrid_test`)."""
         lib = _lib.load()
         dev = self.binaries.device
         o, d = _lib.f32(rays_o.reshape(-1, 3), dev), _lib.f32(rays_d.reshape(-1, 3), dev)
@@ -84,11 +87,15 @@ class OccGridEstimator(torch.nn.Module):
         counts = torch.empty((N,), dtype=torch.int32, device=dev)
         offsets = torch.empty((N + 1,), dtype=torch.int64, device=dev)
 
+        mask = ray_mask.to(dev).reshape(-1).to(torch.uint8).contiguous() if ray_mask is not None else None
+        term = torch.empty((N,), dtype=torch.float32, device=dev) if return_termination else None
+
         def launch(p, ri, ts, te):
-            _lib.check(lib.qf_occgrid_march(C.byref(desc), _lib.ptr(binaries), _lib.ptr(o), _lib.ptr(d), N, _lib.ptr(nears),
-                                            float(near_plane), float(far_plane), float(step_size), float(cone_angle), p,
-                                            _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(ri), _lib.ptr(ts), _lib.ptr(te), st),
-                       "qf_occgrid_march")
+            _lib.check(lib.qf_occgrid_march_limited(C.byref(desc), _lib.ptr(binaries), _lib.ptr(o), _lib.ptr(d), N, _lib.ptr(nears),
+                                                    float(near_plane), float(far_plane), float(step_size), float(cone_angle), p,
+                                                    _lib.ptr(counts), _lib.ptr(offsets), _lib.ptr(ri), _lib.ptr(ts), _lib.ptr(te),
+                                                    int(max_samples), _lib.ptr(mask), _lib.ptr(term), st),
+                       "qf_occgrid_march_limited")
         launch(0, None, None, None)
         ws = _lib.workspace(dev, lib.qf_scan_workspace_bytes(N), "scan")
         _lib.check(lib.qf_hits_offsets(_lib.ptr(counts), N, _lib.ptr(offsets), _lib.ptr(ws), ws.numel(), st), "qf_hits_offsets")
@@ -100,6 +107,8 @@ class OccGridEstimator(torch.nn.Module):
         t_ends = torch.empty((M,), dtype=torch.float32, device=dev)
         if M:
             launch(1, ray_indices, t_starts, t_ends)
+        if return_termination:
+            return ray_indices, t_starts, t_ends, offsets, term
         return ray_indices, t_starts, t_ends, offsets
 
     @torch.no_grad()

@@ -479,6 +479,64 @@ def render_image_with_occgrid(radiance_field, estimator, rays: Rays, near_plane:
             sum(n_rendering_samples), extras)
 
 
+@torch.no_grad()
+def render_image_with_occgrid_test(max_samples: int, radiance_field, estimator, rays: Rays, near_plane: float = 0.0,
+                                   far_plane: float = 1e10, render_step_size: float = 1e-3,
+                                   render_bkgd: Optional[torch.Tensor] = None, cone_angle: float = 0.0, alpha_thre: float = 0.0,
+                                   early_stop_eps: float = 1e-4, timestamps=None):
+    """utils.py:175-350 (imported by train_field.py:14): the evaluation render that marches every ray a few samples at a
+    time — `n_samples = max(min(num_rays // n_alive, 64), min_samples)` per round, the marcher capped at that many samples
+    per ray and resumed from its termination planes — composites each round on top of the accumulated opacity
+    (`prefix_trans`), and retires rays whose opacity passed 1 - early_stop_eps or that left the grid.
+    -> (rgb, opacity, depth (un-normalised, :343), total samples, positions of every evaluated sample)."""
+    from .field_rendering import accumulate_along_rays_, render_weight_from_density
+    if timestamps is not None:
+        raise NotImplementedError("dnerf timestamps are not part of the Quadfield scripts")
+    rays, rays_shape, num_rays = _flatten_rays(rays)
+    dev = estimator.binaries.device
+    origins, viewdirs = _lib.f32(rays.origins, dev), _lib.f32(rays.viewdirs, dev)
+    opacity = torch.zeros((num_rays, 1), device=dev)
+    depth = torch.zeros((num_rays, 1), device=dev)
+    rgb = torch.zeros((num_rays, 3), device=dev)
+    ray_mask = torch.ones((num_rays,), dtype=torch.bool, device=dev)
+    min_samples = 1 if cone_angle == 0 else 4              # 1 for synthetic scenes, 4 for real scenes (:229)
+    iter_samples = total_samples = 0
+    near_planes = torch.full((num_rays,), float(near_plane), dtype=torch.float32, device=dev)
+    opc_thre = 1 - early_stop_eps
+    positions_all = []
+    while iter_samples < max_samples:
+        n_alive = int(ray_mask.sum().item())               # the reference synchronises here too (:254)
+        if n_alive == 0:
+            break
+        n_samples = max(min(num_rays // n_alive, 64), min_samples)
+        iter_samples += n_samples
+        ray_indices, t_starts, t_ends, offsets, termination = estimator.march(
+            origins, viewdirs, near_planes, near_plane, far_plane, render_step_size, cone_angle, max_samples=n_samples,
+            ray_mask=ray_mask, return_termination=True)
+        counts = offsets[1:] - offsets[:-1]
+        positions = origins[ray_indices] + viewdirs[ray_indices] * (t_starts + t_ends)[:, None] / 2.0
+        positions_all.append(positions)
+        if positions.shape[0]:
+            rgbs, sigmas = radiance_field(positions, viewdirs, ray_indices=ray_indices)
+            weights, _, alphas = render_weight_from_density(t_starts, t_ends, sigmas.squeeze(-1), ray_indices=ray_indices,
+                                                            n_rays=num_rays, prefix_trans=1 - opacity[ray_indices].squeeze(-1))
+            ri, ts, te = ray_indices, t_starts, t_ends
+            if alpha_thre > 0:
+                vis = alphas >= alpha_thre
+                ri, rgbs, weights, ts, te = ri[vis], rgbs[vis], weights[vis], ts[vis], te[vis]
+            accumulate_along_rays_(weights, values=rgbs, ray_indices=ri, outputs=rgb)
+            accumulate_along_rays_(weights, values=None, ray_indices=ri, outputs=opacity)
+            accumulate_along_rays_(weights, values=(ts + te)[..., None] / 2.0, ray_indices=ri, outputs=depth)
+            total_samples += int(ri.shape[0])
+        near_planes = termination
+        ray_mask = torch.logical_and(opacity.view(-1) <= opc_thre, counts == n_samples)
+    bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else torch.zeros(3, device=dev)
+    rgb = rgb + bk * (1.0 - opacity)
+    pos = torch.cat(positions_all, dim=0) if positions_all else torch.zeros((0, 3), device=dev)
+    return (rgb.view((*rays_shape[:-1], -1)), opacity.view((*rays_shape[:-1], -1)), depth.view((*rays_shape[:-1], -1)),
+            total_samples, pos)
+
+
 def render_image_field_with_occgrid(radiance_field, estimator, rays: Rays, near_plane: float = 0.0, far_plane: float = 1e10,
                                     render_step_size: float = 1e-3, render_bkgd: Optional[torch.Tensor] = None,
                                     cone_angle: float = 0.0, alpha_thre: float = 0.0, test_chunk_size: int = 8192, timestamps=None):

@@ -1193,6 +1193,52 @@ def test_occgrid_marcher_matches_oracle(dev, levels, cone, near):
     assert est.march(e, e, None, 0.0, 1e10, step, 0.0)[0].shape == (0,)
 
 
+def test_chunked_marcher_and_render_image_with_occgrid_test(dev, smoke_scene):
+    """f-1 neighbour `render_image_with_occgrid_test` (utils.py:175-350, imported by train_field.py:14): the marcher with a
+    per-ray sample cap, retired rays and termination planes bit-exact against the oracle's restatement; the chunked render
+    against the oracle's loop (image 2e-3, same sample count) and against the single-pass volumetric render."""
+    from quadraturefields_b200.datasets.utils import Rays
+    from quadraturefields_b200.occ_grid import OccGridEstimator
+    from quadraturefields_b200.utils import render_image_with_occgrid, render_image_with_occgrid_test
+    sc = smoke_scene
+    rng = np.random.RandomState(11)
+    R = 24
+    est = OccGridEstimator([-1.2, -1.2, -1.2, 1.2, 1.2, 1.2], resolution=R, levels=1).to(dev)
+    B = rng.rand(1, R, R, R) < 0.2
+    est.binaries.copy_(torch.from_numpy(B))
+    aabbs = est.aabbs.cpu().numpy()
+    f, cx, cy, W, H = O.pinhole_intrinsics(32, 32, 0.6911)
+    o, d = O.generate_rays(O.look_at_c2w((2.6, 1.7, 1.2)), W, H, f, cx, cy)
+    N = o.shape[0]
+    step = 0.03
+    mask = rng.rand(N) < 0.8
+    nears = (rng.rand(N) * 0.5).astype(np.float32)
+    for cap in (1, 3, 7):
+        with np.errstate(all="ignore"):
+            r_ref, ts_ref, te_ref, cnt_ref, term_ref = O.occgrid_march(o, d, B, aabbs, nears, 1e10, step, 0.0, max_samples=cap,
+                                                                      ray_mask=mask, return_termination=True)
+        r, ts, te, offsets, term = est.march(T(o).to(dev), T(d).to(dev), T(nears).to(dev), 0.0, 1e10, step, 0.0, max_samples=cap,
+                                             ray_mask=T(mask).to(dev), return_termination=True)
+        assert np.array_equal(np.diff(offsets.cpu().numpy()), cnt_ref) and cnt_ref.max() == cap and (cnt_ref[~mask] == 0).all()
+        assert np.array_equal(r.cpu().numpy(), r_ref) and np.array_equal(ts.cpu().numpy(), ts_ref) and np.array_equal(te.cpu().numpy(), te_ref)
+        assert np.array_equal(term.cpu().numpy(), term_ref)
+    rays = Rays(T(o).to(dev), T(d).to(dev))
+    bk = torch.tensor([0.2, 0.5, 0.9])
+    p = oracle_params(sc)
+    for max_samples in (8, 400):
+        rgb, opac, depth, n, pos = render_image_with_occgrid_test(max_samples, sc.radiance_field, est, rays, render_step_size=step,
+                                                                  render_bkgd=bk.to(dev))
+        rgb_r, opac_r, depth_r, n_r, pos_r = O.render_image_with_occgrid_test(max_samples, o, d, B, aabbs, p, render_step_size=step,
+                                                                            render_bkgd=bk)
+        assert n == n_r and pos.shape == pos_r.shape and n > 500
+        assert maxabs(rgb, rgb_r) <= 2e-3 and maxabs(opac, opac_r) <= 2e-3 and maxabs(depth, depth_r) <= 5e-3
+    # enough rounds to finish every ray == the single-pass render up to the early-stop threshold (depth there is normalised)
+    sc.radiance_field.eval()
+    rgb1, opac1, _, _, _ = render_image_with_occgrid(sc.radiance_field, est, rays, render_step_size=step, render_bkgd=bk.to(dev),
+                                                     test_chunk_size=N)
+    assert maxabs(rgb, rgb1) <= 3e-3 and maxabs(opac, opac1) <= 3e-3
+
+
 def test_volumetric_render_and_field_training_with_occgrid(dev, smoke_scene):
     """f-1 end to end: occupancy grid built from the radiance field (`update_every_n_steps`), `render_image_with_occgrid`
     (sampling with visibility culling + nerfacc-style `rendering`) against the oracle's restatement of the same pipeline,
