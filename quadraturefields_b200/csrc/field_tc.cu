@@ -187,8 +187,13 @@ __device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
   return r;
 }
 
+#ifdef QF_TC_MAXNREG   // experiment: cap the registers below what the launch bound implies (room for co-resident kernels)
+#define QF_TC_BOUNDS __maxnreg__(QF_TC_MAXNREG)
+#else
+#define QF_TC_BOUNDS __launch_bounds__(TcCfg<Q, G, CPS>::kThreads, CPS)
+#endif
 template <int Q, int G, int CPS>
-__global__ void __launch_bounds__(TcCfg<Q, G, CPS>::kThreads, CPS) ngp_forward_tc_kernel(const FieldTcArgs a) {
+__global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
   using Cfg = TcCfg<Q, G, CPS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

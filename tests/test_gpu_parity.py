@@ -615,6 +615,33 @@ def test_embree_restart_semantics_on_closely_spaced_shells(dev):
     assert np.array_equal(count_a.cpu().numpy(), np.minimum(cnt_all, K)) and np.array_equal(tri_a.cpu().numpy(), tri_all[:, :K])
 
 
+def test_render_pose_matches_ray_render_and_bands(dev, smoke_scene):
+    """`MeshRenderer.render_pose` (the reference's eval input: a host pose, rays made on the device as by
+    `SubjectLoader.fetch_data`, nerf_synthetic.py:289-378) equals rendering the loader's rays, a (4,4) / tensor pose is
+    accepted, and row bands (what each rank renders of a ray-sharded frame) tile the full frame bit for bit."""
+    from quadraturefields_b200 import parallel as P
+    sc = smoke_scene
+    o, d = sc.rays(1)
+    ref = {k: v.clone() for k, v in sc.render(o, d, image_width=sc.W).items()}
+    out = sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy)
+    assert torch.equal(out["rgb"], ref["rgb"]) and torch.equal(out["opacity"], ref["opacity"]) and torch.equal(out["depth"], ref["depth"])
+    assert int(out["n_hits"]) == int(ref["n_hits"])
+    pose44 = torch.eye(4)
+    pose44[:3, :4] = torch.from_numpy(np.asarray(sc.poses[1], dtype=np.float32))
+    out4 = sc.renderer.render_pose(pose44, sc.W, sc.H, sc.focal, sc.cx, sc.cy)
+    assert torch.equal(out4["rgb"], ref["rgb"])
+    N, W = sc.n_rays, sc.W
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = P.shard_rays(N, r, world, W)
+            band = sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy, rows=(lo // W, hi // W))
+            assert band["rgb"].shape[0] == hi - lo
+            parts.append(torch.cat([band["rgb"], band["opacity"], band["depth"]], dim=1).clone())
+        full = torch.cat(parts)
+        assert torch.equal(full, torch.cat([ref["rgb"], ref["opacity"], ref["depth"]], dim=1))
+
+
 def test_guarded_buffers_and_determinism(dev, smoke_scene):
     """Stand-in for compute-sanitizer (closed on this GPU pool): every output of the hot path is carved out of a larger
     buffer whose borders hold a canary, the kernels run on awkward sizes (1, 31, 33, 127, 129, 257 rays / samples — partial
