@@ -439,10 +439,11 @@ def _hbm_peak():
 
 def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
     """BASELINE configs[3] (`c4`: Shelly-shaped 1080p, 1.15 M triangles, K=32, T=2^21, neural field) and configs[4] (`c5`:
-    baked spherical-Gaussian textures, 4K): ONE frame per step, its rays sharded over the ranks in 4-row bands
-    (`parallel.shard_rays`; the reference renders such frames in 160 000-ray splits on one GPU, train_finetune.py:590-617,
-    test_baking_texture_images.py:355-371), every rank renders its band from the HOST pose (`render_pose`), and the
-    (rgb, opacity, depth) bands are gathered to rank 0 with one NCCL gather per frame INSIDE the timed region.  Strong
+    baked spherical-Gaussian textures, 4K): ONE frame per step, its rays sharded over the ranks in 4-row bands dealt
+    round-robin (`render_pose(bands=...)`; the reference renders such frames in 160 000-ray splits on one GPU,
+    train_finetune.py:590-617, test_baking_texture_images.py:355-371), every rank renders its share from the HOST pose, and
+    the (rgb, opacity, depth) shares are gathered to rank 0 with one NCCL gather per frame and put back into image order
+    INSIDE the timed region.  Strong
     scaling: the frame is fixed, N grows.  Never fails the main line."""
     import ctypes as C
     import torch
@@ -453,31 +454,31 @@ def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
         sc = S.make_scene(name, device=dev, build_field=not baked)
         renderer = sc.baked_renderer if baked else sc.renderer
         N, W, H = sc.n_rays, sc.W, sc.H
-        lo, hi = P.shard_rays(N, rank, world, W)
-        sizes = [b - a for a, b in (P.shard_rays(N, r, world, W) for r in range(world))]
-        rows = (lo // W, hi // W)
-        n = hi - lo
+        # band-cyclic shares: rank r renders the 4-row bands b with b % world == r (the object sits in the middle of the frame:
+        # contiguous bands left the outer ranks idle — N=4, r2i: c4 strong-scaling efficiency 0.61)
+        sizes = [P.band_rows(H, r, world) * W for r in range(world)]
+        n = sizes[rank]
         out = dict(rgb=torch.empty((n, 3), device=dev), opacity=torch.empty((n, 1), device=dev), depth=torch.empty((n, 1), device=dev))
         band = torch.empty((n, 5), device=dev)
-        frame = torch.empty((N, 5), device=dev) if rank == 0 else None
-        recv = ([torch.empty((sz, 5), device=dev) for sz in sizes] if rank == 0 else None) if world > 1 else None
-        if world > 1 and len(set(sizes)) != 1:
-            recv = None                                   # ragged bands: the padding path of parallel.gather_frame
+        even = len(set(sizes)) == 1                       # ragged bands (rows not divisible) take parallel.gather_frame's padding path
+        recv = [torch.empty((sz, 5), device=dev) for sz in sizes] if (world > 1 and even and rank == 0) else None
         hits = torch.zeros((1,), dtype=torch.int32, device=dev)
         steps, warm = max(3, min(args.steps, 10)), 3
         hit_slots = torch.zeros((warm + steps, 1), dtype=torch.int32, device=dev)
 
         def step(i):
-            renderer.render_pose(sc.poses[i % len(sc.poses)], W, H, sc.focal, sc.cx, sc.cy, out=out, hits_out=hit_slots[i], rows=rows)
+            renderer.render_pose(sc.poses[i % len(sc.poses)], W, H, sc.focal, sc.cx, sc.cy, out=out, hits_out=hit_slots[i],
+                                 bands=(rank, world))
             if world > 1:
                 torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1, out=band)
-                if recv is not None or rank != 0:
-                    if len(set(sizes)) == 1:
-                        dist.gather(band, recv, dst=0)
-                    else:
-                        P.gather_frame(band, sizes, dst=0)
+                if even:
+                    dist.gather(band, recv, dst=0)
+                    if rank == 0:
+                        P.assemble_banded(recv, H, W)                       # the frame, rows back in image order
                 else:
-                    P.gather_frame(band, sizes, dst=0)
+                    flat = P.gather_frame(band, sizes, dst=0)
+                    if rank == 0:
+                        P.assemble_banded(torch.split(flat, sizes), H, W)
 
         for i in range(warm):
             step(i)
@@ -504,7 +505,7 @@ def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
         bytes_per_hit = (4 + 6 * L + 36) if baked else 512
         rank_hits = float(hit_slots[warm:].to(torch.int64).sum().item()) / steps
         shade_gbs = bytes_per_hit * rank_hits / (st[1] * 1e-3) / 1e9 if st[1] > 0 else 0.0
-        res = {"config": workload_name(name), "n_gpus": world, "scaling": "strong (one frame, ray bands over the ranks)",
+        res = {"config": workload_name(name), "n_gpus": world, "scaling": "strong (one frame, 4-row bands dealt round-robin over the ranks)",
                "ms_per_frame": ms, "rays_per_frame": N, "rays_per_sec": N / (ms * 1e-3), "hits_per_ray": hits_per_frame / N,
                "samples_per_sec": hits_per_frame / (ms * 1e-3), "steps": steps, "triangles": int(sc.faces_np.shape[0]), "K": sc.K,
                "bvh_bytes": int(sc.mesh_intersect.rayintersector.info()["device_bytes"]),

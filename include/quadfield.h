@@ -344,6 +344,12 @@ int qf_profile_read(double* ms3, int64_t* n_chunks);
 /* a1: eval-mode pinhole rays of one camera (datasets/nerf_synthetic.py:310-360), c2w (3,4) row-major on host */
 int qf_generate_rays(const float* h_c2w, int W, int H, float focal, float cx, float cy, int opengl,
                      float* d_origins, float* d_viewdirs, void* stream);
+/* The same for the band-cyclic share of one rank of a ray-sharded frame: the image is cut into bands of band_rows rows
+ * (H % band_rows == 0) and the rays of the bands b with b % band_stride == band_offset are written compactly, in order
+ * (qf_band_rows(...) rows of W rays).  Bands dealt round-robin balance the ranks: hit counts vary a lot over an image. */
+int64_t qf_band_rows(int H, int band_rows, int band_stride, int band_offset);
+int qf_generate_rays_banded(const float* c2w_3x4, int W, int H, float focal, float cx, float cy, int opengl, int band_rows,
+                            int band_stride, int band_offset, float* d_origins, float* d_viewdirs, void* stream);
 /* a1, training branch (datasets/nerf_synthetic.py:293-309, 341-370): ray i looks through pixel (x[i], y[i]) of camera
  * image_id[i] (NULL = camera 0 for all).  c2w (n_views,3,4) row-major ON THE DEVICE; x, y fp32 (pixel indices, or index +
  * U[0,1) for add_ray_direction_noise).  An id outside [0, n_views) yields a NaN ray. */

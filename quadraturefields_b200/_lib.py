@@ -83,6 +83,8 @@ _SIGS = {
     "qf_profile_enable": (_I, [_I]),
     "qf_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(_L)]),
     "qf_generate_rays": (_I, [C.POINTER(_F), _I, _I, _F, _F, _F, _I, _P, _P, _P]),
+    "qf_band_rows": (_L, [_I, _I, _I, _I]),
+    "qf_generate_rays_banded": (_I, [C.POINTER(_F), _I, _I, _F, _F, _F, _I, _I, _I, _I, _P, _P, _P]),
     "qf_generate_rays_indexed": (_I, [_P, _L, _P, _P, _P, _L, _F, _F, _F, _I, _P, _P, _P]),
 }
 

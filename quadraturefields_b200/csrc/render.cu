@@ -184,12 +184,16 @@ __global__ void composite_rays_kernel(const int32_t* __restrict__ ray_start, con
   depth_out[i] = D;
 }
 
+// band_rows > 0: only the rows y with (y / band_rows) % band_stride == band_offset are generated, compactly and in
+// order — the band-cyclic share of one rank of a ray-sharded frame (n_local_rows of them); 0: the whole image.
 __global__ void generate_rays_kernel(float r00, float r01, float r02, float r10, float r11, float r12, float r20, float r21,
                                      float r22, float tx, float ty, float tz, int W, int H, float focal, float cx, float cy,
-                                     float sgn, float* __restrict__ origins, float* __restrict__ viewdirs) {
+                                     float sgn, float* __restrict__ origins, float* __restrict__ viewdirs, int band_rows,
+                                     int band_stride, int band_offset, int n_local_rows) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)W * H) return;
+  if (i >= (int64_t)W * (band_rows > 0 ? n_local_rows : H)) return;
   int x = (int)(i % W), y = (int)(i / W);  // meshgrid(indexing="xy") flattened row-major (nerf_synthetic.py:311-317)
+  if (band_rows > 0) y = ((y / band_rows) * band_stride + band_offset) * band_rows + y % band_rows;
   float cxd = __fdiv_rn(__fadd_rn(__fsub_rn((float)x, cx), 0.5f), focal);
   float cyd = __fmul_rn(__fdiv_rn(__fadd_rn(__fsub_rn((float)y, cy), 0.5f), focal), sgn);
   float czd = sgn;
@@ -330,7 +334,30 @@ extern "C" int qf_generate_rays(const float* c, int W, int H, float focal, float
   const int64_t n = (int64_t)W * H;
   generate_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10],
                                                                                 c[3], c[7], c[11], W, H, focal, cx, cy,
-                                                                                opengl ? -1.0f : 1.0f, d_origins, d_viewdirs);
+                                                                                opengl ? -1.0f : 1.0f, d_origins, d_viewdirs, 0, 1, 0, H);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+extern "C" int64_t qf_band_rows(int H, int band_rows, int band_stride, int band_offset) {
+  if (H <= 0 || band_rows <= 0 || band_stride <= 0 || band_offset < 0 || band_offset >= band_stride) return -1;
+  int64_t rows = 0;
+  for (int b = band_offset; b * band_rows < H; b += band_stride) rows += (H - b * band_rows) < band_rows ? (H - b * band_rows) : band_rows;
+  return rows;
+}
+
+extern "C" int qf_generate_rays_banded(const float* c, int W, int H, float focal, float cx, float cy, int opengl, int band_rows,
+                                       int band_stride, int band_offset, float* d_origins, float* d_viewdirs, void* stream) {
+  QF_REQUIRE(c && d_origins && d_viewdirs && W > 0 && H > 0, "qf_generate_rays_banded: bad argument");
+  const int64_t rows = qf_band_rows(H, band_rows, band_stride, band_offset);
+  QF_REQUIRE(rows >= 0, "qf_generate_rays_banded: band_rows=%d band_stride=%d band_offset=%d", band_rows, band_stride, band_offset);
+  QF_REQUIRE(H % band_rows == 0, "qf_generate_rays_banded: H=%d is not a multiple of band_rows=%d", H, band_rows);
+  const int64_t n = (int64_t)W * rows;
+  if (n == 0) return QF_OK;
+  generate_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(c[0], c[1], c[2], c[4], c[5], c[6], c[8], c[9], c[10],
+                                                                                c[3], c[7], c[11], W, H, focal, cx, cy,
+                                                                                opengl ? -1.0f : 1.0f, d_origins, d_viewdirs, band_rows,
+                                                                                band_stride, band_offset, (int)rows);
   QF_LAUNCH_CHECK();
   return QF_OK;
 }

@@ -60,6 +60,28 @@ def shard_rays(n_rays: int, rank: int, world_size: int, image_width: int = 0) ->
     return lo, hi
 
 
+def band_rows(height: int, rank: int, world_size: int, band: int = 4) -> int:
+    """Rows of the band-cyclic share of `rank`: the bands b (of `band` rows) with b % world_size == rank."""
+    n_bands = (height + band - 1) // band
+    mine = len(range(rank, n_bands, world_size))
+    rows = mine * band
+    if mine and (n_bands - 1) % world_size == rank:          # the last band may be short
+        rows -= n_bands * band - height
+    return rows
+
+
+def assemble_banded(parts: Sequence[torch.Tensor], height: int, width: int, band: int = 4) -> torch.Tensor:
+    """Inverse of the band-cyclic split: parts[r] is (band_rows(height, r, world) * width, C), rank r's bands in order;
+    -> the (height * width, C) frame.  `height` must be a multiple of `band`."""
+    world = len(parts)
+    n_bands = height // band
+    C = parts[0].shape[1]
+    frame = parts[0].new_empty((n_bands, band * width, C))
+    for r, p in enumerate(parts):
+        frame[r::world] = p.view(-1, band * width, C)
+    return frame.view(height * width, C)
+
+
 def gather_frame(parts: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Optional[torch.Tensor]:
     """Final image gather: rank r contributes `parts` (sizes[r], C); `dst` gets the (sum(sizes), C) frame."""
     rank, ws = world()

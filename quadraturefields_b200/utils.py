@@ -186,12 +186,16 @@ class MeshRenderer:
 
     @torch.no_grad()
     def render_pose(self, c2w, W: int, H: int, focal: float, cx: float, cy: float, bg_color="white", render_bkgd=None, out=None,
-                    hits_out: Optional[torch.Tensor] = None, opengl: bool = True, rows: Optional[tuple] = None):
+                    hits_out: Optional[torch.Tensor] = None, opengl: bool = True, rows: Optional[tuple] = None,
+                    bands: Optional[tuple] = None):
         """The evaluation frame of the reference from its real input: a 3x4 camera-to-world pose on the HOST.  The reference's
         `SubjectLoader.fetch_data` builds the W*H rays on the device from the pose (nerf_synthetic.py:289-378) and the eval
         loop renders them (train_finetune.py:586-617); here: `qf_generate_rays` (the 48-byte pose travels as kernel
         arguments, no host->device copy of rays) into resident scratch, then the fused render.
-        `rows=(r0, r1)` renders only image rows [r0, r1) — a rank's band of a ray-sharded frame.  -> the `render` dict."""
+        `rows=(r0, r1)` renders only image rows [r0, r1) — a rank's contiguous band of a ray-sharded frame.
+        `bands=(rank, world)` renders the rank's band-CYCLIC share instead: the 4-row bands b with b % world == rank, compact
+        and in order (`parallel.assemble_banded` puts the shares back together); hit counts vary a lot over an image, and
+        dealing the bands round-robin balances the ranks.  -> the `render` dict (of the rendered rows only)."""
         lib = _lib.load()
         dev = self.device
         m = np.ascontiguousarray(np.asarray(c2w.cpu() if isinstance(c2w, torch.Tensor) else c2w, dtype=np.float32)[:3, :4])
@@ -202,6 +206,16 @@ class MeshRenderer:
             buf = (key, torch.empty((n, 3), dtype=torch.float32, device=dev), torch.empty((n, 3), dtype=torch.float32, device=dev))
             self._pose_rays = buf
         _, o, d = buf
+        if bands is not None:
+            rank, world = bands
+            n_rows = int(lib.qf_band_rows(H, 4, world, rank))
+            if n_rows < 0 or H % 4:
+                raise ValueError(f"bands={bands}: needs 0 <= rank < world and an image height that is a multiple of 4")
+            _lib.check(lib.qf_generate_rays_banded(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
+                                                   1 if opengl else 0, 4, world, rank, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)),
+                       "qf_generate_rays_banded")
+            o, d = o[:n_rows * W], d[:n_rows * W]
+            return self.render(o, d, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out, image_width=W)
         _lib.check(lib.qf_generate_rays(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
                                         1 if opengl else 0, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)), "qf_generate_rays")
         if rows is not None:

@@ -640,6 +640,14 @@ def test_render_pose_matches_ray_render_and_bands(dev, smoke_scene):
             parts.append(torch.cat([band["rgb"], band["opacity"], band["depth"]], dim=1).clone())
         full = torch.cat(parts)
         assert torch.equal(full, torch.cat([ref["rgb"], ref["opacity"], ref["depth"]], dim=1))
+    # band-cyclic shares (what bench.py's ray-sharded legs use): 4-row bands dealt round-robin, reassembled
+    for world in (2, 5, 8):
+        parts = []
+        for r in range(world):
+            share = sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy, bands=(r, world))
+            assert share["rgb"].shape[0] == P.band_rows(sc.H, r, world) * W
+            parts.append(torch.cat([share["rgb"], share["opacity"], share["depth"]], dim=1).clone())
+        assert torch.equal(P.assemble_banded(parts, sc.H, W), torch.cat([ref["rgb"], ref["opacity"], ref["depth"]], dim=1))
 
 
 def test_guarded_buffers_and_determinism(dev, smoke_scene):

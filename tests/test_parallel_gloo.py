@@ -76,6 +76,21 @@ def test_sharding_covers_every_ray_once():
     assert views == list(range(200))
 
 
+def test_band_cyclic_split_and_assembly():
+    """Band-cyclic frame sharding (bench.py c4 / c5 legs): every row belongs to exactly one rank, shares reassemble."""
+    for H, W in ((1080, 16), (2160, 8), (48, 48), (100, 4)):
+        rows = torch.arange(H).view(H, 1).expand(H, W).reshape(-1, 1).float()
+        for ws in (1, 2, 3, 4, 8):
+            sizes = [P.band_rows(H, r, ws) for r in range(ws)]
+            assert sum(sizes) == H and max(sizes) - min(sizes) <= 4
+            parts = []
+            for r in range(ws):
+                mine = [y for y in range(H) if (y // 4) % ws == r]
+                assert len(mine) == sizes[r]
+                parts.append(rows.view(H, W)[mine].reshape(-1, 1))
+            assert torch.equal(P.assemble_banded(parts, H, W), rows)
+
+
 def test_reference_arm_under_torchrun_prints_one_line():
     """`bench.py --impl reference` launched the way the driver launches N>1 arms: rank 0 alone measures and prints the
     JSON line (impl, metric, cpu_baseline, e2e with zero copy bytes), the other rank exits 0 without work."""
