@@ -392,25 +392,17 @@ __global__ void __launch_bounds__(128) encode_sum_kernel(const qf_grid_desc desc
   out[i] = acc;
 }
 
-// diagnostic: the same gather as a persistent grid of `blocks_per_sm` x 148 CTAs (occupancy sweep), plain or software-
-// pipelined encode
-template <int PIPE>
+// diagnostic (tools/diag_gather_occ.py): the same gather as a persistent grid of `blocks_per_sm` x 148 CTAs — occupancy /
+// CTA-shape / shared-memory carve-out sweeps
 __global__ void __launch_bounds__(1024) encode_sum_persist_kernel(const qf_grid_desc desc, const __half2* __restrict__ table,
-                                                                 const float* __restrict__ x01, int64_t M, float* __restrict__ out) {
+                                                                  const float* __restrict__ x01, int64_t M, float* __restrict__ out) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < ((M + 31) & ~31ll); i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i < M ? i : M - 1;
     float acc = 0.f;
-    if (PIPE) {
-      encode_point_pipelined(desc, table, x01[3 * j], x01[3 * j + 1], x01[3 * j + 2], [&](int l, uint32_t e, uint32_t o) {
-        float2 f = __half22float2(*reinterpret_cast<__half2*>(&e)), g = __half22float2(*reinterpret_cast<__half2*>(&o));
-        acc += f.x + f.y + g.x + g.y;
-      });
-    } else {
-      encode_point(desc, table, x01[3 * j], x01[3 * j + 1], x01[3 * j + 2], [&](int l, uint32_t h2) {
-        float2 f = __half22float2(*reinterpret_cast<__half2*>(&h2));
-        acc += f.x + f.y;
-      });
-    }
+    encode_point(desc, table, x01[3 * j], x01[3 * j + 1], x01[3 * j + 2], [&](int l, uint32_t h2) {
+      float2 f = __half22float2(*reinterpret_cast<__half2*>(&h2));
+      acc += f.x + f.y;
+    });
     if (i < M) out[i] = acc;
   }
 }
@@ -518,11 +510,9 @@ extern "C" int qf_debug_encode_sum(const qf_ngp* f, const float* d_x01, int64_t 
   if (M == 0) return QF_OK;
   const int bps = getenv("QF_DEBUG_ENC_BLOCKS_PER_SM") ? atoi(getenv("QF_DEBUG_ENC_BLOCKS_PER_SM")) : 0;
   if (bps > 0) {
-    const bool pipe = getenv("QF_DEBUG_ENC_PIPE") && atoi(getenv("QF_DEBUG_ENC_PIPE"));
     const int thr = getenv("QF_DEBUG_ENC_THREADS") ? atoi(getenv("QF_DEBUG_ENC_THREADS")) : 128;
     const int smem = getenv("QF_DEBUG_ENC_SMEM") ? atoi(getenv("QF_DEBUG_ENC_SMEM")) : 0;
-    if (pipe) encode_sum_persist_kernel<1><<<kNumSMs * bps, thr, smem, (cudaStream_t)stream>>>(f->desc, f->d_table, d_x01, M, d_out);
-    else encode_sum_persist_kernel<0><<<kNumSMs * bps, thr, smem, (cudaStream_t)stream>>>(f->desc, f->d_table, d_x01, M, d_out);
+    encode_sum_persist_kernel<<<kNumSMs * bps, thr, smem, (cudaStream_t)stream>>>(f->desc, f->d_table, d_x01, M, d_out);
     QF_LAUNCH_CHECK();
     return QF_OK;
   }

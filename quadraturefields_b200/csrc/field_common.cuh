@@ -126,41 +126,6 @@ __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half
     if (two) store(l + 1, level_blend(c1, v1));
   }
 }
-// Software-pipelined variant for gather-only warps (field_tc.cu): the 8 gathers of level l+1 are issued BEFORE
-// level l is blended, so a warp always has loads queued in the L1TEX pipe while it does its index / blend arithmetic (with
-// encode_point the two phases alternate, and warps fall into a convoy: ncu r2c showed issue 53 % + L1 wavefront pipe 63 %
-// busy, i.e. almost no overlap).  Same arithmetic, bit-identical output; costs 11 more live registers.
-struct LevelLoad { __half2 v[8]; float fx, fy, fz; };
-
-__device__ __forceinline__ void level_issue(const qf_grid_desc& d, int l, const __half2* __restrict__ table, float x, float y,
-                                            float z, LevelLoad& o) {
-  Corner8 c;
-  level_indices(d, l, x, y, z, c);
-  load_corners(d, l, table, c, o.v);
-  o.fx = c.fx; o.fy = c.fy; o.fz = c.fz;
-}
-__device__ __forceinline__ uint32_t level_finish(const LevelLoad& o) {
-  Corner8 c;
-  c.fx = o.fx; c.fy = o.fy; c.fz = o.fz;
-  return level_blend(c, o.v);
-}
-
-template <typename Store2>   // store2(l_even, h2_even, h2_odd) once per level pair; n_levels must be even
-__device__ __forceinline__ void encode_point_pipelined(const qf_grid_desc& d, const __half2* __restrict__ table, float x, float y,
-                                                       float z, Store2 store2) {
-  const int L = d.n_levels;
-  LevelLoad a, b;
-  level_issue(d, 0, table, x, y, z, a);
-#pragma unroll 1
-  for (int l = 0; l < L; l += 2) {
-    level_issue(d, l + 1, table, x, y, z, b);
-    const uint32_t e = level_finish(a);
-    if (l + 2 < L) level_issue(d, l + 2, table, x, y, z, a);
-    const uint32_t o = level_finish(b);
-    store2(l, e, o);
-  }
-}
-
 // backward of one level: scatter the gradient of its two features to the 8 corners (fp32 atomics)
 __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
                                               float z, float g0, float g1) {

@@ -145,12 +145,6 @@ struct FieldTcArgs {
 
 // ---- roles and resources
 // Q gather quads (4 warps each) + G MLP warpgroups per CTA, CPS CTAs per SM.  TMEM: G x 96 pipeline columns, then Q x 40.
-#ifndef QF_TC_PIPELINED
-#define QF_TC_PIPELINED 0
-#endif
-#ifndef QF_TC_DEBUG
-#define QF_TC_DEBUG 0
-#endif
 #ifndef QF_TC_QUADS
 #define QF_TC_QUADS 3
 #endif
@@ -187,13 +181,8 @@ __device__ __forceinline__ uint32_t pack_relu_h2(float lo, float hi) {
   return r;
 }
 
-#ifdef QF_TC_MAXNREG   // experiment: cap the registers below what the launch bound implies (room for co-resident kernels)
-#define QF_TC_BOUNDS __maxnreg__(QF_TC_MAXNREG)
-#else
-#define QF_TC_BOUNDS __launch_bounds__(TcCfg<Q, G, CPS>::kThreads, CPS)
-#endif
 template <int Q, int G, int CPS>
-__global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
+__global__ void __launch_bounds__(TcCfg<Q, G, CPS>::kThreads, CPS) ngp_forward_tc_kernel(const FieldTcArgs a) {
   using Cfg = TcCfg<Q, G, CPS>;
   extern __shared__ __align__(1024) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -257,19 +246,7 @@ __global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
         dy = ((__ldg(dp + 1) + 1.0f) / 2.0f) * 2.0f - 1.0f;
         dz = ((__ldg(dp + 2) + 1.0f) / 2.0f) * 2.0f - 1.0f;
       }
-      // 16 levels in pairs, software-pipelined: the next level's 8 gathers are issued before this one is blended; each
-      // pair writes 2 TMEM columns of the row
-#if QF_TC_DEBUG == 2   // timing experiment: no table gathers (MLP side alone)
-#pragma unroll 1
-      for (int l = 0; l < 16; l += 2) tmem_st2(t_a1 + l, __float_as_uint(x) + l, __float_as_uint(y));
-#elif QF_TC_DEBUG == 4   // timing experiment: DEBUG 3 without the TMEM stores
-      uint32_t dbg_acc = 0;
-      encode_point_pipelined(a.desc, a.table, x, y, z, [&](int l, uint32_t even, uint32_t odd) { dbg_acc += even ^ odd; });
-      if (a.out4 && valid) reinterpret_cast<uint32_t*>(a.out4)[4 * i] = dbg_acc;
-#else
-#if QF_TC_PIPELINED
-      encode_point_pipelined(a.desc, a.table, x, y, z, [&](int l, uint32_t even, uint32_t odd) { tmem_st2(t_a1 + l, even, odd); });
-#else
+      // 16 levels, two per trip: the pair's gathers are in flight together; each trip writes 2 TMEM columns of the row
       {
         uint32_t even = 0;
         encode_point(a.desc, a.table, x, y, z, [&](int l, uint32_t h2) {
@@ -277,25 +254,17 @@ __global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
           else even = h2;
         });
       }
-#endif
-#endif
       {
         float sh[16];
         sh4(dx, dy, dz, sh);
         uint32_t shp[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) shp[q] = pack_h2(sh[2 * q], sh[2 * q + 1]);
-#if QF_TC_DEBUG < 3   // 3: timing experiment, gather warps alone with no hand-over at all
         if (k > 0) {
           mbar_wait(bar_empty + quad * 8, (k - 1) & 1);     // layer 3 of this quad's previous tile has read the SH columns
           tc_fence_after();
         }
-#endif
-#if QF_TC_DEBUG == 4
-        if (a.out4 && valid) reinterpret_cast<uint32_t*>(a.out4)[4 * i + 1] = shp[0] ^ shp[1] ^ shp[2] ^ shp[3] ^ shp[4] ^ shp[5] ^ shp[6] ^ shp[7];
-#else
         tmem_st8(tmem_base + lane_bits + sh_col(quad), shp);
-#endif
       }
       const unsigned selmask = __ballot_sync(0xffffffffu, sel);
       if (lane == 0) s_sel[idx * 4 + sub] = selmask;
@@ -318,12 +287,7 @@ __global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
     // B descriptors: chunk j (16 k-values = two 8x8 core matrices) of a (N x K) K-major canonical image
     auto bdesc = [&](int w_off, int K, int j) { return umma_desc(sW + w_off + j * 256, 128, (K >> 3) * 128); };
     uint32_t phase = 0;
-#if QF_TC_DEBUG >= 3
-    if (a.out4 && blockIdx.x == 0 && row == 0) a.out4[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t n = group; false; n += G) {
-#else
     for (int64_t n = group; ; n += G) {
-#endif
       const int64_t tile = blockIdx.x + n * gridDim.x;
       if (tile >= n_tiles) break;
       const int quad = (int)(n % Q), kq = (int)(n / Q), slot = kq & 1, idx = quad * 2 + slot;
@@ -331,11 +295,6 @@ __global__ void QF_TC_BOUNDS ngp_forward_tc_kernel(const FieldTcArgs a) {
       tc_fence_after();
       const bool sel = (s_sel[idx * 4 + (row >> 5)] >> (row & 31)) & 1u;
       const uint32_t c_a1 = tmem_base + a1_col(quad, slot), c_sh = tmem_base + sh_col(quad);
-#if QF_TC_DEBUG == 1   // timing experiment: no MLP (gather side alone): free the slot at once
-      if (leader) { umma_f16_ts(pipe + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u); umma_commit(bar_empty + quad * 8); }
-      { const int64_t i = tile * 128 + row; if (i < M && a.out4) a.out4[i] = make_float4(0.f, 0.f, 0.f, sel ? 1.f : 0.f); }
-      continue;
-#endif
       // ---- base L1: R = A1 (K=32) * W1^T
       if (leader) {
         umma_f16_ts(pipe + kColR, c_a1, bdesc(kTcW1, 32, 0), id64, 0u);

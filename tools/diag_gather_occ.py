@@ -35,7 +35,7 @@ e1.record(); torch.cuda.synchronize()
 print("blocks/SM=%s threads=%s smem=%s pipe=%s: %d hits, gather %.3f ms" % (os.environ.get("QF_DEBUG_ENC_BLOCKS_PER_SM"), os.environ.get("QF_DEBUG_ENC_THREADS"), os.environ.get("QF_DEBUG_ENC_SMEM"), os.environ.get("QF_DEBUG_ENC_PIPE", "0"), M, e0.elapsed_time(e1) / 20), flush=True)
 '''
 # arguments: "<blocks per SM>[:<threads per block>[:<dynamic smem bytes>]]"
-for pipe in ("0", "1"):
+for pipe in ("0",):
     for arg in sys.argv[1:] or ["4", "5", "6", "8", "10", "12", "16"]:
         bps, _, rest = arg.partition(":")
         thr, _, smem = rest.partition(":")
