@@ -140,8 +140,11 @@ constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4
 // FEAT = false: backward of the full forward (rgb, sigma).  FEAT = true: backward of `query_density(return_feat=True)`
 // — the upstream gradient arrives at the 16 outputs of the base MLP (sigma and the 15 geo features), the tcnn head is
 // not part of the graph (the spherical-Gaussian field feeds the features to a torch decoder instead).
+#ifndef QF_BWD_MIN_CTAS
+#define QF_BWD_MIN_CTAS 3
+#endif
 template <bool FEAT>
-__global__ void __launch_bounds__(128, 3) ngp_backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(128, QF_BWD_MIN_CTAS) ngp_backward_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* s_w = reinterpret_cast<__half*>(smem_raw);
   __half* s_wt = s_w + kWTotal;
