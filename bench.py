@@ -727,10 +727,15 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     O_all, D_all = torch.stack([p[0] for p in pool]), torch.stack([p[1] for p in pool])        # (V, N, 3)
     rf = sc.radiance_field
     params = [rf.mlp_base.params, rf.mlp_head.params]
-    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15, fused=True)
+    # QF_TRAIN_GRAPH=1 replays the step from CUDA graphs (utils.GraphedTrainStep).  Off by default: measured r2 on 2^18 rays,
+    # 1.60 ms graphed against 1.52 ms eager — the step is GPU-bound (ngp_backward_kernel 0.63 ms + the next batch's refill
+    # trace 0.45 ms sharing the SMs from its side stream), not host-bound, and the fixed capacity adds 8-11 % padding samples
+    use_graph = os.environ.get("QF_TRAIN_GRAPH", "0") != "0"
+    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15, fused=True, capturable=use_graph)
     steps, warm = max(5, min(args.steps, 20)), 8      # warm-up also fills the side stream's allocator pool
+    extra = 3 if use_graph else 0                    # graph replays between the eager warm-up and the timed region
     batches = []
-    for i in range(steps + warm + 2):
+    for i in range(steps + warm + extra + 2):
         vi = torch.randint(0, n_views, (n,), device=dev, generator=g)
         pi = torch.randint(0, sc.n_rays, (n,), device=dev, generator=g)
         batches.append((O_all[vi, pi].contiguous(), D_all[vi, pi].contiguous(), torch.rand((n, 3), device=dev, generator=g)))
@@ -738,15 +743,27 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     # DataLoader workers run ahead the same way); every step still performs exactly one trace (of the batch after next)
     pf = HitTuplePrefetcher(sc.mesh_intersect, ring=4)       # tuples in 4 recycled buffer sets: no allocator calls per step
 
+    gs = None            # utils.GraphedTrainStep once captured (after the eager warm-up has shown how many hits a batch has)
+
     def step(i):
         o, d, target = batches[i]
         tup = pf.get()
-        opt.zero_grad(set_to_none=False)
-        rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d, tup=tup)
-        loss = torch.nn.functional.smooth_l1_loss(rgb, target)
-        loss.backward()
-        P.all_reduce_gradients(params, n, n * world)
-        opt.step()
+        done = False
+        if gs is not None:
+            try:
+                gs.load(tup, d, target)
+                gs.step()
+                n_hits, done = gs.n_hits, True
+            except OverflowError:
+                pass                                     # more hits than the captured capacity: this batch runs eagerly
+        if not done:
+            opt.zero_grad(set_to_none=False)
+            rgb, _, _, n_hits = render_train(sc.mesh_intersect, rf, o, d, tup=tup)
+            loss = torch.nn.functional.smooth_l1_loss(rgb, target)
+            loss.backward()
+            P.all_reduce_gradients(params, n, n * world)
+            opt.step()
+            rf.mark_parameters_changed()                 # (a capturable Adam does not bump the version counters)
         pf.submit(batches[i + 2][0], batches[i + 2][1], rays_ready=True)
         return n_hits
 
@@ -755,27 +772,46 @@ def run_train_steps(args, sc, dev, rank, world, barrier):
     rf.accumulate_grad_in_place = True          # backward adds into .grad directly (no 50 MB zero buffer + autograd add per step)
     pf.submit(batches[0][0], batches[0][1], rays_ready=True)
     pf.submit(batches[1][0], batches[1][1], rays_ready=True)
-    for i in range(warm):
-        step(i)
+    warm_hits = [step(i) for i in range(warm)]
+    graph_info = None
+    if use_graph:
+        # the step as two CUDA graphs on fixed-capacity, dummy-padded buffers (utils.GraphedTrainStep): capacity = 8 % above
+        # the largest warm-up batch; a batch that still exceeds it falls back to the eager step
+        try:
+            from quadraturefields_b200.utils import GraphedTrainStep
+            cap = (int(max(warm_hits) * 1.08) + 32767) // 32768 * 32768
+            reduce = (lambda: P.all_reduce_gradients(params, n, n * world)) if world > 1 else None
+            g = GraphedTrainStep(rf, opt, n, cap, sc.mesh_intersect.render_step_size, all_reduce=reduce)
+            tup0 = sc.mesh_intersect.sampling_raytrace(batches[0][1], batches[0][0])
+            g.load(tup0, batches[0][1], batches[0][2])
+            g.capture()
+            gs = g
+            graph_info = {"capacity": cap, "dummy_rays": g.D}
+        except Exception as e:
+            graph_info = {"error": f"{type(e).__name__}: {e}"}
+        for i in range(extra):                       # replays (or eager steps, had the capture failed) outside the timed region
+            step(warm + i)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0.record()
     hits = 0
     for i in range(steps):
-        hits += step(warm + i)
+        hits += step(warm + extra + i)
     e1.record()
     barrier()
     mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs
     rf.accumulate_grad_in_place = False
+    rf.mark_parameters_changed()
     ms = P.max_over_ranks(e0.elapsed_time(e1), dev)
     n_params = sum(p_.numel() for p_ in params)
     return {"metric": "rays_per_sec_train_fwd_bwd", "value": n * world * steps / (ms * 1e-3), "unit": "rays/s", "ms_per_step": ms / steps,
             "cuda_mallocs_in_timed_region": mallocs,
             "steps": steps, "rays_per_step_per_gpu": n, "hits_per_ray": hits / (n * steps), "params": n_params,
-            "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0,
+            "allreduce_bytes_per_step": 4 * n_params if world > 1 else 0, "cuda_graph": graph_info,
             "includes": "trace (of the batch after next, side stream) + field fwd + composite + loss + field/composite bwd + grad all-reduce "
-                        "+ fused Adam step"}
+                        "+ fused Adam step" + ("; fwd/loss/bwd and the Adam step replayed from two CUDA graphs on fixed-capacity, "
+                                               "dummy-padded hit buffers" if (graph_info and "error" not in graph_info) else "")}
 
 
 if __name__ == "__main__":

@@ -224,6 +224,12 @@ class NGPRadianceField(nn.Module):
         self._handle_key = key
         return self._handle
 
+    def mark_parameters_changed(self):
+        """The parameters were modified behind Python's tensor version counters (a CUDA-graph replay of the optimiser step):
+        the next use refreshes the fp16 working copies."""
+        if self._handle_key is not None:
+            self._handle_key = self._handle_key[:2] + (-1, -1) + self._handle_key[4:]
+
     def _free(self):
         if getattr(self, "_handle", None) is not None:
             _lib.load().qf_ngp_destroy(self._handle)

@@ -397,6 +397,119 @@ def render_train(mesh_intersect, radiance_field, origins, viewdirs, bg_color="wh
     return rgb, opacity, depth_img, points.shape[0]
 
 
+class GraphedTrainStep:
+    """The optimiser step of the mesh-path training loop (train_finetune.py:494-531 with scaling=0: field at the hits ->
+    derive_properties -> smooth-L1 against the pixels -> backward into the hash table and the MLPs -> Adam) replayed from
+    two CUDA graphs instead of ~60 Python-driven launches: [zero_grad, forward, loss, backward] and [optimizer.step], with
+    the gradient all-reduce (if any) issued eagerly between them.
+
+    The obstacle to capturing the step is the data-dependent hit count M.  Everything runs on buffers of a fixed capacity C
+    instead: the hits of the batch fill [0, M), the tail [M, C) holds dummy hits (origin of the field's box, depth 0) that
+    belong to `n_dummy` extra rays N, N+1, ... of at most 8 hits each, whose colours reach no loss term — their gradient
+    is exactly zero, the table scatter skips zero gradients and the weight-gradient GEMM adds zeros — so every kernel sees
+    static shapes and the result equals the eager step on the M real hits.  `load()` (eager: a handful of copies) moves a
+    traced tuple into the static buffers; a batch with more than C hits raises `OverflowError` (run it eagerly).
+
+    `optimizer` must be capturable (`torch.optim.Adam(..., fused=True, capturable=True)`) and the parameters must already
+    own `.grad` tensors; `radiance_field.accumulate_grad_in_place = True` is set."""
+
+    def __init__(self, radiance_field, optimizer, n_rays: int, capacity: int, render_step_size: float, bg_color="white",
+                 all_reduce=None):
+        dev = radiance_field.aabb.device
+        self.rf, self.opt, self.N, self.C, self.dev = radiance_field, optimizer, int(n_rays), int(capacity), dev
+        self.delta, self.bg, self.all_reduce = float(render_step_size), _lib.BG_MODES.get(bg_color, 2), all_reduce
+        self.D = (self.C + 7) // 8 + 1                                  # dummy rays: enough for an all-padding batch
+        N, C, D = self.N, self.C, self.D
+        self.points = torch.zeros((C, 3), device=dev)
+        self.depth = torch.zeros((C,), device=dev)
+        self.index_ray = torch.full((C,), N, dtype=torch.int64, device=dev)
+        self.offsets = torch.zeros((N + D + 1,), dtype=torch.int64, device=dev)
+        self.viewdirs = torch.zeros((N + D, 3), device=dev)
+        self.viewdirs[N:, 2] = 1.0
+        self.target = torch.zeros((N, 3), device=dev)
+        self.loss = torch.zeros((), device=dev)
+        self._pad_ray = N + torch.arange(C, device=dev) // 8             # ray of padding slot j (relative to M): N + j // 8
+        self._pad_off = 8 * torch.arange(D + 1, device=dev)
+        self.g_fb = self.g_opt = None
+        radiance_field.accumulate_grad_in_place = True
+
+    @torch.no_grad()
+    def load(self, tup, viewdirs, target):
+        """Copy a hit tuple (`MeshIntersection.sampling_raytrace` / the prefetcher), the batch's view directions (N,3) and
+        target colours (N,3) into the static buffers and pad the tail."""
+        N, C = self.N, self.C
+        M = 0 if tup is None else int(tup[0].shape[0])
+        if M > C:
+            raise OverflowError(f"{M} hits exceed the captured capacity {C}")
+        if M:
+            self.points[:M].copy_(tup[0]); self.index_ray[:M].copy_(tup[2]); self.depth[:M].copy_(tup[3])
+            self.offsets[:N + 1].copy_(tup.offsets)
+        else:
+            self.offsets[:N + 1].zero_()
+        if M < C:
+            self.points[M:].zero_(); self.depth[M:].zero_()
+            self.index_ray[M:].copy_(self._pad_ray[:C - M])
+        self.offsets[N:].copy_(torch.clamp(self._pad_off + M, max=C))
+        self.viewdirs[:N].copy_(viewdirs)
+        self.target.copy_(target)
+        self.n_hits = M
+
+    def _forward_backward(self):
+        N = self.N
+        self.opt.zero_grad(set_to_none=False)
+        # the previous replay's optimiser step changed the parameters without touching Python's version counters (and a
+        # capturable fused Adam does not bump them even when run eagerly): refresh the fp16 working copies explicitly, so
+        # that the refresh kernels are part of the captured forward
+        self.rf.mark_parameters_changed()
+        rgbs, sigmas = self.rf(self.points, self.viewdirs, ray_indices=self.index_ray)
+        rgb, _, _, _ = _DerivePropertiesFn.apply(_lib.f32(rgbs), _lib.f32(sigmas.reshape(-1)), self.depth, self.delta, self.offsets,
+                                                 N + self.D, self.bg, None)
+        loss = torch.nn.functional.smooth_l1_loss(rgb[:N], self.target)
+        loss.backward()
+        self.loss.copy_(loss.detach())
+
+    def capture(self, warmup: int = 3):
+        """Warm the step up on a side stream (allocations, lazily created kernel attributes), then capture the two graphs.
+        The static buffers must hold a valid batch (`load`).  Parameters and optimiser state are restored afterwards (in
+        place: the graphs hold their addresses), so capturing does not advance the training."""
+        dev = self.dev
+        params = [p for g in self.opt.param_groups for p in g["params"]]
+        p_snap = [p.detach().clone() for p in params]
+        s_snap = {id(p): {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self.opt.state.get(p, {}).items()} for p in params}
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._forward_backward()
+                if self.all_reduce is not None:
+                    self.all_reduce()
+                self.opt.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.g_fb, self.g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fb):
+            self._forward_backward()
+        with torch.cuda.graph(self.g_opt, pool=self.g_fb.pool()):
+            self.opt.step()
+        with torch.no_grad():
+            for p, p0 in zip(params, p_snap):
+                p.copy_(p0)
+                for k, v in self.opt.state.get(p, {}).items():
+                    if isinstance(v, torch.Tensor):
+                        old = s_snap[id(p)].get(k)
+                        v.copy_(old) if isinstance(old, torch.Tensor) else v.zero_()
+        self.rf.mark_parameters_changed()
+
+    def step(self):
+        """Replay one optimiser step on the loaded batch.  -> the loss (a device scalar that the next step overwrites)."""
+        self.g_fb.replay()
+        if self.all_reduce is not None:
+            self.all_reduce()
+        self.g_opt.replay()
+        self.rf.mark_parameters_changed()   # the graph moved the parameters behind Python's version counters: the next eager
+        return self.loss                    # use of the field must refresh its fp16 working copies
+
+
 def field_training_batch(mesh_intersect, radiance_field, origins, viewdirs, tup=_NO_TUPLE):
     """The no-grad half of a quadrature-field training step (train_field.py:313-344): sample positions along the rays,
     the frozen radiance field's near-to-far and far-to-near weights at them (`rendering_field`, utils.py:431-446) and the

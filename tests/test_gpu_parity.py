@@ -650,6 +650,71 @@ def test_render_pose_matches_ray_render_and_bands(dev, smoke_scene):
         assert torch.equal(P.assemble_banded(parts, sc.H, W), torch.cat([ref["rgb"], ref["opacity"], ref["depth"]], dim=1))
 
 
+def test_graphed_train_step_matches_eager(dev):
+    """`utils.GraphedTrainStep` (the training step replayed from CUDA graphs on fixed-capacity, dummy-padded buffers) against
+    the eager step (`render_train` + smooth-L1 + backward + Adam) from the same initial parameters and the same batches:
+    identical losses and parameters after several steps (the padding hits contribute exactly zero), an eager render
+    afterwards sees the updated field, and a batch beyond the capacity is refused."""
+    from quadraturefields_b200 import scene
+    from quadraturefields_b200.utils import GraphedTrainStep, render_train
+    torch.manual_seed(0)
+    runs = []
+    batches = None
+    for graphed in (False, True):
+        sc = scene.make_scene("smoke", device=dev)
+        rf, mi = sc.radiance_field, sc.mesh_intersect
+        params = [rf.mlp_base.params, rf.mlp_head.params]
+        for p_ in params:
+            p_.grad = torch.zeros_like(p_)
+        opt = torch.optim.Adam(params, lr=1e-3, eps=1e-15, fused=True, capturable=True)
+        if batches is None:
+            g = torch.Generator(device=dev).manual_seed(5)
+            o_all = torch.cat([sc.rays(v)[0] for v in range(2)])
+            d_all = torch.cat([sc.rays(v)[1] for v in range(2)])
+            batches = []
+            for _ in range(6):
+                pi = torch.randint(0, o_all.shape[0], (1024,), device=dev, generator=g)
+                batches.append((o_all[pi].contiguous(), d_all[pi].contiguous(), torch.rand((1024, 3), device=dev, generator=g)))
+        losses = []
+        if graphed:
+            tups = [mi.sampling_raytrace(d, o) for o, d, _ in batches]
+            cap = max(int(t[0].shape[0]) for t in tups if t is not None) + 100
+            gs = GraphedTrainStep(rf, opt, 1024, cap, mi.render_step_size)
+            gs.load(tups[0], batches[0][1], batches[0][2])
+            state = [p_.detach().clone() for p_ in params]
+            gs.capture(warmup=2)                                   # restores parameters and optimiser state
+            assert all(torch.equal(p_, s0) for p_, s0 in zip(params, state))
+        for k, (o, d, tgt) in enumerate(batches):
+            if graphed:
+                gs.load(tups[k], d, tgt)
+                losses.append(float(gs.step()))
+            else:
+                opt.zero_grad(set_to_none=False)
+                rgb, _, _, _ = render_train(mi, rf, o, d)
+                loss = torch.nn.functional.smooth_l1_loss(rgb, tgt)
+                loss.backward()
+                opt.step()
+                rf.mark_parameters_changed()         # a capturable fused Adam does not bump the tensors' version counters
+                losses.append(float(loss))
+        runs.append((losses, [p_.detach().clone() for p_ in params], sc))
+    (l0, p0, _), (l1, p1, sc1) = runs
+    assert np.allclose(l0, l1, rtol=1e-5, atol=1e-7), (l0, l1)
+    for a, b in zip(p0, p1):
+        assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
+    assert l0[-1] != l0[0] and len(set(l0)) == len(l0)
+    # an eager use after graph replays sees the updated parameters (the fp16 working copies are refreshed)
+    o, d, _ = batches[0]
+    with torch.no_grad():
+        tup = sc1.mesh_intersect.sampling_raytrace(d, o)
+        rgb_g, _ = sc1.radiance_field(tup[0], d, ray_indices=tup[2])
+        rgb_e, _ = runs[0][2].radiance_field(tup[0], d, ray_indices=tup[2])
+    assert maxabs(rgb_g, rgb_e) <= 1e-5
+    with pytest.raises(OverflowError):
+        big = scene.make_scene("smoke", device=dev)
+        oo, dd = big.rays(0)
+        gs.load(big.mesh_intersect.sampling_raytrace(dd, oo), batches[0][1], batches[0][2])
+
+
 def test_guarded_buffers_and_determinism(dev, smoke_scene):
     """Stand-in for compute-sanitizer (closed on this GPU pool): every output of the hot path is carved out of a larger
     buffer whose borders hold a canary, the kernels run on awkward sizes (1, 31, 33, 127, 129, 257 rays / samples — partial
