@@ -7,16 +7,23 @@ One "step" = one 800x800 frame (640 000 rays) of BASELINE.json configs[1] ("c2")
 (K=8, 20 480-triangle quadrature mesh) -> hash grid (16 levels, T=2^19) + 64-wide MLPs at the hits ->
 composite.  Prints ONE JSON line (rank 0).
 
-  value     rays/s with the frame's rays already resident in HBM (200 precomputed views, 3.07 GB > L2, cycled)
-  e2e       rays/s through the reference-facing call with HOST buffers: pinned rays H2D + image D2H every step
-  roofline  dominant kernel (ngp_forward_kernel, hash-grid gather + MLP): algorithmic 512 B per hit sample
-            / its CUDA-event time measured live inside the timed region, vs MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the CPU oracle (pure numpy/PyTorch port of the reference path) on a bounded sample, rank 0
+  value     rays/s with the frame's rays already resident in HBM (200 precomputed views, 3.07 GB > L2, cycled over 3 streams)
+  e2e       rays/s through the reference-facing call from HOST inputs, copies inside the timed region: a 3x4 camera pose in
+            host memory per frame (the reference's loader builds the rays on the device, nerf_synthetic.py:289-378) ->
+            MeshRenderer.render_pose -> rgb + depth copied to pinned host memory (train_finetune.py:620-626)
+  e2e_rays_from_host   round 1's flavour: pinned rays host->device (24 B/ray) + image device->host (20 B/ray) every step
+  roofline  dominant kernel (ngp_forward_tc_kernel: hash-grid gather + tcgen05 MLPs): algorithmic 512 B per hit sample
+            / its CUDA-event time measured live (kernel timed alone on its stream), vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the CPU oracle (C / numpy / PyTorch port of the reference path) on every ray of one frame, rank 0, N=1
+  c2_dense  the same frame from camera radius 2.2 (5 hits / ray instead of 1.7), N=1
+  c4, c5    BASELINE configs[3] / [4] (1080p neural K=32 on a 1.15 M-triangle mesh; 4K baked SG textures): ONE frame per
+            step, ray-sharded over the ranks in 4-row bands dealt round-robin, one NCCL gather per frame in the timed region
+  train, field_train, field_train_occgrid   BASELINE configs[2]: fwd+bwd training steps on 2^18 rays, gradient all-reduce
 
-N > 1 (torchrun): every rank renders its own frames (views are the independent units; weak scaling, no data-path
+N > 1 (torchrun): every rank renders its own c2 frames (views are the independent units; weak scaling, no data-path
 collective), max-over-ranks device time; one NCCL gather of the last frame at the end of the timed region.
 --impl reference times the reference's CPU path (the oracle port: the reference itself is CUDA-only and its native
-dependencies are not installable offline) on the host cores.
+dependencies are not installable offline) on the host cores, every ray of the frame per step.
 """
 from __future__ import annotations
 
