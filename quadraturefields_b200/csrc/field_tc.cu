@@ -94,10 +94,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
   uint32_t done = 0;
   uint32_t spins = 0;
   while (!done) {
+    // the suspend-time hint lets the hardware park the thread until the phase flips (or the hint runs out) instead of
+    // returning at once: without it the waits of r2h polled 4.8 M times per launch — 5 % of all instructions and an extra
+    // shared-memory wavefront each, in a kernel bound by the L1TEX wavefront pipe
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-        : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
-    if (!done && ++spins > (1u << 26)) __trap();   // never hang the GPU on a protocol error
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done) : "r"(mbar), "r"(parity), "r"(0x989680u) : "memory");
+    if (!done && ++spins > (1u << 22)) __trap();   // never hang the GPU on a protocol error
   }
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
