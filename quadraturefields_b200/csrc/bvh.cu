@@ -712,6 +712,9 @@ extern "C" int qf_mesh_info(const qf_mesh* m, int64_t* info4, float* box_pad) {
   return QF_OK;
 }
 
+#ifndef QF_TUPLE_K8_SMEM
+#define QF_TUPLE_K8_SMEM 0
+#endif
 extern "C" size_t qf_trace_workspace_bytes(int64_t n_rays) { return 256 + sizeof(int32_t) * (size_t)(n_rays > 0 ? n_rays : 0) + 256; }
 
 extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
@@ -747,8 +750,13 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   const float eps = m->restart_eps;
   const int k_trav = eps > 0.f ? QF_MAX_HITS : K;
   // the untruncated total needs a traversal without distance culling
-  if (d_total) { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, true); else QF_TRACE(HitBufSmem, true); }
-  else { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, false); else QF_TRACE(HitBufSmem, false); }
+#if QF_TUPLE_K8_SMEM
+  using HitBufK8 = HitBufSmemT<8>;
+#else
+  using HitBufK8 = HitBufReg<8>;
+#endif
+  if (d_total) { if (k_trav <= 8) QF_TRACE(HitBufK8, true); else QF_TRACE(HitBufSmem, true); }
+  else { if (k_trav <= 8) QF_TRACE(HitBufK8, false); else QF_TRACE(HitBufSmem, false); }
 #undef QF_TRACE
   QF_LAUNCH_CHECK();
   return QF_OK;

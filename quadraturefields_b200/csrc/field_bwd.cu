@@ -89,6 +89,19 @@ __device__ __forceinline__ void c_to_a(uint32_t (*a)[4], float (*acc)[4]) {
       a[k][2 * h + 1] = RELU ? pack_h2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)) : pack_h2(c[2], c[3]);
     }
 }
+// The activation / gradient rows (960 B per sample, 424 MB per step at 442 K samples) are written once and read once by
+// weight_grad_kernel: stored with the streaming (evict-first) policy so they do not push the 50 MB gradient table, which
+// the scatter's atomics keep hitting, out of L2.
+#ifndef QF_BWD_STREAM_ROWS
+#define QF_BWD_STREAM_ROWS 1
+#endif
+__device__ __forceinline__ void st_row32(__half* p, uint32_t v) {
+#if QF_BWD_STREAM_ROWS
+  __stcs(reinterpret_cast<unsigned int*>(p), v);
+#else
+  *reinterpret_cast<uint32_t*>(p) = v;
+#endif
+}
 // A fragments (rows g / g+8) -> fp16 row-major global rows: cols [col0, col0 + 16*KT)
 template <int KT>
 __device__ __forceinline__ void store_a(__half* __restrict__ base, int row_len, int col0, int64_t r_lo, int64_t r_hi, int64_t M,
@@ -97,12 +110,12 @@ __device__ __forceinline__ void store_a(__half* __restrict__ base, int row_len, 
   for (int k = 0; k < KT; ++k) {
     const int c = col0 + k * 16 + t * 2;
     if (r_lo < M) {
-      *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c) = a[k][0];
-      *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c + 8) = a[k][2];
+      st_row32(base + r_lo * row_len + c, a[k][0]);
+      st_row32(base + r_lo * row_len + c + 8, a[k][2]);
     }
     if (r_hi < M) {
-      *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c) = a[k][1];
-      *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c + 8) = a[k][3];
+      st_row32(base + r_hi * row_len + c, a[k][1]);
+      st_row32(base + r_hi * row_len + c + 8, a[k][3]);
     }
   }
 }
@@ -113,8 +126,8 @@ __device__ __forceinline__ void store_c(__half* __restrict__ base, int row_len, 
 #pragma unroll
   for (int n = 0; n < NT; ++n) {
     const int c = col0 + n * 8 + t * 2;
-    if (r_lo < M) *reinterpret_cast<uint32_t*>(base + r_lo * row_len + c) = pack_h2(acc[n][0], acc[n][1]);
-    if (r_hi < M) *reinterpret_cast<uint32_t*>(base + r_hi * row_len + c) = pack_h2(acc[n][2], acc[n][3]);
+    if (r_lo < M) st_row32(base + r_lo * row_len + c, pack_h2(acc[n][0], acc[n][1]));
+    if (r_hi < M) st_row32(base + r_hi * row_len + c, pack_h2(acc[n][2], acc[n][3]));
   }
 }
 
@@ -135,7 +148,11 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, float* __r
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
 }
 
-constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4 * 32 * 3 * 4;
+#ifndef QF_BWD_WARPS
+#define QF_BWD_WARPS 4
+#endif
+constexpr int kBwdWarps = QF_BWD_WARPS, kBwdThreads = kBwdWarps * 32;
+constexpr int kBwdSmemBytes = (kWTotal + kTTotal + kBwdWarps * 32 * kTileStride) * 2 + kBwdWarps * 32 * 3 * 4;
 
 // FEAT = false: backward of the full forward (rgb, sigma).  FEAT = true: backward of `query_density(return_feat=True)`
 // — the upstream gradient arrives at the 16 outputs of the base MLP (sigma and the 15 geo features), the tcnn head is
@@ -144,20 +161,20 @@ constexpr int kBwdSmemBytes = (kWTotal + kTTotal + 4 * 32 * kTileStride) * 2 + 4
 #define QF_BWD_MIN_CTAS 3
 #endif
 template <bool FEAT>
-__global__ void __launch_bounds__(128, QF_BWD_MIN_CTAS) ngp_backward_kernel(const BwdArgs a) {
+__global__ void __launch_bounds__(kBwdThreads, QF_BWD_MIN_CTAS) ngp_backward_kernel(const BwdArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* s_w = reinterpret_cast<__half*>(smem_raw);
   __half* s_wt = s_w + kWTotal;
   __half* s_tile_all = s_wt + kTTotal;
-  float* s_x_all = reinterpret_cast<float*>(s_tile_all + 4 * 32 * kTileStride);
+  float* s_x_all = reinterpret_cast<float*>(s_tile_all + kBwdWarps * 32 * kTileStride);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   {
     const uint4* src = reinterpret_cast<const uint4*>(a.weights);
     uint4* dst = reinterpret_cast<uint4*>(s_w);
-    for (int i = tid; i < kWTotal / 8; i += 128) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kWTotal / 8; i += kBwdThreads) dst[i] = __ldg(src + i);
     const uint4* srct = reinterpret_cast<const uint4*>(a.weights_t);
     uint4* dstt = reinterpret_cast<uint4*>(s_wt);
-    for (int i = tid; i < kTTotal / 8; i += 128) dstt[i] = __ldg(srct + i);
+    for (int i = tid; i < kTTotal / 8; i += kBwdThreads) dstt[i] = __ldg(srct + i);
   }
   __syncthreads();
   const int64_t M = a.M;
@@ -167,7 +184,7 @@ __global__ void __launch_bounds__(128, QF_BWD_MIN_CTAS) ngp_backward_kernel(cons
   const float amin[3] = {a.desc.aabb[0], a.desc.aabb[1], a.desc.aabb[2]};
   const float aext[3] = {a.desc.aabb[3] - a.desc.aabb[0], a.desc.aabb[4] - a.desc.aabb[1], a.desc.aabb[5] - a.desc.aabb[2]};
 
-  for (int64_t base = ((int64_t)blockIdx.x * 4 + warp) * 32; base < M; base += (int64_t)gridDim.x * 128) {
+  for (int64_t base = ((int64_t)blockIdx.x * kBwdWarps + warp) * 32; base < M; base += (int64_t)gridDim.x * kBwdThreads) {
     const int64_t i = base + lane;
     const bool valid = i < M;
     float x = 0.5f, y = 0.5f, z = 0.5f;
@@ -200,7 +217,13 @@ __global__ void __launch_bounds__(128, QF_BWD_MIN_CTAS) ngp_backward_kernel(cons
     if (valid) {  // layer-1 input rows (the encoding), one 64-byte row per lane
       uint4* dst = reinterpret_cast<uint4*>(a.act + i * kActRow);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dst[q] = row[q];
+      for (int q = 0; q < 4; ++q) {
+#if QF_BWD_STREAM_ROWS
+        __stcs(dst + q, row[q]);
+#else
+        dst[q] = row[q];
+#endif
+      }
     }
     const unsigned selmask = __ballot_sync(0xffffffffu, sel);
     __syncwarp();
@@ -568,6 +591,7 @@ extern "C" int qf_hashgrid_backward(const qf_ngp* f, const float* d_x01, const f
                                     void* stream) {
   if (M == 0) return QF_OK;
   QF_REQUIRE(f && d_x01 && d_grad_enc && d_grad_table, "qf_hashgrid_backward: NULL argument");
+  QF_REQUIRE((reinterpret_cast<uintptr_t>(d_grad_table) & 15) == 0, "qf_hashgrid_backward: d_grad_table must be 16-byte aligned");
   const int64_t n = M * f->desc.n_levels;
   hashgrid_backward_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(f->desc, d_x01, d_grad_enc, M,
                                                                                        reinterpret_cast<float2*>(d_grad_table));
@@ -597,6 +621,7 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
              "qf_ngp_backward: NULL argument");
   QF_REQUIRE(f->d_weights, "qf_ngp_backward: this field handle holds a grid only (qf_grid_create)");
   QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward: workspace too small");
+  QF_REQUIRE((reinterpret_cast<uintptr_t>(d_grad_table) & 15) == 0, "qf_ngp_backward: d_grad_table must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)d_workspace;
   float* gmax = (float*)ws; ws += 256;
@@ -616,9 +641,9 @@ extern "C" int qf_ngp_backward_inputs(const qf_ngp* f, const float* d_positions,
   a.g_pos = d_grad_positions;
   for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
   QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel<false>, kBwdSmemBytes);
-  int64_t tiles = ceil_div(M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);   // 3 CTAs/SM: 64.5 KB smem, <= 168 registers
-  ngp_backward_kernel<false><<<blocks, 128, kBwdSmemBytes, st>>>(a);
+  int64_t tiles = ceil_div(M, kBwdThreads);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * QF_BWD_MIN_CTAS ? tiles : (int64_t)kNumSMs * QF_BWD_MIN_CTAS);   // 3 CTAs/SM: 64.5 KB smem, <= 168 registers
+  ngp_backward_kernel<false><<<blocks, kBwdThreads, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   { int rc = launch_weight_grad(act, grd, M, stage, false, st); if (rc != QF_OK) return rc; }
   unpack_weight_grads_kernel<<<(int)ceil_div(3072 + 7168, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, d_grad_head_w);
@@ -637,6 +662,7 @@ extern "C" int qf_ngp_backward_features(const qf_ngp* f, const float* d_position
   QF_REQUIRE(f && d_positions && d_grad_feat && d_grad_table && d_grad_base_w && d_workspace, "qf_ngp_backward_features: NULL argument");
   QF_REQUIRE(f->d_weights, "qf_ngp_backward_features: this field handle holds a grid only (qf_grid_create)");
   QF_REQUIRE(workspace_bytes >= qf_ngp_backward_workspace_bytes(M), "qf_ngp_backward_features: workspace too small");
+  QF_REQUIRE((reinterpret_cast<uintptr_t>(d_grad_table) & 15) == 0, "qf_ngp_backward_features: d_grad_table must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = (char*)d_workspace;
   float* gmax = (float*)ws; ws += 256;
@@ -655,9 +681,9 @@ extern "C" int qf_ngp_backward_features(const qf_ngp* f, const float* d_position
   a.act = act; a.grd = grd; a.g_pos = d_grad_positions;
   for (int c = 0; c < 3; ++c) a.inv_ext[c] = 1.0f / (f->desc.aabb[3 + c] - f->desc.aabb[c]);
   QF_ENSURE_DYNAMIC_SMEM(ngp_backward_kernel<true>, kBwdSmemBytes);
-  int64_t tiles = ceil_div(M, 128);
-  int blocks = (int)(tiles < (int64_t)kNumSMs * 3 ? tiles : (int64_t)kNumSMs * 3);
-  ngp_backward_kernel<true><<<blocks, 128, kBwdSmemBytes, st>>>(a);
+  int64_t tiles = ceil_div(M, kBwdThreads);
+  int blocks = (int)(tiles < (int64_t)kNumSMs * QF_BWD_MIN_CTAS ? tiles : (int64_t)kNumSMs * QF_BWD_MIN_CTAS);
+  ngp_backward_kernel<true><<<blocks, kBwdThreads, kBwdSmemBytes, st>>>(a);
   QF_LAUNCH_CHECK();
   { int rc = launch_weight_grad(act, grd, M, stage, true, st); if (rc != QF_OK) return rc; }      // the two base layers only
   unpack_weight_grads_kernel<<<(int)ceil_div(3072, 256), 256, 0, st>>>(stage, gmax, d_grad_base_w, nullptr);

@@ -126,6 +126,9 @@ __device__ __forceinline__ void encode_point(const qf_grid_desc& d, const __half
     if (two) store(l + 1, level_blend(c1, v1));
   }
 }
+#ifndef QF_BWD_PAIR_ATOMICS
+#define QF_BWD_PAIR_ATOMICS 1
+#endif
 // backward of one level: scatter the gradient of its two features to the 8 corners (fp32 atomics)
 __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __restrict__ g_table, int l, float x, float y,
                                               float z, float g0, float g1) {
@@ -133,12 +136,34 @@ __device__ __forceinline__ void scatter_level(const qf_grid_desc& d, float2* __r
   Corner8 c;
   level_indices(d, l, x, y, z, c);
   float2* lvl = g_table + d.offset[l];
+#if QF_BWD_PAIR_ATOMICS
+  // The two x-neighbours of a (y,z) corner pair are adjacent entries whenever their indices differ in bit 0 only (hashed
+  // levels: even cell x; dense levels: even linear index): ONE 16-byte vector reduction (REDG.E.ADD.F32x4) instead of two
+  // 8-byte ones — 6 instead of 8 L2 atomics per level on average.  Level offsets are multiples of 8 entries and the entry
+  // points require a 16-byte aligned table gradient, so the pair is aligned.  Same weights ((wx * wy) * wz), same sums.
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t i0 = c.idx[2 * j], i1 = c.idx[2 * j + 1];
+    const float wy = (j & 1) ? c.fy : 1.f - c.fy, wz = (j & 2) ? c.fz : 1.f - c.fz;
+    const float w0 = ((1.f - c.fx) * wy) * wz, w1 = (c.fx * wy) * wz;
+    if ((i0 ^ i1) == 1u) {
+      const bool lo0 = !(i0 & 1u);                     // i0 is the lower entry of the aligned pair
+      const float a0 = lo0 ? w0 : w1, a1 = lo0 ? w1 : w0;
+      float* p = reinterpret_cast<float*>(lvl + (i0 & ~1u));
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a0 * g0), "f"(a0 * g1), "f"(a1 * g0), "f"(a1 * g1) : "memory");
+    } else {
+      atomicAdd(lvl + i0, make_float2(w0 * g0, w0 * g1));
+      atomicAdd(lvl + i1, make_float2(w1 * g0, w1 * g1));
+    }
+  }
+#else
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     float w = ((k & 1) ? c.fx : 1.f - c.fx) * ((k & 2) ? c.fy : 1.f - c.fy);
     w *= (k & 4) ? c.fz : 1.f - c.fz;
     atomicAdd(lvl + c.idx[k], make_float2(w * g0, w * g1));
   }
+#endif
 }
 
 // scatter_level plus the gradient with respect to the normalised position (tcnn's grid input gradient): with

@@ -64,17 +64,20 @@ struct HitBufReg {
   __device__ __forceinline__ void restart_filter(float, int) {}   // the epsilon-restart mode always runs on HitBufSmem
 };
 
-// HitBufSmem (8 < K <= 32): unsorted in shared memory (slot-major, 128 threads per CTA, conflict free), O(1) append
+// HitBufSmemT<SLOTS> (HitBufSmem = 32 slots for 8 < K <= 32; 8 slots for K <= 8 on the fused frame path since r2i: c2 trace
+// 0.114 -> 0.104 ms against HitBufReg<8>, whose carry insertion costs ~70 instructions per hit of any lane of the warp):
+// unsorted in shared memory (slot-major, 128 threads per CTA, conflict free), O(1) append
 // while fewer than K hits are known — the common case, since K is chosen above the deepest ray — and replace-the-maximum
 // once full; sorted once at the end.  Keeps the traversal kernels at ~60 registers instead of 115 for a 32-slot
 // register buffer whose insertion costs 32 compare-exchange steps per hit.
-struct HitBufSmem {
-  static constexpr int kSmemSlots = QF_MAX_HITS;
+template <int SLOTS>
+struct HitBufSmemT {
+  static constexpr int kSmemSlots = SLOTS;
   float* st;
   int* si;
   int cnt, K, imax, idmax;
   float tmax;
-  __device__ __forceinline__ HitBufSmem(float* t, int* i, int tid) : st(t + tid), si(i + tid) {}
+  __device__ __forceinline__ HitBufSmemT(float* t, int* i, int tid) : st(t + tid), si(i + tid) {}
   __device__ __forceinline__ void init(int K_) { cnt = 0; K = K_; imax = 0; idmax = 0x7fffffff; tmax = __int_as_float(0x7f800000); }
   __device__ __forceinline__ float cull_distance() const { return cnt == K ? tmax : __int_as_float(0x7f800000); }
   __device__ __forceinline__ int count(int) const { return cnt; }
@@ -124,6 +127,7 @@ struct HitBufSmem {
     cnt = w;
   }
 };
+using HitBufSmem = HitBufSmemT<QF_MAX_HITS>;
 
 // one triangle (leaf reference) whose padded box passed the slab test with entry distance tn
 template <class HB>
@@ -253,6 +257,13 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
 // the brute force.  One node visit replaces ~5 levels of two-box visits in which all 32 lanes did the same test.
 constexpr int kWideStack = 256;   // entries of shared memory per warp (a visit pushes <= 32 children, depth ~ log32 F)
 
+#ifdef QF_TRACE_STATS   // diagnostics build only (tools/diag_trace_stats.py): per-packet work counters of the wide traversal
+static __device__ unsigned long long g_trace_stats[8];
+#define QF_STAT(i, v) (st_##i += (v))
+#else
+#define QF_STAT(i, v) ((void)0)
+#endif
+
 template <class HB, bool CULL, int SIGN>
 __device__ __forceinline__ void traverse_packet_wide(const Ray& r, bool active, const float4* __restrict__ wnodes,
                                                      const float4* __restrict__ tris, int K, HB& hb, int& total,
@@ -277,7 +288,11 @@ __device__ __forceinline__ void traverse_packet_wide(const Ray& r, bool active, 
   int sp = 1;
   if (lane == 0) wstack[0] = 0;
   __syncwarp();
+#ifdef QF_TRACE_STATS
+  unsigned st_1 = 0, st_2 = 0, st_3 = 0, st_4 = 0, st_6 = 0;
+#endif
   while (sp > 0) {
+    QF_STAT(1, 1);
     const int node = wstack[--sp];
     __syncwarp();                      // every lane has read the entry before a push may overwrite it
     const float4* rec = wnodes + ((int64_t)node * 32 + lane) * 2;
@@ -305,8 +320,10 @@ __device__ __forceinline__ void traverse_packet_wide(const Ray& r, bool active, 
     unsigned m_tri = __ballot_sync(0xffffffffu, hit && ref < 0);
     if (hit && ref >= 0) wstack[sp + __popc(m_int & lt)] = ref;
     sp += __popc(m_int);
+    QF_STAT(6, __popc(m_int));
     __syncwarp();
     while (m_tri) {
+      QF_STAT(2, 1);
       const int c = __ffs(m_tri) - 1;
       m_tri &= m_tri - 1;
       const float lx = __shfl_sync(0xffffffffu, a.x, c), ly = __shfl_sync(0xffffffffu, a.y, c), lz = __shfl_sync(0xffffffffu, a.z, c);
@@ -314,9 +331,27 @@ __device__ __forceinline__ void traverse_packet_wide(const Ray& r, bool active, 
       const int tref = __shfl_sync(0xffffffffu, ref, c);
       float tn, tf;
       const bool s = slab_signed<SIGN & 7>(r, lx, ly, lz, hx, hy, hz, tn, tf);
+#ifdef QF_TRACE_STATS
+      {
+        const unsigned pm = __ballot_sync(0xffffffffu, s && active && tn <= (CULL ? hb.cull_distance() : inf));
+        st_3 += pm ? 1 : 0;
+        st_4 += __popc(pm);
+      }
+#endif
       if (s && active && tn <= (CULL ? hb.cull_distance() : inf)) leaf_intersect<HB>(r, tris, tref, tn, hb, total);
     }
   }
+#ifdef QF_TRACE_STATS
+  {
+    const unsigned hits = __reduce_add_sync(0xffffffffu, (unsigned)total);
+    if (lane == 0) {
+      atomicAdd(&g_trace_stats[0], 1ull); atomicAdd(&g_trace_stats[1], (unsigned long long)st_1);
+      atomicAdd(&g_trace_stats[2], (unsigned long long)st_2); atomicAdd(&g_trace_stats[3], (unsigned long long)st_3);
+      atomicAdd(&g_trace_stats[4], (unsigned long long)st_4); atomicAdd(&g_trace_stats[5], (unsigned long long)hits);
+      atomicAdd(&g_trace_stats[6], (unsigned long long)st_6); atomicAdd(&g_trace_stats[7], st_1 > 1 ? 1ull : 0ull);
+    }
+  }
+#endif
 }
 
 // Warp-uniform sign pattern of the direction components (bit k: component k negative) when every active lane has
