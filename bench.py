@@ -353,7 +353,41 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(ms_p, op=dist.ReduceOp.MAX)
     e2e_pose_value = N * world * args.steps / (float(ms_p.item()) * 1e-3)
-    del pose_renderers
+    # ---- e2e, PNG-ready flavour: what the reference's eval loop finally keeps of a frame on the host are the uint8 colour and
+    # depth images it writes (train_finetune.py:639-646); made on the device (MeshRenderer.frame_to_uint8) they are 4 B / ray
+    # instead of 16.  Secondary key: with 8 ranks the fp32 images of the headline e2e saturate the host's PCIe ingest.
+    u8_dev = [(torch.empty((N, 3), dtype=torch.uint8, device=dev), torch.empty((N,), dtype=torch.uint8, device=dev)) for _ in range(NB)]
+    u8_host = [(torch.empty((N, 3), dtype=torch.uint8).pin_memory(), torch.empty((N,), dtype=torch.uint8).pin_memory()) for _ in range(NB)]
+
+    def run_e2e_u8(n_steps, first):
+        for j in range(n_steps):
+            i, b = first + j, j % NB
+            s_cmp = s_cmps[b]
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_out[b])               # previous D2H from this slot finished
+                r = pose_renderers[b]
+                r.render_pose(sc.poses[view_of(i) % len(sc.poses)], sc.W, sc.H, sc.focal, sc.cx, sc.cy, out=d_out[b])
+                r.frame_to_uint8(d_out[b], rgb8=u8_dev[b][0], depth8=u8_dev[b][1])
+                ev_cmp[b].record(s_cmp)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(ev_cmp[b])
+                u8_host[b][0].copy_(u8_dev[b][0], non_blocking=True)
+                u8_host[b][1].copy_(u8_dev[b][1], non_blocking=True)
+                ev_out[b].record(s_d2h)
+        for st in (s_d2h, *s_cmps):
+            torch.cuda.current_stream(dev).wait_stream(st)
+
+    run_e2e_u8(max(args.warmup, 3), 0)
+    barrier()
+    ev0.record()
+    run_e2e_u8(args.steps, args.warmup)
+    ev1.record()
+    barrier()
+    ms_u = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms_u, op=dist.ReduceOp.MAX)
+    e2e_u8_value = N * world * args.steps / (float(ms_u.item()) * 1e-3)
+    del pose_renderers, u8_dev, u8_host
     train = None if args.no_train else run_train_steps(args, sc, dev, rank, world, barrier)
     field_train = None if args.no_train else run_field_train_steps(args, sc, dev, rank, world, barrier)
     field_train_occ = None if args.no_train else run_field_train_occgrid_steps(args, sc, dev, rank, world, barrier)
@@ -396,6 +430,9 @@ def run_ours(args):
             "e2e": {"value": e2e_pose_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": N * 16,
                     "input": "3x4 camera-to-world pose in host memory (48 B, passed as kernel arguments of the ray generator)",
                     "output": "rgb (N,3) + depth (N,1) copied device->pinned host every step"},
+            "e2e_png_ready": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": 48, "d2h_bytes_per_step": N * 4,
+                              "output": "uint8 colour (N,3) + uint8 normalised depth (N) — the images the reference's eval loop "
+                                        "writes (train_finetune.py:639-646), converted on the device, copied to pinned host every step"},
             "e2e_rays_from_host": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N * 24, "d2h_bytes_per_step": N * 20},
             "gpu_launches": 3 * args.steps,
             "stage_ms_per_step": {"trace": ms3[0] / max(nch.value, 1), "shade": shade_ms, "composite": ms3[2] / max(nch.value, 1),
@@ -472,8 +509,45 @@ def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
         hits = torch.zeros((1,), dtype=torch.int32, device=dev)
         steps, warm = max(3, min(args.steps, 10)), 3
         hit_slots = torch.zeros((warm + steps, 1), dtype=torch.int32, device=dev)
+        # N > 1: the frame lives on rank 0 and every rank's composite kernel stores its pixels straight into it over NVLink
+        # (parallel.PeerFrame: CUDA IPC peer memory, one 4-byte all-reduce per frame as the fence).  QF_BENCH_PEER_FRAME=0, or
+        # a failed mapping / self-check, falls back to one NCCL gather per frame + reassembly.
+        peer, peer_note = None, "n/a (one GPU)" if world == 1 else "peer frame disabled (QF_BENCH_PEER_FRAME=0)"
+        if world > 1 and os.environ.get("QF_BENCH_PEER_FRAME", "1") != "0":
+            ok = torch.ones((1,), device=dev)
+            try:
+                peer = P.PeerFrame(H, W, dev, dst=0, slots=2)
+            except Exception as e:                       # noqa: BLE001 - any failure means "use the collective"
+                peer_note = f"unavailable ({type(e).__name__}: {e})"
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                peer = None
+            else:
+                # self-check against the collective path on one frame: same pixels, bit for bit
+                renderer.render_pose(sc.poses[0], W, H, sc.focal, sc.cx, sc.cy, hits_out=hits, bands=(rank, world), frame=peer, frame_slot=0)
+                peer.sync()
+                renderer.render_pose(sc.poses[0], W, H, sc.focal, sc.cx, sc.cy, out=out, hits_out=hits, bands=(rank, world))
+                flat = P.gather_frame(torch.cat([out["rgb"], out["opacity"], out["depth"]], dim=1), sizes, dst=0)
+                if rank == 0:
+                    ref = P.assemble_banded(torch.split(flat, sizes), H, W)
+                    got = torch.cat(peer.frame(0), dim=1)
+                    if not torch.equal(ref, got):
+                        ok.zero_()
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if float(ok.item()) < 1.0:
+                    peer_note = "self-check against the NCCL gather FAILED: collective path used"
+                    peer.close()
+                    peer = None
+                else:
+                    peer_note = "peer stores over NVLink into rank 0's frame (bit-identical to the NCCL gather on the check frame)"
 
         def step(i):
+            if peer is not None:
+                renderer.render_pose(sc.poses[i % len(sc.poses)], W, H, sc.focal, sc.cx, sc.cy, hits_out=hit_slots[i],
+                                     bands=(rank, world), frame=peer, frame_slot=i)
+                peer.sync()
+                return
             renderer.render_pose(sc.poses[i % len(sc.poses)], W, H, sc.focal, sc.cx, sc.cy, out=out, hits_out=hit_slots[i],
                                  bands=(rank, world))
             if world > 1:
@@ -517,12 +591,16 @@ def run_sharded_frame_leg(name, args, dev, rank, world, barrier, baked):
                "samples_per_sec": hits_per_frame / (ms * 1e-3), "steps": steps, "triangles": int(sc.faces_np.shape[0]), "K": sc.K,
                "bvh_bytes": int(sc.mesh_intersect.rayintersector.info()["device_bytes"]),
                "gather_bytes_per_frame": (N - sizes[0]) * 20 if world > 1 else 0,
+               "image_gather": peer_note if (world == 1 or peer is not None) else ("NCCL gather + reassembly; " + peer_note),
                "rank0_stage_ms_per_frame": {"trace": st[0], "shade": st[1], "composite": st[2]},
                "roofline_shade": {"bound": "hbm", "kernel": "baked_shade_kernel" if baked else "ngp_forward_tc_kernel",
                                   "algorithmic_bytes_per_hit": bytes_per_hit, "achieved": shade_gbs, "peak": peak, "unit": "GB/s",
                                   "frac": shade_gbs / peak, "peak_source": peak_src},
                "includes": "pose on the host -> ray generation -> BVH first-K trace -> shade -> composite on every rank's band"
-                           + (" -> NCCL gather of the bands to rank 0" if world > 1 else "")}
+                           + ((" -> pixels stored into rank 0's frame over NVLink by the composite kernel, one 4-byte all-reduce as the fence"
+                               if peer is not None else " -> NCCL gather of the bands to rank 0") if world > 1 else "")}
+        if peer is not None:
+            peer.close()
         del sc, renderer
         torch.cuda.empty_cache()
         return res

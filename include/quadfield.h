@@ -259,6 +259,37 @@ int qf_render_mesh_baked(const qf_mesh* mesh, const qf_texture* tex, const float
                          int bg_mode, const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth,
                          int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Ray-sharded frames (BASELINE configs[3] / [4]: one frame over 1/2/4/8 GPUs).  The rays are a rank's band-cyclic share of
+ * a frame `frame_width` pixels wide (qf_generate_rays_banded with the same band_rows / band_stride / band_offset; n_rays =
+ * qf_band_rows(...) * frame_width) and the three outputs address the WHOLE frame (H*W pixels): every pixel is stored where it
+ * sits in the frame.  With the outputs in a buffer of the gathering rank (qf_peer_open below) the final image gather
+ * is the composite kernel's own stores over NVLink — no collective, no reassembly pass.  The reference renders such frames
+ * in 160 000-ray splits on one GPU and scatters them into the frame with rgb[split] = color[split]
+ * (train_finetune.py:590-617, test_baking_texture_images.py:355-371). */
+int qf_render_mesh_ngp_to_frame(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
+                                int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, int band_rows,
+                                int band_stride, int band_offset, int frame_width, float* d_frame_rgb, float* d_frame_alpha,
+                                float* d_frame_depth, int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes,
+                                void* stream);
+int qf_render_mesh_baked_to_frame(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled,
+                                  const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta,
+                                  int bg_mode, const float* d_bkgd, int band_rows, int band_stride, int band_offset,
+                                  int frame_width, float* d_frame_rgb, float* d_frame_alpha, float* d_frame_depth,
+                                  int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream);
+/* The PNG-ready images of the reference's eval loops (train_finetune.py:639-646: rgb8 = uint8(clamp(rgb,0,1)*255),
+ * depth8 = uint8(depth / depth.max() * 255), fp32 arithmetic, truncation), made on the device: 4 instead of 16 bytes per
+ * pixel to copy to the host.  d_depth8 may be NULL (colour only); d_scratch: 4 bytes of device memory. */
+int qf_frame_to_u8(const float* d_rgb, const float* d_depth, int64_t n_pixels, unsigned char* d_rgb8,
+                   unsigned char* d_depth8, int32_t* d_scratch, void* stream);
+/* Peer memory for the ray-sharded frames (one process per GPU of one node): device memory allocated by one rank (cudaMalloc), exported
+ * as a 64-byte CUDA IPC handle that travels to the peers over any host channel, and mapped there (peer access over NVLink is
+ * enabled on first open).  A mapping is closed by the rank that opened it, the allocation freed by its owner afterwards. */
+int qf_peer_alloc(size_t bytes, void** d_ptr);
+int qf_peer_free(void* d_ptr);
+int qf_peer_export(const void* d_ptr, unsigned char* handle64);
+int qf_peer_open(const unsigned char* handle64, void** d_ptr);
+int qf_peer_close(void* d_ptr);
+
 /* ------------------------------------------------------------------------------------------
  * (5b) The quadrature `Field` net (field.py:130-259) with back_prop=False (both reference
  * call sites): out = MLP([x01, grid(x01)]) with a 16-level fp16 hash grid (tcnn.Encoding "Grid"/"Hash") and a

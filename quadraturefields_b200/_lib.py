@@ -80,6 +80,14 @@ _SIGS = {
     "qf_render_workspace_bytes": (_SZ, [_L, _I]),
     "qf_render_mesh_ngp": (_I, [_P, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "qf_render_mesh_baked": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _F, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_render_mesh_ngp_to_frame": (_I, [_P, _P, _P, _P, _L, _I, _F, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_render_mesh_baked_to_frame": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _SZ, _P]),
+    "qf_frame_to_u8": (_I, [_P, _P, _L, _P, _P, _P, _P]),
+    "qf_peer_alloc": (_I, [_SZ, C.POINTER(_P)]),
+    "qf_peer_free": (_I, [_P]),
+    "qf_peer_export": (_I, [_P, C.c_char_p]),
+    "qf_peer_open": (_I, [C.c_char_p, C.POINTER(_P)]),
+    "qf_peer_close": (_I, [_P]),
     "qf_profile_enable": (_I, [_I]),
     "qf_profile_read": (_I, [C.POINTER(C.c_double), C.POINTER(_L)]),
     "qf_generate_rays": (_I, [C.POINTER(_F), _I, _I, _F, _F, _F, _I, _P, _P, _P]),

@@ -247,9 +247,11 @@ __global__ void emit_tiny_root_kernel(const float4* __restrict__ tris, const flo
 //      the smallest ones are dissolved into single triangles while the free slots allow, so no node of 2-3 triangles is
 //      ever emitted next to free slots.
 // Children that are still internal get a wide node of the next level; triangle children carry the triangle's own padded
-// box.  Levels are processed by successive launches (kWideLevels of them: the packet stack holds 8 levels of pushes); a
+// box.  Levels are processed by successive launches (kWideLevels of them: the packet stack, traverse.cuh kWideStack, holds
+// 31 * kWideLevels + 1 pushes); a
 // tree that needs more, or more nodes than were allocated, clears the ok flag and the traversal keeps to the binary tree.
-constexpr int kWideLevels = 8;
+constexpr int kWideLevels = 6;
+static_assert(31 * kWideLevels + 1 <= kWideStack, "packet stack too small for the collapse depth");
 
 __global__ void wide_init_kernel(int32_t* __restrict__ wstate, int32_t* __restrict__ wqueue) {
   wstate[0] = 0; wstate[1] = 1; wstate[2] = 1; wstate[3] = 1; wstate[4] = 0;
@@ -712,9 +714,6 @@ extern "C" int qf_mesh_info(const qf_mesh* m, int64_t* info4, float* box_pad) {
   return QF_OK;
 }
 
-#ifndef QF_TUPLE_K8_SMEM
-#define QF_TUPLE_K8_SMEM 0
-#endif
 extern "C" size_t qf_trace_workspace_bytes(int64_t n_rays) { return 256 + sizeof(int32_t) * (size_t)(n_rays > 0 ? n_rays : 0) + 256; }
 
 extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const float* d_dirs, int64_t n_rays, int K,
@@ -750,13 +749,9 @@ extern "C" int qf_trace_firstk(const qf_mesh* m, const float* d_origins, const f
   const float eps = m->restart_eps;
   const int k_trav = eps > 0.f ? QF_MAX_HITS : K;
   // the untruncated total needs a traversal without distance culling
-#if QF_TUPLE_K8_SMEM
-  using HitBufK8 = HitBufSmemT<8>;
-#else
-  using HitBufK8 = HitBufReg<8>;
-#endif
-  if (d_total) { if (k_trav <= 8) QF_TRACE(HitBufK8, true); else QF_TRACE(HitBufSmem, true); }
-  else { if (k_trav <= 8) QF_TRACE(HitBufK8, false); else QF_TRACE(HitBufSmem, false); }
+  // (an 8-slot shared-memory buffer, the fused frame's choice for K <= 8, is neutral on this path: r2i train step 1.44 vs 1.45 ms)
+  if (d_total) { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, true); else QF_TRACE(HitBufSmem, true); }
+  else { if (k_trav <= 8) QF_TRACE(HitBufReg<8>, false); else QF_TRACE(HitBufSmem, false); }
 #undef QF_TRACE
   QF_LAUNCH_CHECK();
   return QF_OK;

@@ -13,6 +13,7 @@
 //                          samples only (M is read from device memory; persistent grid of 148 x k CTAs).
 //   composite_rays_kernel: derive_properties (utils.py:863-898) per ray.
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -90,8 +91,6 @@ __global__ void __launch_bounds__(128, QF_TRACE_MIN_CTAS) trace_compact_kernel(c
   __shared__ int s_stack[4][kWideStack];
   if (wnodes && !__ldg(wstate + 3)) wnodes = nullptr;    // the collapse gave up on this mesh: binary tree only
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ int s_slot_off[4][QF_MAX_HITS];        // records of the warp's run before slot j
-  __shared__ unsigned s_slot_mask[4][QF_MAX_HITS];  // lanes that have a j-th hit
   const int64_t li = ray_of_thread(blockIdx.x * (int64_t)blockDim.x + tid, lane, img_w);  // ray inside the chunk
   __shared__ float s_ht[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
   __shared__ int s_hi[HB::kSmemSlots ? HB::kSmemSlots * 128 : 1];
@@ -103,6 +102,11 @@ __global__ void __launch_bounds__(128, QF_TRACE_MIN_CTAS) trace_compact_kernel(c
   if (restart_eps > 0.f && valid) hb.restart_filter(restart_eps, K);   // k_trav = QF_MAX_HITS raw hits -> K kept (Embree restart loop)
   // the warp reserves a contiguous run of the compact hit array with ONE atomicAdd (no CTA barrier: packets differ a lot in
   // cost, and a __syncthreads here made every warp wait for the slowest of its CTA — 15 % of the stall samples in r2f)
+  // the traversal is over: its stack now holds the slot tables of the warp's run (records before slot j | lanes with a j-th hit)
+  static_assert(kWideStack >= 2 * QF_MAX_HITS, "slot tables alias the packet stack");
+  __syncwarp();
+  int* const slot_off = s_stack[warp];
+  unsigned* const slot_mask = reinterpret_cast<unsigned*>(s_stack[warp] + QF_MAX_HITS);
   int c = valid ? hb.count(k_trav) : 0;
   const int wsum = __reduce_add_sync(0xffffffffu, c);
   int wbase = 0;
@@ -113,13 +117,13 @@ __global__ void __launch_bounds__(128, QF_TRACE_MIN_CTAS) trace_compact_kernel(c
   const int cmax = __reduce_max_sync(0xffffffffu, c);
   for (int j = 0, off = 0; j < cmax; ++j) {
     const unsigned m = __ballot_sync(0xffffffffu, c > j);
-    if (lane == 0) { s_slot_off[warp][j] = off; s_slot_mask[warp][j] = m; }
+    if (lane == 0) { slot_off[j] = off; slot_mask[j] = m; }
     off += __popc(m);
   }
   __syncwarp();
   if (!valid) return;
   const unsigned lt = (1u << lane) - 1u;
-  auto pos = [&](int j) { return warp_start + s_slot_off[warp][j] + __popc(s_slot_mask[warp][j] & lt); };
+  auto pos = [&](int j) { return warp_start + slot_off[j] + __popc(slot_mask[j] & lt); };
   ray_start[li] = warp_start;
   ray_count[li] = c;
   float prev = -1.f;
@@ -152,11 +156,18 @@ __global__ void __launch_bounds__(128, QF_TRACE_MIN_CTAS) trace_compact_kernel(c
   }
 }
 
+// Output placement of composite_rays_kernel.  band_rows == 0: pixel of ray i at index i (compact).  band_rows > 0: the rays
+// are the band-cyclic share (qf_generate_rays_banded) of a frame `width` pixels wide and the outputs address the WHOLE
+// frame — possibly in the memory of a peer GPU (qf_peer_open): the final image gather of a ray-sharded frame then is the
+// composite kernel's own stores over NVLink, no collective and no reassembly pass.
+struct FrameMap { int band_rows, band_stride, band_offset, width; };
+
 __global__ void composite_rays_kernel(const int32_t* __restrict__ ray_start, const int32_t* __restrict__ ray_count,
                                       const float4* __restrict__ hit_pd, const float4* __restrict__ hit_out, float delta,
                                       int64_t ray0, int64_t n, int bg_mode, const float* __restrict__ bkgd,
                                       float* __restrict__ rgb, float* __restrict__ alpha_out, float* __restrict__ depth_out,
-                                      const int32_t* __restrict__ cursor, int32_t* __restrict__ hits_total, int img_w) {
+                                      const int32_t* __restrict__ cursor, int32_t* __restrict__ hits_total, int img_w,
+                                      FrameMap fm) {
   const int64_t linear = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   if (linear == 0 && hits_total) atomicAdd(hits_total, *cursor);
@@ -189,7 +200,12 @@ __global__ void composite_rays_kernel(const int32_t* __restrict__ ray_start, con
     else if (bg_mode == QF_BG_BLACK) { r = A * cr; g = A * cg; b = A * cb; }
     else { r = A * cr + (1.f - A) * bkgd[0]; g = A * cg + (1.f - A) * bkgd[1]; b = A * cb + (1.f - A) * bkgd[2]; }
   }
-  const int64_t i = ray0 + li;
+  int64_t i = ray0 + li;
+  if (fm.band_rows > 0) {   // the rays are a band-cyclic share of a frame: write the pixel where it sits in the WHOLE frame
+    const int64_t lrow = i / fm.width, col = i - lrow * fm.width;
+    const int64_t grow = ((lrow / fm.band_rows) * fm.band_stride + fm.band_offset) * fm.band_rows + lrow % fm.band_rows;
+    i = grow * fm.width + col;
+  }
   rgb[3 * i] = r; rgb[3 * i + 1] = g; rgb[3 * i + 2] = b;
   alpha_out[i] = A;
   depth_out[i] = D;
@@ -243,6 +259,27 @@ __global__ void generate_rays_indexed_kernel(const float* __restrict__ c2w, int6
   origins[3 * i] = m[3]; origins[3 * i + 1] = m[7]; origins[3 * i + 2] = m[11];
 }
 
+// The images the reference's eval loops write to disk (train_finetune.py:639-646, test_baking_texture_images.py:401-407):
+//   rgb8 = uint8(clamp(rgb, 0, 1) * 255),  depth8 = uint8(depth / depth.max() * 255)   (fp32, truncation as numpy's astype)
+// made on the device so that 4 bytes per pixel instead of 16 cross PCIe when the caller only wants the PNG-ready frame.
+__global__ void depth_max_kernel(const float* __restrict__ depth, int64_t n, int* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, depth[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_int(m));   // depths are >= 0: int order = float order
+}
+__device__ __forceinline__ unsigned char to_u8(float v) { return (v >= 0.f && v < 256.f) ? (unsigned char)(int)v : (unsigned char)0; }
+__global__ void frame_to_u8_kernel(const float* __restrict__ rgb, const float* __restrict__ depth, int64_t n,
+                                   const int* __restrict__ dmax_bits, unsigned char* __restrict__ rgb8,
+                                   unsigned char* __restrict__ depth8) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) rgb8[3 * i + c] = to_u8(__fmul_rn(fminf(fmaxf(rgb[3 * i + c], 0.f), 1.f), 255.f));
+  if (depth8) depth8[i] = to_u8(__fmul_rn(__fdiv_rn(depth[i], __int_as_float(*dmax_bits)), 255.f));
+}
+
 enum class Shade { NGP, BAKED };
 
 // Optional per-stage CUDA-event timing of the fused render (bench.py's roofline uses it): events are recorded on
@@ -263,8 +300,15 @@ static StageProfile g_prof;
 static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, const qf_texture* tex, const float* d_uv,
                          const float* d_origins, const float* d_viewdirs, int64_t n_rays, int image_width, int K, float delta, int bg_mode,
                          const float* d_bkgd, float* d_rgb, float* d_alpha, float* d_depth, int32_t* d_hits_total,
-                         void* d_workspace, size_t workspace_bytes, cudaStream_t st) {
+                         void* d_workspace, size_t workspace_bytes, cudaStream_t st, FrameMap fm = FrameMap{0, 0, 0, 0}) {
   QF_REQUIRE(mesh, "qf_render: NULL mesh");
+  if (fm.band_rows > 0) {
+    QF_REQUIRE(fm.width > 0 && fm.band_stride > 0 && fm.band_offset >= 0 && fm.band_offset < fm.band_stride,
+               "qf_render_*_to_frame: band_rows=%d band_stride=%d band_offset=%d frame_width=%d", fm.band_rows, fm.band_stride,
+               fm.band_offset, fm.width);
+    QF_REQUIRE(n_rays % ((int64_t)fm.band_rows * fm.width) == 0, "qf_render_*_to_frame: n_rays=%lld is not whole bands of %d x %d",
+               (long long)n_rays, fm.band_rows, fm.width);
+  }
   QF_REQUIRE(n_rays >= 0, "qf_render: n_rays=%lld", (long long)n_rays);
   if (n_rays == 0) {   // empty tensors carry NULL data pointers
     if (d_hits_total) QF_CUDA_CHECK(cudaMemsetAsync(d_hits_total, 0, sizeof(int32_t), st));
@@ -308,7 +352,7 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     if (rc != QF_OK) return rc;
     if (g_prof.enabled) cudaEventRecord(pe[2], st);
     composite_rays_kernel<<<(int)ceil_div(n, 256), 256, 0, st>>>(w.ray_start, w.ray_count, w.hit_pd, w.hit_out, delta, ray0, n,
-                                                                 bg_mode, d_bkgd, d_rgb, d_alpha, d_depth, w.cursor, d_hits_total, img_w);
+                                                                 bg_mode, d_bkgd, d_rgb, d_alpha, d_depth, w.cursor, d_hits_total, img_w, fm);
     QF_LAUNCH_CHECK();
     if (g_prof.enabled) { cudaEventRecord(pe[3], st); for (auto e : pe) g_prof.ev.push_back(e); }
   }
@@ -318,6 +362,77 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
 }  // namespace qf
 
 using namespace qf;
+
+extern "C" int qf_render_mesh_ngp_to_frame(const qf_mesh* mesh, const qf_ngp* field, const float* d_origins, const float* d_viewdirs,
+                                           int64_t n_rays, int K, float delta, int bg_mode, const float* d_bkgd, int band_rows,
+                                           int band_stride, int band_offset, int frame_width, float* d_frame_rgb,
+                                           float* d_frame_alpha, float* d_frame_depth, int32_t* d_hits_total, void* d_workspace,
+                                           size_t workspace_bytes, void* stream) {
+  QF_REQUIRE(field, "qf_render_mesh_ngp_to_frame: NULL field");
+  QF_REQUIRE(band_rows > 0, "qf_render_mesh_ngp_to_frame: band_rows=%d", band_rows);
+  return render_common(Shade::NGP, mesh, field, nullptr, nullptr, d_origins, d_viewdirs, n_rays, frame_width, K, delta, bg_mode, d_bkgd,
+                       d_frame_rgb, d_frame_alpha, d_frame_depth, d_hits_total, d_workspace, workspace_bytes, (cudaStream_t)stream,
+                       FrameMap{band_rows, band_stride, band_offset, frame_width});
+}
+
+extern "C" int qf_render_mesh_baked_to_frame(const qf_mesh* mesh, const qf_texture* tex, const float* d_uv_scaled,
+                                             const float* d_origins, const float* d_viewdirs, int64_t n_rays, int K, float delta,
+                                             int bg_mode, const float* d_bkgd, int band_rows, int band_stride, int band_offset,
+                                             int frame_width, float* d_frame_rgb, float* d_frame_alpha, float* d_frame_depth,
+                                             int32_t* d_hits_total, void* d_workspace, size_t workspace_bytes, void* stream) {
+  QF_REQUIRE(tex && d_uv_scaled, "qf_render_mesh_baked_to_frame: NULL texture / uv");
+  QF_REQUIRE(band_rows > 0, "qf_render_mesh_baked_to_frame: band_rows=%d", band_rows);
+  return render_common(Shade::BAKED, mesh, nullptr, tex, d_uv_scaled, d_origins, d_viewdirs, n_rays, frame_width, K, delta, bg_mode,
+                       d_bkgd, d_frame_rgb, d_frame_alpha, d_frame_depth, d_hits_total, d_workspace, workspace_bytes,
+                       (cudaStream_t)stream, FrameMap{band_rows, band_stride, band_offset, frame_width});
+}
+
+extern "C" int qf_frame_to_u8(const float* d_rgb, const float* d_depth, int64_t n_pixels, unsigned char* d_rgb8,
+                              unsigned char* d_depth8, int32_t* d_scratch, void* stream) {
+  if (n_pixels == 0) return QF_OK;
+  QF_REQUIRE(d_rgb && d_rgb8 && n_pixels > 0, "qf_frame_to_u8: NULL argument");
+  QF_REQUIRE(!d_depth8 || (d_depth && d_scratch), "qf_frame_to_u8: the depth image needs d_depth and a 4-byte scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d_depth8) {
+    QF_CUDA_CHECK(cudaMemsetAsync(d_scratch, 0, sizeof(int32_t), st));
+    depth_max_kernel<<<kNumSMs * 2, 256, 0, st>>>(d_depth, n_pixels, d_scratch);
+  }
+  frame_to_u8_kernel<<<(unsigned)ceil_div(n_pixels, 256), 256, 0, st>>>(d_rgb, d_depth, n_pixels, d_scratch, d_rgb8, d_depth8);
+  QF_LAUNCH_CHECK();
+  return QF_OK;
+}
+
+// ---- peer memory (one process per GPU): a frame buffer allocated on one rank and mapped into the others, so that their
+// composite kernels store their pixels straight into it over NVLink.  Plain cudaMalloc + CUDA IPC handles (64 opaque bytes
+// a rank passes to its peers through any host channel, e.g. torch.distributed.broadcast_object_list).
+extern "C" int qf_peer_alloc(size_t bytes, void** d_ptr) {
+  QF_REQUIRE(d_ptr && bytes > 0, "qf_peer_alloc: NULL / empty");
+  QF_CUDA_CHECK(cudaMalloc(d_ptr, bytes));
+  return QF_OK;
+}
+extern "C" int qf_peer_free(void* d_ptr) {
+  if (d_ptr) QF_CUDA_CHECK(cudaFree(d_ptr));
+  return QF_OK;
+}
+extern "C" int qf_peer_export(const void* d_ptr, unsigned char* handle64) {
+  QF_REQUIRE(d_ptr && handle64, "qf_peer_export: NULL argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  cudaIpcMemHandle_t h;
+  QF_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+  memcpy(handle64, &h, 64);
+  return QF_OK;
+}
+extern "C" int qf_peer_open(const unsigned char* handle64, void** d_ptr) {
+  QF_REQUIRE(d_ptr && handle64, "qf_peer_open: NULL argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  QF_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return QF_OK;
+}
+extern "C" int qf_peer_close(void* d_ptr) {
+  if (d_ptr) QF_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+  return QF_OK;
+}
 
 // diagnostics (not part of the ABI): work counters of the wide packet traversal, non-zero only in a -DQF_TRACE_STATS build;
 // reading resets them

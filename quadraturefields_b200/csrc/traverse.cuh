@@ -255,7 +255,11 @@ __device__ __forceinline__ void traverse_packet(const Ray& r, bool active, const
 // monotonicity in the box no descendant triangle's either.  Triangles are then tested per lane with the exact predicate
 // (slab of the triangle's own box, Möller–Trumbore, t >= tn), so results are bit-identical to the binary traversal and to
 // the brute force.  One node visit replaces ~5 levels of two-box visits in which all 32 lanes did the same test.
-constexpr int kWideStack = 256;   // entries of shared memory per warp (a visit pushes <= 32 children, depth ~ log32 F)
+// Entries of shared memory per warp.  A visit pops one entry and pushes <= 32, so a tree of L wide levels needs at most
+// 31 L + 1 entries: 192 hold the kWideLevels = 6 levels the collapse allows (32^5 leaf nodes of ~22 triangles each is far
+// beyond the 2^28-face limit of a mesh; deeper, degenerate trees clear the ok flag and are traversed as binary trees).
+// 192 rather than 256 (8 levels) lets a sixth K=32 CTA fit on the SM (35.8 KB of shared memory each).
+constexpr int kWideStack = 192;
 
 #ifdef QF_TRACE_STATS   // diagnostics build only (tools/diag_trace_stats.py): per-packet work counters of the wide traversal
 static __device__ unsigned long long g_trace_stats[8];

@@ -97,6 +97,83 @@ def gather_frame(parts: torch.Tensor, sizes: Sequence[int], dst: int = 0) -> Opt
     return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0) if rank == dst else None
 
 
+class PeerFrame:
+    """Frame buffers of a ray-sharded frame in the memory of ONE rank (`dst`), mapped into every other rank of the node over
+    CUDA IPC (NVLink peer access): each rank's composite kernel stores its band-cyclic share of the pixels straight into
+    them (`MeshRenderer.render_pose(bands=..., frame=...)`), so the final image gather is those stores — no gather
+    collective, no concatenate / reassembly pass.  `sync()` is the only collective: a 4-byte all-reduce that orders every
+    rank's stores before `dst` reads the frame (and `dst`'s reads of slot b before the peers' next stores to it).
+
+    Collective constructor (every rank of the default process group calls it).  `slots` buffers rotate so that the ranks
+    may run one frame ahead of the consumer.  Layout of a slot: rgb (H*W,3) | opacity (H*W,1) | depth (H*W,1), fp32."""
+
+    def __init__(self, height: int, width: int, device, dst: int = 0, slots: int = 2):
+        import ctypes as C
+        from . import _lib
+        self.H, self.W, self.dst, self.slots = height, width, dst, slots
+        self.device = torch.device(device)
+        self.rank, self.world = world()
+        self._lib = lib = _lib.load()
+        n = height * width
+        self.slot_bytes = n * 5 * 4
+        self._owned = self._mapped = None
+        base = C.c_void_p()
+        if self.rank == dst:
+            _lib.check(lib.qf_peer_alloc(self.slot_bytes * slots, C.byref(base)), "qf_peer_alloc")
+            self._owned = base.value
+        handle = [None]
+        if self.world > 1:
+            if self.rank == dst:
+                buf = C.create_string_buffer(64)
+                _lib.check(lib.qf_peer_export(C.c_void_p(self._owned), buf), "qf_peer_export")
+                handle = [buf.raw]
+            dist.broadcast_object_list(handle, src=dst)
+            if self.rank != dst:
+                _lib.check(lib.qf_peer_open(handle[0], C.byref(base)), "qf_peer_open")
+                self._mapped = base.value
+        self.base = base.value
+        self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
+
+    def pointers(self, slot: int):
+        """(rgb, opacity, depth) device addresses of `slot` as seen from THIS rank."""
+        n = self.H * self.W
+        b = self.base + (slot % self.slots) * self.slot_bytes
+        return b, b + n * 12, b + n * 16
+
+    def frame(self, slot: int):
+        """On `dst`: the (rgb (N,3), opacity (N,1), depth (N,1)) tensors viewing `slot` (no copy); None elsewhere."""
+        if self.rank != self.dst:
+            return None
+        n = self.H * self.W
+
+        class _Mem:      # __cuda_array_interface__ holder: lets torch view memory this library allocated
+            pass
+        out = []
+        for ptr, shape in zip(self.pointers(slot), ((n, 3), (n, 1), (n, 1))):
+            m = _Mem()
+            m.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+            out.append(torch.as_tensor(m, device=self.device))
+        return tuple(out)
+
+    def sync(self):
+        """Stream-ordered fence over all ranks (current stream): after it, `dst` sees every rank's stores of the frames
+        rendered before it."""
+        if self.world > 1:
+            dist.all_reduce(self._flag)
+
+    def close(self):
+        if self._mapped:
+            torch.cuda.synchronize(self.device)
+            self._lib.qf_peer_close(self._mapped)
+            self._mapped = None
+        if self.world > 1:
+            dist.barrier()          # every mapping is closed before the owner frees the allocation
+        if self._owned:
+            torch.cuda.synchronize(self.device)
+            self._lib.qf_peer_free(self._owned)
+            self._owned = None
+
+
 def all_reduce_gradients(params: Sequence[torch.Tensor], n_local, n_global=None) -> None:
     """Training mode: sum the per-rank gradients of the (replicated) hash table and MLPs — large tensors in place,
     the small ones in one flat bucket — and rescale a per-rank MEAN loss to the global sample count: every rank's

@@ -184,10 +184,57 @@ class MeshRenderer:
         return out
 
 
+    def frame_to_uint8(self, out: dict, rgb8: Optional[torch.Tensor] = None, depth8: Optional[torch.Tensor] = None,
+                       with_depth: bool = True):
+        """The images the reference's eval loops save (train_finetune.py:639-646): `rgb8 = uint8(clamp(rgb,0,1)*255)` (N,3)
+        and `depth8 = uint8(depth / depth.max() * 255)` (N,), made on the device from a `render` dict — a quarter of the
+        bytes of the fp32 frame to bring to the host.  -> (rgb8, depth8 or None), CUDA uint8 tensors."""
+        lib = _lib.load()
+        dev = self.device
+        rgb, depth = out["rgb"], out["depth"]
+        n = rgb.shape[0]
+        if rgb8 is None:
+            rgb8 = torch.empty((n, 3), dtype=torch.uint8, device=dev)
+        if with_depth and depth8 is None:
+            depth8 = torch.empty((n,), dtype=torch.uint8, device=dev)
+        if not with_depth:
+            depth8 = None
+        if getattr(self, "_u8_scratch", None) is None:
+            self._u8_scratch = torch.zeros((1,), dtype=torch.int32, device=dev)
+        _lib.check(lib.qf_frame_to_u8(_lib.ptr(rgb), _lib.ptr(depth), n, _lib.ptr(rgb8), _lib.ptr(depth8), _lib.ptr(self._u8_scratch),
+                                      _lib.stream(dev)), "qf_frame_to_u8")
+        return rgb8, depth8
+
+    def _render_to_frame(self, o, d, bg_color, render_bkgd, hits_out, W, band, ptrs):
+        """The fused render of a band-cyclic share with its pixels stored into whole-frame buffers (`ptrs`: raw device
+        addresses of rgb / opacity / depth, local or peer-mapped)."""
+        lib = _lib.load()
+        dev = self.device
+        N = o.shape[0]
+        if N == 0:
+            return None
+        ws = _lib.workspace(dev, lib.qf_render_workspace_bytes(N, self.K), "render")
+        bk = _lib.f32(render_bkgd, dev) if render_bkgd is not None else None
+        bg = _lib.BG_MODES.get(bg_color, 2)
+        hits = self._hits if hits_out is None else hits_out
+        mesh = self.mi.rayintersector.handle
+        p_rgb, p_a, p_d = (C.c_void_p(p) for p in ptrs)
+        if self.compressor is not None:
+            _lib.check(lib.qf_render_mesh_baked_to_frame(mesh, self.compressor.native(), _lib.ptr(self.uv), _lib.ptr(o), _lib.ptr(d), N,
+                                                         self.K, self.delta, bg, _lib.ptr(bk), band[0], band[1], band[2], int(W),
+                                                         p_rgb, p_a, p_d, _lib.ptr(hits), _lib.ptr(ws), ws.numel(), _lib.stream(dev)),
+                       "qf_render_mesh_baked_to_frame")
+        else:
+            _lib.check(lib.qf_render_mesh_ngp_to_frame(mesh, self.field._native(), _lib.ptr(o), _lib.ptr(d), N, self.K, self.delta, bg,
+                                                       _lib.ptr(bk), band[0], band[1], band[2], int(W), p_rgb, p_a, p_d,
+                                                       _lib.ptr(hits), _lib.ptr(ws), ws.numel(), _lib.stream(dev)),
+                       "qf_render_mesh_ngp_to_frame")
+        return None
+
     @torch.no_grad()
     def render_pose(self, c2w, W: int, H: int, focal: float, cx: float, cy: float, bg_color="white", render_bkgd=None, out=None,
                     hits_out: Optional[torch.Tensor] = None, opengl: bool = True, rows: Optional[tuple] = None,
-                    bands: Optional[tuple] = None):
+                    bands: Optional[tuple] = None, frame=None, frame_slot: int = 0):
         """The evaluation frame of the reference from its real input: a 3x4 camera-to-world pose on the HOST.  The reference's
         `SubjectLoader.fetch_data` builds the W*H rays on the device from the pose (nerf_synthetic.py:289-378) and the eval
         loop renders them (train_finetune.py:586-617); here: `qf_generate_rays` (the 48-byte pose travels as kernel
@@ -195,7 +242,10 @@ class MeshRenderer:
         `rows=(r0, r1)` renders only image rows [r0, r1) — a rank's contiguous band of a ray-sharded frame.
         `bands=(rank, world)` renders the rank's band-CYCLIC share instead: the 4-row bands b with b % world == rank, compact
         and in order (`parallel.assemble_banded` puts the shares back together); hit counts vary a lot over an image, and
-        dealing the bands round-robin balances the ranks.  -> the `render` dict (of the rendered rows only)."""
+        dealing the bands round-robin balances the ranks.  -> the `render` dict (of the rendered rows only).
+        `frame` (with `bands`): a `parallel.PeerFrame`; the share's pixels are stored where they sit in slot `frame_slot` of
+        the WHOLE frame, which lives on the gathering rank (peer memory over NVLink) — the image gather of a ray-sharded
+        frame without a collective (`frame.sync()` afterwards orders the stores before the reader).  -> None."""
         lib = _lib.load()
         dev = self.device
         m = np.ascontiguousarray(np.asarray(c2w.cpu() if isinstance(c2w, torch.Tensor) else c2w, dtype=np.float32)[:3, :4])
@@ -215,6 +265,8 @@ class MeshRenderer:
                                                    1 if opengl else 0, 4, world, rank, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)),
                        "qf_generate_rays_banded")
             o, d = o[:n_rows * W], d[:n_rows * W]
+            if frame is not None:
+                return self._render_to_frame(o, d, bg_color, render_bkgd, hits_out, W, (4, world, rank), frame.pointers(frame_slot))
             return self.render(o, d, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out, image_width=W)
         _lib.check(lib.qf_generate_rays(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
                                         1 if opengl else 0, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)), "qf_generate_rays")

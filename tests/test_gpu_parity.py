@@ -650,6 +650,72 @@ def test_render_pose_matches_ray_render_and_bands(dev, smoke_scene):
         assert torch.equal(P.assemble_banded(parts, sc.H, W), torch.cat([ref["rgb"], ref["opacity"], ref["depth"]], dim=1))
 
 
+def test_render_pose_into_whole_frame_buffers(dev, smoke_scene):
+    """Ray-sharded frames without a gather: `render_pose(bands=(r, world), frame=PeerFrame)` stores every share's pixels
+    where they sit in the WHOLE frame (`qf_render_mesh_ngp_to_frame` / `_baked_to_frame`; on several GPUs the frame is
+    peer memory of the gathering rank).  One process here: the shares of all `world` ranks written one after the other into
+    the same local frame must give the full-frame render bit for bit, for the neural and the baked shading, both frame
+    slots, and the CUDA IPC handle of the buffer must export."""
+    import ctypes as C
+    from quadraturefields_b200 import _lib, parallel as P, scene as S
+    lib = _lib.load()
+    sc = smoke_scene
+    ref = {k: v.clone() for k, v in sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy).items()}
+    pf = P.PeerFrame(sc.H, sc.W, dev, slots=2)
+    try:
+        buf = C.create_string_buffer(64)
+        _lib.check(lib.qf_peer_export(C.c_void_p(pf.base), buf), "qf_peer_export")
+        assert any(buf.raw)
+        for slot, world in ((0, 2), (1, 5), (2, 3)):
+            rgb, op, dp = pf.frame(slot)
+            rgb.fill_(-7.0); op.fill_(-7.0); dp.fill_(-7.0)
+            hits = torch.zeros((world, 1), dtype=torch.int32, device=dev)
+            for r in range(world):
+                assert sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy, bands=(r, world), frame=pf,
+                                               frame_slot=slot, hits_out=hits[r]) is None
+            pf.sync()
+            assert torch.equal(rgb, ref["rgb"]) and torch.equal(op, ref["opacity"]) and torch.equal(dp, ref["depth"])
+            assert int(hits.sum()) == int(ref["n_hits"])
+        assert pf.pointers(2) == pf.pointers(0) and pf.pointers(1) != pf.pointers(0)
+    finally:
+        pf.close()
+    # baked shading through the same output mapping
+    scb = S.make_scene("c5_small", device=dev, H=88, build_field=False)
+    refb = {k: v.clone() for k, v in scb.baked_renderer.render_pose(scb.poses[0], scb.W, scb.H, scb.focal, scb.cx, scb.cy).items()}
+    pfb = P.PeerFrame(scb.H, scb.W, dev, slots=1)
+    try:
+        for r in range(3):
+            scb.baked_renderer.render_pose(scb.poses[0], scb.W, scb.H, scb.focal, scb.cx, scb.cy, bands=(r, 3), frame=pfb)
+        rgb, op, dp = pfb.frame(0)
+        assert torch.equal(rgb, refb["rgb"]) and torch.equal(op, refb["opacity"]) and torch.equal(dp, refb["depth"])
+    finally:
+        pfb.close()
+    # argument errors of the new entry points
+    with pytest.raises(RuntimeError):
+        sc.renderer._render_to_frame(*sc.rays(0), "white", None, None, sc.W, (0, 2, 0), (pf.base, pf.base, pf.base))
+
+
+def test_frame_to_uint8_matches_the_reference_expressions(dev, smoke_scene):
+    """`MeshRenderer.frame_to_uint8` = the images the reference's eval loop writes (train_finetune.py:639-646):
+    (clamp(rgb,0,1).cpu().numpy() * 255).astype(uint8) and ((depth / depth.max()).cpu().numpy() * 255).astype(uint8), bit
+    for bit; out-of-range and NaN inputs follow clamp / map to 0."""
+    sc = smoke_scene
+    out = sc.renderer.render_pose(sc.poses[0], sc.W, sc.H, sc.focal, sc.cx, sc.cy, bg_color="white")
+    rgb8, depth8 = sc.renderer.frame_to_uint8(out)
+    ref_rgb = (torch.clamp(out["rgb"], 0, 1).cpu().numpy() * 255).astype(np.uint8)
+    d = out["depth"].reshape(-1)
+    ref_depth = ((d / d.max()).cpu().numpy() * 255).astype(np.uint8)
+    assert rgb8.dtype == torch.uint8 and np.array_equal(rgb8.cpu().numpy(), ref_rgb)
+    assert np.array_equal(depth8.cpu().numpy(), ref_depth)
+    assert int(depth8.max()) == 255 and len(np.unique(ref_rgb)) > 20
+    weird = dict(rgb=torch.tensor([[-0.5, 0.25, 1.5], [float("nan"), 1.0, 0.999999]], device=dev),
+                 depth=torch.tensor([[0.0], [0.0]], device=dev))
+    r8, d8 = sc.renderer.frame_to_uint8(weird)
+    assert r8.cpu().tolist() == [[0, 63, 255], [0, 255, 254]] and d8.cpu().tolist() == [0, 0]
+    r8b, none = sc.renderer.frame_to_uint8(out, with_depth=False)
+    assert none is None and torch.equal(r8b, rgb8)
+
+
 def test_graphed_train_step_matches_eager(dev):
     """`utils.GraphedTrainStep` (the training step replayed from CUDA graphs on fixed-capacity, dummy-padded buffers) against
     the eager step (`render_train` + smooth-L1 + backward + Adam) from the same initial parameters and the same batches:
