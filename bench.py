@@ -272,10 +272,10 @@ def run_ours(args):
     value = N * world * args.steps / (ms_total * 1e-3)
 
     # ---- e2e: reference-facing call with HOST buffers (pinned rays in, image out), copies inside the timed region.
-    # Three streams, double-buffered: H2D of frame i+1 and D2H of frame i-1 overlap the render of frame i.
+    # H2D, D2H and NB compute streams over NB slots: H2D of frame i+1 and D2H of frame i-1 overlap the render of frame i.
     n_host = min(n_views, 8)
     host_rays = [(rays[v][0].cpu().pin_memory(), rays[v][1].cpu().pin_memory()) for v in range(n_host)]
-    NB = 3
+    NB = 4          # slots in flight: with 3 a render waited for the D2H of its slot (r2i: 0.267 -> 0.238 ms per frame, = render only)
     host_out = [dict(rgb=torch.empty((N, 3)).pin_memory(), opacity=torch.empty((N, 1)).pin_memory(),
                      depth=torch.empty((N, 1)).pin_memory()) for _ in range(NB)]
     d_in = [(torch.empty((N, 3), device=dev), torch.empty((N, 3), device=dev)) for _ in range(NB)]
@@ -322,7 +322,7 @@ def run_ours(args):
     e2e_value = N * world * args.steps / (float(ms_e.item()) * 1e-3)
     # ---- e2e, the reference's real eval input: a 48-byte camera pose on the HOST per frame (its loader builds the rays on
     # the device, nerf_synthetic.py:289-378), image (rgb + depth, what the eval loop takes back, train_finetune.py:620-626)
-    # device->host into pinned memory every step.  Two compute streams so the D2H of frame i overlaps frame i+1.
+    # device->host into pinned memory every step.  NB slots / compute streams so the D2H of frame i overlaps the next frames.
     pose_host = [dict(rgb=torch.empty((N, 3)).pin_memory(), depth=torch.empty((N, 1)).pin_memory()) for _ in range(NB)]
     from quadraturefields_b200.utils import MeshRenderer
     pose_renderers = [MeshRenderer(sc.mesh_intersect, radiance_field=sc.radiance_field) for _ in range(NB)]   # private ray scratch per slot

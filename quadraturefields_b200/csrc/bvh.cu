@@ -598,6 +598,47 @@ static int dev_alloc(T** p, size_t count, size_t* total) {
   return QF_OK;
 }
 
+// Build scratch (Morton keys, Karras hierarchy, per-node boxes, radix-sort and collapse queues): needed by build() only.
+static int alloc_build_scratch(qf_mesh* m) {
+  if (m->d_keys) return QF_OK;
+  const size_t F = (size_t)m->n_faces;
+  size_t before = m->bytes;
+  int rc = QF_OK;
+#define QF_A(call) if (rc == QF_OK) rc = (call)
+  QF_A(dev_alloc(&m->d_keys, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_keys_sorted, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_idx, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_idx_sorted, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_left, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_right, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_parent, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_leaf_parent, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_first, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_last, F, &m->bytes));
+  QF_A(dev_alloc(&m->d_flags, F + 8, &m->bytes));
+  QF_A(dev_alloc(&m->d_ibox, 2 * F, &m->bytes));
+  if (m->want_wide) QF_A(dev_alloc(&m->d_wqueue, (size_t)(F / 4 + 64), &m->bytes));
+#undef QF_A
+  if (rc == QF_OK) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_keys, m->d_keys_sorted, m->d_idx, m->d_idx_sorted, (int)F, 0, 63, (cudaStream_t)0);
+    m->sort_tmp_bytes = tmp;
+    if (cudaMalloc(&m->d_sort_tmp, tmp ? tmp : 16) != cudaSuccess) { set_error("qf_mesh: sort scratch alloc failed"); rc = QF_ERR_CUDA; }
+    else m->bytes += tmp;
+  }
+  m->scratch_bytes = m->bytes - before;
+  return rc;
+}
+
+static void free_build_scratch(qf_mesh* m) {
+  void** ptrs[] = {(void**)&m->d_keys, (void**)&m->d_keys_sorted, (void**)&m->d_idx, (void**)&m->d_idx_sorted, (void**)&m->d_left,
+                   (void**)&m->d_right, (void**)&m->d_parent, (void**)&m->d_leaf_parent, (void**)&m->d_first, (void**)&m->d_last,
+                   (void**)&m->d_flags, (void**)&m->d_ibox, (void**)&m->d_wqueue, &m->d_sort_tmp};
+  for (void** p : ptrs) if (*p) { cudaFree(*p); *p = nullptr; }
+  m->bytes -= m->scratch_bytes;
+  m->scratch_bytes = 0;
+}
+
 }  // namespace qf
 
 using namespace qf;
@@ -621,34 +662,16 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
   QF_A(dev_alloc(&m->d_planes, F, &m->bytes));
   QF_A(dev_alloc(&m->d_nodes, 4 * F, &m->bytes));
   QF_A(dev_alloc(&m->d_scene, 8, &m->bytes));
-  QF_A(dev_alloc(&m->d_keys, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_keys_sorted, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_idx, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_idx_sorted, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_left, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_right, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_parent, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_leaf_parent, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_first, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_last, F, &m->bytes));
-  QF_A(dev_alloc(&m->d_flags, F + 8, &m->bytes));
-  QF_A(dev_alloc(&m->d_ibox, 2 * F, &m->bytes));
   QF_A(dev_alloc(&m->d_call_slots, 4 * kCallSlots, &m->bytes));
   // wide nodes: ~F/22 in practice (leaf nodes hold 17-32 triangles); room for F/8 + 64, the collapse falls back to the
   // binary tree if a pathological mesh needs more.  QF_WIDE_BVH=0 disables the wide tree.
   const bool want_wide = !(getenv("QF_WIDE_BVH") && atoi(getenv("QF_WIDE_BVH")) == 0);
   const int64_t queue_capacity = (int64_t)(F / 4 + 64);      // ints only; the node array is sized after a dry run below
-  if (want_wide) {
-    QF_A(dev_alloc(&m->d_wqueue, (size_t)queue_capacity, &m->bytes));
-    QF_A(dev_alloc(&m->d_wstate, 8, &m->bytes));
-  }
+  m->want_wide = want_wide;
+  if (want_wide) QF_A(dev_alloc(&m->d_wstate, 8, &m->bytes));
+  QF_A(alloc_build_scratch(m));
 #undef QF_A
   if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
-  size_t tmp = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, tmp, m->d_keys, m->d_keys_sorted, m->d_idx, m->d_idx_sorted, (int)F, 0, 63, st);
-  m->sort_tmp_bytes = tmp;
-  if (cudaMalloc(&m->d_sort_tmp, tmp ? tmp : 16) != cudaSuccess) { set_error("qf_mesh_create: sort scratch alloc failed"); qf_mesh_destroy(m); return QF_ERR_CUDA; }
-  m->bytes += tmp;
   cudaError_t e = cudaMemcpyAsync(m->d_faces, d_faces, sizeof(int32_t) * 3 * F, cudaMemcpyDeviceToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * n_vertices, cudaMemcpyDeviceToDevice, st);
   if (e != cudaSuccess) { set_error("qf_mesh_create: copy failed: %s", cudaGetErrorString(e)); qf_mesh_destroy(m); return QF_ERR_CUDA; }
@@ -676,6 +699,10 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
     if (e != cudaSuccess) { set_error("qf_mesh_create: build failed: %s", cudaGetErrorString(e)); rc = QF_ERR_CUDA; }
   }
   if (rc != QF_OK) { qf_mesh_destroy(m); return rc; }
+  // A mesh that is only rendered never rebuilds: give the build scratch back (97 of 302 bytes per triangle: 111 MB of the
+  // 346 MB of a 1.15 M-triangle mesh).  The first qf_mesh_update_vertices allocates it again and keeps it from then on, so a
+  // training loop that moves the vertices every step allocates once.  QF_MESH_KEEP_SCRATCH=1 keeps it from the start.
+  if (!(getenv("QF_MESH_KEEP_SCRATCH") && atoi(getenv("QF_MESH_KEEP_SCRATCH")) != 0)) free_build_scratch(m);
   *out = m;
   return QF_OK;
 }
@@ -683,6 +710,7 @@ extern "C" int qf_mesh_create(const float* d_vertices, int64_t n_vertices, const
 extern "C" int qf_mesh_update_vertices(qf_mesh* m, const float* d_vertices, void* stream) {
   QF_REQUIRE(m && d_vertices, "qf_mesh_update_vertices: NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
+  { int rc0 = alloc_build_scratch(m); if (rc0 != QF_OK) return rc0; }     // no-op while the scratch is held
   QF_CUDA_CHECK(cudaMemcpyAsync(m->d_vertices, d_vertices, sizeof(float) * 3 * m->n_vertices, cudaMemcpyDeviceToDevice, st));
   ++m->geometry_version;      // per-triangle caches derived from the vertices (baked path) are rebuilt on next use
   int rc = build(m, st);

@@ -64,7 +64,7 @@ struct qf_mesh {
   int32_t* d_wstate = nullptr;    // [0] level begin, [1] level end, [2] wide nodes allocated, [3] ok flag, [4] level
   int64_t wide_capacity = 0;      // wide nodes that fit in d_wnodes
   float* d_scene = nullptr;       // [0..2] lo, [3..5] hi, [6] pad
-  // build scratch (kept so update_vertices does not allocate)
+  // build scratch (bvh.cu alloc_build_scratch / free_build_scratch)
   uint64_t *d_keys = nullptr, *d_keys_sorted = nullptr;
   uint32_t *d_idx = nullptr, *d_idx_sorted = nullptr;
   int32_t *d_left = nullptr, *d_right = nullptr, *d_parent = nullptr, *d_leaf_parent = nullptr;
@@ -75,6 +75,8 @@ struct qf_mesh {
   int32_t* d_call_slots = nullptr;  // ring of per-call scratch: [coherent chunks, total chunks, ray counter, pad]
   mutable std::atomic<unsigned> call_id{0};   // concurrent qf_trace_firstk calls on one mesh take distinct slots
   size_t bytes = 0;
+  size_t scratch_bytes = 0;       // part of `bytes` that is build scratch (released after create, back on the first vertex update)
+  bool want_wide = true;
   float h_pad = 0.f;
   float restart_eps = 0.f;        // > 0: keep hits like the reference's Embree restart loop (qf_mesh_set_restart_eps)
   // baked path: per-triangle barycentric setup (128 B: v0, e0, e1, d00, d01, d11, 1/den as doubles + the three uv pairs),

@@ -205,17 +205,23 @@ def all_reduce_gradients(params: Sequence[torch.Tensor], n_local, n_global=None)
     else:
         scale = float(n_local) / float(n_global)
     unit = isinstance(scale, float) and scale == 1.0
+    # equal shares (scale == 1 / world) on NCCL: the collective averages by itself (ReduceOp.AVG) — no separate scaling pass
+    # over the 50 MB table gradient (a 100 MB read-modify-write per step); gloo has no AVG and keeps the explicit scale
+    avg = (isinstance(scale, float) and not unit and abs(scale * ws - 1.0) < 1e-12 and dist.get_backend() == "nccl")
+    op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+    if avg:
+        unit = True
     big = [g for g in grads if g.numel() >= (1 << 20) and g.is_contiguous()]
     small = [g for g in grads if not (g.numel() >= (1 << 20) and g.is_contiguous())]
     for g in big:                       # the hash table: reduced in place, no flatten / copy-back of tens of MB
         if not unit:
             g.mul_(scale)
-        dist.all_reduce(g)
+        dist.all_reduce(g, op=op)
     if small:                           # MLP matrices and biases: one bucket, one launch-latency-bound collective
         flat = torch.cat([g.reshape(-1) for g in small])
         if not unit:
             flat.mul_(scale)
-        dist.all_reduce(flat)
+        dist.all_reduce(flat, op=op)
         torch._foreach_copy_(small, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in small]), small)])
 
 
