@@ -148,12 +148,18 @@ class MeshRenderer:
 
     @torch.no_grad()
     def render(self, origins: torch.Tensor, viewdirs: torch.Tensor, bg_color="white", render_bkgd=None, out=None,
-               hits_out: Optional[torch.Tensor] = None, image_width: Optional[int] = None):
+               hits_out: Optional[torch.Tensor] = None, image_width: Optional[int] = None, frame_out: Optional[tuple] = None):
         """-> dict(rgb (N,3), opacity (N,1), depth (N,1), n_hits (device int32 tensor)).
         `hits_out`: optional 1-element int32 CUDA tensor (e.g. a slot of a per-step buffer) receiving the hit count.
-        `image_width`: the rays are a row-major image of that width ((H,W,3) inputs imply it) — a pure speed hint."""
+        `image_width`: the rays are a row-major image of that width ((H,W,3) inputs imply it) — a pure speed hint.
+        `frame_out`: raw device addresses (rgb, opacity, depth) of frame buffers to store the image into instead of `out` —
+        e.g. a slot of a `parallel.PeerFrame` in another GPU's memory (the final image gather as the composite kernel's own
+        stores); needs `image_width` and whole 4-row bands.  -> None."""
         if image_width is None:
             image_width = origins.shape[1] if origins.dim() == 3 else 0
+        if frame_out is not None:
+            return self._render_to_frame(_lib.f32(origins.reshape(-1, 3), self.device), _lib.f32(viewdirs.reshape(-1, 3), self.device),
+                                         bg_color, render_bkgd, hits_out, int(image_width), (4, 1, 0), frame_out)
         lib = _lib.load()
         dev = self.device
         o = _lib.f32(origins.reshape(-1, 3), dev)
@@ -304,7 +310,7 @@ class FramePipeline:
             if after is not None:
                 st.wait_event(after)
             res = self.renderer.render(origins, viewdirs, out=out, **kw)
-        if out is None:
+        if out is None and res is not None:
             # allocated on the pipeline stream but consumed by the caller's stream after join(): tell the allocator
             for t in res.values():
                 if isinstance(t, torch.Tensor):

@@ -677,6 +677,12 @@ def test_render_pose_into_whole_frame_buffers(dev, smoke_scene):
             assert torch.equal(rgb, ref["rgb"]) and torch.equal(op, ref["opacity"]) and torch.equal(dp, ref["depth"])
             assert int(hits.sum()) == int(ref["n_hits"])
         assert pf.pointers(2) == pf.pointers(0) and pf.pointers(1) != pf.pointers(0)
+        # a whole frame from a ray list into raw frame addresses (`render(frame_out=...)`: the last-frame gather of the bench)
+        rgb, op, dp = pf.frame(1)
+        rgb.fill_(-7.0); op.fill_(-7.0); dp.fill_(-7.0)
+        o1, d1 = sc.rays(1)
+        assert sc.renderer.render(o1, d1, image_width=sc.W, frame_out=pf.pointers(1)) is None
+        assert torch.equal(rgb, ref["rgb"]) and torch.equal(op, ref["opacity"]) and torch.equal(dp, ref["depth"])
     finally:
         pf.close()
     # baked shading through the same output mapping
