@@ -117,20 +117,38 @@ class PeerFrame:
         n = height * width
         self.slot_bytes = n * 5 * 4
         self._owned = self._mapped = None
+        # Either every rank ends up with a usable mapping or every rank raises: a rank that fails never leaves its peers
+        # waiting in a collective the others did not enter.
         base = C.c_void_p()
+        err = None
+        handle = None
         if self.rank == dst:
-            _lib.check(lib.qf_peer_alloc(self.slot_bytes * slots, C.byref(base)), "qf_peer_alloc")
-            self._owned = base.value
-        handle = [None]
+            try:
+                _lib.check(lib.qf_peer_alloc(self.slot_bytes * slots, C.byref(base)), "qf_peer_alloc")
+                self._owned = base.value
+                if self.world > 1:
+                    buf = C.create_string_buffer(64)
+                    _lib.check(lib.qf_peer_export(C.c_void_p(self._owned), buf), "qf_peer_export")
+                    handle = buf.raw
+            except Exception as e:                       # noqa: BLE001 - reported to every rank below
+                err = f"{type(e).__name__}: {e}"
         if self.world > 1:
-            if self.rank == dst:
-                buf = C.create_string_buffer(64)
-                _lib.check(lib.qf_peer_export(C.c_void_p(self._owned), buf), "qf_peer_export")
-                handle = [buf.raw]
-            dist.broadcast_object_list(handle, src=dst)
-            if self.rank != dst:
-                _lib.check(lib.qf_peer_open(handle[0], C.byref(base)), "qf_peer_open")
-                self._mapped = base.value
+            box = [(handle, err)]
+            dist.broadcast_object_list(box, src=dst)
+            handle, err = box[0]
+            if err is None and self.rank != dst:
+                try:
+                    _lib.check(lib.qf_peer_open(handle, C.byref(base)), "qf_peer_open")
+                    self._mapped = base.value
+                except Exception as e:                   # noqa: BLE001
+                    err = f"rank {self.rank}: {type(e).__name__}: {e}"
+            ok = torch.tensor([0.0 if err else 1.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 1.0:
+                self.close()
+                raise RuntimeError(f"PeerFrame: peer mapping failed ({err or 'on another rank'})")
+        elif err is not None:
+            raise RuntimeError(f"PeerFrame: {err}")
         self.base = base.value
         self._flag = torch.zeros((1,), dtype=torch.float32, device=self.device)
 

@@ -25,6 +25,14 @@ extra)
   $XCMD > gpurun_out/plain_extra_$TAG.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'baked_shade_kernel|trace_compact_kernel|composite_rays_kernel' -s 12 -c 3 -o gpurun_out/prof_extra_$TAG $XCMD > gpurun_out/ncu_extra_$TAG.log 2>&1
   tail -3 gpurun_out/ncu_extra_$TAG.log ;;
+misc)
+  # the remaining kernels of the path: segmented-scan compositing, the quadrature Field net, the occupancy-grid marcher
+  MCMD="python tools/run_field_legs.py 5"
+  $MCMD > gpurun_out/plain_misc_$TAG.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:'render_weights|field_net_forward|field_net_backward|occgrid_march|accumulate_|derive_properties' -s 40 -c 14 -o gpurun_out/prof_misc_$TAG $MCMD > gpurun_out/ncu_misc_$TAG.log 2>&1
+  tail -3 gpurun_out/ncu_misc_$TAG.log
+  ncu --set full --clock-control none --import-source on -k regex:'occgrid_march' -s 6 -c 1 -o gpurun_out/prof_misc2_$TAG $MCMD > gpurun_out/ncu_misc2_$TAG.log 2>&1
+  tail -2 gpurun_out/ncu_misc2_$TAG.log ;;
 train)
   TCMD="python tools/diag_train.py 3"
   $TCMD > gpurun_out/plain_train_$TAG.log 2>&1 &&

@@ -26,14 +26,16 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"]
 lines = [f"# ncu summary `{tag}`", "",
          "Source: `ncu --set full --clock-control none --import-source on` on `python bench.py --steps 2 --warmup 3 --views 8 "
-         "--no-cpu-baseline --no-train` (configs[1] frame: trace_compact<HitBufReg<8>>, ngp_forward_tc_kernel), `python "
+         "--no-cpu-baseline --no-train` (configs[1] frame: trace_compact<HitBufSmemT<8>>, ngp_forward_tc_kernel), `python "
          "tools/run_leg.py c5 3` (configs[4] 4K baked frame: trace_compact<HitBufSmem>, baked_shade_kernel) and `python "
-         "tools/diag_train.py 3` (training step kernels); B200, one GPU, tools/gpu_profile.sh.  Per-launch values; cold-cache, "
+         "tools/diag_train.py 3` (training step kernels) and `python tools/run_field_legs.py 5` (quadrature-field legs: "
+         "render_weights / field_net / occgrid_march kernels); B200, one GPU, tools/gpu_profile.sh.  Per-launch values; cold-cache, "
          "serialised — compare shares, not absolutes.", ""]
 import os
 traffic = {}
 seen = set()
-for rep in (f"gpurun_out/prof_{tag}.ncu-rep", f"gpurun_out/prof_extra_{tag}.ncu-rep", f"gpurun_out/prof_train_{tag}.ncu-rep"):
+for rep in (f"gpurun_out/prof_{tag}.ncu-rep", f"gpurun_out/prof_extra_{tag}.ncu-rep", f"gpurun_out/prof_train_{tag}.ncu-rep",
+            f"gpurun_out/prof_misc_{tag}.ncu-rep", f"gpurun_out/prof_misc2_{tag}.ncu-rep"):
     if not os.path.exists(rep):
         continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
