@@ -1009,6 +1009,19 @@ def test_full_size_c4_shelly_shaped(dev):
     o_s, d_s = o.cpu().numpy()[sub], d.cpu().numpy()[sub]
     tri_ref, _, count_ref, _ = O.intersect_firstk_c(o_s, d_s, sc.vertices_np, sc.faces_np, sc.K)
     assert np.array_equal(tri.cpu().numpy()[sub], tri_ref) and np.array_equal(count.cpu().numpy()[sub], count_ref)
+    # every 16th 8x4 pixel tile — whole traversal packets, 129 600 rays — through the C BVH oracle (bit-identical to the brute
+    # force, tests/test_oracle_golden.py::test_c_bvh_matches_bruteforce): ids in order and counts, bit for bit
+    import os
+    ty, tx = torch.meshgrid(torch.arange(sc.H // 4), torch.arange(sc.W // 8), indexing="ij")
+    keep = ((ty * (sc.W // 8) + tx) % 16 == 5)
+    pix = keep.repeat_interleave(4, dim=0).repeat_interleave(8, dim=1).reshape(-1)
+    tiles = torch.nonzero(pix).reshape(-1)
+    assert tiles.numel() == N // 16
+    O.set_c_threads(os.cpu_count() or 1)
+    tri_t, _, count_t, _ = O.intersect_firstk_bvh_c(o.cpu().numpy()[tiles], d.cpu().numpy()[tiles], sc.vertices_np, sc.faces_np, sc.K,
+                                                   want_total=False)
+    assert np.array_equal(count.cpu().numpy()[tiles], count_t) and np.array_equal(tri.cpu().numpy()[tiles], tri_t)
+    assert int(count_t.sum()) > 6 * tiles.numel()
     ref = O.render_mesh_ngp(o_s, d_s, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
     assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
 
