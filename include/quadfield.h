@@ -127,7 +127,8 @@ void qf_ngp_destroy(qf_ngp* f);
 
 /* tcnn HashGrid forward alone: x01 (M,3) in [0,1] -> (M, 2*n_levels) fp32 holding fp16-rounded features. */
 int qf_hashgrid_forward(const qf_ngp* f, const float* d_x01, int64_t M, float* d_enc, void* stream);
-/* tcnn HashGrid backward alone: ACCUMULATES dL/dtable (n_entries,2) from dL/denc (M, 2*n_levels) at x01 (M,3). */
+/* tcnn HashGrid backward alone: ACCUMULATES dL/dtable (n_entries,2) from dL/denc (M, 2*n_levels) at x01 (M,3).
+ * Every d_grad_table of this header must be 16-byte aligned (pairs of adjacent entries take one 16-byte reduction). */
 int qf_hashgrid_backward(const qf_ngp* f, const float* d_x01, const float* d_grad_enc, int64_t M, float* d_grad_table,
                          void* stream);
 /* `NGPRadianceField.query_density(x, return_feat)` (ngp.py:757-779): d_feat (M,15) may be NULL. */

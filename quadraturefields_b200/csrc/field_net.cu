@@ -413,6 +413,7 @@ extern "C" int qf_field_backward(const qf_ngp* grid, const qf_field_desc* fd, co
   if (M == 0) return QF_OK;
   QF_REQUIRE(d_w1 && d_w2 && d_w3 && d_x && d_grad_w1 && d_grad_w2 && d_grad_w3, "qf_field_backward: NULL argument");
   QF_REQUIRE(d_grad_field || d_grad_field_grad, "qf_field_backward: no upstream gradient");
+  QF_REQUIRE((reinterpret_cast<uintptr_t>(d_grad_table) & 15) == 0, "qf_field_backward: d_grad_table must be 16-byte aligned");
   FieldNetArgs a = {};
   fill_args(a, grid, fd, d_w1, d_b1, d_w2, d_b2, d_w3, d_b3, d_x, M);
   a.g_field = d_grad_field; a.g_fgrad = d_grad_field_grad;
