@@ -348,10 +348,13 @@ static int render_common(Shade mode, const qf_mesh* mesh, const qf_ngp* field, c
     const int64_t n = (n_rays - ray0) < chunk ? (n_rays - ray0) : chunk;
     QF_CUDA_CHECK(cudaMemsetAsync(w.cursor, 0, sizeof(int32_t), st));
     const int blocks = (int)ceil_div(n, 128);
-    // centre-out band order for the K <= 8 frames only: r2i, c2 trace alone 0.104 -> 0.092 ms (the pipelined frame rate is
-    // unchanged); with K = 32 and a 1.15 M-triangle mesh alternating between the two halves of the image costs more in
-    // BVH locality than the shorter tail returns (c4 1.647 -> 1.664 ms, c5 4.65 -> 4.75 ms at N=1, +-1 % at N=4)
-    const int n_bands = (tiled && (mesh->restart_eps > 0.f ? QF_MAX_HITS : K) <= 8) ? (int)(n / band) : 0;
+    // centre-out band order for the K <= 8 frames (r2i, c2 trace alone 0.104 -> 0.092 ms; the pipelined frame rate is
+    // unchanged) and for K = 32 launches of at most 600 K rays — a rank's share of a ray-sharded 1080p frame at N >= 4, where
+    // the longest packets end the launch (share of 1/4: trace 0.525 -> 0.483 ms, of 1/8: 0.346 -> 0.332 ms,
+    // tools/diag_share.py).  Larger K = 32 launches lose more BVH locality by alternating between the two halves of the image
+    // than the shorter tail returns (c4 1.647 -> 1.664 ms, c5 4.65 -> 4.75 ms at N=1).
+    static const int64_t co_max = getenv("QF_CENTER_OUT_K32_MAX_RAYS") ? atoll(getenv("QF_CENTER_OUT_K32_MAX_RAYS")) : 600000;
+    const int n_bands = (tiled && ((mesh->restart_eps > 0.f ? QF_MAX_HITS : K) <= 8 || n <= co_max)) ? (int)(n / band) : 0;
     cudaEvent_t pe[4] = {nullptr, nullptr, nullptr, nullptr};
     if (g_prof.enabled) { for (auto& e : pe) e = g_prof.get(); cudaEventRecord(pe[0], st); }
     const float eps = mesh->restart_eps;

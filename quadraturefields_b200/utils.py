@@ -240,13 +240,13 @@ class MeshRenderer:
     @torch.no_grad()
     def render_pose(self, c2w, W: int, H: int, focal: float, cx: float, cy: float, bg_color="white", render_bkgd=None, out=None,
                     hits_out: Optional[torch.Tensor] = None, opengl: bool = True, rows: Optional[tuple] = None,
-                    bands: Optional[tuple] = None, frame=None, frame_slot: int = 0):
+                    bands: Optional[tuple] = None, frame=None, frame_slot: int = 0, band_rows: int = 4):
         """The evaluation frame of the reference from its real input: a 3x4 camera-to-world pose on the HOST.  The reference's
         `SubjectLoader.fetch_data` builds the W*H rays on the device from the pose (nerf_synthetic.py:289-378) and the eval
         loop renders them (train_finetune.py:586-617); here: `qf_generate_rays` (the 48-byte pose travels as kernel
         arguments, no host->device copy of rays) into resident scratch, then the fused render.
         `rows=(r0, r1)` renders only image rows [r0, r1) — a rank's contiguous band of a ray-sharded frame.
-        `bands=(rank, world)` renders the rank's band-CYCLIC share instead: the 4-row bands b with b % world == rank, compact
+        `bands=(rank, world)` renders the rank's band-CYCLIC share instead: the `band_rows`-row bands b with b % world == rank, compact
         and in order (`parallel.assemble_banded` puts the shares back together); hit counts vary a lot over an image, and
         dealing the bands round-robin balances the ranks.  -> the `render` dict (of the rendered rows only).
         `frame` (with `bands`): a `parallel.PeerFrame`; the share's pixels are stored where they sit in slot `frame_slot` of
@@ -264,15 +264,18 @@ class MeshRenderer:
         _, o, d = buf
         if bands is not None:
             rank, world = bands
-            n_rows = int(lib.qf_band_rows(H, 4, world, rank))
-            if n_rows < 0 or H % 4:
-                raise ValueError(f"bands={bands}: needs 0 <= rank < world and an image height that is a multiple of 4")
+            if band_rows < 4 or band_rows % 4 or H % band_rows:
+                raise ValueError(f"band_rows={band_rows}: needs a multiple of 4 that divides the image height {H}")
+            n_rows = int(lib.qf_band_rows(H, band_rows, world, rank))
+            if n_rows < 0:
+                raise ValueError(f"bands={bands}: needs 0 <= rank < world")
             _lib.check(lib.qf_generate_rays_banded(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
-                                                   1 if opengl else 0, 4, world, rank, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)),
-                       "qf_generate_rays_banded")
+                                                   1 if opengl else 0, band_rows, world, rank, _lib.ptr(o), _lib.ptr(d),
+                                                   _lib.stream(dev)), "qf_generate_rays_banded")
             o, d = o[:n_rows * W], d[:n_rows * W]
             if frame is not None:
-                return self._render_to_frame(o, d, bg_color, render_bkgd, hits_out, W, (4, world, rank), frame.pointers(frame_slot))
+                return self._render_to_frame(o, d, bg_color, render_bkgd, hits_out, W, (band_rows, world, rank),
+                                             frame.pointers(frame_slot))
             return self.render(o, d, bg_color=bg_color, render_bkgd=render_bkgd, out=out, hits_out=hits_out, image_width=W)
         _lib.check(lib.qf_generate_rays(m.ctypes.data_as(C.POINTER(C.c_float)), W, H, float(focal), float(cx), float(cy),
                                         1 if opengl else 0, _lib.ptr(o), _lib.ptr(d), _lib.stream(dev)), "qf_generate_rays")

@@ -1024,6 +1024,16 @@ def test_full_size_c4_shelly_shaped(dev):
     assert int(count_t.sum()) > 6 * tiles.numel()
     ref = O.render_mesh_ngp(o_s, d_s, sc.vertices_np, sc.faces_np, oracle_params(sc), K=sc.K)
     assert maxabs(out["rgb"].cpu()[sub], ref["rgb"]) <= TOL_IMG and maxabs(out["opacity"].cpu()[sub], ref["opacity"]) <= TOL_IMG
+    # one rank's band-cyclic share of this frame (what each of 8 GPUs renders; K=32 launch below 600 K rays: centre-out band
+    # order) equals the same rows of the whole frame, bit for bit, also with 12-row bands
+    from quadraturefields_b200 import parallel as P
+    for rank, world, rows in ((3, 8, 4), (1, 5, 12)):
+        share = sc.renderer.render_pose(sc.poses[1], sc.W, sc.H, sc.focal, sc.cx, sc.cy, bands=(rank, world), band_rows=rows)
+        row_ids = torch.arange(sc.H, device=dev)
+        mine = ((row_ids // rows) % world) == rank
+        full = out["rgb"].view(sc.H, sc.W, 3)[mine].reshape(-1, 3)
+        assert share["rgb"].shape[0] == int(mine.sum()) * sc.W and torch.equal(share["rgb"], full)
+        assert torch.equal(share["depth"], out["depth"].view(sc.H, sc.W, 1)[mine].reshape(-1, 1))
 
 
 def test_full_size_c5_baked_4k(dev):
