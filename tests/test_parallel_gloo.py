@@ -91,6 +91,28 @@ def test_band_cyclic_split_and_assembly():
             assert torch.equal(P.assemble_banded(parts, H, W), rows)
 
 
+def test_band_cyclic_split_with_other_band_heights():
+    """`render_pose(band_rows=...)` / `qf_band_rows` / `assemble_banded(band=...)` agree for bands thicker than 4 rows (the
+    C ABI's row count is the host helper's; the library is loaded, no kernel runs), and the whole-frame row of a share's local
+    row — the map `composite_rays_kernel` applies for `qf_render_mesh_*_to_frame` — is a bijection onto the frame."""
+    from quadraturefields_b200 import _lib
+    lib = _lib.load()
+    for H, W, band in ((1080, 8, 12), (1080, 8, 40), (2160, 8, 16), (96, 4, 8)):
+        rows = torch.arange(H).view(H, 1).expand(H, W).reshape(-1, 1).float()
+        for ws in (1, 2, 3, 5, 8):
+            parts, seen = [], []
+            for r in range(ws):
+                mine = [y for y in range(H) if (y // band) % ws == r]
+                assert P.band_rows(H, r, ws, band) == len(mine) == int(lib.qf_band_rows(H, band, ws, r))
+                parts.append(rows.view(H, W)[mine].reshape(-1, 1))
+                # FrameMap of render.cu: local row -> whole-frame row
+                seen += [((l // band) * ws + r) * band + l % band for l in range(len(mine))]
+                assert seen[-len(mine):] == mine
+            assert sorted(seen) == list(range(H))
+            assert torch.equal(P.assemble_banded(parts, H, W, band), rows)
+    assert int(lib.qf_band_rows(1080, 4, 8, 8)) < 0          # rank outside the world
+
+
 def test_reference_arm_under_torchrun_prints_one_line():
     """`bench.py --impl reference` launched the way the driver launches N>1 arms: rank 0 alone measures and prints the
     JSON line (impl, metric, cpu_baseline, e2e with zero copy bytes), the other rank exits 0 without work."""
