@@ -64,6 +64,27 @@ def test_argument_validation_without_gpu(lib):
     assert b"qf_ngp_backward_features: NULL" in L.qf_last_error()
 
 
+def test_argument_validation_of_the_frame_and_peer_entry_points(lib):
+    """r2i entry points (ray-sharded frames into whole-frame / peer buffers, uint8 eval images): bad arguments are refused
+    with a message before anything touches the device."""
+    import ctypes as C
+    L = lib.load()
+    assert L.qf_render_mesh_ngp_to_frame(None, None, None, None, 8, 8, 0.005, 0, None, 4, 2, 0, 8, None, None, None, None, None, 0, None) == 1
+    assert b"qf_render_mesh_ngp_to_frame: NULL field" in L.qf_last_error()
+    assert L.qf_render_mesh_baked_to_frame(None, None, None, None, None, 8, 8, 0.005, 0, None, 4, 2, 0, 8, None, None, None, None, None, 0, None) == 1
+    assert b"qf_render_mesh_baked_to_frame: NULL texture" in L.qf_last_error()
+    assert L.qf_frame_to_u8(None, None, 0, None, None, None, None) == 0            # empty frame: nothing to do
+    assert L.qf_frame_to_u8(None, None, 16, None, None, None, None) == 1
+    assert b"qf_frame_to_u8: NULL argument" in L.qf_last_error()
+    buf = C.create_string_buffer(64)
+    assert L.qf_peer_export(None, buf) == 1 and b"qf_peer_export: NULL" in L.qf_last_error()
+    out = C.c_void_p()
+    assert L.qf_peer_open(None, C.byref(out)) == 1 and b"qf_peer_open: NULL" in L.qf_last_error()
+    assert L.qf_peer_alloc(0, C.byref(out)) == 1 and b"qf_peer_alloc" in L.qf_last_error()
+    assert L.qf_peer_close(None) == 0 and L.qf_peer_free(None) == 0                # NULL handles are no-ops
+    assert L.qf_band_rows(1080, 4, 8, 3) == 136 and L.qf_band_rows(1080, 4, 8, 6) == 132 and L.qf_band_rows(1080, 40, 8, 0) == 160
+
+
 def test_ops_fail_loudly_on_cpu_tensors(lib):
     from quadraturefields_b200 import field_rendering as FR
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
